@@ -1,0 +1,183 @@
+/*
+ * tekken_b200.h -- C ABI of the B200-native Tekkenizer encode/decode path.
+ *
+ * This is the drop-in boundary: the entry points a `Tekkenizer` shim in the reference's host
+ * language (Rust, over `extern "C"`) binds in place of
+ * `tiktoken_rs::CoreBPE` and the glue around it.  Every function cites the reference
+ * interface it replaces (paths are into jorge-menjivar/tekken-rs).
+ *
+ * Conventions
+ *   - Return value: TK_OK (0) or a negative tk_status.  One code per variant of the
+ *     reference's `TokenizerError` (src/errors.rs:23-59) plus a few boundary-only codes.
+ *     The message of the last failure on the calling thread is at tk_last_error().
+ *   - Ownership: output buffers returned through `T** out` are allocated by the library
+ *     (pinned host memory) and released with tk_buffer_free().  The reference returns owned
+ *     `Vec<u32>` / `String` (src/tekkenizer.rs:383, 440).
+ *   - Text is UTF-8.  The reference takes `&str`, which is valid by construction; this ABI
+ *     takes bytes and rejects invalid UTF-8 with TK_ERR_INVALID_UTF8 instead of guessing.
+ *   - A tokenizer handle is immutable after construction and may be used from many host
+ *     threads at once (the reference's methods all take `&self`).
+ *   - There is no CPU fallback: encode/decode run on the CUDA device the handle was created
+ *     on and fail with TK_ERR_CUDA if that is impossible.
+ */
+#ifndef TEKKEN_B200_H
+#define TEKKEN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tk_tokenizer tk_tokenizer;
+
+/* src/errors.rs:23-59 */
+typedef enum tk_status {
+    TK_OK = 0,
+    TK_ERR_IO = -1,                   /* TokenizerError::Io                  :25-26 */
+    TK_ERR_JSON = -2,                 /* TokenizerError::Json                :29-30 */
+    TK_ERR_BASE64 = -3,               /* TokenizerError::Base64              :33-34 */
+    TK_ERR_TOKENIZERS = -4,           /* TokenizerError::Tokenizers          :37-38 */
+    TK_ERR_AUDIO = -5,                /* TokenizerError::Audio (unused here) :41-42 */
+    TK_ERR_INVALID_CONFIG = -6,       /* TokenizerError::InvalidConfig       :45-46 */
+    TK_ERR_TOKEN_NOT_FOUND = -7,      /* TokenizerError::TokenNotFound       :49-50 */
+    TK_ERR_SPECIAL_TOKEN_POLICY = -8, /* TokenizerError::SpecialTokenPolicy  :53-54 */
+    TK_ERR_UNSUPPORTED_FORMAT = -9,   /* TokenizerError::UnsupportedFormat   :57-58 */
+    /* boundary-only codes (no reference variant) */
+    TK_ERR_INVALID_UTF8 = -20,        /* encode input is not valid UTF-8 (`&str` in the reference) */
+    TK_ERR_CUDA = -21,                /* CUDA runtime failure / no usable device                  */
+    TK_ERR_BUFFER_TOO_SMALL = -22,    /* caller-provided device buffer cannot hold the result     */
+    TK_ERR_INVALID_ARGUMENT = -23
+} tk_status;
+
+/* src/special_tokens.rs:129-136 */
+typedef enum tk_policy { TK_POLICY_IGNORE = 0, TK_POLICY_KEEP = 1, TK_POLICY_RAISE = 2 } tk_policy;
+
+/* src/config.rs:97-103 */
+typedef enum tk_version { TK_V3 = 3, TK_V7 = 7, TK_V11 = 11, TK_V13 = 13 } tk_version;
+
+/* src/config.rs:16-23 `TokenInfo` (token_str is display-only and not needed) */
+typedef struct tk_vocab_entry {
+    uint64_t rank;
+    const char *token_bytes_b64; /* base64 (STANDARD alphabet, padded), NUL-terminated */
+} tk_vocab_entry;
+
+/* src/special_tokens.rs:161-168 `SpecialTokenInfo` */
+typedef struct tk_special_entry {
+    uint64_t rank;
+    const char *token_str; /* UTF-8, NUL-terminated */
+    int is_control;
+} tk_special_entry;
+
+/* ---- construction ------------------------------------------------------------------ */
+
+/* Tekkenizer::from_file (src/tekkenizer.rs:222-248).  `device` is the CUDA ordinal that will
+   hold the vocabulary tables and run the kernels; -1 builds a host-only handle (accessors
+   work, encode/decode return TK_ERR_CUDA) for use on machines without a GPU. */
+int tk_load_file(const char *path, int device, tk_tokenizer **out);
+
+/* Tekkenizer::new (src/tekkenizer.rs:71-191).  `pattern` is accepted and ignored exactly as
+   the reference ignores it (`_pattern`, :74): the split pattern is the literal of :123.
+   `special` may be NULL with n_special == 0. */
+int tk_new(const tk_vocab_entry *vocab, size_t n_vocab, const tk_special_entry *special,
+           size_t n_special, const char *pattern, size_t vocab_size, size_t num_special_tokens,
+           int version, int device, tk_tokenizer **out);
+
+/* The 20 built-in special tokens used when the file has no `special_tokens`
+   (get_deprecated_special_tokens, src/tekkenizer.rs:827-930).  Returns their count. */
+size_t tk_deprecated_special_tokens(const tk_special_entry **out);
+
+/* Drop (the reference frees on scope exit). */
+void tk_free(tk_tokenizer *t);
+
+/* ---- accessors (host-side) ----------------------------------------------------------- */
+
+size_t tk_vocab_size(const tk_tokenizer *t);                 /* src/tekkenizer.rs:261-263 */
+size_t tk_num_special_tokens(const tk_tokenizer *t);         /* :269-271 */
+int tk_version_of(const tk_tokenizer *t);                    /* :277-279, a tk_version */
+int tk_device_of(const tk_tokenizer *t);
+int tk_get_control_token(const tk_tokenizer *t, const char *token_str, uint32_t *id); /* :331-341 */
+int tk_bos_id(const tk_tokenizer *t, uint32_t *id);          /* :286-288 */
+int tk_eos_id(const tk_tokenizer *t, uint32_t *id);          /* :295-297 */
+int tk_pad_id(const tk_tokenizer *t, uint32_t *id);          /* :304-306 */
+int tk_unk_id(const tk_tokenizer *t, uint32_t *id);          /* :313-315 */
+int tk_is_special_token(const tk_tokenizer *t, uint32_t id); /* :574-576 */
+int tk_is_byte(const tk_tokenizer *t, uint32_t id);          /* :591-600 */
+/* vocab()[id] (:348-350): special string, or the lossy UTF-8 rendering of the token bytes.
+   The pointer is owned by the handle. */
+int tk_vocab_piece(const tk_tokenizer *t, uint32_t id, const char **str, size_t *len);
+/* id_to_piece (:617-628) and id_to_byte_piece (:648-695, including the lossy fallback of
+   :685-686).  Output is library-allocated; free with tk_buffer_free. */
+int tk_id_to_piece(const tk_tokenizer *t, uint32_t id, uint8_t **out, size_t *n);
+int tk_id_to_byte_piece(const tk_tokenizer *t, uint32_t id, int policy, uint8_t **out, size_t *n);
+
+/* ---- encode: Tekkenizer::encode (src/tekkenizer.rs:378-405) --------------------------- */
+
+/* One text.  ids = CoreBPE ranks + num_special_tokens, optional BOS first / EOS last. */
+int tk_encode(const tk_tokenizer *t, const uint8_t *utf8, size_t len, int add_bos, int add_eos,
+              uint32_t **out, size_t *n_out);
+
+/* New: encode_batch.  Documents are data[doc_off[d] .. doc_off[d+1]) (n_docs+1 offsets,
+   doc_off[0] == 0).  ids of all documents are returned back to back in *tokens; *tok_off
+   gets n_docs+1 offsets into it.  Host buffers in, pinned host buffers out. */
+int tk_encode_batch(const tk_tokenizer *t, const uint8_t *data, const uint64_t *doc_off,
+                    size_t n_docs, int add_bos, int add_eos, uint32_t **tokens, uint64_t **tok_off);
+
+/* Zero-copy form: every pointer is a device pointer on the handle's device, `stream` is a
+   cudaStream_t (NULL = default stream).  d_tokens must hold tokens_capacity ids
+   (total_bytes + 2*n_docs always suffices); d_tok_off holds n_docs+1 offsets.  The call
+   synchronises the stream before returning; *n_tokens is the total id count.  On
+   TK_ERR_BUFFER_TOO_SMALL *n_tokens is the capacity that would have been enough. */
+int tk_encode_batch_device(const tk_tokenizer *t, const uint8_t *d_data, const uint64_t *d_doc_off,
+                           size_t n_docs, uint64_t total_bytes, int add_bos, int add_eos,
+                           uint32_t *d_tokens, uint64_t tokens_capacity, uint64_t *d_tok_off,
+                           uint64_t *n_tokens, void *stream);
+
+/* ---- decode: Tekkenizer::decode / decode_all (src/tekkenizer.rs:436-560) -------------- */
+
+int tk_decode(const tk_tokenizer *t, const uint32_t *ids, size_t n, int policy, uint8_t **out,
+              size_t *n_out);
+
+/* decode_all (:463-511): the concatenated bytes plus the end offset of every element the
+   reference would return (one per ordinary run, one per kept special id). */
+int tk_decode_all(const tk_tokenizer *t, const uint32_t *ids, size_t n, int policy, uint8_t **out,
+                  uint64_t **part_end, size_t *n_parts);
+
+/* New: decode_batch.  Sequences are ids[tok_off[d] .. tok_off[d+1]).  On success *byte_off
+   gets n_docs+1 offsets into *out.  If any sequence fails the call returns the error of the
+   first failing sequence (Rust `collect::<Result<Vec<_>>>` semantics) and *bad_doc (may be
+   NULL) its index. */
+int tk_decode_batch(const tk_tokenizer *t, const uint32_t *ids, const uint64_t *tok_off,
+                    size_t n_docs, int policy, uint8_t **out, uint64_t **byte_off, uint64_t *bad_doc);
+
+/* Device form.  d_out must hold out_capacity bytes; d_byte_off n_docs+1 offsets;
+   d_doc_status (may be NULL) n_docs int32 per-sequence status codes. */
+int tk_decode_batch_device(const tk_tokenizer *t, const uint32_t *d_ids, const uint64_t *d_tok_off,
+                           size_t n_docs, uint64_t total_ids, int policy, uint8_t *d_out,
+                           uint64_t out_capacity, uint64_t *d_byte_off, int32_t *d_doc_status,
+                           uint64_t *n_bytes, uint64_t *bad_doc, void *stream);
+
+/* ---- multi-GPU sharding (documents are independent: no collective) -------------------- */
+
+/* Byte-balanced contiguous document ranges: shard s gets documents
+   [shard_begin[s], shard_begin[s+1]).  shard_begin has n_shards+1 entries. */
+int tk_shard_plan(const uint64_t *doc_off, size_t n_docs, size_t n_shards, uint64_t *shard_begin);
+
+/* ---- misc ---------------------------------------------------------------------------- */
+
+void tk_buffer_free(void *p);
+const char *tk_last_error(void);
+const char *tk_status_name(int status);
+/* Kernel launches issued by this process so far (for benchmark accounting). */
+uint64_t tk_kernel_launch_count(void);
+/* Per-stage device time of the most recent tk_encode_batch_device call on this handle, in
+   milliseconds, measured with CUDA events on the call's stream when profiling is enabled
+   with tk_set_stage_timing(t, 1).  names/ms arrays hold up to `cap` entries; returns count. */
+void tk_set_stage_timing(tk_tokenizer *t, int enabled);
+size_t tk_last_stage_times(const tk_tokenizer *t, const char **names, float *ms, size_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TEKKEN_B200_H */

@@ -1,0 +1,86 @@
+// tk_common.h -- types and hash functions shared by the host table builders and the kernels.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define TK_HD __host__ __device__ __forceinline__
+#else
+#define TK_HD inline
+#endif
+
+#define TK_INF 0xFFFFFFFFu
+
+// ---- character classes of the split pattern (src/tekkenizer.rs:123) ----------------------
+// L = \p{L}, N = \p{N}, R = {CR, LF}, W = \s minus R, O = everything else.
+enum { TK_CL_O = 0, TK_CL_L = 1, TK_CL_N = 2, TK_CL_W = 3, TK_CL_R = 4 };
+
+// Two-stage Unicode class table: stage1[cp >> 7] -> block index; stage2 holds 128 two-bit
+// entries per block (32 bytes), values TK_CL_O/L/N/W.  R (CR/LF) is ASCII and handled inline.
+#define TK_UNI_STAGE1_N (0x110000 >> 7)
+
+TK_HD uint32_t tk_class_lookup(const uint16_t* stage1, const uint8_t* stage2, uint32_t cp) {
+    uint32_t blk = stage1[cp >> 7];
+    uint32_t b = stage2[blk * 32u + ((cp & 127u) >> 2)];
+    return (b >> ((cp & 3u) * 2u)) & 3u;
+}
+
+// ---- vocabulary hash table: byte string -> rank ----------------------------------------------
+// Slot is 16 bytes.  len == 0 marks an empty slot.  For len <= 8 `key` is the bytes themselves
+// (little-endian packed, zero padded) so a key+len match is exact; for len > 8 `key` is the
+// 64-bit hash and the caller verifies the bytes against the vocabulary byte table.
+struct TkVocabSlot {
+    uint64_t key;
+    uint32_t rank;
+    uint32_t len;
+};
+
+TK_HD uint64_t tk_mix64(uint64_t x) {
+    x ^= x >> 32;
+    x *= 0xd6e8feb86659fd93ull;
+    x ^= x >> 32;
+    x *= 0xd6e8feb86659fd93ull;
+    x ^= x >> 32;
+    return x;
+}
+
+// Hash of a piece given as little-endian 8-byte words (last one zero padded).
+struct TkPieceHasher {
+    uint64_t h;
+    TK_HD void init(uint32_t len) { h = 0x9e3779b97f4a7c15ull * (uint64_t)(len + 1u); }
+    TK_HD void add(uint64_t w) { h = (h ^ w) * 0xff51afd7ed558ccdull; h ^= h >> 29; }
+    TK_HD uint64_t finish() const { return tk_mix64(h); }
+};
+
+// ---- pair table: (left id, right id) -> rank of the concatenation ------------------------------
+// One u64 per slot: bit 63 = occupied, bits 42..62 = left id, 21..41 = right id, 0..20 = rank.
+// Ids are < 2^21 (checked at load).
+#define TK_ID_BITS 21u
+#define TK_ID_MASK ((1u << TK_ID_BITS) - 1u)
+
+TK_HD uint64_t tk_pair_key(uint32_t l, uint32_t r) { return ((uint64_t)l << TK_ID_BITS) | (uint64_t)r; }
+TK_HD uint64_t tk_pair_slot(uint32_t l, uint32_t r, uint32_t rank) {
+    return (1ull << 63) | (tk_pair_key(l, r) << TK_ID_BITS) | (uint64_t)rank;
+}
+TK_HD uint32_t tk_pair_hash(uint32_t l, uint32_t r) {
+    uint64_t k = tk_pair_key(l, r);
+    k *= 0x9e3779b97f4a7c15ull;
+    return (uint32_t)(k >> 32) ^ (uint32_t)(k >> 13);
+}
+
+// Device-resident tables of one tokenizer (plain pointers; filled by the loader).
+struct TkDeviceTables {
+    const uint16_t* uni_stage1;    // TK_UNI_STAGE1_N entries
+    const uint8_t* uni_stage2;     // n_blocks * 32 bytes
+    const TkVocabSlot* vocab_slots;
+    uint32_t vocab_mask;           // capacity - 1
+    const uint64_t* pair_slots;
+    uint32_t pair_mask;
+    const uint8_t* vocab_bytes;    // concatenated token bytes, rank order
+    const uint32_t* vocab_off;     // n_vocab + 1
+    const uint8_t* special_bytes;  // concatenated special strings, positional order
+    const uint32_t* special_off;   // num_special + 1
+    uint32_t n_vocab;              // inner vocabulary size
+    uint32_t num_special;
+    uint32_t max_token_len;
+    uint32_t bos_id, eos_id;       // TK_INF when absent
+};

@@ -1,0 +1,88 @@
+// tk_host.h -- host-side model of a loaded Tekkenizer: the tekken.json parser, the reference's
+// construction-time validations, and the builders of the tables the kernels read.
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "tk_common.h"
+
+namespace tk {
+
+// Mirrors TokenizerError (src/errors.rs:23-59); `code` is a tk_status.
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+struct VocabEntry {
+    uint64_t rank;
+    std::string token_bytes_b64;
+};
+
+struct SpecialEntry {
+    uint64_t rank;
+    std::string token_str;
+    bool is_control;
+};
+
+// What Tekkenizer::from_file reads from the file (src/config.rs:73-82).
+struct ModelData {
+    std::vector<VocabEntry> vocab;
+    bool has_special_tokens = false;
+    std::vector<SpecialEntry> special_tokens;
+    std::string pattern;
+    uint64_t num_vocab_tokens = 0;
+    uint64_t default_vocab_size = 0;
+    uint64_t default_num_special_tokens = 0;
+    std::string version;
+};
+
+ModelData parse_tekken_json(const std::string& text);           // throws Error(TK_ERR_JSON)
+std::vector<uint8_t> base64_decode_standard(const std::string&); // throws Error(TK_ERR_BASE64)
+const std::vector<SpecialEntry>& deprecated_special_tokens();     // src/tekkenizer.rs:827-930
+int parse_version(const std::string& s);                          // src/config.rs:124-131; 0 if unknown
+
+// The immutable host state of a tokenizer (src/tekkenizer.rs:34-44 minus audio).
+struct HostModel {
+    size_t vocab_size = 0;
+    size_t num_special = 0;
+    int version = 0;
+    std::vector<SpecialEntry> special_tokens;                 // incl. <SPECIAL_i> fillers, positional
+    std::unordered_map<std::string, uint64_t> special_map;    // token_str -> rank
+    std::vector<uint8_t> vocab_bytes;                         // rank order
+    std::vector<uint32_t> vocab_off;                          // n_vocab + 1
+    std::vector<std::string> vocab_strings;                   // vocab() (:141-155), lossy UTF-8
+    uint32_t max_token_len = 0;
+
+    // device table images
+    std::vector<uint16_t> uni_stage1;
+    std::vector<uint8_t> uni_stage2;
+    std::vector<TkVocabSlot> vocab_slots;
+    std::vector<uint64_t> pair_slots;
+    std::vector<uint8_t> special_bytes;
+    std::vector<uint32_t> special_off;
+    size_t n_pairs = 0;
+
+    size_t n_vocab() const { return vocab_off.size() - 1; }
+    uint32_t control_token(const std::string& s) const;        // :331-341, throws TokenNotFound
+    bool has_control_token(const std::string& s) const { return special_map.count(s) != 0; }
+
+    // Tekkenizer::new (src/tekkenizer.rs:71-191)
+    static HostModel build(const std::vector<VocabEntry>& vocab, const std::vector<SpecialEntry>& special,
+                           const std::string& pattern_ignored, size_t vocab_size, size_t num_special,
+                           int version);
+    // Tekkenizer::from_file (src/tekkenizer.rs:222-248)
+    static HostModel from_file(const std::string& path);
+};
+
+void build_unicode_tables(std::vector<uint16_t>& stage1, std::vector<uint8_t>& stage2);
+std::string utf8_lossy(const uint8_t* p, size_t n);  // String::from_utf8_lossy
+bool utf8_valid(const uint8_t* p, size_t n);         // String::from_utf8(..).is_ok()
+
+// Hash of a piece exactly as the kernels compute it (for table construction and host tests).
+uint64_t piece_hash(const uint8_t* p, uint32_t len, uint64_t* key8);
+
+}  // namespace tk
