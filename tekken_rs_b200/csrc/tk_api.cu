@@ -1,0 +1,694 @@
+// tk_api.cu -- the extern "C" boundary declared in include/tekken_b200.h.
+//
+// Host-side glue only: argument checks, device memory for the vocabulary tables and per-call
+// workspaces, host<->device copies for the host-buffer entry points, and the mapping from
+// device-reported conditions to the reference's TokenizerError variants (src/errors.rs:23-59).
+// All arithmetic of the path runs in the kernels (tk_kernels.cu, tk_decode.cu); there is no CPU
+// implementation of encode or decode in this library.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/tekken_b200.h"
+#include "tk_host.h"
+#include "tk_kernels.h"
+
+// ------------------------------------------------------------------------------------------ errors
+
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+extern "C" const char* tk_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" const char* tk_status_name(int s) {
+    switch (s) {
+        case TK_OK: return "Ok";
+        case TK_ERR_IO: return "Io";
+        case TK_ERR_JSON: return "Json";
+        case TK_ERR_BASE64: return "Base64";
+        case TK_ERR_TOKENIZERS: return "Tokenizers";
+        case TK_ERR_AUDIO: return "Audio";
+        case TK_ERR_INVALID_CONFIG: return "InvalidConfig";
+        case TK_ERR_TOKEN_NOT_FOUND: return "TokenNotFound";
+        case TK_ERR_SPECIAL_TOKEN_POLICY: return "SpecialTokenPolicy";
+        case TK_ERR_UNSUPPORTED_FORMAT: return "UnsupportedFormat";
+        case TK_ERR_INVALID_UTF8: return "InvalidUtf8";
+        case TK_ERR_CUDA: return "Cuda";
+        case TK_ERR_BUFFER_TOO_SMALL: return "BufferTooSmall";
+        case TK_ERR_INVALID_ARGUMENT: return "InvalidArgument";
+    }
+    return "Unknown";
+}
+
+#define CUDA_OR_FAIL(x)                                                                           \
+    do {                                                                                          \
+        cudaError_t e_ = (x);                                                                     \
+        if (e_ != cudaSuccess) return fail(TK_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_));    \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------ buffers
+
+// Output buffers handed to the caller are pinned host allocations; freed ones are kept in a
+// small cache so a steady stream of calls does not pay cudaHostAlloc every time.
+namespace {
+struct HostPool {
+    std::mutex mu;
+    std::map<void*, size_t> live;                 // ptr -> capacity
+    std::multimap<size_t, void*> free_list;       // capacity -> ptr
+    size_t cached = 0;
+    static constexpr size_t kMaxCached = 6ull << 30;
+
+    void* get(size_t bytes) {
+        if (bytes == 0) bytes = 1;
+        std::lock_guard<std::mutex> g(mu);
+        auto it = free_list.lower_bound(bytes);
+        if (it != free_list.end() && it->first <= bytes * 2 + 4096) {
+            void* p = it->second;
+            live[p] = it->first;
+            cached -= it->first;
+            free_list.erase(it);
+            return p;
+        }
+        void* p = nullptr;
+        size_t cap = (bytes + 4095) & ~(size_t)4095;
+        if (cudaHostAlloc(&p, cap, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            // no CUDA context (host-only handle): plain memory
+            p = malloc(cap);
+            if (!p) return nullptr;
+            live[p] = cap | 1;   // low bit: malloc'ed
+            return p;
+        }
+        live[p] = cap;
+        return p;
+    }
+    void put(void* p) {
+        if (!p) return;
+        std::lock_guard<std::mutex> g(mu);
+        auto it = live.find(p);
+        if (it == live.end()) return;
+        size_t cap = it->second;
+        live.erase(it);
+        if (cap & 1) { free(p); return; }
+        if (cached + cap > kMaxCached) { cudaFreeHost(p); return; }
+        cached += cap;
+        free_list.emplace(cap, p);
+    }
+};
+HostPool g_pool;
+}  // namespace
+
+extern "C" void tk_buffer_free(void* p) { g_pool.put(p); }
+
+// ------------------------------------------------------------------------------------------ handle
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 4096;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            e = cudaMalloc(&p, bytes);   // retry without slack
+            want = bytes;
+        }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct tk_tokenizer {
+    tk::HostModel host;
+    int device = -1;
+    int sm_count = 148;
+    TkDeviceTables tables{};
+    std::vector<void*> table_allocs;
+    std::mutex mu;                 // serialises device work issued through this handle
+    cudaStream_t stream = nullptr; // used by the host-buffer entry points
+    DevBuf ws, scratch, in_data, in_off, out_a, out_b, status;
+    bool timing = false;
+    tkk::StageTimer timer;
+    std::vector<std::string> stage_names;
+    std::vector<float> stage_ms;
+};
+
+template <class V>
+static cudaError_t upload(tk_tokenizer* t, const V& v, const void** out) {
+    void* p = nullptr;
+    size_t bytes = v.size() * sizeof(v[0]);
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
+    if (e != cudaSuccess) return e;
+    t->table_allocs.push_back(p);
+    if (bytes) e = cudaMemcpy(p, v.data(), bytes, cudaMemcpyHostToDevice);
+    *out = p;
+    return e;
+}
+
+static int finish_handle(tk_tokenizer* t, int device, tk_tokenizer** out) {
+    t->device = device;
+    if (device >= 0) {
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || device >= count) {
+            cudaGetLastError();
+            delete t;
+            return fail(TK_ERR_CUDA, "CUDA device %d is not available (%s); this library has no CPU fallback", device,
+                        e != cudaSuccess ? cudaGetErrorString(e) : "ordinal out of range");
+        }
+        int prev = 0;
+        cudaGetDevice(&prev);
+        cudaError_t err = cudaSetDevice(device);
+        const tk::HostModel& h = t->host;
+        TkDeviceTables& T = t->tables;
+        if (err == cudaSuccess) err = cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, device);
+        if (err == cudaSuccess) err = upload(t, h.uni_stage1, (const void**)&T.uni_stage1);
+        if (err == cudaSuccess) err = upload(t, h.uni_stage2, (const void**)&T.uni_stage2);
+        if (err == cudaSuccess) err = upload(t, h.vocab_slots, (const void**)&T.vocab_slots);
+        if (err == cudaSuccess) err = upload(t, h.pair_slots, (const void**)&T.pair_slots);
+        if (err == cudaSuccess) err = upload(t, h.vocab_bytes, (const void**)&T.vocab_bytes);
+        if (err == cudaSuccess) err = upload(t, h.vocab_off, (const void**)&T.vocab_off);
+        if (err == cudaSuccess) err = upload(t, h.special_bytes, (const void**)&T.special_bytes);
+        if (err == cudaSuccess) err = upload(t, h.special_off, (const void**)&T.special_off);
+        if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking);
+        T.vocab_mask = (uint32_t)h.vocab_slots.size() - 1;
+        T.pair_mask = (uint32_t)h.pair_slots.size() - 1;
+        T.n_vocab = (uint32_t)h.n_vocab();
+        T.num_special = (uint32_t)h.num_special;
+        T.max_token_len = h.max_token_len;
+        T.bos_id = h.has_control_token("<s>") ? h.control_token("<s>") : TK_INF;
+        T.eos_id = h.has_control_token("</s>") ? h.control_token("</s>") : TK_INF;
+        cudaSetDevice(prev);
+        if (err != cudaSuccess) {
+            int rc = fail(TK_ERR_CUDA, "uploading vocabulary tables: %s", cudaGetErrorString(err));
+            tk_free(t);
+            return rc;
+        }
+    }
+    *out = t;
+    return TK_OK;
+}
+
+extern "C" int tk_load_file(const char* path, int device, tk_tokenizer** out) {
+    if (!path || !out) return fail(TK_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    tk_tokenizer* t = new tk_tokenizer();
+    try {
+        t->host = tk::HostModel::from_file(path);
+    } catch (const tk::Error& e) {
+        delete t;
+        return fail(e.code, "%s", e.what());
+    } catch (const std::exception& e) {
+        delete t;
+        return fail(TK_ERR_IO, "%s", e.what());
+    }
+    return finish_handle(t, device, out);
+}
+
+extern "C" int tk_new(const tk_vocab_entry* vocab, size_t n_vocab, const tk_special_entry* special, size_t n_special,
+                      const char* pattern, size_t vocab_size, size_t num_special_tokens, int version, int device,
+                      tk_tokenizer** out) {
+    if (!out || (!vocab && n_vocab) || (!special && n_special)) return fail(TK_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    if (version != TK_V3 && version != TK_V7 && version != TK_V11 && version != TK_V13)
+        return fail(TK_ERR_INVALID_CONFIG, "Unknown version: %d", version);
+    std::vector<tk::VocabEntry> v(n_vocab);
+    for (size_t i = 0; i < n_vocab; ++i) {
+        if (!vocab[i].token_bytes_b64) return fail(TK_ERR_INVALID_ARGUMENT, "vocab[%zu].token_bytes_b64 is null", i);
+        v[i].rank = vocab[i].rank;
+        v[i].token_bytes_b64 = vocab[i].token_bytes_b64;
+    }
+    std::vector<tk::SpecialEntry> s(n_special);
+    for (size_t i = 0; i < n_special; ++i) {
+        if (!special[i].token_str) return fail(TK_ERR_INVALID_ARGUMENT, "special[%zu].token_str is null", i);
+        s[i].rank = special[i].rank;
+        s[i].token_str = special[i].token_str;
+        s[i].is_control = special[i].is_control != 0;
+    }
+    tk_tokenizer* t = new tk_tokenizer();
+    try {
+        t->host = tk::HostModel::build(v, s, pattern ? pattern : "", vocab_size, num_special_tokens, version);
+    } catch (const tk::Error& e) {
+        delete t;
+        return fail(e.code, "%s", e.what());
+    }
+    return finish_handle(t, device, out);
+}
+
+extern "C" size_t tk_deprecated_special_tokens(const tk_special_entry** out) {
+    static std::vector<tk_special_entry> v;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        for (const auto& e : tk::deprecated_special_tokens()) v.push_back({e.rank, e.token_str.c_str(), e.is_control ? 1 : 0});
+    });
+    if (out) *out = v.data();
+    return v.size();
+}
+
+extern "C" void tk_free(tk_tokenizer* t) {
+    if (!t) return;
+    if (t->device >= 0) {
+        int prev = 0;
+        cudaGetDevice(&prev);
+        cudaSetDevice(t->device);
+        t->timer.reset();
+        for (void* p : t->table_allocs) cudaFree(p);
+        t->ws.release(); t->scratch.release(); t->in_data.release(); t->in_off.release();
+        t->out_a.release(); t->out_b.release(); t->status.release();
+        if (t->stream) cudaStreamDestroy(t->stream);
+        cudaSetDevice(prev);
+    }
+    delete t;
+}
+
+// ------------------------------------------------------------------------------------------ accessors
+
+extern "C" size_t tk_vocab_size(const tk_tokenizer* t) { return t ? t->host.vocab_size : 0; }
+extern "C" size_t tk_num_special_tokens(const tk_tokenizer* t) { return t ? t->host.num_special : 0; }
+extern "C" int tk_version_of(const tk_tokenizer* t) { return t ? t->host.version : 0; }
+extern "C" int tk_device_of(const tk_tokenizer* t) { return t ? t->device : -1; }
+
+extern "C" int tk_get_control_token(const tk_tokenizer* t, const char* s, uint32_t* id) {
+    if (!t || !s || !id) return fail(TK_ERR_INVALID_ARGUMENT, "null argument");
+    try {
+        *id = t->host.control_token(s);
+    } catch (const tk::Error& e) {
+        return fail(e.code, "%s", e.what());
+    }
+    return TK_OK;
+}
+extern "C" int tk_bos_id(const tk_tokenizer* t, uint32_t* id) { return tk_get_control_token(t, "<s>", id); }
+extern "C" int tk_eos_id(const tk_tokenizer* t, uint32_t* id) { return tk_get_control_token(t, "</s>", id); }
+extern "C" int tk_pad_id(const tk_tokenizer* t, uint32_t* id) { return tk_get_control_token(t, "<pad>", id); }
+extern "C" int tk_unk_id(const tk_tokenizer* t, uint32_t* id) { return tk_get_control_token(t, "<unk>", id); }
+extern "C" int tk_is_special_token(const tk_tokenizer* t, uint32_t id) { return t && id < t->host.num_special; }
+extern "C" int tk_is_byte(const tk_tokenizer* t, uint32_t id) {
+    return t && id >= t->host.num_special && id - t->host.num_special < 256;
+}
+extern "C" int tk_vocab_piece(const tk_tokenizer* t, uint32_t id, const char** str, size_t* len) {
+    if (!t || !str || !len) return fail(TK_ERR_INVALID_ARGUMENT, "null argument");
+    if (id >= t->host.vocab_strings.size())
+        return fail(TK_ERR_INVALID_CONFIG, "Token ID %u is out of vocabulary range (0-%zu)", id, t->host.vocab_size - 1);
+    *str = t->host.vocab_strings[id].data();
+    *len = t->host.vocab_strings[id].size();
+    return TK_OK;
+}
+
+static int give_bytes(const uint8_t* p, size_t n, uint8_t** out, size_t* n_out) {
+    uint8_t* b = (uint8_t*)g_pool.get(n + 1);
+    if (!b) return fail(TK_ERR_CUDA, "out of host memory");
+    if (n) memcpy(b, p, n);
+    b[n] = 0;
+    *out = b;
+    *n_out = n;
+    return TK_OK;
+}
+
+// id_to_piece (:617-628) = bounds check + decode(&[id], Keep).  One id needs no kernel: a special
+// id yields its string; an ordinary id yields its bytes if they are valid UTF-8 on their own,
+// else the Tokenizers error the reference's CoreBPE::decode returns.
+extern "C" int tk_id_to_piece(const tk_tokenizer* t, uint32_t id, uint8_t** out, size_t* n) {
+    if (!t || !out || !n) return fail(TK_ERR_INVALID_ARGUMENT, "null argument");
+    const tk::HostModel& h = t->host;
+    if (id >= h.vocab_size)
+        return fail(TK_ERR_INVALID_CONFIG, "Token ID %u is out of vocabulary range (0-%zu)", id, h.vocab_size - 1);
+    if (id < h.num_special) {
+        const std::string& s = h.special_tokens[id].token_str;
+        return give_bytes((const uint8_t*)s.data(), s.size(), out, n);
+    }
+    size_t r = id - h.num_special;
+    if (r >= h.n_vocab()) return fail(TK_ERR_TOKENIZERS, "DecodeKeyError: Invalid token for decoding: %zu", r);
+    const uint8_t* p = h.vocab_bytes.data() + h.vocab_off[r];
+    size_t len = h.vocab_off[r + 1] - h.vocab_off[r];
+    if (!tk::utf8_valid(p, len)) return fail(TK_ERR_TOKENIZERS, "DecodeError: token %u is not valid UTF-8 on its own", id);
+    return give_bytes(p, len, out, n);
+}
+
+extern "C" int tk_id_to_byte_piece(const tk_tokenizer* t, uint32_t id, int policy, uint8_t** out, size_t* n) {
+    if (!t || !out || !n) return fail(TK_ERR_INVALID_ARGUMENT, "null argument");
+    const tk::HostModel& h = t->host;
+    if (id >= h.vocab_size)
+        return fail(TK_ERR_INVALID_CONFIG, "Token ID %u is out of vocabulary range (0-%zu)", id, h.vocab_size - 1);
+    if (id < h.num_special) {
+        const std::string& s = h.special_tokens[id].token_str;
+        if (policy == TK_POLICY_KEEP) return give_bytes((const uint8_t*)s.data(), s.size(), out, n);
+        if (policy == TK_POLICY_RAISE)
+            return fail(TK_ERR_SPECIAL_TOKEN_POLICY,
+                        "Token ID %u is a special token (%s), cannot convert to byte piece with Raise policy", id, s.c_str());
+        return give_bytes(nullptr, 0, out, n);
+    }
+    size_t r = id - h.num_special;
+    if (r < h.n_vocab()) {
+        const uint8_t* p = h.vocab_bytes.data() + h.vocab_off[r];
+        size_t len = h.vocab_off[r + 1] - h.vocab_off[r];
+        if (tk::utf8_valid(p, len)) return give_bytes(p, len, out, n);
+    }
+    // :683-687 -- on decode failure the reference returns the bytes of the LOSSY vocab string
+    const std::string& s = h.vocab_strings[id];
+    return give_bytes((const uint8_t*)s.data(), s.size(), out, n);
+}
+
+// ------------------------------------------------------------------------------------------ encode
+
+struct DeviceGuard {
+    int prev = 0;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() { cudaSetDevice(prev); }
+};
+
+static int check_encode_args(const tk_tokenizer* t, int add_bos, int add_eos) {
+    if (!t) return fail(TK_ERR_INVALID_ARGUMENT, "null tokenizer");
+    if (t->device < 0)
+        return fail(TK_ERR_CUDA, "this tokenizer handle is host-only (device -1); encode/decode need a CUDA device and there is no CPU fallback");
+    try {
+        if (add_bos) t->host.control_token("<s>");   // bos_id()? (:395)
+        if (add_eos) t->host.control_token("</s>");  // eos_id()? (:400)
+    } catch (const tk::Error& e) {
+        return fail(e.code, "%s", e.what());
+    }
+    return TK_OK;
+}
+
+// Runs the kernels on device buffers; the caller holds t->mu and has set the device.
+static int run_encode(tk_tokenizer* t, const uint8_t* d_data, const uint64_t* d_doc_off, size_t n_docs, uint64_t total,
+                      int add_bos, int add_eos, uint32_t* d_tokens, uint64_t cap, uint64_t* d_tok_off, uint64_t* n_tokens,
+                      cudaStream_t st) {
+    if (((uintptr_t)d_data & 15u) != 0 && total) return fail(TK_ERR_INVALID_ARGUMENT, "device text pointer must be 16-byte aligned");
+    if (total >= (1ull << 40)) return fail(TK_ERR_INVALID_ARGUMENT, "batch too large; shard it (limit 1 TiB per call)");
+    tkk::EncodeLayout L;
+    size_t ws_bytes = tkk::encode_workspace_bytes(total, n_docs, &L);
+    CUDA_OR_FAIL(t->ws.ensure(ws_bytes));
+    if (t->scratch.cap == 0) CUDA_OR_FAIL(t->scratch.ensure(1 << 20));
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if (t->timing) t->timer.reset();
+        cudaError_t e = tkk::encode_device(t->tables, d_data, d_doc_off, n_docs, total, add_bos, add_eos, d_tokens, cap, d_tok_off,
+                                           t->ws.p, L, (uint32_t*)t->scratch.p, t->scratch.cap / 4, t->sm_count, st,
+                                           t->timing ? &t->timer : nullptr);
+        if (e != cudaSuccess) return fail(TK_ERR_CUDA, "encode launch: %s", cudaGetErrorString(e));
+        uint32_t small[64];
+        CUDA_OR_FAIL(cudaMemcpyAsync(small, (unsigned char*)t->ws.p + L.off_small, sizeof small, cudaMemcpyDeviceToHost, st));
+        CUDA_OR_FAIL(cudaStreamSynchronize(st));
+        if (t->timing) t->timer.collect(t->stage_names, t->stage_ms);
+        const uint32_t flags = small[tkk::TKK_S_FLAGS];
+        uint64_t err_pos, total_out;
+        memcpy(&err_pos, small + tkk::TKK_S_ERRPOS, 8);
+        memcpy(&total_out, small + tkk::TKK_S_TOTAL, 8);
+        if (flags & tkk::TKK_FLAG_BAD_OFFSETS)
+            return fail(TK_ERR_INVALID_ARGUMENT, "document offsets must start at 0, be non-decreasing and end at the text length");
+        if (err_pos != ~0ull) return fail(TK_ERR_INVALID_UTF8, "input is not valid UTF-8 at byte %llu", (unsigned long long)err_pos);
+        if (flags & tkk::TKK_FLAG_SCRATCH_FULL) {
+            // a piece longer than TK_MED_MAX bytes needs 12 bytes of scratch per byte: grow and rerun
+            CUDA_OR_FAIL(t->scratch.ensure((size_t)total * 12 + 4096));
+            continue;
+        }
+        *n_tokens = total_out;
+        if (flags & tkk::TKK_FLAG_OUT_FULL)
+            return fail(TK_ERR_BUFFER_TOO_SMALL, "token buffer holds %llu ids, %llu needed", (unsigned long long)cap,
+                        (unsigned long long)total_out);
+        return TK_OK;
+    }
+    return fail(TK_ERR_CUDA, "huge-piece scratch could not be grown");
+}
+
+extern "C" int tk_encode_batch_device(const tk_tokenizer* tc, const uint8_t* d_data, const uint64_t* d_doc_off, size_t n_docs,
+                                      uint64_t total_bytes, int add_bos, int add_eos, uint32_t* d_tokens,
+                                      uint64_t tokens_capacity, uint64_t* d_tok_off, uint64_t* n_tokens, void* stream) {
+    int rc = check_encode_args(tc, add_bos, add_eos);
+    if (rc) return rc;
+    if (!d_doc_off || !d_tok_off || !n_tokens || (!d_data && total_bytes) || (!d_tokens && tokens_capacity))
+        return fail(TK_ERR_INVALID_ARGUMENT, "null argument");
+    tk_tokenizer* t = const_cast<tk_tokenizer*>(tc);
+    std::lock_guard<std::mutex> g(t->mu);
+    DeviceGuard dg(t->device);
+    if (!dg.ok) return fail(TK_ERR_CUDA, "cudaSetDevice(%d) failed", t->device);
+    return run_encode(t, d_data, d_doc_off, n_docs, total_bytes, add_bos, add_eos, d_tokens, tokens_capacity, d_tok_off, n_tokens,
+                      (cudaStream_t)stream);
+}
+
+extern "C" int tk_encode_batch(const tk_tokenizer* tc, const uint8_t* data, const uint64_t* doc_off, size_t n_docs, int add_bos,
+                               int add_eos, uint32_t** tokens, uint64_t** tok_off) {
+    int rc = check_encode_args(tc, add_bos, add_eos);
+    if (rc) return rc;
+    if (!doc_off || !tokens || !tok_off) return fail(TK_ERR_INVALID_ARGUMENT, "null argument");
+    *tokens = nullptr;
+    *tok_off = nullptr;
+    const uint64_t total = doc_off[n_docs];
+    if (!data && total) return fail(TK_ERR_INVALID_ARGUMENT, "null text");
+    tk_tokenizer* t = const_cast<tk_tokenizer*>(tc);
+    std::lock_guard<std::mutex> g(t->mu);
+    DeviceGuard dg(t->device);
+    if (!dg.ok) return fail(TK_ERR_CUDA, "cudaSetDevice(%d) failed", t->device);
+    cudaStream_t st = t->stream;
+    const uint64_t cap = total + 2 * (uint64_t)n_docs + 2;
+    CUDA_OR_FAIL(t->in_data.ensure(total + 64));
+    CUDA_OR_FAIL(t->in_off.ensure((n_docs + 1) * 8));
+    CUDA_OR_FAIL(t->out_a.ensure(cap * 4));
+    CUDA_OR_FAIL(t->out_b.ensure((n_docs + 1) * 8));
+    if (total) CUDA_OR_FAIL(cudaMemcpyAsync(t->in_data.p, data, total, cudaMemcpyHostToDevice, st));
+    CUDA_OR_FAIL(cudaMemcpyAsync(t->in_off.p, doc_off, (n_docs + 1) * 8, cudaMemcpyHostToDevice, st));
+    uint64_t n_tok = 0;
+    rc = run_encode(t, (const uint8_t*)t->in_data.p, (const uint64_t*)t->in_off.p, n_docs, total, add_bos, add_eos,
+                    (uint32_t*)t->out_a.p, cap, (uint64_t*)t->out_b.p, &n_tok, st);
+    if (rc) return rc;
+    uint32_t* h_tok = (uint32_t*)g_pool.get(n_tok * 4 + 4);
+    uint64_t* h_off = (uint64_t*)g_pool.get((n_docs + 1) * 8);
+    if (!h_tok || !h_off) { g_pool.put(h_tok); g_pool.put(h_off); return fail(TK_ERR_CUDA, "out of pinned host memory"); }
+    cudaError_t e = cudaSuccess;
+    if (n_tok) e = cudaMemcpyAsync(h_tok, t->out_a.p, n_tok * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_off, t->out_b.p, (n_docs + 1) * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { g_pool.put(h_tok); g_pool.put(h_off); return fail(TK_ERR_CUDA, "copying ids back: %s", cudaGetErrorString(e)); }
+    *tokens = h_tok;
+    *tok_off = h_off;
+    return TK_OK;
+}
+
+extern "C" int tk_encode(const tk_tokenizer* t, const uint8_t* utf8, size_t len, int add_bos, int add_eos, uint32_t** out,
+                         size_t* n_out) {
+    if (!out || !n_out) return fail(TK_ERR_INVALID_ARGUMENT, "null argument");
+    uint64_t off[2] = {0, len};
+    uint64_t* tok_off = nullptr;
+    int rc = tk_encode_batch(t, utf8, off, 1, add_bos, add_eos, out, &tok_off);
+    if (rc) return rc;
+    *n_out = (size_t)tok_off[1];
+    tk_buffer_free(tok_off);
+    return TK_OK;
+}
+
+// ------------------------------------------------------------------------------------------ decode
+
+static int run_decode(tk_tokenizer* t, const uint32_t* d_ids, const uint64_t* d_tok_off, size_t n_docs, uint64_t n_ids, int policy,
+                      uint8_t* d_out, uint64_t cap, uint64_t* d_byte_off, int32_t* d_status, uint64_t* n_bytes, uint64_t* bad_doc,
+                      cudaStream_t st) {
+    if (policy != TK_POLICY_IGNORE && policy != TK_POLICY_KEEP && policy != TK_POLICY_RAISE)
+        return fail(TK_ERR_INVALID_ARGUMENT, "unknown special token policy %d", policy);
+    if (((uintptr_t)d_ids & 3u) != 0) return fail(TK_ERR_INVALID_ARGUMENT, "id pointer must be 4-byte aligned");
+    tkk::DecodeLayout L;
+    size_t ws_bytes = tkk::decode_workspace_bytes(n_ids, n_docs, cap, &L);
+    CUDA_OR_FAIL(t->ws.ensure(ws_bytes));
+    cudaError_t e = tkk::decode_device(t->tables, d_ids, d_tok_off, n_docs, n_ids, policy, d_out, cap, d_byte_off, d_status, t->ws.p,
+                                       L, st);
+    if (e != cudaSuccess) return fail(TK_ERR_CUDA, "decode launch: %s", cudaGetErrorString(e));
+    uint32_t small[64];
+    CUDA_OR_FAIL(cudaMemcpyAsync(small, (unsigned char*)t->ws.p + L.off_small, sizeof small, cudaMemcpyDeviceToHost, st));
+    CUDA_OR_FAIL(cudaStreamSynchronize(st));
+    const uint32_t flags = small[tkk::TKK_S_FLAGS];
+    uint64_t total_out, first_bad;
+    memcpy(&total_out, small + tkk::TKK_S_TOTAL, 8);
+    memcpy(&first_bad, small + tkk::TKK_S_BADDOC, 8);
+    if (flags & tkk::TKK_FLAG_BAD_OFFSETS)
+        return fail(TK_ERR_INVALID_ARGUMENT, "id offsets must start at 0, be non-decreasing and end at the id count");
+    *n_bytes = total_out;
+    if (flags & tkk::TKK_FLAG_OUT_FULL)
+        return fail(TK_ERR_BUFFER_TOO_SMALL, "byte buffer holds %llu bytes, %llu needed", (unsigned long long)cap,
+                    (unsigned long long)total_out);
+    if (first_bad != ~0ull) {
+        if (bad_doc) *bad_doc = first_bad;
+        int32_t s = 0;
+        // the status of the first failing sequence decides the error (Result<Vec<_>> semantics)
+        if (d_status) {
+            CUDA_OR_FAIL(cudaMemcpyAsync(&s, d_status + first_bad, 4, cudaMemcpyDeviceToHost, st));
+            CUDA_OR_FAIL(cudaStreamSynchronize(st));
+        }
+        if (s == TK_ERR_SPECIAL_TOKEN_POLICY)
+            return fail(TK_ERR_SPECIAL_TOKEN_POLICY, "Decoding tokens that contain special tokens is not allowed (sequence %llu)",
+                        (unsigned long long)first_bad);
+        return fail(TK_ERR_TOKENIZERS, "decode failed for sequence %llu: unknown token id or the bytes of an ordinary run are not valid UTF-8",
+                    (unsigned long long)first_bad);
+    }
+    return TK_OK;
+}
+
+extern "C" int tk_decode_batch_device(const tk_tokenizer* tc, const uint32_t* d_ids, const uint64_t* d_tok_off, size_t n_docs,
+                                      uint64_t total_ids, int policy, uint8_t* d_out, uint64_t out_capacity, uint64_t* d_byte_off,
+                                      int32_t* d_doc_status, uint64_t* n_bytes, uint64_t* bad_doc, void* stream) {
+    int rc = check_encode_args(tc, 0, 0);
+    if (rc) return rc;
+    if (!d_tok_off || !d_byte_off || !n_bytes || (!d_ids && total_ids) || (!d_out && out_capacity))
+        return fail(TK_ERR_INVALID_ARGUMENT, "null argument");
+    tk_tokenizer* t = const_cast<tk_tokenizer*>(tc);
+    std::lock_guard<std::mutex> g(t->mu);
+    DeviceGuard dg(t->device);
+    if (!dg.ok) return fail(TK_ERR_CUDA, "cudaSetDevice(%d) failed", t->device);
+    int32_t* st_buf = d_doc_status;
+    if (!st_buf) {
+        CUDA_OR_FAIL(t->status.ensure((n_docs + 1) * 4));
+        st_buf = (int32_t*)t->status.p;
+    }
+    return run_decode(t, d_ids, d_tok_off, n_docs, total_ids, policy, d_out, out_capacity, d_byte_off, st_buf, n_bytes, bad_doc,
+                      (cudaStream_t)stream);
+}
+
+extern "C" int tk_decode_batch(const tk_tokenizer* tc, const uint32_t* ids, const uint64_t* tok_off, size_t n_docs, int policy,
+                               uint8_t** out, uint64_t** byte_off, uint64_t* bad_doc) {
+    int rc = check_encode_args(tc, 0, 0);
+    if (rc) return rc;
+    if (!tok_off || !out || !byte_off) return fail(TK_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    *byte_off = nullptr;
+    const uint64_t n_ids = tok_off[n_docs];
+    if (!ids && n_ids) return fail(TK_ERR_INVALID_ARGUMENT, "null ids");
+    tk_tokenizer* t = const_cast<tk_tokenizer*>(tc);
+    const tk::HostModel& h = t->host;
+    // exact output size from the host tables (a length sum over ids; the bytes themselves are
+    // gathered on the device)
+    uint64_t cap = 0;
+    for (uint64_t i = 0; i < n_ids; ++i) {
+        const uint32_t v = ids[i];
+        if (v < h.num_special) { if (policy == TK_POLICY_KEEP) cap += h.special_off[v + 1] - h.special_off[v]; }
+        else if (v - h.num_special < h.n_vocab()) cap += h.vocab_off[v - h.num_special + 1] - h.vocab_off[v - h.num_special];
+    }
+    std::lock_guard<std::mutex> g(t->mu);
+    DeviceGuard dg(t->device);
+    if (!dg.ok) return fail(TK_ERR_CUDA, "cudaSetDevice(%d) failed", t->device);
+    cudaStream_t st = t->stream;
+    CUDA_OR_FAIL(t->in_data.ensure(n_ids * 4 + 64));
+    CUDA_OR_FAIL(t->in_off.ensure((n_docs + 1) * 8));
+    CUDA_OR_FAIL(t->out_a.ensure(cap + 64));
+    CUDA_OR_FAIL(t->out_b.ensure((n_docs + 1) * 8));
+    CUDA_OR_FAIL(t->status.ensure((n_docs + 1) * 4));
+    if (n_ids) CUDA_OR_FAIL(cudaMemcpyAsync(t->in_data.p, ids, n_ids * 4, cudaMemcpyHostToDevice, st));
+    CUDA_OR_FAIL(cudaMemcpyAsync(t->in_off.p, tok_off, (n_docs + 1) * 8, cudaMemcpyHostToDevice, st));
+    uint64_t n_bytes = 0;
+    rc = run_decode(t, (const uint32_t*)t->in_data.p, (const uint64_t*)t->in_off.p, n_docs, n_ids, policy, (uint8_t*)t->out_a.p, cap,
+                    (uint64_t*)t->out_b.p, (int32_t*)t->status.p, &n_bytes, bad_doc, st);
+    if (rc) return rc;
+    uint8_t* h_out = (uint8_t*)g_pool.get(n_bytes + 1);
+    uint64_t* h_off = (uint64_t*)g_pool.get((n_docs + 1) * 8);
+    if (!h_out || !h_off) { g_pool.put(h_out); g_pool.put(h_off); return fail(TK_ERR_CUDA, "out of pinned host memory"); }
+    cudaError_t e = cudaSuccess;
+    if (n_bytes) e = cudaMemcpyAsync(h_out, t->out_a.p, n_bytes, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_off, t->out_b.p, (n_docs + 1) * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { g_pool.put(h_out); g_pool.put(h_off); return fail(TK_ERR_CUDA, "copying text back: %s", cudaGetErrorString(e)); }
+    h_out[n_bytes] = 0;
+    *out = h_out;
+    *byte_off = h_off;
+    return TK_OK;
+}
+
+extern "C" int tk_decode(const tk_tokenizer* t, const uint32_t* ids, size_t n, int policy, uint8_t** out, size_t* n_out) {
+    if (!out || !n_out) return fail(TK_ERR_INVALID_ARGUMENT, "null argument");
+    uint64_t off[2] = {0, n};
+    uint64_t* byte_off = nullptr;
+    int rc = tk_decode_batch(t, ids, off, 1, policy, out, &byte_off, nullptr);
+    if (rc) return rc;
+    *n_out = (size_t)byte_off[1];
+    tk_buffer_free(byte_off);
+    return TK_OK;
+}
+
+// decode_all (:463-511): same bytes as decode; the element boundaries are a host-side walk over
+// the ids (one element per ordinary run, one per kept special id).
+extern "C" int tk_decode_all(const tk_tokenizer* t, const uint32_t* ids, size_t n, int policy, uint8_t** out, uint64_t** part_end,
+                             size_t* n_parts) {
+    if (!out || !part_end || !n_parts) return fail(TK_ERR_INVALID_ARGUMENT, "null argument");
+    size_t n_out = 0;
+    int rc = tk_decode(t, ids, n, policy, out, &n_out);
+    if (rc) return rc;
+    const tk::HostModel& h = t->host;
+    std::vector<uint64_t> ends;
+    uint64_t o = 0;
+    size_t i = 0;
+    while (i < n) {
+        const bool special = ids[i] < h.num_special;
+        size_t j = i;
+        while (j < n && (ids[j] < h.num_special) == special) ++j;
+        if (special) {
+            if (policy == TK_POLICY_KEEP)
+                for (size_t k = i; k < j; ++k) { o += h.special_off[ids[k] + 1] - h.special_off[ids[k]]; ends.push_back(o); }
+        } else {
+            for (size_t k = i; k < j; ++k) { uint32_t r = ids[k] - (uint32_t)h.num_special; o += h.vocab_off[r + 1] - h.vocab_off[r]; }
+            ends.push_back(o);
+        }
+        i = j;
+    }
+    uint64_t* pe = (uint64_t*)g_pool.get(ends.size() * 8 + 8);
+    if (!pe) { tk_buffer_free(*out); *out = nullptr; return fail(TK_ERR_CUDA, "out of host memory"); }
+    if (!ends.empty()) memcpy(pe, ends.data(), ends.size() * 8);
+    *part_end = pe;
+    *n_parts = ends.size();
+    return TK_OK;
+}
+
+// ------------------------------------------------------------------------------------------ sharding, misc
+
+extern "C" int tk_shard_plan(const uint64_t* doc_off, size_t n_docs, size_t n_shards, uint64_t* shard_begin) {
+    if (!doc_off || !shard_begin || n_shards == 0) return fail(TK_ERR_INVALID_ARGUMENT, "null argument");
+    const uint64_t base = doc_off[0], total = doc_off[n_docs] - base;
+    shard_begin[0] = 0;
+    size_t d = 0;
+    for (size_t s = 1; s < n_shards; ++s) {
+        // first document whose start is at or past the s-th byte quantile
+        const uint64_t target = base + (uint64_t)((unsigned __int128)total * s / n_shards);
+        size_t lo = d, hi = n_docs;
+        while (lo < hi) {
+            size_t mid = (lo + hi) / 2;
+            if (doc_off[mid] < target) lo = mid + 1; else hi = mid;
+        }
+        d = lo;
+        shard_begin[s] = d;
+    }
+    shard_begin[n_shards] = n_docs;
+    return TK_OK;
+}
+
+extern "C" uint64_t tk_kernel_launch_count(void) { return tkk::launch_count(); }
+
+extern "C" void tk_set_stage_timing(tk_tokenizer* t, int enabled) {
+    if (t) t->timing = enabled != 0;
+}
+
+extern "C" size_t tk_last_stage_times(const tk_tokenizer* t, const char** names, float* ms, size_t cap) {
+    if (!t) return 0;
+    size_t n = std::min(cap, t->stage_names.size());
+    for (size_t i = 0; i < n; ++i) {
+        if (names) names[i] = t->stage_names[i].c_str();
+        if (ms) ms[i] = t->stage_ms[i];
+    }
+    return n;
+}

@@ -1,0 +1,164 @@
+// tk_device.cuh -- device-side table lookups and the exact BPE merge loops.
+//
+// Replaces tiktoken-rs `CoreBPE`'s `ranks.get(piece)` + `byte_pair_merge` (the engine behind
+// Tekkenizer::encode, src/tekkenizer.rs:384-386).  Definition kept bit-exact: parts start as
+// single bytes; repeatedly merge the adjacent pair whose concatenation has the lowest rank,
+// leftmost on ties; stop when no adjacent pair is a vocabulary entry.  Because every part is
+// always a vocabulary entry, "rank of the concatenated bytes" is looked up by (left id, right
+// id) in a pair table built at load time (tk_host.cpp) instead of by bytes.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "tk_common.h"
+
+__device__ __forceinline__ uint64_t tk_ldg64(const uint64_t* p) { return __ldg((const unsigned long long*)p); }
+
+// rank of bytes(l)+bytes(r), TK_INF if it is not a vocabulary entry
+__device__ __forceinline__ uint32_t tk_pair_rank(const TkDeviceTables& T, uint32_t l, uint32_t r) {
+    uint32_t i = tk_pair_hash(l, r) & T.pair_mask;
+    const uint64_t key = tk_pair_key(l, r);
+    for (;;) {
+        uint64_t s = tk_ldg64(T.pair_slots + i);
+        if (s == 0) return TK_INF;
+        if (((s >> TK_ID_BITS) & ((1ull << (2 * TK_ID_BITS)) - 1ull)) == key) return (uint32_t)s & TK_ID_MASK;
+        i = (i + 1) & T.pair_mask;
+    }
+}
+
+// Whole-piece lookup (CoreBPE's `encoder.get(piece)` shortcut).  p may point to shared or global
+// memory; len >= 1.
+__device__ __forceinline__ uint32_t tk_vocab_lookup(const TkDeviceTables& T, const uint8_t* p, uint32_t len) {
+    if (len > T.max_token_len) return TK_INF;
+    TkPieceHasher h;
+    h.init(len);
+    uint64_t key8 = 0;
+    for (uint32_t i = 0; i < len; i += 8) {
+        uint64_t w = 0;
+        uint32_t m = len - i < 8 ? len - i : 8;
+        for (uint32_t j = 0; j < m; ++j) w |= (uint64_t)p[i + j] << (8 * j);
+        if (i == 0) key8 = w;
+        h.add(w);
+    }
+    const uint64_t hv = h.finish();
+    const uint64_t key = len <= 8 ? key8 : hv;
+    uint32_t i = (uint32_t)hv & T.vocab_mask;
+    for (;;) {
+        const uint4 raw = __ldg((const uint4*)(T.vocab_slots + i));
+        const uint32_t slen = raw.w;
+        if (slen == 0) return TK_INF;
+        const uint64_t skey = (uint64_t)raw.y << 32 | raw.x;
+        if (slen == len && skey == key) {
+            if (len <= 8) return raw.z;
+            const uint8_t* v = T.vocab_bytes + T.vocab_off[raw.z];
+            bool same = true;
+            for (uint32_t j = 0; j < len; ++j)
+                if (__ldg(v + j) != p[j]) { same = false; break; }
+            if (same) return raw.z;
+        }
+        i = (i + 1) & T.vocab_mask;
+    }
+}
+
+// ---- one thread, one short piece ---------------------------------------------------------------
+// Sequential merge loop on a piece of at most TK_SHORT_MAX bytes held by one thread.  out[] gets
+// the ranks (no id offset); returns their count.
+#define TK_SHORT_MAX 64
+
+__device__ inline uint32_t tk_bpe_thread(const TkDeviceTables& T, const uint8_t* p, uint32_t n, uint32_t* out) {
+    uint32_t id[TK_SHORT_MAX];
+    uint32_t rk[TK_SHORT_MAX];
+    uint8_t nx[TK_SHORT_MAX];
+    for (uint32_t i = 0; i < n; ++i) { id[i] = p[i]; nx[i] = (uint8_t)(i + 1); }
+    for (uint32_t i = 0; i + 1 < n; ++i) rk[i] = tk_pair_rank(T, id[i], id[i + 1]);
+    rk[n - 1] = TK_INF;
+    for (;;) {
+        uint32_t best = TK_INF, bpos = 0, bprev = TK_INF, prev = TK_INF;
+        for (uint32_t i = 0; i < n; i = nx[i]) {
+            if (rk[i] < best) { best = rk[i]; bpos = i; bprev = prev; }
+            prev = i;
+        }
+        if (best == TK_INF) break;
+        const uint32_t j = nx[bpos];
+        const uint32_t nn = nx[j];
+        id[bpos] = best;
+        nx[bpos] = (uint8_t)nn;
+        rk[bpos] = nn < n ? tk_pair_rank(T, best, id[nn]) : TK_INF;
+        if (bprev != TK_INF) rk[bprev] = tk_pair_rank(T, id[bprev], best);
+    }
+    uint32_t k = 0;
+    for (uint32_t i = 0; i < n; i = nx[i]) out[k++] = id[i];
+    return k;
+}
+
+// ---- one warp, one medium piece ------------------------------------------------------------------
+// Same loop, parts in shared memory (TK_MED_MAX entries per warp), each lane caching the minimum
+// of its own slice so a merge step costs one warp-wide min + a rescan by the lanes it touched.
+#define TK_MED_MAX 512
+#define TK_DEAD 0xFFFFFFFEu
+
+struct TkWarpBpeSmem {
+    uint32_t id[TK_MED_MAX];
+    uint32_t rk[TK_MED_MAX];
+    uint16_t nx[TK_MED_MAX];
+    uint16_t pv[TK_MED_MAX];
+};
+
+// key = rank << 9 | position : the warp-wide minimum is the lowest rank, leftmost on ties
+__device__ __forceinline__ uint32_t tk_slice_min(const uint32_t* rk, uint32_t lo, uint32_t hi) {
+    uint32_t best = 0xFFFFFFFFu;
+    for (uint32_t i = lo; i < hi; ++i) {
+        uint32_t r = rk[i];
+        if (r != TK_INF) { uint32_t k = (r << 9) | i; best = k < best ? k : best; }
+    }
+    return best;
+}
+
+// src: the piece bytes (global).  out: global buffer for up to n ranks.  Returns the count
+// (same value on all lanes).  Must be called by all 32 lanes.
+__device__ inline uint32_t tk_bpe_warp(const TkDeviceTables& T, TkWarpBpeSmem& S, const uint8_t* src, uint32_t n,
+                                       uint32_t* out) {
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t i = lane; i < n; i += 32) {
+        S.id[i] = __ldg(src + i);
+        S.nx[i] = (uint16_t)(i + 1);
+        S.pv[i] = (uint16_t)(i - 1);   // 0xFFFF for i == 0
+    }
+    __syncwarp();
+    for (uint32_t i = lane; i < n; i += 32) S.rk[i] = (i + 1 < n) ? tk_pair_rank(T, S.id[i], S.id[i + 1]) : TK_INF;
+    __syncwarp();
+    const uint32_t k = (n + 31u) / 32u;
+    const uint32_t lo = lane * k < n ? lane * k : n, hi = (lane + 1) * k < n ? (lane + 1) * k : n;
+    uint32_t mine = tk_slice_min(S.rk, lo, hi);
+    for (;;) {
+        const uint32_t g = __reduce_min_sync(0xFFFFFFFFu, mine);
+        if (g == 0xFFFFFFFFu) break;
+        const uint32_t pos = g & 511u, r = g >> 9;
+        const uint32_t j = S.nx[pos], p = S.pv[pos];
+        const uint32_t nn = S.nx[j];
+        __syncwarp();
+        if (lane == 0) {
+            S.id[pos] = r;
+            S.id[j] = TK_DEAD;
+            S.rk[j] = TK_INF;
+            S.nx[pos] = (uint16_t)nn;
+            if (nn < n) S.pv[nn] = (uint16_t)pos;
+            S.rk[pos] = nn < n ? tk_pair_rank(T, r, S.id[nn]) : TK_INF;
+        } else if (lane == 1) {
+            if (p != 0xFFFFu) S.rk[p] = tk_pair_rank(T, S.id[p], r);
+        }
+        __syncwarp();
+        const bool touched = (pos >= lo && pos < hi) || (j >= lo && j < hi) || (p != 0xFFFFu && p >= lo && p < hi);
+        if (touched) mine = tk_slice_min(S.rk, lo, hi);
+    }
+    // compact the surviving parts
+    uint32_t count = 0;
+    for (uint32_t base = 0; base < n; base += 32) {
+        const uint32_t i = base + lane;
+        const uint32_t v = i < n ? S.id[i] : TK_DEAD;
+        const uint32_t alive = __ballot_sync(0xFFFFFFFFu, v != TK_DEAD);
+        if (v != TK_DEAD) out[count + __popc(alive & ((1u << lane) - 1u))] = v;
+        count += __popc(alive);
+    }
+    __syncwarp();
+    return count;
+}

@@ -1,0 +1,815 @@
+// tk_kernels.cu -- sm_100a kernels of the encode / decode path and their launch sequences.
+//
+// Encode (Tekkenizer::encode, src/tekkenizer.rs:378-405, batched) = the launch sequence in
+// tk_encode_device():
+//   K0 docmark      document-start bitmask from doc offsets
+//   K1 pretok       regex split -> piece-start bitmask (tk_pretok.h), one thread per 32 bytes
+//   K1s/K1f         carry digit/CR-LF/whitespace run state across thread blocks (rarely non-trivial)
+//   K2a longmark    find pieces longer than TK_SHORT_MAX bytes
+//   K3  longmerge   exact BPE for those (warp per piece in shared memory, block per huge piece)
+//   K2  encode      per 8 KiB tile: vocabulary lookup / thread-level BPE per piece, BOS/EOS,
+//                   decoupled look-back prefix over tiles, ids written straight to their final place
+// Decode (Tekkenizer::decode, src/tekkenizer.rs:436-560, batched): lengths, scan, byte gather,
+// per-run UTF-8 validation.
+#include "tk_kernels.h"
+
+#include <cstdio>
+
+#include "tk_device.cuh"
+#include "tk_pretok.h"
+
+namespace tkk {
+
+static std::atomic<uint64_t> g_launches{0};
+uint64_t launch_count() { return g_launches.load(); }
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+#define TK_LAUNCHED() count_launch()
+
+void StageTimer::mark(cudaStream_t st, const char* name) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, st);
+    names.emplace_back(name);
+    events.push_back(e);
+}
+void StageTimer::collect(std::vector<std::string>& out_names, std::vector<float>& out_ms) {
+    out_names.clear();
+    out_ms.clear();
+    for (size_t i = 0; i + 1 < events.size(); ++i) {
+        float ms = 0.f;
+        cudaEventSynchronize(events[i + 1]);
+        cudaEventElapsedTime(&ms, events[i], events[i + 1]);
+        out_names.push_back(names[i]);
+        out_ms.push_back(ms);
+    }
+}
+void StageTimer::reset() {
+    for (cudaEvent_t e : events) cudaEventDestroy(e);
+    events.clear();
+    names.clear();
+}
+StageTimer::~StageTimer() { reset(); }
+
+// =====================================================================================================
+// K0: document-start bitmask.  Bit p is set iff some document starts at byte p; bit `total` is
+// the end-of-data sentinel.  Also validates the offsets.
+// =====================================================================================================
+__global__ void docmark_kernel(const uint64_t* __restrict__ doc_off, uint64_t n_docs, uint64_t total,
+                               uint32_t* __restrict__ ds_mask, uint32_t* __restrict__ flags) {
+    uint64_t d = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d > n_docs) return;
+    uint64_t o = doc_off[d];
+    bool ok = o <= total;
+    if (d == 0 && o != 0) ok = false;
+    if (d == n_docs && o != total) ok = false;
+    if (d < n_docs && doc_off[d + 1] < o) ok = false;
+    if (!ok) { atomicOr(flags, TKK_FLAG_BAD_OFFSETS); return; }
+    atomicOr(ds_mask + (o >> 5), 1u << (o & 31));
+}
+
+// =====================================================================================================
+// K1: pre-tokeniser.  256 threads = 256 windows of 32 bytes = one 8 KiB tile.
+// =====================================================================================================
+#define PT_T 256
+
+__device__ __forceinline__ uint32_t rs_pack(const TkRunSummary& s) {
+    return s.n_all | (s.n_val << 1) | (s.r_mode << 3) | (s.head << 5);
+}
+__device__ __forceinline__ TkRunSummary rs_unpack(uint32_t p) {
+    TkRunSummary s;
+    s.n_all = p & 1u; s.n_val = (p >> 1) & 3u; s.r_mode = (p >> 3) & 3u; s.head = (p >> 5) & 3u;
+    return s;
+}
+#define RS_IDENTITY (1u | (2u << 3))
+
+struct PtSmem {
+    uint32_t lead[PT_T + 2], mL[PT_T + 2], mN[PT_T + 2], mR[PT_T + 2], mW[PT_T + 2], sp[PT_T + 2], ap[PT_T + 2],
+        ds[PT_T + 2];
+    uint32_t head[PT_T + 1];
+    uint32_t wtot[PT_T / 32];
+    long long pend;
+};
+
+__device__ __forceinline__ void pt_store(PtSmem& S, int i, const TkWin& w) {
+    S.lead[i] = w.lead; S.mL[i] = w.mL; S.mN[i] = w.mN; S.mR[i] = w.mR; S.mW[i] = w.mW; S.sp[i] = w.sp; S.ap[i] = w.ap;
+    S.ds[i] = w.ds;
+}
+__device__ __forceinline__ TkWin pt_load(const PtSmem& S, int i) {
+    TkWin w;
+    w.lead = S.lead[i]; w.mL = S.mL[i]; w.mN = S.mN[i]; w.mR = S.mR[i]; w.mW = S.mW[i]; w.sp = S.sp[i]; w.ap = S.ap[i];
+    w.ds = S.ds[i]; w.bad = 0;
+    return w;
+}
+
+__device__ __forceinline__ TkWin pt_classify(const uint8_t* __restrict__ data, uint64_t n, const uint32_t* __restrict__ ds_mask,
+                                             uint64_t n_windows, long long wi, const TkDeviceTables& T) {
+    TkWin z;
+    z.lead = 0xFFFFFFFFu; z.mL = z.mN = z.mR = z.mW = z.sp = z.ap = z.ds = z.bad = 0;
+    if (wi < 0 || (uint64_t)wi >= n_windows) return z;
+    const uint64_t pos = (uint64_t)wi * 32u;
+    uint32_t w[8];
+    if (pos + 32 <= n) {
+        const uint4 a = __ldg((const uint4*)(data + pos));
+        const uint4 b = __ldg((const uint4*)(data + pos) + 1);
+        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint64_t q = pos + 4 * j + k;
+                if (q < n) v |= (uint32_t)data[q] << (8 * k);
+            }
+            w[j] = v;
+        }
+    }
+    return tk_classify_window(data, n, pos, w, ds_mask[wi], T);
+}
+
+// Process tile b.  FIX=false: first pass (entry state guessed from the halo window, summary
+// written).  FIX=true: re-run with the exact entry state / pending verdict from the scan kernel.
+template <bool FIX>
+__device__ __forceinline__ void pretok_tile(PtSmem& S, uint32_t b, const uint8_t* __restrict__ data, uint64_t n,
+                                            const uint32_t* __restrict__ ds_mask, uint32_t* __restrict__ start_mask,
+                                            uint64_t n_windows, const TkDeviceTables& T, TkkTileSummary* __restrict__ summ,
+                                            const uint32_t* __restrict__ carry, unsigned long long* __restrict__ err_pos) {
+    const int t = threadIdx.x;
+    const long long wi = (long long)b * PT_T + t;
+    const uint64_t pos = (uint64_t)wi * 32u;
+    TkWin c = pt_classify(data, n, ds_mask, n_windows, wi, T);
+    pt_store(S, t + 1, c);
+    if (t < 2) {
+        const long long hw = t == 0 ? (long long)b * PT_T - 1 : (long long)b * PT_T + PT_T;
+        TkWin h = pt_classify(data, n, ds_mask, n_windows, hw, T);
+        pt_store(S, t == 0 ? 0 : PT_T + 1, h);
+    }
+    if (t == 0) S.pend = -1;
+    __syncthreads();
+    const TkWin p = pt_load(S, t), nx = pt_load(S, t + 2);
+    TkWin zero;
+    zero.lead = 0xFFFFFFFFu; zero.mL = zero.mN = zero.mR = zero.mW = zero.sp = zero.ap = zero.ds = zero.bad = 0;
+    const TkDerived dp = tk_derive(data, n, pos - 32, zero, p, c, 0);
+    const TkDerived dc = tk_derive(data, n, pos, p, c, nx, dp.sO);
+    const TkRunSummary mine = tk_summarize(c);
+    S.head[t] = mine.head;
+    if (t == 0) S.head[PT_T] = tk_summarize(pt_load(S, PT_T + 1)).head;
+
+    // exclusive scan of the run summaries over the tile
+    const int lane = t & 31, warp = t >> 5;
+    uint32_t inc = rs_pack(mine);
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if (lane >= d) inc = rs_pack(tk_compose(rs_unpack(o), rs_unpack(inc)));
+    }
+    if (lane == 31) S.wtot[warp] = inc;
+    uint32_t exc = __shfl_up_sync(0xFFFFFFFFu, inc, 1);
+    if (lane == 0) exc = RS_IDENTITY;
+    __syncthreads();
+    uint32_t pre = RS_IDENTITY;
+    for (int w = 0; w < warp; ++w) pre = rs_pack(tk_compose(rs_unpack(pre), rs_unpack(S.wtot[w])));
+    const TkRunSummary E = tk_compose(rs_unpack(pre), rs_unpack(exc));
+
+    // state entering the tile
+    uint32_t n0, a0, n_prov = 0, r_prov = 0, confirm = 0;
+    if (FIX) {
+        const uint32_t cw = carry[b];
+        n0 = cw & 3u; a0 = (cw >> 2) & 1u; confirm = (cw >> 3) & 1u;
+    } else if (b == 0) {
+        n0 = 0; a0 = 0;
+    } else {
+        const TkRunSummary hs = tk_summarize(pt_load(S, 0));
+        n_prov = hs.n_all; n0 = hs.n_val;
+        r_prov = hs.r_mode == 2u; a0 = r_prov ? 0u : hs.r_mode;
+    }
+    const uint32_t n_in = E.n_all ? (n0 + E.n_val) % 3u : E.n_val;
+    const uint32_t abs_in = E.r_mode == 2u ? a0 : E.r_mode;
+
+    TkEval ev = tk_eval_window(p, c, nx, dp, dc, n_in, abs_in);
+    uint32_t start = ev.start;
+    if (ev.pend >= 0) {
+        uint32_t verdict = 0;
+        for (int v = t + 2; v <= PT_T; ++v) {
+            verdict = S.head[v];
+            if (verdict) break;
+        }
+        if (verdict == 2u) start |= 1u << ev.pend;
+        else if (verdict == 0u) {
+            if (FIX) { if (confirm) start |= 1u << ev.pend; }
+            else S.pend = (long long)(pos + (uint64_t)ev.pend);
+        }
+    }
+    if ((uint64_t)wi < n_windows) {
+        const uint32_t keep = (pos + 32 <= n) ? 0xFFFFFFFFu : (uint32_t)((2ull << (n - pos)) - 1ull);
+        start_mask[wi] = start & keep;
+        const uint32_t valid = (pos + 32 <= n) ? 0xFFFFFFFFu : (uint32_t)((1ull << (n - pos)) - 1ull);
+        if (c.bad & valid) atomicMin(err_pos, (unsigned long long)(pos + (uint64_t)(__ffs((int)(c.bad & valid)) - 1)));
+    }
+    if (!FIX) {
+        __syncthreads();
+        if (t == PT_T - 1) {
+            TkkTileSummary s;
+            s.packed = rs_pack(tk_compose(E, mine));
+            s.assumed = n0 | (a0 << 2) | (n_prov << 3) | (r_prov << 4);
+            s.pend_pos = S.pend;
+            summ[b] = s;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(PT_T) pretok_kernel(const uint8_t* __restrict__ data, uint64_t n,
+                                                      const uint32_t* __restrict__ ds_mask, uint32_t* __restrict__ start_mask,
+                                                      uint64_t n_windows, TkDeviceTables T, TkkTileSummary* __restrict__ summ,
+                                                      unsigned long long* __restrict__ err_pos) {
+    __shared__ PtSmem S;
+    pretok_tile<false>(S, blockIdx.x, data, n, ds_mask, start_mask, n_windows, T, summ, nullptr, err_pos);
+}
+
+__global__ void __launch_bounds__(PT_T) pretok_fix_kernel(const uint8_t* __restrict__ data, uint64_t n,
+                                                          const uint32_t* __restrict__ ds_mask, uint32_t* __restrict__ start_mask,
+                                                          uint64_t n_windows, TkDeviceTables T, const uint32_t* __restrict__ carry,
+                                                          const uint32_t* __restrict__ worklist, const uint32_t* __restrict__ work_count,
+                                                          unsigned long long* __restrict__ err_pos) {
+    __shared__ PtSmem S;
+    const uint32_t cnt = *work_count;
+    for (uint32_t w = blockIdx.x; w < cnt; w += gridDim.x) {
+        pretok_tile<true>(S, worklist[w], data, n, ds_mask, start_mask, n_windows, T, nullptr, carry, err_pos);
+        __syncthreads();
+    }
+}
+
+// K1s: one block scans the tile summaries: exact entry state of every tile, verdict for every
+// pending whitespace candidate, and the list of tiles whose guess was wrong.
+#define SC_T 1024
+__global__ void __launch_bounds__(SC_T) pretok_scan_kernel(const TkkTileSummary* __restrict__ summ, uint32_t n_tiles,
+                                                           uint32_t* __restrict__ carry, uint32_t* __restrict__ worklist,
+                                                           uint32_t* __restrict__ work_count, uint32_t* __restrict__ start_mask) {
+    __shared__ uint32_t f_chunk[SC_T];     // composite of each chunk
+    __shared__ uint32_t in_state[SC_T];    // n | abs<<2 entering each chunk
+    __shared__ uint32_t h_chunk[SC_T];     // first head event inside each chunk
+    __shared__ uint32_t h_after[SC_T];     // first head event after each chunk
+    const uint32_t t = threadIdx.x;
+    const uint32_t per = (n_tiles + SC_T - 1) / SC_T;
+    const uint32_t lo = t * per < n_tiles ? t * per : n_tiles, hi = (t + 1) * per < n_tiles ? (t + 1) * per : n_tiles;
+    TkRunSummary f = rs_unpack(RS_IDENTITY);
+    for (uint32_t b = lo; b < hi; ++b) f = tk_compose(f, rs_unpack(summ[b].packed));
+    f_chunk[t] = rs_pack(f);
+    h_chunk[t] = f.head;
+    __syncthreads();
+    if (t == 0) {
+        uint32_t nst = 0, ast = 0;
+        for (uint32_t j = 0; j < SC_T; ++j) {
+            in_state[j] = nst | (ast << 2);
+            const TkRunSummary g = rs_unpack(f_chunk[j]);
+            nst = g.n_all ? (nst + g.n_val) % 3u : g.n_val;
+            ast = g.r_mode == 2u ? ast : g.r_mode;
+        }
+        uint32_t nh = 2;  // past the end of the data the run has ended
+        for (int j = SC_T - 1; j >= 0; --j) {
+            h_after[j] = nh;
+            if (h_chunk[j]) nh = h_chunk[j];
+        }
+    }
+    __syncthreads();
+    // forward: entry states; backward: verdicts
+    uint32_t nst = in_state[t] & 3u, ast = in_state[t] >> 2;
+    for (uint32_t b = lo; b < hi; ++b) {
+        carry[b] = nst | (ast << 2);
+        const TkRunSummary g = rs_unpack(summ[b].packed);
+        nst = g.n_all ? (nst + g.n_val) % 3u : g.n_val;
+        ast = g.r_mode == 2u ? ast : g.r_mode;
+    }
+    uint32_t nh = h_after[t];
+    for (uint32_t b = hi; b-- > lo;) {
+        const TkkTileSummary s = summ[b];
+        const uint32_t cw = carry[b];
+        const uint32_t confirm = nh == 2u;
+        const uint32_t n0 = s.assumed & 3u, a0 = (s.assumed >> 2) & 1u, n_prov = (s.assumed >> 3) & 1u, r_prov = (s.assumed >> 4) & 1u;
+        const bool wrong = (n_prov && (cw & 3u) != n0) || (r_prov && ((cw >> 2) & 1u) != a0);
+        carry[b] = cw | (confirm << 3);
+        if (wrong) worklist[atomicAdd(work_count, 1u)] = b;
+        else if (s.pend_pos >= 0 && confirm) atomicOr(start_mask + (s.pend_pos >> 5), 1u << (s.pend_pos & 31));
+        const uint32_t h = rs_unpack(s.packed).head;
+        if (h) nh = h;
+    }
+}
+
+// =====================================================================================================
+// K2a: pieces longer than TK_SHORT_MAX bytes.  Such a piece must start at the highest set bit of
+// its mask word, so one thread per word finds them all.
+// =====================================================================================================
+__global__ void longmark_kernel(const uint32_t* __restrict__ start_mask, uint64_t n_windows, uint64_t n,
+                                uint32_t* __restrict__ long_of_word, TkkLongRec* __restrict__ recs,
+                                uint32_t* __restrict__ n_long) {
+    const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_windows) return;
+    const uint32_t m = start_mask[w];
+    uint32_t idx = 0;
+    if (m) {
+        const uint32_t hb = 31u - (uint32_t)__clz((int)m);
+        const uint64_t pos = w * 32u + hb;
+        if (pos < n) {
+            // next start within TK_SHORT_MAX bytes?  (words beyond n_windows are zero-padded)
+            const uint32_t m1 = start_mask[w + 1], m2 = start_mask[w + 2];
+            uint64_t next;
+            if (m1) next = (w + 1) * 32u + (uint32_t)(__ffs((int)m1) - 1);
+            else if (m2) next = (w + 2) * 32u + (uint32_t)(__ffs((int)m2) - 1);
+            else next = ~0ull;
+            if (next == ~0ull || next - pos > TK_SHORT_MAX) {
+                idx = atomicAdd(n_long, 1u) + 1u;
+                TkkLongRec r;
+                r.start = pos; r.len = 0; r.count = 0; r.tok_base = 0;
+                recs[idx - 1] = r;
+            }
+        }
+    }
+    long_of_word[w] = idx;
+}
+
+// =====================================================================================================
+// K3: long pieces.  Warp per record: measure the piece, claim output space, then either merge it
+// in shared memory (<= TK_MED_MAX bytes) or queue it for the block-level kernel.
+// =====================================================================================================
+#define LM_WARPS 4
+
+__device__ __forceinline__ uint64_t piece_end(const uint32_t* __restrict__ start_mask, uint64_t pos) {
+    // position of the next set bit after pos (the sentinel at n guarantees there is one)
+    const uint32_t lane = threadIdx.x & 31u;
+    uint64_t w = pos >> 5;
+    uint32_t first = start_mask[w] & ~((2u << (pos & 31)) - 1u);
+    if ((pos & 31) == 31) first = 0;
+    if (first) return w * 32u + (uint32_t)(__ffs((int)first) - 1);
+    for (w += 1;; w += 32) {
+        const uint32_t m = start_mask[w + lane];
+        const uint32_t any = __ballot_sync(0xFFFFFFFFu, m != 0);
+        if (any) {
+            const int l = __ffs((int)any) - 1;
+            const uint32_t mm = __shfl_sync(0xFFFFFFFFu, m, l);
+            return (w + (uint64_t)l) * 32u + (uint32_t)(__ffs((int)mm) - 1);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(LM_WARPS * 32) longmerge_warp_kernel(const uint8_t* __restrict__ data,
+                                                                       const uint32_t* __restrict__ start_mask,
+                                                                       TkDeviceTables T, TkkLongRec* __restrict__ recs,
+                                                                       const uint32_t* __restrict__ n_long, uint32_t* __restrict__ pool,
+                                                                       unsigned long long* __restrict__ pool_cursor,
+                                                                       uint32_t* __restrict__ huge_list, uint32_t* __restrict__ n_huge,
+                                                                       uint32_t* __restrict__ work_counter) {
+    __shared__ TkWarpBpeSmem S[LM_WARPS];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t total = *n_long;
+    for (;;) {
+        uint32_t r = 0;
+        if (lane == 0) r = atomicAdd(work_counter, 1u);
+        r = __shfl_sync(0xFFFFFFFFu, r, 0);
+        if (r >= total) break;
+        const uint64_t pos = recs[r].start;
+        const uint64_t end = piece_end(start_mask, pos);
+        const uint64_t len = end - pos;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(pool_cursor, (unsigned long long)len);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        uint32_t count = 0;
+        if (len <= TK_MED_MAX) {
+            // whole-piece shortcut first (CoreBPE checks the encoder map before merging)
+            uint32_t whole = TK_INF;
+            if (len <= T.max_token_len) {
+                if (lane == 0) whole = tk_vocab_lookup(T, data + pos, (uint32_t)len);
+                whole = __shfl_sync(0xFFFFFFFFu, whole, 0);
+            }
+            if (whole != TK_INF) {
+                if (lane == 0) pool[base] = whole;
+                count = 1;
+            } else {
+                count = tk_bpe_warp(T, S[warp], data + pos, (uint32_t)len, pool + base);
+            }
+        } else if (lane == 0) {
+            huge_list[atomicAdd(n_huge, 1u)] = r;
+        }
+        if (lane == 0) {
+            recs[r].len = len;
+            recs[r].count = count;
+            recs[r].tok_base = base;
+        }
+        __syncwarp();
+    }
+}
+
+// Block per huge piece: the same sequential merge loop, parts in global scratch (L2 resident),
+// every thread caching the minimum of its slice.
+#define HG_T 512
+__global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __restrict__ data, TkDeviceTables T,
+                                                               TkkLongRec* __restrict__ recs, const uint32_t* __restrict__ huge_list,
+                                                               const uint32_t* __restrict__ n_huge, uint32_t* __restrict__ pool,
+                                                               uint32_t* __restrict__ scratch, unsigned long long scratch_cap,
+                                                               unsigned long long* __restrict__ scratch_cursor,
+                                                               uint32_t* __restrict__ work_counter, uint32_t* __restrict__ flags) {
+    __shared__ unsigned long long s_key[HG_T / 32];
+    __shared__ unsigned long long s_best;
+    __shared__ uint32_t s_rec;
+    __shared__ unsigned long long s_base;
+    __shared__ uint32_t s_count[HG_T / 32 + 1];
+    const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    const uint32_t total = *n_huge;
+    for (;;) {
+        __syncthreads();
+        if (t == 0) s_rec = atomicAdd(work_counter, 1u);
+        __syncthreads();
+        if (s_rec >= total) break;
+        const uint32_t r = huge_list[s_rec];
+        const uint64_t pos = recs[r].start;
+        const uint32_t n = (uint32_t)recs[r].len;   // pieces are < 4 GiB (checked by the host)
+        if (t == 0) {
+            s_base = atomicAdd(scratch_cursor, 3ull * n);
+        }
+        __syncthreads();
+        if (s_base + 3ull * n > scratch_cap) {
+            if (t == 0) atomicOr(flags, TKK_FLAG_SCRATCH_FULL);
+            continue;
+        }
+        uint32_t* id = pool + recs[r].tok_base;       // ids live where the final tokens go
+        if (n <= T.max_token_len) {                    // whole-piece shortcut (only with giant vocab entries)
+            __shared__ uint32_t s_whole;
+            if (t == 0) s_whole = tk_vocab_lookup(T, data + pos, n);
+            __syncthreads();
+            if (s_whole != TK_INF) {
+                if (t == 0) { id[0] = s_whole; recs[r].count = 1; }
+                continue;
+            }
+        }
+        uint32_t* rk = scratch + s_base;
+        uint32_t* nx = rk + n;
+        uint32_t* pv = nx + n;
+        for (uint32_t i = t; i < n; i += HG_T) { id[i] = data[pos + i]; nx[i] = i + 1; pv[i] = i - 1; }
+        __syncthreads();
+        for (uint32_t i = t; i < n; i += HG_T) rk[i] = (i + 1 < n) ? tk_pair_rank(T, id[i], id[i + 1]) : TK_INF;
+        __syncthreads();
+        const uint32_t k = (n + HG_T - 1) / HG_T;
+        const uint32_t lo = (uint64_t)t * k < n ? t * k : n, hi = (uint64_t)(t + 1) * k < n ? (t + 1) * k : n;
+        unsigned long long mine = ~0ull;
+        for (uint32_t i = lo; i < hi; ++i) {
+            const uint32_t v = rk[i];
+            if (v != TK_INF) { unsigned long long key = (unsigned long long)v << 32 | i; mine = key < mine ? key : mine; }
+        }
+        for (;;) {
+            // block-wide minimum of (rank, position)
+            unsigned long long m = mine;
+#pragma unroll
+            for (int d = 16; d; d >>= 1) {
+                unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, m, d);
+                m = o < m ? o : m;
+            }
+            if (lane == 0) s_key[warp] = m;
+            __syncthreads();
+            if (warp == 0) {
+                unsigned long long v = lane < HG_T / 32 ? s_key[lane] : ~0ull;
+#pragma unroll
+                for (int d = 16; d; d >>= 1) {
+                    unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, v, d);
+                    v = o < v ? o : v;
+                }
+                if (lane == 0) s_best = v;
+            }
+            __syncthreads();
+            const unsigned long long g = s_best;
+            if (g == ~0ull) break;
+            const uint32_t p0 = (uint32_t)g, rnk = (uint32_t)(g >> 32);
+            const uint32_t j = nx[p0], pp = pv[p0];
+            const uint32_t nn = nx[j];
+            __syncthreads();
+            if (t == 0) {
+                id[p0] = rnk; id[j] = TK_DEAD; rk[j] = TK_INF; nx[p0] = nn;
+                if (nn < n) pv[nn] = p0;
+                rk[p0] = nn < n ? tk_pair_rank(T, rnk, id[nn]) : TK_INF;
+            } else if (t == 32) {
+                if (pp != 0xFFFFFFFFu) rk[pp] = tk_pair_rank(T, id[pp], rnk);
+            }
+            __syncthreads();
+            const bool touched = (p0 >= lo && p0 < hi) || (j >= lo && j < hi) || (pp != 0xFFFFFFFFu && pp >= lo && pp < hi);
+            if (touched) {
+                mine = ~0ull;
+                for (uint32_t i = lo; i < hi; ++i) {
+                    const uint32_t v = rk[i];
+                    if (v != TK_INF) { unsigned long long key = (unsigned long long)v << 32 | i; mine = key < mine ? key : mine; }
+                }
+            }
+        }
+        // in-place compaction of the surviving ids, chunk by chunk (a chunk is read completely
+        // before anything is written at or below it)
+        uint32_t outn = 0;
+        for (uint32_t basei = 0; basei < n; basei += HG_T) {
+            const uint32_t i = basei + t;
+            const uint32_t v = i < n ? id[i] : TK_DEAD;
+            const uint32_t alive = __ballot_sync(0xFFFFFFFFu, v != TK_DEAD);
+            if (lane == 0) s_count[warp] = __popc(alive);
+            __syncthreads();
+            uint32_t before = 0, all = 0;
+            for (uint32_t w = 0; w < HG_T / 32; ++w) { if (w < warp) before += s_count[w]; all += s_count[w]; }
+            if (v != TK_DEAD) id[outn + before + __popc(alive & ((1u << lane) - 1u))] = v;
+            outn += all;
+            __syncthreads();
+        }
+        if (t == 0) recs[r].count = outn;
+    }
+}
+
+// =====================================================================================================
+// K2: encode tiles.  256 threads, one per 32-byte window of an 8 KiB tile.
+// =====================================================================================================
+#define EN_T 256
+#define EN_TILE (EN_T * 32)
+#define EN_LAST 0x80000000u
+
+struct EnSmem {
+    uint8_t bytes[EN_TILE + TK_SHORT_MAX + 16];
+    uint32_t stage[EN_TILE + TK_SHORT_MAX];
+    uint32_t mask[EN_T + 4];
+    uint32_t wsum[EN_T / 32];
+    unsigned long long base;
+    uint32_t tile;
+};
+
+// number of documents that start at byte position s, and the index of the first of them
+__device__ __forceinline__ uint64_t docs_at(const uint64_t* __restrict__ doc_off, uint64_t n_docs, uint64_t s, uint64_t* first) {
+    uint64_t lo = 0, hi = n_docs + 1;   // doc_off has n_docs+1 entries; the last one is the virtual end doc
+    while (lo < hi) {
+        uint64_t mid = (lo + hi) >> 1;
+        if (doc_off[mid] < s) lo = mid + 1; else hi = mid;
+    }
+    *first = lo;
+    uint64_t e = lo;
+    while (e <= n_docs && doc_off[e] == s) ++e;
+    return e - lo;
+}
+
+__global__ void __launch_bounds__(EN_T) encode_kernel(const uint8_t* __restrict__ data, uint64_t n,
+                                                      const uint32_t* __restrict__ start_mask, const uint32_t* __restrict__ ds_mask,
+                                                      const uint32_t* __restrict__ long_of_word, const TkkLongRec* __restrict__ recs,
+                                                      const uint32_t* __restrict__ pool, const uint64_t* __restrict__ doc_off,
+                                                      uint64_t n_docs, uint32_t add_bos, uint32_t add_eos, TkDeviceTables T,
+                                                      uint32_t* __restrict__ out, uint64_t out_cap, uint64_t* __restrict__ tok_off,
+                                                      unsigned long long* __restrict__ tile_state, uint32_t* __restrict__ ticket,
+                                                      unsigned long long* __restrict__ total_out, uint32_t* __restrict__ flags) {
+    extern __shared__ __align__(16) unsigned char en_raw[];
+    EnSmem& S = *reinterpret_cast<EnSmem*>(en_raw);
+    const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    if (t == 0) S.tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = S.tile;
+    const uint64_t tile_pos = (uint64_t)tile * EN_TILE;
+    // stage the tile's bytes (+ look-ahead) and mask words
+    {
+        const uint64_t avail = n > tile_pos ? n - tile_pos : 0;
+        const uint32_t want = EN_TILE + TK_SHORT_MAX + 16;
+        const uint32_t full16 = (uint32_t)((avail < want ? avail : want) / 16);
+        uint4* dst = reinterpret_cast<uint4*>(S.bytes);
+        const uint4* src = reinterpret_cast<const uint4*>(data + tile_pos);
+        for (uint32_t i = t; i < full16; i += EN_T) dst[i] = __ldg(src + i);
+        for (uint32_t i = full16 * 16 + t; i < want; i += EN_T) S.bytes[i] = (tile_pos + i < n) ? data[tile_pos + i] : 0;
+        S.mask[t] = start_mask[(uint64_t)tile * EN_T + t];
+        if (t < 4) S.mask[EN_T + t] = start_mask[(uint64_t)tile * EN_T + EN_T + t];
+    }
+    __syncthreads();
+
+    // ---- phase 1: tokens of every piece that starts in my window -> stage[], my token count ----
+    const uint32_t myds = ds_mask[(uint64_t)tile * EN_T + t];
+    uint32_t count = 0;
+    {
+        uint32_t m = S.mask[t];
+        while (m) {
+            const uint32_t bit = (uint32_t)(__ffs((int)m) - 1);
+            m &= m - 1;
+            const uint32_t s = t * 32u + bit;              // tile-relative start
+            const uint64_t gpos = tile_pos + s;
+            if ((myds >> bit) & 1u) {
+                uint64_t first;
+                const uint64_t k = docs_at(doc_off, n_docs, gpos, &first);
+                for (uint64_t d = first; d < first + k; ++d) count += (d > 0 ? add_eos : 0u) + (d < n_docs ? add_bos : 0u);
+            }
+            if (gpos >= n) continue;                       // the end sentinel is not a piece
+            // end of the piece: next set bit
+            uint32_t e;
+            if (m) e = t * 32u + (uint32_t)(__ffs((int)m) - 1);
+            else {
+                e = 0xFFFFFFFFu;
+#pragma unroll
+                for (int w = 1; w <= 3; ++w) {
+                    const uint32_t mm = S.mask[t + w];
+                    if (mm) { e = (t + w) * 32u + (uint32_t)(__ffs((int)mm) - 1); break; }
+                }
+            }
+            if (e == 0xFFFFFFFFu || e - s > TK_SHORT_MAX) {
+                const uint32_t li = long_of_word[(uint64_t)tile * EN_T + t];
+                count += recs[li - 1].count;
+                continue;
+            }
+            const uint32_t len = e - s;
+            const uint32_t whole = tk_vocab_lookup(T, S.bytes + s, len);
+            if (whole != TK_INF) {
+                S.stage[s] = whole | EN_LAST;
+                count += 1;
+            } else {
+                uint32_t tmp[TK_SHORT_MAX];
+                const uint32_t c = tk_bpe_thread(T, S.bytes + s, len, tmp);
+                for (uint32_t j = 0; j < c; ++j) S.stage[s + j] = tmp[j] | (j + 1 == c ? EN_LAST : 0u);
+                count += c;
+            }
+        }
+    }
+    // ---- block scan of the counts ----
+    uint32_t inc = count;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if (lane >= d) inc += o;
+    }
+    if (lane == 31) S.wsum[warp] = inc;
+    __syncthreads();
+    uint32_t before = 0, tile_total = 0;
+#pragma unroll
+    for (int w = 0; w < EN_T / 32; ++w) { if (w < (int)warp) before += S.wsum[w]; tile_total += S.wsum[w]; }
+    const uint32_t my_off = before + inc - count;
+    // ---- decoupled look-back over tiles: state = flag(2 bits) << 62 | value ----
+    if (t == 0) {
+        unsigned long long excl = 0;
+        if (tile > 0) {
+            atomicExch(tile_state + tile, (1ull << 62) | tile_total);
+            long long j = (long long)tile - 1;
+            for (;;) {
+                unsigned long long v = atomicAdd(tile_state + j, 0ull);
+                const unsigned long long f = v >> 62;
+                if (f == 0) continue;
+                excl += v & ((1ull << 62) - 1ull);
+                if (f == 2) break;
+                --j;
+            }
+        }
+        __threadfence();
+        atomicExch(tile_state + tile, (2ull << 62) | (excl + tile_total));
+        S.base = excl;
+        if (tile == gridDim.x - 1) *total_out = excl + tile_total;
+    }
+    __syncthreads();
+    // ---- phase 2: write ids (and document offsets) ----
+    uint64_t o = S.base + my_off;
+    const uint32_t nsp = T.num_special;
+    {
+        uint32_t m = S.mask[t];
+        while (m) {
+            const uint32_t bit = (uint32_t)(__ffs((int)m) - 1);
+            m &= m - 1;
+            const uint32_t s = t * 32u + bit;
+            const uint64_t gpos = tile_pos + s;
+            if ((myds >> bit) & 1u) {
+                uint64_t first;
+                const uint64_t k = docs_at(doc_off, n_docs, gpos, &first);
+                for (uint64_t d = first; d < first + k; ++d) {
+                    if (d > 0 && add_eos) { if (o < out_cap) out[o] = T.eos_id; ++o; }
+                    tok_off[d] = o;
+                    if (d < n_docs && add_bos) { if (o < out_cap) out[o] = T.bos_id; ++o; }
+                }
+            }
+            if (gpos >= n) continue;
+            uint32_t e;
+            if (m) e = t * 32u + (uint32_t)(__ffs((int)m) - 1);
+            else {
+                e = 0xFFFFFFFFu;
+#pragma unroll
+                for (int w = 1; w <= 3; ++w) {
+                    const uint32_t mm = S.mask[t + w];
+                    if (mm) { e = (t + w) * 32u + (uint32_t)(__ffs((int)mm) - 1); break; }
+                }
+            }
+            if (e == 0xFFFFFFFFu || e - s > TK_SHORT_MAX) {
+                const TkkLongRec r = recs[long_of_word[(uint64_t)tile * EN_T + t] - 1];
+                const uint32_t* src = pool + r.tok_base;
+                for (uint32_t j = 0; j < r.count; ++j) { if (o + j < out_cap) out[o + j] = src[j] + nsp; }
+                o += r.count;
+                continue;
+            }
+            for (uint32_t j = 0;; ++j) {
+                const uint32_t v = S.stage[s + j];
+                if (o < out_cap) out[o] = (v & ~EN_LAST) + nsp;
+                ++o;
+                if (v & EN_LAST) break;
+            }
+        }
+    }
+    if (tile == gridDim.x - 1 && t == 0 && S.base + tile_total > out_cap) atomicOr(flags, TKK_FLAG_OUT_FULL);
+}
+
+// =====================================================================================================
+// launch sequence
+// =====================================================================================================
+static inline uint64_t ceil_div(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+
+size_t encode_workspace_bytes(uint64_t n, uint64_t n_docs, EncodeLayout* L) {
+    EncodeLayout l{};
+    const uint64_t n_windows = n / 32 + 1;
+    const uint64_t n_tiles = ceil_div(n_windows, PT_T);
+    const uint64_t words = n_tiles * PT_T + 64;     // padded so tile kernels may read a little past the end
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    l.n_windows = n_windows; l.n_tiles = n_tiles; l.mask_words = words;
+    l.off_small = take(256);                            // counters + flags (zeroed every call)
+    l.off_ds = take(words * 4);
+    l.off_start = take(words * 4);
+    l.off_longword = take(words * 4);
+    l.off_summ = take(n_tiles * sizeof(TkkTileSummary));
+    l.off_carry = take(n_tiles * 4);
+    l.off_worklist = take(n_tiles * 4);
+    l.off_tilestate = take(n_tiles * 8);
+    l.max_long = n / (TK_SHORT_MAX + 1) + 2;
+    l.off_recs = take(l.max_long * sizeof(TkkLongRec));
+    l.off_huge = take(l.max_long * 4);
+    l.off_pool = take((n + 16) * 4);
+    (void)n_docs;
+    l.total = off;
+    if (L) *L = l;
+    return off;
+}
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
+
+cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const uint64_t* d_doc_off, uint64_t n_docs,
+                          uint64_t n, int add_bos, int add_eos, uint32_t* d_out, uint64_t out_cap, uint64_t* d_tok_off,
+                          void* d_ws, const EncodeLayout& L, uint32_t* d_scratch, uint64_t scratch_cap, int sm_count,
+                          cudaStream_t st, StageTimer* timer) {
+    unsigned char* ws = (unsigned char*)d_ws;
+    uint32_t* small = (uint32_t*)(ws + L.off_small);
+    uint32_t* ds = (uint32_t*)(ws + L.off_ds);
+    uint32_t* start = (uint32_t*)(ws + L.off_start);
+    uint32_t* longword = (uint32_t*)(ws + L.off_longword);
+    TkkTileSummary* summ = (TkkTileSummary*)(ws + L.off_summ);
+    uint32_t* carry = (uint32_t*)(ws + L.off_carry);
+    uint32_t* worklist = (uint32_t*)(ws + L.off_worklist);
+    unsigned long long* tilestate = (unsigned long long*)(ws + L.off_tilestate);
+    TkkLongRec* recs = (TkkLongRec*)(ws + L.off_recs);
+    uint32_t* huge = (uint32_t*)(ws + L.off_huge);
+    uint32_t* pool = (uint32_t*)(ws + L.off_pool);
+    // small block layout
+    uint32_t* flags = small + TKK_S_FLAGS;
+    unsigned long long* err_pos = (unsigned long long*)(small + TKK_S_ERRPOS);
+    uint32_t* work_count = small + TKK_S_WORKCOUNT;
+    uint32_t* n_long = small + TKK_S_NLONG;
+    uint32_t* n_huge = small + TKK_S_NHUGE;
+    uint32_t* wc_long = small + TKK_S_WC_LONG;
+    uint32_t* wc_huge = small + TKK_S_WC_HUGE;
+    uint32_t* ticket = small + TKK_S_TICKET;
+    unsigned long long* pool_cursor = (unsigned long long*)(small + TKK_S_POOLCUR);
+    unsigned long long* scratch_cursor = (unsigned long long*)(small + TKK_S_SCRCUR);
+    unsigned long long* total_out = (unsigned long long*)(small + TKK_S_TOTAL);
+
+    if (timer) timer->mark(st, "setup");
+    CK(cudaMemsetAsync(small, 0, 256, st));
+    CK(cudaMemsetAsync(err_pos, 0xFF, 8, st));
+    CK(cudaMemsetAsync(ds, 0, L.mask_words * 4, st));
+    CK(cudaMemsetAsync(start + L.n_windows, 0, (L.mask_words - L.n_windows) * 4, st));
+    CK(cudaMemsetAsync(tilestate, 0, L.n_tiles * 8, st));
+    docmark_kernel<<<(unsigned)ceil_div(n_docs + 1, 256), 256, 0, st>>>(d_doc_off, n_docs, n, ds, flags);
+    TK_LAUNCHED();
+    if (timer) timer->mark(st, "pretok");
+    pretok_kernel<<<(unsigned)L.n_tiles, PT_T, 0, st>>>(d_data, n, ds, start, L.n_windows, T, summ, err_pos);
+    TK_LAUNCHED();
+    if (timer) timer->mark(st, "pretok_carry");
+    pretok_scan_kernel<<<1, SC_T, 0, st>>>(summ, (uint32_t)L.n_tiles, carry, worklist, work_count, start);
+    TK_LAUNCHED();
+    pretok_fix_kernel<<<(unsigned)(L.n_tiles < (uint64_t)(2 * sm_count) ? L.n_tiles : (uint64_t)(2 * sm_count)), PT_T, 0, st>>>(
+        d_data, n, ds, start, L.n_windows, T, carry, worklist, work_count, err_pos);
+    TK_LAUNCHED();
+    if (timer) timer->mark(st, "longmark");
+    longmark_kernel<<<(unsigned)ceil_div(L.n_windows, 256), 256, 0, st>>>(start, L.n_windows, n, longword, recs, n_long);
+    TK_LAUNCHED();
+    if (timer) timer->mark(st, "longmerge");
+    {
+        uint64_t blocks = ceil_div(L.max_long, LM_WARPS);
+        const uint64_t cap = (uint64_t)sm_count * 12;
+        if (blocks > cap) blocks = cap;
+        longmerge_warp_kernel<<<(unsigned)blocks, LM_WARPS * 32, 0, st>>>(d_data, start, T, recs, n_long, pool, pool_cursor, huge,
+                                                                        n_huge, wc_long);
+        TK_LAUNCHED();
+        uint64_t hb = L.max_long < (uint64_t)(2 * sm_count) ? L.max_long : (uint64_t)(2 * sm_count);
+        longmerge_block_kernel<<<(unsigned)hb, HG_T, 0, st>>>(d_data, T, recs, huge, n_huge, pool, d_scratch, scratch_cap,
+                                                             scratch_cursor, wc_huge, flags);
+        TK_LAUNCHED();
+    }
+    if (timer) timer->mark(st, "encode");
+    {
+        static bool attr_set = false;
+        if (!attr_set) {
+            CK(cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EnSmem)));
+            attr_set = true;
+        }
+        encode_kernel<<<(unsigned)L.n_tiles, EN_T, sizeof(EnSmem), st>>>(d_data, n, start, ds, longword, recs, pool, d_doc_off,
+                                                                        n_docs, add_bos ? 1u : 0u, add_eos ? 1u : 0u, T, d_out,
+                                                                        out_cap, d_tok_off, tilestate, ticket, total_out, flags);
+        TK_LAUNCHED();
+    }
+    if (timer) timer->mark(st, "end");
+    return cudaGetLastError();
+}
+
+}  // namespace tkk

@@ -1,0 +1,86 @@
+// tk_kernels.h -- host-visible interface of the kernel launch sequences (tk_kernels.cu, tk_decode.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "tk_common.h"
+
+namespace tkk {
+
+// flags word
+enum : uint32_t {
+    TKK_FLAG_BAD_OFFSETS = 1u,    // doc_off / tok_off not monotone or not covering the data
+    TKK_FLAG_SCRATCH_FULL = 2u,   // huge-piece scratch exhausted (host grows it and retries)
+    TKK_FLAG_OUT_FULL = 4u,       // caller's output buffer too small
+};
+
+// layout of the 256-byte "small" block (uint32 indices)
+enum {
+    TKK_S_FLAGS = 0,
+    TKK_S_WORKCOUNT = 1,
+    TKK_S_NLONG = 2,
+    TKK_S_NHUGE = 3,
+    TKK_S_WC_LONG = 4,
+    TKK_S_WC_HUGE = 5,
+    TKK_S_TICKET = 6,
+    TKK_S_ERRPOS = 8,    // u64
+    TKK_S_POOLCUR = 10,  // u64
+    TKK_S_SCRCUR = 12,   // u64
+    TKK_S_TOTAL = 14,    // u64
+    TKK_S_BADDOC = 16,   // u64 (decode)
+};
+
+struct TkkTileSummary {
+    uint32_t packed;     // composite TkRunSummary of the tile
+    uint32_t assumed;    // entry state used in the first pass: n | abs<<2 | n_prov<<3 | r_prov<<4
+    long long pend_pos;  // byte position of an unresolved whitespace candidate, or -1
+};
+
+struct TkkLongRec {
+    uint64_t start;     // byte position of the piece
+    uint64_t len;       // bytes
+    uint64_t tok_base;  // index into the token pool
+    uint32_t count;     // ranks produced
+    uint32_t pad;
+};
+
+struct EncodeLayout {
+    uint64_t n_windows, n_tiles, mask_words, max_long;
+    size_t off_small, off_ds, off_start, off_longword, off_summ, off_carry, off_worklist, off_tilestate, off_recs,
+        off_huge, off_pool, total;
+};
+
+struct DecodeLayout {
+    uint64_t n_tiles, mask_words_tok, mask_words_out;
+    size_t off_small, off_tds, off_bmask, off_tilestate, off_docerr, total;
+};
+
+// optional per-stage CUDA-event timing
+struct StageTimer {
+    std::vector<std::string> names;
+    std::vector<cudaEvent_t> events;
+    void mark(cudaStream_t st, const char* name);
+    void collect(std::vector<std::string>& out_names, std::vector<float>& out_ms);
+    void reset();
+    ~StageTimer();
+};
+
+size_t encode_workspace_bytes(uint64_t n, uint64_t n_docs, EncodeLayout* L);
+cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const uint64_t* d_doc_off, uint64_t n_docs,
+                          uint64_t n, int add_bos, int add_eos, uint32_t* d_out, uint64_t out_cap, uint64_t* d_tok_off,
+                          void* d_ws, const EncodeLayout& L, uint32_t* d_scratch, uint64_t scratch_cap, int sm_count,
+                          cudaStream_t st, StageTimer* timer);
+
+size_t decode_workspace_bytes(uint64_t n_ids, uint64_t n_docs, uint64_t out_cap, DecodeLayout* L);
+cudaError_t decode_device(const TkDeviceTables& T, const uint32_t* d_ids, const uint64_t* d_tok_off, uint64_t n_docs,
+                          uint64_t n_ids, int policy, uint8_t* d_out, uint64_t out_cap, uint64_t* d_byte_off,
+                          int32_t* d_doc_status, void* d_ws, const DecodeLayout& L, cudaStream_t st);
+
+uint64_t launch_count();
+void count_launch();
+
+}  // namespace tkk
