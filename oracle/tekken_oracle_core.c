@@ -593,3 +593,60 @@ int orc_encode_count_mt(const orc_t *o, const uint8_t *data, const uint64_t *doc
     if (n_tok) *n_tok = sum;
     return rc;
 }
+
+/* Multi-threaded batch encode that returns the ids (parity checks at full config sizes): every
+   thread encodes a contiguous byte-balanced document range into its own buffer; the buffers are
+   then concatenated in document order. */
+typedef struct {
+    const orc_t *o; const uint8_t *data; const uint64_t *doc_off; uint64_t d0, d1;
+    int add_bos, add_eos, mode; uint32_t *buf; uint64_t *cnt; uint64_t n_tok; int rc; uint64_t bad;
+} ejob_t;
+
+static void *encode_worker(void *arg) {
+    ejob_t *j = (ejob_t *)arg;
+    uint64_t k = 0;
+    for (uint64_t d = j->d0; d < j->d1; d++) {
+        int64_t c = orc_encode(j->o, j->data + j->doc_off[d], j->doc_off[d + 1] - j->doc_off[d],
+                               j->add_bos, j->add_eos, j->buf + k, j->mode);
+        if (c < 0) { j->rc = (int)c; j->bad = d; break; }
+        j->cnt[d] = (uint64_t)c;
+        k += (uint64_t)c;
+    }
+    j->n_tok = k;
+    return 0;
+}
+
+int orc_encode_batch_mt(const orc_t *o, const uint8_t *data, const uint64_t *doc_off, uint64_t n_docs,
+                        int add_bos, int add_eos, uint32_t *out, uint64_t *tok_off, int mode,
+                        int n_threads, uint64_t *bad_doc) {
+    if (n_threads < 1) n_threads = 1;
+    ejob_t *jobs = (ejob_t *)calloc((size_t)n_threads, sizeof(ejob_t));
+    pthread_t *th = (pthread_t *)calloc((size_t)n_threads, sizeof(pthread_t));
+    uint64_t *cnt = (uint64_t *)calloc(n_docs + 1, sizeof(uint64_t));
+    uint64_t total = doc_off[n_docs] - doc_off[0], d = 0;
+    for (int t = 0; t < n_threads; t++) {
+        uint64_t target = doc_off[0] + total * (uint64_t)(t + 1) / (uint64_t)n_threads;
+        uint64_t d1 = d;
+        while (d1 < n_docs && (t == n_threads - 1 || doc_off[d1 + 1] <= target)) d1++;
+        jobs[t].o = o; jobs[t].data = data; jobs[t].doc_off = doc_off; jobs[t].d0 = d; jobs[t].d1 = d1;
+        jobs[t].add_bos = add_bos; jobs[t].add_eos = add_eos; jobs[t].mode = mode; jobs[t].cnt = cnt;
+        jobs[t].buf = (uint32_t *)malloc(((doc_off[d1] - doc_off[d]) + 2 * (d1 - d) + 1) * sizeof(uint32_t));
+        d = d1;
+        pthread_create(&th[t], 0, encode_worker, &jobs[t]);
+    }
+    int rc = 0;
+    uint64_t k = 0;
+    for (int t = 0; t < n_threads; t++) {
+        pthread_join(th[t], 0);
+        if (jobs[t].rc && !rc) { rc = jobs[t].rc; if (bad_doc) *bad_doc = jobs[t].bad; }
+        if (!rc) { memcpy(out + k, jobs[t].buf, jobs[t].n_tok * sizeof(uint32_t)); k += jobs[t].n_tok; }
+        free(jobs[t].buf);
+    }
+    if (!rc) {
+        uint64_t acc = 0;
+        for (uint64_t i = 0; i < n_docs; i++) { tok_off[i] = acc; acc += cnt[i]; }
+        tok_off[n_docs] = acc;
+    }
+    free(cnt); free(jobs); free(th);
+    return rc;
+}

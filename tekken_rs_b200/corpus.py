@@ -206,13 +206,13 @@ def single_long_document(n_bytes: int, seed: int = 7, max_ws_run: int = 1 << 14,
     base = english_like(min(n_bytes, 1 << 22), seed + 1)
     reps = -(-n_bytes // len(base))
     buf = bytearray((base * reps)[:n_bytes])
-    n_inj = max(4, n_bytes // (1 << 16))
+    n_inj = max(8, n_bytes >> 15)
     for k in range(n_inj):
-        kind = r.choice(["ws", "ws", "digit", "crlf", "contr", "cr"])
+        kind = r.choice(["ws", "ws", "ws", "digit", "crlf", "crlf", "contr", "contr", "cr", "cr", "ws", "contr"])
         centre = (r.randint(1, max(1, n_bytes // align - 1))) * align
         if kind == "digit":
             ln = int(2 ** r.uniform(0, np.log2(max_digit_run)))
-            ln = min(ln, n_bytes // 8)
+            ln = min(ln, n_bytes // 16)
             run = bytes(r.choice(b"0123456789") for _ in range(min(ln, 4096)))
             run = (run * (ln // len(run) + 1))[:ln]
         elif kind == "ws":

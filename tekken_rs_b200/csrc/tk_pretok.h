@@ -129,19 +129,18 @@ TK_HD TkWin tk_classify_window(const uint8_t* data, uint64_t n, uint64_t pos, co
         uint32_t lc = (uint32_t)(TK_FFS(~cont) - 1);  // number of leading continuation bytes (cont != ~0 -> <32)
         if (cont == 0xFFFFFFFFu) lc = 32;
         if (lc > 0) {
-            if (lc > 3) { bad |= 1u; }
-            else {
-                int back = 0;
-                int64_t q = (int64_t)pos - 1;
-                while (back < 3 && (tk_byte_at(data, n, q) & 0xC0u) == 0x80u && q >= 0) { --q; ++back; }
-                uint32_t cls = TK_CL_O;
-                int len = (q >= 0) ? tk_decode_at(data, n, q, T, &cls) : 0;
-                if (len == 0 || (uint64_t)(q + len) != pos + lc) bad |= 1u;
-                else {
-                    uint32_t m = (1u << lc) - 1u;
-                    covered |= m;
-                    if (cls == TK_CL_L) mL |= m; else if (cls == TK_CL_N) mN |= m; else if (cls == TK_CL_W) mW |= m;
-                }
+            int back = 0;
+            int64_t q = (int64_t)pos - 1;
+            while (back < 3 && q >= 0 && (tk_byte_at(data, n, q) & 0xC0u) == 0x80u) { --q; ++back; }
+            uint32_t cls = TK_CL_O;
+            const int len = (q >= 0) ? tk_decode_at(data, n, q, T, &cls) : 0;
+            // bytes of that char that fall into this window; leading continuation bytes beyond
+            // them stay uncovered and are flagged below
+            const int64_t over = len ? q + len - (int64_t)pos : 0;
+            if (over > 0) {
+                const uint32_t m = (1u << (over < (int64_t)lc ? (uint32_t)over : lc)) - 1u;
+                covered |= m;
+                if (cls == TK_CL_L) mL |= m; else if (cls == TK_CL_N) mN |= m; else if (cls == TK_CL_W) mW |= m;
             }
         }
         // chars whose lead byte is in this window
