@@ -186,6 +186,7 @@ static int finish_handle(tk_tokenizer* t, int device, tk_tokenizer** out) {
         if (err == cudaSuccess) err = upload(t, h.uni_stage2, (const void**)&T.uni_stage2);
         if (err == cudaSuccess) err = upload(t, h.vocab_slots, (const void**)&T.vocab_slots);
         if (err == cudaSuccess) err = upload(t, h.pair_slots, (const void**)&T.pair_slots);
+        if (err == cudaSuccess) err = upload(t, h.byte_pair, (const void**)&T.byte_pair);
         if (err == cudaSuccess) err = upload(t, h.vocab_bytes, (const void**)&T.vocab_bytes);
         if (err == cudaSuccess) err = upload(t, h.vocab_off, (const void**)&T.vocab_off);
         if (err == cudaSuccess) err = upload(t, h.special_bytes, (const void**)&T.special_bytes);

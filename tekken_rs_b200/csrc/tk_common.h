@@ -75,6 +75,7 @@ struct TkDeviceTables {
     uint32_t vocab_mask;           // capacity - 1
     const uint64_t* pair_slots;
     uint32_t pair_mask;
+    const uint32_t* byte_pair;     // [b0 << 8 | b1] -> rank of the two-byte token, TK_INF if none
     const uint8_t* vocab_bytes;    // concatenated token bytes, rank order
     const uint32_t* vocab_off;     // n_vocab + 1
     const uint8_t* special_bytes;  // concatenated special strings, positional order

@@ -96,26 +96,14 @@ __global__ void __launch_bounds__(DC_T) decode_gather_kernel(const uint32_t* __r
     uint32_t before = 0, tile_total = 0;
 #pragma unroll
     for (int w = 0; w < DC_T / 32; ++w) { if (w < (int)warp) before += wsum[w]; tile_total += wsum[w]; }
-    if (t == 0) {
-        unsigned long long excl = 0;
-        if (tile > 0) {
-            atomicExch(tile_state + tile, (1ull << 62) | tile_total);
-            long long j = (long long)tile - 1;
-            for (;;) {
-                unsigned long long v = atomicAdd(tile_state + j, 0ull);
-                const unsigned long long f = v >> 62;
-                if (f == 0) continue;
-                excl += v & ((1ull << 62) - 1ull);
-                if (f == 2) break;
-                --j;
+    if (warp == 0) {
+        const unsigned long long excl = tk_lookback(tile_state, tile, tile_total);
+        if (lane == 0) {
+            s_base = excl;
+            if (tile == gridDim.x - 1) {
+                *total_out = excl + tile_total;
+                if (excl + tile_total > out_cap) atomicOr(flags, TKK_FLAG_OUT_FULL);
             }
-        }
-        __threadfence();
-        atomicExch(tile_state + tile, (2ull << 62) | (excl + tile_total));
-        s_base = excl;
-        if (tile == gridDim.x - 1) {
-            *total_out = excl + tile_total;
-            if (excl + tile_total > out_cap) atomicOr(flags, TKK_FLAG_OUT_FULL);
         }
     }
     __syncthreads();
@@ -196,12 +184,26 @@ __global__ void __launch_bounds__(256) decode_validate_kernel(const uint8_t* __r
         const TkWin c = tk_classify_window(out, n, pos, w, bmask[wi], T);
         const uint32_t valid = (pos + 32 <= n) ? 0xFFFFFFFFu : (uint32_t)((1ull << (n - pos)) - 1ull);
         uint32_t bad = c.bad & valid;
-        // a boundary on a continuation byte breaks the run before it as well: flag the byte before
+        // a boundary on a continuation byte: the run after it is flagged above (it starts inside a
+        // char).  The run BEFORE it is invalid too iff its last char is cut short by the boundary.
         uint32_t split = c.ds & ~c.lead & valid;
         while (split) {
             const uint64_t q = pos + (uint32_t)(__ffs((int)split) - 1);
             split &= split - 1;
             if (q == 0) continue;
+            // lead byte of the char that contains byte q-1, without crossing an earlier boundary
+            uint64_t k = q - 1;
+            int back = 0;
+            bool crossed = false;
+            while (back < 3 && k > 0 && (out[k] & 0xC0u) == 0x80u) {
+                if ((bmask[k >> 5] >> (k & 31)) & 1u) { crossed = true; break; }
+                --k;
+                ++back;
+            }
+            if (crossed) continue;                                  // that run starts with a continuation byte: flagged already
+            const uint32_t b0 = out[k];
+            const uint32_t need = b0 < 0x80u ? 1u : b0 >= 0xF0u ? 4u : b0 >= 0xE0u ? 3u : b0 >= 0xC0u ? 2u : 0u;
+            if (need == 0u || k + need <= q) continue;              // complete (or stray bytes, flagged on their own)
             uint64_t lo = 0, hi = n_docs;
             while (lo < hi) {
                 uint64_t mid = (lo + hi) >> 1;

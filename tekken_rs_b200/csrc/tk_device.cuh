@@ -25,6 +25,77 @@ __device__ __forceinline__ uint32_t tk_pair_rank(const TkDeviceTables& T, uint32
     }
 }
 
+// Two independent pair lookups with their first probes in flight together (a merge creates two
+// new adjacent pairs; their ranks do not depend on each other).  l == TK_INF skips a lookup.
+__device__ __forceinline__ void tk_pair_rank2(const TkDeviceTables& T, uint32_t l0, uint32_t r0, uint32_t l1, uint32_t r1,
+                                              uint32_t* out0, uint32_t* out1) {
+    const bool h0 = l0 != TK_INF && r0 != TK_INF, h1 = l1 != TK_INF && r1 != TK_INF;
+    uint32_t i0 = tk_pair_hash(l0, r0) & T.pair_mask, i1 = tk_pair_hash(l1, r1) & T.pair_mask;
+    const uint64_t k0 = tk_pair_key(l0, r0), k1 = tk_pair_key(l1, r1);
+    uint64_t s0 = h0 ? tk_ldg64(T.pair_slots + i0) : 0ull;
+    uint64_t s1 = h1 ? tk_ldg64(T.pair_slots + i1) : 0ull;
+    const uint64_t km = (1ull << (2 * TK_ID_BITS)) - 1ull;
+    uint32_t a = TK_INF, b = TK_INF;
+    while (s0 != 0) {
+        if (((s0 >> TK_ID_BITS) & km) == k0) { a = (uint32_t)s0 & TK_ID_MASK; break; }
+        i0 = (i0 + 1) & T.pair_mask;
+        s0 = tk_ldg64(T.pair_slots + i0);
+    }
+    while (s1 != 0) {
+        if (((s1 >> TK_ID_BITS) & km) == k1) { b = (uint32_t)s1 & TK_ID_MASK; break; }
+        i1 = (i1 + 1) & T.pair_mask;
+        s1 = tk_ldg64(T.pair_slots + i1);
+    }
+    *out0 = a;
+    *out1 = b;
+}
+
+// ---- decoupled look-back over tiles (single-pass prefix sum) -------------------------------------
+// One 64-bit word per tile: flag << 62 | value; flag 0 = not ready, 1 = value is the tile's own
+// total, 2 = value is the inclusive prefix.  Called by all 32 lanes of ONE warp of the block;
+// publishes this tile's total, inspects 32 predecessors per step, publishes the inclusive prefix
+// and returns the exclusive prefix (same value on every lane).
+__device__ __forceinline__ unsigned long long tk_ld_relaxed_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void tk_st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long tk_lookback(unsigned long long* __restrict__ state, uint32_t tile,
+                                                          unsigned long long total) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const unsigned long long vmask = (1ull << 62) - 1ull;
+    if (tile == 0) {
+        if (lane == 0) tk_st_relaxed_u64(state, (2ull << 62) | total);
+        return 0ull;
+    }
+    if (lane == 0) tk_st_relaxed_u64(state + tile, (1ull << 62) | total);
+    unsigned long long excl = 0;
+    long long base = (long long)tile - 1;
+    for (;;) {
+        const long long j = base - (long long)lane;
+        const unsigned long long v = j >= 0 ? tk_ld_relaxed_u64(state + j) : (2ull << 62);
+        const uint32_t f = (uint32_t)(v >> 62);
+        const uint32_t m2 = __ballot_sync(0xFFFFFFFFu, f == 2u), m0 = __ballot_sync(0xFFFFFFFFu, f == 0u);
+        const uint32_t upto = m2 ? (0xFFFFFFFFu >> (32 - __ffs((int)m2))) : 0xFFFFFFFFu;   // lanes up to the first prefix
+        if (m0 & upto) {
+            __nanosleep(40);
+            continue;
+        }
+        unsigned long long c = ((upto >> lane) & 1u) ? (v & vmask) : 0ull;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, d);
+        excl += c;
+        if (m2) break;
+        base -= 32;
+    }
+    if (lane == 0) tk_st_relaxed_u64(state + tile, (2ull << 62) | (excl + total));
+    return excl;
+}
+
 // Whole-piece lookup (CoreBPE's `encoder.get(piece)` shortcut).  p may point to shared or global
 // memory; len >= 1.
 __device__ __forceinline__ uint32_t tk_vocab_lookup(const TkDeviceTables& T, const uint8_t* p, uint32_t len) {

@@ -621,6 +621,17 @@ HostModel HostModel::build(const std::vector<VocabEntry>& vocab, const std::vect
             m.pair_slots[i] = e;
         }
     }
+    // first-round pair ranks (both parts are single bytes): direct-indexed, no probing
+    {
+        m.byte_pair.assign(65536, TK_INF);
+        uint8_t two[2];
+        for (uint32_t a = 0; a < 256; ++a)
+            for (uint32_t b = 0; b < 256; ++b) {
+                two[0] = (uint8_t)a; two[1] = (uint8_t)b;
+                auto it = ranks.find(BytesKey{two, 2});
+                if (it != ranks.end()) m.byte_pair[(a << 8) | b] = (uint32_t)it->second;
+            }
+    }
     // special strings, positional (decode(Keep) indexes special_tokens[id], :538)
     m.special_off.assign(num_special + 1, 0);
     for (size_t i = 0; i < num_special; ++i)

@@ -62,6 +62,7 @@ struct HostModel {
     std::vector<uint8_t> uni_stage2;
     std::vector<TkVocabSlot> vocab_slots;
     std::vector<uint64_t> pair_slots;
+    std::vector<uint32_t> byte_pair;                          // 65536 entries, direct-indexed
     std::vector<uint8_t> special_bytes;
     std::vector<uint32_t> special_off;
     size_t n_pairs = 0;

@@ -517,17 +517,44 @@ __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __
 }
 
 // =====================================================================================================
-// K2: encode tiles.  256 threads, one per 32-byte window of an 8 KiB tile.
+// K2: encode tiles.  One block per EN_TILE bytes of text.
+//   A  stage the tile's bytes (+ look-ahead) and piece-start mask words in shared memory
+//   B  every piece that starts in the tile: whole-piece vocabulary lookup (CoreBPE's shortcut); misses go
+//      to a shared-memory work queue, longest first
+//   C  all threads drain the queue: exact byte_pair_merge per piece on compact id / rank arrays in
+//      shared memory.  A flattened state machine (fetch / init / merge step) keeps the lanes of a warp
+//      in the same loop while they work on different pieces; the two pair lookups a merge needs are
+//      issued together.
+//   D  tokens per window -> block scan -> decoupled look-back over tiles (one warp, 32 predecessors
+//      per step) -> this tile's position in the output
+//   E  ids (+num_special, BOS/EOS, per-document offsets) are compacted in shared memory and written
+//      to their final place with coalesced stores
 // =====================================================================================================
 #define EN_T 256
-#define EN_TILE (EN_T * 32)
+#define EN_WINS 128
+#define EN_TILE (EN_WINS * 32)
+#define EN_TPW (EN_T / EN_WINS)
 #define EN_LAST 0x80000000u
+#define EN_LONG 0xFFFFFFFFu
+#define EN_QCAP (EN_TILE / 2)
+#define EN_COMP_CAP (EN_TILE + TK_SHORT_MAX)
+#define EN_LONGCAP (EN_TILE / 64 + 2)
+#define EN_LPT_LEN 20
+
+struct EnLongCopy {
+    unsigned long long dst, src;
+    uint32_t count, pad;
+};
 
 struct EnSmem {
     uint8_t bytes[EN_TILE + TK_SHORT_MAX + 16];
-    uint32_t stage[EN_TILE + TK_SHORT_MAX];
-    uint32_t mask[EN_T + 4];
+    uint32_t stage[EN_TILE + TK_SHORT_MAX];   // ids of the parts of every piece, at the piece's byte offset
+    uint32_t rk[EN_TILE + TK_SHORT_MAX];      // pair ranks during C; token count of a piece at its start; compacted ids in E
+    uint32_t mask[EN_WINS + 4];
+    uint16_t queue[EN_QCAP];                  // tile-relative starts of the pieces that need merging
+    EnLongCopy longs[EN_LONGCAP];
     uint32_t wsum[EN_T / 32];
+    uint32_t q_front, q_back, q_pop, n_longs;
     unsigned long long base;
     uint32_t tile;
 };
@@ -545,22 +572,40 @@ __device__ __forceinline__ uint64_t docs_at(const uint64_t* __restrict__ doc_off
     return e - lo;
 }
 
-__global__ void __launch_bounds__(EN_T) encode_kernel(const uint8_t* __restrict__ data, uint64_t n,
-                                                      const uint32_t* __restrict__ start_mask, const uint32_t* __restrict__ ds_mask,
-                                                      const uint32_t* __restrict__ long_of_word, const TkkLongRec* __restrict__ recs,
-                                                      const uint32_t* __restrict__ pool, const uint64_t* __restrict__ doc_off,
-                                                      uint64_t n_docs, uint32_t add_bos, uint32_t add_eos, TkDeviceTables T,
-                                                      uint32_t* __restrict__ out, uint64_t out_cap, uint64_t* __restrict__ tok_off,
-                                                      unsigned long long* __restrict__ tile_state, uint32_t* __restrict__ ticket,
-                                                      unsigned long long* __restrict__ total_out, uint32_t* __restrict__ flags) {
+// tile-relative end of the piece that starts at tile-relative byte s (the next set bit of the start
+// mask), or 0xFFFFFFFF if it is more than three mask words away (a long piece)
+__device__ __forceinline__ uint32_t en_piece_end(const uint32_t* mask, uint32_t s) {
+    const uint32_t w = s >> 5, b = s & 31u;
+    const uint32_t m = b == 31u ? 0u : (mask[w] >> (b + 1u));
+    if (m) return s + (uint32_t)__ffs((int)m);
+#pragma unroll
+    for (int k = 1; k <= 3; ++k) {
+        const uint32_t mm = mask[w + k];
+        if (mm) return (w + k) * 32u + (uint32_t)(__ffs((int)mm) - 1);
+    }
+    return 0xFFFFFFFFu;
+}
+
+__global__ void __launch_bounds__(EN_T, 5) encode_kernel(const uint8_t* __restrict__ data, uint64_t n,
+                                                         const uint32_t* __restrict__ start_mask, const uint32_t* __restrict__ ds_mask,
+                                                         const uint32_t* __restrict__ long_of_word, const TkkLongRec* __restrict__ recs,
+                                                         const uint32_t* __restrict__ pool, const uint64_t* __restrict__ doc_off,
+                                                         uint64_t n_docs, uint32_t add_bos, uint32_t add_eos, TkDeviceTables T,
+                                                         uint32_t* __restrict__ out, uint64_t out_cap, uint64_t* __restrict__ tok_off,
+                                                         unsigned long long* __restrict__ tile_state, uint32_t* __restrict__ ticket,
+                                                         unsigned long long* __restrict__ total_out, uint32_t* __restrict__ flags) {
     extern __shared__ __align__(16) unsigned char en_raw[];
     EnSmem& S = *reinterpret_cast<EnSmem*>(en_raw);
     const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
-    if (t == 0) S.tile = atomicAdd(ticket, 1u);
+    if (t == 0) {
+        S.tile = atomicAdd(ticket, 1u);   // tiles are numbered in the order blocks start: look-back never waits on an unscheduled block
+        S.q_front = S.q_back = S.q_pop = S.n_longs = 0;
+    }
     __syncthreads();
     const uint32_t tile = S.tile;
     const uint64_t tile_pos = (uint64_t)tile * EN_TILE;
-    // stage the tile's bytes (+ look-ahead) and mask words
+    const uint64_t win0 = (uint64_t)tile * EN_WINS;
+    // ---- A: stage bytes and mask words ----
     {
         const uint64_t avail = n > tile_pos ? n - tile_pos : 0;
         const uint32_t want = EN_TILE + TK_SHORT_MAX + 16;
@@ -569,57 +614,108 @@ __global__ void __launch_bounds__(EN_T) encode_kernel(const uint8_t* __restrict_
         const uint4* src = reinterpret_cast<const uint4*>(data + tile_pos);
         for (uint32_t i = t; i < full16; i += EN_T) dst[i] = __ldg(src + i);
         for (uint32_t i = full16 * 16 + t; i < want; i += EN_T) S.bytes[i] = (tile_pos + i < n) ? data[tile_pos + i] : 0;
-        S.mask[t] = start_mask[(uint64_t)tile * EN_T + t];
-        if (t < 4) S.mask[EN_T + t] = start_mask[(uint64_t)tile * EN_T + EN_T + t];
+        if (t < EN_WINS + 4) S.mask[t] = start_mask[win0 + t];
     }
     __syncthreads();
 
-    // ---- phase 1: tokens of every piece that starts in my window -> stage[], my token count ----
-    const uint32_t myds = ds_mask[(uint64_t)tile * EN_T + t];
-    uint32_t count = 0;
+    // ---- B: whole-piece lookups; EN_TPW threads share a window, taking its pieces round-robin ----
     {
+        const uint32_t w = t / EN_TPW, sub = t % EN_TPW;
+        uint32_t m = S.mask[w], idx = 0;
+        while (m) {
+            const uint32_t bit = (uint32_t)(__ffs((int)m) - 1);
+            m &= m - 1;
+            if ((idx++ % EN_TPW) != sub) continue;
+            const uint32_t s = w * 32u + bit;
+            if (tile_pos + s >= n) continue;               // the end-of-data sentinel is not a piece
+            const uint32_t e = en_piece_end(S.mask, s);
+            if (e == 0xFFFFFFFFu || e - s > TK_SHORT_MAX) { S.stage[s] = EN_LONG; continue; }   // merged by K3
+            const uint32_t len = e - s;
+            const uint32_t whole = tk_vocab_lookup(T, S.bytes + s, len);
+            if (whole != TK_INF) { S.stage[s] = whole | EN_LAST; S.rk[s] = 1; }
+            else if (len == 1) { S.stage[s] = (uint32_t)S.bytes[s] | EN_LAST; S.rk[s] = 1; }
+            else if (len > EN_LPT_LEN) S.queue[atomicAdd(&S.q_front, 1u)] = (uint16_t)s;
+            else S.queue[EN_QCAP - 1u - atomicAdd(&S.q_back, 1u)] = (uint16_t)s;
+        }
+    }
+    __syncthreads();
+
+    // ---- C: drain the merge queue ----
+    {
+        const uint32_t qf = S.q_front, qn = qf + S.q_back;
+        uint32_t s = 0, len = 0, m = 0, i = 0;
+        int phase = 0;   // 0 fetch, 1 init, 2 merge
+        for (;;) {
+            if (phase == 0) {
+                const uint32_t k = atomicAdd(&S.q_pop, 1u);
+                if (k >= qn) break;
+                s = k < qf ? S.queue[k] : S.queue[EN_QCAP - 1u - (k - qf)];
+                len = en_piece_end(S.mask, s) - s;
+                i = 0;
+                phase = 1;
+            }
+            uint32_t* id = S.stage + s;
+            uint32_t* rk = S.rk + s;
+            if (phase == 1) {
+                // parts = single bytes; rank of every adjacent byte pair from the direct table
+                const uint8_t* b = S.bytes + s;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t j = i + k;
+                    if (j < len) {
+                        const uint32_t b0 = b[j];
+                        id[j] = b0;
+                        rk[j] = j + 1 < len ? __ldg(T.byte_pair + ((b0 << 8) | b[j + 1])) : TK_INF;
+                    }
+                }
+                i += 4;
+                if (i >= len) { m = len; phase = 2; }
+            } else {
+                // one step of byte_pair_merge: lowest rank, leftmost on ties
+                uint32_t best = TK_INF, bp = 0;
+                for (uint32_t j = 0; j + 1 < m; ++j) {
+                    const uint32_t r = rk[j];
+                    if (r < best) { best = r; bp = j; }
+                }
+                if (best == TK_INF) {
+                    id[m - 1] |= EN_LAST;
+                    rk[0] = m;
+                    phase = 0;
+                    continue;
+                }
+                for (uint32_t j = bp + 1; j + 1 < m; ++j) { id[j] = id[j + 1]; rk[j] = rk[j + 1]; }
+                m -= 1;
+                id[bp] = best;
+                const uint32_t lft = bp ? id[bp - 1] : TK_INF;
+                const uint32_t rgt = bp + 1 < m ? id[bp + 1] : TK_INF;
+                uint32_t r0, r1;
+                tk_pair_rank2(T, lft, best, best, rgt, &r0, &r1);
+                if (bp) rk[bp - 1] = r0;
+                rk[bp] = r1;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- D: token count of every window, block scan, look-back ----
+    const uint32_t myds = t < EN_WINS ? ds_mask[win0 + t] : 0u;
+    uint32_t count = 0;
+    if (t < EN_WINS) {
         uint32_t m = S.mask[t];
         while (m) {
             const uint32_t bit = (uint32_t)(__ffs((int)m) - 1);
             m &= m - 1;
-            const uint32_t s = t * 32u + bit;              // tile-relative start
+            const uint32_t s = t * 32u + bit;
             const uint64_t gpos = tile_pos + s;
             if ((myds >> bit) & 1u) {
                 uint64_t first;
                 const uint64_t k = docs_at(doc_off, n_docs, gpos, &first);
                 for (uint64_t d = first; d < first + k; ++d) count += (d > 0 ? add_eos : 0u) + (d < n_docs ? add_bos : 0u);
             }
-            if (gpos >= n) continue;                       // the end sentinel is not a piece
-            // end of the piece: next set bit
-            uint32_t e;
-            if (m) e = t * 32u + (uint32_t)(__ffs((int)m) - 1);
-            else {
-                e = 0xFFFFFFFFu;
-#pragma unroll
-                for (int w = 1; w <= 3; ++w) {
-                    const uint32_t mm = S.mask[t + w];
-                    if (mm) { e = (t + w) * 32u + (uint32_t)(__ffs((int)mm) - 1); break; }
-                }
-            }
-            if (e == 0xFFFFFFFFu || e - s > TK_SHORT_MAX) {
-                const uint32_t li = long_of_word[(uint64_t)tile * EN_T + t];
-                count += recs[li - 1].count;
-                continue;
-            }
-            const uint32_t len = e - s;
-            const uint32_t whole = tk_vocab_lookup(T, S.bytes + s, len);
-            if (whole != TK_INF) {
-                S.stage[s] = whole | EN_LAST;
-                count += 1;
-            } else {
-                uint32_t tmp[TK_SHORT_MAX];
-                const uint32_t c = tk_bpe_thread(T, S.bytes + s, len, tmp);
-                for (uint32_t j = 0; j < c; ++j) S.stage[s + j] = tmp[j] | (j + 1 == c ? EN_LAST : 0u);
-                count += c;
-            }
+            if (gpos >= n) continue;
+            count += S.stage[s] == EN_LONG ? recs[long_of_word[win0 + t] - 1].count : S.rk[s];
         }
     }
-    // ---- block scan of the counts ----
     uint32_t inc = count;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -632,31 +728,25 @@ __global__ void __launch_bounds__(EN_T) encode_kernel(const uint8_t* __restrict_
 #pragma unroll
     for (int w = 0; w < EN_T / 32; ++w) { if (w < (int)warp) before += S.wsum[w]; tile_total += S.wsum[w]; }
     const uint32_t my_off = before + inc - count;
-    // ---- decoupled look-back over tiles: state = flag(2 bits) << 62 | value ----
-    if (t == 0) {
-        unsigned long long excl = 0;
-        if (tile > 0) {
-            atomicExch(tile_state + tile, (1ull << 62) | tile_total);
-            long long j = (long long)tile - 1;
-            for (;;) {
-                unsigned long long v = atomicAdd(tile_state + j, 0ull);
-                const unsigned long long f = v >> 62;
-                if (f == 0) continue;
-                excl += v & ((1ull << 62) - 1ull);
-                if (f == 2) break;
-                --j;
+    if (warp == 0) {
+        const unsigned long long excl = tk_lookback(tile_state, tile, tile_total);
+        if (lane == 0) {
+            S.base = excl;
+            if (tile == gridDim.x - 1) {
+                *total_out = excl + tile_total;
+                if (excl + tile_total > out_cap) atomicOr(flags, TKK_FLAG_OUT_FULL);
             }
         }
-        __threadfence();
-        atomicExch(tile_state + tile, (2ull << 62) | (excl + tile_total));
-        S.base = excl;
-        if (tile == gridDim.x - 1) *total_out = excl + tile_total;
     }
-    __syncthreads();
-    // ---- phase 2: write ids (and document offsets) ----
-    uint64_t o = S.base + my_off;
+    __syncthreads();   // also: every thread is done reading the counts in S.rk
+
+    // ---- E: emit ----
+    const unsigned long long base = S.base;
+    const bool fits = tile_total <= EN_COMP_CAP;     // block-uniform
+    uint32_t* comp = S.rk;
     const uint32_t nsp = T.num_special;
-    {
+    if (t < EN_WINS) {
+        uint64_t o = my_off;
         uint32_t m = S.mask[t];
         while (m) {
             const uint32_t bit = (uint32_t)(__ffs((int)m) - 1);
@@ -667,38 +757,53 @@ __global__ void __launch_bounds__(EN_T) encode_kernel(const uint8_t* __restrict_
                 uint64_t first;
                 const uint64_t k = docs_at(doc_off, n_docs, gpos, &first);
                 for (uint64_t d = first; d < first + k; ++d) {
-                    if (d > 0 && add_eos) { if (o < out_cap) out[o] = T.eos_id; ++o; }
-                    tok_off[d] = o;
-                    if (d < n_docs && add_bos) { if (o < out_cap) out[o] = T.bos_id; ++o; }
+                    if (d > 0 && add_eos) {
+                        if (fits) comp[o] = T.eos_id; else if (base + o < out_cap) out[base + o] = T.eos_id;
+                        ++o;
+                    }
+                    tok_off[d] = base + o;
+                    if (d < n_docs && add_bos) {
+                        if (fits) comp[o] = T.bos_id; else if (base + o < out_cap) out[base + o] = T.bos_id;
+                        ++o;
+                    }
                 }
             }
             if (gpos >= n) continue;
-            uint32_t e;
-            if (m) e = t * 32u + (uint32_t)(__ffs((int)m) - 1);
-            else {
-                e = 0xFFFFFFFFu;
-#pragma unroll
-                for (int w = 1; w <= 3; ++w) {
-                    const uint32_t mm = S.mask[t + w];
-                    if (mm) { e = (t + w) * 32u + (uint32_t)(__ffs((int)mm) - 1); break; }
+            uint32_t v = S.stage[s];
+            if (v == EN_LONG) {
+                const TkkLongRec r = recs[long_of_word[win0 + t] - 1];
+                if (fits) {
+                    const uint32_t* src = pool + r.tok_base;
+                    for (uint32_t j = 0; j < r.count; ++j) comp[o + j] = src[j] + nsp;
+                } else {
+                    EnLongCopy c;
+                    c.dst = base + o; c.src = r.tok_base; c.count = r.count; c.pad = 0;
+                    S.longs[atomicAdd(&S.n_longs, 1u)] = c;
                 }
-            }
-            if (e == 0xFFFFFFFFu || e - s > TK_SHORT_MAX) {
-                const TkkLongRec r = recs[long_of_word[(uint64_t)tile * EN_T + t] - 1];
-                const uint32_t* src = pool + r.tok_base;
-                for (uint32_t j = 0; j < r.count; ++j) { if (o + j < out_cap) out[o + j] = src[j] + nsp; }
                 o += r.count;
                 continue;
             }
             for (uint32_t j = 0;; ++j) {
-                const uint32_t v = S.stage[s + j];
-                if (o < out_cap) out[o] = (v & ~EN_LAST) + nsp;
+                v = S.stage[s + j];
+                const uint32_t idv = (v & ~EN_LAST) + nsp;
+                if (fits) comp[o] = idv; else if (base + o < out_cap) out[base + o] = idv;
                 ++o;
                 if (v & EN_LAST) break;
             }
         }
     }
-    if (tile == gridDim.x - 1 && t == 0 && S.base + tile_total > out_cap) atomicOr(flags, TKK_FLAG_OUT_FULL);
+    __syncthreads();
+    if (fits) {
+        for (uint32_t i = t; i < tile_total; i += EN_T)
+            if (base + i < out_cap) out[base + i] = comp[i];
+    } else {
+        const uint32_t nl = S.n_longs;
+        for (uint32_t k = 0; k < nl; ++k) {
+            const EnLongCopy c = S.longs[k];
+            for (uint32_t i = t; i < c.count; i += EN_T)
+                if (c.dst + i < out_cap) out[c.dst + i] = pool[c.src + i] + nsp;
+        }
+    }
 }
 
 // =====================================================================================================
@@ -721,7 +826,8 @@ size_t encode_workspace_bytes(uint64_t n, uint64_t n_docs, EncodeLayout* L) {
     l.off_summ = take(n_tiles * sizeof(TkkTileSummary));
     l.off_carry = take(n_tiles * 4);
     l.off_worklist = take(n_tiles * 4);
-    l.off_tilestate = take(n_tiles * 8);
+    l.n_etiles = ceil_div(n_windows, EN_WINS);
+    l.off_tilestate = take(l.n_etiles * 8);
     l.max_long = n / (TK_SHORT_MAX + 1) + 2;
     l.off_recs = take(l.max_long * sizeof(TkkLongRec));
     l.off_huge = take(l.max_long * 4);
@@ -768,7 +874,7 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
     CK(cudaMemsetAsync(err_pos, 0xFF, 8, st));
     CK(cudaMemsetAsync(ds, 0, L.mask_words * 4, st));
     CK(cudaMemsetAsync(start + L.n_windows, 0, (L.mask_words - L.n_windows) * 4, st));
-    CK(cudaMemsetAsync(tilestate, 0, L.n_tiles * 8, st));
+    CK(cudaMemsetAsync(tilestate, 0, L.n_etiles * 8, st));
     docmark_kernel<<<(unsigned)ceil_div(n_docs + 1, 256), 256, 0, st>>>(d_doc_off, n_docs, n, ds, flags);
     TK_LAUNCHED();
     if (timer) timer->mark(st, "pretok");
@@ -798,12 +904,14 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
     }
     if (timer) timer->mark(st, "encode");
     {
-        static bool attr_set = false;
-        if (!attr_set) {
+        static std::atomic<uint64_t> attr_set{0};   // bit per device ordinal
+        int dev = 0;
+        CK(cudaGetDevice(&dev));
+        if (!((attr_set.load() >> (dev & 63)) & 1ull)) {
             CK(cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EnSmem)));
-            attr_set = true;
+            attr_set.fetch_or(1ull << (dev & 63));
         }
-        encode_kernel<<<(unsigned)L.n_tiles, EN_T, sizeof(EnSmem), st>>>(d_data, n, start, ds, longword, recs, pool, d_doc_off,
+        encode_kernel<<<(unsigned)L.n_etiles, EN_T, sizeof(EnSmem), st>>>(d_data, n, start, ds, longword, recs, pool, d_doc_off,
                                                                         n_docs, add_bos ? 1u : 0u, add_eos ? 1u : 0u, T, d_out,
                                                                         out_cap, d_tok_off, tilestate, ticket, total_out, flags);
         TK_LAUNCHED();

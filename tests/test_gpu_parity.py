@@ -1,0 +1,465 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle, the reference's golden vectors and
+the committed engine fixtures.  Token ids must be bit-exact, decoded text byte-exact.
+
+Every test here needs a B200 (`-m gpu`).  The gpu_tok fixture fails -- it never skips -- when the
+CUDA library or the device is missing, so these tests cannot pass on a fallback."""
+import base64
+import ctypes
+import random
+
+import numpy as np
+import pytest
+
+from tekken_rs_b200 import SpecialTokenPolicy, Tekkenizer, TokenizerError, corpus, kernel_launch_count, shard_plan, sharding
+
+pytestmark = pytest.mark.gpu
+
+
+def one_doc(raw):
+    a = np.frombuffer(raw, dtype=np.uint8) if isinstance(raw, (bytes, bytearray)) else raw
+    return a, np.array([0, len(a)], dtype=np.uint64)
+
+
+def assert_same_batch(gpu_tok, oracle, data, off, bos, eos, n_threads=8):
+    ids, toff = gpu_tok.encode_batch_np(data, off, bos, eos)
+    rid, roff = oracle.encode_batch_np(data, off, bos, eos, n_threads=n_threads)
+    if not np.array_equal(toff, roff):
+        d = int(np.nonzero(toff != roff)[0][0]) - 1
+        a, b = int(off[d]), int(off[d + 1])
+        raise AssertionError("doc %d differs: %r\n gpu    %s\n oracle %s" % (
+            d, bytes(data[a:b])[:120], ids[int(toff[d]):int(toff[d + 1])][:40].tolist(), rid[int(roff[d]):int(roff[d + 1])][:40].tolist()))
+    if not np.array_equal(ids, rid):
+        i = int(np.nonzero(ids != rid)[0][0])
+        d = int(np.searchsorted(roff, i, side="right") - 1)
+        a, b = int(off[d]), int(off[d + 1])
+        raise AssertionError("doc %d id %d differs: %r\n gpu    %s\n oracle %s" % (
+            d, i, bytes(data[a:b])[:120], ids[max(0, i - 8):i + 8].tolist(), rid[max(0, i - 8):i + 8].tolist()))
+    return ids, toff
+
+
+# ------------------------------------------------------------------------------------------ known answers
+
+def test_native_library_ran(gpu_tok):
+    before = kernel_launch_count()
+    assert gpu_tok.device() == 0
+    assert gpu_tok.encode("Hello, world!", False, False) == [22177, 1044, 4304, 1033]   # tests/test_tokenizer_output.rs:26
+    assert kernel_launch_count() > before          # our kernels, not a fallback
+
+
+def test_reference_golden_encode(gpu_tok, goldens):
+    # tests/test_tokenizer_output.rs:22-373
+    for e in goldens["encode"]:
+        assert gpu_tok.encode(e["text"], e["add_bos"], e["add_eos"]) == e["ids"], e["source"]
+        assert gpu_tok.decode(e["ids"], SpecialTokenPolicy.Ignore) == e["text"], e["source"]
+
+
+def test_reference_golden_decode(gpu_tok, goldens):
+    # tests/test_rust_tokenizer.rs:16-19,80 ; src/tekkenizer.rs:427
+    for d in goldens["decode"]:
+        assert gpu_tok.decode(d["ids"], d["policy"]) == d["text"], d["source"]
+
+
+def test_engine_fixture_cases(gpu_tok, fixtures):
+    for c in fixtures["cases"]:
+        assert gpu_tok.encode(c["text"], c["add_bos"], c["add_eos"]) == c["ids"], repr(c["text"])
+    texts = [c["text"] for c in fixtures["cases"]]
+    got = gpu_tok.encode_batch(texts, False, False)
+    for c, g in zip(fixtures["cases"], got):
+        want = c["ids"][1 if c["add_bos"] else 0:len(c["ids"]) - (1 if c["add_eos"] else 0)]
+        assert g == want, repr(c["text"])
+
+
+def test_engine_fixture_pieces(gpu_tok, fixtures):
+    # single pre-tokens isolating the merge loop: a piece made only of letters of one script, or an
+    # arbitrary byte string, is not always ONE pre-token, so compare through the oracle's split
+    for p in fixtures["pieces"]:
+        b = base64.b64decode(p["bytes_b64"])
+        try:
+            b.decode("utf-8")
+        except UnicodeDecodeError:
+            continue
+        ids = gpu_tok.encode(b, False, False)
+        if len(set(b)) > 0 and all(0x61 <= x <= 0x7A for x in b):     # pure lowercase = one piece
+            assert ids == [r + 1000 for r in p["ranks"]]
+
+
+def test_engine_fixture_corpora(gpu_tok, fixtures):
+    for c in fixtures["corpora"]:
+        if c["generator"] == "mixed_script_docs":
+            data, off = corpus.mixed_script_docs(**c["kwargs"])
+        else:
+            data, off = one_doc(getattr(corpus, c["generator"])(**c["kwargs"]))
+        ids, _ = gpu_tok.encode_batch_np(data, off, True, True)
+        assert len(ids) == c["n_ids"] and corpus.checksum64(ids) == c["ids_checksum"]
+        assert ids[:32].tolist() == c["ids_head"] and ids[-32:].tolist() == c["ids_tail"]
+
+
+def test_basic_tokenizer_example(gpu_tok):
+    # examples/basic_tokenizer_test.rs:7-18
+    ids = gpu_tok.encode("Hello, world! This is a test.", True, True)
+    assert ids == [1, 22177, 1044, 4304, 1033, 2409, 1395, 1261, 2688, 1046, 2]
+    assert gpu_tok.decode(ids, SpecialTokenPolicy.Keep) == "<s>Hello, world! This is a test.</s>"
+    assert gpu_tok.decode(ids, SpecialTokenPolicy.Ignore) == "Hello, world! This is a test."
+    assert gpu_tok.encode("", True, True) == [1, 2] and gpu_tok.encode("", False, False) == []
+    assert gpu_tok.encode("का", False, False) == [2622, 1658]      # the hard-coded pattern, not Mistral's
+
+
+# ------------------------------------------------------------------------------------------ differential fuzz
+
+def _fuzz_texts(n, seed, lengths):
+    from oracle.tools.make_golden_fixtures import FUZZ_ALPHABET
+    rng = random.Random(seed)
+    return ["".join(rng.choice(FUZZ_ALPHABET) for _ in range(rng.choice(lengths))).encode() for _ in range(n)]
+
+
+def _pack(texts):
+    off = np.zeros(len(texts) + 1, dtype=np.uint64)
+    np.cumsum([len(t) for t in texts], out=off[1:])
+    return np.frombuffer(b"".join(texts), dtype=np.uint8), off
+
+
+@pytest.mark.parametrize("bos,eos", [(False, False), (True, False), (False, True), (True, True)])
+def test_fuzz_batch(gpu_tok, oracle, bos, eos):
+    data, off = _pack(_fuzz_texts(30000, 5, [0, 1, 2, 3, 5, 8, 13, 30, 33, 64, 70, 100, 200]))
+    assert_same_batch(gpu_tok, oracle, data, off, bos, eos)
+
+
+def test_fuzz_as_one_document(gpu_tok, oracle):
+    # the same bytes as ONE text: document boundaries disappear, runs join across them
+    data, _ = _pack(_fuzz_texts(30000, 6, [1, 2, 3, 5, 8, 13, 30, 33, 64, 70, 100, 200]))
+    assert_same_batch(gpu_tok, oracle, data, np.array([0, len(data)], dtype=np.uint64), False, True)
+
+
+def test_fuzz_window_and_tile_edges(gpu_tok, oracle):
+    # every interesting construct slid across the 32-byte window and 8 KiB tile boundaries
+    cons = ["it's", "we'LL", "a'ſb", "  \n\n  x", "!!!\r\n\r\n", "12345678", " \t\n ", "中文字", "😀😀", " !x", "é́", "\r \n"]
+    docs = []
+    for c in cons:
+        cb = c.encode()
+        for edge in (32, 64, 8192, 16384):
+            for shift in range(-len(cb) - 1, 3):
+                pad = edge + shift
+                docs.append(b"ab " * (pad // 3) + b"x" * (pad % 3) + cb + b" tail")   # construct starts at byte `pad`
+    data, off = _pack(docs)
+    assert_same_batch(gpu_tok, oracle, data, off, True, True)
+    assert_same_batch(gpu_tok, oracle, data, np.array([0, len(data)], dtype=np.uint64), False, False)
+
+
+def test_ragged_and_empty_documents(gpu_tok, oracle):
+    texts = [b"", b"", b"a", b"", " ".encode(), b"", "日本".encode(), b"", b""]
+    data, off = _pack(texts)
+    for bos, eos in ((True, True), (False, False), (True, False)):
+        ids, toff = assert_same_batch(gpu_tok, oracle, data, off, bos, eos)
+    assert gpu_tok.encode_batch([], True, True) == []
+    assert gpu_tok.encode_batch(["", "", ""], True, True) == [[1, 2]] * 3
+    assert gpu_tok.encode_batch(["", ""], False, False) == [[], []]
+    ids, toff = gpu_tok.encode_batch_np(np.zeros(0, np.uint8), np.zeros(1, np.uint64), True, True)
+    assert len(ids) == 0 and toff.tolist() == [0]
+
+
+# ------------------------------------------------------------------------------------------ the five configs
+
+def test_config1_english_1mib(gpu_tok, oracle):
+    # BASELINE config 1: encode(text, true, true) then decode(Keep) (examples/basic_tokenizer_test.rs:7-18)
+    raw = corpus.english_like(1 << 20)
+    data, off = one_doc(raw)
+    ids, _ = assert_same_batch(gpu_tok, oracle, data, off, True, True)
+    assert gpu_tok.decode_bytes(ids, SpecialTokenPolicy.Keep) == b"<s>" + raw + b"</s>"
+    assert gpu_tok.decode_bytes(ids, SpecialTokenPolicy.Ignore) == raw
+
+
+def test_config2_mixed_script_docs(gpu_tok, oracle):
+    data, off = corpus.mixed_script_docs(100000, 42)
+    ids, toff = assert_same_batch(gpu_tok, oracle, data, off, True, True)
+    raw, boff = gpu_tok.decode_batch_np(ids, toff, SpecialTokenPolicy.Ignore)
+    assert np.array_equal(raw, data) and np.array_equal(boff, off)
+
+
+def test_config2_full_size_roundtrip_and_sample(gpu_tok, oracle):
+    # 1,000,000 documents: encode -> decode round trip over all of them, shard invariance, and the
+    # oracle on every 16th chunk of 16,384 documents
+    n_docs = 1_000_000
+    data, off = corpus.mixed_script_docs(n_docs, 42)
+    ids, toff = gpu_tok.encode_batch_np(data, off, True, True)
+    assert len(toff) == n_docs + 1 and int(toff[-1]) == len(ids)
+    raw, boff = gpu_tok.decode_batch_np(ids, toff, SpecialTokenPolicy.Ignore)
+    assert np.array_equal(boff, off) and np.array_equal(raw, data)
+    assert np.all(ids[toff[:-1].astype(np.int64)] == 1) and np.all(ids[toff[1:].astype(np.int64) - 1] == 2)
+    for c in range(0, n_docs >> 14, 16):
+        a, b = c << 14, min(n_docs, (c + 1) << 14)
+        rid, roff = oracle.encode_batch_np(data[int(off[a]):int(off[b])], off[a:b + 1] - off[a], True, True, n_threads=8)
+        assert np.array_equal(rid, ids[int(toff[a]):int(toff[b])])
+        assert np.array_equal(roff + toff[a], toff[a:b + 1])
+    # shard invariance (the multi-GPU path on one device): 8 byte-balanced shards, stitched
+    plan = shard_plan(off, 8)
+    parts, counts, offs = [], [], []
+    for s in range(8):
+        b, e = int(plan[s]), int(plan[s + 1])
+        loc_off = sharding.rebase_offsets(off, b, e)
+        sid, stoff = gpu_tok.encode_batch_np(data[int(off[b]):int(off[e])], loc_off, True, True)
+        parts.append(sid); counts.append(len(sid)); offs.append(stoff)
+    assert np.array_equal(np.concatenate(parts), ids)
+    stitched = np.concatenate([sharding.stitch_token_offsets(offs[s], counts, s)[:-1] for s in range(8)] + [toff[-1:]])
+    assert np.array_equal(stitched, toff)
+
+
+def test_config3_single_long_document(gpu_tok, oracle):
+    # cross-tile digit / whitespace / CR-LF runs; 64 MiB against the oracle
+    raw = corpus.single_long_document(1 << 26)
+    data, off = one_doc(raw)
+    ids, _ = assert_same_batch(gpu_tok, oracle, data, off, False, False, n_threads=1)
+    assert gpu_tok.decode_bytes(ids, SpecialTokenPolicy.Ignore) == raw
+
+
+def test_config3_full_size_1gib(gpu_tok, oracle):
+    raw = corpus.single_long_document(1 << 30)
+    data, off = one_doc(raw)
+    ids, toff = gpu_tok.encode_batch_np(data, off, True, True)
+    out, boff = gpu_tok.decode_batch_np(ids, toff, SpecialTokenPolicy.Ignore)
+    assert int(boff[-1]) == len(raw) and np.array_equal(out, data)
+    del out
+    # the oracle is linear on this text except inside the injected whitespace runs: check it all
+    rid, _ = oracle.encode_batch_np(data, off, True, True)
+    assert np.array_equal(rid, ids)
+
+
+def test_long_runs_across_many_tiles(gpu_tok, oracle):
+    # digit and whitespace runs spanning hundreds of 8 KiB tiles, with every alignment mod 3
+    for lead in (0, 1, 2, 31, 8191):
+        for run in (b"7" * 1_000_003, b" " * 300_001, b"\n" * 100_000, b" \t" * 70_001, b"\r\n" * 50_001, b" " * 99_999 + b"\n" + b" " * 99_999):
+            raw = b"a" * lead + run + b"z" + run[:4097] + b"!" + run[:9000]
+            data, off = one_doc(raw)
+            assert_same_batch(gpu_tok, oracle, data, off, False, False, n_threads=1)
+
+
+def test_config4_adversarial_long_pieces(gpu_tok, oracle):
+    for n_pieces, size in ((14, 1 << 9), (14, 1 << 12), (14, 1 << 14), (7, 1 << 16)):
+        data, off = one_doc(corpus.adversarial_pieces(n_pieces, size))
+        ids, _ = assert_same_batch(gpu_tok, oracle, data, off, False, False, n_threads=1)
+        assert gpu_tok.decode_bytes(ids) == data.tobytes()
+
+
+def test_config4_piece_length_sweep(gpu_tok, oracle):
+    # lengths around every escalation threshold (thread <= 64 B, warp <= 512 B, block beyond)
+    rng = random.Random(3)
+    docs = []
+    for L in list(range(1, 80)) + [127, 128, 129, 255, 256, 257, 500, 511, 512, 513, 514, 600, 1023, 1024, 1025, 3000, 5000]:
+        docs.append("".join(rng.choice("abcdefghijklmnopqrstuvwxyz") for _ in range(L)).encode())
+        docs.append(("é" * L).encode()[:L - (L % 2)] or b"e")
+        docs.append(("." * L).encode())
+        docs.append((" " * L).encode())
+        docs.append(("\n" * L).encode())
+    data, off = _pack(docs)
+    assert_same_batch(gpu_tok, oracle, data, off, False, False)
+    one = b" ".join(docs)
+    assert_same_batch(gpu_tok, oracle, *one_doc(one), False, False)
+
+
+# ------------------------------------------------------------------------------------------ decode
+
+def test_decode_policies_and_grouping(gpu_tok, oracle):
+    # tests/test_tekken.rs:53-86, tests/test_tokenizer_detailed.rs:140-180, 326-370
+    ids = gpu_tok.encode("Hello world", True, True)
+    assert gpu_tok.decode(ids, SpecialTokenPolicy.Keep) == "<s>Hello world</s>"
+    assert gpu_tok.decode(ids, SpecialTokenPolicy.Ignore) == "Hello world"
+    with pytest.raises(TokenizerError) as e:
+        gpu_tok.decode(ids, SpecialTokenPolicy.Raise)
+    assert e.value.kind == "SpecialTokenPolicy"
+    assert gpu_tok.decode(ids[1:-1], SpecialTokenPolicy.Raise) == "Hello world"
+    mixed = [1, 3] + gpu_tok.encode("ab cd", False, False) + [4, 4] + gpu_tok.encode("ef", False, False) + [2]
+    for pol in ("Keep", "Ignore"):
+        assert gpu_tok.decode_all(mixed, pol) == oracle.decode_all(mixed, pol)
+        assert gpu_tok.decode(mixed, pol) == oracle.decode(mixed, pol)
+    assert gpu_tok.decode_all(mixed, "Keep") == ["<s>", "[INST]", "ab cd", "[/INST]", "[/INST]", "ef", "</s>"]
+    assert gpu_tok.decode([], "Keep") == "" and gpu_tok.decode_all([], "Keep") == []     # :470-521
+    assert gpu_tok.decode([500], "Keep") == "<SPECIAL_500>"
+
+
+def test_decode_errors_match_oracle(gpu_tok, oracle):
+    from oracle import tekken_oracle as TO
+    e4 = 1000 + 0xE4
+    cases = [([131072], "Ignore"), ([200000], "Keep"), ([e4], "Ignore"), ([e4, 1, 1000 + 0xB8, 1000 + 0xAD], "Ignore"),
+             ([e4, 1000 + 0xB8, 1000 + 0xAD], "Ignore"), ([1000 + 0x80], "Keep"), ([22177, 1000 + 0xC3], "Keep"),
+             ([1, 22177], "Raise"), ([e4, 1], "Raise"), ([1, e4], "Raise"), ([1000 + 0xC3, 1000 + 0xA9], "Raise"),
+             ([1000 + 0xF0, 1000 + 0x9F, 1000 + 0x98, 1000 + 0x80], "Keep"), ([1000 + 0xF0, 1000 + 0x9F, 1000 + 0x98], "Keep"),
+             ([1000 + 0xED, 1000 + 0xA0, 1000 + 0x80], "Keep"), ([1000 + 0xC0, 1000 + 0x80], "Keep"), ([131071], "Keep")]
+    for ids, pol in cases:
+        try:
+            want = ("ok", oracle.decode_bytes(ids, pol))
+        except TO.TokenizerError as e:
+            want = ("err", e.kind)
+        try:
+            got = ("ok", gpu_tok.decode_bytes(ids, pol))
+        except TokenizerError as e:
+            got = ("err", e.kind)
+        assert got == want, (ids, pol)
+
+
+def test_decode_random_ids_match_oracle(gpu_tok, oracle):
+    from oracle import tekken_oracle as TO
+    rng = np.random.default_rng(12)
+    seqs = []
+    for _ in range(3000):
+        n = int(rng.integers(0, 40))
+        kind = rng.integers(0, 4)
+        if kind == 0:
+            s = rng.integers(1000, 131072, size=n)            # arbitrary ordinary ids: often invalid UTF-8 as a run
+        elif kind == 1:
+            s = rng.integers(0, 1300, size=n)                 # specials and raw bytes
+        elif kind == 2:
+            s = rng.integers(1256, 40000, size=n)
+        else:
+            s = rng.integers(130000, 132000, size=n)          # around the end of the vocabulary
+        seqs.append(s.astype(np.uint32))
+    for pol in ("Ignore", "Keep", "Raise"):
+        want = []
+        for s in seqs:
+            try:
+                want.append(("ok", oracle.decode_bytes(s, pol)))
+            except TO.TokenizerError as e:
+                want.append(("err", e.kind))
+        off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+        np.cumsum([len(s) for s in seqs], out=off[1:])
+        flat = np.concatenate(seqs)
+        first_bad = next((i for i, w in enumerate(want) if w[0] == "err"), None)
+        # batch call: Result<Vec<_>> semantics -- the error of the first failing sequence
+        try:
+            gpu_tok.decode_batch_np(flat, off, pol)
+            assert first_bad is None
+        except TokenizerError as e:
+            assert first_bad is not None and e.kind == want[first_bad][1]
+        # per-sequence
+        for s, w in list(zip(seqs, want))[:600]:
+            try:
+                got = ("ok", gpu_tok.decode_bytes(s, pol))
+            except TokenizerError as e:
+                got = ("err", e.kind)
+            assert got == w, (s.tolist(), pol)
+        # the valid ones as one batch
+        good = [s for s, w in zip(seqs, want) if w[0] == "ok"]
+        goff = np.zeros(len(good) + 1, dtype=np.uint64)
+        np.cumsum([len(s) for s in good], out=goff[1:])
+        raw, boff = gpu_tok.decode_batch_np(np.concatenate(good) if good else np.zeros(0, np.uint32), goff, pol)
+        b = raw.tobytes()
+        k = 0
+        for s, w in zip(seqs, want):
+            if w[0] == "ok":
+                assert b[int(boff[k]):int(boff[k + 1])] == w[1]
+                k += 1
+
+
+# ------------------------------------------------------------------------------------------ errors and custom vocabularies
+
+def test_invalid_utf8_is_rejected(gpu_tok):
+    for bad in (b"abc\xff", b"\x80", b"\xc3", b"ab\xe4\xb8", b"\xed\xa0\x80", b"\xf4\x90\x80\x80", b"\xc0\xaf", b"x" * 100 + b"\xe4\xb8" + b"y" * 100):
+        with pytest.raises(TokenizerError) as e:
+            gpu_tok.encode(bad, False, False)
+        assert e.value.kind == "InvalidUtf8", bad
+    # a character may not straddle a document boundary
+    data = np.frombuffer("日本".encode(), dtype=np.uint8)
+    with pytest.raises(TokenizerError) as e:
+        gpu_tok.encode_batch_np(data, np.array([0, 2, 6], dtype=np.uint64), False, False)
+    assert e.value.kind == "InvalidUtf8"
+    with pytest.raises(TokenizerError) as e:
+        gpu_tok.encode_batch_np(data, np.array([0, 7, 6], dtype=np.uint64), False, False)
+    assert e.value.kind == "InvalidArgument"
+
+
+def _mini_vocab():
+    # tests/test_small_vocab.rs:11-67
+    vocab = [{"rank": i, "token_bytes": base64.b64encode(bytes([i])).decode()} for i in range(256)]
+    vocab.append({"rank": 256, "token_bytes": base64.b64encode(b"hello").decode()})
+    vocab.append({"rank": 257, "token_bytes": base64.b64encode(b"world").decode()})
+    return vocab
+
+
+def test_small_vocab_whole_piece_shortcut():
+    # "hello" is reachable only through the whole-piece lookup (no merge path leads to it)
+    sp = [{"rank": i, "token_str": s, "is_control": True} for i, s in enumerate(["<unk>", "<s>", "</s>"])]
+    t = Tekkenizer.new(_mini_vocab(), sp, "ignored", 268, 10, "v7", device=0)
+    assert t.encode("hello", False, False) == [266]
+    assert t.encode("hello world", True, True) == [1, 266] + [10 + b for b in b" world"] + [2]
+    assert t.encode("helloworld", False, False) == [10 + b for b in b"helloworld"]
+    assert t.decode([266, 10 + 32, 267], "Keep") == "hello world"
+    with pytest.raises(TokenizerError) as e:
+        t.decode([268], "Keep")
+    assert e.value.kind == "Tokenizers"
+
+
+def test_missing_bos_eos_is_token_not_found():
+    # src/tekkenizer.rs:335-340 via :394-402
+    sp = [{"rank": 0, "token_str": "<unk>", "is_control": True}]
+    t = Tekkenizer.new(_mini_vocab(), sp, "", 268, 10, "v7", device=0)
+    assert t.encode("hi", False, False) == [10 + ord("h"), 10 + ord("i")]
+    for bos, eos in ((True, False), (False, True)):
+        with pytest.raises(TokenizerError) as e:
+            t.encode("hi", bos, eos)
+        assert e.value.kind == "TokenNotFound"
+
+
+def test_synthetic_vocab_non_monotone_ranks(oracle):
+    # merge order on a vocabulary whose ranks are shuffled (rank(merged) < rank(part) is common):
+    # the oracle's literal loop is the reference definition
+    from oracle import tekken_oracle as TO
+    rng = random.Random(8)
+    toks = set()
+    while len(toks) < 600:
+        toks.add(bytes(rng.choice(b"abcd") for _ in range(rng.randint(2, 5))))
+    toks = list(toks)
+    rng.shuffle(toks)
+    vocab = [{"rank": i, "token_bytes": base64.b64encode(bytes([i])).decode()} for i in range(256)]
+    vocab += [{"rank": 256 + i, "token_bytes": base64.b64encode(t).decode()} for i, t in enumerate(toks)]
+    sp = [{"rank": i, "token_str": s, "is_control": True} for i, s in enumerate(["<unk>", "<s>", "</s>"])]
+    n = len(vocab)
+    t = Tekkenizer.new(vocab, sp, "", n + 3, 3, "v3", device=0)
+    o = TO.OracleTekkenizer(vocab, sp, "", n + 3, 3, "v3")
+    docs = ["".join(rng.choice("abcd") for _ in range(rng.choice([3, 9, 40, 64, 65, 200, 600, 2000]))).encode() for _ in range(400)]
+    data, off = _pack(docs)
+    assert_same_batch(t, o, data, off, True, True)
+
+
+# ------------------------------------------------------------------------------------------ device-pointer ABI
+
+def test_device_pointer_entry_points(gpu_tok, oracle):
+    import torch
+    data, off = corpus.mixed_script_docs(4096, 7)
+    d_data = torch.from_numpy(data.copy()).cuda()
+    d_off = torch.from_numpy(off.astype(np.int64)).cuda()
+    cap = len(data) + 2 * 4096 + 2
+    d_tok = torch.empty(cap, dtype=torch.int32, device="cuda")
+    d_toff = torch.empty(4097, dtype=torch.int64, device="cuda")
+    n = gpu_tok.encode_batch_device(d_data.data_ptr(), d_off.data_ptr(), 4096, len(data), True, True, d_tok.data_ptr(), cap,
+                                    d_toff.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    rid, roff = oracle.encode_batch_np(data, off, True, True)
+    assert n == len(rid)
+    assert np.array_equal(d_tok[:n].cpu().numpy().view(np.uint32), rid)
+    assert np.array_equal(d_toff.cpu().numpy().view(np.uint64), roff)
+    # too small an output buffer is reported, with the size that would have been enough
+    with pytest.raises(TokenizerError) as e:
+        gpu_tok.encode_batch_device(d_data.data_ptr(), d_off.data_ptr(), 4096, len(data), True, True, d_tok.data_ptr(), 1000,
+                                    d_toff.data_ptr(), 0)
+    assert e.value.kind == "BufferTooSmall" and str(n) in e.value.msg
+    # decode on the device
+    d_out = torch.empty(len(data) + 64, dtype=torch.uint8, device="cuda")
+    d_boff = torch.empty(4097, dtype=torch.int64, device="cuda")
+    d_st = torch.empty(4096, dtype=torch.int32, device="cuda")
+    nb = gpu_tok.decode_batch_device(d_tok.data_ptr(), d_toff.data_ptr(), 4096, n, SpecialTokenPolicy.Ignore, d_out.data_ptr(),
+                                     len(data) + 64, d_boff.data_ptr(), d_st.data_ptr(), 0)
+    assert nb == len(data) and np.array_equal(d_out[:nb].cpu().numpy(), data)
+    assert np.array_equal(d_boff.cpu().numpy().view(np.uint64), off) and int(d_st.abs().sum()) == 0
+
+
+def test_concurrent_host_threads(gpu_tok, oracle):
+    # the handle is usable from many host threads at once (&self in the reference)
+    import threading
+    texts = ["thread %d says: %s" % (i, "héllo wörld 123 " * (i % 7 + 1)) for i in range(64)]
+    want = [oracle.encode(t, True, True) for t in texts]
+    got = [None] * len(texts)
+
+    def work(k):
+        for i in range(k, len(texts), 8):
+            got[i] = gpu_tok.encode(texts[i], True, True)
+    th = [threading.Thread(target=work, args=(k,)) for k in range(8)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert got == want
