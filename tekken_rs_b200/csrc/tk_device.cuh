@@ -130,6 +130,51 @@ __device__ __forceinline__ uint32_t tk_vocab_lookup(const TkDeviceTables& T, con
     }
 }
 
+// The same lookup for a piece held in a 4-byte aligned shared-memory array: bytes [s, s+len) of
+// `base`.  Reads aligned 32-bit words and funnel-shifts them into place (up to 11 bytes past the
+// piece are read; the caller's array has that slack).
+__device__ __forceinline__ uint32_t tk_vocab_lookup_w32(const TkDeviceTables& T, const uint8_t* base, uint32_t s, uint32_t len) {
+    if (len > T.max_token_len) return TK_INF;
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(base) + (s >> 2);
+    const uint32_t sh = (s & 3u) * 8u;
+    TkPieceHasher h;
+    h.init(len);
+    uint64_t key8 = 0;
+    uint32_t w0 = wp[0];
+    for (uint32_t i = 0, k = 0; i < len; i += 8, k += 2) {
+        const uint32_t w1 = wp[k + 1], w2 = wp[k + 2];
+        uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+        w0 = w2;
+        const uint32_t rem = len - i;
+        if (rem < 8u) {
+            if (rem <= 4u) { hi = 0u; if (rem < 4u) lo &= (1u << (8u * rem)) - 1u; }
+            else hi &= (1u << (8u * (rem - 4u))) - 1u;
+        }
+        const uint64_t w = (uint64_t)hi << 32 | lo;
+        if (i == 0) key8 = w;
+        h.add(w);
+    }
+    const uint64_t hv = h.finish();
+    const uint64_t key = len <= 8 ? key8 : hv;
+    uint32_t i = (uint32_t)hv & T.vocab_mask;
+    for (;;) {
+        const uint4 raw = __ldg((const uint4*)(T.vocab_slots + i));
+        const uint32_t slen = raw.w;
+        if (slen == 0) return TK_INF;
+        const uint64_t skey = (uint64_t)raw.y << 32 | raw.x;
+        if (slen == len && skey == key) {
+            if (len <= 8) return raw.z;
+            const uint8_t* v = T.vocab_bytes + T.vocab_off[raw.z];
+            const uint8_t* q = base + s;
+            bool same = true;
+            for (uint32_t j = 0; j < len; ++j)
+                if (__ldg(v + j) != q[j]) { same = false; break; }
+            if (same) return raw.z;
+        }
+        i = (i + 1) & T.vocab_mask;
+    }
+}
+
 // ---- one thread, one short piece ---------------------------------------------------------------
 // Sequential merge loop on a piece of at most TK_SHORT_MAX bytes held by one thread.  out[] gets
 // the ranks (no id offset); returns their count.

@@ -517,60 +517,39 @@ __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __
 }
 
 // =====================================================================================================
-// K2: encode tiles.  One block per EN_TILE bytes of text.
+// K2: merge tiles.  One block per MG_TILE bytes of text; no dependence between blocks.
 //   A  stage the tile's bytes (+ look-ahead) and piece-start mask words in shared memory
-//   B  every piece that starts in the tile: whole-piece vocabulary lookup (CoreBPE's shortcut); misses go
-//      to a shared-memory work queue, longest first
-//   C  all threads drain the queue: exact byte_pair_merge per piece on compact id / rank arrays in
-//      shared memory.  A flattened state machine (fetch / init / merge step) keeps the lanes of a warp
-//      in the same loop while they work on different pieces; the two pair lookups a merge needs are
-//      issued together.
-//   D  tokens per window -> block scan -> decoupled look-back over tiles (one warp, 32 predecessors
-//      per step) -> this tile's position in the output
-//   E  ids (+num_special, BOS/EOS, per-document offsets) are compacted in shared memory and written
-//      to their final place with coalesced stores
+//   B  every short piece that starts in the tile: whole-piece vocabulary lookup (CoreBPE's shortcut);
+//      misses go to a shared-memory work queue, longest first
+//   C  all threads drain the queue: exact byte_pair_merge per piece.  Parts stay at their byte offset
+//      (id + rank of the pair with the next live part, in shared memory); which offsets are live is a
+//      64-bit mask in registers, so neighbours come from bit operations and a merge moves nothing.
+//      A flattened state machine (fetch / init / merge step) keeps the lanes of a warp in one loop
+//      while they work on different pieces; the two pair lookups of a merge are issued together.
+//   D  the ranks of the tile (last-of-piece flag in bit 31) are compacted in shared memory and
+//      written with coalesced stores to the tile's slot of the rank stream; per window: offset into
+//      that slot and number of ranks.
+// K4 (emit) turns the stream into the final ids.
 // =====================================================================================================
-#define EN_T 256
-#define EN_WINS 128
-#define EN_TILE (EN_WINS * 32)
-#define EN_TPW (EN_T / EN_WINS)
+#define MG_T 128
+#define MG_WINS 64
+#define MG_TILE (MG_WINS * 32)
+#define MG_TPW (MG_T / MG_WINS)
+#define MG_CAP (MG_TILE + TK_SHORT_MAX)     // ranks a tile can produce (pieces that start in it)
+#define MG_QCAP (MG_TILE / 2)
+#define MG_LPT_LEN 20
 #define EN_LAST 0x80000000u
 #define EN_LONG 0xFFFFFFFFu
-#define EN_QCAP (EN_TILE / 2)
-#define EN_COMP_CAP (EN_TILE + TK_SHORT_MAX)
-#define EN_LONGCAP (EN_TILE / 64 + 2)
-#define EN_LPT_LEN 20
 
-struct EnLongCopy {
-    unsigned long long dst, src;
-    uint32_t count, pad;
+struct MgSmem {
+    uint8_t bytes[MG_TILE + TK_SHORT_MAX + 16];
+    uint32_t stage[MG_CAP];   // ids of the parts of every piece, at the piece's byte offset
+    uint32_t rk[MG_CAP];      // pair ranks during C; rank count of a piece at its start; compacted ranks in D
+    uint32_t mask[MG_WINS + 4];
+    uint16_t queue[MG_QCAP];  // tile-relative starts of the pieces that need merging
+    uint32_t wsum[MG_T / 32];
+    uint32_t q_front, q_back, q_pop;
 };
-
-struct EnSmem {
-    uint8_t bytes[EN_TILE + TK_SHORT_MAX + 16];
-    uint32_t stage[EN_TILE + TK_SHORT_MAX];   // ids of the parts of every piece, at the piece's byte offset
-    uint32_t rk[EN_TILE + TK_SHORT_MAX];      // pair ranks during C; token count of a piece at its start; compacted ids in E
-    uint32_t mask[EN_WINS + 4];
-    uint16_t queue[EN_QCAP];                  // tile-relative starts of the pieces that need merging
-    EnLongCopy longs[EN_LONGCAP];
-    uint32_t wsum[EN_T / 32];
-    uint32_t q_front, q_back, q_pop, n_longs;
-    unsigned long long base;
-    uint32_t tile;
-};
-
-// number of documents that start at byte position s, and the index of the first of them
-__device__ __forceinline__ uint64_t docs_at(const uint64_t* __restrict__ doc_off, uint64_t n_docs, uint64_t s, uint64_t* first) {
-    uint64_t lo = 0, hi = n_docs + 1;   // doc_off has n_docs+1 entries; the last one is the virtual end doc
-    while (lo < hi) {
-        uint64_t mid = (lo + hi) >> 1;
-        if (doc_off[mid] < s) lo = mid + 1; else hi = mid;
-    }
-    *first = lo;
-    uint64_t e = lo;
-    while (e <= n_docs && doc_off[e] == s) ++e;
-    return e - lo;
-}
 
 // tile-relative end of the piece that starts at tile-relative byte s (the next set bit of the start
 // mask), or 0xFFFFFFFF if it is more than three mask words away (a long piece)
@@ -586,56 +565,46 @@ __device__ __forceinline__ uint32_t en_piece_end(const uint32_t* mask, uint32_t 
     return 0xFFFFFFFFu;
 }
 
-__global__ void __launch_bounds__(EN_T, 5) encode_kernel(const uint8_t* __restrict__ data, uint64_t n,
-                                                         const uint32_t* __restrict__ start_mask, const uint32_t* __restrict__ ds_mask,
-                                                         const uint32_t* __restrict__ long_of_word, const TkkLongRec* __restrict__ recs,
-                                                         const uint32_t* __restrict__ pool, const uint64_t* __restrict__ doc_off,
-                                                         uint64_t n_docs, uint32_t add_bos, uint32_t add_eos, TkDeviceTables T,
-                                                         uint32_t* __restrict__ out, uint64_t out_cap, uint64_t* __restrict__ tok_off,
-                                                         unsigned long long* __restrict__ tile_state, uint32_t* __restrict__ ticket,
-                                                         unsigned long long* __restrict__ total_out, uint32_t* __restrict__ flags) {
-    extern __shared__ __align__(16) unsigned char en_raw[];
-    EnSmem& S = *reinterpret_cast<EnSmem*>(en_raw);
+__global__ void __launch_bounds__(MG_T) merge_kernel(const uint8_t* __restrict__ data, uint64_t n,
+                                                     const uint32_t* __restrict__ start_mask, TkDeviceTables T,
+                                                     uint32_t* __restrict__ stream, uint32_t* __restrict__ win_info) {
+    __shared__ __align__(16) MgSmem S;
     const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
-    if (t == 0) {
-        S.tile = atomicAdd(ticket, 1u);   // tiles are numbered in the order blocks start: look-back never waits on an unscheduled block
-        S.q_front = S.q_back = S.q_pop = S.n_longs = 0;
-    }
-    __syncthreads();
-    const uint32_t tile = S.tile;
-    const uint64_t tile_pos = (uint64_t)tile * EN_TILE;
-    const uint64_t win0 = (uint64_t)tile * EN_WINS;
-    // ---- A: stage bytes and mask words ----
+    const uint32_t tile = blockIdx.x;
+    const uint64_t tile_pos = (uint64_t)tile * MG_TILE;
+    const uint64_t win0 = (uint64_t)tile * MG_WINS;
+    if (t == 0) S.q_front = S.q_back = S.q_pop = 0;
+    // ---- A ----
     {
         const uint64_t avail = n > tile_pos ? n - tile_pos : 0;
-        const uint32_t want = EN_TILE + TK_SHORT_MAX + 16;
+        const uint32_t want = MG_TILE + TK_SHORT_MAX + 16;
         const uint32_t full16 = (uint32_t)((avail < want ? avail : want) / 16);
         uint4* dst = reinterpret_cast<uint4*>(S.bytes);
         const uint4* src = reinterpret_cast<const uint4*>(data + tile_pos);
-        for (uint32_t i = t; i < full16; i += EN_T) dst[i] = __ldg(src + i);
-        for (uint32_t i = full16 * 16 + t; i < want; i += EN_T) S.bytes[i] = (tile_pos + i < n) ? data[tile_pos + i] : 0;
-        if (t < EN_WINS + 4) S.mask[t] = start_mask[win0 + t];
+        for (uint32_t i = t; i < full16; i += MG_T) dst[i] = __ldg(src + i);
+        for (uint32_t i = full16 * 16 + t; i < want; i += MG_T) S.bytes[i] = (tile_pos + i < n) ? data[tile_pos + i] : 0;
+        if (t < MG_WINS + 4) S.mask[t] = start_mask[win0 + t];
     }
     __syncthreads();
 
-    // ---- B: whole-piece lookups; EN_TPW threads share a window, taking its pieces round-robin ----
+    // ---- B: whole-piece lookups; MG_TPW threads share a window, taking its pieces round-robin ----
     {
-        const uint32_t w = t / EN_TPW, sub = t % EN_TPW;
+        const uint32_t w = t / MG_TPW, sub = t % MG_TPW;
         uint32_t m = S.mask[w], idx = 0;
         while (m) {
             const uint32_t bit = (uint32_t)(__ffs((int)m) - 1);
             m &= m - 1;
-            if ((idx++ % EN_TPW) != sub) continue;
+            if ((idx++ % MG_TPW) != sub) continue;
             const uint32_t s = w * 32u + bit;
             if (tile_pos + s >= n) continue;               // the end-of-data sentinel is not a piece
             const uint32_t e = en_piece_end(S.mask, s);
             if (e == 0xFFFFFFFFu || e - s > TK_SHORT_MAX) { S.stage[s] = EN_LONG; continue; }   // merged by K3
             const uint32_t len = e - s;
-            const uint32_t whole = tk_vocab_lookup(T, S.bytes + s, len);
+            const uint32_t whole = tk_vocab_lookup_w32(T, S.bytes, s, len);
             if (whole != TK_INF) { S.stage[s] = whole | EN_LAST; S.rk[s] = 1; }
             else if (len == 1) { S.stage[s] = (uint32_t)S.bytes[s] | EN_LAST; S.rk[s] = 1; }
-            else if (len > EN_LPT_LEN) S.queue[atomicAdd(&S.q_front, 1u)] = (uint16_t)s;
-            else S.queue[EN_QCAP - 1u - atomicAdd(&S.q_back, 1u)] = (uint16_t)s;
+            else if (len > MG_LPT_LEN) S.queue[atomicAdd(&S.q_front, 1u)] = (uint16_t)s;
+            else S.queue[MG_QCAP - 1u - atomicAdd(&S.q_back, 1u)] = (uint16_t)s;
         }
     }
     __syncthreads();
@@ -643,13 +612,14 @@ __global__ void __launch_bounds__(EN_T, 5) encode_kernel(const uint8_t* __restri
     // ---- C: drain the merge queue ----
     {
         const uint32_t qf = S.q_front, qn = qf + S.q_back;
-        uint32_t s = 0, len = 0, m = 0, i = 0;
+        uint32_t s = 0, len = 0, i = 0;
+        unsigned long long live = 0;
         int phase = 0;   // 0 fetch, 1 init, 2 merge
         for (;;) {
             if (phase == 0) {
                 const uint32_t k = atomicAdd(&S.q_pop, 1u);
                 if (k >= qn) break;
-                s = k < qf ? S.queue[k] : S.queue[EN_QCAP - 1u - (k - qf)];
+                s = k < qf ? S.queue[k] : S.queue[MG_QCAP - 1u - (k - qf)];
                 len = en_piece_end(S.mask, s) - s;
                 i = 0;
                 phase = 1;
@@ -659,61 +629,185 @@ __global__ void __launch_bounds__(EN_T, 5) encode_kernel(const uint8_t* __restri
             if (phase == 1) {
                 // parts = single bytes; rank of every adjacent byte pair from the direct table
                 const uint8_t* b = S.bytes + s;
+                uint32_t r4[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const uint32_t j = i + k;
-                    if (j < len) {
-                        const uint32_t b0 = b[j];
-                        id[j] = b0;
-                        rk[j] = j + 1 < len ? __ldg(T.byte_pair + ((b0 << 8) | b[j + 1])) : TK_INF;
-                    }
+                    r4[k] = j + 1 < len ? __ldg(T.byte_pair + (((uint32_t)b[j] << 8) | b[j + 1])) : TK_INF;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t j = i + k;
+                    if (j < len) { id[j] = b[j]; rk[j] = r4[k]; }
                 }
                 i += 4;
-                if (i >= len) { m = len; phase = 2; }
+                if (i >= len) { live = len >= 64u ? ~0ull : ((1ull << len) - 1ull); phase = 2; }
             } else {
-                // one step of byte_pair_merge: lowest rank, leftmost on ties
+                // one step of byte_pair_merge: lowest rank, leftmost on ties.  Dead offsets hold TK_INF.
                 uint32_t best = TK_INF, bp = 0;
-                for (uint32_t j = 0; j + 1 < m; ++j) {
-                    const uint32_t r = rk[j];
-                    if (r < best) { best = r; bp = j; }
+                for (uint32_t j = 0; j < len; j += 4) {
+                    const uint32_t a0 = rk[j];
+                    const uint32_t a1 = j + 1 < len ? rk[j + 1] : TK_INF;
+                    const uint32_t a2 = j + 2 < len ? rk[j + 2] : TK_INF;
+                    const uint32_t a3 = j + 3 < len ? rk[j + 3] : TK_INF;
+                    if (a0 < best) { best = a0; bp = j; }
+                    if (a1 < best) { best = a1; bp = j + 1; }
+                    if (a2 < best) { best = a2; bp = j + 2; }
+                    if (a3 < best) { best = a3; bp = j + 3; }
                 }
                 if (best == TK_INF) {
-                    id[m - 1] |= EN_LAST;
-                    rk[0] = m;
+                    // done: compact the surviving ids to the front (dst <= src), flag the last one
+                    uint32_t c = 0;
+                    unsigned long long lv = live;
+                    while (lv) {
+                        const uint32_t j = (uint32_t)(__ffsll((long long)lv) - 1);
+                        lv &= lv - 1;
+                        const uint32_t v = id[j];
+                        id[c++] = lv ? v : (v | EN_LAST);
+                    }
+                    rk[0] = c;
                     phase = 0;
                     continue;
                 }
-                for (uint32_t j = bp + 1; j + 1 < m; ++j) { id[j] = id[j + 1]; rk[j] = rk[j + 1]; }
-                m -= 1;
+                // merge the part at bp with the next live part q
+                const unsigned long long above = live & ~((2ull << bp) - 1ull);           // live offsets > bp
+                const uint32_t q = (uint32_t)(__ffsll((long long)above) - 1);             // exists: rk[bp] != INF
+                const unsigned long long above_q = above & (above - 1);                    // live offsets > q
+                const unsigned long long below = live & ((1ull << bp) - 1ull);            // live offsets < bp
+                live &= ~(1ull << q);
+                const uint32_t nn = above_q ? (uint32_t)(__ffsll((long long)above_q) - 1) : 0xFFFFFFFFu;
+                const uint32_t pv = below ? (uint32_t)(63 - __clzll((long long)below)) : 0xFFFFFFFFu;
                 id[bp] = best;
-                const uint32_t lft = bp ? id[bp - 1] : TK_INF;
-                const uint32_t rgt = bp + 1 < m ? id[bp + 1] : TK_INF;
+                rk[q] = TK_INF;
+                const uint32_t lft = pv != 0xFFFFFFFFu ? id[pv] : TK_INF;
+                const uint32_t rgt = nn != 0xFFFFFFFFu ? id[nn] : TK_INF;
                 uint32_t r0, r1;
                 tk_pair_rank2(T, lft, best, best, rgt, &r0, &r1);
-                if (bp) rk[bp - 1] = r0;
+                if (pv != 0xFFFFFFFFu) rk[pv] = r0;
                 rk[bp] = r1;
             }
         }
     }
     __syncthreads();
 
-    // ---- D: token count of every window, block scan, look-back ----
-    const uint32_t myds = t < EN_WINS ? ds_mask[win0 + t] : 0u;
+    // ---- D: compact the tile's ranks and write them to its slot of the stream ----
     uint32_t count = 0;
-    if (t < EN_WINS) {
+    if (t < MG_WINS) {
         uint32_t m = S.mask[t];
         while (m) {
             const uint32_t bit = (uint32_t)(__ffs((int)m) - 1);
             m &= m - 1;
             const uint32_t s = t * 32u + bit;
-            const uint64_t gpos = tile_pos + s;
-            if ((myds >> bit) & 1u) {
-                uint64_t first;
-                const uint64_t k = docs_at(doc_off, n_docs, gpos, &first);
-                for (uint64_t d = first; d < first + k; ++d) count += (d > 0 ? add_eos : 0u) + (d < n_docs ? add_bos : 0u);
+            if (tile_pos + s >= n) continue;
+            if (S.stage[s] != EN_LONG) count += S.rk[s];
+        }
+    }
+    uint32_t inc = count;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if (lane >= d) inc += o;
+    }
+    if (lane == 31) S.wsum[warp] = inc;
+    __syncthreads();   // also: every thread is done reading the counts in S.rk
+    uint32_t before = 0, tile_total = 0;
+#pragma unroll
+    for (int w = 0; w < MG_T / 32; ++w) { if (w < (int)warp) before += S.wsum[w]; tile_total += S.wsum[w]; }
+    uint32_t* comp = S.rk;
+    if (t < MG_WINS) {
+        uint32_t o = before + inc - count;
+        win_info[win0 + t] = o | (count << 16);
+        uint32_t m = S.mask[t];
+        while (m) {
+            const uint32_t bit = (uint32_t)(__ffs((int)m) - 1);
+            m &= m - 1;
+            const uint32_t s = t * 32u + bit;
+            if (tile_pos + s >= n) continue;
+            uint32_t v = S.stage[s];
+            if (v == EN_LONG) continue;
+            for (uint32_t j = 0;; ++j) {
+                v = S.stage[s + j];
+                comp[o++] = v;
+                if (v & EN_LAST) break;
             }
-            if (gpos >= n) continue;
-            count += S.stage[s] == EN_LONG ? recs[long_of_word[win0 + t] - 1].count : S.rk[s];
+        }
+    }
+    __syncthreads();
+    uint32_t* dst = stream + (uint64_t)tile * MG_CAP;
+    for (uint32_t i = t; i < tile_total; i += MG_T) dst[i] = comp[i];
+}
+
+// =====================================================================================================
+// K4: emit.  One block per 8 KiB of text (256 windows): tokens per window (ranks from the stream,
+// long pieces from K3's records, BOS/EOS at document starts) -> block scan -> decoupled look-back
+// over tiles (one warp, 32 predecessors per step) -> ids (+num_special) compacted in shared memory
+// and written to their final place with coalesced stores; per-document token offsets.
+// =====================================================================================================
+#define EM_T 256
+#define EM_WINS 256
+#define EM_TILE (EM_WINS * 32)
+#define EM_CAP (EM_TILE + 512)
+#define EM_LONGCAP (EM_TILE / 64 + 2)
+
+struct EnLongCopy {
+    unsigned long long dst, src;
+    uint32_t count, pad;
+};
+
+struct EmSmem {
+    uint32_t comp[EM_CAP];
+    EnLongCopy longs[EM_LONGCAP];
+    uint32_t wsum[EM_T / 32];
+    uint32_t n_longs, tile;
+    unsigned long long base;
+};
+
+// number of documents that start at byte position s, and the index of the first of them
+__device__ __forceinline__ uint64_t docs_at(const uint64_t* __restrict__ doc_off, uint64_t n_docs, uint64_t s, uint64_t* first) {
+    uint64_t lo = 0, hi = n_docs + 1;   // doc_off has n_docs+1 entries; the last one is the virtual end doc
+    while (lo < hi) {
+        uint64_t mid = (lo + hi) >> 1;
+        if (doc_off[mid] < s) lo = mid + 1; else hi = mid;
+    }
+    *first = lo;
+    uint64_t e = lo;
+    while (e <= n_docs && doc_off[e] == s) ++e;
+    return e - lo;
+}
+
+__global__ void __launch_bounds__(EM_T) emit_kernel(uint64_t n, const uint32_t* __restrict__ start_mask,
+                                                    const uint32_t* __restrict__ ds_mask, const uint32_t* __restrict__ long_of_word,
+                                                    const TkkLongRec* __restrict__ recs, const uint32_t* __restrict__ pool,
+                                                    const uint32_t* __restrict__ stream, const uint32_t* __restrict__ win_info,
+                                                    const uint64_t* __restrict__ doc_off, uint64_t n_docs, uint32_t add_bos,
+                                                    uint32_t add_eos, uint32_t nsp, uint32_t bos_id, uint32_t eos_id,
+                                                    uint32_t* __restrict__ out, uint64_t out_cap, uint64_t* __restrict__ tok_off,
+                                                    unsigned long long* __restrict__ tile_state, uint32_t* __restrict__ ticket,
+                                                    unsigned long long* __restrict__ total_out, uint32_t* __restrict__ flags) {
+    __shared__ __align__(16) EmSmem S;
+    const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    if (t == 0) {
+        S.tile = atomicAdd(ticket, 1u);   // tiles are numbered in the order blocks start: look-back never waits on an unscheduled block
+        S.n_longs = 0;
+    }
+    __syncthreads();
+    const uint32_t tile = S.tile;
+    const uint64_t gw = (uint64_t)tile * EM_WINS + t;       // my window
+    const uint64_t wpos = gw * 32u;
+    const uint32_t mymask = start_mask[gw], myds = ds_mask[gw], info = win_info[gw];
+    const uint32_t lw = mymask ? long_of_word[gw] : 0u;     // != 0: a long piece starts at my top set bit
+    const uint32_t topbit = mymask ? 31u - (uint32_t)__clz((int)mymask) : 32u;
+    // ---- tokens of my window ----
+    uint32_t count = info >> 16;
+    if (lw) count += recs[lw - 1].count;
+    {
+        uint32_t m = mymask & myds;
+        while (m) {
+            const uint32_t bit = (uint32_t)(__ffs((int)m) - 1);
+            m &= m - 1;
+            uint64_t first;
+            const uint64_t k = docs_at(doc_off, n_docs, wpos + bit, &first);
+            for (uint64_t d = first; d < first + k; ++d) count += (d > 0 ? add_eos : 0u) + (d < n_docs ? add_bos : 0u);
         }
     }
     uint32_t inc = count;
@@ -726,7 +820,7 @@ __global__ void __launch_bounds__(EN_T, 5) encode_kernel(const uint8_t* __restri
     __syncthreads();
     uint32_t before = 0, tile_total = 0;
 #pragma unroll
-    for (int w = 0; w < EN_T / 32; ++w) { if (w < (int)warp) before += S.wsum[w]; tile_total += S.wsum[w]; }
+    for (int w = 0; w < EM_T / 32; ++w) { if (w < (int)warp) before += S.wsum[w]; tile_total += S.wsum[w]; }
     const uint32_t my_off = before + inc - count;
     if (warp == 0) {
         const unsigned long long excl = tk_lookback(tile_state, tile, tile_total);
@@ -738,43 +832,40 @@ __global__ void __launch_bounds__(EN_T, 5) encode_kernel(const uint8_t* __restri
             }
         }
     }
-    __syncthreads();   // also: every thread is done reading the counts in S.rk
-
-    // ---- E: emit ----
+    __syncthreads();
+    // ---- emit ----
     const unsigned long long base = S.base;
-    const bool fits = tile_total <= EN_COMP_CAP;     // block-uniform
-    uint32_t* comp = S.rk;
-    const uint32_t nsp = T.num_special;
-    if (t < EN_WINS) {
+    const bool fits = tile_total <= EM_CAP;     // block-uniform
+    uint32_t* comp = S.comp;
+    {
         uint64_t o = my_off;
-        uint32_t m = S.mask[t];
+        const uint32_t* src = stream + (gw / MG_WINS) * (uint64_t)MG_CAP + (info & 0xFFFFu);
+        uint32_t m = mymask;
         while (m) {
             const uint32_t bit = (uint32_t)(__ffs((int)m) - 1);
             m &= m - 1;
-            const uint32_t s = t * 32u + bit;
-            const uint64_t gpos = tile_pos + s;
+            const uint64_t gpos = wpos + bit;
             if ((myds >> bit) & 1u) {
                 uint64_t first;
                 const uint64_t k = docs_at(doc_off, n_docs, gpos, &first);
                 for (uint64_t d = first; d < first + k; ++d) {
                     if (d > 0 && add_eos) {
-                        if (fits) comp[o] = T.eos_id; else if (base + o < out_cap) out[base + o] = T.eos_id;
+                        if (fits) comp[o] = eos_id; else if (base + o < out_cap) out[base + o] = eos_id;
                         ++o;
                     }
                     tok_off[d] = base + o;
                     if (d < n_docs && add_bos) {
-                        if (fits) comp[o] = T.bos_id; else if (base + o < out_cap) out[base + o] = T.bos_id;
+                        if (fits) comp[o] = bos_id; else if (base + o < out_cap) out[base + o] = bos_id;
                         ++o;
                     }
                 }
             }
-            if (gpos >= n) continue;
-            uint32_t v = S.stage[s];
-            if (v == EN_LONG) {
-                const TkkLongRec r = recs[long_of_word[win0 + t] - 1];
+            if (gpos >= n) continue;                        // the end-of-data sentinel is not a piece
+            if (lw && bit == topbit) {
+                const TkkLongRec r = recs[lw - 1];
                 if (fits) {
-                    const uint32_t* src = pool + r.tok_base;
-                    for (uint32_t j = 0; j < r.count; ++j) comp[o + j] = src[j] + nsp;
+                    const uint32_t* ps = pool + r.tok_base;
+                    for (uint32_t j = 0; j < r.count; ++j) comp[o + j] = ps[j] + nsp;
                 } else {
                     EnLongCopy c;
                     c.dst = base + o; c.src = r.tok_base; c.count = r.count; c.pad = 0;
@@ -783,8 +874,8 @@ __global__ void __launch_bounds__(EN_T, 5) encode_kernel(const uint8_t* __restri
                 o += r.count;
                 continue;
             }
-            for (uint32_t j = 0;; ++j) {
-                v = S.stage[s + j];
+            for (;;) {
+                const uint32_t v = __ldg(src++);
                 const uint32_t idv = (v & ~EN_LAST) + nsp;
                 if (fits) comp[o] = idv; else if (base + o < out_cap) out[base + o] = idv;
                 ++o;
@@ -794,13 +885,13 @@ __global__ void __launch_bounds__(EN_T, 5) encode_kernel(const uint8_t* __restri
     }
     __syncthreads();
     if (fits) {
-        for (uint32_t i = t; i < tile_total; i += EN_T)
+        for (uint32_t i = t; i < tile_total; i += EM_T)
             if (base + i < out_cap) out[base + i] = comp[i];
     } else {
         const uint32_t nl = S.n_longs;
         for (uint32_t k = 0; k < nl; ++k) {
             const EnLongCopy c = S.longs[k];
-            for (uint32_t i = t; i < c.count; i += EN_T)
+            for (uint32_t i = t; i < c.count; i += EM_T)
                 if (c.dst + i < out_cap) out[c.dst + i] = pool[c.src + i] + nsp;
         }
     }
@@ -826,8 +917,10 @@ size_t encode_workspace_bytes(uint64_t n, uint64_t n_docs, EncodeLayout* L) {
     l.off_summ = take(n_tiles * sizeof(TkkTileSummary));
     l.off_carry = take(n_tiles * 4);
     l.off_worklist = take(n_tiles * 4);
-    l.n_etiles = ceil_div(n_windows, EN_WINS);
-    l.off_tilestate = take(l.n_etiles * 8);
+    l.n_mtiles = n_tiles * (PT_T / MG_WINS);           // merge tiles cover exactly the emit tiles
+    l.off_tilestate = take(n_tiles * 8);
+    l.off_wininfo = take(words * 4);
+    l.off_stream = take(l.n_mtiles * (size_t)MG_CAP * 4);
     l.max_long = n / (TK_SHORT_MAX + 1) + 2;
     l.off_recs = take(l.max_long * sizeof(TkkLongRec));
     l.off_huge = take(l.max_long * 4);
@@ -856,6 +949,8 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
     TkkLongRec* recs = (TkkLongRec*)(ws + L.off_recs);
     uint32_t* huge = (uint32_t*)(ws + L.off_huge);
     uint32_t* pool = (uint32_t*)(ws + L.off_pool);
+    uint32_t* win_info = (uint32_t*)(ws + L.off_wininfo);
+    uint32_t* stream = (uint32_t*)(ws + L.off_stream);
     // small block layout
     uint32_t* flags = small + TKK_S_FLAGS;
     unsigned long long* err_pos = (unsigned long long*)(small + TKK_S_ERRPOS);
@@ -874,7 +969,7 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
     CK(cudaMemsetAsync(err_pos, 0xFF, 8, st));
     CK(cudaMemsetAsync(ds, 0, L.mask_words * 4, st));
     CK(cudaMemsetAsync(start + L.n_windows, 0, (L.mask_words - L.n_windows) * 4, st));
-    CK(cudaMemsetAsync(tilestate, 0, L.n_etiles * 8, st));
+    CK(cudaMemsetAsync(tilestate, 0, L.n_tiles * 8, st));
     docmark_kernel<<<(unsigned)ceil_div(n_docs + 1, 256), 256, 0, st>>>(d_doc_off, n_docs, n, ds, flags);
     TK_LAUNCHED();
     if (timer) timer->mark(st, "pretok");
@@ -902,20 +997,15 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
                                                              scratch_cursor, wc_huge, flags);
         TK_LAUNCHED();
     }
-    if (timer) timer->mark(st, "encode");
-    {
-        static std::atomic<uint64_t> attr_set{0};   // bit per device ordinal
-        int dev = 0;
-        CK(cudaGetDevice(&dev));
-        if (!((attr_set.load() >> (dev & 63)) & 1ull)) {
-            CK(cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EnSmem)));
-            attr_set.fetch_or(1ull << (dev & 63));
-        }
-        encode_kernel<<<(unsigned)L.n_etiles, EN_T, sizeof(EnSmem), st>>>(d_data, n, start, ds, longword, recs, pool, d_doc_off,
-                                                                        n_docs, add_bos ? 1u : 0u, add_eos ? 1u : 0u, T, d_out,
-                                                                        out_cap, d_tok_off, tilestate, ticket, total_out, flags);
-        TK_LAUNCHED();
-    }
+    if (timer) timer->mark(st, "merge");
+    merge_kernel<<<(unsigned)L.n_mtiles, MG_T, 0, st>>>(d_data, n, start, T, stream, win_info);
+    TK_LAUNCHED();
+    if (timer) timer->mark(st, "emit");
+    static_assert(EM_WINS == PT_T, "emit tiles are the pre-tokeniser's tiles");
+    emit_kernel<<<(unsigned)L.n_tiles, EM_T, 0, st>>>(n, start, ds, longword, recs, pool, stream, win_info, d_doc_off, n_docs,
+                                                     add_bos ? 1u : 0u, add_eos ? 1u : 0u, T.num_special, T.bos_id, T.eos_id, d_out,
+                                                     out_cap, d_tok_off, tilestate, ticket, total_out, flags);
+    TK_LAUNCHED();
     if (timer) timer->mark(st, "end");
     return cudaGetLastError();
 }

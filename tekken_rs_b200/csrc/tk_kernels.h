@@ -49,9 +49,9 @@ struct TkkLongRec {
 };
 
 struct EncodeLayout {
-    uint64_t n_windows, n_tiles, n_etiles, mask_words, max_long;
+    uint64_t n_windows, n_tiles, n_mtiles, mask_words, max_long;
     size_t off_small, off_ds, off_start, off_longword, off_summ, off_carry, off_worklist, off_tilestate, off_recs,
-        off_huge, off_pool, total;
+        off_huge, off_pool, off_wininfo, off_stream, total;
 };
 
 struct DecodeLayout {
