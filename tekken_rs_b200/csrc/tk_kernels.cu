@@ -541,14 +541,21 @@ __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __
 #define EN_LAST 0x80000000u
 #define EN_LONG 0xFFFFFFFFu
 
+#define MG_DEAD 0xFFFFFFFEu
+#define MG_PCAP (MG_TILE + 1)               // pieces that can start in a tile (+ the end sentinel)
+
 struct MgSmem {
     uint8_t bytes[MG_TILE + TK_SHORT_MAX + 16];
-    uint32_t stage[MG_CAP];   // ids of the parts of every piece, at the piece's byte offset
-    uint32_t rk[MG_CAP];      // pair ranks during C; rank count of a piece at its start; compacted ranks in D
+    uint32_t stage[MG_CAP];    // ids of the parts of every piece, at the piece's byte offset (MG_DEAD = merged away)
+    uint32_t rk[MG_CAP];       // C: rank << 6 | offset of the pair (part, next live part); rank count of a piece at its start; D: compacted ranks
     uint32_t mask[MG_WINS + 4];
-    uint16_t queue[MG_QCAP];  // tile-relative starts of the pieces that need merging
+    uint16_t list[MG_PCAP];    // tile-relative starts of all pieces, in order
+    uint32_t missq[MG_QCAP];   // pieces that need merging: start | len << 16, in discovery order
+    uint16_t queue[MG_QCAP];   // the same, longest first
+    uint32_t hist[TK_SHORT_MAX + 2];
+    uint32_t pfx[MG_WINS];
     uint32_t wsum[MG_T / 32];
-    uint32_t q_front, q_back, q_pop;
+    uint32_t n_pieces, n_miss, q_pop;
 };
 
 // tile-relative end of the piece that starts at tile-relative byte s (the next set bit of the start
@@ -573,8 +580,9 @@ __global__ void __launch_bounds__(MG_T) merge_kernel(const uint8_t* __restrict__
     const uint32_t tile = blockIdx.x;
     const uint64_t tile_pos = (uint64_t)tile * MG_TILE;
     const uint64_t win0 = (uint64_t)tile * MG_WINS;
-    if (t == 0) S.q_front = S.q_back = S.q_pop = 0;
-    // ---- A ----
+    if (t == 0) S.n_miss = S.q_pop = 0;
+    if (t < TK_SHORT_MAX + 2) S.hist[t] = 0;
+    // ---- A: stage bytes and mask words; list the piece starts ----
     {
         const uint64_t avail = n > tile_pos ? n - tile_pos : 0;
         const uint32_t want = MG_TILE + TK_SHORT_MAX + 16;
@@ -583,110 +591,152 @@ __global__ void __launch_bounds__(MG_T) merge_kernel(const uint8_t* __restrict__
         const uint4* src = reinterpret_cast<const uint4*>(data + tile_pos);
         for (uint32_t i = t; i < full16; i += MG_T) dst[i] = __ldg(src + i);
         for (uint32_t i = full16 * 16 + t; i < want; i += MG_T) S.bytes[i] = (tile_pos + i < n) ? data[tile_pos + i] : 0;
-        if (t < MG_WINS + 4) S.mask[t] = start_mask[win0 + t];
-    }
-    __syncthreads();
-
-    // ---- B: whole-piece lookups; MG_TPW threads share a window, taking its pieces round-robin ----
-    {
-        const uint32_t w = t / MG_TPW, sub = t % MG_TPW;
-        uint32_t m = S.mask[w], idx = 0;
-        while (m) {
-            const uint32_t bit = (uint32_t)(__ffs((int)m) - 1);
-            m &= m - 1;
-            if ((idx++ % MG_TPW) != sub) continue;
-            const uint32_t s = w * 32u + bit;
-            if (tile_pos + s >= n) continue;               // the end-of-data sentinel is not a piece
-            const uint32_t e = en_piece_end(S.mask, s);
-            if (e == 0xFFFFFFFFu || e - s > TK_SHORT_MAX) { S.stage[s] = EN_LONG; continue; }   // merged by K3
-            const uint32_t len = e - s;
-            const uint32_t whole = tk_vocab_lookup_w32(T, S.bytes, s, len);
-            if (whole != TK_INF) { S.stage[s] = whole | EN_LAST; S.rk[s] = 1; }
-            else if (len == 1) { S.stage[s] = (uint32_t)S.bytes[s] | EN_LAST; S.rk[s] = 1; }
-            else if (len > MG_LPT_LEN) S.queue[atomicAdd(&S.q_front, 1u)] = (uint16_t)s;
-            else S.queue[MG_QCAP - 1u - atomicAdd(&S.q_back, 1u)] = (uint16_t)s;
+        uint32_t m = 0;
+        if (t < MG_WINS + 4) { m = start_mask[win0 + t]; S.mask[t] = m; }
+        // exclusive prefix of the per-window piece counts (MG_WINS = 64 windows = warps 0 and 1)
+        const uint32_t c = t < MG_WINS ? (uint32_t)__popc(m) : 0u;
+        uint32_t inc = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if (lane >= d) inc += o;
+        }
+        if (lane == 31) S.wsum[warp] = inc;
+        __syncthreads();
+        if (t < MG_WINS) {
+            uint32_t o = inc - c;
+            for (uint32_t w = 0; w < warp; ++w) o += S.wsum[w];
+            while (m) {
+                S.list[o++] = (uint16_t)(t * 32u + (uint32_t)(__ffs((int)m) - 1));
+                m &= m - 1;
+            }
+            if (t == MG_WINS - 1) S.n_pieces = o;
         }
     }
     __syncthreads();
 
-    // ---- C: drain the merge queue ----
+    // ---- B: one lane per piece: whole-piece vocabulary lookup; misses are collected ----
     {
-        const uint32_t qf = S.q_front, qn = qf + S.q_back;
-        uint32_t s = 0, len = 0, i = 0;
-        unsigned long long live = 0;
-        int phase = 0;   // 0 fetch, 1 init, 2 merge
-        for (;;) {
-            if (phase == 0) {
-                const uint32_t k = atomicAdd(&S.q_pop, 1u);
-                if (k >= qn) break;
-                s = k < qf ? S.queue[k] : S.queue[MG_QCAP - 1u - (k - qf)];
-                len = en_piece_end(S.mask, s) - s;
-                i = 0;
-                phase = 1;
+        const uint32_t np = S.n_pieces;
+        for (uint32_t k0 = 0; k0 < np; k0 += MG_T) {
+            const uint32_t k = k0 + t;
+            bool miss = false;
+            uint32_t s = 0, len = 0;
+            if (k < np) {
+                s = S.list[k];
+                if (tile_pos + s < n) {                        // the end-of-data sentinel is not a piece
+                    const uint32_t e = en_piece_end(S.mask, s);
+                    if (e == 0xFFFFFFFFu || e - s > TK_SHORT_MAX) S.stage[s] = EN_LONG;   // merged by K3
+                    else {
+                        len = e - s;
+                        const uint32_t whole = tk_vocab_lookup_w32(T, S.bytes, s, len);
+                        if (whole != TK_INF) { S.stage[s] = whole | EN_LAST; S.rk[s] = 1; }
+                        else if (len == 1) { S.stage[s] = (uint32_t)S.bytes[s] | EN_LAST; S.rk[s] = 1; }
+                        else miss = true;
+                    }
+                }
             }
+            const uint32_t mm = __ballot_sync(0xFFFFFFFFu, miss);
+            if (mm) {
+                uint32_t base = 0;
+                const int leader = __ffs((int)mm) - 1;
+                if ((int)lane == leader) base = atomicAdd(&S.n_miss, (uint32_t)__popc(mm));
+                base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                if (miss) {
+                    S.missq[base + (uint32_t)__popc(mm & ((1u << lane) - 1u))] = s | (len << 16);
+                    atomicAdd(&S.hist[len], 1u);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // order the misses longest first (counting sort on the length): the lanes of a warp then work
+    // on pieces of about the same length, and the longest pieces start first
+    const uint32_t qn = S.n_miss;
+    if (warp == 0) {
+        // exclusive prefix over lengths in DESCENDING order: bins TK_SHORT_MAX .. 2
+        uint32_t run = 0;
+        for (int base = TK_SHORT_MAX; base >= 0; base -= 32) {
+            const int L = base - (int)lane;                 // this lane's length bin
+            const uint32_t c = L >= 2 ? S.hist[L] : 0u;
+            uint32_t inc = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                if ((int)lane >= d) inc += o;
+            }
+            if (L >= 2) S.hist[L] = run + inc - c;
+            run += __shfl_sync(0xFFFFFFFFu, inc, 31);
+        }
+    }
+    __syncthreads();
+    for (uint32_t k = t; k < qn; k += MG_T) {
+        const uint32_t e = S.missq[k];
+        S.queue[atomicAdd(&S.hist[e >> 16], 1u)] = (uint16_t)(e & 0xFFFFu);
+    }
+    __syncthreads();
+
+    // ---- C: exact byte_pair_merge, one lane per piece, a warp takes 32 queue entries at a time ----
+    for (;;) {
+        uint32_t k = 0;
+        if (lane == 0) k = atomicAdd(&S.q_pop, 32u);
+        k = __shfl_sync(0xFFFFFFFFu, k, 0);
+        if (k >= qn) break;
+        k += lane;
+        if (k < qn) {
+            const uint32_t s = S.queue[k];
+            const uint32_t len = en_piece_end(S.mask, s) - s;
             uint32_t* id = S.stage + s;
             uint32_t* rk = S.rk + s;
-            if (phase == 1) {
-                // parts = single bytes; rank of every adjacent byte pair from the direct table
-                const uint8_t* b = S.bytes + s;
+            const uint8_t* b = S.bytes + s;
+            // parts = single bytes; rank of every adjacent byte pair from the direct table
+            for (uint32_t i = 0; i < len; i += 4) {
                 uint32_t r4[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint32_t j = i + k;
-                    r4[k] = j + 1 < len ? __ldg(T.byte_pair + (((uint32_t)b[j] << 8) | b[j + 1])) : TK_INF;
+                for (int c = 0; c < 4; ++c) {
+                    const uint32_t j = i + c;
+                    r4[c] = j + 1 < len ? __ldg(T.byte_pair + (((uint32_t)b[j] << 8) | b[j + 1])) : TK_INF;
                 }
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint32_t j = i + k;
-                    if (j < len) { id[j] = b[j]; rk[j] = r4[k]; }
+                for (int c = 0; c < 4; ++c) {
+                    const uint32_t j = i + c;
+                    if (j < len) { id[j] = b[j]; rk[j] = r4[c] == TK_INF ? TK_INF : ((r4[c] << 6) | j); }
                 }
-                i += 4;
-                if (i >= len) { live = len >= 64u ? ~0ull : ((1ull << len) - 1ull); phase = 2; }
-            } else {
-                // one step of byte_pair_merge: lowest rank, leftmost on ties.  Dead offsets hold TK_INF.
-                uint32_t best = TK_INF, bp = 0;
-                for (uint32_t j = 0; j < len; j += 4) {
-                    const uint32_t a0 = rk[j];
-                    const uint32_t a1 = j + 1 < len ? rk[j + 1] : TK_INF;
-                    const uint32_t a2 = j + 2 < len ? rk[j + 2] : TK_INF;
-                    const uint32_t a3 = j + 3 < len ? rk[j + 3] : TK_INF;
-                    if (a0 < best) { best = a0; bp = j; }
-                    if (a1 < best) { best = a1; bp = j + 1; }
-                    if (a2 < best) { best = a2; bp = j + 2; }
-                    if (a3 < best) { best = a3; bp = j + 3; }
+            }
+            unsigned long long live = len >= 64u ? ~0ull : ((1ull << len) - 1ull);
+            for (;;) {
+                // lowest rank, leftmost on ties: the minimum of rank << 6 | offset (dead offsets hold TK_INF)
+                uint32_t best = TK_INF;
+                uint32_t j = 0;
+                for (; j + 4 <= len; j += 4) {
+                    const uint32_t a0 = rk[j], a1 = rk[j + 1], a2 = rk[j + 2], a3 = rk[j + 3];
+                    best = min(min(best, a0), min(a1, min(a2, a3)));
                 }
-                if (best == TK_INF) {
-                    // done: compact the surviving ids to the front (dst <= src), flag the last one
-                    uint32_t c = 0;
-                    unsigned long long lv = live;
-                    while (lv) {
-                        const uint32_t j = (uint32_t)(__ffsll((long long)lv) - 1);
-                        lv &= lv - 1;
-                        const uint32_t v = id[j];
-                        id[c++] = lv ? v : (v | EN_LAST);
-                    }
-                    rk[0] = c;
-                    phase = 0;
-                    continue;
-                }
+                for (; j < len; ++j) best = min(best, rk[j]);
+                if (best == TK_INF) break;
+                const uint32_t bp = best & 63u, rank = best >> 6;
                 // merge the part at bp with the next live part q
                 const unsigned long long above = live & ~((2ull << bp) - 1ull);           // live offsets > bp
-                const uint32_t q = (uint32_t)(__ffsll((long long)above) - 1);             // exists: rk[bp] != INF
+                const uint32_t q = (uint32_t)(__ffsll((long long)above) - 1);             // exists: the pair has a rank
                 const unsigned long long above_q = above & (above - 1);                    // live offsets > q
                 const unsigned long long below = live & ((1ull << bp) - 1ull);            // live offsets < bp
                 live &= ~(1ull << q);
                 const uint32_t nn = above_q ? (uint32_t)(__ffsll((long long)above_q) - 1) : 0xFFFFFFFFu;
                 const uint32_t pv = below ? (uint32_t)(63 - __clzll((long long)below)) : 0xFFFFFFFFu;
-                id[bp] = best;
+                id[bp] = rank;
+                id[q] = MG_DEAD;
                 rk[q] = TK_INF;
                 const uint32_t lft = pv != 0xFFFFFFFFu ? id[pv] : TK_INF;
                 const uint32_t rgt = nn != 0xFFFFFFFFu ? id[nn] : TK_INF;
                 uint32_t r0, r1;
-                tk_pair_rank2(T, lft, best, best, rgt, &r0, &r1);
-                if (pv != 0xFFFFFFFFu) rk[pv] = r0;
-                rk[bp] = r1;
+                tk_pair_rank2(T, lft, rank, rank, rgt, &r0, &r1);
+                if (pv != 0xFFFFFFFFu) rk[pv] = r0 == TK_INF ? TK_INF : ((r0 << 6) | pv);
+                rk[bp] = r1 == TK_INF ? TK_INF : ((r1 << 6) | bp);
             }
+            id[63 - __clzll((long long)live)] |= EN_LAST;
+            rk[0] = (uint32_t)__popcll(live);
         }
+        __syncwarp();
     }
     __syncthreads();
 
@@ -708,6 +758,7 @@ __global__ void __launch_bounds__(MG_T) merge_kernel(const uint8_t* __restrict__
         uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
         if (lane >= d) inc += o;
     }
+    __syncthreads();   // S.wsum is reused
     if (lane == 31) S.wsum[warp] = inc;
     __syncthreads();   // also: every thread is done reading the counts in S.rk
     uint32_t before = 0, tile_total = 0;
@@ -727,6 +778,7 @@ __global__ void __launch_bounds__(MG_T) merge_kernel(const uint8_t* __restrict__
             if (v == EN_LONG) continue;
             for (uint32_t j = 0;; ++j) {
                 v = S.stage[s + j];
+                if (v == MG_DEAD) continue;
                 comp[o++] = v;
                 if (v & EN_LAST) break;
             }
