@@ -175,35 +175,50 @@ __device__ __forceinline__ uint32_t tk_vocab_lookup_w32(const TkDeviceTables& T,
     }
 }
 
-// ---- one thread, one short piece ---------------------------------------------------------------
-// Sequential merge loop on a piece of at most TK_SHORT_MAX bytes held by one thread.  out[] gets
-// the ranks (no id offset); returns their count.
-#define TK_SHORT_MAX 64
+// ---- one lane, one piece of at most TK_LANE_MAX bytes ---------------------------------------------
+// Length classes of pieces (bytes):  <= TK_TILE_MAX  merged inside the text tile (merge_kernel);
+// <= TK_LANE_MAX  one lane per piece from a global queue (medmerge_kernel);  <= TK_MED_MAX  one warp per
+// piece;  beyond: one block per piece.  All run the same sequential definition.
+#define TK_TILE_MAX 32
+#define TK_LANE_MAX 64
+#define TK_LANE_DEAD 0xFFFFFFFEu
 
-__device__ inline uint32_t tk_bpe_thread(const TkDeviceTables& T, const uint8_t* p, uint32_t n, uint32_t* out) {
-    uint32_t id[TK_SHORT_MAX];
-    uint32_t rk[TK_SHORT_MAX];
-    uint8_t nx[TK_SHORT_MAX];
-    for (uint32_t i = 0; i < n; ++i) { id[i] = p[i]; nx[i] = (uint8_t)(i + 1); }
-    for (uint32_t i = 0; i + 1 < n; ++i) rk[i] = tk_pair_rank(T, id[i], id[i + 1]);
-    rk[n - 1] = TK_INF;
+// Exact byte_pair_merge of one piece by one lane.  id[j] = id of the part that starts at byte
+// offset j (initially the byte itself), key[j] = rank << 6 | j of the pair (part at j, next live
+// part), TK_INF if that pair is not a vocabulary entry or j is the last part.  Parts never move: a
+// merge writes the new id at the left part's offset, marks the right part's offset TK_LANE_DEAD,
+// and the set of live offsets is a 64-bit mask in registers, so neighbours come from bit
+// operations.  The minimum key is the lowest rank, leftmost on ties.  Returns the live mask.
+__device__ __forceinline__ unsigned long long tk_bpe_merge_loop(const TkDeviceTables& T, uint32_t len, uint32_t* id, uint32_t* key) {
+    unsigned long long live = len >= 64u ? ~0ull : ((1ull << len) - 1ull);
     for (;;) {
-        uint32_t best = TK_INF, bpos = 0, bprev = TK_INF, prev = TK_INF;
-        for (uint32_t i = 0; i < n; i = nx[i]) {
-            if (rk[i] < best) { best = rk[i]; bpos = i; bprev = prev; }
-            prev = i;
+        uint32_t best = TK_INF;
+        uint32_t j = 0;
+        for (; j + 4 <= len; j += 4) {
+            const uint32_t a0 = key[j], a1 = key[j + 1], a2 = key[j + 2], a3 = key[j + 3];
+            best = min(min(best, a0), min(a1, min(a2, a3)));
         }
+        for (; j < len; ++j) best = min(best, key[j]);
         if (best == TK_INF) break;
-        const uint32_t j = nx[bpos];
-        const uint32_t nn = nx[j];
-        id[bpos] = best;
-        nx[bpos] = (uint8_t)nn;
-        rk[bpos] = nn < n ? tk_pair_rank(T, best, id[nn]) : TK_INF;
-        if (bprev != TK_INF) rk[bprev] = tk_pair_rank(T, id[bprev], best);
+        const uint32_t bp = best & 63u, rank = best >> 6;
+        const unsigned long long above = live & ~((2ull << bp) - 1ull);           // live offsets > bp
+        const uint32_t q = (uint32_t)(__ffsll((long long)above) - 1);             // exists: the pair has a rank
+        const unsigned long long above_q = above & (above - 1);                    // live offsets > q
+        const unsigned long long below = live & ((1ull << bp) - 1ull);            // live offsets < bp
+        live &= ~(1ull << q);
+        const uint32_t nn = above_q ? (uint32_t)(__ffsll((long long)above_q) - 1) : 0xFFFFFFFFu;
+        const uint32_t pv = below ? (uint32_t)(63 - __clzll((long long)below)) : 0xFFFFFFFFu;
+        id[bp] = rank;
+        id[q] = TK_LANE_DEAD;
+        key[q] = TK_INF;
+        const uint32_t lft = pv != 0xFFFFFFFFu ? id[pv] : TK_INF;
+        const uint32_t rgt = nn != 0xFFFFFFFFu ? id[nn] : TK_INF;
+        uint32_t r0, r1;
+        tk_pair_rank2(T, lft, rank, rank, rgt, &r0, &r1);
+        if (pv != 0xFFFFFFFFu) key[pv] = r0 == TK_INF ? TK_INF : ((r0 << 6) | pv);
+        key[bp] = r1 == TK_INF ? TK_INF : ((r1 << 6) | bp);
     }
-    uint32_t k = 0;
-    for (uint32_t i = 0; i < n; i = nx[i]) out[k++] = id[i];
-    return k;
+    return live;
 }
 
 // ---- one warp, one medium piece ------------------------------------------------------------------

@@ -296,35 +296,144 @@ __global__ void __launch_bounds__(SC_T) pretok_scan_kernel(const TkkTileSummary*
 }
 
 // =====================================================================================================
-// K2a: pieces longer than TK_SHORT_MAX bytes.  Such a piece must start at the highest set bit of
-// its mask word, so one thread per word finds them all.
+// K2a: pieces longer than TK_TILE_MAX bytes.  Such a piece must start at the highest set bit of its
+// mask word, so one thread per word finds them all.  Pieces of up to TK_LANE_MAX bytes ("medium")
+// get their record, output space and a slot in the queue of their length class here; longer ones
+// are listed for the warp / block kernels, which measure them first.
 // =====================================================================================================
+#define MD_CLASSES 4
+__device__ __forceinline__ uint32_t med_class(uint32_t len) { return (len - (TK_TILE_MAX + 1)) >> 3; }   // 33..40, 41..48, 49..56, 57..64
+
+// one atomicAdd per warp: lanes with `pred` get consecutive slots starting at the returned base
+__device__ __forceinline__ uint32_t warp_claim(uint32_t* counter, bool pred) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, pred);
+    if (!m) return 0;
+    const int leader = __ffs((int)m) - 1;
+    uint32_t base = 0;
+    if ((int)lane == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    return base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+}
+
 __global__ void longmark_kernel(const uint32_t* __restrict__ start_mask, uint64_t n_windows, uint64_t n,
                                 uint32_t* __restrict__ long_of_word, TkkLongRec* __restrict__ recs,
-                                uint32_t* __restrict__ n_long) {
-    const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= n_windows) return;
-    const uint32_t m = start_mask[w];
-    uint32_t idx = 0;
+                                uint32_t* __restrict__ n_recs, uint32_t* __restrict__ long_list, uint32_t* __restrict__ n_long,
+                                uint32_t* __restrict__ med_q, uint64_t med_stride, uint32_t* __restrict__ med_n,
+                                unsigned long long* __restrict__ pool_cursor) {
+    const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;     // blockDim.x is a multiple of 32
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t m = w < n_windows ? start_mask[w] : 0u;
+    bool need = false, med = false;
+    uint64_t pos = 0;
+    uint32_t len = 0;
     if (m) {
         const uint32_t hb = 31u - (uint32_t)__clz((int)m);
-        const uint64_t pos = w * 32u + hb;
+        pos = w * 32u + hb;
         if (pos < n) {
-            // next start within TK_SHORT_MAX bytes?  (words beyond n_windows are zero-padded)
+            // next start within TK_LANE_MAX bytes?  (words beyond n_windows are zero-padded)
             const uint32_t m1 = start_mask[w + 1], m2 = start_mask[w + 2];
             uint64_t next;
             if (m1) next = (w + 1) * 32u + (uint32_t)(__ffs((int)m1) - 1);
             else if (m2) next = (w + 2) * 32u + (uint32_t)(__ffs((int)m2) - 1);
             else next = ~0ull;
-            if (next == ~0ull || next - pos > TK_SHORT_MAX) {
-                idx = atomicAdd(n_long, 1u) + 1u;
-                TkkLongRec r;
-                r.start = pos; r.len = 0; r.count = 0; r.tok_base = 0;
-                recs[idx - 1] = r;
-            }
+            need = next == ~0ull || next - pos > TK_TILE_MAX;
+            med = need && next != ~0ull && next - pos <= TK_LANE_MAX;
+            if (med) len = (uint32_t)(next - pos);
         }
     }
-    long_of_word[w] = idx;
+    const uint32_t slot = warp_claim(n_recs, need);
+    // output space of the medium pieces of this warp: one atomic for their total length
+    uint32_t inc = len;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if (lane >= (uint32_t)d) inc += o;
+    }
+    const uint32_t warp_total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+    unsigned long long pbase = 0;
+    if (lane == 0 && warp_total) pbase = atomicAdd(pool_cursor, (unsigned long long)warp_total);
+    pbase = __shfl_sync(0xFFFFFFFFu, pbase, 0);
+    const uint32_t cls = med ? med_class(len) : 0xFFFFFFFFu;
+#pragma unroll
+    for (uint32_t c = 0; c < MD_CLASSES; ++c) {
+        const uint32_t qpos = warp_claim(med_n + c, cls == c);
+        if (cls == c) med_q[c * med_stride + qpos] = slot;
+    }
+    const uint32_t lpos = warp_claim(n_long, need && !med);
+    if (need && !med) long_list[lpos] = slot;
+    if (need) {
+        TkkLongRec r;
+        r.start = pos; r.len = len; r.count = 0; r.tok_base = med ? pbase + (inc - len) : 0ull; r.pad = 0;
+        recs[slot] = r;
+    }
+    if (w < n_windows) long_of_word[w] = need ? slot + 1u : 0u;
+}
+
+// =====================================================================================================
+// K3m: medium pieces (TK_TILE_MAX < bytes <= TK_LANE_MAX), one lane per piece.  Persistent warps take
+// 32 records at a time from the queue of one length class (longest class first), so the lanes of a
+// warp run merge chains of about the same length and no block waits for a straggler.  Per-lane
+// scratch in shared memory, skewed by one word per lane against bank conflicts.
+// =====================================================================================================
+#define MD_T 128
+#define MD_STRIDE (TK_LANE_MAX + 1)
+
+__global__ void __launch_bounds__(MD_T) medmerge_kernel(const uint8_t* __restrict__ data, TkDeviceTables T,
+                                                        TkkLongRec* __restrict__ recs, const uint32_t* __restrict__ med_q,
+                                                        uint64_t med_stride, const uint32_t* __restrict__ med_n,
+                                                        uint32_t* __restrict__ med_w, uint32_t* __restrict__ pool) {
+    extern __shared__ __align__(16) uint32_t md_raw[];
+    uint32_t* id = md_raw + threadIdx.x * MD_STRIDE;
+    uint32_t* key = md_raw + MD_T * MD_STRIDE + threadIdx.x * MD_STRIDE;
+    const uint32_t lane = threadIdx.x & 31u;
+    for (int c = MD_CLASSES - 1; c >= 0; --c) {
+        const uint32_t total = med_n[c];
+        const uint32_t* q = med_q + (uint64_t)c * med_stride;
+        for (;;) {
+            uint32_t k = 0;
+            if (lane == 0) k = atomicAdd(med_w + c, 32u);
+            k = __shfl_sync(0xFFFFFFFFu, k, 0);
+            if (k >= total) break;
+            k += lane;
+            if (k < total) {
+                const uint32_t ri = q[k];
+                const TkkLongRec r = recs[ri];
+                const uint32_t len = (uint32_t)r.len;
+                const uint8_t* b = data + r.start;
+                for (uint32_t i = 0; i < len; i += 4) {
+                    uint32_t v[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) v[e] = i + e < len ? (uint32_t)__ldg(b + i + e) : 0u;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) if (i + e < len) id[i + e] = v[e];
+                }
+                for (uint32_t i = 0; i < len; i += 4) {
+                    uint32_t r4[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const uint32_t j = i + e;
+                        r4[e] = j + 1 < len ? __ldg(T.byte_pair + ((id[j] << 8) | id[j + 1])) : TK_INF;
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const uint32_t j = i + e;
+                        if (j < len) key[j] = r4[e] == TK_INF ? TK_INF : ((r4[e] << 6) | j);
+                    }
+                }
+                unsigned long long live = tk_bpe_merge_loop(T, len, id, key);
+                uint32_t* dst = pool + r.tok_base;
+                uint32_t cnt = 0;
+                while (live) {
+                    const uint32_t j = (uint32_t)(__ffsll((long long)live) - 1);
+                    live &= live - 1;
+                    dst[cnt++] = id[j];
+                }
+                recs[ri].count = cnt;
+            }
+            __syncwarp();
+        }
+    }
 }
 
 // =====================================================================================================
@@ -354,6 +463,7 @@ __device__ __forceinline__ uint64_t piece_end(const uint32_t* __restrict__ start
 __global__ void __launch_bounds__(LM_WARPS * 32) longmerge_warp_kernel(const uint8_t* __restrict__ data,
                                                                        const uint32_t* __restrict__ start_mask,
                                                                        TkDeviceTables T, TkkLongRec* __restrict__ recs,
+                                                                       const uint32_t* __restrict__ long_list,
                                                                        const uint32_t* __restrict__ n_long, uint32_t* __restrict__ pool,
                                                                        unsigned long long* __restrict__ pool_cursor,
                                                                        uint32_t* __restrict__ huge_list, uint32_t* __restrict__ n_huge,
@@ -366,6 +476,7 @@ __global__ void __launch_bounds__(LM_WARPS * 32) longmerge_warp_kernel(const uin
         if (lane == 0) r = atomicAdd(work_counter, 1u);
         r = __shfl_sync(0xFFFFFFFFu, r, 0);
         if (r >= total) break;
+        r = long_list[r];
         const uint64_t pos = recs[r].start;
         const uint64_t end = piece_end(start_mask, pos);
         const uint64_t len = end - pos;
@@ -534,26 +645,29 @@ __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __
 #define MG_T 128
 #define MG_WINS 64
 #define MG_TILE (MG_WINS * 32)
-#define MG_TPW (MG_T / MG_WINS)
-#define MG_CAP (MG_TILE + TK_SHORT_MAX)     // ranks a tile can produce (pieces that start in it)
-#define MG_QCAP (MG_TILE / 2)
-#define MG_LPT_LEN 20
+#define MG_CAP (MG_TILE + TK_TILE_MAX)      // ranks a tile can produce (pieces that start in it)
+#define MG_QCAP (MG_TILE / 2 + 4)
+#define MG_PCAP (MG_TILE + 4)               // pieces that can start in a tile (+ the end sentinel)
 #define EN_LAST 0x80000000u
 #define EN_LONG 0xFFFFFFFFu
-
-#define MG_DEAD 0xFFFFFFFEu
-#define MG_PCAP (MG_TILE + 1)               // pieces that can start in a tile (+ the end sentinel)
+#define MG_DEAD TK_LANE_DEAD
 
 struct MgSmem {
-    uint8_t bytes[MG_TILE + TK_SHORT_MAX + 16];
+    uint8_t bytes[MG_TILE + TK_TILE_MAX + 16];
     uint32_t stage[MG_CAP];    // ids of the parts of every piece, at the piece's byte offset (MG_DEAD = merged away)
-    uint32_t rk[MG_CAP];       // C: rank << 6 | offset of the pair (part, next live part); rank count of a piece at its start; D: compacted ranks
+    uint32_t rk[MG_CAP];       // C: pair keys (tk_bpe_merge_loop); rank count of a piece at its start; D: compacted ranks
     uint32_t mask[MG_WINS + 4];
     uint16_t list[MG_PCAP];    // tile-relative starts of all pieces, in order
-    uint32_t missq[MG_QCAP];   // pieces that need merging: start | len << 16, in discovery order
-    uint16_t queue[MG_QCAP];   // the same, longest first
-    uint32_t hist[TK_SHORT_MAX + 2];
-    uint32_t pfx[MG_WINS];
+    union {
+        uint32_t missq[MG_QCAP];   // B: pieces that need merging: start | len << 16, in discovery order
+        uint16_t poff[MG_PCAP];    // D: offset of every piece's ranks in the tile's compacted output
+    };
+    union {
+        uint16_t queue[MG_QCAP];   // C: the misses, longest first
+        uint8_t pcnt[MG_PCAP];     // D: ranks of every piece
+    };
+    uint32_t hist[TK_TILE_MAX + 2];
+    uint32_t pfx[MG_WINS + 1];     // index of the first piece of every window
     uint32_t wsum[MG_T / 32];
     uint32_t n_pieces, n_miss, q_pop;
 };
@@ -572,20 +686,39 @@ __device__ __forceinline__ uint32_t en_piece_end(const uint32_t* mask, uint32_t 
     return 0xFFFFFFFFu;
 }
 
+// block-wide exclusive prefix of one value per thread (MG_T threads); *total = sum over the block
+__device__ __forceinline__ uint32_t mg_block_excl(uint32_t v, uint32_t* wsum, uint32_t* total) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if (lane >= (uint32_t)d) inc += o;
+    }
+    __syncthreads();          // wsum may still be read from an earlier use
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    uint32_t before = 0, all = 0;
+#pragma unroll
+    for (int w = 0; w < MG_T / 32; ++w) { if (w < (int)warp) before += wsum[w]; all += wsum[w]; }
+    *total = all;
+    return before + inc - v;
+}
+
 __global__ void __launch_bounds__(MG_T) merge_kernel(const uint8_t* __restrict__ data, uint64_t n,
                                                      const uint32_t* __restrict__ start_mask, TkDeviceTables T,
                                                      uint32_t* __restrict__ stream, uint32_t* __restrict__ win_info) {
     __shared__ __align__(16) MgSmem S;
-    const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    const uint32_t t = threadIdx.x, lane = t & 31u;
     const uint32_t tile = blockIdx.x;
     const uint64_t tile_pos = (uint64_t)tile * MG_TILE;
     const uint64_t win0 = (uint64_t)tile * MG_WINS;
     if (t == 0) S.n_miss = S.q_pop = 0;
-    if (t < TK_SHORT_MAX + 2) S.hist[t] = 0;
+    if (t < TK_TILE_MAX + 2) S.hist[t] = 0;
     // ---- A: stage bytes and mask words; list the piece starts ----
     {
         const uint64_t avail = n > tile_pos ? n - tile_pos : 0;
-        const uint32_t want = MG_TILE + TK_SHORT_MAX + 16;
+        const uint32_t want = MG_TILE + TK_TILE_MAX + 16;
         const uint32_t full16 = (uint32_t)((avail < want ? avail : want) / 16);
         uint4* dst = reinterpret_cast<uint4*>(S.bytes);
         const uint4* src = reinterpret_cast<const uint4*>(data + tile_pos);
@@ -593,59 +726,47 @@ __global__ void __launch_bounds__(MG_T) merge_kernel(const uint8_t* __restrict__
         for (uint32_t i = full16 * 16 + t; i < want; i += MG_T) S.bytes[i] = (tile_pos + i < n) ? data[tile_pos + i] : 0;
         uint32_t m = 0;
         if (t < MG_WINS + 4) { m = start_mask[win0 + t]; S.mask[t] = m; }
-        // exclusive prefix of the per-window piece counts (MG_WINS = 64 windows = warps 0 and 1)
-        const uint32_t c = t < MG_WINS ? (uint32_t)__popc(m) : 0u;
-        uint32_t inc = c;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-            if (lane >= d) inc += o;
-        }
-        if (lane == 31) S.wsum[warp] = inc;
-        __syncthreads();
-        if (t < MG_WINS) {
-            uint32_t o = inc - c;
-            for (uint32_t w = 0; w < warp; ++w) o += S.wsum[w];
-            while (m) {
-                S.list[o++] = (uint16_t)(t * 32u + (uint32_t)(__ffs((int)m) - 1));
-                m &= m - 1;
-            }
-            if (t == MG_WINS - 1) S.n_pieces = o;
+        if (t >= MG_WINS) m = 0;
+        uint32_t np;
+        uint32_t o = mg_block_excl((uint32_t)__popc(m), S.wsum, &np);
+        if (t < MG_WINS) S.pfx[t] = o;
+        if (t == 0) { S.pfx[MG_WINS] = np; S.n_pieces = np; }
+        while (m) {
+            S.list[o++] = (uint16_t)(t * 32u + (uint32_t)(__ffs((int)m) - 1));
+            m &= m - 1;
         }
     }
     __syncthreads();
+    const uint32_t np = S.n_pieces;
 
     // ---- B: one lane per piece: whole-piece vocabulary lookup; misses are collected ----
-    {
-        const uint32_t np = S.n_pieces;
-        for (uint32_t k0 = 0; k0 < np; k0 += MG_T) {
-            const uint32_t k = k0 + t;
-            bool miss = false;
-            uint32_t s = 0, len = 0;
-            if (k < np) {
-                s = S.list[k];
-                if (tile_pos + s < n) {                        // the end-of-data sentinel is not a piece
-                    const uint32_t e = en_piece_end(S.mask, s);
-                    if (e == 0xFFFFFFFFu || e - s > TK_SHORT_MAX) S.stage[s] = EN_LONG;   // merged by K3
-                    else {
-                        len = e - s;
-                        const uint32_t whole = tk_vocab_lookup_w32(T, S.bytes, s, len);
-                        if (whole != TK_INF) { S.stage[s] = whole | EN_LAST; S.rk[s] = 1; }
-                        else if (len == 1) { S.stage[s] = (uint32_t)S.bytes[s] | EN_LAST; S.rk[s] = 1; }
-                        else miss = true;
-                    }
+    for (uint32_t k0 = 0; k0 < np; k0 += MG_T) {
+        const uint32_t k = k0 + t;
+        bool miss = false;
+        uint32_t s = 0, len = 0;
+        if (k < np) {
+            s = S.list[k];
+            if (tile_pos + s < n) {                        // the end-of-data sentinel is not a piece
+                const uint32_t e = en_piece_end(S.mask, s);
+                if (e == 0xFFFFFFFFu || e - s > TK_TILE_MAX) S.stage[s] = EN_LONG;   // merged by K3 / K3m
+                else {
+                    len = e - s;
+                    const uint32_t whole = tk_vocab_lookup_w32(T, S.bytes, s, len);
+                    if (whole != TK_INF) { S.stage[s] = whole | EN_LAST; S.rk[s] = 1; }
+                    else if (len == 1) { S.stage[s] = (uint32_t)S.bytes[s] | EN_LAST; S.rk[s] = 1; }
+                    else miss = true;
                 }
             }
-            const uint32_t mm = __ballot_sync(0xFFFFFFFFu, miss);
-            if (mm) {
-                uint32_t base = 0;
-                const int leader = __ffs((int)mm) - 1;
-                if ((int)lane == leader) base = atomicAdd(&S.n_miss, (uint32_t)__popc(mm));
-                base = __shfl_sync(0xFFFFFFFFu, base, leader);
-                if (miss) {
-                    S.missq[base + (uint32_t)__popc(mm & ((1u << lane) - 1u))] = s | (len << 16);
-                    atomicAdd(&S.hist[len], 1u);
-                }
+        }
+        const uint32_t mm = __ballot_sync(0xFFFFFFFFu, miss);
+        if (mm) {
+            uint32_t base = 0;
+            const int leader = __ffs((int)mm) - 1;
+            if ((int)lane == leader) base = atomicAdd(&S.n_miss, (uint32_t)__popc(mm));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (miss) {
+                S.missq[base + (uint32_t)__popc(mm & ((1u << lane) - 1u))] = s | (len << 16);
+                atomicAdd(&S.hist[len], 1u);
             }
         }
     }
@@ -653,21 +774,16 @@ __global__ void __launch_bounds__(MG_T) merge_kernel(const uint8_t* __restrict__
     // order the misses longest first (counting sort on the length): the lanes of a warp then work
     // on pieces of about the same length, and the longest pieces start first
     const uint32_t qn = S.n_miss;
-    if (warp == 0) {
-        // exclusive prefix over lengths in DESCENDING order: bins TK_SHORT_MAX .. 2
-        uint32_t run = 0;
-        for (int base = TK_SHORT_MAX; base >= 0; base -= 32) {
-            const int L = base - (int)lane;                 // this lane's length bin
-            const uint32_t c = L >= 2 ? S.hist[L] : 0u;
-            uint32_t inc = c;
+    if (t < 32) {
+        const int L = TK_TILE_MAX - (int)lane;              // lane 0 = longest; lengths 32 .. 1
+        const uint32_t c = L >= 2 ? S.hist[L] : 0u;
+        uint32_t inc = c;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-                if ((int)lane >= d) inc += o;
-            }
-            if (L >= 2) S.hist[L] = run + inc - c;
-            run += __shfl_sync(0xFFFFFFFFu, inc, 31);
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if ((int)lane >= d) inc += o;
         }
+        if (L >= 2) S.hist[L] = inc - c;
     }
     __syncthreads();
     for (uint32_t k = t; k < qn; k += MG_T) {
@@ -687,7 +803,7 @@ __global__ void __launch_bounds__(MG_T) merge_kernel(const uint8_t* __restrict__
             const uint32_t s = S.queue[k];
             const uint32_t len = en_piece_end(S.mask, s) - s;
             uint32_t* id = S.stage + s;
-            uint32_t* rk = S.rk + s;
+            uint32_t* key = S.rk + s;
             const uint8_t* b = S.bytes + s;
             // parts = single bytes; rank of every adjacent byte pair from the direct table
             for (uint32_t i = 0; i < len; i += 4) {
@@ -700,89 +816,49 @@ __global__ void __launch_bounds__(MG_T) merge_kernel(const uint8_t* __restrict__
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const uint32_t j = i + c;
-                    if (j < len) { id[j] = b[j]; rk[j] = r4[c] == TK_INF ? TK_INF : ((r4[c] << 6) | j); }
+                    if (j < len) { id[j] = b[j]; key[j] = r4[c] == TK_INF ? TK_INF : ((r4[c] << 6) | j); }
                 }
             }
-            unsigned long long live = len >= 64u ? ~0ull : ((1ull << len) - 1ull);
-            for (;;) {
-                // lowest rank, leftmost on ties: the minimum of rank << 6 | offset (dead offsets hold TK_INF)
-                uint32_t best = TK_INF;
-                uint32_t j = 0;
-                for (; j + 4 <= len; j += 4) {
-                    const uint32_t a0 = rk[j], a1 = rk[j + 1], a2 = rk[j + 2], a3 = rk[j + 3];
-                    best = min(min(best, a0), min(a1, min(a2, a3)));
-                }
-                for (; j < len; ++j) best = min(best, rk[j]);
-                if (best == TK_INF) break;
-                const uint32_t bp = best & 63u, rank = best >> 6;
-                // merge the part at bp with the next live part q
-                const unsigned long long above = live & ~((2ull << bp) - 1ull);           // live offsets > bp
-                const uint32_t q = (uint32_t)(__ffsll((long long)above) - 1);             // exists: the pair has a rank
-                const unsigned long long above_q = above & (above - 1);                    // live offsets > q
-                const unsigned long long below = live & ((1ull << bp) - 1ull);            // live offsets < bp
-                live &= ~(1ull << q);
-                const uint32_t nn = above_q ? (uint32_t)(__ffsll((long long)above_q) - 1) : 0xFFFFFFFFu;
-                const uint32_t pv = below ? (uint32_t)(63 - __clzll((long long)below)) : 0xFFFFFFFFu;
-                id[bp] = rank;
-                id[q] = MG_DEAD;
-                rk[q] = TK_INF;
-                const uint32_t lft = pv != 0xFFFFFFFFu ? id[pv] : TK_INF;
-                const uint32_t rgt = nn != 0xFFFFFFFFu ? id[nn] : TK_INF;
-                uint32_t r0, r1;
-                tk_pair_rank2(T, lft, rank, rank, rgt, &r0, &r1);
-                if (pv != 0xFFFFFFFFu) rk[pv] = r0 == TK_INF ? TK_INF : ((r0 << 6) | pv);
-                rk[bp] = r1 == TK_INF ? TK_INF : ((r1 << 6) | bp);
-            }
+            const unsigned long long live = tk_bpe_merge_loop(T, len, id, key);
             id[63 - __clzll((long long)live)] |= EN_LAST;
-            rk[0] = (uint32_t)__popcll(live);
+            key[0] = (uint32_t)__popcll(live);
         }
         __syncwarp();
     }
     __syncthreads();
 
-    // ---- D: compact the tile's ranks and write them to its slot of the stream ----
-    uint32_t count = 0;
-    if (t < MG_WINS) {
-        uint32_t m = S.mask[t];
-        while (m) {
-            const uint32_t bit = (uint32_t)(__ffs((int)m) - 1);
-            m &= m - 1;
-            const uint32_t s = t * 32u + bit;
-            if (tile_pos + s >= n) continue;
-            if (S.stage[s] != EN_LONG) count += S.rk[s];
-        }
+    // ---- D: compact the tile's ranks (one lane per piece) and write them to its slot of the stream ----
+    for (uint32_t k = t; k < np; k += MG_T) {
+        const uint32_t s = S.list[k];
+        S.pcnt[k] = (tile_pos + s >= n || S.stage[s] == EN_LONG) ? 0u : (uint8_t)S.rk[s];
     }
-    uint32_t inc = count;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-        if (lane >= d) inc += o;
+    __syncthreads();          // every count in S.rk has been read: S.rk becomes the compaction buffer
+    uint32_t tile_total;
+    {
+        const uint32_t per = (np + MG_T - 1) / MG_T;
+        const uint32_t lo = t * per < np ? t * per : np, hi = lo + per < np ? lo + per : np;
+        uint32_t sum = 0;
+        for (uint32_t k = lo; k < hi; ++k) sum += S.pcnt[k];
+        uint32_t o = mg_block_excl(sum, S.wsum, &tile_total);
+        for (uint32_t k = lo; k < hi; ++k) { S.poff[k] = (uint16_t)o; o += S.pcnt[k]; }
+        if (t == 0) S.poff[np] = (uint16_t)tile_total;
     }
-    __syncthreads();   // S.wsum is reused
-    if (lane == 31) S.wsum[warp] = inc;
-    __syncthreads();   // also: every thread is done reading the counts in S.rk
-    uint32_t before = 0, tile_total = 0;
-#pragma unroll
-    for (int w = 0; w < MG_T / 32; ++w) { if (w < (int)warp) before += S.wsum[w]; tile_total += S.wsum[w]; }
+    __syncthreads();
     uint32_t* comp = S.rk;
-    if (t < MG_WINS) {
-        uint32_t o = before + inc - count;
-        win_info[win0 + t] = o | (count << 16);
-        uint32_t m = S.mask[t];
-        while (m) {
-            const uint32_t bit = (uint32_t)(__ffs((int)m) - 1);
-            m &= m - 1;
-            const uint32_t s = t * 32u + bit;
-            if (tile_pos + s >= n) continue;
-            uint32_t v = S.stage[s];
-            if (v == EN_LONG) continue;
-            for (uint32_t j = 0;; ++j) {
-                v = S.stage[s + j];
-                if (v == MG_DEAD) continue;
-                comp[o++] = v;
-                if (v & EN_LAST) break;
-            }
+    for (uint32_t k = t; k < np; k += MG_T) {
+        if (!S.pcnt[k]) continue;
+        const uint32_t s = S.list[k];
+        uint32_t o = S.poff[k];
+        for (uint32_t j = 0;; ++j) {
+            const uint32_t v = S.stage[s + j];
+            if (v == MG_DEAD) continue;
+            comp[o++] = v;
+            if (v & EN_LAST) break;
         }
+    }
+    if (t < MG_WINS) {
+        const uint32_t o0 = S.poff[S.pfx[t]], o1 = S.poff[S.pfx[t + 1]];
+        win_info[win0 + t] = o0 | ((o1 - o0) << 16);
     }
     __syncthreads();
     uint32_t* dst = stream + (uint64_t)tile * MG_CAP;
@@ -973,7 +1049,9 @@ size_t encode_workspace_bytes(uint64_t n, uint64_t n_docs, EncodeLayout* L) {
     l.off_tilestate = take(n_tiles * 8);
     l.off_wininfo = take(words * 4);
     l.off_stream = take(l.n_mtiles * (size_t)MG_CAP * 4);
-    l.max_long = n / (TK_SHORT_MAX + 1) + 2;
+    l.off_longlist = take((n / (TK_TILE_MAX + 1) + 2) * 4);
+    l.off_medq = take((n / (TK_TILE_MAX + 1) + 2) * 4 * MD_CLASSES);
+    l.max_long = n / (TK_TILE_MAX + 1) + 2;
     l.off_recs = take(l.max_long * sizeof(TkkLongRec));
     l.off_huge = take(l.max_long * 4);
     l.off_pool = take((n + 16) * 4);
@@ -1003,6 +1081,8 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
     uint32_t* pool = (uint32_t*)(ws + L.off_pool);
     uint32_t* win_info = (uint32_t*)(ws + L.off_wininfo);
     uint32_t* stream = (uint32_t*)(ws + L.off_stream);
+    uint32_t* long_list = (uint32_t*)(ws + L.off_longlist);
+    uint32_t* med_q = (uint32_t*)(ws + L.off_medq);
     // small block layout
     uint32_t* flags = small + TKK_S_FLAGS;
     unsigned long long* err_pos = (unsigned long long*)(small + TKK_S_ERRPOS);
@@ -1012,6 +1092,9 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
     uint32_t* wc_long = small + TKK_S_WC_LONG;
     uint32_t* wc_huge = small + TKK_S_WC_HUGE;
     uint32_t* ticket = small + TKK_S_TICKET;
+    uint32_t* n_longonly = small + TKK_S_NLONGONLY;
+    uint32_t* med_n = small + TKK_S_MEDN;
+    uint32_t* med_w = small + TKK_S_MEDW;
     unsigned long long* pool_cursor = (unsigned long long*)(small + TKK_S_POOLCUR);
     unsigned long long* scratch_cursor = (unsigned long long*)(small + TKK_S_SCRCUR);
     unsigned long long* total_out = (unsigned long long*)(small + TKK_S_TOTAL);
@@ -1034,19 +1117,33 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
         d_data, n, ds, start, L.n_windows, T, carry, worklist, work_count, err_pos);
     TK_LAUNCHED();
     if (timer) timer->mark(st, "longmark");
-    longmark_kernel<<<(unsigned)ceil_div(L.n_windows, 256), 256, 0, st>>>(start, L.n_windows, n, longword, recs, n_long);
+    longmark_kernel<<<(unsigned)ceil_div(L.n_windows, 256), 256, 0, st>>>(start, L.n_windows, n, longword, recs, n_long, long_list,
+                                                                          n_longonly, med_q, L.max_long, med_n, pool_cursor);
     TK_LAUNCHED();
     if (timer) timer->mark(st, "longmerge");
     {
         uint64_t blocks = ceil_div(L.max_long, LM_WARPS);
         const uint64_t cap = (uint64_t)sm_count * 12;
         if (blocks > cap) blocks = cap;
-        longmerge_warp_kernel<<<(unsigned)blocks, LM_WARPS * 32, 0, st>>>(d_data, start, T, recs, n_long, pool, pool_cursor, huge,
-                                                                        n_huge, wc_long);
+        longmerge_warp_kernel<<<(unsigned)blocks, LM_WARPS * 32, 0, st>>>(d_data, start, T, recs, long_list, n_longonly, pool,
+                                                                        pool_cursor, huge, n_huge, wc_long);
         TK_LAUNCHED();
         uint64_t hb = L.max_long < (uint64_t)(2 * sm_count) ? L.max_long : (uint64_t)(2 * sm_count);
         longmerge_block_kernel<<<(unsigned)hb, HG_T, 0, st>>>(d_data, T, recs, huge, n_huge, pool, d_scratch, scratch_cap,
                                                              scratch_cursor, wc_huge, flags);
+        TK_LAUNCHED();
+    }
+    if (timer) timer->mark(st, "medmerge");
+    {
+        const size_t smem = (size_t)2 * MD_T * MD_STRIDE * sizeof(uint32_t);
+        static std::atomic<uint64_t> attr_set{0};   // bit per device ordinal
+        int dev = 0;
+        CK(cudaGetDevice(&dev));
+        if (!((attr_set.load() >> (dev & 63)) & 1ull)) {
+            CK(cudaFuncSetAttribute(medmerge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set.fetch_or(1ull << (dev & 63));
+        }
+        medmerge_kernel<<<(unsigned)(sm_count * 3), MD_T, smem, st>>>(d_data, T, recs, med_q, L.max_long, med_n, med_w, pool);
         TK_LAUNCHED();
     }
     if (timer) timer->mark(st, "merge");

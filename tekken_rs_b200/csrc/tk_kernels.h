@@ -32,6 +32,9 @@ enum {
     TKK_S_SCRCUR = 12,   // u64
     TKK_S_TOTAL = 14,    // u64
     TKK_S_BADDOC = 16,   // u64 (decode)
+    TKK_S_NLONGONLY = 18,
+    TKK_S_MEDN = 20,     // 4 counters: medium pieces per length class
+    TKK_S_MEDW = 24,     // 4 work counters
 };
 
 struct TkkTileSummary {
@@ -51,7 +54,7 @@ struct TkkLongRec {
 struct EncodeLayout {
     uint64_t n_windows, n_tiles, n_mtiles, mask_words, max_long;
     size_t off_small, off_ds, off_start, off_longword, off_summ, off_carry, off_worklist, off_tilestate, off_recs,
-        off_huge, off_pool, off_wininfo, off_stream, total;
+        off_huge, off_pool, off_wininfo, off_stream, off_longlist, off_medq, total;
 };
 
 struct DecodeLayout {
