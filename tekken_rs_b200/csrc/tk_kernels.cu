@@ -296,14 +296,9 @@ __global__ void __launch_bounds__(SC_T) pretok_scan_kernel(const TkkTileSummary*
 }
 
 // =====================================================================================================
-// K2a: pieces longer than TK_TILE_MAX bytes.  Such a piece must start at the highest set bit of its
-// mask word, so one thread per word finds them all.  Pieces of up to TK_LANE_MAX bytes ("medium")
-// get their record, output space and a slot in the queue of their length class here; longer ones
-// are listed for the warp / block kernels, which measure them first.
+// K2a: pieces longer than TK_LANE_MAX bytes.  Such a piece must start at the highest set bit of its
+// mask word, so one thread per word finds them all.
 // =====================================================================================================
-#define MD_CLASSES 4
-__device__ __forceinline__ uint32_t med_class(uint32_t len) { return (len - (TK_TILE_MAX + 1)) >> 3; }   // 33..40, 41..48, 49..56, 57..64
-
 // one atomicAdd per warp: lanes with `pred` get consecutive slots starting at the returned base
 __device__ __forceinline__ uint32_t warp_claim(uint32_t* counter, bool pred) {
     const uint32_t lane = threadIdx.x & 31u;
@@ -318,15 +313,11 @@ __device__ __forceinline__ uint32_t warp_claim(uint32_t* counter, bool pred) {
 
 __global__ void longmark_kernel(const uint32_t* __restrict__ start_mask, uint64_t n_windows, uint64_t n,
                                 uint32_t* __restrict__ long_of_word, TkkLongRec* __restrict__ recs,
-                                uint32_t* __restrict__ n_recs, uint32_t* __restrict__ long_list, uint32_t* __restrict__ n_long,
-                                uint32_t* __restrict__ med_q, uint64_t med_stride, uint32_t* __restrict__ med_n,
-                                unsigned long long* __restrict__ pool_cursor) {
+                                uint32_t* __restrict__ n_long) {
     const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;     // blockDim.x is a multiple of 32
-    const uint32_t lane = threadIdx.x & 31u;
     const uint32_t m = w < n_windows ? start_mask[w] : 0u;
-    bool need = false, med = false;
+    bool need = false;
     uint64_t pos = 0;
-    uint32_t len = 0;
     if (m) {
         const uint32_t hb = 31u - (uint32_t)__clz((int)m);
         pos = w * 32u + hb;
@@ -337,103 +328,16 @@ __global__ void longmark_kernel(const uint32_t* __restrict__ start_mask, uint64_
             if (m1) next = (w + 1) * 32u + (uint32_t)(__ffs((int)m1) - 1);
             else if (m2) next = (w + 2) * 32u + (uint32_t)(__ffs((int)m2) - 1);
             else next = ~0ull;
-            need = next == ~0ull || next - pos > TK_TILE_MAX;
-            med = need && next != ~0ull && next - pos <= TK_LANE_MAX;
-            if (med) len = (uint32_t)(next - pos);
+            need = next == ~0ull || next - pos > TK_LANE_MAX;
         }
     }
-    const uint32_t slot = warp_claim(n_recs, need);
-    // output space of the medium pieces of this warp: one atomic for their total length
-    uint32_t inc = len;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-        if (lane >= (uint32_t)d) inc += o;
-    }
-    const uint32_t warp_total = __shfl_sync(0xFFFFFFFFu, inc, 31);
-    unsigned long long pbase = 0;
-    if (lane == 0 && warp_total) pbase = atomicAdd(pool_cursor, (unsigned long long)warp_total);
-    pbase = __shfl_sync(0xFFFFFFFFu, pbase, 0);
-    const uint32_t cls = med ? med_class(len) : 0xFFFFFFFFu;
-#pragma unroll
-    for (uint32_t c = 0; c < MD_CLASSES; ++c) {
-        const uint32_t qpos = warp_claim(med_n + c, cls == c);
-        if (cls == c) med_q[c * med_stride + qpos] = slot;
-    }
-    const uint32_t lpos = warp_claim(n_long, need && !med);
-    if (need && !med) long_list[lpos] = slot;
+    const uint32_t slot = warp_claim(n_long, need);
     if (need) {
         TkkLongRec r;
-        r.start = pos; r.len = len; r.count = 0; r.tok_base = med ? pbase + (inc - len) : 0ull; r.pad = 0;
+        r.start = pos; r.len = 0; r.count = 0; r.tok_base = 0; r.pad = 0;
         recs[slot] = r;
     }
     if (w < n_windows) long_of_word[w] = need ? slot + 1u : 0u;
-}
-
-// =====================================================================================================
-// K3m: medium pieces (TK_TILE_MAX < bytes <= TK_LANE_MAX), one lane per piece.  Persistent warps take
-// 32 records at a time from the queue of one length class (longest class first), so the lanes of a
-// warp run merge chains of about the same length and no block waits for a straggler.  Per-lane
-// scratch in shared memory, skewed by one word per lane against bank conflicts.
-// =====================================================================================================
-#define MD_T 128
-#define MD_STRIDE (TK_LANE_MAX + 1)
-
-__global__ void __launch_bounds__(MD_T) medmerge_kernel(const uint8_t* __restrict__ data, TkDeviceTables T,
-                                                        TkkLongRec* __restrict__ recs, const uint32_t* __restrict__ med_q,
-                                                        uint64_t med_stride, const uint32_t* __restrict__ med_n,
-                                                        uint32_t* __restrict__ med_w, uint32_t* __restrict__ pool) {
-    extern __shared__ __align__(16) uint32_t md_raw[];
-    uint32_t* id = md_raw + threadIdx.x * MD_STRIDE;
-    uint32_t* key = md_raw + MD_T * MD_STRIDE + threadIdx.x * MD_STRIDE;
-    const uint32_t lane = threadIdx.x & 31u;
-    for (int c = MD_CLASSES - 1; c >= 0; --c) {
-        const uint32_t total = med_n[c];
-        const uint32_t* q = med_q + (uint64_t)c * med_stride;
-        for (;;) {
-            uint32_t k = 0;
-            if (lane == 0) k = atomicAdd(med_w + c, 32u);
-            k = __shfl_sync(0xFFFFFFFFu, k, 0);
-            if (k >= total) break;
-            k += lane;
-            if (k < total) {
-                const uint32_t ri = q[k];
-                const TkkLongRec r = recs[ri];
-                const uint32_t len = (uint32_t)r.len;
-                const uint8_t* b = data + r.start;
-                for (uint32_t i = 0; i < len; i += 4) {
-                    uint32_t v[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) v[e] = i + e < len ? (uint32_t)__ldg(b + i + e) : 0u;
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) if (i + e < len) id[i + e] = v[e];
-                }
-                for (uint32_t i = 0; i < len; i += 4) {
-                    uint32_t r4[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const uint32_t j = i + e;
-                        r4[e] = j + 1 < len ? __ldg(T.byte_pair + ((id[j] << 8) | id[j + 1])) : TK_INF;
-                    }
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const uint32_t j = i + e;
-                        if (j < len) key[j] = r4[e] == TK_INF ? TK_INF : ((r4[e] << 6) | j);
-                    }
-                }
-                unsigned long long live = tk_bpe_merge_loop(T, len, id, key);
-                uint32_t* dst = pool + r.tok_base;
-                uint32_t cnt = 0;
-                while (live) {
-                    const uint32_t j = (uint32_t)(__ffsll((long long)live) - 1);
-                    live &= live - 1;
-                    dst[cnt++] = id[j];
-                }
-                recs[ri].count = cnt;
-            }
-            __syncwarp();
-        }
-    }
 }
 
 // =====================================================================================================
@@ -463,7 +367,6 @@ __device__ __forceinline__ uint64_t piece_end(const uint32_t* __restrict__ start
 __global__ void __launch_bounds__(LM_WARPS * 32) longmerge_warp_kernel(const uint8_t* __restrict__ data,
                                                                        const uint32_t* __restrict__ start_mask,
                                                                        TkDeviceTables T, TkkLongRec* __restrict__ recs,
-                                                                       const uint32_t* __restrict__ long_list,
                                                                        const uint32_t* __restrict__ n_long, uint32_t* __restrict__ pool,
                                                                        unsigned long long* __restrict__ pool_cursor,
                                                                        uint32_t* __restrict__ huge_list, uint32_t* __restrict__ n_huge,
@@ -476,7 +379,6 @@ __global__ void __launch_bounds__(LM_WARPS * 32) longmerge_warp_kernel(const uin
         if (lane == 0) r = atomicAdd(work_counter, 1u);
         r = __shfl_sync(0xFFFFFFFFu, r, 0);
         if (r >= total) break;
-        r = long_list[r];
         const uint64_t pos = recs[r].start;
         const uint64_t end = piece_end(start_mask, pos);
         const uint64_t len = end - pos;
@@ -628,48 +530,43 @@ __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __
 }
 
 // =====================================================================================================
-// K2: merge tiles.  One block per MG_TILE bytes of text; no dependence between blocks.
-//   A  stage the tile's bytes (+ look-ahead) and piece-start mask words in shared memory
-//   B  every short piece that starts in the tile: whole-piece vocabulary lookup (CoreBPE's shortcut);
-//      misses go to a shared-memory work queue, longest first
-//   C  all threads drain the queue: exact byte_pair_merge per piece.  Parts stay at their byte offset
-//      (id + rank of the pair with the next live part, in shared memory); which offsets are live is a
-//      64-bit mask in registers, so neighbours come from bit operations and a merge moves nothing.
-//      A flattened state machine (fetch / init / merge step) keeps the lanes of a warp in one loop
-//      while they work on different pieces; the two pair lookups of a merge are issued together.
-//   D  the ranks of the tile (last-of-piece flag in bit 31) are compacted in shared memory and
-//      written with coalesced stores to the tile's slot of the rank stream; per window: offset into
-//      that slot and number of ranks.
+// K2: lookup tiles.  One block per LK_TILE bytes of text, one lane per piece: the whole-piece
+// vocabulary lookup (CoreBPE's shortcut).  Every piece of at most TK_LANE_MAX bytes gets room in the
+// tile's slot of the rank stream: 1 slot if it is a vocabulary entry (written here, last-of-piece
+// flag in bit 31), `len` slots otherwise -- those pieces are queued, by length class, for K2m, which
+// writes their ranks at the front of the reserved slots.  (A piece that needs merging always yields
+// >= 2 ranks, so "the first rank carries the flag" tells the reader which kind a piece is.)
+// K2m: one lane per queued piece: exact byte_pair_merge (tk_bpe_merge_loop).  Persistent warps take
+// 32 queue entries at a time; a queue holds one length class, so the lanes of a warp run merge
+// chains of similar length, every lane always has a piece, and nothing waits for a straggler.
 // K4 (emit) turns the stream into the final ids.
 // =====================================================================================================
-#define MG_T 128
-#define MG_WINS 64
-#define MG_TILE (MG_WINS * 32)
-#define MG_CAP (MG_TILE + TK_TILE_MAX)      // ranks a tile can produce (pieces that start in it)
-#define MG_QCAP (MG_TILE / 2 + 4)
-#define MG_PCAP (MG_TILE + 4)               // pieces that can start in a tile (+ the end sentinel)
+#define LK_T 256
+#define LK_WINS 128
+#define LK_TILE (LK_WINS * 32)
+#define LK_CAP (LK_TILE + TK_LANE_MAX)      // slots a tile can need (pieces that start in it)
+#define LK_PCAP (LK_TILE + 4)               // pieces that can start in a tile (+ the end sentinel)
 #define EN_LAST 0x80000000u
-#define EN_LONG 0xFFFFFFFFu
-#define MG_DEAD TK_LANE_DEAD
+#define LK_MISS 0x40000000u
+#define LK_NONE 0xFFFFFFFFu
+#define QE_START_BITS 40
+#define QE_LEN_BITS 7
 
-struct MgSmem {
-    uint8_t bytes[MG_TILE + TK_TILE_MAX + 16];
-    uint32_t stage[MG_CAP];    // ids of the parts of every piece, at the piece's byte offset (MG_DEAD = merged away)
-    uint32_t rk[MG_CAP];       // C: pair keys (tk_bpe_merge_loop); rank count of a piece at its start; D: compacted ranks
-    uint32_t mask[MG_WINS + 4];
-    uint16_t list[MG_PCAP];    // tile-relative starts of all pieces, in order
-    union {
-        uint32_t missq[MG_QCAP];   // B: pieces that need merging: start | len << 16, in discovery order
-        uint16_t poff[MG_PCAP];    // D: offset of every piece's ranks in the tile's compacted output
-    };
-    union {
-        uint16_t queue[MG_QCAP];   // C: the misses, longest first
-        uint8_t pcnt[MG_PCAP];     // D: ranks of every piece
-    };
-    uint32_t hist[TK_TILE_MAX + 2];
-    uint32_t pfx[MG_WINS + 1];     // index of the first piece of every window
-    uint32_t wsum[MG_T / 32];
-    uint32_t n_pieces, n_miss, q_pop;
+__host__ __device__ __forceinline__ uint32_t lane_class(uint32_t len) {        // 2..4, 5..8, 9..16, 17..32, 33..64
+    return len <= 4u ? 0u : len <= 8u ? 1u : len <= 16u ? 2u : len <= 32u ? 3u : 4u;
+}
+
+struct LkSmem {
+    uint8_t bytes[LK_TILE + TK_LANE_MAX + 16];
+    uint32_t mask[LK_WINS + 4];
+    uint16_t list[LK_PCAP];     // tile-relative starts of all pieces, in order
+    uint32_t ptk[LK_PCAP];      // per piece: rank | EN_LAST (vocabulary entry), len | LK_MISS, or LK_NONE (no slots)
+    uint16_t poff[LK_PCAP];     // first slot of every piece
+    uint32_t comp[LK_CAP];      // the tile's slots
+    uint32_t pfx[LK_WINS + 1];  // index of the first piece of every window
+    uint32_t wsum[LK_T / 32];
+    uint32_t cls_n[TKK_N_CLASSES], cls_base[TKK_N_CLASSES], cls_pos[TKK_N_CLASSES];
+    uint32_t n_pieces;
 };
 
 // tile-relative end of the piece that starts at tile-relative byte s (the next set bit of the start
@@ -686,8 +583,8 @@ __device__ __forceinline__ uint32_t en_piece_end(const uint32_t* mask, uint32_t 
     return 0xFFFFFFFFu;
 }
 
-// block-wide exclusive prefix of one value per thread (MG_T threads); *total = sum over the block
-__device__ __forceinline__ uint32_t mg_block_excl(uint32_t v, uint32_t* wsum, uint32_t* total) {
+// block-wide exclusive prefix of one value per thread (LK_T threads); *total = sum over the block
+__device__ __forceinline__ uint32_t lk_block_excl(uint32_t v, uint32_t* wsum, uint32_t* total) {
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     uint32_t inc = v;
 #pragma unroll
@@ -700,37 +597,39 @@ __device__ __forceinline__ uint32_t mg_block_excl(uint32_t v, uint32_t* wsum, ui
     __syncthreads();
     uint32_t before = 0, all = 0;
 #pragma unroll
-    for (int w = 0; w < MG_T / 32; ++w) { if (w < (int)warp) before += wsum[w]; all += wsum[w]; }
+    for (int w = 0; w < LK_T / 32; ++w) { if (w < (int)warp) before += wsum[w]; all += wsum[w]; }
     *total = all;
     return before + inc - v;
 }
 
-__global__ void __launch_bounds__(MG_T) merge_kernel(const uint8_t* __restrict__ data, uint64_t n,
-                                                     const uint32_t* __restrict__ start_mask, TkDeviceTables T,
-                                                     uint32_t* __restrict__ stream, uint32_t* __restrict__ win_info) {
-    __shared__ __align__(16) MgSmem S;
+__global__ void __launch_bounds__(LK_T) lookup_kernel(const uint8_t* __restrict__ data, uint64_t n,
+                                                      const uint32_t* __restrict__ start_mask, TkDeviceTables T,
+                                                      uint32_t* __restrict__ stream, uint32_t* __restrict__ win_info,
+                                                      unsigned long long* __restrict__ queues, TkkQueueLayout Q,
+                                                      uint32_t* __restrict__ q_n) {
+    extern __shared__ __align__(16) unsigned char lk_raw[];
+    LkSmem& S = *reinterpret_cast<LkSmem*>(lk_raw);
     const uint32_t t = threadIdx.x, lane = t & 31u;
     const uint32_t tile = blockIdx.x;
-    const uint64_t tile_pos = (uint64_t)tile * MG_TILE;
-    const uint64_t win0 = (uint64_t)tile * MG_WINS;
-    if (t == 0) S.n_miss = S.q_pop = 0;
-    if (t < TK_TILE_MAX + 2) S.hist[t] = 0;
+    const uint64_t tile_pos = (uint64_t)tile * LK_TILE;
+    const uint64_t win0 = (uint64_t)tile * LK_WINS;
+    if (t < TKK_N_CLASSES) { S.cls_n[t] = 0; S.cls_pos[t] = 0; }
     // ---- A: stage bytes and mask words; list the piece starts ----
     {
         const uint64_t avail = n > tile_pos ? n - tile_pos : 0;
-        const uint32_t want = MG_TILE + TK_TILE_MAX + 16;
+        const uint32_t want = LK_TILE + TK_LANE_MAX + 16;
         const uint32_t full16 = (uint32_t)((avail < want ? avail : want) / 16);
         uint4* dst = reinterpret_cast<uint4*>(S.bytes);
         const uint4* src = reinterpret_cast<const uint4*>(data + tile_pos);
-        for (uint32_t i = t; i < full16; i += MG_T) dst[i] = __ldg(src + i);
-        for (uint32_t i = full16 * 16 + t; i < want; i += MG_T) S.bytes[i] = (tile_pos + i < n) ? data[tile_pos + i] : 0;
+        for (uint32_t i = t; i < full16; i += LK_T) dst[i] = __ldg(src + i);
+        for (uint32_t i = full16 * 16 + t; i < want; i += LK_T) S.bytes[i] = (tile_pos + i < n) ? data[tile_pos + i] : 0;
         uint32_t m = 0;
-        if (t < MG_WINS + 4) { m = start_mask[win0 + t]; S.mask[t] = m; }
-        if (t >= MG_WINS) m = 0;
+        if (t < LK_WINS + 4) { m = start_mask[win0 + t]; S.mask[t] = m; }
+        if (t >= LK_WINS) m = 0;
         uint32_t np;
-        uint32_t o = mg_block_excl((uint32_t)__popc(m), S.wsum, &np);
-        if (t < MG_WINS) S.pfx[t] = o;
-        if (t == 0) { S.pfx[MG_WINS] = np; S.n_pieces = np; }
+        uint32_t o = lk_block_excl((uint32_t)__popc(m), S.wsum, &np);
+        if (t < LK_WINS) S.pfx[t] = o;
+        if (t == 0) { S.pfx[LK_WINS] = np; S.n_pieces = np; }
         while (m) {
             S.list[o++] = (uint16_t)(t * 32u + (uint32_t)(__ffs((int)m) - 1));
             m &= m - 1;
@@ -739,130 +638,133 @@ __global__ void __launch_bounds__(MG_T) merge_kernel(const uint8_t* __restrict__
     __syncthreads();
     const uint32_t np = S.n_pieces;
 
-    // ---- B: one lane per piece: whole-piece vocabulary lookup; misses are collected ----
-    for (uint32_t k0 = 0; k0 < np; k0 += MG_T) {
+    // ---- B: one lane per piece: whole-piece vocabulary lookup ----
+    for (uint32_t k0 = 0; k0 < np; k0 += LK_T) {
         const uint32_t k = k0 + t;
-        bool miss = false;
-        uint32_t s = 0, len = 0;
+        uint32_t cls = 0xFFFFFFFFu;
         if (k < np) {
-            s = S.list[k];
+            const uint32_t s = S.list[k];
+            uint32_t v = LK_NONE;
             if (tile_pos + s < n) {                        // the end-of-data sentinel is not a piece
                 const uint32_t e = en_piece_end(S.mask, s);
-                if (e == 0xFFFFFFFFu || e - s > TK_TILE_MAX) S.stage[s] = EN_LONG;   // merged by K3 / K3m
-                else {
-                    len = e - s;
+                if (e != 0xFFFFFFFFu && e - s <= TK_LANE_MAX) {         // longer pieces: K3
+                    const uint32_t len = e - s;
                     const uint32_t whole = tk_vocab_lookup_w32(T, S.bytes, s, len);
-                    if (whole != TK_INF) { S.stage[s] = whole | EN_LAST; S.rk[s] = 1; }
-                    else if (len == 1) { S.stage[s] = (uint32_t)S.bytes[s] | EN_LAST; S.rk[s] = 1; }
-                    else miss = true;
+                    if (whole != TK_INF) v = whole | EN_LAST;
+                    else if (len == 1) v = (uint32_t)S.bytes[s] | EN_LAST;
+                    else { v = len | LK_MISS; cls = lane_class(len); }
                 }
             }
+            S.ptk[k] = v;
         }
-        const uint32_t mm = __ballot_sync(0xFFFFFFFFu, miss);
-        if (mm) {
-            uint32_t base = 0;
-            const int leader = __ffs((int)mm) - 1;
-            if ((int)lane == leader) base = atomicAdd(&S.n_miss, (uint32_t)__popc(mm));
-            base = __shfl_sync(0xFFFFFFFFu, base, leader);
-            if (miss) {
-                S.missq[base + (uint32_t)__popc(mm & ((1u << lane) - 1u))] = s | (len << 16);
-                atomicAdd(&S.hist[len], 1u);
+        // misses per length class (one shared-memory atomic per class per warp)
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, cls);
+        if (cls != 0xFFFFFFFFu && (uint32_t)(__ffs((int)peers) - 1) == lane) atomicAdd(&S.cls_n[cls], (uint32_t)__popc(peers));
+    }
+    __syncthreads();
+    if (t < TKK_N_CLASSES && S.cls_n[t]) S.cls_base[t] = atomicAdd(q_n + t, S.cls_n[t]);   // this tile's range of every queue
+    // ---- C: slots of every piece: exclusive prefix over the pieces ----
+    uint32_t tile_total;
+    {
+        const uint32_t per = (np + LK_T - 1) / LK_T;
+        const uint32_t lo = t * per < np ? t * per : np, hi = lo + per < np ? lo + per : np;
+        uint32_t sum = 0;
+        for (uint32_t k = lo; k < hi; ++k) {
+            const uint32_t v = S.ptk[k];
+            sum += v == LK_NONE ? 0u : (v & EN_LAST) ? 1u : (v & 0xFFu);
+        }
+        uint32_t o = lk_block_excl(sum, S.wsum, &tile_total);
+        for (uint32_t k = lo; k < hi; ++k) {
+            const uint32_t v = S.ptk[k];
+            S.poff[k] = (uint16_t)o;
+            o += v == LK_NONE ? 0u : (v & EN_LAST) ? 1u : (v & 0xFFu);
+        }
+        if (t == 0) S.poff[np] = (uint16_t)tile_total;
+    }
+    __syncthreads();
+    // ---- D: vocabulary entries into their slots, misses into the queues ----
+    for (uint32_t k0 = 0; k0 < np; k0 += LK_T) {
+        const uint32_t k = k0 + t;
+        uint32_t cls = 0xFFFFFFFFu, v = LK_NONE;
+        if (k < np) {
+            v = S.ptk[k];
+            if (v != LK_NONE) {
+                if (v & EN_LAST) S.comp[S.poff[k]] = v;
+                else cls = lane_class(v & 0xFFu);
             }
         }
-    }
-    __syncthreads();
-    // order the misses longest first (counting sort on the length): the lanes of a warp then work
-    // on pieces of about the same length, and the longest pieces start first
-    const uint32_t qn = S.n_miss;
-    if (t < 32) {
-        const int L = TK_TILE_MAX - (int)lane;              // lane 0 = longest; lengths 32 .. 1
-        const uint32_t c = L >= 2 ? S.hist[L] : 0u;
-        uint32_t inc = c;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-            if ((int)lane >= d) inc += o;
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, cls);
+        if (cls != 0xFFFFFFFFu) {
+            const int leader = __ffs((int)peers) - 1;
+            uint32_t base = 0;
+            if ((int)lane == leader) base = atomicAdd(&S.cls_pos[cls], (uint32_t)__popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            const uint32_t pos = S.cls_base[cls] + base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+            const unsigned long long e = (tile_pos + S.list[k]) | ((unsigned long long)(v & 0xFFu) << QE_START_BITS) |
+                                         ((unsigned long long)S.poff[k] << (QE_START_BITS + QE_LEN_BITS));
+            queues[Q.off[cls] + pos] = e;
         }
-        if (L >= 2) S.hist[L] = inc - c;
     }
+    if (t < LK_WINS) win_info[win0 + t] = S.poff[S.pfx[t]];
     __syncthreads();
-    for (uint32_t k = t; k < qn; k += MG_T) {
-        const uint32_t e = S.missq[k];
-        S.queue[atomicAdd(&S.hist[e >> 16], 1u)] = (uint16_t)(e & 0xFFFFu);
-    }
-    __syncthreads();
+    uint32_t* dst = stream + (uint64_t)tile * LK_CAP;
+    for (uint32_t i = t; i < tile_total; i += LK_T) dst[i] = S.comp[i];
+}
 
-    // ---- C: exact byte_pair_merge, one lane per piece, a warp takes 32 queue entries at a time ----
+template <int MAXLEN, int THREADS>
+__global__ void __launch_bounds__(THREADS) lanemerge_kernel(const uint8_t* __restrict__ data, TkDeviceTables T,
+                                                            const unsigned long long* __restrict__ queue,
+                                                            const uint32_t* __restrict__ q_n, uint32_t* __restrict__ q_w,
+                                                            uint32_t* __restrict__ stream) {
+    constexpr int STRIDE = MAXLEN + 1;      // odd: lane i's arrays start at bank i (no conflicts when lanes sweep together)
+    extern __shared__ __align__(16) uint32_t lm_raw[];
+    uint32_t* id = lm_raw + threadIdx.x * STRIDE;
+    uint32_t* key = lm_raw + THREADS * STRIDE + threadIdx.x * STRIDE;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t total = *q_n;
     for (;;) {
         uint32_t k = 0;
-        if (lane == 0) k = atomicAdd(&S.q_pop, 32u);
+        if (lane == 0) k = atomicAdd(q_w, 32u);
         k = __shfl_sync(0xFFFFFFFFu, k, 0);
-        if (k >= qn) break;
+        if (k >= total) break;
         k += lane;
-        if (k < qn) {
-            const uint32_t s = S.queue[k];
-            const uint32_t len = en_piece_end(S.mask, s) - s;
-            uint32_t* id = S.stage + s;
-            uint32_t* key = S.rk + s;
-            const uint8_t* b = S.bytes + s;
+        if (k < total) {
+            const unsigned long long e = queue[k];
+            const uint64_t start = e & ((1ull << QE_START_BITS) - 1ull);
+            const uint32_t len = (uint32_t)(e >> QE_START_BITS) & ((1u << QE_LEN_BITS) - 1u);
+            const uint32_t off = (uint32_t)(e >> (QE_START_BITS + QE_LEN_BITS));
+            const uint8_t* b = data + start;
+            for (uint32_t i = 0; i < len; i += 4) {
+                uint32_t v[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) v[c] = i + c < len ? (uint32_t)__ldg(b + i + c) : 0u;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) if (i + c < len) id[i + c] = v[c];
+            }
             // parts = single bytes; rank of every adjacent byte pair from the direct table
             for (uint32_t i = 0; i < len; i += 4) {
                 uint32_t r4[4];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const uint32_t j = i + c;
-                    r4[c] = j + 1 < len ? __ldg(T.byte_pair + (((uint32_t)b[j] << 8) | b[j + 1])) : TK_INF;
+                    r4[c] = j + 1 < len ? __ldg(T.byte_pair + ((id[j] << 8) | id[j + 1])) : TK_INF;
                 }
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const uint32_t j = i + c;
-                    if (j < len) { id[j] = b[j]; key[j] = r4[c] == TK_INF ? TK_INF : ((r4[c] << 6) | j); }
+                    if (j < len) key[j] = r4[c] == TK_INF ? TK_INF : ((r4[c] << 6) | j);
                 }
             }
-            const unsigned long long live = tk_bpe_merge_loop(T, len, id, key);
-            id[63 - __clzll((long long)live)] |= EN_LAST;
-            key[0] = (uint32_t)__popcll(live);
+            unsigned long long live = tk_bpe_merge_loop(T, len, id, key);
+            uint32_t* dst = stream + (start / LK_TILE) * (uint64_t)LK_CAP + off;
+            while (live) {
+                const uint32_t j = (uint32_t)(__ffsll((long long)live) - 1);
+                live &= live - 1;
+                *dst++ = live ? id[j] : (id[j] | EN_LAST);
+            }
         }
         __syncwarp();
     }
-    __syncthreads();
-
-    // ---- D: compact the tile's ranks (one lane per piece) and write them to its slot of the stream ----
-    for (uint32_t k = t; k < np; k += MG_T) {
-        const uint32_t s = S.list[k];
-        S.pcnt[k] = (tile_pos + s >= n || S.stage[s] == EN_LONG) ? 0u : (uint8_t)S.rk[s];
-    }
-    __syncthreads();          // every count in S.rk has been read: S.rk becomes the compaction buffer
-    uint32_t tile_total;
-    {
-        const uint32_t per = (np + MG_T - 1) / MG_T;
-        const uint32_t lo = t * per < np ? t * per : np, hi = lo + per < np ? lo + per : np;
-        uint32_t sum = 0;
-        for (uint32_t k = lo; k < hi; ++k) sum += S.pcnt[k];
-        uint32_t o = mg_block_excl(sum, S.wsum, &tile_total);
-        for (uint32_t k = lo; k < hi; ++k) { S.poff[k] = (uint16_t)o; o += S.pcnt[k]; }
-        if (t == 0) S.poff[np] = (uint16_t)tile_total;
-    }
-    __syncthreads();
-    uint32_t* comp = S.rk;
-    for (uint32_t k = t; k < np; k += MG_T) {
-        if (!S.pcnt[k]) continue;
-        const uint32_t s = S.list[k];
-        uint32_t o = S.poff[k];
-        for (uint32_t j = 0;; ++j) {
-            const uint32_t v = S.stage[s + j];
-            if (v == MG_DEAD) continue;
-            comp[o++] = v;
-            if (v & EN_LAST) break;
-        }
-    }
-    if (t < MG_WINS) {
-        const uint32_t o0 = S.poff[S.pfx[t]], o1 = S.poff[S.pfx[t + 1]];
-        win_info[win0 + t] = o0 | ((o1 - o0) << 16);
-    }
-    __syncthreads();
-    uint32_t* dst = stream + (uint64_t)tile * MG_CAP;
-    for (uint32_t i = t; i < tile_total; i += MG_T) dst[i] = comp[i];
 }
 
 // =====================================================================================================
@@ -903,6 +805,16 @@ __device__ __forceinline__ uint64_t docs_at(const uint64_t* __restrict__ doc_off
     return e - lo;
 }
 
+// length of the piece that starts at bit `bit` of window gw (not a long piece: the next start is at most
+// two words away)
+__device__ __forceinline__ uint32_t em_piece_len(const uint32_t* __restrict__ start_mask, uint64_t gw, uint32_t mymask, uint32_t bit) {
+    const uint32_t m = bit == 31u ? 0u : (mymask >> (bit + 1u));
+    if (m) return (uint32_t)__ffs((int)m);
+    const uint32_t m1 = start_mask[gw + 1];
+    if (m1) return 32u - bit + (uint32_t)(__ffs((int)m1) - 1);
+    return 64u - bit + (uint32_t)(__ffs((int)start_mask[gw + 2]) - 1);
+}
+
 __global__ void __launch_bounds__(EM_T) emit_kernel(uint64_t n, const uint32_t* __restrict__ start_mask,
                                                     const uint32_t* __restrict__ ds_mask, const uint32_t* __restrict__ long_of_word,
                                                     const TkkLongRec* __restrict__ recs, const uint32_t* __restrict__ pool,
@@ -922,20 +834,31 @@ __global__ void __launch_bounds__(EM_T) emit_kernel(uint64_t n, const uint32_t* 
     const uint32_t tile = S.tile;
     const uint64_t gw = (uint64_t)tile * EM_WINS + t;       // my window
     const uint64_t wpos = gw * 32u;
-    const uint32_t mymask = start_mask[gw], myds = ds_mask[gw], info = win_info[gw];
+    const uint32_t mymask = start_mask[gw], myds = ds_mask[gw];
     const uint32_t lw = mymask ? long_of_word[gw] : 0u;     // != 0: a long piece starts at my top set bit
     const uint32_t topbit = mymask ? 31u - (uint32_t)__clz((int)mymask) : 32u;
+    const uint32_t* src0 = stream + (gw / LK_WINS) * (uint64_t)LK_CAP + (mymask ? win_info[gw] : 0u);
     // ---- tokens of my window ----
-    uint32_t count = info >> 16;
-    if (lw) count += recs[lw - 1].count;
+    uint32_t count = 0;
     {
-        uint32_t m = mymask & myds;
+        const uint32_t* src = src0;
+        uint32_t m = mymask;
         while (m) {
             const uint32_t bit = (uint32_t)(__ffs((int)m) - 1);
             m &= m - 1;
-            uint64_t first;
-            const uint64_t k = docs_at(doc_off, n_docs, wpos + bit, &first);
-            for (uint64_t d = first; d < first + k; ++d) count += (d > 0 ? add_eos : 0u) + (d < n_docs ? add_bos : 0u);
+            const uint64_t gpos = wpos + bit;
+            if ((myds >> bit) & 1u) {
+                uint64_t first;
+                const uint64_t k = docs_at(doc_off, n_docs, gpos, &first);
+                for (uint64_t d = first; d < first + k; ++d) count += (d > 0 ? add_eos : 0u) + (d < n_docs ? add_bos : 0u);
+            }
+            if (gpos >= n) continue;                        // the end-of-data sentinel is not a piece
+            if (lw && bit == topbit) { count += recs[lw - 1].count; continue; }
+            if (__ldg(src) & EN_LAST) { count += 1; src += 1; continue; }
+            uint32_t c = 1;
+            while (!(__ldg(src + c) & EN_LAST)) ++c;
+            count += c + 1;
+            src += em_piece_len(start_mask, gw, mymask, bit);
         }
     }
     uint32_t inc = count;
@@ -967,7 +890,7 @@ __global__ void __launch_bounds__(EM_T) emit_kernel(uint64_t n, const uint32_t* 
     uint32_t* comp = S.comp;
     {
         uint64_t o = my_off;
-        const uint32_t* src = stream + (gw / MG_WINS) * (uint64_t)MG_CAP + (info & 0xFFFFu);
+        const uint32_t* src = src0;
         uint32_t m = mymask;
         while (m) {
             const uint32_t bit = (uint32_t)(__ffs((int)m) - 1);
@@ -1002,13 +925,17 @@ __global__ void __launch_bounds__(EM_T) emit_kernel(uint64_t n, const uint32_t* 
                 o += r.count;
                 continue;
             }
+            const uint32_t* p = src;
+            bool first_tok = true, hit = false;
             for (;;) {
-                const uint32_t v = __ldg(src++);
+                const uint32_t v = __ldg(p++);
+                if (first_tok) { hit = (v & EN_LAST) != 0u; first_tok = false; }
                 const uint32_t idv = (v & ~EN_LAST) + nsp;
                 if (fits) comp[o] = idv; else if (base + o < out_cap) out[base + o] = idv;
                 ++o;
                 if (v & EN_LAST) break;
             }
+            src += hit ? 1u : em_piece_len(start_mask, gw, mymask, bit);
         }
     }
     __syncthreads();
@@ -1045,13 +972,18 @@ size_t encode_workspace_bytes(uint64_t n, uint64_t n_docs, EncodeLayout* L) {
     l.off_summ = take(n_tiles * sizeof(TkkTileSummary));
     l.off_carry = take(n_tiles * 4);
     l.off_worklist = take(n_tiles * 4);
-    l.n_mtiles = n_tiles * (PT_T / MG_WINS);           // merge tiles cover exactly the emit tiles
+    l.n_ltiles = n_tiles * (PT_T / LK_WINS);            // lookup tiles cover exactly the emit tiles
     l.off_tilestate = take(n_tiles * 8);
     l.off_wininfo = take(words * 4);
-    l.off_stream = take(l.n_mtiles * (size_t)MG_CAP * 4);
-    l.off_longlist = take((n / (TK_TILE_MAX + 1) + 2) * 4);
-    l.off_medq = take((n / (TK_TILE_MAX + 1) + 2) * 4 * MD_CLASSES);
-    l.max_long = n / (TK_TILE_MAX + 1) + 2;
+    l.off_stream = take(l.n_ltiles * (size_t)LK_CAP * 4);
+    {
+        // a queue per length class; a class whose shortest piece has m bytes holds at most n/m + 1 pieces
+        const uint32_t shortest[TKK_N_CLASSES] = {2, 5, 9, 17, 33};
+        uint64_t e = 0;
+        for (int c = 0; c < TKK_N_CLASSES; ++c) { l.queues.off[c] = e; e += n / shortest[c] + 32; }
+        l.off_queues = take(e * 8);
+    }
+    l.max_long = n / (TK_LANE_MAX + 1) + 2;
     l.off_recs = take(l.max_long * sizeof(TkkLongRec));
     l.off_huge = take(l.max_long * 4);
     l.off_pool = take((n + 16) * 4);
@@ -1062,6 +994,23 @@ size_t encode_workspace_bytes(uint64_t n, uint64_t n_docs, EncodeLayout* L) {
 }
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
+
+template <int MAXLEN, int THREADS>
+static cudaError_t launch_lanemerge(int blocks_per_sm, int sm_count, const uint8_t* d_data, const TkDeviceTables& T,
+                                    const unsigned long long* queue, const uint32_t* q_n, uint32_t* q_w, uint32_t* stream,
+                                    cudaStream_t st) {
+    const size_t smem = (size_t)2 * THREADS * (MAXLEN + 1) * sizeof(uint32_t);
+    static std::atomic<uint64_t> attr_set{0};   // bit per device ordinal
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (!((attr_set.load() >> (dev & 63)) & 1ull)) {
+        CK(cudaFuncSetAttribute(lanemerge_kernel<MAXLEN, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set.fetch_or(1ull << (dev & 63));
+    }
+    lanemerge_kernel<MAXLEN, THREADS><<<(unsigned)(sm_count * blocks_per_sm), THREADS, smem, st>>>(d_data, T, queue, q_n, q_w, stream);
+    count_launch();
+    return cudaSuccess;
+}
 
 cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const uint64_t* d_doc_off, uint64_t n_docs,
                           uint64_t n, int add_bos, int add_eos, uint32_t* d_out, uint64_t out_cap, uint64_t* d_tok_off,
@@ -1081,8 +1030,7 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
     uint32_t* pool = (uint32_t*)(ws + L.off_pool);
     uint32_t* win_info = (uint32_t*)(ws + L.off_wininfo);
     uint32_t* stream = (uint32_t*)(ws + L.off_stream);
-    uint32_t* long_list = (uint32_t*)(ws + L.off_longlist);
-    uint32_t* med_q = (uint32_t*)(ws + L.off_medq);
+    unsigned long long* queues = (unsigned long long*)(ws + L.off_queues);
     // small block layout
     uint32_t* flags = small + TKK_S_FLAGS;
     unsigned long long* err_pos = (unsigned long long*)(small + TKK_S_ERRPOS);
@@ -1092,9 +1040,8 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
     uint32_t* wc_long = small + TKK_S_WC_LONG;
     uint32_t* wc_huge = small + TKK_S_WC_HUGE;
     uint32_t* ticket = small + TKK_S_TICKET;
-    uint32_t* n_longonly = small + TKK_S_NLONGONLY;
-    uint32_t* med_n = small + TKK_S_MEDN;
-    uint32_t* med_w = small + TKK_S_MEDW;
+    uint32_t* q_n = small + TKK_S_QN;
+    uint32_t* q_w = small + TKK_S_QW;
     unsigned long long* pool_cursor = (unsigned long long*)(small + TKK_S_POOLCUR);
     unsigned long long* scratch_cursor = (unsigned long long*)(small + TKK_S_SCRCUR);
     unsigned long long* total_out = (unsigned long long*)(small + TKK_S_TOTAL);
@@ -1117,38 +1064,39 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
         d_data, n, ds, start, L.n_windows, T, carry, worklist, work_count, err_pos);
     TK_LAUNCHED();
     if (timer) timer->mark(st, "longmark");
-    longmark_kernel<<<(unsigned)ceil_div(L.n_windows, 256), 256, 0, st>>>(start, L.n_windows, n, longword, recs, n_long, long_list,
-                                                                          n_longonly, med_q, L.max_long, med_n, pool_cursor);
+    longmark_kernel<<<(unsigned)ceil_div(L.n_windows, 256), 256, 0, st>>>(start, L.n_windows, n, longword, recs, n_long);
     TK_LAUNCHED();
     if (timer) timer->mark(st, "longmerge");
     {
         uint64_t blocks = ceil_div(L.max_long, LM_WARPS);
         const uint64_t cap = (uint64_t)sm_count * 12;
         if (blocks > cap) blocks = cap;
-        longmerge_warp_kernel<<<(unsigned)blocks, LM_WARPS * 32, 0, st>>>(d_data, start, T, recs, long_list, n_longonly, pool,
-                                                                        pool_cursor, huge, n_huge, wc_long);
+        longmerge_warp_kernel<<<(unsigned)blocks, LM_WARPS * 32, 0, st>>>(d_data, start, T, recs, n_long, pool, pool_cursor, huge,
+                                                                        n_huge, wc_long);
         TK_LAUNCHED();
         uint64_t hb = L.max_long < (uint64_t)(2 * sm_count) ? L.max_long : (uint64_t)(2 * sm_count);
         longmerge_block_kernel<<<(unsigned)hb, HG_T, 0, st>>>(d_data, T, recs, huge, n_huge, pool, d_scratch, scratch_cap,
                                                              scratch_cursor, wc_huge, flags);
         TK_LAUNCHED();
     }
-    if (timer) timer->mark(st, "medmerge");
+    if (timer) timer->mark(st, "lookup");
     {
-        const size_t smem = (size_t)2 * MD_T * MD_STRIDE * sizeof(uint32_t);
         static std::atomic<uint64_t> attr_set{0};   // bit per device ordinal
         int dev = 0;
         CK(cudaGetDevice(&dev));
         if (!((attr_set.load() >> (dev & 63)) & 1ull)) {
-            CK(cudaFuncSetAttribute(medmerge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LkSmem)));
             attr_set.fetch_or(1ull << (dev & 63));
         }
-        medmerge_kernel<<<(unsigned)(sm_count * 3), MD_T, smem, st>>>(d_data, T, recs, med_q, L.max_long, med_n, med_w, pool);
+        lookup_kernel<<<(unsigned)L.n_ltiles, LK_T, sizeof(LkSmem), st>>>(d_data, n, start, T, stream, win_info, queues, L.queues, q_n);
         TK_LAUNCHED();
     }
-    if (timer) timer->mark(st, "merge");
-    merge_kernel<<<(unsigned)L.n_mtiles, MG_T, 0, st>>>(d_data, n, start, T, stream, win_info);
-    TK_LAUNCHED();
+    if (timer) timer->mark(st, "lanemerge");
+    CK((launch_lanemerge<64, 128>(3, sm_count, d_data, T, queues + L.queues.off[4], q_n + 4, q_w + 4, stream, st)));
+    CK((launch_lanemerge<32, 256>(3, sm_count, d_data, T, queues + L.queues.off[3], q_n + 3, q_w + 3, stream, st)));
+    CK((launch_lanemerge<16, 256>(6, sm_count, d_data, T, queues + L.queues.off[2], q_n + 2, q_w + 2, stream, st)));
+    CK((launch_lanemerge<8, 256>(8, sm_count, d_data, T, queues + L.queues.off[1], q_n + 1, q_w + 1, stream, st)));
+    CK((launch_lanemerge<4, 256>(8, sm_count, d_data, T, queues + L.queues.off[0], q_n + 0, q_w + 0, stream, st)));
     if (timer) timer->mark(st, "emit");
     static_assert(EM_WINS == PT_T, "emit tiles are the pre-tokeniser's tiles");
     emit_kernel<<<(unsigned)L.n_tiles, EM_T, 0, st>>>(n, start, ds, longword, recs, pool, stream, win_info, d_doc_off, n_docs,

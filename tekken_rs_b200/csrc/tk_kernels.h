@@ -32,9 +32,13 @@ enum {
     TKK_S_SCRCUR = 12,   // u64
     TKK_S_TOTAL = 14,    // u64
     TKK_S_BADDOC = 16,   // u64 (decode)
-    TKK_S_NLONGONLY = 18,
-    TKK_S_MEDN = 20,     // 4 counters: medium pieces per length class
-    TKK_S_MEDW = 24,     // 4 work counters
+    TKK_S_QN = 20,       // TKK_N_CLASSES counters: queued pieces per length class
+    TKK_S_QW = 26,       // TKK_N_CLASSES work counters
+};
+
+#define TKK_N_CLASSES 5
+struct TkkQueueLayout {
+    uint64_t off[TKK_N_CLASSES];   // first entry of every class in the queue array
 };
 
 struct TkkTileSummary {
@@ -52,9 +56,10 @@ struct TkkLongRec {
 };
 
 struct EncodeLayout {
-    uint64_t n_windows, n_tiles, n_mtiles, mask_words, max_long;
+    uint64_t n_windows, n_tiles, n_ltiles, mask_words, max_long;
+    TkkQueueLayout queues;
     size_t off_small, off_ds, off_start, off_longword, off_summ, off_carry, off_worklist, off_tilestate, off_recs,
-        off_huge, off_pool, off_wininfo, off_stream, off_longlist, off_medq, total;
+        off_huge, off_pool, off_wininfo, off_stream, off_queues, total;
 };
 
 struct DecodeLayout {
