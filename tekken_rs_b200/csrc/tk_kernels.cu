@@ -562,7 +562,6 @@ struct LkSmem {
     uint16_t list[LK_PCAP];     // tile-relative starts of all pieces, in order
     uint32_t ptk[LK_PCAP];      // per piece: rank | EN_LAST (vocabulary entry), len | LK_MISS, or LK_NONE (no slots)
     uint16_t poff[LK_PCAP];     // first slot of every piece
-    uint32_t comp[LK_CAP];      // the tile's slots
     uint32_t pfx[LK_WINS + 1];  // index of the first piece of every window
     uint32_t wsum[LK_T / 32];
     uint32_t cls_n[TKK_N_CLASSES], cls_base[TKK_N_CLASSES], cls_pos[TKK_N_CLASSES];
@@ -663,6 +662,7 @@ __global__ void __launch_bounds__(LK_T) lookup_kernel(const uint8_t* __restrict_
     }
     __syncthreads();
     if (t < TKK_N_CLASSES && S.cls_n[t]) S.cls_base[t] = atomicAdd(q_n + t, S.cls_n[t]);   // this tile's range of every queue
+    uint32_t* dst = stream + (uint64_t)tile * LK_CAP;
     // ---- C: slots of every piece: exclusive prefix over the pieces ----
     uint32_t tile_total;
     {
@@ -689,7 +689,7 @@ __global__ void __launch_bounds__(LK_T) lookup_kernel(const uint8_t* __restrict_
         if (k < np) {
             v = S.ptk[k];
             if (v != LK_NONE) {
-                if (v & EN_LAST) S.comp[S.poff[k]] = v;
+                if (v & EN_LAST) dst[S.poff[k]] = v;
                 else cls = lane_class(v & 0xFFu);
             }
         }
@@ -705,17 +705,23 @@ __global__ void __launch_bounds__(LK_T) lookup_kernel(const uint8_t* __restrict_
             queues[Q.off[cls] + pos] = e;
         }
     }
-    if (t < LK_WINS) win_info[win0 + t] = S.poff[S.pfx[t]];
-    __syncthreads();
-    uint32_t* dst = stream + (uint64_t)tile * LK_CAP;
-    for (uint32_t i = t; i < tile_total; i += LK_T) dst[i] = S.comp[i];
+    // per window: first slot | number of vocabulary-entry pieces << 16 (K2m adds the ranks of the merged pieces)
+    if (t < LK_WINS) {
+        uint32_t hits = 0;
+        for (uint32_t k = S.pfx[t]; k < S.pfx[t + 1]; ++k) {
+            const uint32_t v = S.ptk[k];
+            hits += (v != LK_NONE && (v & EN_LAST)) ? 1u : 0u;
+        }
+        win_info[win0 + t] = S.poff[S.pfx[t]] | (hits << 16);
+    }
+    (void)tile_total;
 }
 
 template <int MAXLEN, int THREADS>
 __global__ void __launch_bounds__(THREADS) lanemerge_kernel(const uint8_t* __restrict__ data, TkDeviceTables T,
                                                             const unsigned long long* __restrict__ queue,
                                                             const uint32_t* __restrict__ q_n, uint32_t* __restrict__ q_w,
-                                                            uint32_t* __restrict__ stream) {
+                                                            uint32_t* __restrict__ stream, uint32_t* __restrict__ win_info) {
     constexpr int STRIDE = MAXLEN + 1;      // odd: lane i's arrays start at bank i (no conflicts when lanes sweep together)
     extern __shared__ __align__(16) uint32_t lm_raw[];
     uint32_t* id = lm_raw + threadIdx.x * STRIDE;
@@ -757,6 +763,7 @@ __global__ void __launch_bounds__(THREADS) lanemerge_kernel(const uint8_t* __res
             }
             unsigned long long live = tk_bpe_merge_loop(T, len, id, key);
             uint32_t* dst = stream + (start / LK_TILE) * (uint64_t)LK_CAP + off;
+            atomicAdd(win_info + (start >> 5), (uint32_t)__popcll(live) << 16);        // ranks of the window the piece starts in
             while (live) {
                 const uint32_t j = (uint32_t)(__ffsll((long long)live) - 1);
                 live &= live - 1;
@@ -837,28 +844,19 @@ __global__ void __launch_bounds__(EM_T) emit_kernel(uint64_t n, const uint32_t* 
     const uint32_t mymask = start_mask[gw], myds = ds_mask[gw];
     const uint32_t lw = mymask ? long_of_word[gw] : 0u;     // != 0: a long piece starts at my top set bit
     const uint32_t topbit = mymask ? 31u - (uint32_t)__clz((int)mymask) : 32u;
-    const uint32_t* src0 = stream + (gw / LK_WINS) * (uint64_t)LK_CAP + (mymask ? win_info[gw] : 0u);
+    const uint32_t info = mymask ? win_info[gw] : 0u;      // first slot | ranks of the short pieces << 16
+    const uint32_t* src0 = stream + (gw / LK_WINS) * (uint64_t)LK_CAP + (info & 0xFFFFu);
     // ---- tokens of my window ----
-    uint32_t count = 0;
+    uint32_t count = info >> 16;
+    if (lw) count += recs[lw - 1].count;
     {
-        const uint32_t* src = src0;
-        uint32_t m = mymask;
+        uint32_t m = mymask & myds;
         while (m) {
             const uint32_t bit = (uint32_t)(__ffs((int)m) - 1);
             m &= m - 1;
-            const uint64_t gpos = wpos + bit;
-            if ((myds >> bit) & 1u) {
-                uint64_t first;
-                const uint64_t k = docs_at(doc_off, n_docs, gpos, &first);
-                for (uint64_t d = first; d < first + k; ++d) count += (d > 0 ? add_eos : 0u) + (d < n_docs ? add_bos : 0u);
-            }
-            if (gpos >= n) continue;                        // the end-of-data sentinel is not a piece
-            if (lw && bit == topbit) { count += recs[lw - 1].count; continue; }
-            if (__ldg(src) & EN_LAST) { count += 1; src += 1; continue; }
-            uint32_t c = 1;
-            while (!(__ldg(src + c) & EN_LAST)) ++c;
-            count += c + 1;
-            src += em_piece_len(start_mask, gw, mymask, bit);
+            uint64_t first;
+            const uint64_t k = docs_at(doc_off, n_docs, wpos + bit, &first);
+            for (uint64_t d = first; d < first + k; ++d) count += (d > 0 ? add_eos : 0u) + (d < n_docs ? add_bos : 0u);
         }
     }
     uint32_t inc = count;
@@ -998,7 +996,7 @@ size_t encode_workspace_bytes(uint64_t n, uint64_t n_docs, EncodeLayout* L) {
 template <int MAXLEN, int THREADS>
 static cudaError_t launch_lanemerge(int blocks_per_sm, int sm_count, const uint8_t* d_data, const TkDeviceTables& T,
                                     const unsigned long long* queue, const uint32_t* q_n, uint32_t* q_w, uint32_t* stream,
-                                    cudaStream_t st) {
+                                    uint32_t* win_info, cudaStream_t st) {
     const size_t smem = (size_t)2 * THREADS * (MAXLEN + 1) * sizeof(uint32_t);
     static std::atomic<uint64_t> attr_set{0};   // bit per device ordinal
     int dev = 0;
@@ -1007,7 +1005,7 @@ static cudaError_t launch_lanemerge(int blocks_per_sm, int sm_count, const uint8
         CK(cudaFuncSetAttribute(lanemerge_kernel<MAXLEN, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set.fetch_or(1ull << (dev & 63));
     }
-    lanemerge_kernel<MAXLEN, THREADS><<<(unsigned)(sm_count * blocks_per_sm), THREADS, smem, st>>>(d_data, T, queue, q_n, q_w, stream);
+    lanemerge_kernel<MAXLEN, THREADS><<<(unsigned)(sm_count * blocks_per_sm), THREADS, smem, st>>>(d_data, T, queue, q_n, q_w, stream, win_info);
     count_launch();
     return cudaSuccess;
 }
@@ -1091,12 +1089,16 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
         lookup_kernel<<<(unsigned)L.n_ltiles, LK_T, sizeof(LkSmem), st>>>(d_data, n, start, T, stream, win_info, queues, L.queues, q_n);
         TK_LAUNCHED();
     }
-    if (timer) timer->mark(st, "lanemerge");
-    CK((launch_lanemerge<64, 128>(3, sm_count, d_data, T, queues + L.queues.off[4], q_n + 4, q_w + 4, stream, st)));
-    CK((launch_lanemerge<32, 256>(3, sm_count, d_data, T, queues + L.queues.off[3], q_n + 3, q_w + 3, stream, st)));
-    CK((launch_lanemerge<16, 256>(6, sm_count, d_data, T, queues + L.queues.off[2], q_n + 2, q_w + 2, stream, st)));
-    CK((launch_lanemerge<8, 256>(8, sm_count, d_data, T, queues + L.queues.off[1], q_n + 1, q_w + 1, stream, st)));
-    CK((launch_lanemerge<4, 256>(8, sm_count, d_data, T, queues + L.queues.off[0], q_n + 0, q_w + 0, stream, st)));
+    if (timer) timer->mark(st, "lanemerge64");
+    CK((launch_lanemerge<64, 128>(3, sm_count, d_data, T, queues + L.queues.off[4], q_n + 4, q_w + 4, stream, win_info, st)));
+    if (timer) timer->mark(st, "lanemerge32");
+    CK((launch_lanemerge<32, 256>(3, sm_count, d_data, T, queues + L.queues.off[3], q_n + 3, q_w + 3, stream, win_info, st)));
+    if (timer) timer->mark(st, "lanemerge16");
+    CK((launch_lanemerge<16, 256>(6, sm_count, d_data, T, queues + L.queues.off[2], q_n + 2, q_w + 2, stream, win_info, st)));
+    if (timer) timer->mark(st, "lanemerge8");
+    CK((launch_lanemerge<8, 256>(8, sm_count, d_data, T, queues + L.queues.off[1], q_n + 1, q_w + 1, stream, win_info, st)));
+    if (timer) timer->mark(st, "lanemerge4");
+    CK((launch_lanemerge<4, 256>(8, sm_count, d_data, T, queues + L.queues.off[0], q_n + 0, q_w + 0, stream, win_info, st)));
     if (timer) timer->mark(st, "emit");
     static_assert(EM_WINS == PT_T, "emit tiles are the pre-tokeniser's tiles");
     emit_kernel<<<(unsigned)L.n_tiles, EM_T, 0, st>>>(n, start, ds, longword, recs, pool, stream, win_info, d_doc_off, n_docs,
