@@ -146,7 +146,16 @@ struct tk_tokenizer {
     std::vector<void*> table_allocs;
     std::mutex mu;                 // serialises device work issued through this handle
     cudaStream_t stream = nullptr; // used by the host-buffer entry points
-    DevBuf ws, scratch, in_data, in_off, out_a, out_b, status;
+    DevBuf ws, in_data, in_off, out_a, out_b, status;     // decode + single-shot paths
+    struct EncSlot {
+        cudaStream_t st = nullptr;
+        DevBuf ws, scratch, in_data, in_off, out_tok, out_off;
+        uint32_t* h_small = nullptr;   // pinned copy of the workspace's counter block
+        tkk::EncodeLayout L;
+    };
+    static constexpr int kSlots = 3;
+    EncSlot slot[kSlots];          // host-buffer encode: chunks of a batch pipeline through these
+    EncSlot dev_slot;              // device-pointer encode (caller's stream)
     bool timing = false;
     tkk::StageTimer timer;
     std::vector<std::string> stage_names;
@@ -274,8 +283,15 @@ extern "C" void tk_free(tk_tokenizer* t) {
         cudaSetDevice(t->device);
         t->timer.reset();
         for (void* p : t->table_allocs) cudaFree(p);
-        t->ws.release(); t->scratch.release(); t->in_data.release(); t->in_off.release();
+        t->ws.release(); t->in_data.release(); t->in_off.release();
         t->out_a.release(); t->out_b.release(); t->status.release();
+        auto drop = [](tk_tokenizer::EncSlot& s) {
+            if (s.st) { cudaStreamSynchronize(s.st); cudaStreamDestroy(s.st); }
+            s.ws.release(); s.scratch.release(); s.in_data.release(); s.in_off.release(); s.out_tok.release(); s.out_off.release();
+            if (s.h_small) cudaFreeHost(s.h_small);
+        };
+        for (auto& sl : t->slot) drop(sl);
+        drop(t->dev_slot);
         if (t->stream) cudaStreamDestroy(t->stream);
         cudaSetDevice(prev);
     }
@@ -394,45 +410,54 @@ static int check_encode_args(const tk_tokenizer* t, int add_bos, int add_eos) {
     return TK_OK;
 }
 
-// Runs the kernels on device buffers; the caller holds t->mu and has set the device.
-static int run_encode(tk_tokenizer* t, const uint8_t* d_data, const uint64_t* d_doc_off, size_t n_docs, uint64_t total,
-                      int add_bos, int add_eos, uint32_t* d_tokens, uint64_t cap, uint64_t* d_tok_off, uint64_t* n_tokens,
-                      cudaStream_t st) {
+// Queue the encode kernels for one batch (or one chunk of a batch) on `st`, plus the copy of the
+// workspace's counter block to pinned host memory.  Does not wait.  The caller holds t->mu and has
+// set the device.
+static int encode_issue(tk_tokenizer* t, tk_tokenizer::EncSlot& s, const uint8_t* d_data, const uint64_t* d_doc_off, uint64_t off_base,
+                        size_t n_docs, uint64_t total, int add_bos, int add_eos, uint32_t* d_tokens, uint64_t cap,
+                        uint64_t* d_tok_off, cudaStream_t st, bool timing) {
     if (((uintptr_t)d_data & 15u) != 0 && total) return fail(TK_ERR_INVALID_ARGUMENT, "device text pointer must be 16-byte aligned");
     if (total >= (1ull << 40)) return fail(TK_ERR_INVALID_ARGUMENT, "batch too large; shard it (limit 1 TiB per call)");
-    tkk::EncodeLayout L;
-    size_t ws_bytes = tkk::encode_workspace_bytes(total, n_docs, &L);
-    CUDA_OR_FAIL(t->ws.ensure(ws_bytes));
-    if (t->scratch.cap == 0) CUDA_OR_FAIL(t->scratch.ensure(1 << 20));
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        if (t->timing) t->timer.reset();
-        cudaError_t e = tkk::encode_device(t->tables, d_data, d_doc_off, n_docs, total, add_bos, add_eos, d_tokens, cap, d_tok_off,
-                                           t->ws.p, L, (uint32_t*)t->scratch.p, t->scratch.cap / 4, t->sm_count, st,
-                                           t->timing ? &t->timer : nullptr);
-        if (e != cudaSuccess) return fail(TK_ERR_CUDA, "encode launch: %s", cudaGetErrorString(e));
-        uint32_t small[64];
-        CUDA_OR_FAIL(cudaMemcpyAsync(small, (unsigned char*)t->ws.p + L.off_small, sizeof small, cudaMemcpyDeviceToHost, st));
-        CUDA_OR_FAIL(cudaStreamSynchronize(st));
-        if (t->timing) t->timer.collect(t->stage_names, t->stage_ms);
-        const uint32_t flags = small[tkk::TKK_S_FLAGS];
-        uint64_t err_pos, total_out;
-        memcpy(&err_pos, small + tkk::TKK_S_ERRPOS, 8);
-        memcpy(&total_out, small + tkk::TKK_S_TOTAL, 8);
-        if (flags & tkk::TKK_FLAG_BAD_OFFSETS)
-            return fail(TK_ERR_INVALID_ARGUMENT, "document offsets must start at 0, be non-decreasing and end at the text length");
-        if (err_pos != ~0ull) return fail(TK_ERR_INVALID_UTF8, "input is not valid UTF-8 at byte %llu", (unsigned long long)err_pos);
-        if (flags & tkk::TKK_FLAG_SCRATCH_FULL) {
-            // a piece longer than TK_MED_MAX bytes needs 12 bytes of scratch per byte: grow and rerun
-            CUDA_OR_FAIL(t->scratch.ensure((size_t)total * 12 + 4096));
-            continue;
-        }
-        *n_tokens = total_out;
-        if (flags & tkk::TKK_FLAG_OUT_FULL)
-            return fail(TK_ERR_BUFFER_TOO_SMALL, "token buffer holds %llu ids, %llu needed", (unsigned long long)cap,
-                        (unsigned long long)total_out);
+    size_t ws_bytes = tkk::encode_workspace_bytes(total, n_docs, &s.L);
+    CUDA_OR_FAIL(s.ws.ensure(ws_bytes));
+    if (s.scratch.cap == 0) CUDA_OR_FAIL(s.scratch.ensure(1 << 20));
+    if (!s.h_small) CUDA_OR_FAIL(cudaHostAlloc((void**)&s.h_small, 256, cudaHostAllocDefault));
+    if (timing) t->timer.reset();
+    cudaError_t e = tkk::encode_device(t->tables, d_data, d_doc_off, off_base, n_docs, total, add_bos, add_eos, d_tokens, cap, d_tok_off,
+                                       s.ws.p, s.L, (uint32_t*)s.scratch.p, s.scratch.cap / 4, t->sm_count, st,
+                                       timing ? &t->timer : nullptr);
+    if (e != cudaSuccess) return fail(TK_ERR_CUDA, "encode launch: %s", cudaGetErrorString(e));
+    CUDA_OR_FAIL(cudaMemcpyAsync(s.h_small, (unsigned char*)s.ws.p + s.L.off_small, 256, cudaMemcpyDeviceToHost, st));
+    return TK_OK;
+}
+
+// Wait for an issued encode and interpret what the kernels reported.  *retry is set when the
+// huge-piece scratch was too small: it has been grown and the same encode must be issued again.
+static int encode_finish(tk_tokenizer* t, tk_tokenizer::EncSlot& s, cudaStream_t st, uint64_t total, uint64_t cap, uint64_t byte_base,
+                         uint64_t* n_tokens, bool* retry, bool timing) {
+    *retry = false;
+    CUDA_OR_FAIL(cudaStreamSynchronize(st));
+    if (timing) t->timer.collect(t->stage_names, t->stage_ms);
+    const uint32_t* small = s.h_small;
+    const uint32_t flags = small[tkk::TKK_S_FLAGS];
+    uint64_t err_pos, total_out;
+    memcpy(&err_pos, small + tkk::TKK_S_ERRPOS, 8);
+    memcpy(&total_out, small + tkk::TKK_S_TOTAL, 8);
+    if (flags & tkk::TKK_FLAG_BAD_OFFSETS)
+        return fail(TK_ERR_INVALID_ARGUMENT, "document offsets must start at 0, be non-decreasing and end at the text length");
+    if (err_pos != ~0ull)
+        return fail(TK_ERR_INVALID_UTF8, "input is not valid UTF-8 at byte %llu", (unsigned long long)(err_pos + byte_base));
+    if (flags & tkk::TKK_FLAG_SCRATCH_FULL) {
+        // a piece longer than TK_MED_MAX bytes needs 12 bytes of scratch per byte: grow and rerun
+        CUDA_OR_FAIL(s.scratch.ensure((size_t)total * 12 + 4096));
+        *retry = true;
         return TK_OK;
     }
-    return fail(TK_ERR_CUDA, "huge-piece scratch could not be grown");
+    *n_tokens = total_out;
+    if (flags & tkk::TKK_FLAG_OUT_FULL)
+        return fail(TK_ERR_BUFFER_TOO_SMALL, "token buffer holds %llu ids, %llu needed", (unsigned long long)cap,
+                    (unsigned long long)total_out);
+    return TK_OK;
 }
 
 extern "C" int tk_encode_batch_device(const tk_tokenizer* tc, const uint8_t* d_data, const uint64_t* d_doc_off, size_t n_docs,
@@ -446,10 +471,21 @@ extern "C" int tk_encode_batch_device(const tk_tokenizer* tc, const uint8_t* d_d
     std::lock_guard<std::mutex> g(t->mu);
     DeviceGuard dg(t->device);
     if (!dg.ok) return fail(TK_ERR_CUDA, "cudaSetDevice(%d) failed", t->device);
-    return run_encode(t, d_data, d_doc_off, n_docs, total_bytes, add_bos, add_eos, d_tokens, tokens_capacity, d_tok_off, n_tokens,
-                      (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        rc = encode_issue(t, t->dev_slot, d_data, d_doc_off, 0, n_docs, total_bytes, add_bos, add_eos, d_tokens, tokens_capacity,
+                          d_tok_off, st, t->timing);
+        if (rc) return rc;
+        bool retry = false;
+        rc = encode_finish(t, t->dev_slot, st, total_bytes, tokens_capacity, 0, n_tokens, &retry, t->timing);
+        if (rc || !retry) return rc;
+    }
+    return fail(TK_ERR_CUDA, "huge-piece scratch could not be grown");
 }
 
+// Host buffers in, pinned host buffers out.  The batch is cut at document boundaries into chunks of
+// about kChunkBytes that flow through kSlots streams: while chunk i is being encoded, chunk i+1 is
+// on its way to the device and the ids of chunk i-1 are on their way back.
 extern "C" int tk_encode_batch(const tk_tokenizer* tc, const uint8_t* data, const uint64_t* doc_off, size_t n_docs, int add_bos,
                                int add_eos, uint32_t** tokens, uint64_t** tok_off) {
     int rc = check_encode_args(tc, add_bos, add_eos);
@@ -457,32 +493,106 @@ extern "C" int tk_encode_batch(const tk_tokenizer* tc, const uint8_t* data, cons
     if (!doc_off || !tokens || !tok_off) return fail(TK_ERR_INVALID_ARGUMENT, "null argument");
     *tokens = nullptr;
     *tok_off = nullptr;
+    if (doc_off[0] != 0) return fail(TK_ERR_INVALID_ARGUMENT, "document offsets must start at 0, be non-decreasing and end at the text length");
     const uint64_t total = doc_off[n_docs];
     if (!data && total) return fail(TK_ERR_INVALID_ARGUMENT, "null text");
     tk_tokenizer* t = const_cast<tk_tokenizer*>(tc);
     std::lock_guard<std::mutex> g(t->mu);
     DeviceGuard dg(t->device);
     if (!dg.ok) return fail(TK_ERR_CUDA, "cudaSetDevice(%d) failed", t->device);
-    cudaStream_t st = t->stream;
-    const uint64_t cap = total + 2 * (uint64_t)n_docs + 2;
-    CUDA_OR_FAIL(t->in_data.ensure(total + 64));
-    CUDA_OR_FAIL(t->in_off.ensure((n_docs + 1) * 8));
-    CUDA_OR_FAIL(t->out_a.ensure(cap * 4));
-    CUDA_OR_FAIL(t->out_b.ensure((n_docs + 1) * 8));
-    if (total) CUDA_OR_FAIL(cudaMemcpyAsync(t->in_data.p, data, total, cudaMemcpyHostToDevice, st));
-    CUDA_OR_FAIL(cudaMemcpyAsync(t->in_off.p, doc_off, (n_docs + 1) * 8, cudaMemcpyHostToDevice, st));
-    uint64_t n_tok = 0;
-    rc = run_encode(t, (const uint8_t*)t->in_data.p, (const uint64_t*)t->in_off.p, n_docs, total, add_bos, add_eos,
-                    (uint32_t*)t->out_a.p, cap, (uint64_t*)t->out_b.p, &n_tok, st);
-    if (rc) return rc;
-    uint32_t* h_tok = (uint32_t*)g_pool.get(n_tok * 4 + 4);
+
+    // chunk plan: [begin doc, end doc)
+    constexpr uint64_t kChunkBytes = 48ull << 20;
+    std::vector<size_t> cut{0};
+    while (cut.back() < n_docs) {
+        const size_t b = cut.back();
+        const uint64_t target = doc_off[b] + kChunkBytes;
+        size_t e = std::upper_bound(doc_off + b + 1, doc_off + n_docs + 1, target) - doc_off;   // first doc END beyond the target
+        if (e > n_docs) e = n_docs;
+        if (e <= b) e = b + 1;
+        if (doc_off[e] < doc_off[b]) return fail(TK_ERR_INVALID_ARGUMENT, "document offsets must start at 0, be non-decreasing and end at the text length");
+        cut.push_back(e);
+    }
+    if (n_docs == 0) cut.push_back(0);
+    const size_t n_chunks = cut.size() - 1;
+
+    // result buffers: the id count is not known in advance; start from an estimate and grow if needed
+    uint64_t h_cap = total / 2 + 2 * (uint64_t)n_docs + 4096;
+    uint32_t* h_tok = (uint32_t*)g_pool.get(h_cap * 4);
     uint64_t* h_off = (uint64_t*)g_pool.get((n_docs + 1) * 8);
     if (!h_tok || !h_off) { g_pool.put(h_tok); g_pool.put(h_off); return fail(TK_ERR_CUDA, "out of pinned host memory"); }
-    cudaError_t e = cudaSuccess;
-    if (n_tok) e = cudaMemcpyAsync(h_tok, t->out_a.p, n_tok * 4, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(h_off, t->out_b.p, (n_docs + 1) * 8, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) { g_pool.put(h_tok); g_pool.put(h_off); return fail(TK_ERR_CUDA, "copying ids back: %s", cudaGetErrorString(e)); }
+    auto bail = [&](int code) {
+        for (auto& sl : t->slot) if (sl.st) cudaStreamSynchronize(sl.st);
+        g_pool.put(h_tok); g_pool.put(h_off);
+        return code;
+    };
+    struct Chunk { uint64_t byte_begin, n_bytes, cap; size_t doc_begin, n; };
+    auto chunk_of = [&](size_t i) {
+        Chunk c;
+        c.doc_begin = cut[i]; c.n = cut[i + 1] - cut[i];
+        c.byte_begin = n_docs ? doc_off[cut[i]] : 0; c.n_bytes = n_docs ? doc_off[cut[i + 1]] - c.byte_begin : 0;
+        c.cap = c.n_bytes + 2 * (uint64_t)c.n + 2;
+        return c;
+    };
+    auto issue = [&](size_t i) -> int {
+        tk_tokenizer::EncSlot& s = t->slot[i % tk_tokenizer::kSlots];
+        const Chunk c = chunk_of(i);
+        if (!s.st) CUDA_OR_FAIL(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+        CUDA_OR_FAIL(s.in_data.ensure(c.n_bytes + 64));
+        CUDA_OR_FAIL(s.in_off.ensure((c.n + 1) * 8));
+        CUDA_OR_FAIL(s.out_tok.ensure(c.cap * 4));
+        CUDA_OR_FAIL(s.out_off.ensure((c.n + 1) * 8));
+        if (c.n_bytes) CUDA_OR_FAIL(cudaMemcpyAsync(s.in_data.p, data + c.byte_begin, c.n_bytes, cudaMemcpyHostToDevice, s.st));
+        CUDA_OR_FAIL(cudaMemcpyAsync(s.in_off.p, doc_off + c.doc_begin, (c.n + 1) * 8, cudaMemcpyHostToDevice, s.st));
+        return encode_issue(t, s, (const uint8_t*)s.in_data.p, (const uint64_t*)s.in_off.p, c.byte_begin, c.n, c.n_bytes, add_bos, add_eos,
+                            (uint32_t*)s.out_tok.p, c.cap, (uint64_t*)s.out_off.p, s.st, false);
+    };
+    std::vector<uint64_t> prefix(n_chunks + 1, 0);
+    rc = issue(0);
+    if (rc) return bail(rc);
+    for (size_t i = 0; i < n_chunks; ++i) {
+        if (i + 1 < n_chunks) { rc = issue(i + 1); if (rc) return bail(rc); }
+        tk_tokenizer::EncSlot& s = t->slot[i % tk_tokenizer::kSlots];
+        const Chunk c = chunk_of(i);
+        uint64_t n_tok = 0;
+        for (int attempt = 0;; ++attempt) {
+            bool retry = false;
+            rc = encode_finish(t, s, s.st, c.n_bytes, c.cap, c.byte_begin, &n_tok, &retry, false);
+            if (rc) return bail(rc);
+            if (!retry) break;
+            if (attempt) return bail(fail(TK_ERR_CUDA, "huge-piece scratch could not be grown"));
+            rc = encode_issue(t, s, (const uint8_t*)s.in_data.p, (const uint64_t*)s.in_off.p, c.byte_begin, c.n, c.n_bytes, add_bos, add_eos,
+                              (uint32_t*)s.out_tok.p, c.cap, (uint64_t*)s.out_off.p, s.st, false);
+            if (rc) return bail(rc);
+        }
+        if (prefix[i] + n_tok > h_cap) {
+            // estimate too small: finish the copies into the old buffer, move to a bigger one
+            for (auto& sl : t->slot) if (sl.st) CUDA_OR_FAIL(cudaStreamSynchronize(sl.st));
+            uint64_t want = std::max(2 * h_cap, prefix[i] + n_tok + (total - c.byte_begin - c.n_bytes) + 2 * (uint64_t)(n_docs - c.doc_begin) + 4096);
+            uint32_t* bigger = (uint32_t*)g_pool.get(want * 4);
+            if (!bigger) return bail(fail(TK_ERR_CUDA, "out of pinned host memory"));
+            memcpy(bigger, h_tok, prefix[i] * 4);
+            g_pool.put(h_tok);
+            h_tok = bigger;
+            h_cap = want;
+        }
+        cudaError_t e = cudaSuccess;
+        if (n_tok) e = cudaMemcpyAsync(h_tok + prefix[i], s.out_tok.p, n_tok * 4, cudaMemcpyDeviceToHost, s.st);
+        if (e == cudaSuccess && c.n) e = cudaMemcpyAsync(h_off + c.doc_begin, s.out_off.p, c.n * 8, cudaMemcpyDeviceToHost, s.st);
+        if (e != cudaSuccess) return bail(fail(TK_ERR_CUDA, "copying ids back: %s", cudaGetErrorString(e)));
+        prefix[i + 1] = prefix[i] + n_tok;
+    }
+    for (auto& sl : t->slot)
+        if (sl.st) {
+            cudaError_t e = cudaStreamSynchronize(sl.st);
+            if (e != cudaSuccess) return bail(fail(TK_ERR_CUDA, "copying ids back: %s", cudaGetErrorString(e)));
+        }
+    // chunk-local token offsets -> batch offsets
+    for (size_t i = 1; i < n_chunks; ++i) {
+        const uint64_t add = prefix[i];
+        for (size_t d = cut[i]; d < cut[i + 1]; ++d) h_off[d] += add;
+    }
+    h_off[n_docs] = prefix[n_chunks];
     *tokens = h_tok;
     *tok_off = h_off;
     return TK_OK;

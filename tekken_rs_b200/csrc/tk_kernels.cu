@@ -54,15 +54,15 @@ StageTimer::~StageTimer() { reset(); }
 // K0: document-start bitmask.  Bit p is set iff some document starts at byte p; bit `total` is
 // the end-of-data sentinel.  Also validates the offsets.
 // =====================================================================================================
-__global__ void docmark_kernel(const uint64_t* __restrict__ doc_off, uint64_t n_docs, uint64_t total,
+__global__ void docmark_kernel(const uint64_t* __restrict__ doc_off, uint64_t off_base, uint64_t n_docs, uint64_t total,
                                uint32_t* __restrict__ ds_mask, uint32_t* __restrict__ flags) {
     uint64_t d = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (d > n_docs) return;
-    uint64_t o = doc_off[d];
-    bool ok = o <= total;
+    uint64_t o = doc_off[d] - off_base;      // offsets may be a slice of a larger batch (off_base = its first entry)
+    bool ok = doc_off[d] >= off_base && o <= total;
     if (d == 0 && o != 0) ok = false;
     if (d == n_docs && o != total) ok = false;
-    if (d < n_docs && doc_off[d + 1] < o) ok = false;
+    if (d < n_docs && doc_off[d + 1] < doc_off[d]) ok = false;
     if (!ok) { atomicOr(flags, TKK_FLAG_BAD_OFFSETS); return; }
     atomicOr(ds_mask + (o >> 5), 1u << (o & 31));
 }
@@ -826,7 +826,7 @@ __global__ void __launch_bounds__(EM_T) emit_kernel(uint64_t n, const uint32_t* 
                                                     const uint32_t* __restrict__ ds_mask, const uint32_t* __restrict__ long_of_word,
                                                     const TkkLongRec* __restrict__ recs, const uint32_t* __restrict__ pool,
                                                     const uint32_t* __restrict__ stream, const uint32_t* __restrict__ win_info,
-                                                    const uint64_t* __restrict__ doc_off, uint64_t n_docs, uint32_t add_bos,
+                                                    const uint64_t* __restrict__ doc_off, uint64_t off_base, uint64_t n_docs, uint32_t add_bos,
                                                     uint32_t add_eos, uint32_t nsp, uint32_t bos_id, uint32_t eos_id,
                                                     uint32_t* __restrict__ out, uint64_t out_cap, uint64_t* __restrict__ tok_off,
                                                     unsigned long long* __restrict__ tile_state, uint32_t* __restrict__ ticket,
@@ -855,7 +855,7 @@ __global__ void __launch_bounds__(EM_T) emit_kernel(uint64_t n, const uint32_t* 
             const uint32_t bit = (uint32_t)(__ffs((int)m) - 1);
             m &= m - 1;
             uint64_t first;
-            const uint64_t k = docs_at(doc_off, n_docs, wpos + bit, &first);
+            const uint64_t k = docs_at(doc_off, n_docs, wpos + bit + off_base, &first);
             for (uint64_t d = first; d < first + k; ++d) count += (d > 0 ? add_eos : 0u) + (d < n_docs ? add_bos : 0u);
         }
     }
@@ -896,7 +896,7 @@ __global__ void __launch_bounds__(EM_T) emit_kernel(uint64_t n, const uint32_t* 
             const uint64_t gpos = wpos + bit;
             if ((myds >> bit) & 1u) {
                 uint64_t first;
-                const uint64_t k = docs_at(doc_off, n_docs, gpos, &first);
+                const uint64_t k = docs_at(doc_off, n_docs, gpos + off_base, &first);
                 for (uint64_t d = first; d < first + k; ++d) {
                     if (d > 0 && add_eos) {
                         if (fits) comp[o] = eos_id; else if (base + o < out_cap) out[base + o] = eos_id;
@@ -1010,8 +1010,8 @@ static cudaError_t launch_lanemerge(int blocks_per_sm, int sm_count, const uint8
     return cudaSuccess;
 }
 
-cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const uint64_t* d_doc_off, uint64_t n_docs,
-                          uint64_t n, int add_bos, int add_eos, uint32_t* d_out, uint64_t out_cap, uint64_t* d_tok_off,
+cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const uint64_t* d_doc_off, uint64_t off_base,
+                          uint64_t n_docs, uint64_t n, int add_bos, int add_eos, uint32_t* d_out, uint64_t out_cap, uint64_t* d_tok_off,
                           void* d_ws, const EncodeLayout& L, uint32_t* d_scratch, uint64_t scratch_cap, int sm_count,
                           cudaStream_t st, StageTimer* timer) {
     unsigned char* ws = (unsigned char*)d_ws;
@@ -1050,7 +1050,7 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
     CK(cudaMemsetAsync(ds, 0, L.mask_words * 4, st));
     CK(cudaMemsetAsync(start + L.n_windows, 0, (L.mask_words - L.n_windows) * 4, st));
     CK(cudaMemsetAsync(tilestate, 0, L.n_tiles * 8, st));
-    docmark_kernel<<<(unsigned)ceil_div(n_docs + 1, 256), 256, 0, st>>>(d_doc_off, n_docs, n, ds, flags);
+    docmark_kernel<<<(unsigned)ceil_div(n_docs + 1, 256), 256, 0, st>>>(d_doc_off, off_base, n_docs, n, ds, flags);
     TK_LAUNCHED();
     if (timer) timer->mark(st, "pretok");
     pretok_kernel<<<(unsigned)L.n_tiles, PT_T, 0, st>>>(d_data, n, ds, start, L.n_windows, T, summ, err_pos);
@@ -1101,7 +1101,7 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
     CK((launch_lanemerge<4, 256>(8, sm_count, d_data, T, queues + L.queues.off[0], q_n + 0, q_w + 0, stream, win_info, st)));
     if (timer) timer->mark(st, "emit");
     static_assert(EM_WINS == PT_T, "emit tiles are the pre-tokeniser's tiles");
-    emit_kernel<<<(unsigned)L.n_tiles, EM_T, 0, st>>>(n, start, ds, longword, recs, pool, stream, win_info, d_doc_off, n_docs,
+    emit_kernel<<<(unsigned)L.n_tiles, EM_T, 0, st>>>(n, start, ds, longword, recs, pool, stream, win_info, d_doc_off, off_base, n_docs,
                                                      add_bos ? 1u : 0u, add_eos ? 1u : 0u, T.num_special, T.bos_id, T.eos_id, d_out,
                                                      out_cap, d_tok_off, tilestate, ticket, total_out, flags);
     TK_LAUNCHED();
