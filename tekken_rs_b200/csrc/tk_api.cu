@@ -418,6 +418,7 @@ static int encode_issue(tk_tokenizer* t, tk_tokenizer::EncSlot& s, const uint8_t
                         uint64_t* d_tok_off, cudaStream_t st, bool timing) {
     if (((uintptr_t)d_data & 15u) != 0 && total) return fail(TK_ERR_INVALID_ARGUMENT, "device text pointer must be 16-byte aligned");
     if (total >= (1ull << 40)) return fail(TK_ERR_INVALID_ARGUMENT, "batch too large; shard it (limit 1 TiB per call)");
+    if ((uint64_t)n_docs >= 0xFFFFFFFEull) return fail(TK_ERR_INVALID_ARGUMENT, "too many documents in one call; shard the batch");
     size_t ws_bytes = tkk::encode_workspace_bytes(total, n_docs, &s.L);
     CUDA_OR_FAIL(s.ws.ensure(ws_bytes));
     if (s.scratch.cap == 0) CUDA_OR_FAIL(s.scratch.ensure(1 << 20));

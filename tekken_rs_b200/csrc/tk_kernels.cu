@@ -55,7 +55,7 @@ StageTimer::~StageTimer() { reset(); }
 // the end-of-data sentinel.  Also validates the offsets.
 // =====================================================================================================
 __global__ void docmark_kernel(const uint64_t* __restrict__ doc_off, uint64_t off_base, uint64_t n_docs, uint64_t total,
-                               uint32_t* __restrict__ ds_mask, uint32_t* __restrict__ flags) {
+                               uint32_t* __restrict__ ds_mask, uint32_t* __restrict__ doc_first, uint32_t* __restrict__ flags) {
     uint64_t d = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (d > n_docs) return;
     uint64_t o = doc_off[d] - off_base;      // offsets may be a slice of a larger batch (off_base = its first entry)
@@ -65,6 +65,7 @@ __global__ void docmark_kernel(const uint64_t* __restrict__ doc_off, uint64_t of
     if (d < n_docs && doc_off[d + 1] < doc_off[d]) ok = false;
     if (!ok) { atomicOr(flags, TKK_FLAG_BAD_OFFSETS); return; }
     atomicOr(ds_mask + (o >> 5), 1u << (o & 31));
+    atomicMin(doc_first + (o >> 5), (uint32_t)d);     // first document that starts in this 32-byte window
 }
 
 // =====================================================================================================
@@ -553,7 +554,7 @@ __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __
 #define QE_LEN_BITS 7
 
 __host__ __device__ __forceinline__ uint32_t lane_class(uint32_t len) {        // 2..4, 5..8, 9..16, 17..32, 33..64
-    return len <= 4u ? 0u : len <= 8u ? 1u : len <= 16u ? 2u : len <= 32u ? 3u : 4u;
+    return len <= 4u ? 0u : 30u - (uint32_t)TK_CLZ(len - 1u);
 }
 
 struct LkSmem {
@@ -728,12 +729,17 @@ __global__ void __launch_bounds__(THREADS) lanemerge_kernel(const uint8_t* __res
     uint32_t* key = lm_raw + THREADS * STRIDE + threadIdx.x * STRIDE;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t total = *q_n;
-    for (;;) {
-        uint32_t k = 0;
-        if (lane == 0) k = atomicAdd(q_w, 32u);
-        k = __shfl_sync(0xFFFFFFFFu, k, 0);
-        if (k >= total) break;
-        k += lane;
+    // short pieces cost about the same: warps stride over the queue.  Long ones vary more: warps take
+    // the next 32 entries from a work counter.
+    constexpr bool kDynamic = MAXLEN >= 16;
+    const uint32_t warps = gridDim.x * (THREADS / 32);
+    for (uint32_t k0 = (blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5)) * 32u;; k0 += warps * 32u) {
+        if (kDynamic) {
+            if (lane == 0) k0 = atomicAdd(q_w, 32u);
+            k0 = __shfl_sync(0xFFFFFFFFu, k0, 0);
+        }
+        if (k0 >= total) break;
+        const uint32_t k = k0 + lane;
         if (k < total) {
             const unsigned long long e = queue[k];
             const uint64_t start = e & ((1ull << QE_START_BITS) - 1ull);
@@ -799,17 +805,11 @@ struct EmSmem {
     unsigned long long base;
 };
 
-// number of documents that start at byte position s, and the index of the first of them
-__device__ __forceinline__ uint64_t docs_at(const uint64_t* __restrict__ doc_off, uint64_t n_docs, uint64_t s, uint64_t* first) {
-    uint64_t lo = 0, hi = n_docs + 1;   // doc_off has n_docs+1 entries; the last one is the virtual end doc
-    while (lo < hi) {
-        uint64_t mid = (lo + hi) >> 1;
-        if (doc_off[mid] < s) lo = mid + 1; else hi = mid;
-    }
-    *first = lo;
-    uint64_t e = lo;
-    while (e <= n_docs && doc_off[e] == s) ++e;
-    return e - lo;
+// number of documents that start at batch byte position s, given the index of the first of them
+__device__ __forceinline__ uint32_t docs_from(const uint64_t* __restrict__ doc_off, uint64_t n_docs, uint64_t s, uint64_t first) {
+    uint64_t e = first + 1;
+    while (e <= n_docs && doc_off[e] == s) ++e;     // doc_off has n_docs+1 entries; the last one is the virtual end doc
+    return (uint32_t)(e - first);
 }
 
 // length of the piece that starts at bit `bit` of window gw (not a long piece: the next start is at most
@@ -823,7 +823,8 @@ __device__ __forceinline__ uint32_t em_piece_len(const uint32_t* __restrict__ st
 }
 
 __global__ void __launch_bounds__(EM_T) emit_kernel(uint64_t n, const uint32_t* __restrict__ start_mask,
-                                                    const uint32_t* __restrict__ ds_mask, const uint32_t* __restrict__ long_of_word,
+                                                    const uint32_t* __restrict__ ds_mask, const uint32_t* __restrict__ doc_first,
+                                                    const uint32_t* __restrict__ long_of_word,
                                                     const TkkLongRec* __restrict__ recs, const uint32_t* __restrict__ pool,
                                                     const uint32_t* __restrict__ stream, const uint32_t* __restrict__ win_info,
                                                     const uint64_t* __restrict__ doc_off, uint64_t off_base, uint64_t n_docs, uint32_t add_bos,
@@ -846,17 +847,19 @@ __global__ void __launch_bounds__(EM_T) emit_kernel(uint64_t n, const uint32_t* 
     const uint32_t topbit = mymask ? 31u - (uint32_t)__clz((int)mymask) : 32u;
     const uint32_t info = mymask ? win_info[gw] : 0u;      // first slot | ranks of the short pieces << 16
     const uint32_t* src0 = stream + (gw / LK_WINS) * (uint64_t)LK_CAP + (info & 0xFFFFu);
+    const uint64_t mydoc = myds ? doc_first[gw] : 0;        // first document that starts in my window
     // ---- tokens of my window ----
     uint32_t count = info >> 16;
     if (lw) count += recs[lw - 1].count;
     {
         uint32_t m = mymask & myds;
+        uint64_t d0 = mydoc;
         while (m) {
             const uint32_t bit = (uint32_t)(__ffs((int)m) - 1);
             m &= m - 1;
-            uint64_t first;
-            const uint64_t k = docs_at(doc_off, n_docs, wpos + bit + off_base, &first);
-            for (uint64_t d = first; d < first + k; ++d) count += (d > 0 ? add_eos : 0u) + (d < n_docs ? add_bos : 0u);
+            const uint32_t k = docs_from(doc_off, n_docs, wpos + bit + off_base, d0);
+            for (uint64_t d = d0; d < d0 + k; ++d) count += (d > 0 ? add_eos : 0u) + (d < n_docs ? add_bos : 0u);
+            d0 += k;
         }
     }
     uint32_t inc = count;
@@ -888,6 +891,7 @@ __global__ void __launch_bounds__(EM_T) emit_kernel(uint64_t n, const uint32_t* 
     uint32_t* comp = S.comp;
     {
         uint64_t o = my_off;
+        uint64_t d0 = mydoc;
         const uint32_t* src = src0;
         uint32_t m = mymask;
         while (m) {
@@ -895,9 +899,8 @@ __global__ void __launch_bounds__(EM_T) emit_kernel(uint64_t n, const uint32_t* 
             m &= m - 1;
             const uint64_t gpos = wpos + bit;
             if ((myds >> bit) & 1u) {
-                uint64_t first;
-                const uint64_t k = docs_at(doc_off, n_docs, gpos + off_base, &first);
-                for (uint64_t d = first; d < first + k; ++d) {
+                const uint32_t k = docs_from(doc_off, n_docs, gpos + off_base, d0);
+                for (uint64_t d = d0; d < d0 + k; ++d) {
                     if (d > 0 && add_eos) {
                         if (fits) comp[o] = eos_id; else if (base + o < out_cap) out[base + o] = eos_id;
                         ++o;
@@ -908,45 +911,65 @@ __global__ void __launch_bounds__(EM_T) emit_kernel(uint64_t n, const uint32_t* 
                         ++o;
                     }
                 }
+                d0 += k;
             }
             if (gpos >= n) continue;                        // the end-of-data sentinel is not a piece
             if (lw && bit == topbit) {
+                // long piece: all threads copy it after the walk
                 const TkkLongRec r = recs[lw - 1];
-                if (fits) {
-                    const uint32_t* ps = pool + r.tok_base;
-                    for (uint32_t j = 0; j < r.count; ++j) comp[o + j] = ps[j] + nsp;
-                } else {
-                    EnLongCopy c;
-                    c.dst = base + o; c.src = r.tok_base; c.count = r.count; c.pad = 0;
-                    S.longs[atomicAdd(&S.n_longs, 1u)] = c;
-                }
+                EnLongCopy c;
+                c.dst = o; c.src = r.tok_base; c.count = r.count; c.pad = 0;
+                S.longs[atomicAdd(&S.n_longs, 1u)] = c;
                 o += r.count;
                 continue;
             }
-            const uint32_t* p = src;
-            bool first_tok = true, hit = false;
-            for (;;) {
-                const uint32_t v = __ldg(p++);
-                if (first_tok) { hit = (v & EN_LAST) != 0u; first_tok = false; }
-                const uint32_t idv = (v & ~EN_LAST) + nsp;
+            // ranks of the piece: up to four slots are fetched at a time (reading past the piece is harmless)
+            const uint32_t v0 = __ldg(src);
+            if (v0 & EN_LAST) {
+                const uint32_t idv = (v0 & ~EN_LAST) + nsp;
                 if (fits) comp[o] = idv; else if (base + o < out_cap) out[base + o] = idv;
                 ++o;
-                if (v & EN_LAST) break;
+                src += 1;
+                continue;
             }
-            src += hit ? 1u : em_piece_len(start_mask, gw, mymask, bit);
+            const uint32_t len = em_piece_len(start_mask, gw, mymask, bit);
+            uint32_t v[4] = {v0, __ldg(src + 1), len > 2 ? __ldg(src + 2) : EN_LAST, len > 3 ? __ldg(src + 3) : EN_LAST};
+            for (uint32_t j = 0;;) {
+                bool done = false;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (!done) {
+                        const uint32_t idv = (v[c] & ~EN_LAST) + nsp;
+                        if (fits) comp[o] = idv; else if (base + o < out_cap) out[base + o] = idv;
+                        ++o;
+                        done = (v[c] & EN_LAST) != 0u;
+                    }
+                }
+                if (done) break;
+                j += 4;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) v[c] = j + c < len ? __ldg(src + j + c) : EN_LAST;
+            }
+            src += len;
         }
     }
     __syncthreads();
-    if (fits) {
-        for (uint32_t i = t; i < tile_total; i += EM_T)
-            if (base + i < out_cap) out[base + i] = comp[i];
-    } else {
+    {
         const uint32_t nl = S.n_longs;
         for (uint32_t k = 0; k < nl; ++k) {
             const EnLongCopy c = S.longs[k];
-            for (uint32_t i = t; i < c.count; i += EM_T)
-                if (c.dst + i < out_cap) out[c.dst + i] = pool[c.src + i] + nsp;
+            if (fits) {
+                for (uint32_t i = t; i < c.count; i += EM_T) comp[c.dst + i] = pool[c.src + i] + nsp;
+            } else {
+                for (uint32_t i = t; i < c.count; i += EM_T)
+                    if (base + c.dst + i < out_cap) out[base + c.dst + i] = pool[c.src + i] + nsp;
+            }
         }
+        if (nl && fits) __syncthreads();
+    }
+    if (fits) {
+        for (uint32_t i = t; i < tile_total; i += EM_T)
+            if (base + i < out_cap) out[base + i] = comp[i];
     }
 }
 
@@ -967,6 +990,7 @@ size_t encode_workspace_bytes(uint64_t n, uint64_t n_docs, EncodeLayout* L) {
     l.off_ds = take(words * 4);
     l.off_start = take(words * 4);
     l.off_longword = take(words * 4);
+    l.off_docfirst = take(words * 4);
     l.off_summ = take(n_tiles * sizeof(TkkTileSummary));
     l.off_carry = take(n_tiles * 4);
     l.off_worklist = take(n_tiles * 4);
@@ -1019,6 +1043,7 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
     uint32_t* ds = (uint32_t*)(ws + L.off_ds);
     uint32_t* start = (uint32_t*)(ws + L.off_start);
     uint32_t* longword = (uint32_t*)(ws + L.off_longword);
+    uint32_t* docfirst = (uint32_t*)(ws + L.off_docfirst);
     TkkTileSummary* summ = (TkkTileSummary*)(ws + L.off_summ);
     uint32_t* carry = (uint32_t*)(ws + L.off_carry);
     uint32_t* worklist = (uint32_t*)(ws + L.off_worklist);
@@ -1048,9 +1073,10 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
     CK(cudaMemsetAsync(small, 0, 256, st));
     CK(cudaMemsetAsync(err_pos, 0xFF, 8, st));
     CK(cudaMemsetAsync(ds, 0, L.mask_words * 4, st));
+    CK(cudaMemsetAsync(docfirst, 0xFF, L.mask_words * 4, st));
     CK(cudaMemsetAsync(start + L.n_windows, 0, (L.mask_words - L.n_windows) * 4, st));
     CK(cudaMemsetAsync(tilestate, 0, L.n_tiles * 8, st));
-    docmark_kernel<<<(unsigned)ceil_div(n_docs + 1, 256), 256, 0, st>>>(d_doc_off, off_base, n_docs, n, ds, flags);
+    docmark_kernel<<<(unsigned)ceil_div(n_docs + 1, 256), 256, 0, st>>>(d_doc_off, off_base, n_docs, n, ds, docfirst, flags);
     TK_LAUNCHED();
     if (timer) timer->mark(st, "pretok");
     pretok_kernel<<<(unsigned)L.n_tiles, PT_T, 0, st>>>(d_data, n, ds, start, L.n_windows, T, summ, err_pos);
@@ -1101,7 +1127,7 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
     CK((launch_lanemerge<4, 256>(8, sm_count, d_data, T, queues + L.queues.off[0], q_n + 0, q_w + 0, stream, win_info, st)));
     if (timer) timer->mark(st, "emit");
     static_assert(EM_WINS == PT_T, "emit tiles are the pre-tokeniser's tiles");
-    emit_kernel<<<(unsigned)L.n_tiles, EM_T, 0, st>>>(n, start, ds, longword, recs, pool, stream, win_info, d_doc_off, off_base, n_docs,
+    emit_kernel<<<(unsigned)L.n_tiles, EM_T, 0, st>>>(n, start, ds, docfirst, longword, recs, pool, stream, win_info, d_doc_off, off_base, n_docs,
                                                      add_bos ? 1u : 0u, add_eos ? 1u : 0u, T.num_special, T.bos_id, T.eos_id, d_out,
                                                      out_cap, d_tok_off, tilestate, ticket, total_out, flags);
     TK_LAUNCHED();
