@@ -83,7 +83,9 @@ __device__ __forceinline__ TkRunSummary rs_unpack(uint32_t p) {
 }
 #define RS_IDENTITY (1u | (2u << 3))
 
+#define PT_HALO 64
 struct PtSmem {
+    uint8_t bytes[PT_HALO + PT_T * 32 + PT_HALO];   // the tile's text with a halo; zero outside the text
     uint32_t lead[PT_T + 2], mL[PT_T + 2], mN[PT_T + 2], mR[PT_T + 2], mW[PT_T + 2], sp[PT_T + 2], ap[PT_T + 2],
         ds[PT_T + 2];
     uint32_t head[PT_T + 1];
@@ -102,30 +104,16 @@ __device__ __forceinline__ TkWin pt_load(const PtSmem& S, int i) {
     return w;
 }
 
-__device__ __forceinline__ TkWin pt_classify(const uint8_t* __restrict__ data, uint64_t n, const uint32_t* __restrict__ ds_mask,
-                                             uint64_t n_windows, long long wi, const TkDeviceTables& T) {
+// classify window wi of the text from the staged tile (wl = its index inside the tile, -1 .. PT_T)
+__device__ __forceinline__ TkWin pt_classify(const PtSmem& S, const TkBytesTile& src, const uint32_t* __restrict__ ds_mask,
+                                             uint64_t n_windows, long long wi, int wl, const TkDeviceTables& T) {
     TkWin z;
     z.lead = 0xFFFFFFFFu; z.mL = z.mN = z.mR = z.mW = z.sp = z.ap = z.ds = z.bad = 0;
     if (wi < 0 || (uint64_t)wi >= n_windows) return z;
-    const uint64_t pos = (uint64_t)wi * 32u;
-    uint32_t w[8];
-    if (pos + 32 <= n) {
-        const uint4 a = __ldg((const uint4*)(data + pos));
-        const uint4 b = __ldg((const uint4*)(data + pos) + 1);
-        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
-    } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            uint32_t v = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                uint64_t q = pos + 4 * j + k;
-                if (q < n) v |= (uint32_t)data[q] << (8 * k);
-            }
-            w[j] = v;
-        }
-    }
-    return tk_classify_window(data, n, pos, w, ds_mask[wi], T);
+    const uint4* q = reinterpret_cast<const uint4*>(S.bytes + PT_HALO + wl * 32);
+    const uint4 a = q[0], b = q[1];
+    uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    return tk_classify_window(src, (uint64_t)wi * 32u, w, ds_mask[wi], T);
 }
 
 // Process tile b.  FIX=false: first pass (entry state guessed from the halo window, summary
@@ -138,11 +126,32 @@ __device__ __forceinline__ void pretok_tile(PtSmem& S, uint32_t b, const uint8_t
     const int t = threadIdx.x;
     const long long wi = (long long)b * PT_T + t;
     const uint64_t pos = (uint64_t)wi * 32u;
-    TkWin c = pt_classify(data, n, ds_mask, n_windows, wi, T);
+    // stage [tile - halo, tile + 8 KiB + halo) in shared memory, zero outside the text
+    {
+        const long long g0 = (long long)b * (PT_T * 32) - PT_HALO;
+        uint4* dst = reinterpret_cast<uint4*>(S.bytes);
+        for (int i = t; i < (int)(sizeof(S.bytes) / 16); i += PT_T) {
+            const long long g = g0 + 16ll * i;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (g >= 0 && (uint64_t)g + 16u <= n) v = __ldg(reinterpret_cast<const uint4*>(data + g));
+            else if (g + 16 > 0 && (uint64_t)(g < 0 ? 0 : g) < n) {
+                uint32_t x[4] = {0u, 0u, 0u, 0u};
+                for (int k = 0; k < 16; ++k) {
+                    const long long q = g + k;
+                    if (q >= 0 && (uint64_t)q < n) x[k >> 2] |= (uint32_t)data[q] << (8 * (k & 3));
+                }
+                v = make_uint4(x[0], x[1], x[2], x[3]);
+            }
+            dst[i] = v;
+        }
+    }
+    __syncthreads();
+    const TkBytesTile src{S.bytes + PT_HALO, (int64_t)b * (PT_T * 32)};
+    TkWin c = pt_classify(S, src, ds_mask, n_windows, wi, t, T);
     pt_store(S, t + 1, c);
     if (t < 2) {
         const long long hw = t == 0 ? (long long)b * PT_T - 1 : (long long)b * PT_T + PT_T;
-        TkWin h = pt_classify(data, n, ds_mask, n_windows, hw, T);
+        TkWin h = pt_classify(S, src, ds_mask, n_windows, hw, t == 0 ? -1 : PT_T, T);
         pt_store(S, t == 0 ? 0 : PT_T + 1, h);
     }
     if (t == 0) S.pend = -1;
@@ -150,8 +159,8 @@ __device__ __forceinline__ void pretok_tile(PtSmem& S, uint32_t b, const uint8_t
     const TkWin p = pt_load(S, t), nx = pt_load(S, t + 2);
     TkWin zero;
     zero.lead = 0xFFFFFFFFu; zero.mL = zero.mN = zero.mR = zero.mW = zero.sp = zero.ap = zero.ds = zero.bad = 0;
-    const TkDerived dp = tk_derive(data, n, pos - 32, zero, p, c, 0);
-    const TkDerived dc = tk_derive(data, n, pos, p, c, nx, dp.sO);
+    const TkDerived dp = tk_derive(src, pos - 32, zero, p, c, 0);
+    const TkDerived dc = tk_derive(src, pos, p, c, nx, dp.sO);
     const TkRunSummary mine = tk_summarize(c);
     S.head[t] = mine.head;
     if (t == 0) S.head[PT_T] = tk_summarize(pt_load(S, PT_T + 1)).head;
@@ -223,7 +232,7 @@ __global__ void __launch_bounds__(PT_T) pretok_kernel(const uint8_t* __restrict_
                                                       const uint32_t* __restrict__ ds_mask, uint32_t* __restrict__ start_mask,
                                                       uint64_t n_windows, TkDeviceTables T, TkkTileSummary* __restrict__ summ,
                                                       unsigned long long* __restrict__ err_pos) {
-    __shared__ PtSmem S;
+    __shared__ __align__(16) PtSmem S;
     pretok_tile<false>(S, blockIdx.x, data, n, ds_mask, start_mask, n_windows, T, summ, nullptr, err_pos);
 }
 
@@ -232,7 +241,7 @@ __global__ void __launch_bounds__(PT_T) pretok_fix_kernel(const uint8_t* __restr
                                                           uint64_t n_windows, TkDeviceTables T, const uint32_t* __restrict__ carry,
                                                           const uint32_t* __restrict__ worklist, const uint32_t* __restrict__ work_count,
                                                           unsigned long long* __restrict__ err_pos) {
-    __shared__ PtSmem S;
+    __shared__ __align__(16) PtSmem S;
     const uint32_t cnt = *work_count;
     for (uint32_t w = blockIdx.x; w < cnt; w += gridDim.x) {
         pretok_tile<true>(S, worklist[w], data, n, ds_mask, start_mask, n_windows, T, nullptr, carry, err_pos);

@@ -52,38 +52,55 @@ TK_HD uint32_t tk_swar_eq(uint32_t w7, uint32_t c) { return ~((w7 ^ (c * 0x01010
 // gather the four 0x80 flag bits of a word into bits 0..3
 TK_HD uint32_t tk_swar_nib(uint32_t flags) { return (((flags >> 7) * 0x00204081u) >> 21) & 0xFu; }
 
-// One byte of the text with bounds (bytes outside [0, n) read as 0).
+// Where the bytes around a window come from.  TkBytesChecked reads the text itself (bytes outside
+// [0, n) read as 0).  TkBytesTile reads a shared-memory copy of a tile and its halo in which the
+// bytes outside the text are already zero, so no bounds are checked; a character cut off by the
+// end of the text then fails on its missing continuation bytes.
+struct TkBytesChecked {
+    const uint8_t* data;
+    uint64_t n;
+    TK_HD uint32_t at(int64_t pos) const { return (pos >= 0 && (uint64_t)pos < n) ? (uint32_t)data[pos] : 0u; }
+    TK_HD bool past_end(int64_t end) const { return (uint64_t)end > n; }
+};
+struct TkBytesTile {
+    const uint8_t* base;   // base[pos - origin] is the byte at text position pos
+    int64_t origin;
+    TK_HD uint32_t at(int64_t pos) const { return (uint32_t)base[pos - origin]; }
+    TK_HD bool past_end(int64_t) const { return false; }
+};
+
 TK_HD uint32_t tk_byte_at(const uint8_t* data, uint64_t n, int64_t pos) {
     return (pos >= 0 && (uint64_t)pos < n) ? (uint32_t)data[pos] : 0u;
 }
 
 // Strict decode of the scalar value whose lead byte is at pos.  Returns its length (1..4) and
 // class in *cls, or 0 if the bytes are not valid UTF-8.
-TK_HD int tk_decode_at(const uint8_t* data, uint64_t n, int64_t pos, const TkDeviceTables& T, uint32_t* cls) {
-    uint32_t b0 = tk_byte_at(data, n, pos);
+template <class B>
+TK_HD int tk_decode_at(const B& src, int64_t pos, const TkDeviceTables& T, uint32_t* cls) {
+    uint32_t b0 = src.at(pos);
     uint32_t cp;
     int len;
     if (b0 < 0x80u) { cp = b0; len = 1; }
     else if (b0 < 0xC2u) return 0;
     else if (b0 < 0xE0u) {
-        uint32_t b1 = tk_byte_at(data, n, pos + 1);
+        uint32_t b1 = src.at(pos + 1);
         if ((b1 & 0xC0u) != 0x80u) return 0;
         cp = ((b0 & 0x1Fu) << 6) | (b1 & 0x3Fu);
         len = 2;
     } else if (b0 < 0xF0u) {
-        uint32_t b1 = tk_byte_at(data, n, pos + 1), b2 = tk_byte_at(data, n, pos + 2);
+        uint32_t b1 = src.at(pos + 1), b2 = src.at(pos + 2);
         if ((b1 & 0xC0u) != 0x80u || (b2 & 0xC0u) != 0x80u) return 0;
         cp = ((b0 & 0x0Fu) << 12) | ((b1 & 0x3Fu) << 6) | (b2 & 0x3Fu);
         if (cp < 0x800u || (cp >= 0xD800u && cp <= 0xDFFFu)) return 0;
         len = 3;
     } else if (b0 < 0xF5u) {
-        uint32_t b1 = tk_byte_at(data, n, pos + 1), b2 = tk_byte_at(data, n, pos + 2), b3 = tk_byte_at(data, n, pos + 3);
+        uint32_t b1 = src.at(pos + 1), b2 = src.at(pos + 2), b3 = src.at(pos + 3);
         if ((b1 & 0xC0u) != 0x80u || (b2 & 0xC0u) != 0x80u || (b3 & 0xC0u) != 0x80u) return 0;
         cp = ((b0 & 0x07u) << 18) | ((b1 & 0x3Fu) << 12) | ((b2 & 0x3Fu) << 6) | (b3 & 0x3Fu);
         if (cp < 0x10000u || cp > 0x10FFFFu) return 0;
         len = 4;
     } else return 0;
-    if ((uint64_t)(pos + len) > n) return 0;
+    if (src.past_end(pos + len)) return 0;
     if (cp == 0x0Au || cp == 0x0Du) *cls = TK_CL_R;
     else *cls = tk_class_lookup(T.uni_stage1, T.uni_stage2, cp);
     return len;
@@ -91,8 +108,8 @@ TK_HD int tk_decode_at(const uint8_t* data, uint64_t n, int64_t pos, const TkDev
 
 // Classify the 32-byte window at byte offset `pos` (a multiple of 32).  w[0..7] are its bytes as
 // little-endian words, zero padded beyond n.  ds_word = document-start bits of the window.
-TK_HD TkWin tk_classify_window(const uint8_t* data, uint64_t n, uint64_t pos, const uint32_t* w,
-                               uint32_t ds_word, const TkDeviceTables& T) {
+template <class B>
+TK_HD TkWin tk_classify_window(const B& src, uint64_t pos, const uint32_t* w, uint32_t ds_word, const TkDeviceTables& T) {
     TkWin r;
     uint32_t mL = 0, mN = 0, mR = 0, mW = 0, sp = 0, ap = 0, hi = 0;
 #pragma unroll
@@ -131,9 +148,9 @@ TK_HD TkWin tk_classify_window(const uint8_t* data, uint64_t n, uint64_t pos, co
         if (lc > 0) {
             int back = 0;
             int64_t q = (int64_t)pos - 1;
-            while (back < 3 && q >= 0 && (tk_byte_at(data, n, q) & 0xC0u) == 0x80u) { --q; ++back; }
+            while (back < 3 && q >= 0 && (src.at(q) & 0xC0u) == 0x80u) { --q; ++back; }
             uint32_t cls = TK_CL_O;
-            const int len = (q >= 0) ? tk_decode_at(data, n, q, T, &cls) : 0;
+            const int len = (q >= 0) ? tk_decode_at(src, q, T, &cls) : 0;
             // bytes of that char that fall into this window; leading continuation bytes beyond
             // them stay uncovered and are flagged below
             const int64_t over = len ? q + len - (int64_t)pos : 0;
@@ -149,7 +166,7 @@ TK_HD TkWin tk_classify_window(const uint8_t* data, uint64_t n, uint64_t pos, co
             int i = TK_FFS(todo) - 1;
             todo &= todo - 1;
             uint32_t cls = TK_CL_O;
-            int len = tk_decode_at(data, n, (int64_t)pos + i, T, &cls);
+            int len = tk_decode_at(src, (int64_t)pos + i, T, &cls);
             if (len == 0) { bad |= 1u << i; continue; }
             uint32_t m = (len >= 32 - i) ? (0xFFFFFFFFu << i) : (((1u << len) - 1u) << i);
             covered |= m;
@@ -162,16 +179,22 @@ TK_HD TkWin tk_classify_window(const uint8_t* data, uint64_t n, uint64_t pos, co
     return r;
 }
 
+TK_HD TkWin tk_classify_window(const uint8_t* data, uint64_t n, uint64_t pos, const uint32_t* w,
+                               uint32_t ds_word, const TkDeviceTables& T) {
+    return tk_classify_window(TkBytesChecked{data, n}, pos, w, ds_word, T);
+}
+
 // ---- contraction alternative (?i:'s|'t|'re|'ve|'m|'ll|'d) ------------------------------------
 // Unicode simple case folding adds exactly one non-ASCII member: U+017F (long s, C5 BF) ~ 's'.
 // Returns 0 (no match), 2 ('x), 3 ('xy) or 4 (' + long s: 3 bytes).  `stop` = number of bytes
 // after the apostrophe that still belong to the same document.
-TK_HD int tk_contraction_len(const uint8_t* data, uint64_t n, int64_t apos, int stop) {
+template <class B>
+TK_HD int tk_contraction_len(const B& src, int64_t apos, int stop) {
     if (stop < 1) return 0;
-    uint32_t c1 = tk_byte_at(data, n, apos + 1) | 0x20u;
+    uint32_t c1 = src.at(apos + 1) | 0x20u;
     if (c1 == 's' || c1 == 't' || c1 == 'm' || c1 == 'd') return 2;
     if (stop < 2) return 0;
-    uint32_t b1 = tk_byte_at(data, n, apos + 1), b2 = tk_byte_at(data, n, apos + 2);
+    uint32_t b1 = src.at(apos + 1), b2 = src.at(apos + 2);
     if (b1 == 0xC5u && b2 == 0xBFu) return 4;
     uint32_t c2 = b2 | 0x20u;
     if ((c1 == 'r' || c1 == 'v') && c2 == 'e') return 3;
@@ -191,8 +214,8 @@ TK_HD uint32_t tk_shl(uint32_t c, uint32_t p, int k) { return (c << k) | (p >> (
 TK_HD uint32_t tk_shr(uint32_t c, uint32_t nx, int k) { return (c >> k) | (nx << (32 - k)); }
 
 // p = previous window (may be all-zero when unknown; then only bits >= 4 of the result are exact).
-TK_HD TkDerived tk_derive(const uint8_t* data, uint64_t n, uint64_t pos, const TkWin& p, const TkWin& c,
-                          const TkWin& nx, uint32_t sO_prev) {
+template <class B>
+TK_HD TkDerived tk_derive(const B& src, uint64_t pos, const TkWin& p, const TkWin& c, const TkWin& nx, uint32_t sO_prev) {
     TkDerived d;
     uint32_t P_O = tk_shl(tk_mO(c), tk_mO(p), 1), P_SP = tk_shl(c.sp, p.sp, 1);
     uint32_t startok = c.ds | ~(P_O | P_SP);
@@ -211,10 +234,15 @@ TK_HD TkDerived tk_derive(const uint8_t* data, uint64_t n, uint64_t pos, const T
         // bytes after the apostrophe up to the next document start
         uint64_t dsn = ((uint64_t)nx.ds << 32 | c.ds) >> (i + 1);
         int stop = dsn ? TK_FFSLL(dsn) - 1 : 8;
-        int len = tk_contraction_len(data, n, (int64_t)pos + i, stop);
+        int len = tk_contraction_len(src, (int64_t)pos + i, stop);
         if (len == 2) d.f2 |= 1u << i; else if (len == 3) d.f3 |= 1u << i; else if (len == 4) d.f4 |= 1u << i;
     }
     return d;
+}
+
+TK_HD TkDerived tk_derive(const uint8_t* data, uint64_t n, uint64_t pos, const TkWin& p, const TkWin& c,
+                          const TkWin& nx, uint32_t sO_prev) {
+    return tk_derive(TkBytesChecked{data, n}, pos, p, c, nx, sO_prev);
 }
 
 // ---- run summaries carried between windows ---------------------------------------------------
