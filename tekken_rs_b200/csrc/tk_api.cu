@@ -196,6 +196,8 @@ static int finish_handle(tk_tokenizer* t, int device, tk_tokenizer** out) {
         if (err == cudaSuccess) err = upload(t, h.vocab_slots, (const void**)&T.vocab_slots);
         if (err == cudaSuccess) err = upload(t, h.pair_slots, (const void**)&T.pair_slots);
         if (err == cudaSuccess) err = upload(t, h.byte_pair, (const void**)&T.byte_pair);
+        if (err == cudaSuccess) err = upload(t, h.vocab_pad16, (const void**)&T.vocab_pad16);
+        if (err == cudaSuccess) err = upload(t, h.vocab_len8, (const void**)&T.vocab_len);
         if (err == cudaSuccess) err = upload(t, h.vocab_bytes, (const void**)&T.vocab_bytes);
         if (err == cudaSuccess) err = upload(t, h.vocab_off, (const void**)&T.vocab_off);
         if (err == cudaSuccess) err = upload(t, h.special_bytes, (const void**)&T.special_bytes);
@@ -619,6 +621,7 @@ static int run_decode(tk_tokenizer* t, const uint32_t* d_ids, const uint64_t* d_
     if (policy != TK_POLICY_IGNORE && policy != TK_POLICY_KEEP && policy != TK_POLICY_RAISE)
         return fail(TK_ERR_INVALID_ARGUMENT, "unknown special token policy %d", policy);
     if (((uintptr_t)d_ids & 3u) != 0) return fail(TK_ERR_INVALID_ARGUMENT, "id pointer must be 4-byte aligned");
+    if ((uint64_t)n_docs >= 0xFFFFFFFEull) return fail(TK_ERR_INVALID_ARGUMENT, "too many sequences in one call; shard the batch");
     tkk::DecodeLayout L;
     size_t ws_bytes = tkk::decode_workspace_bytes(n_ids, n_docs, cap, &L);
     CUDA_OR_FAIL(t->ws.ensure(ws_bytes));

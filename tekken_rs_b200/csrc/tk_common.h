@@ -1,6 +1,11 @@
 // tk_common.h -- types and hash functions shared by the host table builders and the kernels.
 #pragma once
 #include <stdint.h>
+#if defined(__CUDACC__)
+#include <vector_types.h>
+#else
+struct uint4 { uint32_t x, y, z, w; };
+#endif
 
 #if defined(__CUDACC__)
 #define TK_HD __host__ __device__ __forceinline__
@@ -76,6 +81,8 @@ struct TkDeviceTables {
     const uint64_t* pair_slots;
     uint32_t pair_mask;
     const uint32_t* byte_pair;     // [b0 << 8 | b1] -> rank of the two-byte token, TK_INF if none
+    const uint4* vocab_pad16;      // token bytes zero-padded to 16 (tokens longer than that: first 16 bytes)
+    const uint8_t* vocab_len;      // token length, 255 = look at vocab_off
     const uint8_t* vocab_bytes;    // concatenated token bytes, rank order
     const uint32_t* vocab_off;     // n_vocab + 1
     const uint8_t* special_bytes;  // concatenated special strings, positional order

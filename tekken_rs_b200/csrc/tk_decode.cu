@@ -27,7 +27,7 @@ struct DocErr {
 };
 
 __global__ void tokmark_kernel(const uint64_t* __restrict__ tok_off, uint64_t n_docs, uint64_t total,
-                               uint32_t* __restrict__ tds, uint32_t* __restrict__ flags) {
+                               uint32_t* __restrict__ tds, uint32_t* __restrict__ seq_first, uint32_t* __restrict__ flags) {
     uint64_t d = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (d > n_docs) return;
     uint64_t o = tok_off[d];
@@ -37,6 +37,7 @@ __global__ void tokmark_kernel(const uint64_t* __restrict__ tok_off, uint64_t n_
     if (d < n_docs && tok_off[d + 1] < o) ok = false;
     if (!ok) { atomicOr(flags, TKK_FLAG_BAD_OFFSETS); return; }
     atomicOr(tds + (o >> 5), 1u << (o & 31));
+    atomicMin(seq_first + (o >> 5), (uint32_t)d);     // first sequence that starts in this group of 32 ids
 }
 
 // index of the sequence that contains position i (last d < n_docs with off[d] <= i)
@@ -53,14 +54,28 @@ __device__ __forceinline__ void mark_boundary(uint32_t* __restrict__ bmask, uint
     if (o <= cap) atomicOr(bmask + (o >> 5), 1u << (o & 31));
 }
 
+#define DC_BUF 12288      // bytes of a tile's text staged in shared memory (larger tiles write straight to global memory)
+
+// Copy l bytes of a token into the tile's staging buffer or, for an oversized tile, to the output.
+__device__ __forceinline__ void dc_put(uint8_t* __restrict__ buf, bool fits, uint32_t p, uint8_t* __restrict__ out, uint64_t o,
+                                       uint64_t out_cap, const uint8_t* __restrict__ src, uint32_t l) {
+    if (fits) {
+        for (uint32_t j = 0; j < l; ++j) buf[p + j] = __ldg(src + j);
+    } else if (o + l <= out_cap) {
+        for (uint32_t j = 0; j < l; ++j) out[o + j] = __ldg(src + j);
+    }
+}
+
 __global__ void __launch_bounds__(DC_T) decode_gather_kernel(const uint32_t* __restrict__ ids, uint64_t n_ids,
                                                              const uint64_t* __restrict__ tok_off, uint64_t n_docs,
-                                                             const uint32_t* __restrict__ tds, int policy, TkDeviceTables T,
+                                                             const uint32_t* __restrict__ tds, const uint32_t* __restrict__ seq_first,
+                                                             int policy, TkDeviceTables T,
                                                              uint8_t* __restrict__ out, uint64_t out_cap,
                                                              uint64_t* __restrict__ byte_off, uint32_t* __restrict__ bmask,
                                                              DocErr* __restrict__ docerr, unsigned long long* __restrict__ tile_state,
                                                              uint32_t* __restrict__ ticket, unsigned long long* __restrict__ total_out,
                                                              uint32_t* __restrict__ flags) {
+    __shared__ __align__(16) uint8_t buf[DC_BUF + 32];
     __shared__ uint32_t wsum[DC_T / 32];
     __shared__ unsigned long long s_base;
     __shared__ uint32_t s_tile;
@@ -71,19 +86,31 @@ __global__ void __launch_bounds__(DC_T) decode_gather_kernel(const uint32_t* __r
     const uint64_t i0 = (uint64_t)tile * DC_TILE + (uint64_t)t * DC_PER;
     uint32_t id[DC_PER], len[DC_PER];
     uint32_t sum = 0;
+    {
+        // 8 consecutive ids per thread: two 16-byte loads when they are all there
+        uint32_t raw[DC_PER];
+        if (i0 + DC_PER <= n_ids && ((uintptr_t)ids & 15u) == 0) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(ids + i0)), b = __ldg(reinterpret_cast<const uint4*>(ids + i0) + 1);
+            raw[0] = a.x; raw[1] = a.y; raw[2] = a.z; raw[3] = a.w; raw[4] = b.x; raw[5] = b.y; raw[6] = b.z; raw[7] = b.w;
+        } else {
 #pragma unroll
-    for (int k = 0; k < DC_PER; ++k) {
-        const uint64_t i = i0 + k;
-        uint32_t l = 0, v = 0;
-        if (i < n_ids) {
-            v = __ldg(ids + i);
-            if (v < T.num_special) l = policy == TK_POLICY_KEEP ? T.special_off[v + 1] - T.special_off[v] : 0u;
-            else {
-                const uint32_t r = v - T.num_special;
-                l = r < T.n_vocab ? T.vocab_off[r + 1] - T.vocab_off[r] : 0u;
-            }
+            for (int k = 0; k < DC_PER; ++k) raw[k] = i0 + k < n_ids ? __ldg(ids + i0 + k) : 0u;
         }
-        id[k] = v; len[k] = l; sum += l;
+#pragma unroll
+        for (int k = 0; k < DC_PER; ++k) {
+            const uint64_t i = i0 + k;
+            uint32_t l = 0;
+            const uint32_t v = raw[k];
+            if (i < n_ids) {
+                if (v < T.num_special) l = policy == TK_POLICY_KEEP ? T.special_off[v + 1] - T.special_off[v] : 0u;
+                else {
+                    const uint32_t r = v - T.num_special;
+                    l = r < T.n_vocab ? (uint32_t)__ldg(T.vocab_len + r) : 0u;
+                    if (l == 255u) l = T.vocab_off[r + 1] - T.vocab_off[r];
+                }
+            }
+            id[k] = v; len[k] = l; sum += l;
+        }
     }
     uint32_t inc = sum;
 #pragma unroll
@@ -107,20 +134,21 @@ __global__ void __launch_bounds__(DC_T) decode_gather_kernel(const uint32_t* __r
         }
     }
     __syncthreads();
-    uint64_t o = s_base + before + inc - sum;
+    const uint64_t base = s_base;
+    const bool fits = tile_total <= DC_BUF;              // block-uniform
+    const uint32_t shift = (uint32_t)(base & 15u);         // staging keeps the output's 16-byte phase
+    uint32_t p = shift + before + inc - sum;               // my first byte in the staging buffer
+    uint64_t o = base + before + inc - sum;
     // sequence starts among my positions (the sentinel position n_ids included)
     const uint32_t tw = tds[i0 >> 5] >> (i0 & 31);   // DC_PER divides 32 -> my 8 bits are in one word
+    uint64_t seq = (tw & 0xFFu) ? seq_first[i0 >> 5] : 0;   // first sequence of my group of 32 ids; advanced below
 #pragma unroll
     for (int k = 0; k < DC_PER; ++k) {
         const uint64_t i = i0 + k;
         if (i > n_ids) break;
         if ((tw >> k) & 1u) {
-            uint64_t lo = 0, hi = n_docs + 1;
-            while (lo < hi) {
-                uint64_t mid = (lo + hi) >> 1;
-                if (tok_off[mid] < i) lo = mid + 1; else hi = mid;
-            }
-            for (uint64_t d = lo; d <= n_docs && tok_off[d] == i; ++d) byte_off[d] = o;
+            while (tok_off[seq] < i) ++seq;              // sequences that start earlier in the group
+            for (; seq <= n_docs && tok_off[seq] == i; ++seq) byte_off[seq] = o;
             mark_boundary(bmask, o, out_cap);
         }
         if (i == n_ids) break;
@@ -133,9 +161,7 @@ __global__ void __launch_bounds__(DC_T) decode_gather_kernel(const uint32_t* __r
                 atomicMin(&docerr[d].sp_tok, (unsigned long long)i);
                 atomicMin(&docerr[d].sp_byte, (unsigned long long)o);
             } else if (policy == TK_POLICY_KEEP) {
-                const uint8_t* src = T.special_bytes + T.special_off[v];
-                if (o + l <= out_cap)
-                    for (uint32_t j = 0; j < l; ++j) out[o + j] = __ldg(src + j);
+                dc_put(buf, fits, p, out, o, out_cap, T.special_bytes + T.special_off[v], l);
                 mark_boundary(bmask, o + l, out_cap);
             }
         } else {
@@ -143,13 +169,40 @@ __global__ void __launch_bounds__(DC_T) decode_gather_kernel(const uint32_t* __r
             if (r >= T.n_vocab) {
                 const uint64_t d = seq_of(tok_off, n_docs, i);
                 atomicMin(&docerr[d].unk_tok, (unsigned long long)i);
+            } else if (l <= 16u && fits) {
+                // the token's bytes in one aligned 16-byte load from the padded table
+                const uint4 q = __ldg(T.vocab_pad16 + r);
+                uint32_t cur = q.x;
+                for (uint32_t j = 0; j < l; ++j) {
+                    if ((j & 3u) == 0u && j) cur = j == 4u ? q.y : j == 8u ? q.z : q.w;
+                    buf[p + j] = (uint8_t)cur;
+                    cur >>= 8;
+                }
             } else {
-                const uint8_t* src = T.vocab_bytes + T.vocab_off[r];
-                if (o + l <= out_cap)
-                    for (uint32_t j = 0; j < l; ++j) out[o + j] = __ldg(src + j);
+                dc_put(buf, fits, p, out, o, out_cap, T.vocab_bytes + T.vocab_off[r], l);
             }
         }
         o += l;
+        p += l;
+    }
+    if (!fits) return;
+    __syncthreads();
+    // staging buffer -> output: aligned 16-byte stores in the middle, single bytes at the ragged ends
+    {
+        const uint64_t lim = base + tile_total < out_cap ? base + tile_total : out_cap;   // never write past the caller's buffer
+        if (lim <= base) return;
+        const uint64_t a0 = base - shift;                       // 16-byte aligned global address of buf[0]
+        const uint32_t n_chunks = (uint32_t)((lim - a0 + 15u) / 16u);
+        const bool aligned = ((uintptr_t)out & 15u) == 0;
+        for (uint32_t c = t; c < n_chunks; c += DC_T) {
+            const uint64_t g = a0 + 16ull * c;
+            if (aligned && g >= base && g + 16u <= lim) {
+                *reinterpret_cast<uint4*>(out + g) = *reinterpret_cast<const uint4*>(buf + 16u * c);
+            } else {
+                for (uint32_t j = 0; j < 16u; ++j)
+                    if (g + j >= base && g + j < lim) out[g + j] = buf[16u * c + j];
+            }
+        }
     }
 }
 
@@ -255,6 +308,7 @@ size_t decode_workspace_bytes(uint64_t n_ids, uint64_t n_docs, uint64_t out_cap,
     l.mask_words_out = out_cap / 32 + 8;
     l.off_small = take(256);
     l.off_tds = take(l.mask_words_tok * 4);
+    l.off_seqfirst = take(l.mask_words_tok * 4);
     l.off_bmask = take(l.mask_words_out * 4);
     l.off_tilestate = take(l.n_tiles * 8);
     l.off_docerr = take((n_docs + 1) * sizeof(DocErr));
@@ -271,6 +325,7 @@ cudaError_t decode_device(const TkDeviceTables& T, const uint32_t* d_ids, const 
     unsigned char* ws = (unsigned char*)d_ws;
     uint32_t* small = (uint32_t*)(ws + L.off_small);
     uint32_t* tds = (uint32_t*)(ws + L.off_tds);
+    uint32_t* seq_first = (uint32_t*)(ws + L.off_seqfirst);
     uint32_t* bmask = (uint32_t*)(ws + L.off_bmask);
     unsigned long long* tilestate = (unsigned long long*)(ws + L.off_tilestate);
     DocErr* docerr = (DocErr*)(ws + L.off_docerr);
@@ -281,12 +336,13 @@ cudaError_t decode_device(const TkDeviceTables& T, const uint32_t* d_ids, const 
     CK(cudaMemsetAsync(small, 0, 256, st));
     CK(cudaMemsetAsync(first_bad, 0xFF, 8, st));
     CK(cudaMemsetAsync(tds, 0, L.mask_words_tok * 4, st));
+    CK(cudaMemsetAsync(seq_first, 0xFF, L.mask_words_tok * 4, st));
     CK(cudaMemsetAsync(bmask, 0, L.mask_words_out * 4, st));
     CK(cudaMemsetAsync(tilestate, 0, L.n_tiles * 8, st));
     CK(cudaMemsetAsync(docerr, 0xFF, (n_docs + 1) * sizeof(DocErr), st));
-    tokmark_kernel<<<(unsigned)ceil_div(n_docs + 1, 256), 256, 0, st>>>(d_tok_off, n_docs, n_ids, tds, flags);
+    tokmark_kernel<<<(unsigned)ceil_div(n_docs + 1, 256), 256, 0, st>>>(d_tok_off, n_docs, n_ids, tds, seq_first, flags);
     count_launch();
-    decode_gather_kernel<<<(unsigned)L.n_tiles, DC_T, 0, st>>>(d_ids, n_ids, d_tok_off, n_docs, tds, policy, T, d_out, out_cap,
+    decode_gather_kernel<<<(unsigned)L.n_tiles, DC_T, 0, st>>>(d_ids, n_ids, d_tok_off, n_docs, tds, seq_first, policy, T, d_out, out_cap,
                                                              d_byte_off, bmask, docerr, tilestate, ticket, total_out, flags);
     count_launch();
     {

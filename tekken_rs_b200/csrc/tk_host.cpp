@@ -621,6 +621,16 @@ HostModel HostModel::build(const std::vector<VocabEntry>& vocab, const std::vect
             m.pair_slots[i] = e;
         }
     }
+    // decode's gather source: every token in an aligned 16-byte cell + its length in a byte
+    {
+        m.vocab_pad16.assign(16 * std::max<size_t>(n_vocab, 1), 0);
+        m.vocab_len8.assign(std::max<size_t>(n_vocab, 1), 0);
+        for (size_t r = 0; r < n_vocab; ++r) {
+            uint32_t len = m.vocab_off[r + 1] - m.vocab_off[r];
+            memcpy(&m.vocab_pad16[16 * r], &m.vocab_bytes[m.vocab_off[r]], std::min<uint32_t>(len, 16));
+            m.vocab_len8[r] = (uint8_t)std::min<uint32_t>(len, 255);
+        }
+    }
     // first-round pair ranks (both parts are single bytes): direct-indexed, no probing
     {
         m.byte_pair.assign(65536, TK_INF);

@@ -63,6 +63,8 @@ struct HostModel {
     std::vector<TkVocabSlot> vocab_slots;
     std::vector<uint64_t> pair_slots;
     std::vector<uint32_t> byte_pair;                          // 65536 entries, direct-indexed
+    std::vector<uint8_t> vocab_pad16;                         // 16 bytes per rank (decode's gather source)
+    std::vector<uint8_t> vocab_len8;                          // length per rank, 255 = longer than 254
     std::vector<uint8_t> special_bytes;
     std::vector<uint32_t> special_off;
     size_t n_pairs = 0;

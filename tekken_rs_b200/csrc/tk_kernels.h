@@ -64,7 +64,7 @@ struct EncodeLayout {
 
 struct DecodeLayout {
     uint64_t n_tiles, mask_words_tok, mask_words_out;
-    size_t off_small, off_tds, off_bmask, off_tilestate, off_docerr, total;
+    size_t off_small, off_tds, off_seqfirst, off_bmask, off_tilestate, off_docerr, total;
 };
 
 // optional per-stage CUDA-event timing
