@@ -127,10 +127,24 @@ def cpu_rate(orc, data, off, threads: int, reps: int = 1):
     return len(data) / best / 1e9, n_tok / best, best
 
 
-def cpu_sample(n_docs_total: int, threads: int):
+WORKLOAD = "mixed"
+
+
+def make_docs(n_docs: int, first_doc: int = 0):
+    """The step's documents: (bytes uint8, doc_off uint64[n_docs+1])."""
     from tekken_rs_b200 import corpus
+    if WORKLOAD == "mixed":
+        return corpus.mixed_script_docs(n_docs, SEED, first_doc=first_doc)
+    # English-like ASCII (config 1's generator), 1 KiB per document; the 64 MiB base text repeats
+    base = np.frombuffer(corpus.english_like(1 << 26, 1234 + first_doc), dtype=np.uint8)
+    reps = -(-n_docs * 1024 // len(base))
+    data = np.tile(base, reps)[:n_docs * 1024]
+    return data, np.arange(n_docs + 1, dtype=np.uint64) * np.uint64(1024)
+
+
+def cpu_sample(n_docs_total: int, threads: int):
     n = int(min(n_docs_total, max(16384, 32768 * threads)))
-    data, off = corpus.mixed_script_docs(n, SEED)
+    data, off = make_docs(n)
     return data, off, "first %d of %d documents of the workload (%.0f MB), all ids computed, %d threads" % (
         n, n_docs_total, len(data) / 1e6, threads)
 
@@ -168,7 +182,10 @@ def run_reference(args):
 
 
 def workload_config(args, n_docs, n_bytes):
-    return {"workload": "BASELINE configs[1]: batch encode of %d synthetic mixed-script UTF-8 documents x <=1 KiB per GPU (seed %d), add_bos+add_eos" % (args.docs, SEED),
+    name = ("BASELINE configs[1]: batch encode of %d synthetic mixed-script UTF-8 documents x <=1 KiB per GPU (seed %d), add_bos+add_eos" % (args.docs, SEED)
+            if WORKLOAD == "mixed" else
+            "context only (not the bench line): %d documents x 1 KiB of configs[0]'s English-like ASCII text per GPU, add_bos+add_eos" % args.docs)
+    return {"workload": name,
             "docs_per_step": int(n_docs), "bytes_per_step": int(n_bytes), "parallelism": "documents sharded by rank, no collective",
             "l2": ("input per GPU per step (%.0f MB) exceeds the 126 MB L2; no flush needed" % (args_bytes_per_gpu(args, n_bytes) / 1e6))
             if args_bytes_per_gpu(args, n_bytes) > 2 * L2_BYTES else "L2 flushed between steps (256 MiB write), outside the per-step events"}
@@ -223,7 +240,7 @@ def run_ours(args):
     tk = Tekkenizer.from_file(path, device=local)
 
     # this rank's shard of the corpus, in pinned host memory (the e2e arm reads it from there)
-    data_np, off_np = corpus.mixed_script_docs(args.docs, SEED, first_doc=rank * args.docs)
+    data_np, off_np = make_docs(args.docs, first_doc=rank * args.docs)
     n_docs, n_bytes = len(off_np) - 1, len(data_np)
     h_data = torch.empty(n_bytes + 64, dtype=torch.uint8).pin_memory()
     h_data[:n_bytes].numpy()[:] = data_np
@@ -395,7 +412,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--docs", type=int, default=1_000_000, help="documents per GPU per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="mixed", choices=["mixed", "english"],
+                    help="mixed = BASELINE configs[1] (the bench line); english = configs[0]'s English-like text cut into 1 KiB documents (context only)")
     args = ap.parse_args()
+    global WORKLOAD
+    WORKLOAD = args.workload
     if args.gpus > 1 and "RANK" not in os.environ:
         # convenience: relaunch one rank per GPU the way the driver does
         import socket
