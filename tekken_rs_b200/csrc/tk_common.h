@@ -48,12 +48,26 @@ TK_HD uint64_t tk_mix64(uint64_t x) {
     return x;
 }
 
-// Hash of a piece given as little-endian 8-byte words (last one zero padded).
+// Hash of a piece given as little-endian 8-byte words (last one zero padded).  32-bit arithmetic
+// only (two multiply lanes + a murmur-style finaliser): the GPU has no 64-bit multiplier, and the
+// whole-piece lookup runs once per pre-token.  finish(): low 32 bits index the table, all 64 bits
+// are the stored key of entries longer than 8 bytes.
 struct TkPieceHasher {
-    uint64_t h;
-    TK_HD void init(uint32_t len) { h = 0x9e3779b97f4a7c15ull * (uint64_t)(len + 1u); }
-    TK_HD void add(uint64_t w) { h = (h ^ w) * 0xff51afd7ed558ccdull; h ^= h >> 29; }
-    TK_HD uint64_t finish() const { return tk_mix64(h); }
+    uint32_t a, b;
+    TK_HD void init(uint32_t len) { a = 0x9E3779B9u * (len + 1u); b = 0x85EBCA6Bu ^ (len * 0x27D4EB2Fu); }
+    TK_HD void add(uint64_t w) {
+        a = (a ^ (uint32_t)w) * 0xCC9E2D51u;
+        a = (a << 15) | (a >> 17);
+        b = (b ^ (uint32_t)(w >> 32)) * 0x1B873593u;
+        b = ((b << 13) | (b >> 19)) + a;
+    }
+    TK_HD uint64_t finish() const {
+        uint32_t h = a ^ ((b << 16) | (b >> 16));
+        h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+        uint32_t g = (b ^ (a >> 7)) * 0x9E3779B1u;
+        g ^= g >> 15;
+        return ((uint64_t)g << 32) | h;
+    }
 };
 
 // ---- pair table: (left id, right id) -> rank of the concatenation ------------------------------

@@ -569,13 +569,14 @@ __host__ __device__ __forceinline__ uint32_t lane_class(uint32_t len) {        /
 struct LkSmem {
     uint8_t bytes[LK_TILE + TK_LANE_MAX + 16];
     uint32_t mask[LK_WINS + 4];
-    uint16_t list[LK_PCAP];     // tile-relative starts of all pieces, in order
-    uint32_t ptk[LK_PCAP];      // per piece: rank | EN_LAST (vocabulary entry), len | LK_MISS, or LK_NONE (no slots)
-    uint16_t poff[LK_PCAP];     // first slot of every piece
-    uint32_t pfx[LK_WINS + 1];  // index of the first piece of every window
+    uint16_t list[LK_PCAP];            // tile-relative starts of all pieces, in order
+    uint32_t missq[LK_TILE / 2 + 4];   // pieces to merge: start | len << 12 | first slot << 19
+    uint32_t wfirst[LK_WINS];          // first slot of every window
+    uint32_t whits[LK_WINS];           // vocabulary-entry pieces of every window
+    uint32_t pfx[LK_WINS + 1];         // index of the first piece of every window
     uint32_t wsum[LK_T / 32];
     uint32_t cls_n[TKK_N_CLASSES], cls_base[TKK_N_CLASSES], cls_pos[TKK_N_CLASSES];
-    uint32_t n_pieces;
+    uint32_t n_pieces, n_miss;
 };
 
 // tile-relative end of the piece that starts at tile-relative byte s (the next set bit of the start
@@ -616,13 +617,14 @@ __global__ void __launch_bounds__(LK_T) lookup_kernel(const uint8_t* __restrict_
                                                       uint32_t* __restrict__ stream, uint32_t* __restrict__ win_info,
                                                       unsigned long long* __restrict__ queues, TkkQueueLayout Q,
                                                       uint32_t* __restrict__ q_n) {
-    extern __shared__ __align__(16) unsigned char lk_raw[];
-    LkSmem& S = *reinterpret_cast<LkSmem*>(lk_raw);
+    __shared__ __align__(16) LkSmem S;
     const uint32_t t = threadIdx.x, lane = t & 31u;
     const uint32_t tile = blockIdx.x;
     const uint64_t tile_pos = (uint64_t)tile * LK_TILE;
     const uint64_t win0 = (uint64_t)tile * LK_WINS;
     if (t < TKK_N_CLASSES) { S.cls_n[t] = 0; S.cls_pos[t] = 0; }
+    if (t == 0) S.n_miss = 0;
+    if (t < LK_WINS) S.whits[t] = 0;
     // ---- A: stage bytes and mask words; list the piece starts ----
     {
         const uint64_t avail = n > tile_pos ? n - tile_pos : 0;
@@ -646,63 +648,58 @@ __global__ void __launch_bounds__(LK_T) lookup_kernel(const uint8_t* __restrict_
     }
     __syncthreads();
     const uint32_t np = S.n_pieces;
+    uint32_t* dst = stream + (uint64_t)tile * LK_CAP;
 
-    // ---- B: one lane per piece: whole-piece vocabulary lookup ----
+    // ---- B: one lane per piece, LK_T pieces per round: whole-piece vocabulary lookup, slots by a block
+    //         scan, vocabulary entries straight into their slot, misses collected ----
+    uint32_t run = 0;                                   // slots taken by earlier rounds
     for (uint32_t k0 = 0; k0 < np; k0 += LK_T) {
         const uint32_t k = k0 + t;
-        uint32_t cls = 0xFFFFFFFFu;
+        uint32_t s = 0, len = 0, v = LK_NONE, slots = 0, cls = 0xFFFFFFFFu;
         if (k < np) {
-            const uint32_t s = S.list[k];
-            uint32_t v = LK_NONE;
+            s = S.list[k];
             if (tile_pos + s < n) {                        // the end-of-data sentinel is not a piece
                 const uint32_t e = en_piece_end(S.mask, s);
                 if (e != 0xFFFFFFFFu && e - s <= TK_LANE_MAX) {         // longer pieces: K3
-                    const uint32_t len = e - s;
+                    len = e - s;
                     const uint32_t whole = tk_vocab_lookup_w32(T, S.bytes, s, len);
-                    if (whole != TK_INF) v = whole | EN_LAST;
-                    else if (len == 1) v = (uint32_t)S.bytes[s] | EN_LAST;
-                    else { v = len | LK_MISS; cls = lane_class(len); }
+                    if (whole != TK_INF) { v = whole | EN_LAST; slots = 1; }
+                    else if (len == 1) { v = (uint32_t)S.bytes[s] | EN_LAST; slots = 1; }
+                    else { v = LK_MISS; slots = len; cls = lane_class(len); }
                 }
             }
-            S.ptk[k] = v;
         }
-        // misses per length class (one shared-memory atomic per class per warp)
-        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, cls);
-        if (cls != 0xFFFFFFFFu && (uint32_t)(__ffs((int)peers) - 1) == lane) atomicAdd(&S.cls_n[cls], (uint32_t)__popc(peers));
+        uint32_t round_total;
+        const uint32_t slot = run + lk_block_excl(slots, S.wsum, &round_total);
+        run += round_total;
+        if (k < np) {
+            const uint32_t w = s >> 5;
+            if (k == S.pfx[w]) S.wfirst[w] = slot;         // first piece of its window
+            if (v & EN_LAST && v != LK_NONE) { dst[slot] = v; atomicAdd(&S.whits[w], 1u); }
+        }
+        const uint32_t mm = __ballot_sync(0xFFFFFFFFu, cls != 0xFFFFFFFFu);
+        if (mm) {
+            uint32_t base = 0;
+            const int leader = __ffs((int)mm) - 1;
+            if ((int)lane == leader) base = atomicAdd(&S.n_miss, (uint32_t)__popc(mm));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (cls != 0xFFFFFFFFu) S.missq[base + (uint32_t)__popc(mm & ((1u << lane) - 1u))] = s | (len << 12) | (slot << 19);
+            // misses per length class (one shared-memory atomic per class per warp)
+            const uint32_t peers = __match_any_sync(0xFFFFFFFFu, cls);
+            if (cls != 0xFFFFFFFFu && (uint32_t)(__ffs((int)peers) - 1) == lane) atomicAdd(&S.cls_n[cls], (uint32_t)__popc(peers));
+        }
     }
     __syncthreads();
     if (t < TKK_N_CLASSES && S.cls_n[t]) S.cls_base[t] = atomicAdd(q_n + t, S.cls_n[t]);   // this tile's range of every queue
-    uint32_t* dst = stream + (uint64_t)tile * LK_CAP;
-    // ---- C: slots of every piece: exclusive prefix over the pieces ----
-    uint32_t tile_total;
-    {
-        const uint32_t per = (np + LK_T - 1) / LK_T;
-        const uint32_t lo = t * per < np ? t * per : np, hi = lo + per < np ? lo + per : np;
-        uint32_t sum = 0;
-        for (uint32_t k = lo; k < hi; ++k) {
-            const uint32_t v = S.ptk[k];
-            sum += v == LK_NONE ? 0u : (v & EN_LAST) ? 1u : (v & 0xFFu);
-        }
-        uint32_t o = lk_block_excl(sum, S.wsum, &tile_total);
-        for (uint32_t k = lo; k < hi; ++k) {
-            const uint32_t v = S.ptk[k];
-            S.poff[k] = (uint16_t)o;
-            o += v == LK_NONE ? 0u : (v & EN_LAST) ? 1u : (v & 0xFFu);
-        }
-        if (t == 0) S.poff[np] = (uint16_t)tile_total;
-    }
+    // per window: first slot | number of vocabulary-entry pieces << 16 (K2m adds the ranks of the merged pieces)
+    if (t < LK_WINS) win_info[win0 + t] = (S.wfirst[t] & 0xFFFFu) | (S.whits[t] << 16);
     __syncthreads();
-    // ---- D: vocabulary entries into their slots, misses into the queues ----
-    for (uint32_t k0 = 0; k0 < np; k0 += LK_T) {
-        const uint32_t k = k0 + t;
-        uint32_t cls = 0xFFFFFFFFu, v = LK_NONE;
-        if (k < np) {
-            v = S.ptk[k];
-            if (v != LK_NONE) {
-                if (v & EN_LAST) dst[S.poff[k]] = v;
-                else cls = lane_class(v & 0xFFu);
-            }
-        }
+    // ---- C: misses into the queue of their length class ----
+    const uint32_t nm = S.n_miss;
+    for (uint32_t i0 = 0; i0 < nm; i0 += LK_T) {
+        const uint32_t i = i0 + t;
+        uint32_t e = 0, cls = 0xFFFFFFFFu;
+        if (i < nm) { e = S.missq[i]; cls = lane_class((e >> 12) & 127u); }
         const uint32_t peers = __match_any_sync(0xFFFFFFFFu, cls);
         if (cls != 0xFFFFFFFFu) {
             const int leader = __ffs((int)peers) - 1;
@@ -710,21 +707,10 @@ __global__ void __launch_bounds__(LK_T) lookup_kernel(const uint8_t* __restrict_
             if ((int)lane == leader) base = atomicAdd(&S.cls_pos[cls], (uint32_t)__popc(peers));
             base = __shfl_sync(peers, base, leader);
             const uint32_t pos = S.cls_base[cls] + base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
-            const unsigned long long e = (tile_pos + S.list[k]) | ((unsigned long long)(v & 0xFFu) << QE_START_BITS) |
-                                         ((unsigned long long)S.poff[k] << (QE_START_BITS + QE_LEN_BITS));
-            queues[Q.off[cls] + pos] = e;
+            queues[Q.off[cls] + pos] = (tile_pos + (e & 4095u)) | ((unsigned long long)((e >> 12) & 127u) << QE_START_BITS) |
+                                       ((unsigned long long)(e >> 19) << (QE_START_BITS + QE_LEN_BITS));
         }
     }
-    // per window: first slot | number of vocabulary-entry pieces << 16 (K2m adds the ranks of the merged pieces)
-    if (t < LK_WINS) {
-        uint32_t hits = 0;
-        for (uint32_t k = S.pfx[t]; k < S.pfx[t + 1]; ++k) {
-            const uint32_t v = S.ptk[k];
-            hits += (v != LK_NONE && (v & EN_LAST)) ? 1u : 0u;
-        }
-        win_info[win0 + t] = S.poff[S.pfx[t]] | (hits << 16);
-    }
-    (void)tile_total;
 }
 
 template <int MAXLEN, int THREADS>
@@ -1114,14 +1100,7 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
     }
     if (timer) timer->mark(st, "lookup");
     {
-        static std::atomic<uint64_t> attr_set{0};   // bit per device ordinal
-        int dev = 0;
-        CK(cudaGetDevice(&dev));
-        if (!((attr_set.load() >> (dev & 63)) & 1ull)) {
-            CK(cudaFuncSetAttribute(lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LkSmem)));
-            attr_set.fetch_or(1ull << (dev & 63));
-        }
-        lookup_kernel<<<(unsigned)L.n_ltiles, LK_T, sizeof(LkSmem), st>>>(d_data, n, start, T, stream, win_info, queues, L.queues, q_n);
+        lookup_kernel<<<(unsigned)L.n_ltiles, LK_T, 0, st>>>(d_data, n, start, T, stream, win_info, queues, L.queues, q_n);
         TK_LAUNCHED();
     }
     if (timer) timer->mark(st, "lanemerge64");
