@@ -249,21 +249,52 @@ __global__ void __launch_bounds__(PT_T) pretok_fix_kernel(const uint8_t* __restr
     }
 }
 
-// K1s: one block scans the tile summaries: exact entry state of every tile, verdict for every
-// pending whitespace candidate, and the list of tiles whose guess was wrong.
+// K1s: scan of the tile summaries in three small kernels: (1) composite of every segment of
+// SG_TILES tiles, (2) one block scans the segment composites (state entering every segment, first
+// whitespace event after it), (3) every segment again: exact entry state of every tile, verdict
+// for every pending whitespace candidate, and the list of tiles whose guess was wrong.
+#define SG_T 256
+#define SG_PER 8
+#define SG_TILES (SG_T * SG_PER)
 #define SC_T 1024
-__global__ void __launch_bounds__(SC_T) pretok_scan_kernel(const TkkTileSummary* __restrict__ summ, uint32_t n_tiles,
-                                                           uint32_t* __restrict__ carry, uint32_t* __restrict__ worklist,
-                                                           uint32_t* __restrict__ work_count, uint32_t* __restrict__ start_mask) {
-    __shared__ uint32_t f_chunk[SC_T];     // composite of each chunk
-    __shared__ uint32_t in_state[SC_T];    // n | abs<<2 entering each chunk
-    __shared__ uint32_t h_chunk[SC_T];     // first head event inside each chunk
-    __shared__ uint32_t h_after[SC_T];     // first head event after each chunk
+
+__device__ __forceinline__ void rs_step(uint32_t& nst, uint32_t& ast, const TkRunSummary& g) {
+    nst = g.n_all ? (nst + g.n_val) % 3u : g.n_val;
+    ast = g.r_mode == 2u ? ast : g.r_mode;
+}
+
+__global__ void __launch_bounds__(SG_T) pretok_seg_kernel(const TkkTileSummary* __restrict__ summ, uint32_t n_tiles,
+                                                          uint32_t* __restrict__ seg_packed) {
+    __shared__ uint32_t f_chunk[SG_T];
     const uint32_t t = threadIdx.x;
-    const uint32_t per = (n_tiles + SC_T - 1) / SC_T;
-    const uint32_t lo = t * per < n_tiles ? t * per : n_tiles, hi = (t + 1) * per < n_tiles ? (t + 1) * per : n_tiles;
+    const uint64_t lo0 = (uint64_t)blockIdx.x * SG_TILES + (uint64_t)t * SG_PER;
+    const uint32_t lo = lo0 < n_tiles ? (uint32_t)lo0 : n_tiles, hi = lo + SG_PER < n_tiles ? lo + SG_PER : n_tiles;
     TkRunSummary f = rs_unpack(RS_IDENTITY);
     for (uint32_t b = lo; b < hi; ++b) f = tk_compose(f, rs_unpack(summ[b].packed));
+    f_chunk[t] = rs_pack(f);
+    __syncthreads();
+    // ordered reduction (the composition is not commutative): warp 0, 8 chunks per lane, then a shuffle chain
+    if (t < 32) {
+        TkRunSummary g = rs_unpack(RS_IDENTITY);
+        for (int j = 0; j < SG_T / 32; ++j) g = tk_compose(g, rs_unpack(f_chunk[t * (SG_T / 32) + j]));
+        uint32_t v = rs_pack(g);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, v, d);
+            if ((int)t >= d) v = rs_pack(tk_compose(rs_unpack(o), rs_unpack(v)));
+        }
+        if (t == 31) seg_packed[blockIdx.x] = v;
+    }
+}
+
+__global__ void __launch_bounds__(SC_T) pretok_segscan_kernel(const uint32_t* __restrict__ seg_packed, uint32_t n_seg,
+                                                              uint32_t* __restrict__ seg_in, uint32_t* __restrict__ seg_after) {
+    __shared__ uint32_t f_chunk[SC_T], in_state[SC_T], h_chunk[SC_T], h_after[SC_T];
+    const uint32_t t = threadIdx.x;
+    const uint32_t per = (n_seg + SC_T - 1) / SC_T;
+    const uint32_t lo = t * per < n_seg ? t * per : n_seg, hi = (t + 1) * per < n_seg ? (t + 1) * per : n_seg;
+    TkRunSummary f = rs_unpack(RS_IDENTITY);
+    for (uint32_t b = lo; b < hi; ++b) f = tk_compose(f, rs_unpack(seg_packed[b]));
     f_chunk[t] = rs_pack(f);
     h_chunk[t] = f.head;
     __syncthreads();
@@ -271,9 +302,7 @@ __global__ void __launch_bounds__(SC_T) pretok_scan_kernel(const TkkTileSummary*
         uint32_t nst = 0, ast = 0;
         for (uint32_t j = 0; j < SC_T; ++j) {
             in_state[j] = nst | (ast << 2);
-            const TkRunSummary g = rs_unpack(f_chunk[j]);
-            nst = g.n_all ? (nst + g.n_val) % 3u : g.n_val;
-            ast = g.r_mode == 2u ? ast : g.r_mode;
+            rs_step(nst, ast, rs_unpack(f_chunk[j]));
         }
         uint32_t nh = 2;  // past the end of the data the run has ended
         for (int j = SC_T - 1; j >= 0; --j) {
@@ -282,26 +311,71 @@ __global__ void __launch_bounds__(SC_T) pretok_scan_kernel(const TkkTileSummary*
         }
     }
     __syncthreads();
-    // forward: entry states; backward: verdicts
     uint32_t nst = in_state[t] & 3u, ast = in_state[t] >> 2;
     for (uint32_t b = lo; b < hi; ++b) {
-        carry[b] = nst | (ast << 2);
-        const TkRunSummary g = rs_unpack(summ[b].packed);
-        nst = g.n_all ? (nst + g.n_val) % 3u : g.n_val;
-        ast = g.r_mode == 2u ? ast : g.r_mode;
+        seg_in[b] = nst | (ast << 2);
+        rs_step(nst, ast, rs_unpack(seg_packed[b]));
     }
     uint32_t nh = h_after[t];
     for (uint32_t b = hi; b-- > lo;) {
-        const TkkTileSummary s = summ[b];
-        const uint32_t cw = carry[b];
-        const uint32_t confirm = nh == 2u;
-        const uint32_t n0 = s.assumed & 3u, a0 = (s.assumed >> 2) & 1u, n_prov = (s.assumed >> 3) & 1u, r_prov = (s.assumed >> 4) & 1u;
-        const bool wrong = (n_prov && (cw & 3u) != n0) || (r_prov && ((cw >> 2) & 1u) != a0);
-        carry[b] = cw | (confirm << 3);
-        if (wrong) worklist[atomicAdd(work_count, 1u)] = b;
-        else if (s.pend_pos >= 0 && confirm) atomicOr(start_mask + (s.pend_pos >> 5), 1u << (s.pend_pos & 31));
-        const uint32_t h = rs_unpack(s.packed).head;
+        seg_after[b] = nh;
+        const uint32_t h = rs_unpack(seg_packed[b]).head;
         if (h) nh = h;
+    }
+}
+
+__global__ void __launch_bounds__(SG_T) pretok_apply_kernel(const TkkTileSummary* __restrict__ summ, uint32_t n_tiles,
+                                                            const uint32_t* __restrict__ seg_in, const uint32_t* __restrict__ seg_after,
+                                                            uint32_t* __restrict__ carry, uint32_t* __restrict__ worklist,
+                                                            uint32_t* __restrict__ work_count, uint32_t* __restrict__ start_mask) {
+    __shared__ uint32_t f_chunk[SG_T];     // composite of each thread's tiles
+    __shared__ uint32_t in_state[SG_T];    // n | abs<<2 entering each thread's tiles
+    __shared__ uint32_t h_after[SG_T];     // first head event after each thread's tiles
+    const uint32_t t = threadIdx.x;
+    const uint64_t lo0 = (uint64_t)blockIdx.x * SG_TILES + (uint64_t)t * SG_PER;
+    const uint32_t lo = lo0 < n_tiles ? (uint32_t)lo0 : n_tiles, hi = lo + SG_PER < n_tiles ? lo + SG_PER : n_tiles;
+    TkkTileSummary mine[SG_PER];
+    TkRunSummary f = rs_unpack(RS_IDENTITY);
+#pragma unroll
+    for (int k = 0; k < SG_PER; ++k)
+        if (lo + k < hi) { mine[k] = summ[lo + k]; f = tk_compose(f, rs_unpack(mine[k].packed)); }
+    f_chunk[t] = rs_pack(f);
+    __syncthreads();
+    if (t == 0) {
+        uint32_t nst = seg_in[blockIdx.x] & 3u, ast = seg_in[blockIdx.x] >> 2;
+        for (uint32_t j = 0; j < SG_T; ++j) {
+            in_state[j] = nst | (ast << 2);
+            rs_step(nst, ast, rs_unpack(f_chunk[j]));
+        }
+    } else if (t == 32) {
+        uint32_t nh = seg_after[blockIdx.x];
+        for (int j = SG_T - 1; j >= 0; --j) {
+            h_after[j] = nh;
+            const uint32_t h = rs_unpack(f_chunk[j]).head;
+            if (h) nh = h;
+        }
+    }
+    __syncthreads();
+    // forward: entry states; backward: verdicts
+    uint32_t cw[SG_PER];
+    uint32_t nst = in_state[t] & 3u, ast = in_state[t] >> 2;
+#pragma unroll
+    for (int k = 0; k < SG_PER; ++k)
+        if (lo + k < hi) { cw[k] = nst | (ast << 2); rs_step(nst, ast, rs_unpack(mine[k].packed)); }
+    uint32_t nh = h_after[t];
+#pragma unroll
+    for (int k = SG_PER - 1; k >= 0; --k) {
+        if (lo + k < hi) {
+            const TkkTileSummary s = mine[k];
+            const uint32_t confirm = nh == 2u;
+            const uint32_t n0 = s.assumed & 3u, a0 = (s.assumed >> 2) & 1u, n_prov = (s.assumed >> 3) & 1u, r_prov = (s.assumed >> 4) & 1u;
+            const bool wrong = (n_prov && (cw[k] & 3u) != n0) || (r_prov && ((cw[k] >> 2) & 1u) != a0);
+            carry[lo + k] = cw[k] | (confirm << 3);
+            if (wrong) worklist[atomicAdd(work_count, 1u)] = lo + k;
+            else if (s.pend_pos >= 0 && confirm) atomicOr(start_mask + (s.pend_pos >> 5), 1u << (s.pend_pos & 31));
+            const uint32_t h = rs_unpack(s.packed).head;
+            if (h) nh = h;
+        }
     }
 }
 
@@ -809,10 +883,9 @@ __device__ __forceinline__ uint32_t docs_from(const uint64_t* __restrict__ doc_o
 
 // length of the piece that starts at bit `bit` of window gw (not a long piece: the next start is at most
 // two words away)
-__device__ __forceinline__ uint32_t em_piece_len(const uint32_t* __restrict__ start_mask, uint64_t gw, uint32_t mymask, uint32_t bit) {
+__device__ __forceinline__ uint32_t em_piece_len(const uint32_t* __restrict__ start_mask, uint64_t gw, uint32_t mymask, uint32_t m1, uint32_t bit) {
     const uint32_t m = bit == 31u ? 0u : (mymask >> (bit + 1u));
     if (m) return (uint32_t)__ffs((int)m);
-    const uint32_t m1 = start_mask[gw + 1];
     if (m1) return 32u - bit + (uint32_t)(__ffs((int)m1) - 1);
     return 64u - bit + (uint32_t)(__ffs((int)start_mask[gw + 2]) - 1);
 }
@@ -843,6 +916,13 @@ __global__ void __launch_bounds__(EM_T) emit_kernel(uint64_t n, const uint32_t* 
     const uint32_t info = mymask ? win_info[gw] : 0u;      // first slot | ranks of the short pieces << 16
     const uint32_t* src0 = stream + (gw / LK_WINS) * (uint64_t)LK_CAP + (info & 0xFFFFu);
     const uint64_t mydoc = myds ? doc_first[gw] : 0;        // first document that starts in my window
+    // the slots of my window are read one piece at a time during the walk below: start fetching
+    // their sectors now, so that they arrive while the block scans and looks back
+    if (mymask) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) asm volatile("prefetch.global.L1 [%0];" ::"l"(src0 + 8 * k));
+    }
+    const uint32_t nextmask = start_mask[gw + 1];           // the last piece of my window usually ends there
     // ---- tokens of my window ----
     uint32_t count = info >> 16;
     if (lw) count += recs[lw - 1].count;
@@ -927,7 +1007,7 @@ __global__ void __launch_bounds__(EM_T) emit_kernel(uint64_t n, const uint32_t* 
                 src += 1;
                 continue;
             }
-            const uint32_t len = em_piece_len(start_mask, gw, mymask, bit);
+            const uint32_t len = em_piece_len(start_mask, gw, mymask, nextmask, bit);
             uint32_t v[4] = {v0, __ldg(src + 1), len > 2 ? __ldg(src + 2) : EN_LAST, len > 3 ? __ldg(src + 3) : EN_LAST};
             for (uint32_t j = 0;;) {
                 bool done = false;
@@ -989,6 +1069,7 @@ size_t encode_workspace_bytes(uint64_t n, uint64_t n_docs, EncodeLayout* L) {
     l.off_summ = take(n_tiles * sizeof(TkkTileSummary));
     l.off_carry = take(n_tiles * 4);
     l.off_worklist = take(n_tiles * 4);
+    l.off_seg = take((ceil_div(n_tiles, SG_TILES) + 1) * 3 * 4);
     l.n_ltiles = n_tiles * (PT_T / LK_WINS);            // lookup tiles cover exactly the emit tiles
     l.off_tilestate = take(n_tiles * 8);
     l.off_wininfo = take(words * 4);
@@ -1077,8 +1158,18 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
     pretok_kernel<<<(unsigned)L.n_tiles, PT_T, 0, st>>>(d_data, n, ds, start, L.n_windows, T, summ, err_pos);
     TK_LAUNCHED();
     if (timer) timer->mark(st, "pretok_carry");
-    pretok_scan_kernel<<<1, SC_T, 0, st>>>(summ, (uint32_t)L.n_tiles, carry, worklist, work_count, start);
-    TK_LAUNCHED();
+    {
+        const uint32_t n_seg = (uint32_t)ceil_div(L.n_tiles, SG_TILES);
+        uint32_t* seg_packed = (uint32_t*)(ws + L.off_seg);
+        uint32_t* seg_in = seg_packed + n_seg;
+        uint32_t* seg_after = seg_in + n_seg;
+        pretok_seg_kernel<<<n_seg, SG_T, 0, st>>>(summ, (uint32_t)L.n_tiles, seg_packed);
+        TK_LAUNCHED();
+        pretok_segscan_kernel<<<1, SC_T, 0, st>>>(seg_packed, n_seg, seg_in, seg_after);
+        TK_LAUNCHED();
+        pretok_apply_kernel<<<n_seg, SG_T, 0, st>>>(summ, (uint32_t)L.n_tiles, seg_in, seg_after, carry, worklist, work_count, start);
+        TK_LAUNCHED();
+    }
     pretok_fix_kernel<<<(unsigned)(L.n_tiles < (uint64_t)(2 * sm_count) ? L.n_tiles : (uint64_t)(2 * sm_count)), PT_T, 0, st>>>(
         d_data, n, ds, start, L.n_windows, T, carry, worklist, work_count, err_pos);
     TK_LAUNCHED();
