@@ -81,9 +81,11 @@ TK_HD uint64_t tk_pair_slot(uint32_t l, uint32_t r, uint32_t rank) {
     return (1ull << 63) | (tk_pair_key(l, r) << TK_ID_BITS) | (uint64_t)rank;
 }
 TK_HD uint32_t tk_pair_hash(uint32_t l, uint32_t r) {
-    uint64_t k = tk_pair_key(l, r);
-    k *= 0x9e3779b97f4a7c15ull;
-    return (uint32_t)(k >> 32) ^ (uint32_t)(k >> 13);
+    // 32-bit multiplies only (the lookup runs twice per merge step)
+    uint32_t h = (l * 0x9E3779B1u) ^ (r * 0x85EBCA77u);
+    h ^= h >> 15;
+    h *= 0x2C1B3C6Du;
+    return h ^ (h >> 13);
 }
 
 // Device-resident tables of one tokenizer (plain pointers; filled by the loader).

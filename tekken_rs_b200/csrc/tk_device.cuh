@@ -189,8 +189,19 @@ __device__ __forceinline__ uint32_t tk_vocab_lookup_w32(const TkDeviceTables& T,
 // merge writes the new id at the left part's offset, marks the right part's offset TK_LANE_DEAD,
 // and the set of live offsets is a 64-bit mask in registers, so neighbours come from bit
 // operations.  The minimum key is the lowest rank, leftmost on ties.  Returns the live mask.
-__device__ __forceinline__ unsigned long long tk_bpe_merge_loop(const TkDeviceTables& T, uint32_t len, uint32_t* id, uint32_t* key) {
-    unsigned long long live = len >= 64u ? ~0ull : ((1ull << len) - 1ull);
+// bit helpers for the live mask: 32-bit when the piece class fits, else 64-bit
+__device__ __forceinline__ uint32_t tk_ffs_m(uint32_t m) { return (uint32_t)__ffs((int)m); }
+__device__ __forceinline__ uint32_t tk_ffs_m(unsigned long long m) { return (uint32_t)__ffsll((long long)m); }
+__device__ __forceinline__ uint32_t tk_top_m(uint32_t m) { return 31u - (uint32_t)__clz((int)m); }
+__device__ __forceinline__ uint32_t tk_top_m(unsigned long long m) { return 63u - (uint32_t)__clzll((long long)m); }
+__device__ __forceinline__ uint32_t tk_popc_m(uint32_t m) { return (uint32_t)__popc(m); }
+__device__ __forceinline__ uint32_t tk_popc_m(unsigned long long m) { return (uint32_t)__popcll(m); }
+
+template <class M>
+__device__ __forceinline__ M tk_bpe_merge_loop(const TkDeviceTables& T, uint32_t len, uint32_t* id, uint32_t* key) {
+    constexpr uint32_t kBits = sizeof(M) * 8;
+    const M one = 1;
+    M live = len >= kBits ? ~(M)0 : (M)((one << len) - one);
     for (;;) {
         uint32_t best = TK_INF;
         uint32_t j = 0;
@@ -201,13 +212,13 @@ __device__ __forceinline__ unsigned long long tk_bpe_merge_loop(const TkDeviceTa
         for (; j < len; ++j) best = min(best, key[j]);
         if (best == TK_INF) break;
         const uint32_t bp = best & 63u, rank = best >> 6;
-        const unsigned long long above = live & ~((2ull << bp) - 1ull);           // live offsets > bp
-        const uint32_t q = (uint32_t)(__ffsll((long long)above) - 1);             // exists: the pair has a rank
-        const unsigned long long above_q = above & (above - 1);                    // live offsets > q
-        const unsigned long long below = live & ((1ull << bp) - 1ull);            // live offsets < bp
-        live &= ~(1ull << q);
-        const uint32_t nn = above_q ? (uint32_t)(__ffsll((long long)above_q) - 1) : 0xFFFFFFFFu;
-        const uint32_t pv = below ? (uint32_t)(63 - __clzll((long long)below)) : 0xFFFFFFFFu;
+        const M above = live & ~(M)(((one << bp) << 1) - one);     // live offsets > bp (bp is never the top bit: it has a right neighbour)
+        const uint32_t q = tk_ffs_m(above) - 1u;                   // exists: the pair has a rank
+        const M above_q = above & (above - one);                    // live offsets > q
+        const M below = live & (M)((one << bp) - one);              // live offsets < bp
+        live &= ~(M)(one << q);
+        const uint32_t nn = above_q ? tk_ffs_m(above_q) - 1u : 0xFFFFFFFFu;
+        const uint32_t pv = below ? tk_top_m(below) : 0xFFFFFFFFu;
         id[bp] = rank;
         id[q] = TK_LANE_DEAD;
         key[q] = TK_INF;

@@ -14,6 +14,7 @@
 #include "tk_kernels.h"
 
 #include <cstdio>
+#include <type_traits>
 
 #include "tk_device.cuh"
 #include "tk_pretok.h"
@@ -836,11 +837,12 @@ __global__ void __launch_bounds__(THREADS) lanemerge_kernel(const uint8_t* __res
                     if (j < len) key[j] = r4[c] == TK_INF ? TK_INF : ((r4[c] << 6) | j);
                 }
             }
-            unsigned long long live = tk_bpe_merge_loop(T, len, id, key);
+            using Mask = typename std::conditional<(MAXLEN <= 32), uint32_t, unsigned long long>::type;
+            Mask live = tk_bpe_merge_loop<Mask>(T, len, id, key);
             uint32_t* dst = stream + (start / LK_TILE) * (uint64_t)LK_CAP + off;
-            atomicAdd(win_info + (start >> 5), (uint32_t)__popcll(live) << 16);        // ranks of the window the piece starts in
+            atomicAdd(win_info + (start >> 5), tk_popc_m(live) << 16);        // ranks of the window the piece starts in
             while (live) {
-                const uint32_t j = (uint32_t)(__ffsll((long long)live) - 1);
+                const uint32_t j = tk_ffs_m(live) - 1u;
                 live &= live - 1;
                 *dst++ = live ? id[j] : (id[j] | EN_LAST);
             }
