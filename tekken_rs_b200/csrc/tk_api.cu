@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -150,7 +151,9 @@ struct tk_tokenizer {
     struct EncSlot {
         cudaStream_t st = nullptr;
         DevBuf ws, scratch, in_data, in_off, out_tok, out_off;
-        uint32_t* h_small = nullptr;   // pinned copy of the workspace's counter block
+        uint32_t* h_small = nullptr;   // mapped pinned copy of the workspace's counter block
+        uint32_t* d_small_map = nullptr;   // its device address
+        cudaEvent_t done = nullptr;    // recorded after the counters have been published
         tkk::EncodeLayout L;
     };
     static constexpr int kSlots = 3;
@@ -291,6 +294,7 @@ extern "C" void tk_free(tk_tokenizer* t) {
             if (s.st) { cudaStreamSynchronize(s.st); cudaStreamDestroy(s.st); }
             s.ws.release(); s.scratch.release(); s.in_data.release(); s.in_off.release(); s.out_tok.release(); s.out_off.release();
             if (s.h_small) cudaFreeHost(s.h_small);
+            if (s.done) cudaEventDestroy(s.done);
         };
         for (auto& sl : t->slot) drop(sl);
         drop(t->dev_slot);
@@ -424,13 +428,18 @@ static int encode_issue(tk_tokenizer* t, tk_tokenizer::EncSlot& s, const uint8_t
     size_t ws_bytes = tkk::encode_workspace_bytes(total, n_docs, &s.L);
     CUDA_OR_FAIL(s.ws.ensure(ws_bytes));
     if (s.scratch.cap == 0) CUDA_OR_FAIL(s.scratch.ensure(1 << 20));
-    if (!s.h_small) CUDA_OR_FAIL(cudaHostAlloc((void**)&s.h_small, 256, cudaHostAllocDefault));
+    if (!s.h_small) {
+        CUDA_OR_FAIL(cudaHostAlloc((void**)&s.h_small, 256, cudaHostAllocMapped));
+        CUDA_OR_FAIL(cudaHostGetDevicePointer((void**)&s.d_small_map, s.h_small, 0));
+        CUDA_OR_FAIL(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    }
     if (timing) t->timer.reset();
     cudaError_t e = tkk::encode_device(t->tables, d_data, d_doc_off, off_base, n_docs, total, add_bos, add_eos, d_tokens, cap, d_tok_off,
                                        s.ws.p, s.L, (uint32_t*)s.scratch.p, s.scratch.cap / 4, t->sm_count, st,
                                        timing ? &t->timer : nullptr);
     if (e != cudaSuccess) return fail(TK_ERR_CUDA, "encode launch: %s", cudaGetErrorString(e));
-    CUDA_OR_FAIL(cudaMemcpyAsync(s.h_small, (unsigned char*)s.ws.p + s.L.off_small, 256, cudaMemcpyDeviceToHost, st));
+    CUDA_OR_FAIL(tkk::publish_counters(s.ws.p, s.L, s.d_small_map, st));
+    CUDA_OR_FAIL(cudaEventRecord(s.done, st));
     return TK_OK;
 }
 
@@ -439,7 +448,8 @@ static int encode_issue(tk_tokenizer* t, tk_tokenizer::EncSlot& s, const uint8_t
 static int encode_finish(tk_tokenizer* t, tk_tokenizer::EncSlot& s, cudaStream_t st, uint64_t total, uint64_t cap, uint64_t byte_base,
                          uint64_t* n_tokens, bool* retry, bool timing) {
     *retry = false;
-    CUDA_OR_FAIL(cudaStreamSynchronize(st));
+    (void)st;
+    CUDA_OR_FAIL(cudaEventSynchronize(s.done));
     if (timing) t->timer.collect(t->stage_names, t->stage_ms);
     const uint32_t* small = s.h_small;
     const uint32_t flags = small[tkk::TKK_S_FLAGS];
@@ -505,7 +515,11 @@ extern "C" int tk_encode_batch(const tk_tokenizer* tc, const uint8_t* data, cons
     if (!dg.ok) return fail(TK_ERR_CUDA, "cudaSetDevice(%d) failed", t->device);
 
     // chunk plan: [begin doc, end doc)
-    constexpr uint64_t kChunkBytes = 48ull << 20;
+    static const uint64_t kChunkBytes = [] {
+        const char* e = getenv("TEKKEN_B200_CHUNK_MB");          // tuning knob; default 48 MB
+        const long mb = e ? atol(e) : 0;
+        return (uint64_t)(mb > 0 ? mb : 48) << 20;
+    }();
     std::vector<size_t> cut{0};
     while (cut.back() < n_docs) {
         const size_t b = cut.back();
@@ -551,10 +565,10 @@ extern "C" int tk_encode_batch(const tk_tokenizer* tc, const uint8_t* data, cons
                             (uint32_t*)s.out_tok.p, c.cap, (uint64_t*)s.out_off.p, s.st, false);
     };
     std::vector<uint64_t> prefix(n_chunks + 1, 0);
-    rc = issue(0);
-    if (rc) return bail(rc);
+    // two chunks are always queued ahead, so the host sits in the wait for chunk i when it completes and
+    // its ids start their way back at once
+    for (size_t i = 0; i < 2 && i < n_chunks; ++i) { rc = issue(i); if (rc) return bail(rc); }
     for (size_t i = 0; i < n_chunks; ++i) {
-        if (i + 1 < n_chunks) { rc = issue(i + 1); if (rc) return bail(rc); }
         tk_tokenizer::EncSlot& s = t->slot[i % tk_tokenizer::kSlots];
         const Chunk c = chunk_of(i);
         uint64_t n_tok = 0;
@@ -584,6 +598,7 @@ extern "C" int tk_encode_batch(const tk_tokenizer* tc, const uint8_t* data, cons
         if (e == cudaSuccess && c.n) e = cudaMemcpyAsync(h_off + c.doc_begin, s.out_off.p, c.n * 8, cudaMemcpyDeviceToHost, s.st);
         if (e != cudaSuccess) return bail(fail(TK_ERR_CUDA, "copying ids back: %s", cudaGetErrorString(e)));
         prefix[i + 1] = prefix[i] + n_tok;
+        if (i + 2 < n_chunks) { rc = issue(i + 2); if (rc) return bail(rc); }
     }
     for (auto& sl : t->slot)
         if (sl.st) {

@@ -1095,6 +1095,18 @@ size_t encode_workspace_bytes(uint64_t n, uint64_t n_docs, EncodeLayout* L) {
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
 
+// The 256-byte counter block goes to mapped pinned host memory with a kernel, not a copy: a copy
+// would queue behind the large id transfers of other chunks on the device-to-host copy engine.
+__global__ void publish_kernel(const uint32_t* __restrict__ small, uint32_t* __restrict__ mapped) {
+    mapped[threadIdx.x] = small[threadIdx.x];
+    __threadfence_system();
+}
+cudaError_t publish_counters(const void* d_ws, const EncodeLayout& L, uint32_t* mapped_dev, cudaStream_t st) {
+    publish_kernel<<<1, 64, 0, st>>>((const uint32_t*)((const unsigned char*)d_ws + L.off_small), mapped_dev);
+    count_launch();
+    return cudaGetLastError();
+}
+
 template <int MAXLEN, int THREADS>
 static cudaError_t launch_lanemerge(int blocks_per_sm, int sm_count, const uint8_t* d_data, const TkDeviceTables& T,
                                     const unsigned long long* queue, const uint32_t* q_n, uint32_t* q_w, uint32_t* stream,

@@ -83,6 +83,8 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
                           void* d_ws, const EncodeLayout& L, uint32_t* d_scratch, uint64_t scratch_cap, int sm_count,
                           cudaStream_t st, StageTimer* timer);
 
+cudaError_t publish_counters(const void* d_ws, const EncodeLayout& L, uint32_t* mapped_dev, cudaStream_t st);
+
 size_t decode_workspace_bytes(uint64_t n_ids, uint64_t n_docs, uint64_t out_cap, DecodeLayout* L);
 cudaError_t decode_device(const TkDeviceTables& T, const uint32_t* d_ids, const uint64_t* d_tok_off, uint64_t n_docs,
                           uint64_t n_ids, int policy, uint8_t* d_out, uint64_t out_cap, uint64_t* d_byte_off,
