@@ -21,6 +21,8 @@
 
 namespace tkk {
 
+#define TKK_COUNT_TILE 4096u      // tokens are counted per 4 KiB of text (= lookup / emit tile)
+
 static std::atomic<uint64_t> g_launches{0};
 uint64_t launch_count() { return g_launches.load(); }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
@@ -56,7 +58,8 @@ StageTimer::~StageTimer() { reset(); }
 // the end-of-data sentinel.  Also validates the offsets.
 // =====================================================================================================
 __global__ void docmark_kernel(const uint64_t* __restrict__ doc_off, uint64_t off_base, uint64_t n_docs, uint64_t total,
-                               uint32_t* __restrict__ ds_mask, uint32_t* __restrict__ doc_first, uint32_t* __restrict__ flags) {
+                               uint32_t add_bos, uint32_t add_eos, uint32_t* __restrict__ ds_mask, uint32_t* __restrict__ doc_first,
+                               unsigned long long* __restrict__ tile_count, uint32_t* __restrict__ flags) {
     uint64_t d = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (d > n_docs) return;
     uint64_t o = doc_off[d] - off_base;      // offsets may be a slice of a larger batch (off_base = its first entry)
@@ -67,6 +70,9 @@ __global__ void docmark_kernel(const uint64_t* __restrict__ doc_off, uint64_t of
     if (!ok) { atomicOr(flags, TKK_FLAG_BAD_OFFSETS); return; }
     atomicOr(ds_mask + (o >> 5), 1u << (o & 31));
     atomicMin(doc_first + (o >> 5), (uint32_t)d);     // first document that starts in this 32-byte window
+    // the EOS of the document before and the BOS of this one count towards the tile this document starts in
+    const unsigned long long sp = (d > 0 ? add_eos : 0u) + (d < n_docs ? add_bos : 0u);
+    if (sp) atomicAdd(tile_count + o / TKK_COUNT_TILE, sp);
 }
 
 // =====================================================================================================
@@ -455,7 +461,8 @@ __global__ void __launch_bounds__(LM_WARPS * 32) longmerge_warp_kernel(const uin
                                                                        const uint32_t* __restrict__ n_long, uint32_t* __restrict__ pool,
                                                                        unsigned long long* __restrict__ pool_cursor,
                                                                        uint32_t* __restrict__ huge_list, uint32_t* __restrict__ n_huge,
-                                                                       uint32_t* __restrict__ work_counter) {
+                                                                       uint32_t* __restrict__ work_counter,
+                                                                       unsigned long long* __restrict__ tile_count) {
     __shared__ TkWarpBpeSmem S[LM_WARPS];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t total = *n_long;
@@ -490,6 +497,7 @@ __global__ void __launch_bounds__(LM_WARPS * 32) longmerge_warp_kernel(const uin
         if (lane == 0) {
             recs[r].len = len;
             recs[r].count = count;
+            if (count) atomicAdd(tile_count + pos / TKK_COUNT_TILE, (unsigned long long)count);
             recs[r].tok_base = base;
         }
         __syncwarp();
@@ -504,7 +512,8 @@ __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __
                                                                const uint32_t* __restrict__ n_huge, uint32_t* __restrict__ pool,
                                                                uint32_t* __restrict__ scratch, unsigned long long scratch_cap,
                                                                unsigned long long* __restrict__ scratch_cursor,
-                                                               uint32_t* __restrict__ work_counter, uint32_t* __restrict__ flags) {
+                                                               uint32_t* __restrict__ work_counter, uint32_t* __restrict__ flags,
+                                                               unsigned long long* __restrict__ tile_count) {
     __shared__ unsigned long long s_key[HG_T / 32];
     __shared__ unsigned long long s_best;
     __shared__ uint32_t s_rec;
@@ -534,7 +543,7 @@ __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __
             if (t == 0) s_whole = tk_vocab_lookup(T, data + pos, n);
             __syncthreads();
             if (s_whole != TK_INF) {
-                if (t == 0) { id[0] = s_whole; recs[r].count = 1; }
+                if (t == 0) { id[0] = s_whole; recs[r].count = 1; atomicAdd(tile_count + pos / TKK_COUNT_TILE, 1ull); }
                 continue;
             }
         }
@@ -610,7 +619,7 @@ __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __
             outn += all;
             __syncthreads();
         }
-        if (t == 0) recs[r].count = outn;
+        if (t == 0) { recs[r].count = outn; atomicAdd(tile_count + pos / TKK_COUNT_TILE, (unsigned long long)outn); }
     }
 }
 
@@ -632,8 +641,8 @@ __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __
 #define LK_CAP (LK_TILE + TK_LANE_MAX)      // slots a tile can need (pieces that start in it)
 #define LK_PCAP (LK_TILE + 4)               // pieces that can start in a tile (+ the end sentinel)
 #define EN_LAST 0x80000000u
-#define LK_MISS 0x40000000u
-#define LK_NONE 0xFFFFFFFFu
+#define EN_COUNT_SHIFT 21                   // a merged piece's first rank carries its rank count here (ids are < 2^21)
+#define EN_ID_MASK ((1u << EN_COUNT_SHIFT) - 1u)
 #define QE_START_BITS 40
 #define QE_LEN_BITS 7
 
@@ -645,13 +654,10 @@ struct LkSmem {
     uint8_t bytes[LK_TILE + TK_LANE_MAX + 16];
     uint32_t mask[LK_WINS + 4];
     uint16_t list[LK_PCAP];            // tile-relative starts of all pieces, in order
-    uint32_t missq[LK_TILE / 2 + 4];   // pieces to merge: start | len << 12 | first slot << 19
-    uint32_t wfirst[LK_WINS];          // first slot of every window
-    uint32_t whits[LK_WINS];           // vocabulary-entry pieces of every window
-    uint32_t pfx[LK_WINS + 1];         // index of the first piece of every window
+    uint32_t missq[LK_TILE / 2 + 4];   // pieces to merge: start | len << 12
     uint32_t wsum[LK_T / 32];
     uint32_t cls_n[TKK_N_CLASSES], cls_base[TKK_N_CLASSES], cls_pos[TKK_N_CLASSES];
-    uint32_t n_pieces, n_miss;
+    uint32_t n_pieces, n_miss, n_hit;
 };
 
 // tile-relative end of the piece that starts at tile-relative byte s (the next set bit of the start
@@ -689,17 +695,17 @@ __device__ __forceinline__ uint32_t lk_block_excl(uint32_t v, uint32_t* wsum, ui
 
 __global__ void __launch_bounds__(LK_T) lookup_kernel(const uint8_t* __restrict__ data, uint64_t n,
                                                       const uint32_t* __restrict__ start_mask, TkDeviceTables T,
-                                                      uint32_t* __restrict__ stream, uint32_t* __restrict__ win_info,
-                                                      unsigned long long* __restrict__ queues, TkkQueueLayout Q,
-                                                      uint32_t* __restrict__ q_n) {
+                                                      uint32_t* __restrict__ stream, unsigned long long* __restrict__ queues,
+                                                      TkkQueueLayout Q, uint32_t* __restrict__ q_n,
+                                                      unsigned long long* __restrict__ tile_count) {
+    static_assert(LK_TILE == TKK_COUNT_TILE, "token counts are kept per lookup tile");
     __shared__ __align__(16) LkSmem S;
     const uint32_t t = threadIdx.x, lane = t & 31u;
     const uint32_t tile = blockIdx.x;
     const uint64_t tile_pos = (uint64_t)tile * LK_TILE;
     const uint64_t win0 = (uint64_t)tile * LK_WINS;
     if (t < TKK_N_CLASSES) { S.cls_n[t] = 0; S.cls_pos[t] = 0; }
-    if (t == 0) S.n_miss = 0;
-    if (t < LK_WINS) S.whits[t] = 0;
+    if (t == 0) { S.n_miss = 0; S.n_hit = 0; }
     // ---- A: stage bytes and mask words; list the piece starts ----
     {
         const uint64_t avail = n > tile_pos ? n - tile_pos : 0;
@@ -714,8 +720,7 @@ __global__ void __launch_bounds__(LK_T) lookup_kernel(const uint8_t* __restrict_
         if (t >= LK_WINS) m = 0;
         uint32_t np;
         uint32_t o = lk_block_excl((uint32_t)__popc(m), S.wsum, &np);
-        if (t < LK_WINS) S.pfx[t] = o;
-        if (t == 0) { S.pfx[LK_WINS] = np; S.n_pieces = np; }
+        if (t == 0) S.n_pieces = np;
         while (m) {
             S.list[o++] = (uint16_t)(t * 32u + (uint32_t)(__ffs((int)m) - 1));
             m &= m - 1;
@@ -723,14 +728,13 @@ __global__ void __launch_bounds__(LK_T) lookup_kernel(const uint8_t* __restrict_
     }
     __syncthreads();
     const uint32_t np = S.n_pieces;
-    uint32_t* dst = stream + (uint64_t)tile * LK_CAP;
+    uint32_t* dst = stream + tile_pos;                  // the rank(s) of the piece that starts at byte p go to stream[p ...]
 
-    // ---- B: one lane per piece, LK_T pieces per round: whole-piece vocabulary lookup, slots by a block
-    //         scan, vocabulary entries straight into their slot, misses collected ----
-    uint32_t run = 0;                                   // slots taken by earlier rounds
+    // ---- B: one lane per piece: whole-piece vocabulary lookup; entries written, misses collected ----
     for (uint32_t k0 = 0; k0 < np; k0 += LK_T) {
         const uint32_t k = k0 + t;
-        uint32_t s = 0, len = 0, v = LK_NONE, slots = 0, cls = 0xFFFFFFFFu;
+        uint32_t s = 0, len = 0, cls = 0xFFFFFFFFu;
+        bool hit = false;
         if (k < np) {
             s = S.list[k];
             if (tile_pos + s < n) {                        // the end-of-data sentinel is not a piece
@@ -738,27 +742,21 @@ __global__ void __launch_bounds__(LK_T) lookup_kernel(const uint8_t* __restrict_
                 if (e != 0xFFFFFFFFu && e - s <= TK_LANE_MAX) {         // longer pieces: K3
                     len = e - s;
                     const uint32_t whole = tk_vocab_lookup_w32(T, S.bytes, s, len);
-                    if (whole != TK_INF) { v = whole | EN_LAST; slots = 1; }
-                    else if (len == 1) { v = (uint32_t)S.bytes[s] | EN_LAST; slots = 1; }
-                    else { v = LK_MISS; slots = len; cls = lane_class(len); }
+                    if (whole != TK_INF) { dst[s] = whole | EN_LAST; hit = true; }
+                    else if (len == 1) { dst[s] = (uint32_t)S.bytes[s] | EN_LAST; hit = true; }
+                    else cls = lane_class(len);
                 }
             }
         }
-        uint32_t round_total;
-        const uint32_t slot = run + lk_block_excl(slots, S.wsum, &round_total);
-        run += round_total;
-        if (k < np) {
-            const uint32_t w = s >> 5;
-            if (k == S.pfx[w]) S.wfirst[w] = slot;         // first piece of its window
-            if (v & EN_LAST && v != LK_NONE) { dst[slot] = v; atomicAdd(&S.whits[w], 1u); }
-        }
+        const uint32_t hm = __ballot_sync(0xFFFFFFFFu, hit);
+        if (lane == 0 && hm) atomicAdd(&S.n_hit, (uint32_t)__popc(hm));
         const uint32_t mm = __ballot_sync(0xFFFFFFFFu, cls != 0xFFFFFFFFu);
         if (mm) {
             uint32_t base = 0;
             const int leader = __ffs((int)mm) - 1;
             if ((int)lane == leader) base = atomicAdd(&S.n_miss, (uint32_t)__popc(mm));
             base = __shfl_sync(0xFFFFFFFFu, base, leader);
-            if (cls != 0xFFFFFFFFu) S.missq[base + (uint32_t)__popc(mm & ((1u << lane) - 1u))] = s | (len << 12) | (slot << 19);
+            if (cls != 0xFFFFFFFFu) S.missq[base + (uint32_t)__popc(mm & ((1u << lane) - 1u))] = s | (len << 12);
             // misses per length class (one shared-memory atomic per class per warp)
             const uint32_t peers = __match_any_sync(0xFFFFFFFFu, cls);
             if (cls != 0xFFFFFFFFu && (uint32_t)(__ffs((int)peers) - 1) == lane) atomicAdd(&S.cls_n[cls], (uint32_t)__popc(peers));
@@ -766,15 +764,14 @@ __global__ void __launch_bounds__(LK_T) lookup_kernel(const uint8_t* __restrict_
     }
     __syncthreads();
     if (t < TKK_N_CLASSES && S.cls_n[t]) S.cls_base[t] = atomicAdd(q_n + t, S.cls_n[t]);   // this tile's range of every queue
-    // per window: first slot | number of vocabulary-entry pieces << 16 (K2m adds the ranks of the merged pieces)
-    if (t < LK_WINS) win_info[win0 + t] = (S.wfirst[t] & 0xFFFFu) | (S.whits[t] << 16);
+    if (t == 32 && S.n_hit) atomicAdd(tile_count + tile, (unsigned long long)S.n_hit);
     __syncthreads();
     // ---- C: misses into the queue of their length class ----
     const uint32_t nm = S.n_miss;
     for (uint32_t i0 = 0; i0 < nm; i0 += LK_T) {
         const uint32_t i = i0 + t;
         uint32_t e = 0, cls = 0xFFFFFFFFu;
-        if (i < nm) { e = S.missq[i]; cls = lane_class((e >> 12) & 127u); }
+        if (i < nm) { e = S.missq[i]; cls = lane_class(e >> 12); }
         const uint32_t peers = __match_any_sync(0xFFFFFFFFu, cls);
         if (cls != 0xFFFFFFFFu) {
             const int leader = __ffs((int)peers) - 1;
@@ -782,8 +779,7 @@ __global__ void __launch_bounds__(LK_T) lookup_kernel(const uint8_t* __restrict_
             if ((int)lane == leader) base = atomicAdd(&S.cls_pos[cls], (uint32_t)__popc(peers));
             base = __shfl_sync(peers, base, leader);
             const uint32_t pos = S.cls_base[cls] + base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
-            queues[Q.off[cls] + pos] = (tile_pos + (e & 4095u)) | ((unsigned long long)((e >> 12) & 127u) << QE_START_BITS) |
-                                       ((unsigned long long)(e >> 19) << (QE_START_BITS + QE_LEN_BITS));
+            queues[Q.off[cls] + pos] = (tile_pos + (e & 4095u)) | ((unsigned long long)(e >> 12) << QE_START_BITS);
         }
     }
 }
@@ -792,7 +788,7 @@ template <int MAXLEN, int THREADS>
 __global__ void __launch_bounds__(THREADS) lanemerge_kernel(const uint8_t* __restrict__ data, TkDeviceTables T,
                                                             const unsigned long long* __restrict__ queue,
                                                             const uint32_t* __restrict__ q_n, uint32_t* __restrict__ q_w,
-                                                            uint32_t* __restrict__ stream, uint32_t* __restrict__ win_info) {
+                                                            uint32_t* __restrict__ stream, unsigned long long* __restrict__ tile_count) {
     constexpr int STRIDE = MAXLEN + 1;      // odd: lane i's arrays start at bank i (no conflicts when lanes sweep together)
     extern __shared__ __align__(16) uint32_t lm_raw[];
     uint32_t* id = lm_raw + threadIdx.x * STRIDE;
@@ -814,7 +810,6 @@ __global__ void __launch_bounds__(THREADS) lanemerge_kernel(const uint8_t* __res
             const unsigned long long e = queue[k];
             const uint64_t start = e & ((1ull << QE_START_BITS) - 1ull);
             const uint32_t len = (uint32_t)(e >> QE_START_BITS) & ((1u << QE_LEN_BITS) - 1u);
-            const uint32_t off = (uint32_t)(e >> (QE_START_BITS + QE_LEN_BITS));
             const uint8_t* b = data + start;
             for (uint32_t i = 0; i < len; i += 4) {
                 uint32_t v[4];
@@ -839,12 +834,15 @@ __global__ void __launch_bounds__(THREADS) lanemerge_kernel(const uint8_t* __res
             }
             using Mask = typename std::conditional<(MAXLEN <= 32), uint32_t, unsigned long long>::type;
             Mask live = tk_bpe_merge_loop<Mask>(T, len, id, key);
-            uint32_t* dst = stream + (start / LK_TILE) * (uint64_t)LK_CAP + off;
-            atomicAdd(win_info + (start >> 5), tk_popc_m(live) << 16);        // ranks of the window the piece starts in
+            // ranks to stream[start ...]; the first one carries the count (>= 2) in bits 21..27, the last one bit 31
+            uint32_t* dst = stream + start;
+            atomicAdd(tile_count + start / TKK_COUNT_TILE, (unsigned long long)tk_popc_m(live));
+            uint32_t first = tk_popc_m(live) << EN_COUNT_SHIFT;
             while (live) {
                 const uint32_t j = tk_ffs_m(live) - 1u;
                 live &= live - 1;
-                *dst++ = live ? id[j] : (id[j] | EN_LAST);
+                *dst++ = (live ? id[j] : (id[j] | EN_LAST)) | first;
+                first = 0;
             }
         }
         __syncwarp();
@@ -852,28 +850,108 @@ __global__ void __launch_bounds__(THREADS) lanemerge_kernel(const uint8_t* __res
 }
 
 // =====================================================================================================
-// K4: emit.  One block per 8 KiB of text (256 windows): tokens per window (ranks from the stream,
-// long pieces from K3's records, BOS/EOS at document starts) -> block scan -> decoupled look-back
-// over tiles (one warp, 32 predecessors per step) -> ids (+num_special) compacted in shared memory
-// and written to their final place with coalesced stores; per-document token offsets.
+// K3s: exclusive prefix of the per-tile token counts (lookup, lane-merge, long-piece and document
+// kernels add to them) -> first output position of every tile.  Three tiny kernels: block sums,
+// scan of the block sums, apply.
 // =====================================================================================================
-#define EM_T 256
-#define EM_WINS 256
-#define EM_TILE (EM_WINS * 32)
-#define EM_CAP (EM_TILE + 512)
-#define EM_LONGCAP (EM_TILE / 64 + 2)
+#define TS_T 256
+#define TS_PER 8
+#define TS_BLOCK (TS_T * TS_PER)
 
-struct EnLongCopy {
-    unsigned long long dst, src;
-    uint32_t count, pad;
+__device__ __forceinline__ unsigned long long ts_block_excl(unsigned long long v, unsigned long long* wsum, unsigned long long* total) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    unsigned long long inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned long long o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if (lane >= (uint32_t)d) inc += o;
+    }
+    __syncthreads();
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    unsigned long long before = 0, all = 0;
+#pragma unroll
+    for (int w = 0; w < TS_T / 32; ++w) { if (w < (int)warp) before += wsum[w]; all += wsum[w]; }
+    *total = all;
+    return before + inc - v;
+}
+
+__global__ void __launch_bounds__(TS_T) tilesum_kernel(const unsigned long long* __restrict__ tile_count, uint32_t n_tiles,
+                                                       unsigned long long* __restrict__ bsum) {
+    __shared__ unsigned long long wsum[TS_T / 32];
+    unsigned long long v = 0;
+#pragma unroll
+    for (int j = 0; j < TS_PER; ++j) {
+        const uint64_t i = (uint64_t)blockIdx.x * TS_BLOCK + (uint64_t)j * TS_T + threadIdx.x;
+        if (i < n_tiles) v += tile_count[i];
+    }
+    unsigned long long total;
+    ts_block_excl(v, wsum, &total);
+    if (threadIdx.x == 0) bsum[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(TS_T) tilescan_kernel(unsigned long long* __restrict__ bsum, uint32_t n_blocks, uint64_t out_cap,
+                                                        unsigned long long* __restrict__ total_out, uint32_t* __restrict__ flags) {
+    __shared__ unsigned long long wsum[TS_T / 32];
+    unsigned long long run = 0;
+    for (uint32_t b0 = 0; b0 < n_blocks; b0 += TS_T) {
+        const uint32_t i = b0 + threadIdx.x;
+        const unsigned long long v = i < n_blocks ? bsum[i] : 0ull;
+        unsigned long long total;
+        const unsigned long long e = ts_block_excl(v, wsum, &total);
+        if (i < n_blocks) bsum[i] = run + e;          // in place: sum -> exclusive prefix
+        run += total;
+    }
+    if (threadIdx.x == 0) {
+        *total_out = run;
+        if (run > out_cap) atomicOr(flags, TKK_FLAG_OUT_FULL);
+    }
+}
+
+__global__ void __launch_bounds__(TS_T) tileapply_kernel(const unsigned long long* __restrict__ tile_count, uint32_t n_tiles,
+                                                         const unsigned long long* __restrict__ bbase,
+                                                         unsigned long long* __restrict__ tile_base) {
+    __shared__ unsigned long long wsum[TS_T / 32];
+    unsigned long long run = bbase[blockIdx.x];
+#pragma unroll
+    for (int j = 0; j < TS_PER; ++j) {
+        const uint64_t i = (uint64_t)blockIdx.x * TS_BLOCK + (uint64_t)j * TS_T + threadIdx.x;
+        const unsigned long long v = i < n_tiles ? tile_count[i] : 0ull;
+        unsigned long long total;
+        const unsigned long long e = ts_block_excl(v, wsum, &total);
+        if (i < n_tiles) tile_base[i] = run + e;
+        run += total;
+    }
+}
+
+// =====================================================================================================
+// K4: emit.  One block per 4 KiB of text, E2_PER consecutive pieces per lane: tokens of the piece (its
+// ranks from the stream, a long piece's count from K3's record) plus BOS/EOS of the documents that
+// start at it -> block scan -> ids (+num_special) staged in shared memory -> coalesced stores starting
+// at the tile's first output position (known from K3s: no tile waits for another); per-document
+// token offsets.  Long pieces are copied from K3's pool by the whole block.  A
+// tile whose specials do not fit the staging buffer (thousands of empty documents in 4 KiB) is
+// finished by emit_slow_kernel.
+// =====================================================================================================
+#define E2_T 256
+#define E2_PER 4
+#define E2_COMP (LK_TILE + 1024)
+#define E2_LONGCAP (LK_TILE / 64 + 2)
+
+struct E2Long {
+    unsigned long long src, dst_local;
+    uint32_t count, comp_pos;
 };
 
-struct EmSmem {
-    uint32_t comp[EM_CAP];
-    EnLongCopy longs[EM_LONGCAP];
-    uint32_t wsum[EM_T / 32];
-    uint32_t n_longs, tile;
-    unsigned long long base;
+struct E2Smem {
+    uint32_t comp[E2_COMP];
+    uint32_t mask[LK_WINS + 4];
+    uint32_t ds[LK_WINS], lw[LK_WINS], dfirst[LK_WINS];
+    uint16_t list[LK_PCAP];
+    E2Long longs[E2_LONGCAP];
+    unsigned long long wsum64[E2_T / 32];
+    uint32_t wsum[E2_T / 32];
+    uint32_t n_pieces, n_longs, overflow;
 };
 
 // number of documents that start at batch byte position s, given the index of the first of them
@@ -883,170 +961,242 @@ __device__ __forceinline__ uint32_t docs_from(const uint64_t* __restrict__ doc_o
     return (uint32_t)(e - first);
 }
 
-// length of the piece that starts at bit `bit` of window gw (not a long piece: the next start is at most
-// two words away)
-__device__ __forceinline__ uint32_t em_piece_len(const uint32_t* __restrict__ start_mask, uint64_t gw, uint32_t mymask, uint32_t m1, uint32_t bit) {
-    const uint32_t m = bit == 31u ? 0u : (mymask >> (bit + 1u));
-    if (m) return (uint32_t)__ffs((int)m);
-    if (m1) return 32u - bit + (uint32_t)(__ffs((int)m1) - 1);
-    return 64u - bit + (uint32_t)(__ffs((int)start_mask[gw + 2]) - 1);
+// block-wide exclusive prefix of one 64-bit value per thread (E2_T threads); *total = sum over the block
+__device__ __forceinline__ unsigned long long e2_block_excl64(unsigned long long v, unsigned long long* wsum, unsigned long long* total) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    unsigned long long inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned long long o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if (lane >= (uint32_t)d) inc += o;
+    }
+    __syncthreads();          // wsum may still be read from the previous round
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    unsigned long long before = 0, all = 0;
+#pragma unroll
+    for (int w = 0; w < E2_T / 32; ++w) { if (w < (int)warp) before += wsum[w]; all += wsum[w]; }
+    *total = all;
+    return before + inc - v;
 }
 
-__global__ void __launch_bounds__(EM_T) emit_kernel(uint64_t n, const uint32_t* __restrict__ start_mask,
+struct TkkSlowTile {
+    unsigned long long base;
+    uint32_t tile, pad;
+};
+
+__global__ void __launch_bounds__(E2_T) emit_kernel(uint64_t n, const uint32_t* __restrict__ start_mask,
                                                     const uint32_t* __restrict__ ds_mask, const uint32_t* __restrict__ doc_first,
                                                     const uint32_t* __restrict__ long_of_word,
                                                     const TkkLongRec* __restrict__ recs, const uint32_t* __restrict__ pool,
-                                                    const uint32_t* __restrict__ stream, const uint32_t* __restrict__ win_info,
+                                                    const uint32_t* __restrict__ stream,
                                                     const uint64_t* __restrict__ doc_off, uint64_t off_base, uint64_t n_docs, uint32_t add_bos,
                                                     uint32_t add_eos, uint32_t nsp, uint32_t bos_id, uint32_t eos_id,
                                                     uint32_t* __restrict__ out, uint64_t out_cap, uint64_t* __restrict__ tok_off,
-                                                    unsigned long long* __restrict__ tile_state, uint32_t* __restrict__ ticket,
-                                                    unsigned long long* __restrict__ total_out, uint32_t* __restrict__ flags) {
-    __shared__ __align__(16) EmSmem S;
-    const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
-    if (t == 0) {
-        S.tile = atomicAdd(ticket, 1u);   // tiles are numbered in the order blocks start: look-back never waits on an unscheduled block
-        S.n_longs = 0;
-    }
-    __syncthreads();
-    const uint32_t tile = S.tile;
-    const uint64_t gw = (uint64_t)tile * EM_WINS + t;       // my window
-    const uint64_t wpos = gw * 32u;
-    const uint32_t mymask = start_mask[gw], myds = ds_mask[gw];
-    const uint32_t lw = mymask ? long_of_word[gw] : 0u;     // != 0: a long piece starts at my top set bit
-    const uint32_t topbit = mymask ? 31u - (uint32_t)__clz((int)mymask) : 32u;
-    const uint32_t info = mymask ? win_info[gw] : 0u;      // first slot | ranks of the short pieces << 16
-    const uint32_t* src0 = stream + (gw / LK_WINS) * (uint64_t)LK_CAP + (info & 0xFFFFu);
-    const uint64_t mydoc = myds ? doc_first[gw] : 0;        // first document that starts in my window
-    // the slots of my window are read one piece at a time during the walk below: start fetching
-    // their sectors now, so that they arrive while the block scans and looks back
-    if (mymask) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) asm volatile("prefetch.global.L1 [%0];" ::"l"(src0 + 8 * k));
-    }
-    const uint32_t nextmask = start_mask[gw + 1];           // the last piece of my window usually ends there
-    // ---- tokens of my window ----
-    uint32_t count = info >> 16;
-    if (lw) count += recs[lw - 1].count;
+                                                    const unsigned long long* __restrict__ tile_base,
+                                                    TkkSlowTile* __restrict__ slow_list, uint32_t* __restrict__ slow_n) {
+    __shared__ __align__(16) E2Smem S;
+    const uint32_t t = threadIdx.x;
+    if (t == 0) { S.n_longs = 0; S.overflow = 0; }
+    const uint32_t tile = blockIdx.x;
+    const unsigned long long base = tile_base[tile];     // first output position of this tile's tokens (K3s)
+    const uint64_t tile_pos = (uint64_t)tile * LK_TILE;
+    const uint64_t win0 = (uint64_t)tile * LK_WINS;
+    // ---- masks of the tile; list of the piece starts ----
     {
-        uint32_t m = mymask & myds;
-        uint64_t d0 = mydoc;
+        uint32_t m = 0;
+        if (t < LK_WINS + 4) { m = start_mask[win0 + t]; S.mask[t] = m; }
+        if (t < LK_WINS) {
+            const uint32_t d = ds_mask[win0 + t];
+            S.ds[t] = d;
+            S.lw[t] = m ? long_of_word[win0 + t] : 0u;
+            S.dfirst[t] = d ? doc_first[win0 + t] : 0u;
+        } else m = 0;
+        uint32_t np;
+        uint32_t o = lk_block_excl((uint32_t)__popc(m), S.wsum, &np);
+        if (t == 0) S.n_pieces = np;
         while (m) {
-            const uint32_t bit = (uint32_t)(__ffs((int)m) - 1);
+            S.list[o++] = (uint16_t)(t * 32u + (uint32_t)(__ffs((int)m) - 1));
             m &= m - 1;
-            const uint32_t k = docs_from(doc_off, n_docs, wpos + bit + off_base, d0);
-            for (uint64_t d = d0; d < d0 + k; ++d) count += (d > 0 ? add_eos : 0u) + (d < n_docs ? add_bos : 0u);
-            d0 += k;
-        }
-    }
-    uint32_t inc = count;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-        if (lane >= d) inc += o;
-    }
-    if (lane == 31) S.wsum[warp] = inc;
-    __syncthreads();
-    uint32_t before = 0, tile_total = 0;
-#pragma unroll
-    for (int w = 0; w < EM_T / 32; ++w) { if (w < (int)warp) before += S.wsum[w]; tile_total += S.wsum[w]; }
-    const uint32_t my_off = before + inc - count;
-    if (warp == 0) {
-        const unsigned long long excl = tk_lookback(tile_state, tile, tile_total);
-        if (lane == 0) {
-            S.base = excl;
-            if (tile == gridDim.x - 1) {
-                *total_out = excl + tile_total;
-                if (excl + tile_total > out_cap) atomicOr(flags, TKK_FLAG_OUT_FULL);
-            }
         }
     }
     __syncthreads();
-    // ---- emit ----
-    const unsigned long long base = S.base;
-    const bool fits = tile_total <= EM_CAP;     // block-uniform
-    uint32_t* comp = S.comp;
-    {
-        uint64_t o = my_off;
-        uint64_t d0 = mydoc;
-        const uint32_t* src = src0;
-        uint32_t m = mymask;
-        while (m) {
-            const uint32_t bit = (uint32_t)(__ffs((int)m) - 1);
-            m &= m - 1;
-            const uint64_t gpos = wpos + bit;
-            if ((myds >> bit) & 1u) {
-                const uint32_t k = docs_from(doc_off, n_docs, gpos + off_base, d0);
-                for (uint64_t d = d0; d < d0 + k; ++d) {
-                    if (d > 0 && add_eos) {
-                        if (fits) comp[o] = eos_id; else if (base + o < out_cap) out[base + o] = eos_id;
-                        ++o;
-                    }
-                    tok_off[d] = base + o;
-                    if (d < n_docs && add_bos) {
-                        if (fits) comp[o] = bos_id; else if (base + o < out_cap) out[base + o] = bos_id;
-                        ++o;
-                    }
+    const uint32_t np = S.n_pieces;
+    uint32_t run_comp = 0;                 // staged tokens so far (short pieces + specials)
+    unsigned long long run_all = 0;        // all tokens so far (long pieces included)
+    // E2_PER consecutive pieces per lane and round: their stream loads are in flight together and
+    // one block scan serves E2_T * E2_PER pieces (a 4 KiB tile is usually a single round)
+    for (uint32_t k0 = 0; k0 < np; k0 += E2_T * E2_PER) {
+        uint32_t spec[E2_PER], cnt[E2_PER], v0[E2_PER], kdocs[E2_PER], d0[E2_PER], pos[E2_PER], lrec[E2_PER];
+        bool is_long[E2_PER];
+#pragma unroll
+        for (int j = 0; j < E2_PER; ++j) {
+            const uint32_t k = k0 + t * E2_PER + j;
+            spec[j] = cnt[j] = v0[j] = kdocs[j] = d0[j] = lrec[j] = 0;
+            pos[j] = 0xFFFFFFFFu;          // not a piece (past the list, or the end-of-data sentinel)
+            is_long[j] = false;
+            if (k < np) {
+                const uint32_t s = S.list[k];
+                const uint32_t w = s >> 5, bit = s & 31u;
+                if (tile_pos + s < n) {
+                    pos[j] = s;
+                    const uint32_t lwi = S.lw[w];
+                    is_long[j] = lwi != 0u && bit == 31u - (uint32_t)__clz((int)S.mask[w]);
+                    if (is_long[j]) lrec[j] = lwi - 1u;
+                    else v0[j] = __ldg(stream + tile_pos + s);
                 }
-                d0 += k;
-            }
-            if (gpos >= n) continue;                        // the end-of-data sentinel is not a piece
-            if (lw && bit == topbit) {
-                // long piece: all threads copy it after the walk
-                const TkkLongRec r = recs[lw - 1];
-                EnLongCopy c;
-                c.dst = o; c.src = r.tok_base; c.count = r.count; c.pad = 0;
-                S.longs[atomicAdd(&S.n_longs, 1u)] = c;
-                o += r.count;
-                continue;
-            }
-            // ranks of the piece: up to four slots are fetched at a time (reading past the piece is harmless)
-            const uint32_t v0 = __ldg(src);
-            if (v0 & EN_LAST) {
-                const uint32_t idv = (v0 & ~EN_LAST) + nsp;
-                if (fits) comp[o] = idv; else if (base + o < out_cap) out[base + o] = idv;
-                ++o;
-                src += 1;
-                continue;
-            }
-            const uint32_t len = em_piece_len(start_mask, gw, mymask, nextmask, bit);
-            uint32_t v[4] = {v0, __ldg(src + 1), len > 2 ? __ldg(src + 2) : EN_LAST, len > 3 ? __ldg(src + 3) : EN_LAST};
-            for (uint32_t j = 0;;) {
-                bool done = false;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    if (!done) {
-                        const uint32_t idv = (v[c] & ~EN_LAST) + nsp;
-                        if (fits) comp[o] = idv; else if (base + o < out_cap) out[base + o] = idv;
-                        ++o;
-                        done = (v[c] & EN_LAST) != 0u;
+                if ((S.ds[w] >> bit) & 1u) {
+                    uint64_t d = S.dfirst[w];
+                    uint32_t earlier = S.ds[w] & ((1u << bit) - 1u);      // document starts earlier in the same window
+                    while (earlier) {
+                        const uint32_t b2 = (uint32_t)(__ffs((int)earlier) - 1);
+                        earlier &= earlier - 1;
+                        d += docs_from(doc_off, n_docs, tile_pos + w * 32u + b2 + off_base, d);
                     }
+                    d0[j] = (uint32_t)d;
+                    kdocs[j] = docs_from(doc_off, n_docs, tile_pos + s + off_base, d);
+                    for (uint64_t x = d; x < d + kdocs[j]; ++x) spec[j] += (x > 0 ? add_eos : 0u) + (x < n_docs ? add_bos : 0u);
                 }
-                if (done) break;
-                j += 4;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) v[c] = j + c < len ? __ldg(src + j + c) : EN_LAST;
             }
-            src += len;
         }
-    }
-    __syncthreads();
-    {
-        const uint32_t nl = S.n_longs;
-        for (uint32_t k = 0; k < nl; ++k) {
-            const EnLongCopy c = S.longs[k];
-            if (fits) {
-                for (uint32_t i = t; i < c.count; i += EM_T) comp[c.dst + i] = pool[c.src + i] + nsp;
+        // token counts, lane-local prefix
+        unsigned long long mine = 0;       // low 24 bits: staged tokens; above: all tokens
+        bool clamped = false;
+#pragma unroll
+        for (int j = 0; j < E2_PER; ++j) {
+            if (pos[j] != 0xFFFFFFFFu) cnt[j] = is_long[j] ? recs[lrec[j]].count : (v0[j] & EN_LAST) ? 1u : (v0[j] >> EN_COUNT_SHIFT) & 127u;
+            const uint32_t ct = spec[j] + (is_long[j] ? 0u : cnt[j]);
+            clamped |= ct > 0xFFFFu;
+            mine += (unsigned long long)(ct > 0xFFFFu ? 0xFFFFu : ct) | ((unsigned long long)spec[j] + cnt[j]) << 24;
+        }
+        unsigned long long total;
+        const unsigned long long excl = e2_block_excl64(mine, S.wsum64, &total);
+        uint32_t oc = run_comp + (uint32_t)(excl & 0xFFFFFFu);
+        unsigned long long oa = run_all + (excl >> 24);
+        run_comp += (uint32_t)(total & 0xFFFFFFu);
+        run_all += total >> 24;
+        const bool fits_here = !clamped && oc + (uint32_t)(mine & 0xFFFFFFu) <= E2_COMP;
+        if (!fits_here && mine) S.overflow = 1;
+#pragma unroll
+        for (int j = 0; j < E2_PER; ++j) {
+            if (kdocs[j]) {
+                for (uint64_t d = d0[j]; d < (uint64_t)d0[j] + kdocs[j]; ++d) {
+                    if (d > 0 && add_eos) { if (fits_here) S.comp[oc] = eos_id; ++oc; ++oa; }
+                    tok_off[d] = base + oa;
+                    if (d < n_docs && add_bos) { if (fits_here) S.comp[oc] = bos_id; ++oc; ++oa; }
+                }
+            }
+            if (pos[j] == 0xFFFFFFFFu) continue;
+            if (is_long[j]) {
+                const uint32_t li = atomicAdd(&S.n_longs, 1u);
+                E2Long L;
+                L.src = recs[lrec[j]].tok_base; L.dst_local = oa; L.count = cnt[j]; L.comp_pos = oc;
+                S.longs[li] = L;
+                oa += cnt[j];
             } else {
-                for (uint32_t i = t; i < c.count; i += EM_T)
-                    if (base + c.dst + i < out_cap) out[base + c.dst + i] = pool[c.src + i] + nsp;
+                if (fits_here) {
+                    S.comp[oc] = (v0[j] & EN_ID_MASK) + nsp;
+                    const uint32_t* src = stream + tile_pos + pos[j];
+                    for (uint32_t i = 1; i < cnt[j]; ++i) S.comp[oc + i] = (__ldg(src + i) & EN_ID_MASK) + nsp;
+                }
+                oc += cnt[j];
+                oa += cnt[j];
             }
         }
-        if (nl && fits) __syncthreads();
     }
-    if (fits) {
-        for (uint32_t i = t; i < tile_total; i += EM_T)
-            if (base + i < out_cap) out[base + i] = comp[i];
+    __syncthreads();
+    if (S.overflow) {
+        if (t == 0) {
+            TkkSlowTile e;
+            e.base = base; e.tile = tile; e.pad = 0;
+            slow_list[atomicAdd(slow_n, 1u)] = e;
+        }
+        return;
+    }
+    // staged ids -> output; ids after a long piece shift by its length
+    const uint32_t nl = S.n_longs;
+    for (uint32_t i = t; i < run_comp; i += E2_T) {
+        unsigned long long o = base + i;
+        for (uint32_t l = 0; l < nl; ++l) o += S.longs[l].comp_pos <= i ? S.longs[l].count : 0u;
+        if (o < out_cap) out[o] = S.comp[i];
+    }
+    for (uint32_t l = 0; l < nl; ++l) {
+        const E2Long L = S.longs[l];
+        for (uint32_t i = t; i < L.count; i += E2_T)
+            if (base + L.dst_local + i < out_cap) out[base + L.dst_local + i] = pool[L.src + i] + nsp;
+    }
+}
+
+// Tiles emit_kernel could not stage (listed with their base): one thread per window walks its pieces
+// twice (count, then write straight to the output).
+__global__ void __launch_bounds__(LK_WINS) emit_slow_kernel(uint64_t n, const uint32_t* __restrict__ start_mask,
+                                                            const uint32_t* __restrict__ ds_mask, const uint32_t* __restrict__ doc_first,
+                                                            const uint32_t* __restrict__ long_of_word,
+                                                            const TkkLongRec* __restrict__ recs, const uint32_t* __restrict__ pool,
+                                                            const uint32_t* __restrict__ stream,
+                                                            const uint64_t* __restrict__ doc_off, uint64_t off_base, uint64_t n_docs,
+                                                            uint32_t add_bos, uint32_t add_eos, uint32_t nsp, uint32_t bos_id, uint32_t eos_id,
+                                                            uint32_t* __restrict__ out, uint64_t out_cap, uint64_t* __restrict__ tok_off,
+                                                            const TkkSlowTile* __restrict__ slow_list, const uint32_t* __restrict__ slow_n) {
+    __shared__ unsigned long long wsum[LK_WINS / 32];
+    const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    const uint32_t total = *slow_n;
+    for (uint32_t e = blockIdx.x; e < total; e += gridDim.x) {
+        const TkkSlowTile st = slow_list[e];
+        const uint64_t gw = (uint64_t)st.tile * LK_WINS + t;
+        const uint64_t wpos = gw * 32u;
+        const uint32_t mymask = start_mask[gw], myds = ds_mask[gw];
+        const uint32_t lw = mymask ? long_of_word[gw] : 0u;
+        const uint32_t topbit = mymask ? 31u - (uint32_t)__clz((int)mymask) : 32u;
+        const uint64_t mydoc = myds ? doc_first[gw] : 0;
+        unsigned long long o = 0;
+        for (int pass = 0; pass < 2; ++pass) {
+            uint64_t d0 = mydoc;
+            uint32_t m = mymask;
+            while (m) {
+                const uint32_t bit = (uint32_t)(__ffs((int)m) - 1);
+                m &= m - 1;
+                const uint64_t gpos = wpos + bit;
+                if ((myds >> bit) & 1u) {
+                    const uint32_t k = docs_from(doc_off, n_docs, gpos + off_base, d0);
+                    for (uint64_t d = d0; d < d0 + k; ++d) {
+                        if (d > 0 && add_eos) { if (pass && o < out_cap) out[o] = eos_id; ++o; }
+                        if (pass) tok_off[d] = o;
+                        if (d < n_docs && add_bos) { if (pass && o < out_cap) out[o] = bos_id; ++o; }
+                    }
+                    d0 += k;
+                }
+                if (gpos >= n) continue;
+                if (lw && bit == topbit) {
+                    const TkkLongRec r = recs[lw - 1];
+                    if (pass) for (uint32_t j = 0; j < r.count; ++j) if (o + j < out_cap) out[o + j] = pool[r.tok_base + j] + nsp;
+                    o += r.count;
+                    continue;
+                }
+                for (uint32_t j = 0;; ++j) {
+                    const uint32_t v = __ldg(stream + gpos + j);
+                    if (pass && o < out_cap) out[o] = (v & EN_ID_MASK) + nsp;
+                    ++o;
+                    if (v & EN_LAST) break;
+                }
+            }
+            if (pass == 0) {
+                // exclusive prefix of the window totals -> where my window starts
+                unsigned long long inc = o;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    unsigned long long x = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                    if (lane >= (uint32_t)d) inc += x;
+                }
+                __syncthreads();
+                if (lane == 31) wsum[warp] = inc;
+                __syncthreads();
+                unsigned long long before = 0;
+                for (uint32_t w = 0; w < warp; ++w) before += wsum[w];
+                o = st.base + before + inc - o;
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -1073,9 +1223,11 @@ size_t encode_workspace_bytes(uint64_t n, uint64_t n_docs, EncodeLayout* L) {
     l.off_worklist = take(n_tiles * 4);
     l.off_seg = take((ceil_div(n_tiles, SG_TILES) + 1) * 3 * 4);
     l.n_ltiles = n_tiles * (PT_T / LK_WINS);            // lookup tiles cover exactly the emit tiles
-    l.off_tilestate = take(n_tiles * 8);
-    l.off_wininfo = take(words * 4);
-    l.off_stream = take(l.n_ltiles * (size_t)LK_CAP * 4);
+    l.off_tilecount = take((l.n_ltiles + 1) * 8);
+    l.off_tilebase = take((l.n_ltiles + 1) * 8);
+    l.off_bsum = take((ceil_div(l.n_ltiles, TS_BLOCK) + 1) * 8);
+    l.off_slow = take((l.n_ltiles + 1) * sizeof(TkkSlowTile));
+    l.off_stream = take((n + TK_LANE_MAX + 64) * 4);
     {
         // a queue per length class; a class whose shortest piece has m bytes holds at most n/m + 1 pieces
         const uint32_t shortest[TKK_N_CLASSES] = {2, 5, 9, 17, 33};
@@ -1110,7 +1262,7 @@ cudaError_t publish_counters(const void* d_ws, const EncodeLayout& L, uint32_t* 
 template <int MAXLEN, int THREADS>
 static cudaError_t launch_lanemerge(int blocks_per_sm, int sm_count, const uint8_t* d_data, const TkDeviceTables& T,
                                     const unsigned long long* queue, const uint32_t* q_n, uint32_t* q_w, uint32_t* stream,
-                                    uint32_t* win_info, cudaStream_t st) {
+                                    unsigned long long* tile_count, cudaStream_t st) {
     const size_t smem = (size_t)2 * THREADS * (MAXLEN + 1) * sizeof(uint32_t);
     static std::atomic<uint64_t> attr_set{0};   // bit per device ordinal
     int dev = 0;
@@ -1119,7 +1271,7 @@ static cudaError_t launch_lanemerge(int blocks_per_sm, int sm_count, const uint8
         CK(cudaFuncSetAttribute(lanemerge_kernel<MAXLEN, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set.fetch_or(1ull << (dev & 63));
     }
-    lanemerge_kernel<MAXLEN, THREADS><<<(unsigned)(sm_count * blocks_per_sm), THREADS, smem, st>>>(d_data, T, queue, q_n, q_w, stream, win_info);
+    lanemerge_kernel<MAXLEN, THREADS><<<(unsigned)(sm_count * blocks_per_sm), THREADS, smem, st>>>(d_data, T, queue, q_n, q_w, stream, tile_count);
     count_launch();
     return cudaSuccess;
 }
@@ -1137,11 +1289,13 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
     TkkTileSummary* summ = (TkkTileSummary*)(ws + L.off_summ);
     uint32_t* carry = (uint32_t*)(ws + L.off_carry);
     uint32_t* worklist = (uint32_t*)(ws + L.off_worklist);
-    unsigned long long* tilestate = (unsigned long long*)(ws + L.off_tilestate);
+    unsigned long long* tile_count = (unsigned long long*)(ws + L.off_tilecount);
+    unsigned long long* tile_base = (unsigned long long*)(ws + L.off_tilebase);
+    unsigned long long* bsum = (unsigned long long*)(ws + L.off_bsum);
     TkkLongRec* recs = (TkkLongRec*)(ws + L.off_recs);
     uint32_t* huge = (uint32_t*)(ws + L.off_huge);
     uint32_t* pool = (uint32_t*)(ws + L.off_pool);
-    uint32_t* win_info = (uint32_t*)(ws + L.off_wininfo);
+    TkkSlowTile* slow_list = (TkkSlowTile*)(ws + L.off_slow);
     uint32_t* stream = (uint32_t*)(ws + L.off_stream);
     unsigned long long* queues = (unsigned long long*)(ws + L.off_queues);
     // small block layout
@@ -1152,9 +1306,9 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
     uint32_t* n_huge = small + TKK_S_NHUGE;
     uint32_t* wc_long = small + TKK_S_WC_LONG;
     uint32_t* wc_huge = small + TKK_S_WC_HUGE;
-    uint32_t* ticket = small + TKK_S_TICKET;
     uint32_t* q_n = small + TKK_S_QN;
     uint32_t* q_w = small + TKK_S_QW;
+    uint32_t* slow_n = small + TKK_S_SLOWN;
     unsigned long long* pool_cursor = (unsigned long long*)(small + TKK_S_POOLCUR);
     unsigned long long* scratch_cursor = (unsigned long long*)(small + TKK_S_SCRCUR);
     unsigned long long* total_out = (unsigned long long*)(small + TKK_S_TOTAL);
@@ -1165,8 +1319,8 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
     CK(cudaMemsetAsync(ds, 0, L.mask_words * 4, st));
     CK(cudaMemsetAsync(docfirst, 0xFF, L.mask_words * 4, st));
     CK(cudaMemsetAsync(start + L.n_windows, 0, (L.mask_words - L.n_windows) * 4, st));
-    CK(cudaMemsetAsync(tilestate, 0, L.n_tiles * 8, st));
-    docmark_kernel<<<(unsigned)ceil_div(n_docs + 1, 256), 256, 0, st>>>(d_doc_off, off_base, n_docs, n, ds, docfirst, flags);
+    CK(cudaMemsetAsync(tile_count, 0, (L.n_ltiles + 1) * 8, st));
+    docmark_kernel<<<(unsigned)ceil_div(n_docs + 1, 256), 256, 0, st>>>(d_doc_off, off_base, n_docs, n, add_bos ? 1u : 0u, add_eos ? 1u : 0u, ds, docfirst, tile_count, flags);
     TK_LAUNCHED();
     if (timer) timer->mark(st, "pretok");
     pretok_kernel<<<(unsigned)L.n_tiles, PT_T, 0, st>>>(d_data, n, ds, start, L.n_windows, T, summ, err_pos);
@@ -1196,33 +1350,45 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
         const uint64_t cap = (uint64_t)sm_count * 12;
         if (blocks > cap) blocks = cap;
         longmerge_warp_kernel<<<(unsigned)blocks, LM_WARPS * 32, 0, st>>>(d_data, start, T, recs, n_long, pool, pool_cursor, huge,
-                                                                        n_huge, wc_long);
+                                                                        n_huge, wc_long, tile_count);
         TK_LAUNCHED();
         uint64_t hb = L.max_long < (uint64_t)(2 * sm_count) ? L.max_long : (uint64_t)(2 * sm_count);
         longmerge_block_kernel<<<(unsigned)hb, HG_T, 0, st>>>(d_data, T, recs, huge, n_huge, pool, d_scratch, scratch_cap,
-                                                             scratch_cursor, wc_huge, flags);
+                                                             scratch_cursor, wc_huge, flags, tile_count);
         TK_LAUNCHED();
     }
     if (timer) timer->mark(st, "lookup");
     {
-        lookup_kernel<<<(unsigned)L.n_ltiles, LK_T, 0, st>>>(d_data, n, start, T, stream, win_info, queues, L.queues, q_n);
+        lookup_kernel<<<(unsigned)L.n_ltiles, LK_T, 0, st>>>(d_data, n, start, T, stream, queues, L.queues, q_n, tile_count);
         TK_LAUNCHED();
     }
     if (timer) timer->mark(st, "lanemerge64");
-    CK((launch_lanemerge<64, 128>(3, sm_count, d_data, T, queues + L.queues.off[4], q_n + 4, q_w + 4, stream, win_info, st)));
+    CK((launch_lanemerge<64, 128>(3, sm_count, d_data, T, queues + L.queues.off[4], q_n + 4, q_w + 4, stream, tile_count, st)));
     if (timer) timer->mark(st, "lanemerge32");
-    CK((launch_lanemerge<32, 256>(3, sm_count, d_data, T, queues + L.queues.off[3], q_n + 3, q_w + 3, stream, win_info, st)));
+    CK((launch_lanemerge<32, 256>(3, sm_count, d_data, T, queues + L.queues.off[3], q_n + 3, q_w + 3, stream, tile_count, st)));
     if (timer) timer->mark(st, "lanemerge16");
-    CK((launch_lanemerge<16, 256>(6, sm_count, d_data, T, queues + L.queues.off[2], q_n + 2, q_w + 2, stream, win_info, st)));
+    CK((launch_lanemerge<16, 256>(6, sm_count, d_data, T, queues + L.queues.off[2], q_n + 2, q_w + 2, stream, tile_count, st)));
     if (timer) timer->mark(st, "lanemerge8");
-    CK((launch_lanemerge<8, 256>(8, sm_count, d_data, T, queues + L.queues.off[1], q_n + 1, q_w + 1, stream, win_info, st)));
+    CK((launch_lanemerge<8, 256>(8, sm_count, d_data, T, queues + L.queues.off[1], q_n + 1, q_w + 1, stream, tile_count, st)));
     if (timer) timer->mark(st, "lanemerge4");
-    CK((launch_lanemerge<4, 256>(8, sm_count, d_data, T, queues + L.queues.off[0], q_n + 0, q_w + 0, stream, win_info, st)));
+    CK((launch_lanemerge<4, 256>(8, sm_count, d_data, T, queues + L.queues.off[0], q_n + 0, q_w + 0, stream, tile_count, st)));
     if (timer) timer->mark(st, "emit");
-    static_assert(EM_WINS == PT_T, "emit tiles are the pre-tokeniser's tiles");
-    emit_kernel<<<(unsigned)L.n_tiles, EM_T, 0, st>>>(n, start, ds, docfirst, longword, recs, pool, stream, win_info, d_doc_off, off_base, n_docs,
-                                                     add_bos ? 1u : 0u, add_eos ? 1u : 0u, T.num_special, T.bos_id, T.eos_id, d_out,
-                                                     out_cap, d_tok_off, tilestate, ticket, total_out, flags);
+    {
+        const uint32_t nb = (uint32_t)ceil_div(L.n_ltiles, TS_BLOCK);
+        tilesum_kernel<<<nb, TS_T, 0, st>>>(tile_count, (uint32_t)L.n_ltiles, bsum);
+        TK_LAUNCHED();
+        tilescan_kernel<<<1, TS_T, 0, st>>>(bsum, nb, out_cap, total_out, flags);
+        TK_LAUNCHED();
+        tileapply_kernel<<<nb, TS_T, 0, st>>>(tile_count, (uint32_t)L.n_ltiles, bsum, tile_base);
+        TK_LAUNCHED();
+    }
+    emit_kernel<<<(unsigned)L.n_ltiles, E2_T, 0, st>>>(n, start, ds, docfirst, longword, recs, pool, stream, d_doc_off, off_base, n_docs,
+                                                      add_bos ? 1u : 0u, add_eos ? 1u : 0u, T.num_special, T.bos_id, T.eos_id, d_out,
+                                                      out_cap, d_tok_off, tile_base, slow_list, slow_n);
+    TK_LAUNCHED();
+    emit_slow_kernel<<<(unsigned)(2 * sm_count), LK_WINS, 0, st>>>(n, start, ds, docfirst, longword, recs, pool, stream, d_doc_off, off_base,
+                                                                  n_docs, add_bos ? 1u : 0u, add_eos ? 1u : 0u, T.num_special, T.bos_id,
+                                                                  T.eos_id, d_out, out_cap, d_tok_off, slow_list, slow_n);
     TK_LAUNCHED();
     if (timer) timer->mark(st, "end");
     return cudaGetLastError();

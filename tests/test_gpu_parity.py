@@ -157,6 +157,23 @@ def test_ragged_and_empty_documents(gpu_tok, oracle):
     assert len(ids) == 0 and toff.tolist() == [0]
 
 
+def test_many_tiny_and_empty_documents(gpu_tok, oracle):
+    # thousands of document starts inside one 4 KiB tile: more BOS/EOS than the emit kernel stages in shared
+    # memory (its slow path), several documents per 32-byte window, runs of empty documents
+    rng = random.Random(21)
+    texts = []
+    for _ in range(30000):
+        r = rng.random()
+        texts.append(b"" if r < 0.5 else rng.choice([b"a", b"ab", b" x", "é".encode(), b"12", b"\n", b"hi there", b"!"]) if r < 0.97
+                     else ("word " * rng.randint(1, 300)).encode())
+    texts += [b""] * 5000 + [b"tail"] + [b""] * 3000
+    data, off = _pack(texts)
+    for bos, eos in ((True, True), (False, True), (False, False)):
+        ids, toff = assert_same_batch(gpu_tok, oracle, data, off, bos, eos)
+    raw, boff = gpu_tok.decode_batch_np(ids, toff, SpecialTokenPolicy.Ignore)
+    assert np.array_equal(boff, off)
+
+
 # ------------------------------------------------------------------------------------------ the five configs
 
 def test_config1_english_1mib(gpu_tok, oracle):
