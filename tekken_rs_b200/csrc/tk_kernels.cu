@@ -640,9 +640,8 @@ __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __
 #define LK_TILE (LK_WINS * 32)
 #define LK_CAP (LK_TILE + TK_LANE_MAX)      // slots a tile can need (pieces that start in it)
 #define LK_PCAP (LK_TILE + 4)               // pieces that can start in a tile (+ the end sentinel)
-#define EN_LAST 0x80000000u
-#define EN_COUNT_SHIFT 21                   // a merged piece's first rank carries its rank count here (ids are < 2^21)
-#define EN_ID_MASK ((1u << EN_COUNT_SHIFT) - 1u)
+#define EN_INVALID 0xFFFFFFFFu               // stream word: no rank at this byte position
+#define EN_LONGREF 0xFFFFFFFEu               // stream word: a long piece starts here (its ranks are in K3's pool)
 #define QE_START_BITS 40
 #define QE_LEN_BITS 7
 
@@ -651,7 +650,8 @@ __host__ __device__ __forceinline__ uint32_t lane_class(uint32_t len) {        /
 }
 
 struct LkSmem {
-    uint8_t bytes[LK_TILE + TK_LANE_MAX + 16];
+    uint32_t words[LK_TILE];           // the tile's stream words (rank / EN_INVALID / EN_LONGREF per byte position); 16-byte aligned
+    uint8_t bytes[LK_TILE + TK_LANE_MAX + 16];   // 16-byte aligned
     uint32_t mask[LK_WINS + 4];
     uint16_t list[LK_PCAP];            // tile-relative starts of all pieces, in order
     uint32_t missq[LK_TILE / 2 + 4];   // pieces to merge: start | len << 12
@@ -726,9 +726,9 @@ __global__ void __launch_bounds__(LK_T) lookup_kernel(const uint8_t* __restrict_
             m &= m - 1;
         }
     }
+    for (uint32_t i = t; i < LK_TILE; i += LK_T) S.words[i] = EN_INVALID;
     __syncthreads();
     const uint32_t np = S.n_pieces;
-    uint32_t* dst = stream + tile_pos;                  // the rank(s) of the piece that starts at byte p go to stream[p ...]
 
     // ---- B: one lane per piece: whole-piece vocabulary lookup; entries written, misses collected ----
     for (uint32_t k0 = 0; k0 < np; k0 += LK_T) {
@@ -739,13 +739,13 @@ __global__ void __launch_bounds__(LK_T) lookup_kernel(const uint8_t* __restrict_
             s = S.list[k];
             if (tile_pos + s < n) {                        // the end-of-data sentinel is not a piece
                 const uint32_t e = en_piece_end(S.mask, s);
-                if (e != 0xFFFFFFFFu && e - s <= TK_LANE_MAX) {         // longer pieces: K3
+                if (e != 0xFFFFFFFFu && e - s <= TK_LANE_MAX) {
                     len = e - s;
                     const uint32_t whole = tk_vocab_lookup_w32(T, S.bytes, s, len);
-                    if (whole != TK_INF) { dst[s] = whole | EN_LAST; hit = true; }
-                    else if (len == 1) { dst[s] = (uint32_t)S.bytes[s] | EN_LAST; hit = true; }
+                    if (whole != TK_INF) { S.words[s] = whole; hit = true; }
+                    else if (len == 1) { S.words[s] = (uint32_t)S.bytes[s]; hit = true; }
                     else cls = lane_class(len);
-                }
+                } else S.words[s] = EN_LONGREF;                        // longer pieces: K3
             }
         }
         const uint32_t hm = __ballot_sync(0xFFFFFFFFu, hit);
@@ -765,6 +765,12 @@ __global__ void __launch_bounds__(LK_T) lookup_kernel(const uint8_t* __restrict_
     __syncthreads();
     if (t < TKK_N_CLASSES && S.cls_n[t]) S.cls_base[t] = atomicAdd(q_n + t, S.cls_n[t]);   // this tile's range of every queue
     if (t == 32 && S.n_hit) atomicAdd(tile_count + tile, (unsigned long long)S.n_hit);
+    {
+        // the tile's stream words, coalesced.  K2m later overwrites the positions of merged pieces.
+        uint4* dst = reinterpret_cast<uint4*>(stream + tile_pos);
+        const uint4* src = reinterpret_cast<const uint4*>(S.words);
+        for (uint32_t i = t; i < LK_TILE / 4; i += LK_T) dst[i] = src[i];
+    }
     __syncthreads();
     // ---- C: misses into the queue of their length class ----
     const uint32_t nm = S.n_miss;
@@ -834,15 +840,20 @@ __global__ void __launch_bounds__(THREADS) lanemerge_kernel(const uint8_t* __res
             }
             using Mask = typename std::conditional<(MAXLEN <= 32), uint32_t, unsigned long long>::type;
             Mask live = tk_bpe_merge_loop<Mask>(T, len, id, key);
-            // ranks to stream[start ...]; the first one carries the count (>= 2) in bits 21..27, the last one bit 31
+            {
+                // the ranks go to consecutive byte positions from `start`: count them for the tile each one lands in
+                const uint32_t cnt = tk_popc_m(live);
+                const uint64_t tile0 = start / TKK_COUNT_TILE;
+                const uint32_t room = (uint32_t)((tile0 + 1) * TKK_COUNT_TILE - start);
+                atomicAdd(tile_count + tile0, (unsigned long long)(cnt < room ? cnt : room));
+                if (cnt > room) atomicAdd(tile_count + tile0 + 1, (unsigned long long)(cnt - room));
+            }
+            // ranks to stream[start ...] (the piece's remaining positions stay EN_INVALID)
             uint32_t* dst = stream + start;
-            atomicAdd(tile_count + start / TKK_COUNT_TILE, (unsigned long long)tk_popc_m(live));
-            uint32_t first = tk_popc_m(live) << EN_COUNT_SHIFT;
             while (live) {
                 const uint32_t j = tk_ffs_m(live) - 1u;
                 live &= live - 1;
-                *dst++ = (live ? id[j] : (id[j] | EN_LAST)) | first;
-                first = 0;
+                *dst++ = id[j];
             }
         }
         __syncwarp();
@@ -925,33 +936,20 @@ __global__ void __launch_bounds__(TS_T) tileapply_kernel(const unsigned long lon
 }
 
 // =====================================================================================================
-// K4: emit.  One block per 4 KiB of text, E2_PER consecutive pieces per lane: tokens of the piece (its
-// ranks from the stream, a long piece's count from K3's record) plus BOS/EOS of the documents that
-// start at it -> block scan -> ids (+num_special) staged in shared memory -> coalesced stores starting
-// at the tile's first output position (known from K3s: no tile waits for another); per-document
-// token offsets.  Long pieces are copied from K3's pool by the whole block.  A
-// tile whose specials do not fit the staging buffer (thousands of empty documents in 4 KiB) is
-// finished by emit_slow_kernel.
+// K4: emit.  The rank stream holds, for every byte position of the text, the rank of the token that
+// the reference emits there, EN_INVALID, or EN_LONGREF; emit is a compaction of it.  One block per
+// 4 KiB of text, 16 consecutive positions per thread: four 16-byte loads, count (ranks + the long
+// piece's tokens + BOS/EOS of the documents that start here), block scan, ids (+num_special) written
+// from the tile's first output position (known from K3s: no tile waits for another); per-document
+// token offsets.  Long pieces are copied from K3's pool by the whole block.
 // =====================================================================================================
-#define E2_T 256
-#define E2_PER 4
-#define E2_COMP (LK_TILE + 1024)
-#define E2_LONGCAP (LK_TILE / 64 + 2)
+#define E3_T 256
+#define E3_PER 16
+#define E3_LONGCAP (LK_TILE / 64 + 2)
 
-struct E2Long {
-    unsigned long long src, dst_local;
-    uint32_t count, comp_pos;
-};
-
-struct E2Smem {
-    uint32_t comp[E2_COMP];
-    uint32_t mask[LK_WINS + 4];
-    uint32_t ds[LK_WINS], lw[LK_WINS], dfirst[LK_WINS];
-    uint16_t list[LK_PCAP];
-    E2Long longs[E2_LONGCAP];
-    unsigned long long wsum64[E2_T / 32];
-    uint32_t wsum[E2_T / 32];
-    uint32_t n_pieces, n_longs, overflow;
+struct E3Long {
+    unsigned long long src, dst;
+    uint32_t count, pad;
 };
 
 // number of documents that start at batch byte position s, given the index of the first of them
@@ -961,242 +959,109 @@ __device__ __forceinline__ uint32_t docs_from(const uint64_t* __restrict__ doc_o
     return (uint32_t)(e - first);
 }
 
-// block-wide exclusive prefix of one 64-bit value per thread (E2_T threads); *total = sum over the block
-__device__ __forceinline__ unsigned long long e2_block_excl64(unsigned long long v, unsigned long long* wsum, unsigned long long* total) {
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    unsigned long long inc = v;
+__global__ void __launch_bounds__(E3_T) emit_kernel(const uint32_t* __restrict__ stream, const uint32_t* __restrict__ ds_mask,
+                                                    const uint32_t* __restrict__ doc_first, const uint32_t* __restrict__ long_of_word,
+                                                    const TkkLongRec* __restrict__ recs, const uint32_t* __restrict__ pool,
+                                                    const uint64_t* __restrict__ doc_off, uint64_t off_base, uint64_t n_docs,
+                                                    uint32_t add_bos, uint32_t add_eos, uint32_t nsp, uint32_t bos_id, uint32_t eos_id,
+                                                    uint32_t* __restrict__ out, uint64_t out_cap, uint64_t* __restrict__ tok_off,
+                                                    const unsigned long long* __restrict__ tile_base) {
+    static_assert(E3_T * E3_PER == LK_TILE, "one emit block per lookup tile");
+    __shared__ unsigned long long wsum[E3_T / 32];
+    __shared__ E3Long longs[E3_LONGCAP];
+    __shared__ uint32_t n_longs;
+    const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    const uint32_t tile = blockIdx.x;
+    if (t == 0) n_longs = 0;
+    const uint64_t p0 = (uint64_t)tile * LK_TILE + (uint64_t)t * E3_PER;        // my first byte position
+    // ---- my 16 stream words ----
+    uint32_t w[E3_PER];
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(stream + p0);
+#pragma unroll
+        for (int k = 0; k < E3_PER / 4; ++k) {
+            const uint4 v = __ldg(src + k);
+            w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+        }
+    }
+    const uint32_t myds = (ds_mask[p0 >> 5] >> (p0 & 31u)) & 0xFFFFu;          // document starts among my positions
+    uint32_t valid = 0, longm = 0;
+#pragma unroll
+    for (int k = 0; k < E3_PER; ++k) {
+        valid |= (w[k] < EN_LONGREF ? 1u : 0u) << k;
+        longm |= (w[k] == EN_LONGREF ? 1u : 0u) << k;
+    }
+    // ---- tokens that start at my positions ----
+    unsigned long long count = (unsigned long long)__popc(valid);
+    TkkLongRec lr;
+    lr.count = 0; lr.tok_base = 0;
+    if (longm) {                                   // at most one: a long piece has more than 64 bytes
+        lr = recs[long_of_word[p0 >> 5] - 1];
+        count += lr.count;
+    }
+    uint64_t d_first = 0;
+    if (myds) {
+        d_first = doc_first[p0 >> 5];
+        uint32_t earlier = ds_mask[p0 >> 5] & ((1u << (p0 & 31u)) - 1u);       // document starts earlier in the same window
+        while (earlier) {
+            const uint32_t b = (uint32_t)(__ffs((int)earlier) - 1);
+            earlier &= earlier - 1;
+            d_first += docs_from(doc_off, n_docs, (p0 & ~31ull) + b + off_base, d_first);
+        }
+        uint64_t d = d_first;
+        uint32_t m = myds;
+        while (m) {
+            const uint32_t b = (uint32_t)(__ffs((int)m) - 1);
+            m &= m - 1;
+            const uint32_t k = docs_from(doc_off, n_docs, p0 + b + off_base, d);
+            for (uint64_t x = d; x < d + k; ++x) count += (x > 0 ? add_eos : 0u) + (x < n_docs ? add_bos : 0u);
+            d += k;
+        }
+    }
+    // ---- block scan ----
+    unsigned long long inc = count;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         unsigned long long o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
         if (lane >= (uint32_t)d) inc += o;
     }
-    __syncthreads();          // wsum may still be read from the previous round
     if (lane == 31) wsum[warp] = inc;
     __syncthreads();
-    unsigned long long before = 0, all = 0;
+    unsigned long long o = tile_base[tile] + inc - count;
+    for (uint32_t x = 0; x < warp; ++x) o += wsum[x];
+    // ---- write ----
+    if (!myds && !longm) {
 #pragma unroll
-    for (int w = 0; w < E2_T / 32; ++w) { if (w < (int)warp) before += wsum[w]; all += wsum[w]; }
-    *total = all;
-    return before + inc - v;
-}
-
-struct TkkSlowTile {
-    unsigned long long base;
-    uint32_t tile, pad;
-};
-
-__global__ void __launch_bounds__(E2_T) emit_kernel(uint64_t n, const uint32_t* __restrict__ start_mask,
-                                                    const uint32_t* __restrict__ ds_mask, const uint32_t* __restrict__ doc_first,
-                                                    const uint32_t* __restrict__ long_of_word,
-                                                    const TkkLongRec* __restrict__ recs, const uint32_t* __restrict__ pool,
-                                                    const uint32_t* __restrict__ stream,
-                                                    const uint64_t* __restrict__ doc_off, uint64_t off_base, uint64_t n_docs, uint32_t add_bos,
-                                                    uint32_t add_eos, uint32_t nsp, uint32_t bos_id, uint32_t eos_id,
-                                                    uint32_t* __restrict__ out, uint64_t out_cap, uint64_t* __restrict__ tok_off,
-                                                    const unsigned long long* __restrict__ tile_base,
-                                                    TkkSlowTile* __restrict__ slow_list, uint32_t* __restrict__ slow_n) {
-    __shared__ __align__(16) E2Smem S;
-    const uint32_t t = threadIdx.x;
-    if (t == 0) { S.n_longs = 0; S.overflow = 0; }
-    const uint32_t tile = blockIdx.x;
-    const unsigned long long base = tile_base[tile];     // first output position of this tile's tokens (K3s)
-    const uint64_t tile_pos = (uint64_t)tile * LK_TILE;
-    const uint64_t win0 = (uint64_t)tile * LK_WINS;
-    // ---- masks of the tile; list of the piece starts ----
-    {
-        uint32_t m = 0;
-        if (t < LK_WINS + 4) { m = start_mask[win0 + t]; S.mask[t] = m; }
-        if (t < LK_WINS) {
-            const uint32_t d = ds_mask[win0 + t];
-            S.ds[t] = d;
-            S.lw[t] = m ? long_of_word[win0 + t] : 0u;
-            S.dfirst[t] = d ? doc_first[win0 + t] : 0u;
-        } else m = 0;
-        uint32_t np;
-        uint32_t o = lk_block_excl((uint32_t)__popc(m), S.wsum, &np);
-        if (t == 0) S.n_pieces = np;
-        while (m) {
-            S.list[o++] = (uint16_t)(t * 32u + (uint32_t)(__ffs((int)m) - 1));
-            m &= m - 1;
-        }
-    }
-    __syncthreads();
-    const uint32_t np = S.n_pieces;
-    uint32_t run_comp = 0;                 // staged tokens so far (short pieces + specials)
-    unsigned long long run_all = 0;        // all tokens so far (long pieces included)
-    // E2_PER consecutive pieces per lane and round: their stream loads are in flight together and
-    // one block scan serves E2_T * E2_PER pieces (a 4 KiB tile is usually a single round)
-    for (uint32_t k0 = 0; k0 < np; k0 += E2_T * E2_PER) {
-        uint32_t spec[E2_PER], cnt[E2_PER], v0[E2_PER], kdocs[E2_PER], d0[E2_PER], pos[E2_PER], lrec[E2_PER];
-        bool is_long[E2_PER];
+        for (int k = 0; k < E3_PER; ++k)
+            if ((valid >> k) & 1u) { if (o < out_cap) out[o] = w[k] + nsp; ++o; }
+    } else {
+        uint64_t d = d_first;
 #pragma unroll
-        for (int j = 0; j < E2_PER; ++j) {
-            const uint32_t k = k0 + t * E2_PER + j;
-            spec[j] = cnt[j] = v0[j] = kdocs[j] = d0[j] = lrec[j] = 0;
-            pos[j] = 0xFFFFFFFFu;          // not a piece (past the list, or the end-of-data sentinel)
-            is_long[j] = false;
-            if (k < np) {
-                const uint32_t s = S.list[k];
-                const uint32_t w = s >> 5, bit = s & 31u;
-                if (tile_pos + s < n) {
-                    pos[j] = s;
-                    const uint32_t lwi = S.lw[w];
-                    is_long[j] = lwi != 0u && bit == 31u - (uint32_t)__clz((int)S.mask[w]);
-                    if (is_long[j]) lrec[j] = lwi - 1u;
-                    else v0[j] = __ldg(stream + tile_pos + s);
+        for (int k = 0; k < E3_PER; ++k) {
+            if ((myds >> k) & 1u) {
+                const uint32_t nd = docs_from(doc_off, n_docs, p0 + k + off_base, d);
+                for (uint64_t x = d; x < d + nd; ++x) {
+                    if (x > 0 && add_eos) { if (o < out_cap) out[o] = eos_id; ++o; }
+                    tok_off[x] = o;
+                    if (x < n_docs && add_bos) { if (o < out_cap) out[o] = bos_id; ++o; }
                 }
-                if ((S.ds[w] >> bit) & 1u) {
-                    uint64_t d = S.dfirst[w];
-                    uint32_t earlier = S.ds[w] & ((1u << bit) - 1u);      // document starts earlier in the same window
-                    while (earlier) {
-                        const uint32_t b2 = (uint32_t)(__ffs((int)earlier) - 1);
-                        earlier &= earlier - 1;
-                        d += docs_from(doc_off, n_docs, tile_pos + w * 32u + b2 + off_base, d);
-                    }
-                    d0[j] = (uint32_t)d;
-                    kdocs[j] = docs_from(doc_off, n_docs, tile_pos + s + off_base, d);
-                    for (uint64_t x = d; x < d + kdocs[j]; ++x) spec[j] += (x > 0 ? add_eos : 0u) + (x < n_docs ? add_bos : 0u);
-                }
+                d += nd;
             }
-        }
-        // token counts, lane-local prefix
-        unsigned long long mine = 0;       // low 24 bits: staged tokens; above: all tokens
-        bool clamped = false;
-#pragma unroll
-        for (int j = 0; j < E2_PER; ++j) {
-            if (pos[j] != 0xFFFFFFFFu) cnt[j] = is_long[j] ? recs[lrec[j]].count : (v0[j] & EN_LAST) ? 1u : (v0[j] >> EN_COUNT_SHIFT) & 127u;
-            const uint32_t ct = spec[j] + (is_long[j] ? 0u : cnt[j]);
-            clamped |= ct > 0xFFFFu;
-            mine += (unsigned long long)(ct > 0xFFFFu ? 0xFFFFu : ct) | ((unsigned long long)spec[j] + cnt[j]) << 24;
-        }
-        unsigned long long total;
-        const unsigned long long excl = e2_block_excl64(mine, S.wsum64, &total);
-        uint32_t oc = run_comp + (uint32_t)(excl & 0xFFFFFFu);
-        unsigned long long oa = run_all + (excl >> 24);
-        run_comp += (uint32_t)(total & 0xFFFFFFu);
-        run_all += total >> 24;
-        const bool fits_here = !clamped && oc + (uint32_t)(mine & 0xFFFFFFu) <= E2_COMP;
-        if (!fits_here && mine) S.overflow = 1;
-#pragma unroll
-        for (int j = 0; j < E2_PER; ++j) {
-            if (kdocs[j]) {
-                for (uint64_t d = d0[j]; d < (uint64_t)d0[j] + kdocs[j]; ++d) {
-                    if (d > 0 && add_eos) { if (fits_here) S.comp[oc] = eos_id; ++oc; ++oa; }
-                    tok_off[d] = base + oa;
-                    if (d < n_docs && add_bos) { if (fits_here) S.comp[oc] = bos_id; ++oc; ++oa; }
-                }
-            }
-            if (pos[j] == 0xFFFFFFFFu) continue;
-            if (is_long[j]) {
-                const uint32_t li = atomicAdd(&S.n_longs, 1u);
-                E2Long L;
-                L.src = recs[lrec[j]].tok_base; L.dst_local = oa; L.count = cnt[j]; L.comp_pos = oc;
-                S.longs[li] = L;
-                oa += cnt[j];
-            } else {
-                if (fits_here) {
-                    S.comp[oc] = (v0[j] & EN_ID_MASK) + nsp;
-                    const uint32_t* src = stream + tile_pos + pos[j];
-                    for (uint32_t i = 1; i < cnt[j]; ++i) S.comp[oc + i] = (__ldg(src + i) & EN_ID_MASK) + nsp;
-                }
-                oc += cnt[j];
-                oa += cnt[j];
+            if ((valid >> k) & 1u) { if (o < out_cap) out[o] = w[k] + nsp; ++o; }
+            else if ((longm >> k) & 1u) {
+                E3Long L;
+                L.src = lr.tok_base; L.dst = o; L.count = lr.count; L.pad = 0;
+                longs[atomicAdd(&n_longs, 1u)] = L;
+                o += lr.count;
             }
         }
     }
     __syncthreads();
-    if (S.overflow) {
-        if (t == 0) {
-            TkkSlowTile e;
-            e.base = base; e.tile = tile; e.pad = 0;
-            slow_list[atomicAdd(slow_n, 1u)] = e;
-        }
-        return;
-    }
-    // staged ids -> output; ids after a long piece shift by its length
-    const uint32_t nl = S.n_longs;
-    for (uint32_t i = t; i < run_comp; i += E2_T) {
-        unsigned long long o = base + i;
-        for (uint32_t l = 0; l < nl; ++l) o += S.longs[l].comp_pos <= i ? S.longs[l].count : 0u;
-        if (o < out_cap) out[o] = S.comp[i];
-    }
+    const uint32_t nl = n_longs;
     for (uint32_t l = 0; l < nl; ++l) {
-        const E2Long L = S.longs[l];
-        for (uint32_t i = t; i < L.count; i += E2_T)
-            if (base + L.dst_local + i < out_cap) out[base + L.dst_local + i] = pool[L.src + i] + nsp;
-    }
-}
-
-// Tiles emit_kernel could not stage (listed with their base): one thread per window walks its pieces
-// twice (count, then write straight to the output).
-__global__ void __launch_bounds__(LK_WINS) emit_slow_kernel(uint64_t n, const uint32_t* __restrict__ start_mask,
-                                                            const uint32_t* __restrict__ ds_mask, const uint32_t* __restrict__ doc_first,
-                                                            const uint32_t* __restrict__ long_of_word,
-                                                            const TkkLongRec* __restrict__ recs, const uint32_t* __restrict__ pool,
-                                                            const uint32_t* __restrict__ stream,
-                                                            const uint64_t* __restrict__ doc_off, uint64_t off_base, uint64_t n_docs,
-                                                            uint32_t add_bos, uint32_t add_eos, uint32_t nsp, uint32_t bos_id, uint32_t eos_id,
-                                                            uint32_t* __restrict__ out, uint64_t out_cap, uint64_t* __restrict__ tok_off,
-                                                            const TkkSlowTile* __restrict__ slow_list, const uint32_t* __restrict__ slow_n) {
-    __shared__ unsigned long long wsum[LK_WINS / 32];
-    const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
-    const uint32_t total = *slow_n;
-    for (uint32_t e = blockIdx.x; e < total; e += gridDim.x) {
-        const TkkSlowTile st = slow_list[e];
-        const uint64_t gw = (uint64_t)st.tile * LK_WINS + t;
-        const uint64_t wpos = gw * 32u;
-        const uint32_t mymask = start_mask[gw], myds = ds_mask[gw];
-        const uint32_t lw = mymask ? long_of_word[gw] : 0u;
-        const uint32_t topbit = mymask ? 31u - (uint32_t)__clz((int)mymask) : 32u;
-        const uint64_t mydoc = myds ? doc_first[gw] : 0;
-        unsigned long long o = 0;
-        for (int pass = 0; pass < 2; ++pass) {
-            uint64_t d0 = mydoc;
-            uint32_t m = mymask;
-            while (m) {
-                const uint32_t bit = (uint32_t)(__ffs((int)m) - 1);
-                m &= m - 1;
-                const uint64_t gpos = wpos + bit;
-                if ((myds >> bit) & 1u) {
-                    const uint32_t k = docs_from(doc_off, n_docs, gpos + off_base, d0);
-                    for (uint64_t d = d0; d < d0 + k; ++d) {
-                        if (d > 0 && add_eos) { if (pass && o < out_cap) out[o] = eos_id; ++o; }
-                        if (pass) tok_off[d] = o;
-                        if (d < n_docs && add_bos) { if (pass && o < out_cap) out[o] = bos_id; ++o; }
-                    }
-                    d0 += k;
-                }
-                if (gpos >= n) continue;
-                if (lw && bit == topbit) {
-                    const TkkLongRec r = recs[lw - 1];
-                    if (pass) for (uint32_t j = 0; j < r.count; ++j) if (o + j < out_cap) out[o + j] = pool[r.tok_base + j] + nsp;
-                    o += r.count;
-                    continue;
-                }
-                for (uint32_t j = 0;; ++j) {
-                    const uint32_t v = __ldg(stream + gpos + j);
-                    if (pass && o < out_cap) out[o] = (v & EN_ID_MASK) + nsp;
-                    ++o;
-                    if (v & EN_LAST) break;
-                }
-            }
-            if (pass == 0) {
-                // exclusive prefix of the window totals -> where my window starts
-                unsigned long long inc = o;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    unsigned long long x = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-                    if (lane >= (uint32_t)d) inc += x;
-                }
-                __syncthreads();
-                if (lane == 31) wsum[warp] = inc;
-                __syncthreads();
-                unsigned long long before = 0;
-                for (uint32_t w = 0; w < warp; ++w) before += wsum[w];
-                o = st.base + before + inc - o;
-            }
-        }
-        __syncthreads();
+        const E3Long L = longs[l];
+        for (uint32_t i = t; i < L.count; i += E3_T)
+            if (L.dst + i < out_cap) out[L.dst + i] = pool[L.src + i] + nsp;
     }
 }
 
@@ -1226,8 +1091,7 @@ size_t encode_workspace_bytes(uint64_t n, uint64_t n_docs, EncodeLayout* L) {
     l.off_tilecount = take((l.n_ltiles + 1) * 8);
     l.off_tilebase = take((l.n_ltiles + 1) * 8);
     l.off_bsum = take((ceil_div(l.n_ltiles, TS_BLOCK) + 1) * 8);
-    l.off_slow = take((l.n_ltiles + 1) * sizeof(TkkSlowTile));
-    l.off_stream = take((n + TK_LANE_MAX + 64) * 4);
+    l.off_stream = take((l.n_ltiles * (size_t)LK_TILE + TK_LANE_MAX + 64) * 4);
     {
         // a queue per length class; a class whose shortest piece has m bytes holds at most n/m + 1 pieces
         const uint32_t shortest[TKK_N_CLASSES] = {2, 5, 9, 17, 33};
@@ -1295,7 +1159,6 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
     TkkLongRec* recs = (TkkLongRec*)(ws + L.off_recs);
     uint32_t* huge = (uint32_t*)(ws + L.off_huge);
     uint32_t* pool = (uint32_t*)(ws + L.off_pool);
-    TkkSlowTile* slow_list = (TkkSlowTile*)(ws + L.off_slow);
     uint32_t* stream = (uint32_t*)(ws + L.off_stream);
     unsigned long long* queues = (unsigned long long*)(ws + L.off_queues);
     // small block layout
@@ -1308,7 +1171,6 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
     uint32_t* wc_huge = small + TKK_S_WC_HUGE;
     uint32_t* q_n = small + TKK_S_QN;
     uint32_t* q_w = small + TKK_S_QW;
-    uint32_t* slow_n = small + TKK_S_SLOWN;
     unsigned long long* pool_cursor = (unsigned long long*)(small + TKK_S_POOLCUR);
     unsigned long long* scratch_cursor = (unsigned long long*)(small + TKK_S_SCRCUR);
     unsigned long long* total_out = (unsigned long long*)(small + TKK_S_TOTAL);
@@ -1382,13 +1244,9 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
         tileapply_kernel<<<nb, TS_T, 0, st>>>(tile_count, (uint32_t)L.n_ltiles, bsum, tile_base);
         TK_LAUNCHED();
     }
-    emit_kernel<<<(unsigned)L.n_ltiles, E2_T, 0, st>>>(n, start, ds, docfirst, longword, recs, pool, stream, d_doc_off, off_base, n_docs,
+    emit_kernel<<<(unsigned)L.n_ltiles, E3_T, 0, st>>>(stream, ds, docfirst, longword, recs, pool, d_doc_off, off_base, n_docs,
                                                       add_bos ? 1u : 0u, add_eos ? 1u : 0u, T.num_special, T.bos_id, T.eos_id, d_out,
-                                                      out_cap, d_tok_off, tile_base, slow_list, slow_n);
-    TK_LAUNCHED();
-    emit_slow_kernel<<<(unsigned)(2 * sm_count), LK_WINS, 0, st>>>(n, start, ds, docfirst, longword, recs, pool, stream, d_doc_off, off_base,
-                                                                  n_docs, add_bos ? 1u : 0u, add_eos ? 1u : 0u, T.num_special, T.bos_id,
-                                                                  T.eos_id, d_out, out_cap, d_tok_off, slow_list, slow_n);
+                                                      out_cap, d_tok_off, tile_base);
     TK_LAUNCHED();
     if (timer) timer->mark(st, "end");
     return cudaGetLastError();

@@ -34,7 +34,6 @@ enum {
     TKK_S_BADDOC = 16,   // u64 (decode)
     TKK_S_QN = 20,       // TKK_N_CLASSES counters: queued pieces per length class
     TKK_S_QW = 26,       // TKK_N_CLASSES work counters
-    TKK_S_SLOWN = 32,    // tiles left to emit_slow_kernel
 };
 
 #define TKK_N_CLASSES 5
@@ -60,7 +59,7 @@ struct EncodeLayout {
     uint64_t n_windows, n_tiles, n_ltiles, mask_words, max_long;
     TkkQueueLayout queues;
     size_t off_small, off_ds, off_start, off_longword, off_docfirst, off_summ, off_carry, off_worklist, off_seg, off_tilecount, off_tilebase, off_bsum, off_recs,
-        off_huge, off_pool, off_slow, off_stream, off_queues, total;
+        off_huge, off_pool, off_stream, off_queues, total;
 };
 
 struct DecodeLayout {
