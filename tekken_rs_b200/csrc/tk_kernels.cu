@@ -59,7 +59,8 @@ StageTimer::~StageTimer() { reset(); }
 // =====================================================================================================
 __global__ void docmark_kernel(const uint64_t* __restrict__ doc_off, uint64_t off_base, uint64_t n_docs, uint64_t total,
                                uint32_t add_bos, uint32_t add_eos, uint32_t* __restrict__ ds_mask, uint32_t* __restrict__ doc_first,
-                               unsigned long long* __restrict__ tile_count, uint32_t* __restrict__ flags) {
+                               uint32_t* __restrict__ doc_cnt, unsigned long long* __restrict__ tile_count,
+                               uint32_t* __restrict__ flags) {
     uint64_t d = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (d > n_docs) return;
     uint64_t o = doc_off[d] - off_base;      // offsets may be a slice of a larger batch (off_base = its first entry)
@@ -70,6 +71,7 @@ __global__ void docmark_kernel(const uint64_t* __restrict__ doc_off, uint64_t of
     if (!ok) { atomicOr(flags, TKK_FLAG_BAD_OFFSETS); return; }
     atomicOr(ds_mask + (o >> 5), 1u << (o & 31));
     atomicMin(doc_first + (o >> 5), (uint32_t)d);     // first document that starts in this 32-byte window
+    atomicAdd(doc_cnt + (o >> 5), 1u);                // ... and how many do
     // the EOS of the document before and the BOS of this one count towards the tile this document starts in
     const unsigned long long sp = (d > 0 ? add_eos : 0u) + (d < n_docs ? add_bos : 0u);
     if (sp) atomicAdd(tile_count + o / TKK_COUNT_TILE, sp);
@@ -952,6 +954,13 @@ struct E3Long {
     uint32_t count, pad;
 };
 
+// BOS/EOS tokens emitted at the start position of documents d .. d+k-1 (the EOS of the document before
+// each, the BOS of each; document n_docs is the virtual end document)
+__device__ __forceinline__ uint32_t e3_specials(uint64_t d, uint32_t k, uint64_t n_docs, uint32_t add_bos, uint32_t add_eos) {
+    const uint32_t n_eos = k - (d == 0 ? 1u : 0u), n_bos = k - (d + k - 1 == n_docs ? 1u : 0u);
+    return (add_eos ? n_eos : 0u) + (add_bos ? n_bos : 0u);
+}
+
 // number of documents that start at batch byte position s, given the index of the first of them
 __device__ __forceinline__ uint32_t docs_from(const uint64_t* __restrict__ doc_off, uint64_t n_docs, uint64_t s, uint64_t first) {
     uint64_t e = first + 1;
@@ -959,8 +968,9 @@ __device__ __forceinline__ uint32_t docs_from(const uint64_t* __restrict__ doc_o
     return (uint32_t)(e - first);
 }
 
-__global__ void __launch_bounds__(E3_T) emit_kernel(const uint32_t* __restrict__ stream, const uint32_t* __restrict__ ds_mask,
-                                                    const uint32_t* __restrict__ doc_first, const uint32_t* __restrict__ long_of_word,
+__global__ void __launch_bounds__(E3_T, 6) emit_kernel(const uint32_t* __restrict__ stream, const uint32_t* __restrict__ ds_mask,
+                                                    const uint32_t* __restrict__ doc_first, const uint32_t* __restrict__ doc_cnt,
+                                                    const uint32_t* __restrict__ long_of_word,
                                                     const TkkLongRec* __restrict__ recs, const uint32_t* __restrict__ pool,
                                                     const uint64_t* __restrict__ doc_off, uint64_t off_base, uint64_t n_docs,
                                                     uint32_t add_bos, uint32_t add_eos, uint32_t nsp, uint32_t bos_id, uint32_t eos_id,
@@ -999,23 +1009,33 @@ __global__ void __launch_bounds__(E3_T) emit_kernel(const uint32_t* __restrict__
         lr = recs[long_of_word[p0 >> 5] - 1];
         count += lr.count;
     }
+    // Documents that start at my positions.  Usual case: one start position in the 32-byte window;
+    // then the window's document count (K0) says how many documents start there and no offset has to
+    // be read.  Several start positions in one window (documents shorter than 32 bytes): read offsets.
     uint64_t d_first = 0;
+    uint32_t nd_single = 0;                        // != 0: all nd_single documents of the window start at my one position
     if (myds) {
+        const uint32_t wds = ds_mask[p0 >> 5];
         d_first = doc_first[p0 >> 5];
-        uint32_t earlier = ds_mask[p0 >> 5] & ((1u << (p0 & 31u)) - 1u);       // document starts earlier in the same window
-        while (earlier) {
-            const uint32_t b = (uint32_t)(__ffs((int)earlier) - 1);
-            earlier &= earlier - 1;
-            d_first += docs_from(doc_off, n_docs, (p0 & ~31ull) + b + off_base, d_first);
-        }
-        uint64_t d = d_first;
-        uint32_t m = myds;
-        while (m) {
-            const uint32_t b = (uint32_t)(__ffs((int)m) - 1);
-            m &= m - 1;
-            const uint32_t k = docs_from(doc_off, n_docs, p0 + b + off_base, d);
-            for (uint64_t x = d; x < d + k; ++x) count += (x > 0 ? add_eos : 0u) + (x < n_docs ? add_bos : 0u);
-            d += k;
+        if ((wds & (wds - 1u)) == 0u) {
+            nd_single = doc_cnt[p0 >> 5];
+            count += e3_specials(d_first, nd_single, n_docs, add_bos, add_eos);
+        } else {
+            uint32_t earlier = wds & ((1u << (p0 & 31u)) - 1u);                 // document starts earlier in the same window
+            while (earlier) {
+                const uint32_t b = (uint32_t)(__ffs((int)earlier) - 1);
+                earlier &= earlier - 1;
+                d_first += docs_from(doc_off, n_docs, (p0 & ~31ull) + b + off_base, d_first);
+            }
+            uint64_t d = d_first;
+            uint32_t m = myds;
+            while (m) {
+                const uint32_t b = (uint32_t)(__ffs((int)m) - 1);
+                m &= m - 1;
+                const uint32_t k = docs_from(doc_off, n_docs, p0 + b + off_base, d);
+                count += e3_specials(d, k, n_docs, add_bos, add_eos);
+                d += k;
+            }
         }
     }
     // ---- block scan ----
@@ -1039,7 +1059,7 @@ __global__ void __launch_bounds__(E3_T) emit_kernel(const uint32_t* __restrict__
 #pragma unroll
         for (int k = 0; k < E3_PER; ++k) {
             if ((myds >> k) & 1u) {
-                const uint32_t nd = docs_from(doc_off, n_docs, p0 + k + off_base, d);
+                const uint32_t nd = nd_single ? nd_single : docs_from(doc_off, n_docs, p0 + k + off_base, d);
                 for (uint64_t x = d; x < d + nd; ++x) {
                     if (x > 0 && add_eos) { if (o < out_cap) out[o] = eos_id; ++o; }
                     tok_off[x] = o;
@@ -1083,6 +1103,7 @@ size_t encode_workspace_bytes(uint64_t n, uint64_t n_docs, EncodeLayout* L) {
     l.off_start = take(words * 4);
     l.off_longword = take(words * 4);
     l.off_docfirst = take(words * 4);
+    l.off_doccnt = take(words * 4);
     l.off_summ = take(n_tiles * sizeof(TkkTileSummary));
     l.off_carry = take(n_tiles * 4);
     l.off_worklist = take(n_tiles * 4);
@@ -1150,6 +1171,7 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
     uint32_t* start = (uint32_t*)(ws + L.off_start);
     uint32_t* longword = (uint32_t*)(ws + L.off_longword);
     uint32_t* docfirst = (uint32_t*)(ws + L.off_docfirst);
+    uint32_t* doccnt = (uint32_t*)(ws + L.off_doccnt);
     TkkTileSummary* summ = (TkkTileSummary*)(ws + L.off_summ);
     uint32_t* carry = (uint32_t*)(ws + L.off_carry);
     uint32_t* worklist = (uint32_t*)(ws + L.off_worklist);
@@ -1180,9 +1202,10 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
     CK(cudaMemsetAsync(err_pos, 0xFF, 8, st));
     CK(cudaMemsetAsync(ds, 0, L.mask_words * 4, st));
     CK(cudaMemsetAsync(docfirst, 0xFF, L.mask_words * 4, st));
+    CK(cudaMemsetAsync(doccnt, 0, L.mask_words * 4, st));
     CK(cudaMemsetAsync(start + L.n_windows, 0, (L.mask_words - L.n_windows) * 4, st));
     CK(cudaMemsetAsync(tile_count, 0, (L.n_ltiles + 1) * 8, st));
-    docmark_kernel<<<(unsigned)ceil_div(n_docs + 1, 256), 256, 0, st>>>(d_doc_off, off_base, n_docs, n, add_bos ? 1u : 0u, add_eos ? 1u : 0u, ds, docfirst, tile_count, flags);
+    docmark_kernel<<<(unsigned)ceil_div(n_docs + 1, 256), 256, 0, st>>>(d_doc_off, off_base, n_docs, n, add_bos ? 1u : 0u, add_eos ? 1u : 0u, ds, docfirst, doccnt, tile_count, flags);
     TK_LAUNCHED();
     if (timer) timer->mark(st, "pretok");
     pretok_kernel<<<(unsigned)L.n_tiles, PT_T, 0, st>>>(d_data, n, ds, start, L.n_windows, T, summ, err_pos);
@@ -1244,7 +1267,7 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
         tileapply_kernel<<<nb, TS_T, 0, st>>>(tile_count, (uint32_t)L.n_ltiles, bsum, tile_base);
         TK_LAUNCHED();
     }
-    emit_kernel<<<(unsigned)L.n_ltiles, E3_T, 0, st>>>(stream, ds, docfirst, longword, recs, pool, d_doc_off, off_base, n_docs,
+    emit_kernel<<<(unsigned)L.n_ltiles, E3_T, 0, st>>>(stream, ds, docfirst, doccnt, longword, recs, pool, d_doc_off, off_base, n_docs,
                                                       add_bos ? 1u : 0u, add_eos ? 1u : 0u, T.num_special, T.bos_id, T.eos_id, d_out,
                                                       out_cap, d_tok_off, tile_base);
     TK_LAUNCHED();

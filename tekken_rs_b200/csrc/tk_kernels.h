@@ -58,7 +58,7 @@ struct TkkLongRec {
 struct EncodeLayout {
     uint64_t n_windows, n_tiles, n_ltiles, mask_words, max_long;
     TkkQueueLayout queues;
-    size_t off_small, off_ds, off_start, off_longword, off_docfirst, off_summ, off_carry, off_worklist, off_seg, off_tilecount, off_tilebase, off_bsum, off_recs,
+    size_t off_small, off_ds, off_start, off_longword, off_docfirst, off_doccnt, off_summ, off_carry, off_worklist, off_seg, off_tilecount, off_tilebase, off_bsum, off_recs,
         off_huge, off_pool, off_stream, off_queues, total;
 };
 
