@@ -461,8 +461,12 @@ static int encode_finish(tk_tokenizer* t, tk_tokenizer::EncSlot& s, cudaStream_t
     if (err_pos != ~0ull)
         return fail(TK_ERR_INVALID_UTF8, "input is not valid UTF-8 at byte %llu", (unsigned long long)(err_pos + byte_base));
     if (flags & tkk::TKK_FLAG_SCRATCH_FULL) {
-        // a piece longer than TK_MED_MAX bytes needs 12 bytes of scratch per byte: grow and rerun
-        CUDA_OR_FAIL(s.scratch.ensure((size_t)total * 12 + 4096));
+        // pieces longer than TK_MED_MAX bytes are merged in global scratch; the kernel's cursor says how many
+        // 32-bit words this batch needs: grow and rerun
+        uint64_t need_words;
+        memcpy(&need_words, small + tkk::TKK_S_SCRCUR, 8);
+        (void)total;
+        CUDA_OR_FAIL(s.scratch.ensure((size_t)need_words * 4 + 4096));
         *retry = true;
         return TK_OK;
     }

@@ -506,9 +506,30 @@ __global__ void __launch_bounds__(LM_WARPS * 32) longmerge_warp_kernel(const uin
     }
 }
 
-// Block per huge piece: the same sequential merge loop, parts in global scratch (L2 resident),
-// every thread caching the minimum of its slice.
+// Block per huge piece (> TK_MED_MAX bytes): the same result as the sequential merge loop, computed in
+// ROUNDS ("rank-rounds with hazard cut").  A round takes the lowest pair rank m of the
+// piece, selects the rank-m pairs left to right without overlaps, and computes for every selected pair
+// the ranks of the two pairs its merge creates, exactly as the sequential order would see them (left
+// neighbour already merged if it was selected, right neighbour not yet).  If one of those new ranks is
+// <= m the sequential loop would turn to that pair next: the round applies the selected merges up to and
+// including the leftmost such pair and drops the rest.  Parts and pair ranks live in compact arrays in
+// global scratch (L2-resident for pieces of tens of KiB) and are rebuilt each round with a block scan.
+// A run of thousands of spaces takes a handful of rounds instead of thousands of dependent steps.
 #define HG_T 512
+#define HG_ARRAYS 6                 // id / rank, double-buffered, + the two new-rank arrays of a round
+#define HG_UNSEL 0xFFFFFFFEu        // rL marker: pair not selected this round
+
+__device__ __forceinline__ uint32_t hg_block_min(uint32_t v, uint32_t* s_tmp) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    v = __reduce_min_sync(0xFFFFFFFFu, v);
+    __syncthreads();
+    if (lane == 0) s_tmp[warp] = v;
+    __syncthreads();
+    uint32_t r = s_tmp[lane < HG_T / 32 ? lane : 0];
+    r = __reduce_min_sync(0xFFFFFFFFu, r);
+    return r;
+}
+
 __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __restrict__ data, TkDeviceTables T,
                                                                TkkLongRec* __restrict__ recs, const uint32_t* __restrict__ huge_list,
                                                                const uint32_t* __restrict__ n_huge, uint32_t* __restrict__ pool,
@@ -516,11 +537,13 @@ __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __
                                                                unsigned long long* __restrict__ scratch_cursor,
                                                                uint32_t* __restrict__ work_counter, uint32_t* __restrict__ flags,
                                                                unsigned long long* __restrict__ tile_count) {
+    __shared__ uint32_t s_tmp[HG_T / 32];
+    __shared__ uint32_t s_par[HG_T / 32];      // run-parity summaries of the warps
+    __shared__ uint32_t s_cnt[HG_T / 32];
     __shared__ unsigned long long s_key[HG_T / 32];
     __shared__ unsigned long long s_best;
     __shared__ uint32_t s_rec;
     __shared__ unsigned long long s_base;
-    __shared__ uint32_t s_count[HG_T / 32 + 1];
     const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
     const uint32_t total = *n_huge;
     for (;;) {
@@ -531,95 +554,193 @@ __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __
         const uint32_t r = huge_list[s_rec];
         const uint64_t pos = recs[r].start;
         const uint32_t n = (uint32_t)recs[r].len;   // pieces are < 4 GiB (checked by the host)
-        if (t == 0) {
-            s_base = atomicAdd(scratch_cursor, 3ull * n);
-        }
+        if (t == 0) s_base = atomicAdd(scratch_cursor, (unsigned long long)HG_ARRAYS * n);   // the cursor also tells the host how much is needed
         __syncthreads();
-        if (s_base + 3ull * n > scratch_cap) {
+        if (s_base + (unsigned long long)HG_ARRAYS * n > scratch_cap) {
             if (t == 0) atomicOr(flags, TKK_FLAG_SCRATCH_FULL);
             continue;
         }
-        uint32_t* id = pool + recs[r].tok_base;       // ids live where the final tokens go
+        uint32_t* out = pool + recs[r].tok_base;
         if (n <= T.max_token_len) {                    // whole-piece shortcut (only with giant vocab entries)
             __shared__ uint32_t s_whole;
             if (t == 0) s_whole = tk_vocab_lookup(T, data + pos, n);
             __syncthreads();
             if (s_whole != TK_INF) {
-                if (t == 0) { id[0] = s_whole; recs[r].count = 1; atomicAdd(tile_count + pos / TKK_COUNT_TILE, 1ull); }
+                if (t == 0) { out[0] = s_whole; recs[r].count = 1; atomicAdd(tile_count + pos / TKK_COUNT_TILE, 1ull); }
                 continue;
             }
         }
-        uint32_t* rk = scratch + s_base;
-        uint32_t* nx = rk + n;
-        uint32_t* pv = nx + n;
-        for (uint32_t i = t; i < n; i += HG_T) { id[i] = data[pos + i]; nx[i] = i + 1; pv[i] = i - 1; }
-        __syncthreads();
-        for (uint32_t i = t; i < n; i += HG_T) rk[i] = (i + 1 < n) ? tk_pair_rank(T, id[i], id[i + 1]) : TK_INF;
-        __syncthreads();
-        const uint32_t k = (n + HG_T - 1) / HG_T;
-        const uint32_t lo = (uint64_t)t * k < n ? t * k : n, hi = (uint64_t)(t + 1) * k < n ? (t + 1) * k : n;
-        unsigned long long mine = ~0ull;
-        for (uint32_t i = lo; i < hi; ++i) {
-            const uint32_t v = rk[i];
-            if (v != TK_INF) { unsigned long long key = (unsigned long long)v << 32 | i; mine = key < mine ? key : mine; }
+        uint32_t* id = scratch + s_base;
+        uint32_t* rk = id + n;
+        uint32_t* id2 = rk + n;
+        uint32_t* rk2 = id2 + n;
+        uint32_t* rL = rk2 + n;
+        uint32_t* rR = rL + n;
+        for (uint32_t i = t; i < n; i += HG_T) {
+            const uint32_t b0 = data[pos + i];
+            id[i] = b0;
+            rk[i] = i + 1 < n ? __ldg(T.byte_pair + ((b0 << 8) | data[pos + i + 1])) : TK_INF;
         }
+        __syncthreads();
+        uint32_t m = n;
+        bool sequential = false;
         for (;;) {
-            // block-wide minimum of (rank, position)
-            unsigned long long m = mine;
+            const uint32_t c = (m + HG_T - 1) / HG_T;
+            const uint32_t lo = (uint64_t)t * c < m ? t * c : m, hi = (uint64_t)lo + c < m ? lo + c : m;
+            // 1. lowest pair rank of the piece
+            uint32_t mine = TK_INF;
+            for (uint32_t i = lo; i < hi; ++i) mine = min(mine, rk[i]);
+            const uint32_t mn = hg_block_min(mine, s_tmp);
+            if (mn == TK_INF) break;
+            // 2. selection: in every maximal run of adjacent rank-mn pairs take the 1st, 3rd, ...  A chunk's
+            //    summary: all = every pair of the chunk has rank mn; par = parity of the run that ends the chunk
+            uint32_t all = 1, par = 0;
+            for (uint32_t i = lo; i < hi; ++i) { if (rk[i] == mn) par ^= 1u; else { par = 0; all = 0; } }
+            // exclusive scan of (all, par) over the threads: parity of the run that reaches my chunk
+            uint32_t a = all, p = par;
 #pragma unroll
-            for (int d = 16; d; d >>= 1) {
-                unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, m, d);
-                m = o < m ? o : m;
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t oa = __shfl_up_sync(0xFFFFFFFFu, a, d), op = __shfl_up_sync(0xFFFFFFFFu, p, d);
+                if (lane >= (uint32_t)d) { p = a ? (p ^ op) : p; a &= oa; }
             }
-            if (lane == 0) s_key[warp] = m;
+            if (lane == 31) s_par[warp] = a | (p << 1);
+            uint32_t ea = __shfl_up_sync(0xFFFFFFFFu, a, 1), ep = __shfl_up_sync(0xFFFFFFFFu, p, 1);   // exclusive within the warp
+            if (lane == 0) { ea = 1; ep = 0; }
             __syncthreads();
-            if (warp == 0) {
-                unsigned long long v = lane < HG_T / 32 ? s_key[lane] : ~0ull;
+            uint32_t wp = 0;                                   // parity of the run that reaches my warp
+            for (uint32_t w = 0; w < warp; ++w) { const uint32_t x = s_par[w]; wp = (x & 1u) ? (wp ^ (x >> 1)) : (x >> 1); }
+            uint32_t entry = ea ? (ep ^ wp) : ep;
+            for (uint32_t i = lo; i < hi; ++i) {
+                if (rk[i] == mn) { rL[i] = entry ? HG_UNSEL : TK_INF; entry ^= 1u; }   // TK_INF: selected, new rank filled in below
+                else { rL[i] = HG_UNSEL; entry = 0; }
+            }
+            __syncthreads();
+            // 3. the two pairs every selected merge creates, as the sequential order would see them
+            uint32_t hazard = TK_INF;
+            for (uint32_t i = lo; i < hi; ++i) {
+                if (rL[i] == HG_UNSEL) continue;
+                const uint32_t lf = i == 0 ? TK_INF : (i >= 2 && rL[i - 2] != HG_UNSEL) ? mn : id[i - 1];
+                const uint32_t rt = i + 2 < m ? id[i + 2] : TK_INF;
+                uint32_t x, y;
+                tk_pair_rank2(T, lf, mn, mn, rt, &x, &y);
+                rR[i] = y;
+                rL[i] = x == HG_UNSEL ? TK_INF : x;           // (ranks are < 2^21: never equal to the marker)
+                if (x <= mn || y <= mn) hazard = min(hazard, i);
+            }
+            // NOTE: rL[i - 2] of a neighbouring chunk may already hold its new rank instead of TK_INF; both mean "selected"
+            const uint32_t cut = hg_block_min(hazard, s_tmp);    // merges after the leftmost hazard wait for the next round
+            // 4. apply the merges at positions <= cut and rebuild the compact arrays
+            uint32_t napp = 0;
+            for (uint32_t i = lo; i < hi; ++i) napp += (rL[i] != HG_UNSEL && i <= cut) ? 1u : 0u;
+            uint32_t inc = napp;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                if (lane >= (uint32_t)d) inc += o;
+            }
+            if (lane == 31) s_cnt[warp] = inc;
+            __syncthreads();
+            uint32_t before = inc - napp, all_app = 0;
+            for (uint32_t w = 0; w < HG_T / 32; ++w) { if (w < warp) before += s_cnt[w]; all_app += s_cnt[w]; }
+            for (uint32_t j = lo; j < hi; ++j) {
+                const bool app = rL[j] != HG_UNSEL && j <= cut;
+                if (j > 0 && rL[j - 1] != HG_UNSEL && j - 1 <= cut) continue;      // right part of an applied merge: gone
+                const uint32_t q = j - before;
+                uint32_t nr;
+                if (app) {
+                    id2[q] = mn;
+                    if (j + 2 >= m) nr = TK_INF;
+                    else nr = (rL[j + 2] != HG_UNSEL && j + 2 <= cut) ? rL[j + 2] : rR[j];
+                    ++before;
+                } else {
+                    id2[q] = id[j];
+                    if (j + 1 >= m) nr = TK_INF;
+                    else nr = (rL[j + 1] != HG_UNSEL && j + 1 <= cut) ? rL[j + 1] : rk[j];
+                }
+                rk2[q] = nr;
+            }
+            m -= all_app;
+            { uint32_t* x = id; id = id2; id2 = x; x = rk; rk = rk2; rk2 = x; }
+            __syncthreads();
+            // A round costs a few passes over the m parts; a single merge of the sequential loop below costs a
+            // block-wide minimum.  Once a round applies only a handful of merges (text without repetition) the
+            // sequential loop is cheaper -- and pair ranks only get more distinct from here on.
+            if (m >= 16384u && all_app < (m >> 12)) { sequential = true; break; }
+        }
+        uint32_t outn = m;
+        if (sequential) {
+            // the sequential definition on the compact arrays: parts become a linked list (nx / pv), a merged-away
+            // part is marked TK_DEAD, every thread caches the minimum of its slice
+            uint32_t* nx = id2;
+            uint32_t* pv = rk2;
+            for (uint32_t i = t; i < m; i += HG_T) { nx[i] = i + 1; pv[i] = i - 1; }
+            __syncthreads();
+            const uint32_t k = (m + HG_T - 1) / HG_T;
+            const uint32_t lo = (uint64_t)t * k < m ? t * k : m, hi = (uint64_t)(t + 1) * k < m ? (t + 1) * k : m;
+            unsigned long long mine = ~0ull;
+            for (uint32_t i = lo; i < hi; ++i) {
+                const uint32_t v = rk[i];
+                if (v != TK_INF) { unsigned long long key = (unsigned long long)v << 32 | i; mine = key < mine ? key : mine; }
+            }
+            for (;;) {
+                // block-wide minimum of (rank, position)
+                unsigned long long mm = mine;
 #pragma unroll
                 for (int d = 16; d; d >>= 1) {
-                    unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, v, d);
-                    v = o < v ? o : v;
+                    unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, mm, d);
+                    mm = o < mm ? o : mm;
                 }
-                if (lane == 0) s_best = v;
-            }
-            __syncthreads();
-            const unsigned long long g = s_best;
-            if (g == ~0ull) break;
-            const uint32_t p0 = (uint32_t)g, rnk = (uint32_t)(g >> 32);
-            const uint32_t j = nx[p0], pp = pv[p0];
-            const uint32_t nn = nx[j];
-            __syncthreads();
-            if (t == 0) {
-                id[p0] = rnk; id[j] = TK_DEAD; rk[j] = TK_INF; nx[p0] = nn;
-                if (nn < n) pv[nn] = p0;
-                rk[p0] = nn < n ? tk_pair_rank(T, rnk, id[nn]) : TK_INF;
-            } else if (t == 32) {
-                if (pp != 0xFFFFFFFFu) rk[pp] = tk_pair_rank(T, id[pp], rnk);
-            }
-            __syncthreads();
-            const bool touched = (p0 >= lo && p0 < hi) || (j >= lo && j < hi) || (pp != 0xFFFFFFFFu && pp >= lo && pp < hi);
-            if (touched) {
-                mine = ~0ull;
-                for (uint32_t i = lo; i < hi; ++i) {
-                    const uint32_t v = rk[i];
-                    if (v != TK_INF) { unsigned long long key = (unsigned long long)v << 32 | i; mine = key < mine ? key : mine; }
+                if (lane == 0) s_key[warp] = mm;
+                __syncthreads();
+                if (warp == 0) {
+                    unsigned long long v = lane < HG_T / 32 ? s_key[lane] : ~0ull;
+#pragma unroll
+                    for (int d = 16; d; d >>= 1) {
+                        unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, v, d);
+                        v = o < v ? o : v;
+                    }
+                    if (lane == 0) s_best = v;
+                }
+                __syncthreads();
+                const unsigned long long g = s_best;
+                if (g == ~0ull) break;
+                const uint32_t p0 = (uint32_t)g, rnk = (uint32_t)(g >> 32);
+                const uint32_t j = nx[p0], pp = pv[p0];
+                const uint32_t nn = nx[j];
+                __syncthreads();
+                if (t == 0) {
+                    id[p0] = rnk; id[j] = TK_DEAD; rk[j] = TK_INF; nx[p0] = nn;
+                    if (nn < m) pv[nn] = p0;
+                    rk[p0] = nn < m ? tk_pair_rank(T, rnk, id[nn]) : TK_INF;
+                } else if (t == 32) {
+                    if (pp != 0xFFFFFFFFu) rk[pp] = tk_pair_rank(T, id[pp], rnk);
+                }
+                __syncthreads();
+                const bool touched = (p0 >= lo && p0 < hi) || (j >= lo && j < hi) || (pp != 0xFFFFFFFFu && pp >= lo && pp < hi);
+                if (touched) {
+                    mine = ~0ull;
+                    for (uint32_t i = lo; i < hi; ++i) {
+                        const uint32_t v = rk[i];
+                        if (v != TK_INF) { unsigned long long key = (unsigned long long)v << 32 | i; mine = key < mine ? key : mine; }
+                    }
                 }
             }
-        }
-        // in-place compaction of the surviving ids, chunk by chunk (a chunk is read completely
-        // before anything is written at or below it)
-        uint32_t outn = 0;
-        for (uint32_t basei = 0; basei < n; basei += HG_T) {
-            const uint32_t i = basei + t;
-            const uint32_t v = i < n ? id[i] : TK_DEAD;
-            const uint32_t alive = __ballot_sync(0xFFFFFFFFu, v != TK_DEAD);
-            if (lane == 0) s_count[warp] = __popc(alive);
-            __syncthreads();
-            uint32_t before = 0, all = 0;
-            for (uint32_t w = 0; w < HG_T / 32; ++w) { if (w < warp) before += s_count[w]; all += s_count[w]; }
-            if (v != TK_DEAD) id[outn + before + __popc(alive & ((1u << lane) - 1u))] = v;
-            outn += all;
-            __syncthreads();
+            // compaction of the surviving ids into the output
+            outn = 0;
+            for (uint32_t basei = 0; basei < m; basei += HG_T) {
+                const uint32_t i = basei + t;
+                const uint32_t v = i < m ? id[i] : TK_DEAD;
+                const uint32_t alive = __ballot_sync(0xFFFFFFFFu, v != TK_DEAD);
+                if (lane == 0) s_cnt[warp] = __popc(alive);
+                __syncthreads();
+                uint32_t before = 0, all = 0;
+                for (uint32_t w = 0; w < HG_T / 32; ++w) { if (w < warp) before += s_cnt[w]; all += s_cnt[w]; }
+                if (v != TK_DEAD) out[outn + before + __popc(alive & ((1u << lane) - 1u))] = v;
+                outn += all;
+                __syncthreads();
+            }
+        } else {
+            for (uint32_t i = t; i < m; i += HG_T) out[i] = id[i];
         }
         if (t == 0) { recs[r].count = outn; atomicAdd(tile_count + pos / TKK_COUNT_TILE, (unsigned long long)outn); }
     }
