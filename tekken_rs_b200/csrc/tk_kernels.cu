@@ -1,16 +1,20 @@
-// tk_kernels.cu -- sm_100a kernels of the encode / decode path and their launch sequences.
+// tk_kernels.cu -- sm_100a kernels of the encode path and their launch sequence.
 //
 // Encode (Tekkenizer::encode, src/tekkenizer.rs:378-405, batched) = the launch sequence in
-// tk_encode_device():
-//   K0 docmark      document-start bitmask from doc offsets
-//   K1 pretok       regex split -> piece-start bitmask (tk_pretok.h), one thread per 32 bytes
-//   K1s/K1f         carry digit/CR-LF/whitespace run state across thread blocks (rarely non-trivial)
-//   K2a longmark    find pieces longer than TK_SHORT_MAX bytes
-//   K3  longmerge   exact BPE for those (warp per piece in shared memory, block per huge piece)
-//   K2  encode      per 8 KiB tile: vocabulary lookup / thread-level BPE per piece, BOS/EOS,
-//                   decoupled look-back prefix over tiles, ids written straight to their final place
-// Decode (Tekkenizer::decode, src/tekkenizer.rs:436-560, batched): lengths, scan, byte gather,
-// per-run UTF-8 validation.
+// encode_device():
+//   K0  docmark      document-start bitmask, first document / document count per 32-byte window,
+//                    BOS/EOS counted per 4 KiB tile
+//   K1  pretok       regex split -> piece-start bitmask (tk_pretok.h), one thread per 32 bytes
+//   K1s/K1f          carry digit / CR-LF / whitespace run state across tiles (three small scan kernels
+//                    + a fix-up pass that is rarely non-trivial)
+//   K2a longmark     find pieces longer than TK_LANE_MAX bytes
+//   K3  longmerge    exact BPE for those: warp per piece in shared memory, block per huge piece in rounds
+//   K2  lookup       one lane per piece: whole-piece vocabulary lookup -> rank stream (one word per byte
+//                    position); other pieces -> global queues by length class
+//   K2m lanemerge    x5: one lane per queued piece: exact byte_pair_merge
+//   K3s tilesum/scan/apply   prefix of the per-tile token counts -> first output position of every tile
+//   K4  emit         compaction of the rank stream: ids (+num_special), BOS/EOS, per-document offsets
+// Decode lives in tk_decode.cu.
 #include "tk_kernels.h"
 
 #include <cstdio>
