@@ -211,7 +211,16 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the encode path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    numa = None
     if world > 1:
+        # one process per GPU: run on (and allocate the pinned staging buffers from) the CPUs next to this GPU
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+            numa = "cpu affinity set to GPU %d's NUMA node (%d cpus)" % (local, len(os.sched_getaffinity(0)))
+        except Exception as e:   # not fatal: the numbers are then just measured without the binding
+            numa = "cpu affinity not set (%s)" % type(e).__name__
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
@@ -383,6 +392,8 @@ def run_ours(args):
                    "hbm_frac": (4 * n_tokens + n_bytes + 16 * (n_docs + 1)) / (dec_ms * 1e-3) / 1e9 / peak if world == 1 else None},
         "tokens_per_step": int(total_tokens), "bytes_per_token": total_bytes / max(total_tokens, 1.0),
     }
+    if numa:
+        line["host_binding"] = numa
 
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import tekken_oracle as TO
