@@ -145,6 +145,19 @@ def test_fuzz_window_and_tile_edges(gpu_tok, oracle):
     assert_same_batch(gpu_tok, oracle, data, np.array([0, len(data)], dtype=np.uint64), False, False)
 
 
+def test_every_unicode_scalar_value(gpu_tok, oracle):
+    # the UTF-8 decoder and the two-stage class table of the CUDA path against the oracle for EVERY scalar value:
+    # each one between letters, before a digit, doubled, and after a space
+    cps = [c for c in range(0x110000) if not 0xD800 <= c <= 0xDFFF]
+    docs = [("x%sy1 %s%s" % (chr(c), chr(c), chr(c))).encode("utf-8") for c in cps]
+    data, off = _pack(docs)
+    assert_same_batch(gpu_tok, oracle, data, off, False, False)
+    # and as running text (classes of neighbouring characters interact across the 32-byte windows)
+    rng = random.Random(4)
+    text = "".join(chr(rng.choice(cps)) if rng.random() < 0.5 else rng.choice("ab 1\n'.") for _ in range(400000)).encode("utf-8")
+    assert_same_batch(gpu_tok, oracle, *one_doc(text), False, False, n_threads=1)
+
+
 def test_ragged_and_empty_documents(gpu_tok, oracle):
     texts = [b"", b"", b"a", b"", " ".encode(), b"", "日本".encode(), b"", b""]
     data, off = _pack(texts)
