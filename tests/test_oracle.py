@@ -67,6 +67,19 @@ def test_live_engine_fuzz(oracle):
         assert oracle.encode(t, False, False) == [x + 1000 for x in r], repr(t)
 
 
+def test_live_engine_every_unicode_scalar_value(oracle):
+    # pins the oracle's Unicode class tables (and its UTF-8 handling) to the engine for EVERY scalar value: each one
+    # between letters, before a digit, doubled after a space, and followed by a line feed
+    tiktoken = pytest.importorskip("tiktoken")
+    del tiktoken
+    enc = TO.tiktoken_engine(oracle.ranks)
+    cps = [c for c in range(0x110000) if not 0xD800 <= c <= 0xDFFF]
+    texts = ["".join("x%sy1 %s%s\n" % (chr(c), chr(c), chr(c)) for c in cps[i:i + 64]) for i in range(0, len(cps), 64)]
+    ref = enc.encode_ordinary_batch(texts, num_threads=8)
+    for t, r in zip(texts, ref):
+        assert oracle.encode(t, False, False) == [x + 1000 for x in r], repr(t[:40])
+
+
 def test_split_examples(oracle):
     # SURVEY.md section 3.2 consequences
     def sp(s):
