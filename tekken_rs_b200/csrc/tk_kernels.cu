@@ -777,7 +777,6 @@ __host__ __device__ __forceinline__ uint32_t lane_class(uint32_t len) {        /
 }
 
 struct LkSmem {
-    uint32_t words[LK_TILE];           // the tile's stream words (rank / EN_INVALID / EN_LONGREF per byte position); 16-byte aligned
     uint8_t bytes[LK_TILE + TK_LANE_MAX + 16];   // 16-byte aligned
     uint32_t mask[LK_WINS + 4];
     uint16_t list[LK_PCAP];            // tile-relative starts of all pieces, in order
@@ -853,7 +852,15 @@ __global__ void __launch_bounds__(LK_T) lookup_kernel(const uint8_t* __restrict_
             m &= m - 1;
         }
     }
-    for (uint32_t i = t; i < LK_TILE; i += LK_T) S.words[i] = EN_INVALID;
+    // the tile's stream words start out EN_INVALID (coalesced 16-byte stores); ranks and long-piece marks are
+    // stored over them after the barrier (same block: ordered), K2m fills in the merged pieces later
+    uint32_t* dst = stream + tile_pos;
+    {
+        const uint4 inv = make_uint4(EN_INVALID, EN_INVALID, EN_INVALID, EN_INVALID);
+        uint4* d4 = reinterpret_cast<uint4*>(dst);
+        for (uint32_t i = t; i < LK_TILE / 4; i += LK_T) d4[i] = inv;
+    }
+    __threadfence_block();
     __syncthreads();
     const uint32_t np = S.n_pieces;
 
@@ -869,10 +876,10 @@ __global__ void __launch_bounds__(LK_T) lookup_kernel(const uint8_t* __restrict_
                 if (e != 0xFFFFFFFFu && e - s <= TK_LANE_MAX) {
                     len = e - s;
                     const uint32_t whole = tk_vocab_lookup_w32(T, S.bytes, s, len);
-                    if (whole != TK_INF) { S.words[s] = whole; hit = true; }
-                    else if (len == 1) { S.words[s] = (uint32_t)S.bytes[s]; hit = true; }
+                    if (whole != TK_INF) { dst[s] = whole; hit = true; }
+                    else if (len == 1) { dst[s] = (uint32_t)S.bytes[s]; hit = true; }
                     else cls = lane_class(len);
-                } else S.words[s] = EN_LONGREF;                        // longer pieces: K3
+                } else dst[s] = EN_LONGREF;                           // longer pieces: K3
             }
         }
         const uint32_t hm = __ballot_sync(0xFFFFFFFFu, hit);
@@ -892,12 +899,6 @@ __global__ void __launch_bounds__(LK_T) lookup_kernel(const uint8_t* __restrict_
     __syncthreads();
     if (t < TKK_N_CLASSES && S.cls_n[t]) S.cls_base[t] = atomicAdd(q_n + t, S.cls_n[t]);   // this tile's range of every queue
     if (t == 32 && S.n_hit) atomicAdd(tile_count + tile, (unsigned long long)S.n_hit);
-    {
-        // the tile's stream words, coalesced.  K2m later overwrites the positions of merged pieces.
-        uint4* dst = reinterpret_cast<uint4*>(stream + tile_pos);
-        const uint4* src = reinterpret_cast<const uint4*>(S.words);
-        for (uint32_t i = t; i < LK_TILE / 4; i += LK_T) dst[i] = src[i];
-    }
     __syncthreads();
     // ---- C: misses into the queue of their length class ----
     const uint32_t nm = S.n_miss;
