@@ -241,7 +241,7 @@ __device__ __forceinline__ void pretok_tile(PtSmem& S, uint32_t b, const uint8_t
     }
 }
 
-__global__ void __launch_bounds__(PT_T) pretok_kernel(const uint8_t* __restrict__ data, uint64_t n,
+__global__ void __launch_bounds__(PT_T, 6) pretok_kernel(const uint8_t* __restrict__ data, uint64_t n,
                                                       const uint32_t* __restrict__ ds_mask, uint32_t* __restrict__ start_mask,
                                                       uint64_t n_windows, TkDeviceTables T, TkkTileSummary* __restrict__ summ,
                                                       unsigned long long* __restrict__ err_pos) {
