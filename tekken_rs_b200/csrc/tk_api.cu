@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <chrono>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -154,10 +155,12 @@ struct tk_tokenizer {
         uint32_t* h_small = nullptr;   // mapped pinned copy of the workspace's counter block
         uint32_t* d_small_map = nullptr;   // its device address
         cudaEvent_t done = nullptr;    // recorded after the counters have been published
+        cudaEvent_t ev_in = nullptr, ev_out = nullptr;   // pipeline: text has arrived / ids have left
         tkk::EncodeLayout L;
     };
-    static constexpr int kSlots = 3;
+    static constexpr int kSlots = 4;
     EncSlot slot[kSlots];          // host-buffer encode: chunks of a batch pipeline through these
+    cudaStream_t pipe_st[3] = {nullptr, nullptr, nullptr};   // ... on an upload, a kernel and a download stream
     EncSlot dev_slot;              // device-pointer encode (caller's stream)
     bool timing = false;
     tkk::StageTimer timer;
@@ -295,7 +298,10 @@ extern "C" void tk_free(tk_tokenizer* t) {
             s.ws.release(); s.scratch.release(); s.in_data.release(); s.in_off.release(); s.out_tok.release(); s.out_off.release();
             if (s.h_small) cudaFreeHost(s.h_small);
             if (s.done) cudaEventDestroy(s.done);
+            if (s.ev_in) cudaEventDestroy(s.ev_in);
+            if (s.ev_out) cudaEventDestroy(s.ev_out);
         };
+        for (auto& ps : t->pipe_st) if (ps) { cudaStreamSynchronize(ps); cudaStreamDestroy(ps); }
         for (auto& sl : t->slot) drop(sl);
         drop(t->dev_slot);
         if (t->stream) cudaStreamDestroy(t->stream);
@@ -543,7 +549,7 @@ extern "C" int tk_encode_batch(const tk_tokenizer* tc, const uint8_t* data, cons
     uint64_t* h_off = (uint64_t*)g_pool.get((n_docs + 1) * 8);
     if (!h_tok || !h_off) { g_pool.put(h_tok); g_pool.put(h_off); return fail(TK_ERR_CUDA, "out of pinned host memory"); }
     auto bail = [&](int code) {
-        for (auto& sl : t->slot) if (sl.st) cudaStreamSynchronize(sl.st);
+        for (auto& ps : t->pipe_st) if (ps) cudaStreamSynchronize(ps);
         g_pool.put(h_tok); g_pool.put(h_off);
         return code;
     };
@@ -555,40 +561,73 @@ extern "C" int tk_encode_batch(const tk_tokenizer* tc, const uint8_t* data, cons
         c.cap = c.n_bytes + 2 * (uint64_t)c.n + 2;
         return c;
     };
+    // Three role streams: text goes up on one, the kernels of successive chunks run back to back on the
+    // second, ids come down on the third.  Events order them per slot: kernels(i) after H2D(i) and after
+    // D2H(i - kSlots) has emptied the slot's id buffer; H2D(i) after kernels(i - kSlots) have read the
+    // slot's text.  TEKKEN_B200_TRACE=1 prints the device timeline of every chunk on stderr.
+    for (auto& ps : t->pipe_st) if (!ps) CUDA_OR_FAIL(cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
+    cudaStream_t st_up = t->pipe_st[0], st_k = t->pipe_st[1], st_down = t->pipe_st[2];
+    static const bool kTrace = getenv("TEKKEN_B200_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    std::vector<double> thost;
+    const auto host_now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    if (kTrace) {
+        tev.resize(n_chunks * 6 + 1);
+        thost.resize(n_chunks * 3 + 1);
+        for (auto& e : tev) cudaEventCreate(&e);
+        cudaEventRecord(tev[0], st_up);
+        thost[0] = host_now();
+    }
+    auto mark = [&](size_t i, int k, cudaStream_t st) { if (kTrace) cudaEventRecord(tev[1 + i * 6 + k], st); };
     auto issue = [&](size_t i) -> int {
         tk_tokenizer::EncSlot& s = t->slot[i % tk_tokenizer::kSlots];
         const Chunk c = chunk_of(i);
-        if (!s.st) CUDA_OR_FAIL(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+        if (!s.ev_in) {
+            CUDA_OR_FAIL(cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
+            CUDA_OR_FAIL(cudaEventCreateWithFlags(&s.ev_out, cudaEventDisableTiming));
+        }
+        if (kTrace) thost[1 + i * 3] = host_now();
         CUDA_OR_FAIL(s.in_data.ensure(c.n_bytes + 64));
         CUDA_OR_FAIL(s.in_off.ensure((c.n + 1) * 8));
         CUDA_OR_FAIL(s.out_tok.ensure(c.cap * 4));
         CUDA_OR_FAIL(s.out_off.ensure((c.n + 1) * 8));
-        if (c.n_bytes) CUDA_OR_FAIL(cudaMemcpyAsync(s.in_data.p, data + c.byte_begin, c.n_bytes, cudaMemcpyHostToDevice, s.st));
-        CUDA_OR_FAIL(cudaMemcpyAsync(s.in_off.p, doc_off + c.doc_begin, (c.n + 1) * 8, cudaMemcpyHostToDevice, s.st));
-        return encode_issue(t, s, (const uint8_t*)s.in_data.p, (const uint64_t*)s.in_off.p, c.byte_begin, c.n, c.n_bytes, add_bos, add_eos,
-                            (uint32_t*)s.out_tok.p, c.cap, (uint64_t*)s.out_off.p, s.st, false);
+        if (i >= (size_t)tk_tokenizer::kSlots) CUDA_OR_FAIL(cudaStreamWaitEvent(st_up, s.done, 0));
+        mark(i, 0, st_up);
+        if (c.n_bytes) CUDA_OR_FAIL(cudaMemcpyAsync(s.in_data.p, data + c.byte_begin, c.n_bytes, cudaMemcpyHostToDevice, st_up));
+        CUDA_OR_FAIL(cudaMemcpyAsync(s.in_off.p, doc_off + c.doc_begin, (c.n + 1) * 8, cudaMemcpyHostToDevice, st_up));
+        mark(i, 1, st_up);
+        CUDA_OR_FAIL(cudaEventRecord(s.ev_in, st_up));
+        CUDA_OR_FAIL(cudaStreamWaitEvent(st_k, s.ev_in, 0));
+        if (i >= (size_t)tk_tokenizer::kSlots) CUDA_OR_FAIL(cudaStreamWaitEvent(st_k, s.ev_out, 0));
+        mark(i, 2, st_k);
+        const int r = encode_issue(t, s, (const uint8_t*)s.in_data.p, (const uint64_t*)s.in_off.p, c.byte_begin, c.n, c.n_bytes, add_bos, add_eos,
+                                   (uint32_t*)s.out_tok.p, c.cap, (uint64_t*)s.out_off.p, st_k, false);
+        mark(i, 3, st_k);
+        if (kTrace) thost[2 + i * 3] = host_now();
+        return r;
     };
     std::vector<uint64_t> prefix(n_chunks + 1, 0);
-    // two chunks are always queued ahead, so the host sits in the wait for chunk i when it completes and
-    // its ids start their way back at once
-    for (size_t i = 0; i < 2 && i < n_chunks; ++i) { rc = issue(i); if (rc) return bail(rc); }
+    // kAhead chunks are always queued ahead, so the host sits in the wait for chunk i when it completes
+    // and its ids start their way back at once
+    constexpr size_t kAhead = tk_tokenizer::kSlots - 1;
+    for (size_t i = 0; i < kAhead && i < n_chunks; ++i) { rc = issue(i); if (rc) return bail(rc); }
     for (size_t i = 0; i < n_chunks; ++i) {
         tk_tokenizer::EncSlot& s = t->slot[i % tk_tokenizer::kSlots];
         const Chunk c = chunk_of(i);
         uint64_t n_tok = 0;
         for (int attempt = 0;; ++attempt) {
             bool retry = false;
-            rc = encode_finish(t, s, s.st, c.n_bytes, c.cap, c.byte_begin, &n_tok, &retry, false);
+            rc = encode_finish(t, s, st_k, c.n_bytes, c.cap, c.byte_begin, &n_tok, &retry, false);
             if (rc) return bail(rc);
             if (!retry) break;
             if (attempt) return bail(fail(TK_ERR_CUDA, "huge-piece scratch could not be grown"));
             rc = encode_issue(t, s, (const uint8_t*)s.in_data.p, (const uint64_t*)s.in_off.p, c.byte_begin, c.n, c.n_bytes, add_bos, add_eos,
-                              (uint32_t*)s.out_tok.p, c.cap, (uint64_t*)s.out_off.p, s.st, false);
+                              (uint32_t*)s.out_tok.p, c.cap, (uint64_t*)s.out_off.p, st_k, false);
             if (rc) return bail(rc);
         }
         if (prefix[i] + n_tok > h_cap) {
             // estimate too small: finish the copies into the old buffer, move to a bigger one
-            for (auto& sl : t->slot) if (sl.st) CUDA_OR_FAIL(cudaStreamSynchronize(sl.st));
+            CUDA_OR_FAIL(cudaStreamSynchronize(st_down));
             uint64_t want = std::max(2 * h_cap, prefix[i] + n_tok + (total - c.byte_begin - c.n_bytes) + 2 * (uint64_t)(n_docs - c.doc_begin) + 4096);
             uint32_t* bigger = (uint32_t*)g_pool.get(want * 4);
             if (!bigger) return bail(fail(TK_ERR_CUDA, "out of pinned host memory"));
@@ -598,17 +637,31 @@ extern "C" int tk_encode_batch(const tk_tokenizer* tc, const uint8_t* data, cons
             h_cap = want;
         }
         cudaError_t e = cudaSuccess;
-        if (n_tok) e = cudaMemcpyAsync(h_tok + prefix[i], s.out_tok.p, n_tok * 4, cudaMemcpyDeviceToHost, s.st);
-        if (e == cudaSuccess && c.n) e = cudaMemcpyAsync(h_off + c.doc_begin, s.out_off.p, c.n * 8, cudaMemcpyDeviceToHost, s.st);
+        if (kTrace) thost[3 + i * 3] = host_now();
+        mark(i, 4, st_down);
+        if (n_tok) e = cudaMemcpyAsync(h_tok + prefix[i], s.out_tok.p, n_tok * 4, cudaMemcpyDeviceToHost, st_down);
+        if (e == cudaSuccess && c.n) e = cudaMemcpyAsync(h_off + c.doc_begin, s.out_off.p, c.n * 8, cudaMemcpyDeviceToHost, st_down);
+        mark(i, 5, st_down);
+        if (e == cudaSuccess) e = cudaEventRecord(s.ev_out, st_down);
         if (e != cudaSuccess) return bail(fail(TK_ERR_CUDA, "copying ids back: %s", cudaGetErrorString(e)));
         prefix[i + 1] = prefix[i] + n_tok;
-        if (i + 2 < n_chunks) { rc = issue(i + 2); if (rc) return bail(rc); }
+        if (i + kAhead < n_chunks) { rc = issue(i + kAhead); if (rc) return bail(rc); }
     }
-    for (auto& sl : t->slot)
-        if (sl.st) {
-            cudaError_t e = cudaStreamSynchronize(sl.st);
-            if (e != cudaSuccess) return bail(fail(TK_ERR_CUDA, "copying ids back: %s", cudaGetErrorString(e)));
+    {
+        cudaError_t e = cudaStreamSynchronize(st_down);
+        if (e != cudaSuccess) return bail(fail(TK_ERR_CUDA, "copying ids back: %s", cudaGetErrorString(e)));
+    }
+    if (kTrace) {
+        fprintf(stderr, "[tekken_b200 trace] chunk: host issue..issued | h2d begin..end | kernels begin..end | host saw done | d2h begin..end  (ms)\n");
+        for (size_t i = 0; i < n_chunks; ++i) {
+            float v[6];
+            for (int k = 0; k < 6; ++k) cudaEventElapsedTime(&v[k], tev[0], tev[1 + i * 6 + k]);
+            fprintf(stderr, "[tekken_b200 trace] %3zu: %7.2f..%7.2f | %7.2f..%7.2f | %7.2f..%7.2f | %7.2f | %7.2f..%7.2f\n", i,
+                    thost[1 + i * 3] - thost[0], thost[2 + i * 3] - thost[0], v[0], v[1], v[2], v[3], thost[3 + i * 3] - thost[0], v[4], v[5]);
         }
+        fprintf(stderr, "[tekken_b200 trace] all copies done at host %.2f ms\n", host_now() - thost[0]);
+        for (auto& e : tev) cudaEventDestroy(e);
+    }
     // chunk-local token offsets -> batch offsets
     for (size_t i = 1; i < n_chunks; ++i) {
         const uint64_t add = prefix[i];
