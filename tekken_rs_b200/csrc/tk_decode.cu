@@ -142,48 +142,70 @@ __global__ void __launch_bounds__(DC_T) decode_gather_kernel(const uint32_t* __r
     // sequence starts among my positions (the sentinel position n_ids included)
     const uint32_t tw = tds[i0 >> 5] >> (i0 & 31);   // DC_PER divides 32 -> my 8 bits are in one word
     uint64_t seq = (tw & 0xFFu) ? seq_first[i0 >> 5] : 0;   // first sequence of my group of 32 ids; advanced below
+    // Usual case, unrolled: an ordinary token of at most 16 bytes, no sequence start -> one aligned 16-byte
+    // load from the padded table.  Everything else (sequence starts, special and unknown ids, longer
+    // tokens, oversized tiles, the sentinel position) is noted in `slow` and handled by one compact loop
+    // below, so the kernel stays small enough for the instruction cache.
+    uint32_t slow = 0;
+    {
+        uint32_t pk = p;
 #pragma unroll
-    for (int k = 0; k < DC_PER; ++k) {
+        for (int k = 0; k < DC_PER; ++k) {
+            const uint64_t i = i0 + k;
+            const uint32_t v = id[k], l = len[k];
+            const uint32_t r = v - T.num_special;
+            const bool fast = fits && i < n_ids && !((tw >> k) & 1u) && v >= T.num_special && r < T.n_vocab && l <= 16u;
+            if (fast) {
+                const uint4 q = __ldg(T.vocab_pad16 + r);
+                uint32_t cur = q.x;
+                for (uint32_t j = 0; j < l; ++j) {
+                    if ((j & 3u) == 0u && j) cur = j == 4u ? q.y : j == 8u ? q.z : q.w;
+                    buf[pk + j] = (uint8_t)cur;
+                    cur >>= 8;
+                }
+            } else if (i <= n_ids) slow |= 1u << k;
+            pk += l;
+        }
+    }
+#pragma unroll 1
+    while (slow) {
+        const uint32_t k = (uint32_t)(__ffs((int)slow) - 1);
+        slow &= slow - 1;
         const uint64_t i = i0 + k;
-        if (i > n_ids) break;
+        uint32_t pre = 0, v = 0, l = 0;                      // bytes of my ids before position k; its id and length
+#pragma unroll
+        for (int j = 0; j < DC_PER; ++j) {
+            pre += (uint32_t)j < k ? len[j] : 0u;
+            if ((uint32_t)j == k) { v = id[j]; l = len[j]; }
+        }
+        const uint64_t ok = o + pre;
+        const uint32_t pk = p + pre;
         if ((tw >> k) & 1u) {
             while (tok_off[seq] < i) ++seq;              // sequences that start earlier in the group
-            for (; seq <= n_docs && tok_off[seq] == i; ++seq) byte_off[seq] = o;
-            mark_boundary(bmask, o, out_cap);
+            for (; seq <= n_docs && tok_off[seq] == i; ++seq) byte_off[seq] = ok;
+            mark_boundary(bmask, ok, out_cap);
         }
         if (i == n_ids) break;
-        const uint32_t v = id[k], l = len[k];
         if (v < T.num_special) {
             // a special id ends the ordinary run before it and starts a new one after it
-            mark_boundary(bmask, o, out_cap);
+            mark_boundary(bmask, ok, out_cap);
             if (policy == TK_POLICY_RAISE) {
                 const uint64_t d = seq_of(tok_off, n_docs, i);
                 atomicMin(&docerr[d].sp_tok, (unsigned long long)i);
-                atomicMin(&docerr[d].sp_byte, (unsigned long long)o);
+                atomicMin(&docerr[d].sp_byte, (unsigned long long)ok);
             } else if (policy == TK_POLICY_KEEP) {
-                dc_put(buf, fits, p, out, o, out_cap, T.special_bytes + T.special_off[v], l);
-                mark_boundary(bmask, o + l, out_cap);
+                dc_put(buf, fits, pk, out, ok, out_cap, T.special_bytes + T.special_off[v], l);
+                mark_boundary(bmask, ok + l, out_cap);
             }
         } else {
             const uint32_t r = v - T.num_special;
             if (r >= T.n_vocab) {
                 const uint64_t d = seq_of(tok_off, n_docs, i);
                 atomicMin(&docerr[d].unk_tok, (unsigned long long)i);
-            } else if (l <= 16u && fits) {
-                // the token's bytes in one aligned 16-byte load from the padded table
-                const uint4 q = __ldg(T.vocab_pad16 + r);
-                uint32_t cur = q.x;
-                for (uint32_t j = 0; j < l; ++j) {
-                    if ((j & 3u) == 0u && j) cur = j == 4u ? q.y : j == 8u ? q.z : q.w;
-                    buf[p + j] = (uint8_t)cur;
-                    cur >>= 8;
-                }
             } else {
-                dc_put(buf, fits, p, out, o, out_cap, T.vocab_bytes + T.vocab_off[r], l);
+                dc_put(buf, fits, pk, out, ok, out_cap, T.vocab_bytes + T.vocab_off[r], l);
             }
         }
-        o += l;
-        p += l;
     }
     if (!fits) return;
     __syncthreads();

@@ -186,8 +186,8 @@ __device__ __forceinline__ uint32_t tk_vocab_lookup_w32(const TkDeviceTables& T,
 // Exact byte_pair_merge of one piece by one lane.  id[j] = id of the part that starts at byte
 // offset j (initially the byte itself), key[j] = rank << 6 | j of the pair (part at j, next live
 // part), TK_INF if that pair is not a vocabulary entry or j is the last part.  Parts never move: a
-// merge writes the new id at the left part's offset, marks the right part's offset TK_LANE_DEAD,
-// and the set of live offsets is a 64-bit mask in registers, so neighbours come from bit
+// merge writes the new id at the left part's offset, clears the right part's bit in the live mask
+// (the set of live offsets, 32 or 64 bits in registers), so neighbours come from bit
 // operations.  The minimum key is the lowest rank, leftmost on ties.  Returns the live mask.
 // bit helpers for the live mask: 32-bit when the piece class fits, else 64-bit
 __device__ __forceinline__ uint32_t tk_ffs_m(uint32_t m) { return (uint32_t)__ffs((int)m); }
@@ -197,19 +197,21 @@ __device__ __forceinline__ uint32_t tk_top_m(unsigned long long m) { return 63u 
 __device__ __forceinline__ uint32_t tk_popc_m(uint32_t m) { return (uint32_t)__popc(m); }
 __device__ __forceinline__ uint32_t tk_popc_m(unsigned long long m) { return (uint32_t)__popcll(m); }
 
-template <class M>
+template <class M, int MAXLEN>
 __device__ __forceinline__ M tk_bpe_merge_loop(const TkDeviceTables& T, uint32_t len, uint32_t* id, uint32_t* key) {
     constexpr uint32_t kBits = sizeof(M) * 8;
+    static_assert(MAXLEN % 4 == 0 && MAXLEN <= (int)kBits, "scan is unrolled by four; one live bit per offset");
     const M one = 1;
     M live = len >= kBits ? ~(M)0 : (M)((one << len) - one);
     for (;;) {
+        // all MAXLEN slots are scanned (the caller set the ones past the piece to TK_INF): a fixed trip
+        // count keeps the loop free of remainder branches, and a class holds lengths near MAXLEN anyway
         uint32_t best = TK_INF;
-        uint32_t j = 0;
-        for (; j + 4 <= len; j += 4) {
+#pragma unroll
+        for (int j = 0; j < MAXLEN; j += 4) {
             const uint32_t a0 = key[j], a1 = key[j + 1], a2 = key[j + 2], a3 = key[j + 3];
             best = min(min(best, a0), min(a1, min(a2, a3)));
         }
-        for (; j < len; ++j) best = min(best, key[j]);
         if (best == TK_INF) break;
         const uint32_t bp = best & 63u, rank = best >> 6;
         const M above = live & ~(M)(((one << bp) << 1) - one);     // live offsets > bp (bp is never the top bit: it has a right neighbour)
@@ -220,7 +222,6 @@ __device__ __forceinline__ M tk_bpe_merge_loop(const TkDeviceTables& T, uint32_t
         const uint32_t nn = above_q ? tk_ffs_m(above_q) - 1u : 0xFFFFFFFFu;
         const uint32_t pv = below ? tk_top_m(below) : 0xFFFFFFFFu;
         id[bp] = rank;
-        id[q] = TK_LANE_DEAD;
         key[q] = TK_INF;
         const uint32_t lft = pv != 0xFFFFFFFFu ? id[pv] : TK_INF;
         const uint32_t rgt = nn != 0xFFFFFFFFu ? id[nn] : TK_INF;

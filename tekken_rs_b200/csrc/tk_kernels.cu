@@ -17,7 +17,9 @@
 // Decode lives in tk_decode.cu.
 #include "tk_kernels.h"
 
+#include <array>
 #include <cstdio>
+#include <cstdlib>
 #include <type_traits>
 
 #include "tk_device.cuh"
@@ -311,19 +313,23 @@ __global__ void __launch_bounds__(SC_T) pretok_segscan_kernel(const uint32_t* __
     f_chunk[t] = rs_pack(f);
     h_chunk[t] = f.head;
     __syncthreads();
+    // threads past `act` hold no segment; the two serial walks (one lane each, in different warps) skip them
+    const uint32_t act = per ? (n_seg + per - 1) / per : 0u;
     if (t == 0) {
         uint32_t nst = 0, ast = 0;
-        for (uint32_t j = 0; j < SC_T; ++j) {
+        for (uint32_t j = 0; j < act; ++j) {
             in_state[j] = nst | (ast << 2);
             rs_step(nst, ast, rs_unpack(f_chunk[j]));
         }
+    } else if (t == 32) {
         uint32_t nh = 2;  // past the end of the data the run has ended
-        for (int j = SC_T - 1; j >= 0; --j) {
+        for (int j = (int)act - 1; j >= 0; --j) {
             h_after[j] = nh;
             if (h_chunk[j]) nh = h_chunk[j];
         }
     }
     __syncthreads();
+    if (t >= act) return;
     uint32_t nst = in_state[t] & 3u, ast = in_state[t] >> 2;
     for (uint32_t b = lo; b < hi; ++b) {
         seg_in[b] = nst | (ast << 2);
@@ -354,15 +360,18 @@ __global__ void __launch_bounds__(SG_T) pretok_apply_kernel(const TkkTileSummary
         if (lo + k < hi) { mine[k] = summ[lo + k]; f = tk_compose(f, rs_unpack(mine[k].packed)); }
     f_chunk[t] = rs_pack(f);
     __syncthreads();
+    // threads of the last block past `act` hold no tile
+    const uint64_t left = (uint64_t)n_tiles - (uint64_t)blockIdx.x * SG_TILES;
+    const uint32_t act = left >= SG_TILES ? SG_T : (uint32_t)((left + SG_PER - 1) / SG_PER);
     if (t == 0) {
         uint32_t nst = seg_in[blockIdx.x] & 3u, ast = seg_in[blockIdx.x] >> 2;
-        for (uint32_t j = 0; j < SG_T; ++j) {
+        for (uint32_t j = 0; j < act; ++j) {
             in_state[j] = nst | (ast << 2);
             rs_step(nst, ast, rs_unpack(f_chunk[j]));
         }
     } else if (t == 32) {
         uint32_t nh = seg_after[blockIdx.x];
-        for (int j = SG_T - 1; j >= 0; --j) {
+        for (int j = (int)act - 1; j >= 0; --j) {
             h_after[j] = nh;
             const uint32_t h = rs_unpack(f_chunk[j]).head;
             if (h) nh = h;
@@ -772,8 +781,11 @@ __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __
 #define QE_START_BITS 40
 #define QE_LEN_BITS 7
 
-__host__ __device__ __forceinline__ uint32_t lane_class(uint32_t len) {        // 2..4, 5..8, 9..16, 17..32, 33..64
-    return len <= 4u ? 0u : 30u - (uint32_t)TK_CLZ(len - 1u);
+// length class of a piece that goes to K2m: 2..4, 5..8, 9..12, 13..16, 17..24, 25..32, 33..48, 49..64 bytes
+__host__ __device__ __forceinline__ uint32_t lane_class(uint32_t len) {
+    if (len <= 8u) return len <= 4u ? 0u : 1u;
+    const uint32_t p = 31u - (uint32_t)TK_CLZ(len - 1u);             // 3, 4, 5 for 9..16, 17..32, 33..64
+    return 2u * (p - 2u) + (((len - 1u) >> (p - 1u)) & 1u);
 }
 
 struct LkSmem {
@@ -919,7 +931,7 @@ __global__ void __launch_bounds__(LK_T) lookup_kernel(const uint8_t* __restrict_
 }
 
 template <int MAXLEN, int THREADS>
-__global__ void __launch_bounds__(THREADS) lanemerge_kernel(const uint8_t* __restrict__ data, TkDeviceTables T,
+__global__ void __launch_bounds__(THREADS, (MAXLEN <= 12 ? 8 : MAXLEN <= 16 ? 6 : 1)) lanemerge_kernel(const uint8_t* __restrict__ data, TkDeviceTables T,
                                                             const unsigned long long* __restrict__ queue,
                                                             const uint32_t* __restrict__ q_n, uint32_t* __restrict__ q_w,
                                                             uint32_t* __restrict__ stream, unsigned long long* __restrict__ tile_count) {
@@ -931,7 +943,7 @@ __global__ void __launch_bounds__(THREADS) lanemerge_kernel(const uint8_t* __res
     const uint32_t total = *q_n;
     // short pieces cost about the same: warps stride over the queue.  Long ones vary more: warps take
     // the next 32 entries from a work counter.
-    constexpr bool kDynamic = MAXLEN >= 16;
+    constexpr bool kDynamic = MAXLEN >= 12;
     const uint32_t warps = gridDim.x * (THREADS / 32);
     for (uint32_t k0 = (blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5)) * 32u;; k0 += warps * 32u) {
         if (kDynamic) {
@@ -952,22 +964,16 @@ __global__ void __launch_bounds__(THREADS) lanemerge_kernel(const uint8_t* __res
 #pragma unroll
                 for (int c = 0; c < 4; ++c) if (i + c < len) id[i + c] = v[c];
             }
-            // parts = single bytes; rank of every adjacent byte pair from the direct table
-            for (uint32_t i = 0; i < len; i += 4) {
-                uint32_t r4[4];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const uint32_t j = i + c;
-                    r4[c] = j + 1 < len ? __ldg(T.byte_pair + ((id[j] << 8) | id[j + 1])) : TK_INF;
-                }
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const uint32_t j = i + c;
-                    if (j < len) key[j] = r4[c] == TK_INF ? TK_INF : ((r4[c] << 6) | j);
-                }
+            // parts = single bytes; rank of every adjacent byte pair from the direct table.  Slots past the
+            // piece get TK_INF: the merge loop scans all MAXLEN of them.
+#pragma unroll(MAXLEN <= 12 ? MAXLEN : 8)
+            for (int j = 0; j < MAXLEN; ++j) {
+                uint32_t r = TK_INF;
+                if ((uint32_t)j + 1u < len) r = __ldg(T.byte_pair + ((id[j] << 8) | id[j + 1]));
+                key[j] = r == TK_INF ? TK_INF : ((r << 6) | (uint32_t)j);
             }
             using Mask = typename std::conditional<(MAXLEN <= 32), uint32_t, unsigned long long>::type;
-            Mask live = tk_bpe_merge_loop<Mask>(T, len, id, key);
+            Mask live = tk_bpe_merge_loop<Mask, MAXLEN>(T, len, id, key);
             {
                 // the ranks go to consecutive byte positions from `start`: count them for the tile each one lands in
                 const uint32_t cnt = tk_popc_m(live);
@@ -1181,9 +1187,15 @@ __global__ void __launch_bounds__(E3_T, 6) emit_kernel(const uint32_t* __restric
         for (int k = 0; k < E3_PER; ++k)
             if ((valid >> k) & 1u) { if (o < out_cap) out[o] = w[k] + nsp; ++o; }
     } else {
+        // a document starts or a long piece sits among my positions (about one thread in sixty): a compact
+        // loop over the positions that emit something, re-reading their stream words (L1 hits), so that this
+        // path stays a few hundred bytes of code instead of sixteen unrolled copies
         uint64_t d = d_first;
-#pragma unroll
-        for (int k = 0; k < E3_PER; ++k) {
+        uint32_t todo = valid | myds | longm;
+#pragma unroll 1
+        while (todo) {
+            const uint32_t k = (uint32_t)(__ffs((int)todo) - 1);
+            todo &= todo - 1;
             if ((myds >> k) & 1u) {
                 const uint32_t nd = nd_single ? nd_single : docs_from(doc_off, n_docs, p0 + k + off_base, d);
                 for (uint64_t x = d; x < d + nd; ++x) {
@@ -1193,7 +1205,7 @@ __global__ void __launch_bounds__(E3_T, 6) emit_kernel(const uint32_t* __restric
                 }
                 d += nd;
             }
-            if ((valid >> k) & 1u) { if (o < out_cap) out[o] = w[k] + nsp; ++o; }
+            if ((valid >> k) & 1u) { if (o < out_cap) out[o] = __ldg(stream + p0 + k) + nsp; ++o; }
             else if ((longm >> k) & 1u) {
                 E3Long L;
                 L.src = lr.tok_base; L.dst = o; L.count = lr.count; L.pad = 0;
@@ -1241,7 +1253,7 @@ size_t encode_workspace_bytes(uint64_t n, uint64_t n_docs, EncodeLayout* L) {
     l.off_stream = take((l.n_ltiles * (size_t)LK_TILE + TK_LANE_MAX + 64) * 4);
     {
         // a queue per length class; a class whose shortest piece has m bytes holds at most n/m + 1 pieces
-        const uint32_t shortest[TKK_N_CLASSES] = {2, 5, 9, 17, 33};
+        const uint32_t shortest[TKK_N_CLASSES] = {2, 5, 9, 13, 17, 25, 33, 49};
         uint64_t e = 0;
         for (int c = 0; c < TKK_N_CLASSES; ++c) { l.queues.off[c] = e; e += n / shortest[c] + 32; }
         l.off_queues = take(e * 8);
@@ -1373,16 +1385,30 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
         lookup_kernel<<<(unsigned)L.n_ltiles, LK_T, 0, st>>>(d_data, n, start, T, stream, queues, L.queues, q_n, tile_count);
         TK_LAUNCHED();
     }
-    if (timer) timer->mark(st, "lanemerge64");
-    CK((launch_lanemerge<64, 128>(3, sm_count, d_data, T, queues + L.queues.off[4], q_n + 4, q_w + 4, stream, tile_count, st)));
-    if (timer) timer->mark(st, "lanemerge32");
-    CK((launch_lanemerge<32, 256>(3, sm_count, d_data, T, queues + L.queues.off[3], q_n + 3, q_w + 3, stream, tile_count, st)));
-    if (timer) timer->mark(st, "lanemerge16");
-    CK((launch_lanemerge<16, 256>(6, sm_count, d_data, T, queues + L.queues.off[2], q_n + 2, q_w + 2, stream, tile_count, st)));
-    if (timer) timer->mark(st, "lanemerge8");
-    CK((launch_lanemerge<8, 256>(8, sm_count, d_data, T, queues + L.queues.off[1], q_n + 1, q_w + 1, stream, tile_count, st)));
-    if (timer) timer->mark(st, "lanemerge4");
-    CK((launch_lanemerge<4, 256>(8, sm_count, d_data, T, queues + L.queues.off[0], q_n + 0, q_w + 0, stream, tile_count, st)));
+    // resident blocks per SM of the lane-merge launches, longest class first (what shared memory allows;
+    // tuning knob: TEKKEN_B200_LM_BPS="a,b,c,d,e,f,g,h")
+    static const std::array<int, TKK_N_CLASSES> bps = [] {
+        std::array<int, TKK_N_CLASSES> v{3, 4, 3, 4, 6, 8, 8, 8};
+        if (const char* e = getenv("TEKKEN_B200_LM_BPS")) {
+            int x[TKK_N_CLASSES];
+            if (sscanf(e, "%d,%d,%d,%d,%d,%d,%d,%d", &x[0], &x[1], &x[2], &x[3], &x[4], &x[5], &x[6], &x[7]) == TKK_N_CLASSES)
+                for (int i = 0; i < TKK_N_CLASSES; ++i) if (x[i] > 0 && x[i] <= 32) v[i] = x[i];
+        }
+        return v;
+    }();
+#define TK_LANEMERGE(MAXLEN, THREADS, CLS, NAME)                                                                                  \
+    if (timer) timer->mark(st, NAME);                                                                                             \
+    CK((launch_lanemerge<MAXLEN, THREADS>(bps[TKK_N_CLASSES - 1 - CLS], sm_count, d_data, T, queues + L.queues.off[CLS], q_n + CLS, \
+                                          q_w + CLS, stream, tile_count, st)));
+    TK_LANEMERGE(64, 128, 7, "lanemerge64")
+    TK_LANEMERGE(48, 128, 6, "lanemerge48")
+    TK_LANEMERGE(32, 256, 5, "lanemerge32")
+    TK_LANEMERGE(24, 256, 4, "lanemerge24")
+    TK_LANEMERGE(16, 256, 3, "lanemerge16")
+    TK_LANEMERGE(12, 256, 2, "lanemerge12")
+    TK_LANEMERGE(8, 256, 1, "lanemerge8")
+    TK_LANEMERGE(4, 256, 0, "lanemerge4")
+#undef TK_LANEMERGE
     if (timer) timer->mark(st, "emit");
     {
         const uint32_t nb = (uint32_t)ceil_div(L.n_ltiles, TS_BLOCK);
