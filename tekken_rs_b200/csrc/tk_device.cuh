@@ -139,7 +139,7 @@ __device__ __forceinline__ uint32_t tk_vocab_lookup_w32(const TkDeviceTables& T,
     const uint32_t sh = (s & 3u) * 8u;
     TkPieceHasher h;
     h.init(len);
-    uint64_t key8 = 0;
+    uint64_t key8 = 0, key16 = 0;                          // bytes 0..7 and 8..15 of the piece, zero padded
     uint32_t w0 = wp[0];
     for (uint32_t i = 0, k = 0; i < len; i += 8, k += 2) {
         const uint32_t w1 = wp[k + 1], w2 = wp[k + 2];
@@ -152,6 +152,7 @@ __device__ __forceinline__ uint32_t tk_vocab_lookup_w32(const TkDeviceTables& T,
         }
         const uint64_t w = (uint64_t)hi << 32 | lo;
         if (i == 0) key8 = w;
+        if (i == 8) key16 = w;
         h.add(w);
     }
     const uint64_t hv = h.finish();
@@ -164,12 +165,18 @@ __device__ __forceinline__ uint32_t tk_vocab_lookup_w32(const TkDeviceTables& T,
         const uint64_t skey = (uint64_t)raw.y << 32 | raw.x;
         if (slen == len && skey == key) {
             if (len <= 8) return raw.z;
-            const uint8_t* v = T.vocab_bytes + T.vocab_off[raw.z];
-            const uint8_t* q = base + s;
-            bool same = true;
-            for (uint32_t j = 0; j < len; ++j)
-                if (__ldg(v + j) != q[j]) { same = false; break; }
-            if (same) return raw.z;
+            if (len <= 16) {
+                // the token's bytes, zero padded to 16, in one load
+                const uint4 c = __ldg(T.vocab_pad16 + raw.z);
+                if (((uint64_t)c.y << 32 | c.x) == key8 && ((uint64_t)c.w << 32 | c.z) == key16) return raw.z;
+            } else {
+                const uint8_t* v = T.vocab_bytes + T.vocab_off[raw.z];
+                const uint8_t* q = base + s;
+                bool same = true;
+                for (uint32_t j = 0; j < len; ++j)
+                    if (__ldg(v + j) != q[j]) { same = false; break; }
+                if (same) return raw.z;
+            }
         }
         i = (i + 1) & T.vocab_mask;
     }
@@ -180,14 +187,14 @@ __device__ __forceinline__ uint32_t tk_vocab_lookup_w32(const TkDeviceTables& T,
 // <= TK_LANE_MAX  one lane per piece from a global queue (medmerge_kernel);  <= TK_MED_MAX  one warp per
 // piece;  beyond: one block per piece.  All run the same sequential definition.
 #define TK_TILE_MAX 32
-#define TK_LANE_MAX 64
+#define TK_LANE_MAX 96
 #define TK_LANE_DEAD 0xFFFFFFFEu
 
 // Exact byte_pair_merge of one piece by one lane.  id[j] = id of the part that starts at byte
-// offset j (initially the byte itself), key[j] = rank << 6 | j of the pair (part at j, next live
+// offset j (initially the byte itself), key[j] = rank << 7 | j of the pair (part at j, next live
 // part), TK_INF if that pair is not a vocabulary entry or j is the last part.  Parts never move: a
 // merge writes the new id at the left part's offset, clears the right part's bit in the live mask
-// (the set of live offsets, 32 or 64 bits in registers), so neighbours come from bit
+// (the set of live offsets, 32, 64 or 128 bits in registers), so neighbours come from bit
 // operations.  The minimum key is the lowest rank, leftmost on ties.  Returns the live mask.
 // bit helpers for the live mask: 32-bit when the piece class fits, else 64-bit
 __device__ __forceinline__ uint32_t tk_ffs_m(uint32_t m) { return (uint32_t)__ffs((int)m); }
@@ -196,6 +203,19 @@ __device__ __forceinline__ uint32_t tk_top_m(uint32_t m) { return 31u - (uint32_
 __device__ __forceinline__ uint32_t tk_top_m(unsigned long long m) { return 63u - (uint32_t)__clzll((long long)m); }
 __device__ __forceinline__ uint32_t tk_popc_m(uint32_t m) { return (uint32_t)__popc(m); }
 __device__ __forceinline__ uint32_t tk_popc_m(unsigned long long m) { return (uint32_t)__popcll(m); }
+typedef unsigned __int128 tk_u128;
+__device__ __forceinline__ uint32_t tk_ffs_m(tk_u128 m) {
+    const unsigned long long lo = (unsigned long long)m, hi = (unsigned long long)(m >> 64);
+    return lo ? (uint32_t)__ffsll((long long)lo) : (hi ? 64u + (uint32_t)__ffsll((long long)hi) : 0u);
+}
+__device__ __forceinline__ uint32_t tk_top_m(tk_u128 m) {
+    const unsigned long long lo = (unsigned long long)m, hi = (unsigned long long)(m >> 64);
+    return hi ? 127u - (uint32_t)__clzll((long long)hi) : 63u - (uint32_t)__clzll((long long)lo);
+}
+__device__ __forceinline__ uint32_t tk_popc_m(tk_u128 m) {
+    return (uint32_t)__popcll((unsigned long long)m) + (uint32_t)__popcll((unsigned long long)(m >> 64));
+}
+#define TK_KEY_SHIFT 7u                                  // key = rank << TK_KEY_SHIFT | offset; offsets < 128
 
 template <class M, int MAXLEN>
 __device__ __forceinline__ M tk_bpe_merge_loop(const TkDeviceTables& T, uint32_t len, uint32_t* id, uint32_t* key) {
@@ -213,7 +233,7 @@ __device__ __forceinline__ M tk_bpe_merge_loop(const TkDeviceTables& T, uint32_t
             best = min(min(best, a0), min(a1, min(a2, a3)));
         }
         if (best == TK_INF) break;
-        const uint32_t bp = best & 63u, rank = best >> 6;
+        const uint32_t bp = best & ((1u << TK_KEY_SHIFT) - 1u), rank = best >> TK_KEY_SHIFT;
         const M above = live & ~(M)(((one << bp) << 1) - one);     // live offsets > bp (bp is never the top bit: it has a right neighbour)
         const uint32_t q = tk_ffs_m(above) - 1u;                   // exists: the pair has a rank
         const M above_q = above & (above - one);                    // live offsets > q
@@ -227,8 +247,8 @@ __device__ __forceinline__ M tk_bpe_merge_loop(const TkDeviceTables& T, uint32_t
         const uint32_t rgt = nn != 0xFFFFFFFFu ? id[nn] : TK_INF;
         uint32_t r0, r1;
         tk_pair_rank2(T, lft, rank, rank, rgt, &r0, &r1);
-        if (pv != 0xFFFFFFFFu) key[pv] = r0 == TK_INF ? TK_INF : ((r0 << 6) | pv);
-        key[bp] = r1 == TK_INF ? TK_INF : ((r1 << 6) | bp);
+        if (pv != 0xFFFFFFFFu) key[pv] = r0 == TK_INF ? TK_INF : ((r0 << TK_KEY_SHIFT) | pv);
+        key[bp] = r1 == TK_INF ? TK_INF : ((r1 << TK_KEY_SHIFT) | bp);
     }
     return live;
 }

@@ -429,10 +429,12 @@ __global__ void longmark_kernel(const uint32_t* __restrict__ start_mask, uint64_
         pos = w * 32u + hb;
         if (pos < n) {
             // next start within TK_LANE_MAX bytes?  (words beyond n_windows are zero-padded)
-            const uint32_t m1 = start_mask[w + 1], m2 = start_mask[w + 2];
+            static_assert(TK_LANE_MAX <= 97, "a piece of TK_LANE_MAX bytes ends within three mask words");
+            const uint32_t m1 = start_mask[w + 1], m2 = start_mask[w + 2], m3 = start_mask[w + 3];
             uint64_t next;
             if (m1) next = (w + 1) * 32u + (uint32_t)(__ffs((int)m1) - 1);
             else if (m2) next = (w + 2) * 32u + (uint32_t)(__ffs((int)m2) - 1);
+            else if (m3) next = (w + 3) * 32u + (uint32_t)(__ffs((int)m3) - 1);
             else next = ~0ull;
             need = next == ~0ull || next - pos > TK_LANE_MAX;
         }
@@ -781,9 +783,10 @@ __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __
 #define QE_START_BITS 40
 #define QE_LEN_BITS 7
 
-// length class of a piece that goes to K2m: 2..4, 5..8, 9..12, 13..16, 17..24, 25..32, 33..48, 49..64 bytes
+// length class of a piece that goes to K2m: 2..4, 5..8, 9..12, 13..16, 17..24, 25..32, 33..48, 49..64, 65..96 bytes
 __host__ __device__ __forceinline__ uint32_t lane_class(uint32_t len) {
     if (len <= 8u) return len <= 4u ? 0u : 1u;
+    if (len > 64u) return 8u;
     const uint32_t p = 31u - (uint32_t)TK_CLZ(len - 1u);             // 3, 4, 5 for 9..16, 17..32, 33..64
     return 2u * (p - 2u) + (((len - 1u) >> (p - 1u)) & 1u);
 }
@@ -970,9 +973,10 @@ __global__ void __launch_bounds__(THREADS, (MAXLEN <= 12 ? 8 : MAXLEN <= 16 ? 6 
             for (int j = 0; j < MAXLEN; ++j) {
                 uint32_t r = TK_INF;
                 if ((uint32_t)j + 1u < len) r = __ldg(T.byte_pair + ((id[j] << 8) | id[j + 1]));
-                key[j] = r == TK_INF ? TK_INF : ((r << 6) | (uint32_t)j);
+                key[j] = r == TK_INF ? TK_INF : ((r << TK_KEY_SHIFT) | (uint32_t)j);
             }
-            using Mask = typename std::conditional<(MAXLEN <= 32), uint32_t, unsigned long long>::type;
+            using Mask = typename std::conditional<(MAXLEN <= 32), uint32_t,
+                                                   typename std::conditional<(MAXLEN <= 64), unsigned long long, tk_u128>::type>::type;
             Mask live = tk_bpe_merge_loop<Mask, MAXLEN>(T, len, id, key);
             {
                 // the ranks go to consecutive byte positions from `start`: count them for the tile each one lands in
@@ -1253,7 +1257,7 @@ size_t encode_workspace_bytes(uint64_t n, uint64_t n_docs, EncodeLayout* L) {
     l.off_stream = take((l.n_ltiles * (size_t)LK_TILE + TK_LANE_MAX + 64) * 4);
     {
         // a queue per length class; a class whose shortest piece has m bytes holds at most n/m + 1 pieces
-        const uint32_t shortest[TKK_N_CLASSES] = {2, 5, 9, 13, 17, 25, 33, 49};
+        const uint32_t shortest[TKK_N_CLASSES] = {2, 5, 9, 13, 17, 25, 33, 49, 65};
         uint64_t e = 0;
         for (int c = 0; c < TKK_N_CLASSES; ++c) { l.queues.off[c] = e; e += n / shortest[c] + 32; }
         l.off_queues = take(e * 8);
@@ -1386,13 +1390,17 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
         TK_LAUNCHED();
     }
     // resident blocks per SM of the lane-merge launches, longest class first (what shared memory allows;
-    // tuning knob: TEKKEN_B200_LM_BPS="a,b,c,d,e,f,g,h")
+    // tuning knob: TEKKEN_B200_LM_BPS="a,b,...")
     static const std::array<int, TKK_N_CLASSES> bps = [] {
-        std::array<int, TKK_N_CLASSES> v{3, 4, 3, 4, 6, 8, 8, 8};
+        std::array<int, TKK_N_CLASSES> v{4, 3, 4, 3, 4, 6, 8, 8, 8};
         if (const char* e = getenv("TEKKEN_B200_LM_BPS")) {
-            int x[TKK_N_CLASSES];
-            if (sscanf(e, "%d,%d,%d,%d,%d,%d,%d,%d", &x[0], &x[1], &x[2], &x[3], &x[4], &x[5], &x[6], &x[7]) == TKK_N_CLASSES)
-                for (int i = 0; i < TKK_N_CLASSES; ++i) if (x[i] > 0 && x[i] <= 32) v[i] = x[i];
+            for (int i = 0; i < TKK_N_CLASSES && *e; ++i) {
+                char* end = nullptr;
+                const long x = strtol(e, &end, 10);
+                if (end == e) break;
+                if (x > 0 && x <= 32) v[i] = (int)x;
+                e = *end == ',' ? end + 1 : end;
+            }
         }
         return v;
     }();
@@ -1400,6 +1408,7 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
     if (timer) timer->mark(st, NAME);                                                                                             \
     CK((launch_lanemerge<MAXLEN, THREADS>(bps[TKK_N_CLASSES - 1 - CLS], sm_count, d_data, T, queues + L.queues.off[CLS], q_n + CLS, \
                                           q_w + CLS, stream, tile_count, st)));
+    TK_LANEMERGE(96, 64, 8, "lanemerge96")
     TK_LANEMERGE(64, 128, 7, "lanemerge64")
     TK_LANEMERGE(48, 128, 6, "lanemerge48")
     TK_LANEMERGE(32, 256, 5, "lanemerge32")

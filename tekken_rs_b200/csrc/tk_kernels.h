@@ -33,10 +33,10 @@ enum {
     TKK_S_TOTAL = 14,    // u64
     TKK_S_BADDOC = 16,   // u64 (decode)
     TKK_S_QN = 20,       // TKK_N_CLASSES counters: queued pieces per length class
-    TKK_S_QW = 28,       // TKK_N_CLASSES work counters
+    TKK_S_QW = 30,       // TKK_N_CLASSES work counters
 };
 
-#define TKK_N_CLASSES 8
+#define TKK_N_CLASSES 9
 struct TkkQueueLayout {
     uint64_t off[TKK_N_CLASSES];   // first entry of every class in the queue array
 };
