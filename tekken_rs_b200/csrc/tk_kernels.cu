@@ -933,8 +933,8 @@ __global__ void __launch_bounds__(LK_T) lookup_kernel(const uint8_t* __restrict_
     }
 }
 
-template <int MAXLEN, int THREADS>
-__global__ void __launch_bounds__(THREADS, (MAXLEN <= 12 ? 8 : MAXLEN <= 16 ? 6 : 1)) lanemerge_kernel(const uint8_t* __restrict__ data, TkDeviceTables T,
+template <int MAXLEN, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) lanemerge_kernel(const uint8_t* __restrict__ data, TkDeviceTables T,
                                                             const unsigned long long* __restrict__ queue,
                                                             const uint32_t* __restrict__ q_n, uint32_t* __restrict__ q_w,
                                                             uint32_t* __restrict__ stream, unsigned long long* __restrict__ tile_count) {
@@ -1286,7 +1286,7 @@ cudaError_t publish_counters(const void* d_ws, const EncodeLayout& L, uint32_t* 
     return cudaGetLastError();
 }
 
-template <int MAXLEN, int THREADS>
+template <int MAXLEN, int THREADS, int MINB>
 static cudaError_t launch_lanemerge(int blocks_per_sm, int sm_count, const uint8_t* d_data, const TkDeviceTables& T,
                                     const unsigned long long* queue, const uint32_t* q_n, uint32_t* q_w, uint32_t* stream,
                                     unsigned long long* tile_count, cudaStream_t st) {
@@ -1295,10 +1295,10 @@ static cudaError_t launch_lanemerge(int blocks_per_sm, int sm_count, const uint8
     int dev = 0;
     CK(cudaGetDevice(&dev));
     if (!((attr_set.load() >> (dev & 63)) & 1ull)) {
-        CK(cudaFuncSetAttribute(lanemerge_kernel<MAXLEN, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(lanemerge_kernel<MAXLEN, THREADS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set.fetch_or(1ull << (dev & 63));
     }
-    lanemerge_kernel<MAXLEN, THREADS><<<(unsigned)(sm_count * blocks_per_sm), THREADS, smem, st>>>(d_data, T, queue, q_n, q_w, stream, tile_count);
+    lanemerge_kernel<MAXLEN, THREADS, MINB><<<(unsigned)(sm_count * blocks_per_sm), THREADS, smem, st>>>(d_data, T, queue, q_n, q_w, stream, tile_count);
     count_launch();
     return cudaSuccess;
 }
@@ -1392,7 +1392,7 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
     // resident blocks per SM of the lane-merge launches, longest class first (what shared memory allows;
     // tuning knob: TEKKEN_B200_LM_BPS="a,b,...")
     static const std::array<int, TKK_N_CLASSES> bps = [] {
-        std::array<int, TKK_N_CLASSES> v{4, 3, 4, 3, 4, 6, 8, 8, 8};
+        std::array<int, TKK_N_CLASSES> v{4, 3, 4, 3, 4, 4, 6, 8, 6};
         if (const char* e = getenv("TEKKEN_B200_LM_BPS")) {
             for (int i = 0; i < TKK_N_CLASSES && *e; ++i) {
                 char* end = nullptr;
@@ -1404,19 +1404,21 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
         }
         return v;
     }();
-#define TK_LANEMERGE(MAXLEN, THREADS, CLS, NAME)                                                                                  \
+#define TK_LANEMERGE(MAXLEN, THREADS, MINB, CLS, NAME)                                                                            \
     if (timer) timer->mark(st, NAME);                                                                                             \
-    CK((launch_lanemerge<MAXLEN, THREADS>(bps[TKK_N_CLASSES - 1 - CLS], sm_count, d_data, T, queues + L.queues.off[CLS], q_n + CLS, \
-                                          q_w + CLS, stream, tile_count, st)));
-    TK_LANEMERGE(96, 64, 8, "lanemerge96")
-    TK_LANEMERGE(64, 128, 7, "lanemerge64")
-    TK_LANEMERGE(48, 128, 6, "lanemerge48")
-    TK_LANEMERGE(32, 256, 5, "lanemerge32")
-    TK_LANEMERGE(24, 256, 4, "lanemerge24")
-    TK_LANEMERGE(16, 256, 3, "lanemerge16")
-    TK_LANEMERGE(12, 256, 2, "lanemerge12")
-    TK_LANEMERGE(8, 256, 1, "lanemerge8")
-    TK_LANEMERGE(4, 256, 0, "lanemerge4")
+    CK((launch_lanemerge<MAXLEN, THREADS, MINB>(bps[TKK_N_CLASSES - 1 - CLS], sm_count, d_data, T, queues + L.queues.off[CLS],     \
+                                                q_n + CLS, q_w + CLS, stream, tile_count, st)));
+    // MINB (the resident blocks the compiler plans registers for) is set from measurements: capping the 12- and
+    // 16-byte classes at 32 / 40 registers for more resident warps made them 1.4x slower
+    TK_LANEMERGE(96, 64, 1, 8, "lanemerge96")
+    TK_LANEMERGE(64, 128, 1, 7, "lanemerge64")
+    TK_LANEMERGE(48, 128, 1, 6, "lanemerge48")
+    TK_LANEMERGE(32, 256, 1, 5, "lanemerge32")
+    TK_LANEMERGE(24, 256, 1, 4, "lanemerge24")
+    TK_LANEMERGE(16, 256, 1, 3, "lanemerge16")
+    TK_LANEMERGE(12, 256, 6, 2, "lanemerge12")
+    TK_LANEMERGE(8, 256, 8, 1, "lanemerge8")
+    TK_LANEMERGE(4, 256, 6, 0, "lanemerge4")
 #undef TK_LANEMERGE
     if (timer) timer->mark(st, "emit");
     {
