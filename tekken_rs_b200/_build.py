@@ -7,7 +7,8 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libtekken_b200.so")
+# TEKKEN_B200_LIB: load (and build into) another file, e.g. an experimental build with TEKKEN_B200_NVCC_FLAGS="-DPT_MINB=5"
+LIB = os.environ.get("TEKKEN_B200_LIB") or os.path.join(HERE, "libtekken_b200.so")
 SOURCES = ["tk_kernels.cu", "tk_decode.cu", "tk_api.cu", "tk_host.cpp"]
 HEADERS = ["tk_common.h", "tk_host.h", "tk_pretok.h", "tk_device.cuh", "tk_kernels.h", "unicode_ranges.inc",
            os.path.join("..", "..", "include", "tekken_b200.h")]
@@ -33,6 +34,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
            "-Xcompiler", "-fPIC", "-shared", "-o", LIB + ".tmp"] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd[1:1] = os.environ.get("TEKKEN_B200_NVCC_FLAGS", "").split()
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.check_call(cmd)
