@@ -939,8 +939,26 @@ __global__ void __launch_bounds__(LK_T, LK_MINB) lookup_kernel(const uint8_t* __
     }
 }
 
+// the aligned 32-bit words that hold bytes [start, start + len) of the text (NW = MAXLEN / 4 + 1 of them cover any
+// piece of the class); words that do not overlap the piece are 0
+template <int NW>
+__device__ __forceinline__ void lm_load_words(const uint8_t* __restrict__ data, uint64_t n, uint64_t start, uint32_t len,
+                                              uint32_t (&w)[NW]) {
+    const uint64_t base = start & ~3ull, end = start + len;
+#pragma unroll
+    for (int k = 0; k < NW; ++k) {
+        const uint64_t a = base + 4u * k;
+        uint32_t v = 0;
+        if (len && a < end) {
+            if (a + 4u <= n) v = __ldg(reinterpret_cast<const uint32_t*>(data + a));
+            else for (uint32_t c = 0; c < 4u; ++c) if (a + c < n) v |= (uint32_t)__ldg(data + a + c) << (8u * c);   // last word of the text
+        }
+        w[k] = v;
+    }
+}
+
 template <int MAXLEN, int THREADS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) lanemerge_kernel(const uint8_t* __restrict__ data, TkDeviceTables T,
+__global__ void __launch_bounds__(THREADS, MINB) lanemerge_kernel(const uint8_t* __restrict__ data, uint64_t n, TkDeviceTables T,
                                                             const unsigned long long* __restrict__ queue,
                                                             const uint32_t* __restrict__ q_n, uint32_t* __restrict__ q_w,
                                                             uint32_t* __restrict__ stream, unsigned long long* __restrict__ tile_count) {
@@ -953,25 +971,72 @@ __global__ void __launch_bounds__(THREADS, MINB) lanemerge_kernel(const uint8_t*
     // short pieces cost about the same: warps stride over the queue.  Long ones vary more: warps take
     // the next 32 entries from a work counter.
     constexpr bool kDynamic = MAXLEN >= 12;
+    // Software pipeline over a warp's batches of 32 entries: the queue entries are read two batches ahead and, for
+    // the short classes (where the two dependent round trips entry -> text bytes are most of a piece's time), the
+    // aligned words of the text that hold the piece one batch ahead, in registers.
+    constexpr bool kWordsAhead = MAXLEN <= 16;
+    constexpr int NW = MAXLEN / 4 + 1;
     const uint32_t warps = gridDim.x * (THREADS / 32);
-    for (uint32_t k0 = (blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5)) * 32u;; k0 += warps * 32u) {
+    auto next_batch = [&](uint32_t prev) -> uint32_t {
+        if (prev >= total) return prev;                  // past the end: stay there
+        uint32_t k = prev + warps * 32u;
         if (kDynamic) {
-            if (lane == 0) k0 = atomicAdd(q_w, 32u);
-            k0 = __shfl_sync(0xFFFFFFFFu, k0, 0);
+            if (lane == 0) k = atomicAdd(q_w, 32u);
+            k = __shfl_sync(0xFFFFFFFFu, k, 0);
+        } else if (k < prev) k = 0xFFFFFFFFu;            // wrapped
+        return k;
+    };
+    auto entry_of = [&](uint32_t k0) -> unsigned long long {    // 0 = no piece (len field 0)
+        return (k0 < total && k0 + lane < total) ? queue[k0 + lane] : 0ull;
+    };
+    uint32_t k1;                                          // batch whose entry (and words) are loaded
+    if (kDynamic) {
+        k1 = 0;
+        if (lane == 0) k1 = atomicAdd(q_w, 32u);
+        k1 = __shfl_sync(0xFFFFFFFFu, k1, 0);
+    } else k1 = (blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5)) * 32u;
+    unsigned long long e1 = entry_of(k1);
+    uint32_t w1[kWordsAhead ? NW : 1];
+    if (kWordsAhead)
+        lm_load_words<kWordsAhead ? NW : 1>(data, n, e1 & ((1ull << QE_START_BITS) - 1ull),
+                                            (uint32_t)(e1 >> QE_START_BITS) & ((1u << QE_LEN_BITS) - 1u), w1);
+    uint32_t k2 = next_batch(k1);
+    unsigned long long e2 = entry_of(k2);
+    while (k1 < total) {
+        const unsigned long long e = e1;
+        uint32_t w[kWordsAhead ? NW : 1];
+        if (kWordsAhead) {
+#pragma unroll
+            for (int k = 0; k < NW; ++k) w[k] = w1[k];
         }
-        if (k0 >= total) break;
-        const uint32_t k = k0 + lane;
-        if (k < total) {
-            const unsigned long long e = queue[k];
-            const uint64_t start = e & ((1ull << QE_START_BITS) - 1ull);
-            const uint32_t len = (uint32_t)(e >> QE_START_BITS) & ((1u << QE_LEN_BITS) - 1u);
-            const uint8_t* b = data + start;
-            for (uint32_t i = 0; i < len; i += 4) {
-                uint32_t v[4];
+        // advance the pipeline before working on this batch
+        k1 = k2; e1 = e2;
+        if (kWordsAhead)
+            lm_load_words<kWordsAhead ? NW : 1>(data, n, e1 & ((1ull << QE_START_BITS) - 1ull),
+                                                (uint32_t)(e1 >> QE_START_BITS) & ((1u << QE_LEN_BITS) - 1u), w1);
+        k2 = next_batch(k2);
+        e2 = entry_of(k2);
+
+        const uint64_t start = e & ((1ull << QE_START_BITS) - 1ull);
+        const uint32_t len = (uint32_t)(e >> QE_START_BITS) & ((1u << QE_LEN_BITS) - 1u);
+        if (len) {
+            if (kWordsAhead) {
+                // realign (funnel shift by the start's offset in its word), then one byte per part
+                const uint32_t sh = ((uint32_t)start & 3u) * 8u;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) v[c] = i + c < len ? (uint32_t)__ldg(b + i + c) : 0u;
+                for (int k = 0; k < MAXLEN / 4; ++k) {
+                    const uint32_t r = __funnelshift_r(w[k], w[k + 1], sh);
+                    id[4 * k] = r & 0xFFu; id[4 * k + 1] = (r >> 8) & 0xFFu; id[4 * k + 2] = (r >> 16) & 0xFFu; id[4 * k + 3] = r >> 24;
+                }
+            } else {
+                const uint8_t* b = data + start;
+                for (uint32_t i = 0; i < len; i += 4) {
+                    uint32_t v[4];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) if (i + c < len) id[i + c] = v[c];
+                    for (int c = 0; c < 4; ++c) v[c] = i + c < len ? (uint32_t)__ldg(b + i + c) : 0u;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) if (i + c < len) id[i + c] = v[c];
+                }
             }
             // parts = single bytes; rank of every adjacent byte pair from the direct table.  Slots past the
             // piece get TK_INF: the merge loop scans all MAXLEN of them.
@@ -1296,7 +1361,7 @@ cudaError_t publish_counters(const void* d_ws, const EncodeLayout& L, uint32_t* 
 }
 
 template <int MAXLEN, int THREADS, int MINB>
-static cudaError_t launch_lanemerge(int blocks_per_sm, int sm_count, const uint8_t* d_data, const TkDeviceTables& T,
+static cudaError_t launch_lanemerge(int blocks_per_sm, int sm_count, const uint8_t* d_data, uint64_t n, const TkDeviceTables& T,
                                     const unsigned long long* queue, const uint32_t* q_n, uint32_t* q_w, uint32_t* stream,
                                     unsigned long long* tile_count, cudaStream_t st) {
     const size_t smem = (size_t)2 * THREADS * (MAXLEN + 1) * sizeof(uint32_t);
@@ -1307,7 +1372,7 @@ static cudaError_t launch_lanemerge(int blocks_per_sm, int sm_count, const uint8
         CK(cudaFuncSetAttribute(lanemerge_kernel<MAXLEN, THREADS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set.fetch_or(1ull << (dev & 63));
     }
-    lanemerge_kernel<MAXLEN, THREADS, MINB><<<(unsigned)(sm_count * blocks_per_sm), THREADS, smem, st>>>(d_data, T, queue, q_n, q_w, stream, tile_count);
+    lanemerge_kernel<MAXLEN, THREADS, MINB><<<(unsigned)(sm_count * blocks_per_sm), THREADS, smem, st>>>(d_data, n, T, queue, q_n, q_w, stream, tile_count);
     count_launch();
     return cudaSuccess;
 }
@@ -1415,7 +1480,7 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
     }();
 #define TK_LANEMERGE(MAXLEN, THREADS, MINB, CLS, NAME)                                                                            \
     if (timer) timer->mark(st, NAME);                                                                                             \
-    CK((launch_lanemerge<MAXLEN, THREADS, MINB>(bps[TKK_N_CLASSES - 1 - CLS], sm_count, d_data, T, queues + L.queues.off[CLS],     \
+    CK((launch_lanemerge<MAXLEN, THREADS, MINB>(bps[TKK_N_CLASSES - 1 - CLS], sm_count, d_data, n, T, queues + L.queues.off[CLS],     \
                                                 q_n + CLS, q_w + CLS, stream, tile_count, st)));
     // MINB (the resident blocks the compiler plans registers for) is set from measurements: capping the 12- and
     // 16-byte classes at 32 / 40 registers for more resident warps made them 1.4x slower
