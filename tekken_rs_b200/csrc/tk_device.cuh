@@ -183,10 +183,9 @@ __device__ __forceinline__ uint32_t tk_vocab_lookup_w32(const TkDeviceTables& T,
 }
 
 // ---- one lane, one piece of at most TK_LANE_MAX bytes ---------------------------------------------
-// Length classes of pieces (bytes):  <= TK_TILE_MAX  merged inside the text tile (merge_kernel);
-// <= TK_LANE_MAX  one lane per piece from a global queue (medmerge_kernel);  <= TK_MED_MAX  one warp per
+// Pieces by length (bytes):  <= TK_LANE_MAX  one lane per piece from a global queue of its length
+// class (lanemerge_kernel);  <= TK_MED_MAX  one warp per
 // piece;  beyond: one block per piece.  All run the same sequential definition.
-#define TK_TILE_MAX 32
 #define TK_LANE_MAX 96
 #define TK_LANE_DEAD 0xFFFFFFFEu
 

@@ -11,7 +11,7 @@
 //   K3  longmerge    exact BPE for those: warp per piece in shared memory, block per huge piece in rounds
 //   K2  lookup       one lane per piece: whole-piece vocabulary lookup -> rank stream (one word per byte
 //                    position); other pieces -> global queues by length class
-//   K2m lanemerge    x5: one lane per queued piece: exact byte_pair_merge
+//   K2m lanemerge    x9 (one launch per length class, 2..96 bytes): one lane per queued piece: exact byte_pair_merge
 //   K3s tilesum/scan/apply   prefix of the per-tile token counts -> first output position of every tile
 //   K4  emit         compaction of the rank stream: ids (+num_special), BOS/EOS, per-document offsets
 // Decode lives in tk_decode.cu.

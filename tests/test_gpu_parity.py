@@ -270,10 +270,11 @@ def test_config4_adversarial_long_pieces(gpu_tok, oracle):
 
 
 def test_config4_piece_length_sweep(gpu_tok, oracle):
-    # lengths around every escalation threshold (thread <= 64 B, warp <= 512 B, block beyond)
+    # every length across the lane-merge classes (one lane per piece <= 96 B, class limits 4, 8, 12, 16, 24, 32, 48,
+    # 64, 96) and around the later escalation thresholds (warp <= 512 B, block beyond)
     rng = random.Random(3)
     docs = []
-    for L in list(range(1, 80)) + [127, 128, 129, 255, 256, 257, 500, 511, 512, 513, 514, 600, 1023, 1024, 1025, 3000, 5000]:
+    for L in list(range(1, 132)) + [255, 256, 257, 500, 511, 512, 513, 514, 600, 1023, 1024, 1025, 3000, 5000]:
         docs.append("".join(rng.choice("abcdefghijklmnopqrstuvwxyz") for _ in range(L)).encode())
         docs.append(("é" * L).encode()[:L - (L % 2)] or b"e")
         docs.append(("." * L).encode())
