@@ -1147,10 +1147,11 @@ __global__ void __launch_bounds__(TS_T) tileapply_kernel(const unsigned long lon
 // =====================================================================================================
 // K4: emit.  The rank stream holds, for every byte position of the text, the rank of the token that
 // the reference emits there, EN_INVALID, or EN_LONGREF; emit is a compaction of it.  One block per
-// 4 KiB of text, 16 consecutive positions per thread: four 16-byte loads, count (ranks + the long
-// piece's tokens + BOS/EOS of the documents that start here), block scan, ids (+num_special) written
-// from the tile's first output position (known from K3s: no tile waits for another); per-document
-// token offsets.  Long pieces are copied from K3's pool by the whole block.
+// 4 KiB of text, one warp per 512 positions, one 32-byte window per warp iteration (lane = position in
+// the window): count (ranks + the long piece's tokens + BOS/EOS of the documents that start here) per
+// window, prefix over windows / warps, ids (+num_special) written from the tile's first output position
+// (known from K3s: no tile waits for another); per-document token offsets.  Long pieces are copied from
+// K3's pool by the whole block.
 // =====================================================================================================
 #define E3_T 256
 #define E3_PER 16
@@ -1176,8 +1177,58 @@ __device__ __forceinline__ uint32_t docs_from(const uint64_t* __restrict__ doc_o
 }
 
 #ifndef E3_MINB
-#define E3_MINB 6
+#define E3_MINB 5
 #endif
+// state of one lane's position in a window that needs the slow path (a document starts in it or a long piece)
+struct E3Slow {
+    uint64_t d;          // first document that starts at my position
+    uint32_t nd;         // documents that start at my position
+    uint32_t extra;      // BOS/EOS ids emitted before my position's own ids
+    uint32_t own;        // my position's own ids: 1 (a rank), the long piece's count, or 0
+};
+
+__device__ __forceinline__ E3Slow e3_slow_lane(uint32_t word, uint32_t wds, uint64_t w_first, uint32_t w_cnt, uint64_t win_pos,
+                                               uint32_t lane, const uint64_t* __restrict__ doc_off, uint64_t off_base,
+                                               uint64_t n_docs, uint32_t add_bos, uint32_t add_eos, uint32_t long_count) {
+    E3Slow r;
+    r.d = 0; r.nd = 0; r.extra = 0;
+    r.own = word < EN_LONGREF ? 1u : (word == EN_LONGREF ? long_count : 0u);
+    if ((wds >> lane) & 1u) {
+        // Usual case: one start position in the 32-byte window; then the window's document count (K0) says how
+        // many documents start there and no offset has to be read.  Several start positions in one window
+        // (documents shorter than 32 bytes): read offsets.
+        uint64_t d = w_first;
+        if ((wds & (wds - 1u)) == 0u) r.nd = w_cnt;
+        else {
+            uint32_t earlier = wds & ((1u << lane) - 1u);
+            while (earlier) {
+                const uint32_t b = (uint32_t)(__ffs((int)earlier) - 1);
+                earlier &= earlier - 1;
+                d += docs_from(doc_off, n_docs, win_pos + b + off_base, d);
+            }
+            r.nd = docs_from(doc_off, n_docs, win_pos + lane + off_base, d);
+        }
+        r.d = d;
+        r.extra = e3_specials(d, r.nd, n_docs, add_bos, add_eos);
+    }
+    return r;
+}
+
+__device__ __forceinline__ unsigned long long e3_warp_incl(unsigned long long v) {
+    const uint32_t lane = threadIdx.x & 31u;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long o = __shfl_up_sync(0xFFFFFFFFu, v, d);
+        if (lane >= (uint32_t)d) v += o;
+    }
+    return v;
+}
+
+// One block per 4 KiB tile, one warp per 512 positions, INTERLEAVED: in iteration k lane l holds position
+// 32 k + l of the warp's range (one 32-byte window per iteration).  The ids of a window are then consecutive
+// in the output, so a store instruction of the warp writes one contiguous run (two or three 32-byte sectors)
+// instead of one sector per lane, and the offset of a lane's id is a ballot + popcount.  Windows in which a
+// document starts or a long piece sits (warp-uniform test) take a slower path with per-lane counts.
 __global__ void __launch_bounds__(E3_T, E3_MINB) emit_kernel(const uint32_t* __restrict__ stream, const uint32_t* __restrict__ ds_mask,
                                                     const uint32_t* __restrict__ doc_first, const uint32_t* __restrict__ doc_cnt,
                                                     const uint32_t* __restrict__ long_of_word,
@@ -1186,110 +1237,124 @@ __global__ void __launch_bounds__(E3_T, E3_MINB) emit_kernel(const uint32_t* __r
                                                     uint32_t add_bos, uint32_t add_eos, uint32_t nsp, uint32_t bos_id, uint32_t eos_id,
                                                     uint32_t* __restrict__ out, uint64_t out_cap, uint64_t* __restrict__ tok_off,
                                                     const unsigned long long* __restrict__ tile_base) {
-    static_assert(E3_T * E3_PER == LK_TILE, "one emit block per lookup tile");
+    static_assert(E3_T * E3_PER == LK_TILE && E3_PER == 16, "one emit block per lookup tile, 16 windows per warp");
     __shared__ unsigned long long wsum[E3_T / 32];
     __shared__ E3Long longs[E3_LONGCAP];
     __shared__ uint32_t n_longs;
     const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
     const uint32_t tile = blockIdx.x;
     if (t == 0) n_longs = 0;
-    const uint64_t p0 = (uint64_t)tile * LK_TILE + (uint64_t)t * E3_PER;        // my first byte position
-    // ---- my 16 stream words ----
+    const uint64_t wp0 = (uint64_t)tile * LK_TILE + (uint64_t)warp * (32u * E3_PER);   // first position of my warp
+    const uint64_t word0 = wp0 >> 5;                                                    // its first mask word
+    // ---- loads: 16 coalesced rows of the stream; lanes 0..15 hold the window tables of window `lane` ----
     uint32_t w[E3_PER];
-    {
-        const uint4* src = reinterpret_cast<const uint4*>(stream + p0);
 #pragma unroll
-        for (int k = 0; k < E3_PER / 4; ++k) {
-            const uint4 v = __ldg(src + k);
-            w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
-        }
+    for (int k = 0; k < E3_PER; ++k) w[k] = __ldg(stream + wp0 + 32u * k + lane);
+    uint32_t wds_l = 0, wfirst_l = 0, wcnt_l = 0, wlong_l = 0;
+    if (lane < E3_PER) {
+        wds_l = ds_mask[word0 + lane];
+        wfirst_l = doc_first[word0 + lane];
+        wcnt_l = doc_cnt[word0 + lane];
+        wlong_l = long_of_word[word0 + lane];
     }
-    const uint32_t myds = (ds_mask[p0 >> 5] >> (p0 & 31u)) & 0xFFFFu;          // document starts among my positions
-    uint32_t valid = 0, longm = 0;
+    // ---- pass 1: ids per window (lane k keeps the count of window k) ----
+    // Windows by kind (bit k = window k): `single` = documents start at exactly one position and no long piece:
+    // the BOS/EOS count is a property of the window (lane k computes it from its own table entries) and shifts
+    // the lanes from the start position on; `general` = several start positions or a long piece (the long-piece
+    // table is only read for windows whose stream row marks one: it is not written past the end of the text).
+    uint32_t long_windows = 0;
+#pragma unroll
+    for (int k = 0; k < E3_PER; ++k)
+        if (__ballot_sync(0xFFFFFFFFu, w[k] == EN_LONGREF)) long_windows |= 1u << k;
+    const uint32_t single_windows = __ballot_sync(0xFFFFFFFFu, wds_l != 0u && (wds_l & (wds_l - 1u)) == 0u) & ~long_windows;
+    const uint32_t general_windows = (__ballot_sync(0xFFFFFFFFu, wds_l != 0u) | long_windows) & ~single_windows;
+    const uint32_t extra_l = ((single_windows >> lane) & 1u) ? e3_specials(wfirst_l, wcnt_l, n_docs, add_bos, add_eos) : 0u;
+    unsigned long long cnt_l = 0;
 #pragma unroll
     for (int k = 0; k < E3_PER; ++k) {
-        valid |= (w[k] < EN_LONGREF ? 1u : 0u) << k;
-        longm |= (w[k] == EN_LONGREF ? 1u : 0u) << k;
+        const uint32_t c = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, w[k] < EN_LONGREF));
+        if (lane == (uint32_t)k) cnt_l = c;
     }
-    // ---- tokens that start at my positions ----
-    unsigned long long count = (unsigned long long)__popc(valid);
-    TkkLongRec lr;
-    lr.count = 0; lr.tok_base = 0;
-    if (longm) {                                   // at most one: a long piece has more than 64 bytes
-        lr = recs[long_of_word[p0 >> 5] - 1];
-        count += lr.count;
+    cnt_l += extra_l;
+    // general windows: one compact loop (not unrolled: the kernel has to stay small for the instruction cache), the
+    // window's stream row is read again (an L1 hit)
+#pragma unroll 1
+    for (uint32_t sw = general_windows; sw; sw &= sw - 1) {
+        const uint32_t k = (uint32_t)(__ffs((int)sw) - 1);
+        const uint32_t wk = __ldg(stream + wp0 + 32u * k + lane);
+        const uint32_t wds = __shfl_sync(0xFFFFFFFFu, wds_l, k);
+        const uint32_t wl = ((long_windows >> k) & 1u) ? __shfl_sync(0xFFFFFFFFu, wlong_l, k) : 0u;
+        const uint32_t lc = wl ? recs[wl - 1].count : 0u;
+        const E3Slow sl = e3_slow_lane(wk, wds, __shfl_sync(0xFFFFFFFFu, wfirst_l, k), __shfl_sync(0xFFFFFFFFu, wcnt_l, k),
+                                       wp0 + 32u * k, lane, doc_off, off_base, n_docs, add_bos, add_eos, lc);
+        unsigned long long mine = (unsigned long long)sl.extra + sl.own;
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, d);
+        if (lane == k) cnt_l = mine;
     }
-    // Documents that start at my positions.  Usual case: one start position in the 32-byte window;
-    // then the window's document count (K0) says how many documents start there and no offset has to
-    // be read.  Several start positions in one window (documents shorter than 32 bytes): read offsets.
-    uint64_t d_first = 0;
-    uint32_t nd_single = 0;                        // != 0: all nd_single documents of the window start at my one position
-    if (myds) {
-        const uint32_t wds = ds_mask[p0 >> 5];
-        d_first = doc_first[p0 >> 5];
-        if ((wds & (wds - 1u)) == 0u) {
-            nd_single = doc_cnt[p0 >> 5];
-            count += e3_specials(d_first, nd_single, n_docs, add_bos, add_eos);
-        } else {
-            uint32_t earlier = wds & ((1u << (p0 & 31u)) - 1u);                 // document starts earlier in the same window
-            while (earlier) {
-                const uint32_t b = (uint32_t)(__ffs((int)earlier) - 1);
-                earlier &= earlier - 1;
-                d_first += docs_from(doc_off, n_docs, (p0 & ~31ull) + b + off_base, d_first);
-            }
-            uint64_t d = d_first;
-            uint32_t m = myds;
-            while (m) {
-                const uint32_t b = (uint32_t)(__ffs((int)m) - 1);
-                m &= m - 1;
-                const uint32_t k = docs_from(doc_off, n_docs, p0 + b + off_base, d);
-                count += e3_specials(d, k, n_docs, add_bos, add_eos);
-                d += k;
+    // ---- exclusive prefix over the windows of the warp, then over the warps of the block ----
+    const unsigned long long inc = e3_warp_incl(cnt_l);
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    unsigned long long warp_out = tile_base[tile];
+    for (uint32_t x = 0; x < warp; ++x) warp_out += wsum[x];
+    const unsigned long long excl_l = warp_out + inc - cnt_l;                            // lane k: first output index of window k
+    // ---- pass 2: write ----
+    const uint32_t le_mask = (2u << lane) - 1u;                                          // lanes 0..lane
+#pragma unroll
+    for (int k = 0; k < E3_PER; ++k) {
+        const unsigned long long base = __shfl_sync(0xFFFFFFFFu, excl_l, k);
+        const uint32_t ex = __shfl_sync(0xFFFFFFFFu, extra_l, k), wds = __shfl_sync(0xFFFFFFFFu, wds_l, k);
+        const bool valid = w[k] < EN_LONGREF;
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, valid);
+        if (valid && !((general_windows >> k) & 1u)) {
+            // in a single window the BOS/EOS ids come before the id of the start position itself
+            const unsigned long long o = base + (unsigned long long)__popc(m & (le_mask >> 1)) + ((wds & le_mask) ? ex : 0u);
+            if (o < out_cap) out[o] = w[k] + nsp;
+        }
+    }
+    // single windows: the lane of the start position writes the BOS/EOS ids and the documents' offsets
+#pragma unroll 1
+    for (uint32_t sw = single_windows; sw; sw &= sw - 1) {
+        const uint32_t k = (uint32_t)(__ffs((int)sw) - 1);
+        const unsigned long long base = __shfl_sync(0xFFFFFFFFu, excl_l, k);
+        const uint32_t wds = __shfl_sync(0xFFFFFFFFu, wds_l, k);
+        const uint32_t nd = __shfl_sync(0xFFFFFFFFu, wcnt_l, k);
+        const uint64_t d0 = __shfl_sync(0xFFFFFFFFu, wfirst_l, k);
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, __ldg(stream + wp0 + 32u * k + lane) < EN_LONGREF);
+        if ((wds >> lane) & 1u) {
+            unsigned long long o = base + (unsigned long long)__popc(m & (le_mask >> 1));
+            for (uint64_t x = d0; x < d0 + nd; ++x) {
+                if (x > 0 && add_eos) { if (o < out_cap) out[o] = eos_id; ++o; }
+                tok_off[x] = o;
+                if (x < n_docs && add_bos) { if (o < out_cap) out[o] = bos_id; ++o; }
             }
         }
     }
-    // ---- block scan ----
-    unsigned long long inc = count;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        unsigned long long o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-        if (lane >= (uint32_t)d) inc += o;
-    }
-    if (lane == 31) wsum[warp] = inc;
-    __syncthreads();
-    unsigned long long o = tile_base[tile] + inc - count;
-    for (uint32_t x = 0; x < warp; ++x) o += wsum[x];
-    // ---- write ----
-    if (!myds && !longm) {
-#pragma unroll
-        for (int k = 0; k < E3_PER; ++k)
-            if ((valid >> k) & 1u) { if (o < out_cap) out[o] = w[k] + nsp; ++o; }
-    } else {
-        // a document starts or a long piece sits among my positions (about one thread in sixty): a compact
-        // loop over the positions that emit something, re-reading their stream words (L1 hits), so that this
-        // path stays a few hundred bytes of code instead of sixteen unrolled copies
-        uint64_t d = d_first;
-        uint32_t todo = valid | myds | longm;
 #pragma unroll 1
-        while (todo) {
-            const uint32_t k = (uint32_t)(__ffs((int)todo) - 1);
-            todo &= todo - 1;
-            if ((myds >> k) & 1u) {
-                const uint32_t nd = nd_single ? nd_single : docs_from(doc_off, n_docs, p0 + k + off_base, d);
-                for (uint64_t x = d; x < d + nd; ++x) {
-                    if (x > 0 && add_eos) { if (o < out_cap) out[o] = eos_id; ++o; }
-                    tok_off[x] = o;
-                    if (x < n_docs && add_bos) { if (o < out_cap) out[o] = bos_id; ++o; }
-                }
-                d += nd;
-            }
-            if ((valid >> k) & 1u) { if (o < out_cap) out[o] = __ldg(stream + p0 + k) + nsp; ++o; }
-            else if ((longm >> k) & 1u) {
-                E3Long L;
-                L.src = lr.tok_base; L.dst = o; L.count = lr.count; L.pad = 0;
-                longs[atomicAdd(&n_longs, 1u)] = L;
-                o += lr.count;
-            }
+    for (uint32_t sw = general_windows; sw; sw &= sw - 1) {
+        const uint32_t k = (uint32_t)(__ffs((int)sw) - 1);
+        const unsigned long long base = __shfl_sync(0xFFFFFFFFu, excl_l, k);
+        const uint32_t wk = __ldg(stream + wp0 + 32u * k + lane);
+        const uint32_t wds = __shfl_sync(0xFFFFFFFFu, wds_l, k);
+        const uint32_t wl = ((long_windows >> k) & 1u) ? __shfl_sync(0xFFFFFFFFu, wlong_l, k) : 0u;
+        TkkLongRec lr;
+        lr.count = 0; lr.tok_base = 0;
+        if (wl) lr = recs[wl - 1];
+        const E3Slow sl = e3_slow_lane(wk, wds, __shfl_sync(0xFFFFFFFFu, wfirst_l, k), __shfl_sync(0xFFFFFFFFu, wcnt_l, k),
+                                       wp0 + 32u * k, lane, doc_off, off_base, n_docs, add_bos, add_eos, lr.count);
+        const unsigned long long mine = (unsigned long long)sl.extra + sl.own;
+        unsigned long long o = base + e3_warp_incl(mine) - mine;
+        for (uint64_t x = sl.d; x < sl.d + sl.nd; ++x) {
+            if (x > 0 && add_eos) { if (o < out_cap) out[o] = eos_id; ++o; }
+            tok_off[x] = o;
+            if (x < n_docs && add_bos) { if (o < out_cap) out[o] = bos_id; ++o; }
+        }
+        if (wk < EN_LONGREF) { if (o < out_cap) out[o] = wk + nsp; }
+        else if (wk == EN_LONGREF) {
+            E3Long L;
+            L.src = lr.tok_base; L.dst = o; L.count = lr.count; L.pad = 0;
+            longs[atomicAdd(&n_longs, 1u)] = L;
         }
     }
     __syncthreads();

@@ -62,7 +62,8 @@ def full(path, traffic_out=None):
             "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
             "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
             "launch__registers_per_thread", "smsp__thread_inst_executed_per_inst_executed.ratio",
-            "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct"]
+            "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+            "lts__throughput.avg.pct_of_peak_sustained_elapsed"]
     units = rows[1]
     print("kernel | " + " | ".join("%s [%s]" % (c, units[idx[c]]) for c in cols if c in idx))
     traffic = {}
