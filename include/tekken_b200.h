@@ -120,7 +120,9 @@ int tk_encode(const tk_tokenizer *t, const uint8_t *utf8, size_t len, int add_bo
 
 /* New: encode_batch.  Documents are data[doc_off[d] .. doc_off[d+1]) (n_docs+1 offsets,
    doc_off[0] == 0).  ids of all documents are returned back to back in *tokens; *tok_off
-   gets n_docs+1 offsets into it.  Host buffers in, pinned host buffers out. */
+   gets n_docs+1 offsets into it.  Host buffers in, pinned host buffers out.  The batch may be
+   of any size (it is streamed through the device in chunks cut at document boundaries); one
+   document is limited to 8 GiB. */
 int tk_encode_batch(const tk_tokenizer *t, const uint8_t *data, const uint64_t *doc_off,
                     size_t n_docs, int add_bos, int add_eos, uint32_t **tokens, uint64_t **tok_off);
 
@@ -128,7 +130,9 @@ int tk_encode_batch(const tk_tokenizer *t, const uint8_t *data, const uint64_t *
    cudaStream_t (NULL = default stream).  d_tokens must hold tokens_capacity ids
    (total_bytes + 2*n_docs always suffices); d_tok_off holds n_docs+1 offsets.  The call
    synchronises the stream before returning; *n_tokens is the total id count.  On
-   TK_ERR_BUFFER_TOO_SMALL *n_tokens is the capacity that would have been enough. */
+   TK_ERR_BUFFER_TOO_SMALL *n_tokens is the capacity that would have been enough.  d_data must
+   be 16-byte aligned; total_bytes < 8 GiB and n_docs < 2^32 - 2 per call (TK_ERR_INVALID_ARGUMENT
+   otherwise: shard the batch, tk_shard_plan). */
 int tk_encode_batch_device(const tk_tokenizer *t, const uint8_t *d_data, const uint64_t *d_doc_off,
                            size_t n_docs, uint64_t total_bytes, int add_bos, int add_eos,
                            uint32_t *d_tokens, uint64_t tokens_capacity, uint64_t *d_tok_off,

@@ -429,7 +429,9 @@ static int encode_issue(tk_tokenizer* t, tk_tokenizer::EncSlot& s, const uint8_t
                         size_t n_docs, uint64_t total, int add_bos, int add_eos, uint32_t* d_tokens, uint64_t cap,
                         uint64_t* d_tok_off, cudaStream_t st, bool timing) {
     if (((uintptr_t)d_data & 15u) != 0 && total) return fail(TK_ERR_INVALID_ARGUMENT, "device text pointer must be 16-byte aligned");
-    if (total >= (1ull << 40)) return fail(TK_ERR_INVALID_ARGUMENT, "batch too large; shard it (limit 1 TiB per call)");
+    // per-class piece counters and queue indices are 32-bit: a class of 2-byte pieces overflows them at 8 GiB of text
+    // (the workspace, about 16 B per text byte, does not fit one GPU beyond that anyway)
+    if (total >= (1ull << 33)) return fail(TK_ERR_INVALID_ARGUMENT, "batch too large; shard it (limit 8 GiB of text per device call)");
     if ((uint64_t)n_docs >= 0xFFFFFFFEull) return fail(TK_ERR_INVALID_ARGUMENT, "too many documents in one call; shard the batch");
     size_t ws_bytes = tkk::encode_workspace_bytes(total, n_docs, &s.L);
     CUDA_OR_FAIL(s.ws.ensure(ws_bytes));
