@@ -187,6 +187,32 @@ def test_many_tiny_and_empty_documents(gpu_tok, oracle):
     assert np.array_equal(boff, off)
 
 
+def test_document_starts_at_every_window_position(gpu_tok, oracle):
+    # the emit kernel works on 32-byte windows (one lane per position), 512-byte warp ranges and 4 KiB tiles: put
+    # document starts -- single ones, several per window, empty documents, starts next to pieces longer than
+    # 96 bytes -- at every position of those units, with every BOS/EOS combination
+    rng = random.Random(77)
+    texts = []
+    for rep in range(3):
+        for gap in list(range(0, 70)) + [95, 96, 97, 127, 128, 129, 480, 511, 512, 513, 4000, 4095, 4096, 4097]:
+            filler = "".join(rng.choice("abc de.\n") for _ in range(gap)).encode()
+            texts.append(filler)
+            kind = rng.randrange(5)
+            if kind == 0:
+                texts += [b"", b""]                                   # empty documents at this position
+            elif kind == 1:
+                texts += [b"x", b"", b"yz"]                           # several starts in one window
+            elif kind == 2:
+                texts.append(("q" * rng.randint(97, 300)).encode())   # a long piece right at a document start
+            elif kind == 3:
+                texts.append(("é" * rng.randint(20, 60)).encode())    # a merge-class piece right at a document start
+    data, off = _pack(texts)
+    for bos, eos in ((True, True), (True, False), (False, True), (False, False)):
+        ids, toff = assert_same_batch(gpu_tok, oracle, data, off, bos, eos)
+    raw, boff = gpu_tok.decode_batch_np(ids, toff, SpecialTokenPolicy.Ignore)
+    assert np.array_equal(boff, off) and raw.tobytes() == data.tobytes()
+
+
 # ------------------------------------------------------------------------------------------ the five configs
 
 def test_config1_english_1mib(gpu_tok, oracle):
