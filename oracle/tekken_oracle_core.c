@@ -33,13 +33,17 @@
 #include <string.h>
 
 #include "unicode_ranges.h"
+#include "unicode_subclasses.h"
 
 #define ORC_INF 0xFFFFFFFFu
 
 enum { CL_O = 0, CL_L = 1, CL_N = 2, CL_R = 3, CL_W = 4 };
 
 static uint8_t g_cls[0x110000];
+static uint8_t g_sub[0x110000];      /* sub-class for the pattern stored in tekken.json: SUB_* */
 static int g_cls_ready = 0;
+
+enum { SUB_NONE = 0, SUB_UPPER = 1, SUB_LOWER = 2, SUB_BOTH = 3, SUB_MARK = 4 };
 
 static void fill_ranges(const uint32_t (*r)[2], int n, uint8_t v) {
     for (int i = 0; i < n; i++)
@@ -54,6 +58,13 @@ static void init_classes(void) {
     fill_ranges(UNI_S_RANGES, UNI_S_COUNT, CL_W);
     g_cls['\r'] = CL_R;
     g_cls['\n'] = CL_R;
+    memset(g_sub, SUB_NONE, sizeof g_sub);
+#define FILL_SUB(T, v) for (size_t i = 0; i < sizeof(T) / sizeof(T[0]); i++) for (uint32_t c = T[i][0]; c <= T[i][1]; c++) g_sub[c] = v
+    FILL_SUB(ORC_SUB_UPPER, SUB_UPPER);
+    FILL_SUB(ORC_SUB_LOWER, SUB_LOWER);
+    FILL_SUB(ORC_SUB_BOTH, SUB_BOTH);
+    FILL_SUB(ORC_SUB_MARK, SUB_MARK);
+#undef FILL_SUB
     g_cls_ready = 1;
 }
 
@@ -300,6 +311,125 @@ int64_t orc_split(const uint8_t *text, uint64_t n, uint64_t *ends) {
     return k;
 }
 
+/* ------------------------------------------------------------------ the pattern stored in tekken.json
+ *
+ * GROUNDWORK for SURVEY section 8(f) rank 1 ("config-driven pattern").  The reference IGNORES config.pattern
+ * (src/tekkenizer.rs:74,123); Mistral's own tokenizer (mistral_common) compiles it:
+ *   [^\r\n\p{L}\p{N}]?[\p{Lu}\p{Lt}\p{Lm}\p{Lo}\p{M}]*[\p{Ll}\p{Lm}\p{Lo}\p{M}]+|
+ *   [^\r\n\p{L}\p{N}]?[\p{Lu}\p{Lt}\p{Lm}\p{Lo}\p{M}]+[\p{Ll}\p{Lm}\p{Lo}\p{M}]*|
+ *   \p{N}| ?[^\s\p{L}\p{N}]+[\r\n/]*|\s*[\r\n]+|\s+(?!\S)|\s+
+ * Restated here as a literal matcher with the backtracking outcomes written out, pinned against the engine in
+ * tests/test_oracle.py.  U = {Lu,Lt,Lm,Lo,M} ("upper or caseless"), L = {Ll,Lm,Lo,M} ("lower or caseless");
+ * Lm, Lo and M are in both sets, and M is neither \p{L} nor \p{N} (it can be a prefix or punctuation char).
+ */
+static inline int in_U(int sub) { return sub == SUB_UPPER || sub == SUB_BOTH || sub == SUB_MARK; }
+static inline int in_L(int sub) { return sub == SUB_LOWER || sub == SUB_BOTH || sub == SUB_MARK; }
+
+/* U*L+ at s: end of the match, or 0.  Greedy U* takes the whole U run; L+ then takes the L run that follows.  If
+   nothing in L follows, U* gives characters back until the one it gives back is in L (Lm, Lo or M): the match
+   ends after the LAST character of the U run that is in both sets (what follows it in the run is Lu/Lt). */
+static const uint8_t *match_UL(const uint8_t *s, const uint8_t *end) {
+    const uint8_t *q = s, *last_both_end = 0;
+    while (q < end) {
+        uint32_t c;
+        int l = utf8_decode(q, end, &c);
+        int sub = g_sub[c];
+        if (!in_U(sub)) break;
+        q += l;
+        if (in_L(sub)) last_both_end = q;
+    }
+    const uint8_t *r = q;
+    while (r < end) {
+        uint32_t c;
+        int l = utf8_decode(r, end, &c);
+        if (!in_L(g_sub[c])) break;
+        r += l;
+    }
+    if (r > q) return r;
+    return last_both_end;
+}
+
+/* U+L* at s: end of the match, or 0 */
+static const uint8_t *match_UpL(const uint8_t *s, const uint8_t *end) {
+    const uint8_t *q = s;
+    while (q < end) {
+        uint32_t c;
+        int l = utf8_decode(q, end, &c);
+        if (!in_U(g_sub[c])) break;
+        q += l;
+    }
+    if (q == s) return 0;
+    while (q < end) {
+        uint32_t c;
+        int l = utf8_decode(q, end, &c);
+        if (!in_L(g_sub[c])) break;
+        q += l;
+    }
+    return q;
+}
+
+static size_t match_at_config(const uint8_t *q, const uint8_t *end) {
+    uint32_t c0, c1 = 0;
+    int k0, k1 = -1;
+    int l0 = char_at(q, end, &c0, &k0), l1 = 0;
+    if (q + l0 < end) l1 = char_at(q + l0, end, &c1, &k1);
+    const int prefix_ok = k0 != CL_R && k0 != CL_L && k0 != CL_N;          /* [^\r\n\p{L}\p{N}] */
+    const uint8_t *e;
+    /* B1: P?U*L+  (greedy optional prefix first, then without it) */
+    if (prefix_ok && l1 && (e = match_UL(q + l0, end)) != 0) return (size_t)(e - q);
+    if ((e = match_UL(q, end)) != 0) return (size_t)(e - q);
+    /* B2: P?U+L* */
+    if (prefix_ok && l1 && (e = match_UpL(q + l0, end)) != 0) return (size_t)(e - q);
+    if ((e = match_UpL(q, end)) != 0) return (size_t)(e - q);
+    /* B3: \p{N} */
+    if (k0 == CL_N) return (size_t)l0;
+    /* B4:  ?[^\s\p{L}\p{N}]+[\r\n/]* */
+    {
+        const uint8_t *s = 0;
+        if (c0 == ' ' && k1 == CL_O) s = q + l0;
+        else if (k0 == CL_O) s = q;
+        if (s) {
+            while (s < end) {
+                uint32_t c; int k;
+                int l = char_at(s, end, &c, &k);
+                if (k != CL_O) break;
+                s += l;
+            }
+            while (s < end && (*s == '\r' || *s == '\n' || *s == '/')) s++;
+            return (size_t)(s - q);
+        }
+    }
+    /* whitespace: B5 \s*[\r\n]+, B6 \s+(?!\S), B7 \s+ -- as A5..A7 above */
+    {
+        const uint8_t *e2 = q, *last_r_end = 0, *last_char = q;
+        while (e2 < end) {
+            uint32_t c; int k;
+            int l = char_at(e2, end, &c, &k);
+            if (!is_ws(k)) break;
+            last_char = e2;
+            e2 += l;
+            if (k == CL_R) last_r_end = e2;
+        }
+        if (last_r_end) return (size_t)(last_r_end - q);
+        if (e2 == end) return (size_t)(e2 - q);
+        if (last_char > q) return (size_t)(last_char - q);
+        return (size_t)(e2 - q);
+    }
+}
+
+/* orc_split / orc_encode for the stored pattern (same contracts) */
+int64_t orc_split_config(const uint8_t *text, uint64_t n, uint64_t *ends) {
+    init_classes();
+    if (!orc_utf8_valid(text, n)) return -1;
+    const uint8_t *q = text, *end = text + n;
+    int64_t k = 0;
+    while (q < end) {
+        q += match_at_config(q, end);
+        ends[k++] = (uint64_t)(q - text);
+    }
+    return k;
+}
+
 /* ------------------------------------------------------------------ byte pair merge */
 
 typedef struct { uint32_t start; uint32_t rank; } part_t;
@@ -448,6 +578,25 @@ int64_t orc_encode(const orc_t *o, const uint8_t *text, uint64_t n, int add_bos,
     const uint8_t *q = text, *end = text + n;
     while (q < end) {
         size_t len = match_at(q, end);
+        uint64_t c = orc_encode_piece(o, q, len, out + k, mode);
+        for (uint64_t j = 0; j < c; j++) out[k + j] += o->num_special;
+        k += (int64_t)c;
+        q += len;
+    }
+    if (add_eos) { if (o->eos_id < 0) return -2; out[k++] = (uint32_t)o->eos_id; }
+    return k;
+}
+
+/* orc_encode with the pattern stored in tekken.json (see match_at_config) */
+int64_t orc_encode_config(const orc_t *o, const uint8_t *text, uint64_t n, int add_bos, int add_eos,
+                          uint32_t *out, int mode) {
+    init_classes();
+    if (!orc_utf8_valid(text, n)) return -1;
+    int64_t k = 0;
+    if (add_bos) { if (o->bos_id < 0) return -2; out[k++] = (uint32_t)o->bos_id; }
+    const uint8_t *q = text, *end = text + n;
+    while (q < end) {
+        size_t len = match_at_config(q, end);
         uint64_t c = orc_encode_piece(o, q, len, out + k, mode);
         for (uint64_t j = 0; j < c; j++) out[k + j] += o->num_special;
         k += (int64_t)c;

@@ -80,6 +80,54 @@ def test_live_engine_every_unicode_scalar_value(oracle):
         assert oracle.encode(t, False, False) == [x + 1000 for x in r], repr(t[:40])
 
 
+# ---- groundwork for SURVEY 8(f) rank 1: the pattern stored in tekken.json (the reference ignores it) ----
+
+def test_config_pattern_fixtures(oracle):
+    import json
+    import os
+    path = os.path.join(os.path.dirname(__file__), "golden", "config_pattern_fixtures.json")
+    fx = json.load(open(path))
+    for c in fx["cases"]:
+        assert oracle.encode_config(c["text"], False, False) == c["ids"], repr(c["text"])
+        assert b"".join(oracle.split_config(c["text"])) == c["text"].encode("utf-8")
+
+
+def test_config_pattern_live_engine_fuzz(oracle, tekken_json):
+    tiktoken = pytest.importorskip("tiktoken")
+    import json
+    from oracle.tools.make_config_pattern_fixtures import ALPHABET
+    pattern = json.load(open(tekken_json))["config"]["pattern"]
+    enc = tiktoken.Encoding("tekken-config-pattern", pat_str=pattern,
+                            mergeable_ranks={b: r for r, b in enumerate(oracle.ranks)}, special_tokens={})
+    rng = random.Random(5)
+    texts = ["".join(rng.choice(ALPHABET) for _ in range(rng.choice([1, 2, 3, 5, 9, 17, 40, 90]))) for _ in range(8000)]
+    ref = enc.encode_ordinary_batch(texts, num_threads=4)
+    for t, r in zip(texts, ref):
+        assert oracle.encode_config(t, False, False) == [x + 1000 for x in r], repr(t)
+
+
+def test_config_pattern_every_unicode_scalar_value(oracle, tekken_json):
+    # pins the sub-class tables (Lu|Lt, Ll, Lm|Lo, M) to the engine for EVERY scalar value: each one after an upper-case
+    # and before a lower-case letter, the other way round, alone after a space, after a digit and before a slash
+    tiktoken = pytest.importorskip("tiktoken")
+    import json
+    pattern = json.load(open(tekken_json))["config"]["pattern"]
+    enc = tiktoken.Encoding("tekken-config-pattern", pat_str=pattern,
+                            mergeable_ranks={b: r for r, b in enumerate(oracle.ranks)}, special_tokens={})
+    cps = [c for c in range(0x110000) if not 0xD800 <= c <= 0xDFFF]
+    texts = ["".join("A%sb %sB %s 1%s/\n" % (chr(c), chr(c), chr(c), chr(c)) for c in cps[i:i + 64]) for i in range(0, len(cps), 64)]
+    ref = enc.encode_ordinary_batch(texts, num_threads=8)
+    for t, r in zip(texts, ref):
+        assert oracle.encode_config(t, False, False) == [x + 1000 for x in r], repr(t[:40])
+
+
+def test_config_pattern_differs_from_reference_pattern(oracle):
+    # the hard-coded pattern splits the Devanagari matra off, the stored pattern keeps it
+    assert oracle.encode("\u0915\u093e", False, False) == [2622, 1658]
+    assert oracle.encode_config("\u0915\u093e", False, False) == [15729]
+    assert [p.decode() for p in oracle.split_config("HelloWORLD helloWorld 123")] == ["Hello", "WORLD", " hello", "World", " ", "1", "2", "3"]
+
+
 def test_split_examples(oracle):
     # SURVEY.md section 3.2 consequences
     def sp(s):
