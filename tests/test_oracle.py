@@ -121,6 +121,14 @@ def test_config_pattern_every_unicode_scalar_value(oracle, tekken_json):
         assert oracle.encode_config(t, False, False) == [x + 1000 for x in r], repr(t[:40])
 
 
+def test_config_pattern_run_predicate(oracle):
+    # the run-based "is a piece start" predicate a GPU split for the stored pattern would use (research prototype,
+    # oracle/research/): no mismatch against the sequential restatement
+    from oracle.research import config_pattern_positionwise as pw
+    assert pw.check(20000, seed=7) == 0
+    assert pw.check(2000, seed=8, lengths=(60, 200)) == 0
+
+
 def test_config_pattern_differs_from_reference_pattern(oracle):
     # the hard-coded pattern splits the Devanagari matra off, the stored pattern keeps it
     assert oracle.encode("\u0915\u093e", False, False) == [2622, 1658]
