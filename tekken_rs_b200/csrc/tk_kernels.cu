@@ -1263,9 +1263,16 @@ __global__ void __launch_bounds__(E3_T, E3_MINB) emit_kernel(const uint32_t* __r
     // the lanes from the start position on; `general` = several start positions or a long piece (the long-piece
     // table is only read for windows whose stream row marks one: it is not written past the end of the text).
     uint32_t long_windows = 0;
+    {
+        bool mine = false;
 #pragma unroll
-    for (int k = 0; k < E3_PER; ++k)
-        if (__ballot_sync(0xFFFFFFFFu, w[k] == EN_LONGREF)) long_windows |= 1u << k;
+        for (int k = 0; k < E3_PER; ++k) mine |= w[k] == EN_LONGREF;
+        if (__any_sync(0xFFFFFFFFu, mine)) {                     // rare: a long piece starts in my warp's range
+#pragma unroll
+            for (int k = 0; k < E3_PER; ++k)
+                if (__ballot_sync(0xFFFFFFFFu, w[k] == EN_LONGREF)) long_windows |= 1u << k;
+        }
+    }
     const uint32_t single_windows = __ballot_sync(0xFFFFFFFFu, wds_l != 0u && (wds_l & (wds_l - 1u)) == 0u) & ~long_windows;
     const uint32_t general_windows = (__ballot_sync(0xFFFFFFFFu, wds_l != 0u) | long_windows) & ~single_windows;
     const uint32_t extra_l = ((single_windows >> lane) & 1u) ? e3_specials(wfirst_l, wcnt_l, n_docs, add_bos, add_eos) : 0u;
@@ -1301,6 +1308,21 @@ __global__ void __launch_bounds__(E3_T, E3_MINB) emit_kernel(const uint32_t* __r
     const unsigned long long excl_l = warp_out + inc - cnt_l;                            // lane k: first output index of window k
     // ---- pass 2: write ----
     const uint32_t le_mask = (2u << lane) - 1u;                                          // lanes 0..lane
+    if ((single_windows | general_windows) == 0u) {
+        // no document start and no long piece in my warp's 512 positions (warp-uniform, the usual case): a window adds
+        // at most 32 ids, so offsets inside the warp's range fit 32 bits and need one shuffle per window
+        const uint32_t rel_l = (uint32_t)(inc - cnt_l);
+#pragma unroll
+        for (int k = 0; k < E3_PER; ++k) {
+            const uint32_t rel = __shfl_sync(0xFFFFFFFFu, rel_l, k);
+            const bool valid = w[k] < EN_LONGREF;
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, valid);
+            if (valid) {
+                const unsigned long long o = warp_out + (rel + (uint32_t)__popc(m & (le_mask >> 1)));
+                if (o < out_cap) out[o] = w[k] + nsp;
+            }
+        }
+    } else {
 #pragma unroll
     for (int k = 0; k < E3_PER; ++k) {
         const unsigned long long base = __shfl_sync(0xFFFFFFFFu, excl_l, k);
@@ -1357,6 +1379,7 @@ __global__ void __launch_bounds__(E3_T, E3_MINB) emit_kernel(const uint32_t* __r
             longs[atomicAdd(&n_longs, 1u)] = L;
         }
     }
+    }   // warps with document starts or long pieces
     __syncthreads();
     const uint32_t nl = n_longs;
     for (uint32_t l = 0; l < nl; ++l) {
