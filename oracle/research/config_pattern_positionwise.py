@@ -195,3 +195,49 @@ def check(n_strings=200000, seed=1, lengths=(1, 2, 3, 4, 5, 7, 9, 14, 25)):
 
 if __name__ == "__main__":
     sys.exit(1 if check(int(sys.argv[1]) if len(sys.argv) > 1 else 200000) else 0)
+
+
+def safe_starts(text, K):
+    """Positions that are piece starts by a purely LOCAL rule (own class + previous class).  A first GPU split for the
+    stored pattern can cut the text at these and let one lane run the sequential matcher over each segment."""
+    n = len(K)
+    out = []
+    for i in range(n):
+        k = K[i]
+        p = K[i - 1] if i else None
+        if i == 0:
+            out.append(i)
+        elif k == "N" or p == "N":
+            out.append(i)                               # every digit is a piece; whatever follows a digit starts one
+        elif k == "W" and p not in "RW":
+            out.append(i)                               # a whitespace run that does not begin with CR/LF starts a piece
+        elif k == "O" and p in "UlC":
+            out.append(i)                               # punctuation after a letter is never absorbed
+    return out
+
+
+def check_safe(n_strings=100000, seed=3):
+    from oracle import tekken_oracle as TO
+    orc = TO.OracleTekkenizer.from_file(TO.find_tekken_json())
+    cl = Classifier()
+    alphabet = list("aAbBzZ\u01c5\u02b0\u4e2d\u3042\u0915\u093e\u093f\u094d\u064b\u0301\u0308 \u3000\t\n\r/\\.,;!?-'\"(0123\u0663\u2460\u20ac\U0001f600\u200d") + ["\u00a0", "\u0085", "/", "\n", " ", "A", "a"]
+    cache = {ch: cl.cls(ch) for ch in alphabet}
+    rng = random.Random(seed)
+    bad = 0
+    n_safe = n_all = 0
+    for it in range(n_strings):
+        text = "".join(rng.choice(alphabet) for _ in range(rng.choice([2, 3, 5, 9, 14, 25, 60])))
+        K = [cache[ch] for ch in text]
+        want, pos = set(), 0
+        for p in orc.split_config(text):
+            want.add(pos)
+            pos += len(p.decode("utf-8"))
+        got = safe_starts(text, K)
+        n_safe += len(got)
+        n_all += len(want)
+        if not set(got) <= want:
+            bad += 1
+            if bad <= 5:
+                print("NOT A START", repr(text), "".join(K), sorted(set(got) - want))
+    print("%d strings, %d with a wrong safe start; %d of %d starts are safe starts" % (n_strings, bad, n_safe, n_all))
+    return bad

@@ -127,6 +127,7 @@ def test_config_pattern_run_predicate(oracle):
     from oracle.research import config_pattern_positionwise as pw
     assert pw.check(20000, seed=7) == 0
     assert pw.check(2000, seed=8, lengths=(60, 200)) == 0
+    assert pw.check_safe(5000) == 0          # the purely local "safe start" rules only ever mark real starts
 
 
 def test_config_pattern_differs_from_reference_pattern(oracle):
