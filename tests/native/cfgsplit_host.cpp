@@ -1,0 +1,68 @@
+// cfgsplit_host.cpp -- runs the groundwork split for the pattern stored in tekken.json
+// (tekken_rs_b200/csrc/tk_pretok_cfg.h: safe starts + one sequential matcher walk per segment) on the CPU, so the
+// CPU test-suite can compare its piece boundaries with the oracle.  Test infrastructure.
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../tekken_rs_b200/csrc/tk_pretok.h"       // TkBytesChecked
+#include "../../tekken_rs_b200/csrc/tk_pretok_cfg.h"
+
+static std::vector<uint16_t> g_s1;
+static std::vector<uint8_t> g_s2;
+
+// cls_flat: one class (TK_CC_*, CR/LF excluded) per scalar value 0 .. 0x10FFFF
+extern "C" void cfgsplit_set_classes(const uint8_t* cls_flat) {
+    g_s1.assign(0x110000 >> 7, 0);
+    g_s2.clear();
+    std::map<std::string, uint16_t> seen;
+    for (uint32_t b = 0; b < (0x110000u >> 7); ++b) {
+        std::string blk(64, '\0');
+        for (uint32_t i = 0; i < 128; ++i) {
+            const uint8_t c = cls_flat[b * 128 + i] & 15u;
+            blk[i >> 1] = (char)((uint8_t)blk[i >> 1] | (c << ((i & 1u) * 4u)));
+        }
+        auto it = seen.find(blk);
+        if (it == seen.end()) {
+            it = seen.emplace(blk, (uint16_t)(g_s2.size() / 64)).first;
+            g_s2.insert(g_s2.end(), blk.begin(), blk.end());
+        }
+        g_s1[b] = it->second;
+    }
+}
+
+// start_mask: (n/32 + 1) words, bit = a piece starts at that byte.  Returns the number of safe starts, or
+// -1 - position when a matcher walk from a safe start does not land on the next safe start (the scheme would be wrong).
+extern "C" int64_t cfgsplit_host(const uint8_t* data, uint64_t n, const uint64_t* doc_off, uint64_t n_docs, uint32_t* start_mask) {
+    const TkCfgTables T{g_s1.data(), g_s2.data()};
+    const TkBytesChecked src{data, n};
+    memset(start_mask, 0, (n / 32 + 1) * 4);
+    int64_t n_safe = 0;
+    for (uint64_t d = 0; d < n_docs; ++d) {
+        const int64_t a = (int64_t)doc_off[d], e = (int64_t)doc_off[d + 1];
+        // pass 1 (what K1 would do with bit logic): safe starts
+        std::vector<int64_t> safe;
+        uint32_t prev = 0xFFu;
+        for (int64_t p = a; p < e;) {
+            uint32_t c, cp;
+            const int l = tk_cfg_char(src, p, T, &c, &cp);
+            if (tk_cfg_safe_start(p == a, prev, c)) safe.push_back(p);
+            prev = c;
+            p += l;
+        }
+        safe.push_back(e);
+        n_safe += (int64_t)safe.size() - 1;
+        // pass 2 (one lane per segment): sequential matcher from a safe start to the next one
+        for (size_t i = 0; i + 1 < safe.size(); ++i) {
+            int64_t q = safe[i];
+            while (q < safe[i + 1]) {
+                start_mask[q >> 5] |= 1u << (q & 31);
+                q = tk_cfg_match_end(src, q, e, T);
+            }
+            if (q != safe[i + 1]) return -1 - safe[i + 1];
+        }
+    }
+    return n_safe;
+}
