@@ -12,6 +12,7 @@
 // No kernel includes this header yet.
 #pragma once
 #include "tk_common.h"
+#include "tk_pretok.h"      // SWAR helpers, byte sources, TK_FFS
 
 // classes of the stored pattern: U = Lu|Lt, LO = Ll, C = Lm|Lo (caseless letters), M = \p{M} (a word character, a
 // punctuation character and a possible prefix at once), N = \p{N}, W = \s minus CR/LF, R = CR/LF, O = the rest
@@ -159,4 +160,130 @@ TK_HD bool tk_cfg_safe_start(bool doc_start, uint32_t prev, uint32_t cur) {
     if (cur == TK_CC_W && !tk_cfg_is_ws(prev)) return true;
     if (cur == TK_CC_O && tk_cfg_is_letter(prev)) return true;
     return false;
+}
+
+// ---- the same rules as bit logic over a 32-byte window (what K1 would run: one thread per window) ------------
+// Class bits are spread over all bytes of a char (as in TkWin), so `mask << 1` with a carry from the previous window
+// is "class of the previous char" at a lead byte.
+struct TkCfgWin {
+    uint32_t lead;                       // byte starts a char
+    uint32_t mU, mLO, mC, mM, mN, mW, mR;  // classes; O = none of them
+    uint32_t ds;                         // a document starts at this byte
+    uint32_t bad;                        // invalid UTF-8 detected at this byte
+};
+
+// strict decode of the char whose lead byte is at pos: length (0 = invalid UTF-8) and class
+template <class B>
+TK_HD int tk_cfg_decode_strict(const B& src, int64_t pos, const TkCfgTables& T, uint32_t* cls) {
+    const uint32_t b0 = src.at(pos);
+    uint32_t cp;
+    int len;
+    if (b0 < 0x80u) { cp = b0; len = 1; }
+    else if (b0 < 0xC2u) return 0;
+    else if (b0 < 0xE0u) {
+        const uint32_t b1 = src.at(pos + 1);
+        if ((b1 & 0xC0u) != 0x80u) return 0;
+        cp = ((b0 & 0x1Fu) << 6) | (b1 & 0x3Fu);
+        len = 2;
+    } else if (b0 < 0xF0u) {
+        const uint32_t b1 = src.at(pos + 1), b2 = src.at(pos + 2);
+        if ((b1 & 0xC0u) != 0x80u || (b2 & 0xC0u) != 0x80u) return 0;
+        cp = ((b0 & 0x0Fu) << 12) | ((b1 & 0x3Fu) << 6) | (b2 & 0x3Fu);
+        if (cp < 0x800u || (cp >= 0xD800u && cp <= 0xDFFFu)) return 0;
+        len = 3;
+    } else if (b0 < 0xF5u) {
+        const uint32_t b1 = src.at(pos + 1), b2 = src.at(pos + 2), b3 = src.at(pos + 3);
+        if ((b1 & 0xC0u) != 0x80u || (b2 & 0xC0u) != 0x80u || (b3 & 0xC0u) != 0x80u) return 0;
+        cp = ((b0 & 0x07u) << 18) | ((b1 & 0x3Fu) << 12) | ((b2 & 0x3Fu) << 6) | (b3 & 0x3Fu);
+        if (cp < 0x10000u || cp > 0x10FFFFu) return 0;
+        len = 4;
+    } else return 0;
+    if (src.past_end(pos + len)) return 0;
+    *cls = tk_cfg_class(T, cp);
+    return len;
+}
+
+TK_HD void tk_cfg_set(TkCfgWin& r, uint32_t cls, uint32_t m) {
+    if (cls == TK_CC_U) r.mU |= m;
+    else if (cls == TK_CC_LO) r.mLO |= m;
+    else if (cls == TK_CC_C) r.mC |= m;
+    else if (cls == TK_CC_M) r.mM |= m;
+    else if (cls == TK_CC_N) r.mN |= m;
+    else if (cls == TK_CC_W) r.mW |= m;
+    else if (cls == TK_CC_R) r.mR |= m;
+}
+
+// Classify the 32-byte window at byte offset `pos` (a multiple of 32).  w[0..7] = its bytes as little-endian words,
+// zero padded beyond the text.
+template <class B>
+TK_HD TkCfgWin tk_cfg_classify_window(const B& src, uint64_t pos, const uint32_t* w, uint32_t ds_word, const TkCfgTables& T) {
+    TkCfgWin r;
+    r.mU = r.mLO = r.mC = r.mM = r.mN = r.mW = r.mR = 0;
+    uint32_t hi = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t x = w[j];
+        const uint32_t h = x & TK_H;
+        const uint32_t w7 = x & 0x7F7F7F7Fu;
+        const uint32_t ok = ~h;
+        const uint32_t upper = tk_swar_ge(w7, 0x41u) & tk_swar_le(w7, 0x5Au) & ok;
+        const uint32_t lower = tk_swar_ge(w7, 0x61u) & tk_swar_le(w7, 0x7Au) & ok;
+        const uint32_t digit = tk_swar_ge(w7, 0x30u) & tk_swar_le(w7, 0x39u) & ok;
+        const uint32_t c9_13 = tk_swar_ge(w7, 0x09u) & tk_swar_le(w7, 0x0Du) & ok;
+        const uint32_t rr = (tk_swar_eq(w7, 0x0Au) | tk_swar_eq(w7, 0x0Du)) & ok;
+        const uint32_t e20 = tk_swar_eq(w7, 0x20u) & ok;
+        const int s = 4 * j;
+        r.mU |= tk_swar_nib(upper) << s;
+        r.mLO |= tk_swar_nib(lower) << s;
+        r.mN |= tk_swar_nib(digit) << s;
+        r.mR |= tk_swar_nib(rr) << s;
+        r.mW |= tk_swar_nib((c9_13 & ~rr) | e20) << s;
+        hi |= tk_swar_nib(h) << s;
+    }
+    uint32_t lead = 0xFFFFFFFFu, bad = 0;
+    if (hi) {
+        uint32_t cont = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cont |= tk_swar_nib((w[j] & TK_H) & ~((w[j] << 1) & TK_H)) << (4 * j);
+        lead = ~cont;
+        uint32_t covered = ~hi;
+        uint32_t lc = (uint32_t)(TK_FFS(~cont) - 1);          // leading continuation bytes: a char that starts in the previous window
+        if (cont == 0xFFFFFFFFu) lc = 32;
+        if (lc > 0) {
+            int back = 0;
+            int64_t q = (int64_t)pos - 1;
+            while (back < 3 && q >= 0 && (src.at(q) & 0xC0u) == 0x80u) { --q; ++back; }
+            uint32_t cls = TK_CC_O;
+            const int len = (q >= 0) ? tk_cfg_decode_strict(src, q, T, &cls) : 0;
+            const int64_t over = len ? q + len - (int64_t)pos : 0;
+            if (over > 0) {
+                const uint32_t m = (1u << (over < (int64_t)lc ? (uint32_t)over : lc)) - 1u;
+                covered |= m;
+                tk_cfg_set(r, cls, m);
+            }
+        }
+        uint32_t todo = hi & lead;
+        while (todo) {
+            const int i = TK_FFS(todo) - 1;
+            todo &= todo - 1;
+            uint32_t cls = TK_CC_O;
+            const int len = tk_cfg_decode_strict(src, (int64_t)pos + i, T, &cls);
+            if (len == 0) { bad |= 1u << i; continue; }
+            const uint32_t m = (len >= 32 - i) ? (0xFFFFFFFFu << i) : (((1u << len) - 1u) << i);
+            covered |= m;
+            tk_cfg_set(r, cls, m);
+        }
+        bad |= ~covered;
+    }
+    bad |= ds_word & ~lead;
+    r.lead = lead; r.ds = ds_word; r.bad = bad;
+    return r;
+}
+
+// Safe starts of window c (p = the window before it; all-zero masks for the window before the text)
+TK_HD uint32_t tk_cfg_safe_mask(const TkCfgWin& p, const TkCfgWin& c) {
+    const uint32_t P_N = tk_shl(c.mN, p.mN, 1), P_W = tk_shl(c.mW, p.mW, 1), P_R = tk_shl(c.mR, p.mR, 1);
+    const uint32_t P_letter = tk_shl(c.mU | c.mLO | c.mC, p.mU | p.mLO | p.mC, 1);
+    const uint32_t mO = ~(c.mU | c.mLO | c.mC | c.mM | c.mN | c.mW | c.mR);
+    return c.lead & (c.ds | c.mN | P_N | (c.mW & ~(P_W | P_R)) | (mO & P_letter));
 }

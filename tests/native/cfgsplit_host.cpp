@@ -42,7 +42,7 @@ extern "C" int64_t cfgsplit_host(const uint8_t* data, uint64_t n, const uint64_t
     int64_t n_safe = 0;
     for (uint64_t d = 0; d < n_docs; ++d) {
         const int64_t a = (int64_t)doc_off[d], e = (int64_t)doc_off[d + 1];
-        // pass 1 (what K1 would do with bit logic): safe starts
+        // pass 1: safe starts by the scalar rule (pass 1b below: the same from window bit logic)
         std::vector<int64_t> safe;
         uint32_t prev = 0xFFu;
         for (int64_t p = a; p < e;) {
@@ -62,6 +62,37 @@ extern "C" int64_t cfgsplit_host(const uint8_t* data, uint64_t n, const uint64_t
                 q = tk_cfg_match_end(src, q, e, T);
             }
             if (q != safe[i + 1]) return -1 - safe[i + 1];
+        }
+    }
+    // pass 1b: what K1 would run -- one "thread" per 32-byte window, class masks + bit logic; must give the same safe
+    // starts (documents back to back: a document start is always a safe start)
+    {
+        const uint64_t nw = n / 32 + 1;
+        std::vector<uint32_t> ds(nw + 1, 0);
+        for (uint64_t d = 0; d < n_docs; ++d) if (doc_off[d] < n) ds[doc_off[d] >> 5] |= 1u << (doc_off[d] & 31);
+        TkCfgWin prev{};
+        std::vector<uint32_t> want(nw, 0);
+        for (uint64_t d = 0; d < n_docs; ++d) {
+            uint32_t pc = 0xFFu;
+            for (int64_t p = (int64_t)doc_off[d]; p < (int64_t)doc_off[d + 1];) {
+                uint32_t c, cp;
+                const int l = tk_cfg_char(src, p, T, &c, &cp);
+                if (tk_cfg_safe_start(p == (int64_t)doc_off[d], pc, c)) want[p >> 5] |= 1u << (p & 31);
+                pc = c;
+                p += l;
+            }
+        }
+        for (uint64_t w = 0; w < nw; ++w) {
+            uint32_t words[8] = {0};
+            const uint64_t pos = w * 32;
+            const uint64_t m = pos < n ? (n - pos < 32 ? n - pos : 32) : 0;
+            memcpy(words, data + pos, m);
+            const TkCfgWin c = tk_cfg_classify_window(src, pos, words, ds[w], T);
+            const uint64_t valid = (pos + 32 <= n) ? 0xFFFFFFFFull : ((1ull << (n - pos)) - 1ull);
+            if (c.bad & (uint32_t)valid) return -2000000000LL - (int64_t)pos;
+            const uint32_t got = tk_cfg_safe_mask(prev, c) & (uint32_t)valid;
+            if (got != want[w]) return -1000000000LL - (int64_t)pos;
+            prev = c;
         }
     }
     return n_safe;
