@@ -55,21 +55,37 @@ TK_HD int tk_cfg_char(const B& src, int64_t pos, const TkCfgTables& T, uint32_t*
     return len;
 }
 
+// Where a document ends.  The matcher never looks past it.  TkCfgEndAt: a known end offset (host tests).
+// TkCfgEndMask: the end of the text or the next document-start bit (what a kernel has: the K0 bitmask), so a lane
+// needs no search for its document's end.
+struct TkCfgEndAt {
+    int64_t end;
+    TK_HD bool at_end(int64_t pos) const { return pos >= end; }
+};
+struct TkCfgEndMask {
+    const uint32_t* ds_mask;     // bit = a document starts at this byte
+    int64_t n;                   // end of the text
+    int64_t own_start;           // the start of the walk's own document segment is not an end
+    TK_HD bool at_end(int64_t pos) const {
+        return pos >= n || (pos > own_start && ((ds_mask[pos >> 5] >> (pos & 31)) & 1u));
+    }
+};
+
 // U*L+ at s: end of the match, or -1.  Greedy U* takes the whole U run, L+ the L run that follows; if nothing in L
 // follows, U* gives characters back until the one it gives back is in L: the match then ends after the LAST
 // character of the U run that is in both sets (Lm, Lo, M).
-template <class B>
-TK_HD int64_t tk_cfg_match_UL(const B& src, int64_t s, int64_t end, const TkCfgTables& T) {
+template <class B, class E>
+TK_HD int64_t tk_cfg_match_UL(const B& src, int64_t s, const E& end, const TkCfgTables& T) {
     int64_t q = s, last_both_end = -1;
     uint32_t c, cp;
-    while (q < end) {
+    while (!end.at_end(q)) {
         const int l = tk_cfg_char(src, q, T, &c, &cp);
         if (!tk_cfg_in_U(c)) break;
         q += l;
         if (tk_cfg_in_L(c)) last_both_end = q;
     }
     int64_t r = q;
-    while (r < end) {
+    while (!end.at_end(r)) {
         const int l = tk_cfg_char(src, r, T, &c, &cp);
         if (!tk_cfg_in_L(c)) break;
         r += l;
@@ -78,17 +94,17 @@ TK_HD int64_t tk_cfg_match_UL(const B& src, int64_t s, int64_t end, const TkCfgT
 }
 
 // U+L* at s: end of the match, or -1
-template <class B>
-TK_HD int64_t tk_cfg_match_UpL(const B& src, int64_t s, int64_t end, const TkCfgTables& T) {
+template <class B, class E>
+TK_HD int64_t tk_cfg_match_UpL(const B& src, int64_t s, const E& end, const TkCfgTables& T) {
     int64_t q = s;
     uint32_t c, cp;
-    while (q < end) {
+    while (!end.at_end(q)) {
         const int l = tk_cfg_char(src, q, T, &c, &cp);
         if (!tk_cfg_in_U(c)) break;
         q += l;
     }
     if (q == s) return -1;
-    while (q < end) {
+    while (!end.at_end(q)) {
         const int l = tk_cfg_char(src, q, T, &c, &cp);
         if (!tk_cfg_in_L(c)) break;
         q += l;
@@ -97,12 +113,12 @@ TK_HD int64_t tk_cfg_match_UpL(const B& src, int64_t s, int64_t end, const TkCfg
 }
 
 // End of the leftmost-first match of the stored pattern that starts at q (q < end, q is a character boundary).
-// `end` is the end of the document: matches never cross it.
-template <class B>
-TK_HD int64_t tk_cfg_match_end(const B& src, int64_t q, int64_t end, const TkCfgTables& T) {
+// `end` says where the document ends: matches never cross it.
+template <class B, class E>
+TK_HD int64_t tk_cfg_match_end(const B& src, int64_t q, const E& end, const TkCfgTables& T) {
     uint32_t k0, c0, k1 = 0xFFu, c1 = 0;
     const int l0 = tk_cfg_char(src, q, T, &k0, &c0);
-    const bool has1 = q + l0 < end;
+    const bool has1 = !end.at_end(q + l0);
     if (has1) tk_cfg_char(src, q + l0, T, &k1, &c1);
     int64_t e;
     // B1: P?U*L+ (greedy optional prefix first, then without it), B2: P?U+L*
@@ -119,12 +135,12 @@ TK_HD int64_t tk_cfg_match_end(const B& src, int64_t q, int64_t end, const TkCfg
         else if (tk_cfg_is_punct(k0)) s = q;
         if (s >= 0) {
             uint32_t c, cp;
-            while (s < end) {
+            while (!end.at_end(s)) {
                 const int l = tk_cfg_char(src, s, T, &c, &cp);
                 if (!tk_cfg_is_punct(c)) break;
                 s += l;
             }
-            while (s < end) {
+            while (!end.at_end(s)) {
                 const uint32_t b = src.at(s);
                 if (b != 0x0Au && b != 0x0Du && b != 0x2Fu) break;
                 ++s;
@@ -137,7 +153,7 @@ TK_HD int64_t tk_cfg_match_end(const B& src, int64_t q, int64_t end, const TkCfg
     {
         int64_t e2 = q, last_r_end = -1, last_char = q;
         uint32_t c, cp;
-        while (e2 < end) {
+        while (!end.at_end(e2)) {
             const int l = tk_cfg_char(src, e2, T, &c, &cp);
             if (!tk_cfg_is_ws(c)) break;
             last_char = e2;
@@ -145,7 +161,7 @@ TK_HD int64_t tk_cfg_match_end(const B& src, int64_t q, int64_t end, const TkCfg
             if (c == TK_CC_R) last_r_end = e2;
         }
         if (last_r_end >= 0) return last_r_end;
-        if (e2 == end) return e2;
+        if (end.at_end(e2)) return e2;
         if (last_char > q) return last_char;
         return e2;
     }

@@ -40,6 +40,8 @@ extern "C" int64_t cfgsplit_host(const uint8_t* data, uint64_t n, const uint64_t
     const TkBytesChecked src{data, n};
     memset(start_mask, 0, (n / 32 + 1) * 4);
     int64_t n_safe = 0;
+    std::vector<uint32_t> ds_bits(n / 32 + 2, 0);
+    for (uint64_t d = 0; d <= n_docs; ++d) if (doc_off[d] < n) ds_bits[doc_off[d] >> 5] |= 1u << (doc_off[d] & 31);
     for (uint64_t d = 0; d < n_docs; ++d) {
         const int64_t a = (int64_t)doc_off[d], e = (int64_t)doc_off[d + 1];
         // pass 1: safe starts by the scalar rule (pass 1b below: the same from window bit logic)
@@ -57,9 +59,13 @@ extern "C" int64_t cfgsplit_host(const uint8_t* data, uint64_t n, const uint64_t
         // pass 2 (one lane per segment): sequential matcher from a safe start to the next one
         for (size_t i = 0; i + 1 < safe.size(); ++i) {
             int64_t q = safe[i];
+            // the document's end is given the way a kernel has it: the document-start bitmask
+            const TkCfgEndMask stop{ds_bits.data(), (int64_t)n, a};
             while (q < safe[i + 1]) {
                 start_mask[q >> 5] |= 1u << (q & 31);
-                q = tk_cfg_match_end(src, q, e, T);
+                const int64_t e1 = tk_cfg_match_end(src, q, stop, T);
+                if (e1 != tk_cfg_match_end(src, q, TkCfgEndAt{e}, T)) return -3000000000LL - q;
+                q = e1;
             }
             if (q != safe[i + 1]) return -1 - safe[i + 1];
         }
