@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 # TEKKEN_B200_LIB: load (and build into) another file, e.g. an experimental build with TEKKEN_B200_NVCC_FLAGS="-DPT_MINB=5"
 LIB = os.environ.get("TEKKEN_B200_LIB") or os.path.join(HERE, "libtekken_b200.so")
 SOURCES = ["tk_kernels.cu", "tk_decode.cu", "tk_api.cu", "tk_host.cpp"]
-HEADERS = ["tk_common.h", "tk_host.h", "tk_pretok.h", "tk_device.cuh", "tk_kernels.h", "unicode_ranges.inc",
+HEADERS = ["tk_common.h", "tk_host.h", "tk_pretok.h", "tk_device.cuh", "tk_kernels.h", "unicode_ranges.inc", "unicode_subclasses.inc",
            os.path.join("..", "..", "include", "tekken_b200.h")]
 
 

@@ -18,6 +18,7 @@
 
 #include "../../include/tekken_b200.h"
 #include "unicode_ranges.inc"
+#include "unicode_subclasses.inc"
 
 namespace tk {
 
@@ -443,6 +444,37 @@ void build_unicode_tables(std::vector<uint16_t>& stage1, std::vector<uint8_t>& s
         } else {
             stage1[b] = it->second;
         }
+    }
+}
+
+// GROUNDWORK (config-driven pattern, not used by the library yet): 4-bit classes of tk_pretok_cfg.h (TK_CC_*), two-stage:
+// stage1[cp >> 7] -> block, 64 bytes (128 nibbles) per block.  CR/LF are tested inline by tk_cfg_class.
+void build_cfg_unicode_tables(std::vector<uint16_t>& stage1, std::vector<uint8_t>& stage2) {
+    enum { CC_O = 0, CC_U = 1, CC_LO = 2, CC_C = 3, CC_M = 4, CC_N = 5, CC_W = 6 };
+    std::vector<uint8_t> cls(0x110000, CC_O);
+    auto fill = [&](const uint32_t (*r)[2], int n, uint8_t v) {
+        for (int i = 0; i < n; ++i)
+            for (uint32_t c = r[i][0]; c <= r[i][1]; ++c) cls[c] = v;
+    };
+    fill(UNI_S_RANGES, UNI_S_COUNT, CC_W);
+    fill(UNI_N_RANGES, UNI_N_COUNT, CC_N);
+    fill(UNI_SUB_UPPER_RANGES, UNI_SUB_UPPER_COUNT, CC_U);
+    fill(UNI_SUB_LOWER_RANGES, UNI_SUB_LOWER_COUNT, CC_LO);
+    fill(UNI_SUB_BOTH_RANGES, UNI_SUB_BOTH_COUNT, CC_C);
+    fill(UNI_SUB_MARK_RANGES, UNI_SUB_MARK_COUNT, CC_M);
+    stage1.assign(TK_UNI_STAGE1_N, 0);
+    stage2.clear();
+    std::unordered_map<std::string, uint16_t> seen;
+    for (uint32_t b = 0; b < TK_UNI_STAGE1_N; ++b) {
+        std::string blk(64, '\0');
+        for (uint32_t i = 0; i < 128; ++i)
+            blk[i >> 1] = (char)((uint8_t)blk[i >> 1] | (uint8_t)(cls[b * 128 + i] << ((i & 1) * 4)));
+        auto it = seen.find(blk);
+        if (it == seen.end()) {
+            it = seen.emplace(blk, (uint16_t)seen.size()).first;
+            stage2.insert(stage2.end(), blk.begin(), blk.end());
+        }
+        stage1[b] = it->second;
     }
 }
 

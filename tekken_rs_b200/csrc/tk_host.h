@@ -82,6 +82,7 @@ struct HostModel {
 };
 
 void build_unicode_tables(std::vector<uint16_t>& stage1, std::vector<uint8_t>& stage2);
+void build_cfg_unicode_tables(std::vector<uint16_t>& stage1, std::vector<uint8_t>& stage2);   // groundwork, see tk_pretok_cfg.h
 std::string utf8_lossy(const uint8_t* p, size_t n);  // String::from_utf8_lossy
 bool utf8_valid(const uint8_t* p, size_t n);         // String::from_utf8(..).is_ok()
 

@@ -7,11 +7,23 @@
 #include <string>
 #include <vector>
 
+#include "../../tekken_rs_b200/csrc/tk_host.h"         // build_cfg_unicode_tables (the library's own table builder)
 #include "../../tekken_rs_b200/csrc/tk_pretok.h"       // TkBytesChecked
 #include "../../tekken_rs_b200/csrc/tk_pretok_cfg.h"
 
 static std::vector<uint16_t> g_s1;
 static std::vector<uint8_t> g_s2;
+
+// the tables the library itself would upload; returns the number of scalar values whose class differs from cls_flat
+// (one class per scalar value, measured from the engine by the oracle tools) -- must be 0
+extern "C" int64_t cfgsplit_use_library_tables(const uint8_t* cls_flat) {
+    tk::build_cfg_unicode_tables(g_s1, g_s2);
+    const TkCfgTables T{g_s1.data(), g_s2.data()};
+    int64_t diff = 0;
+    for (uint32_t c = 0; c < 0x110000u; ++c)
+        if (c != 0x0A && c != 0x0D && tk_cfg_class(T, c) != cls_flat[c]) ++diff;
+    return diff;
+}
 
 // cls_flat: one class (TK_CC_*, CR/LF excluded) per scalar value 0 .. 0x10FFFF
 extern "C" void cfgsplit_set_classes(const uint8_t* cls_flat) {

@@ -34,13 +34,17 @@ def flat_classes():
 def model(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("native") / "libcfgsplit_host.so")
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", out,
-                           os.path.join(ROOT, "tests", "native", "cfgsplit_host.cpp")])
+                           os.path.join(ROOT, "tests", "native", "cfgsplit_host.cpp"),
+                           os.path.join(ROOT, "tekken_rs_b200", "csrc", "tk_host.cpp")])
     lib = ctypes.CDLL(out)
     lib.cfgsplit_host.restype = ctypes.c_int64
     lib.cfgsplit_host.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p]
     lib.cfgsplit_set_classes.argtypes = [ctypes.c_void_p]
+    lib.cfgsplit_use_library_tables.restype = ctypes.c_int64
+    lib.cfgsplit_use_library_tables.argtypes = [ctypes.c_void_p]
     flat = flat_classes()
-    lib.cfgsplit_set_classes(flat.ctypes.data)
+    # the library's own table builder (csrc/unicode_subclasses.inc) against the classes measured from the engine
+    assert lib.cfgsplit_use_library_tables(flat.ctypes.data) == 0
     return lib
 
 
