@@ -303,3 +303,19 @@ TK_HD uint32_t tk_cfg_safe_mask(const TkCfgWin& p, const TkCfgWin& c) {
     const uint32_t mO = ~(c.mU | c.mLO | c.mC | c.mM | c.mN | c.mW | c.mR);
     return c.lead & (c.ds | c.mN | P_N | (c.mW & ~(P_W | P_R)) | (mO & P_letter));
 }
+
+// What one lane of the walk kernel does for one safe start at byte q0: run the matcher from piece to piece and mark
+// every piece start until the walk reaches the next safe start (its bit is set in safe_mask), the next document or
+// the end of the text.  set_bit(pos) records a piece start (an atomicOr into the piece-start mask in a kernel).
+template <class B, class F>
+TK_HD void tk_cfg_walk(const B& src, int64_t q0, const uint32_t* safe_mask, const uint32_t* ds_mask, int64_t n,
+                       const TkCfgTables& T, F set_bit) {
+    const TkCfgEndMask stop{ds_mask, n, q0};
+    int64_t q = q0;
+    for (;;) {
+        const int64_t e = tk_cfg_match_end(src, q, stop, T);
+        if (e >= n || ((safe_mask[e >> 5] >> (e & 31)) & 1u)) return;      // the next segment's lane takes over
+        set_bit(e);
+        q = e;
+    }
+}

@@ -112,6 +112,21 @@ extern "C" int64_t cfgsplit_host(const uint8_t* data, uint64_t n, const uint64_t
             if (got != want[w]) return -1000000000LL - (int64_t)pos;
             prev = c;
         }
+        // pass 2b: the walk exactly as a kernel would run it -- one "lane" per safe start, in no particular order,
+        // knowing only the safe-start mask and the document-start mask; must reproduce the piece-start mask of pass 2
+        std::vector<uint32_t> starts(nw, 0);
+        for (uint64_t wi = nw; wi-- > 0;) {
+            uint32_t m = want[wi];
+            starts[wi] |= m;
+            while (m) {
+                const int b = __builtin_ctz(m);
+                m &= m - 1;
+                tk_cfg_walk(src, (int64_t)(wi * 32 + b), want.data(), ds_bits.data(), (int64_t)n, T,
+                            [&](int64_t pos) { starts[pos >> 5] |= 1u << (pos & 31); });
+            }
+        }
+        for (uint64_t w = 0; w < nw; ++w)
+            if (starts[w] != start_mask[w]) return -4000000000LL - (int64_t)(w * 32);
     }
     return n_safe;
 }
