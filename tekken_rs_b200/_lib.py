@@ -66,6 +66,7 @@ PROTOTYPES = {
     "tk_status_name": (ctypes.c_char_p, [ctypes.c_int]),
     "tk_kernel_launch_count": (ctypes.c_uint64, []),
     "tk_set_stage_timing": (None, [c_vp, ctypes.c_int]),
+    "tk_last_encode_counters": (ctypes.c_size_t, [c_vp, c_u64p, ctypes.c_size_t]),
     "tk_last_stage_times": (ctypes.c_size_t, [c_vp, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_float),
                                               ctypes.c_size_t]),
 }

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
@@ -73,11 +74,19 @@ struct HostPool {
     std::map<void*, size_t> live;                 // ptr -> capacity
     std::multimap<size_t, void*> free_list;       // capacity -> ptr
     size_t cached = 0;
-    static constexpr size_t kMaxCached = 6ull << 30;
+    static constexpr size_t kMaxCached = 6ull << 30;   // enough for the id buffers of two 1 GB batches in flight
 
-    void* get(size_t bytes) {
+    // small results (accessor strings, the ids of one short text) are plain heap memory: pinning 4 KiB for a
+    // five-byte answer costs more than it saves, and a host-only handle must not create a CUDA context
+    static constexpr size_t kSmall = 16384;
+    void* get(size_t bytes, bool pinned = true) {
         if (bytes == 0) bytes = 1;
         std::lock_guard<std::mutex> g(mu);
+        if (!pinned || bytes <= kSmall) {
+            void* p = malloc(bytes);
+            if (p) live[p] = bytes | 1;
+            return p;
+        }
         auto it = free_list.lower_bound(bytes);
         if (it != free_list.end() && it->first <= bytes * 2 + 4096) {
             void* p = it->second;
@@ -88,7 +97,7 @@ struct HostPool {
         }
         void* p = nullptr;
         size_t cap = (bytes + 4095) & ~(size_t)4095;
-        if (cudaHostAlloc(&p, cap, cudaHostAllocDefault) != cudaSuccess) {
+        if (cudaHostAlloc(&p, cap, cudaHostAllocPortable) != cudaSuccess) {
             cudaGetLastError();
             // no CUDA context (host-only handle): plain memory
             p = malloc(cap);
@@ -98,6 +107,13 @@ struct HostPool {
         }
         live[p] = cap;
         return p;
+    }
+    // drop the cached (not the live) pinned buffers: called when the last tokenizer handle goes away
+    void trim() {
+        std::lock_guard<std::mutex> g(mu);
+        for (auto& kv : free_list) cudaFreeHost(kv.second);
+        free_list.clear();
+        cached = 0;
     }
     void put(void* p) {
         if (!p) return;
@@ -113,11 +129,41 @@ struct HostPool {
     }
 };
 HostPool g_pool;
+std::atomic<int> g_live_handles{0};
 }  // namespace
 
 extern "C" void tk_buffer_free(void* p) { g_pool.put(p); }
 
 // ------------------------------------------------------------------------------------------ handle
+
+// Is a CUDA context current on this thread?  (cudaGetDevice answers 0 also when none is, and restoring "device 0"
+// would then create a primary context -- a few hundred MB -- on a GPU this process never meant to touch.)
+static bool thread_has_context() {
+    typedef int (*ctx_fn)(void**);
+    static const ctx_fn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuCtxGetCurrent", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return (ctx_fn) nullptr;
+        }
+        return (ctx_fn)p;
+    }();
+    if (!fn) return true;
+    void* ctx = nullptr;
+    return fn(&ctx) == 0 && ctx != nullptr;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (thread_has_context()) cudaGetDevice(&prev);
+        ok = cudaSetDevice(dev) == cudaSuccess;
+        if (prev == dev) prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 struct DevBuf {
     void* p = nullptr;
@@ -163,6 +209,8 @@ struct tk_tokenizer {
     cudaStream_t pipe_st[3] = {nullptr, nullptr, nullptr};   // ... on an upload, a kernel and a download stream
     EncSlot dev_slot;              // device-pointer encode (caller's stream)
     bool timing = false;
+    bool counted = false;          // included in g_live_handles
+    tkk::HotTables hot;            // pair + byte-pair table allocation (L2 persistence window of the merge kernels)
     tkk::StageTimer timer;
     std::vector<std::string> stage_names;
     std::vector<float> stage_ms;
@@ -191,17 +239,38 @@ static int finish_handle(tk_tokenizer* t, int device, tk_tokenizer** out) {
             return fail(TK_ERR_CUDA, "CUDA device %d is not available (%s); this library has no CPU fallback", device,
                         e != cudaSuccess ? cudaGetErrorString(e) : "ordinal out of range");
         }
-        int prev = 0;
-        cudaGetDevice(&prev);
-        cudaError_t err = cudaSetDevice(device);
+        DeviceGuard dg(device);
+        cudaError_t err = dg.ok ? cudaSuccess : cudaErrorInvalidDevice;
         const tk::HostModel& h = t->host;
         TkDeviceTables& T = t->tables;
         if (err == cudaSuccess) err = cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, device);
         if (err == cudaSuccess) err = upload(t, h.uni_stage1, (const void**)&T.uni_stage1);
         if (err == cudaSuccess) err = upload(t, h.uni_stage2, (const void**)&T.uni_stage2);
         if (err == cudaSuccess) err = upload(t, h.vocab_slots, (const void**)&T.vocab_slots);
-        if (err == cudaSuccess) err = upload(t, h.pair_slots, (const void**)&T.pair_slots);
-        if (err == cudaSuccess) err = upload(t, h.byte_pair, (const void**)&T.byte_pair);
+        if (err == cudaSuccess) {
+            // the merge kernels' tables (pair table + byte-pair table, 8.25 MB for the Tekken vocabulary) live in ONE
+            // allocation so that one L2 access-policy window can keep them resident while text / queue / stream
+            // traffic passes through (tk_kernels.cu launch_lanemerge)
+            const size_t pb = h.pair_slots.size() * sizeof(uint64_t), bb = h.byte_pair.size() * sizeof(uint32_t);
+            void* hot = nullptr;
+            err = cudaMalloc(&hot, pb + bb);
+            if (err == cudaSuccess) {
+                t->table_allocs.push_back(hot);
+                err = cudaMemcpy(hot, h.pair_slots.data(), pb, cudaMemcpyHostToDevice);
+                if (err == cudaSuccess) err = cudaMemcpy((char*)hot + pb, h.byte_pair.data(), bb, cudaMemcpyHostToDevice);
+                T.pair_slots = (const uint64_t*)hot;
+                T.byte_pair = (const uint32_t*)((const char*)hot + pb);
+                t->hot.ptr = hot;
+                t->hot.bytes = pb + bb;
+                int max_persist = 0, max_window = 0;
+                cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
+                cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device);
+                const size_t want = std::min<size_t>((size_t)max_persist, std::max<size_t>(t->hot.bytes * 2, (size_t)32 << 20));
+                if (max_persist > 0 && (size_t)max_window >= t->hot.bytes && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess)
+                    t->hot.enabled = true;
+                else cudaGetLastError();
+            }
+        }
         if (err == cudaSuccess) err = upload(t, h.vocab_pad16, (const void**)&T.vocab_pad16);
         if (err == cudaSuccess) err = upload(t, h.vocab_len8, (const void**)&T.vocab_len);
         if (err == cudaSuccess) err = upload(t, h.vocab_bytes, (const void**)&T.vocab_bytes);
@@ -216,7 +285,6 @@ static int finish_handle(tk_tokenizer* t, int device, tk_tokenizer** out) {
         T.max_token_len = h.max_token_len;
         T.bos_id = h.has_control_token("<s>") ? h.control_token("<s>") : TK_INF;
         T.eos_id = h.has_control_token("</s>") ? h.control_token("</s>") : TK_INF;
-        cudaSetDevice(prev);
         if (err != cudaSuccess) {
             int rc = fail(TK_ERR_CUDA, "uploading vocabulary tables: %s", cudaGetErrorString(err));
             tk_free(t);
@@ -224,6 +292,8 @@ static int finish_handle(tk_tokenizer* t, int device, tk_tokenizer** out) {
         }
     }
     *out = t;
+    t->counted = true;
+    g_live_handles.fetch_add(1);
     return TK_OK;
 }
 
@@ -286,9 +356,7 @@ extern "C" size_t tk_deprecated_special_tokens(const tk_special_entry** out) {
 extern "C" void tk_free(tk_tokenizer* t) {
     if (!t) return;
     if (t->device >= 0) {
-        int prev = 0;
-        cudaGetDevice(&prev);
-        cudaSetDevice(t->device);
+        DeviceGuard dg(t->device);
         t->timer.reset();
         for (void* p : t->table_allocs) cudaFree(p);
         t->ws.release(); t->in_data.release(); t->in_off.release();
@@ -305,9 +373,10 @@ extern "C" void tk_free(tk_tokenizer* t) {
         for (auto& sl : t->slot) drop(sl);
         drop(t->dev_slot);
         if (t->stream) cudaStreamDestroy(t->stream);
-        cudaSetDevice(prev);
     }
+    const bool last = t->counted && g_live_handles.fetch_sub(1) == 1;
     delete t;
+    if (last) g_pool.trim();
 }
 
 // ------------------------------------------------------------------------------------------ accessors
@@ -399,16 +468,6 @@ extern "C" int tk_id_to_byte_piece(const tk_tokenizer* t, uint32_t id, int polic
 
 // ------------------------------------------------------------------------------------------ encode
 
-struct DeviceGuard {
-    int prev = 0;
-    bool ok = false;
-    explicit DeviceGuard(int dev) {
-        cudaGetDevice(&prev);
-        ok = cudaSetDevice(dev) == cudaSuccess;
-    }
-    ~DeviceGuard() { cudaSetDevice(prev); }
-};
-
 static int check_encode_args(const tk_tokenizer* t, int add_bos, int add_eos) {
     if (!t) return fail(TK_ERR_INVALID_ARGUMENT, "null tokenizer");
     if (t->device < 0)
@@ -429,9 +488,9 @@ static int encode_issue(tk_tokenizer* t, tk_tokenizer::EncSlot& s, const uint8_t
                         size_t n_docs, uint64_t total, int add_bos, int add_eos, uint32_t* d_tokens, uint64_t cap,
                         uint64_t* d_tok_off, cudaStream_t st, bool timing) {
     if (((uintptr_t)d_data & 15u) != 0 && total) return fail(TK_ERR_INVALID_ARGUMENT, "device text pointer must be 16-byte aligned");
-    // per-class piece counters and queue indices are 32-bit: a class of 2-byte pieces overflows them at 8 GiB of text
-    // (the workspace, about 16 B per text byte, does not fit one GPU beyond that anyway)
-    if (total >= (1ull << 33)) return fail(TK_ERR_INVALID_ARGUMENT, "batch too large; shard it (limit 8 GiB of text per device call)");
+    // piece lengths, per-class piece counters and queue indices are 32-bit: one device call takes < 4 GiB of text
+    // (the host-buffer entry points stream larger batches through in chunks; a single document is limited to this)
+    if (total >= (1ull << 32)) return fail(TK_ERR_INVALID_ARGUMENT, "batch too large; shard it (limit 4 GiB of text per device call)");
     if ((uint64_t)n_docs >= 0xFFFFFFFEull) return fail(TK_ERR_INVALID_ARGUMENT, "too many documents in one call; shard the batch");
     size_t ws_bytes = tkk::encode_workspace_bytes(total, n_docs, &s.L);
     CUDA_OR_FAIL(s.ws.ensure(ws_bytes));
@@ -444,7 +503,7 @@ static int encode_issue(tk_tokenizer* t, tk_tokenizer::EncSlot& s, const uint8_t
     if (timing) t->timer.reset();
     cudaError_t e = tkk::encode_device(t->tables, d_data, d_doc_off, off_base, n_docs, total, add_bos, add_eos, d_tokens, cap, d_tok_off,
                                        s.ws.p, s.L, (uint32_t*)s.scratch.p, s.scratch.cap / 4, t->sm_count, st,
-                                       timing ? &t->timer : nullptr);
+                                       timing ? &t->timer : nullptr, &t->hot);
     if (e != cudaSuccess) return fail(TK_ERR_CUDA, "encode launch: %s", cudaGetErrorString(e));
     CUDA_OR_FAIL(tkk::publish_counters(s.ws.p, s.L, s.d_small_map, st));
     CUDA_OR_FAIL(cudaEventRecord(s.done, st));
@@ -518,7 +577,12 @@ extern "C" int tk_encode_batch(const tk_tokenizer* tc, const uint8_t* data, cons
     if (!doc_off || !tokens || !tok_off) return fail(TK_ERR_INVALID_ARGUMENT, "null argument");
     *tokens = nullptr;
     *tok_off = nullptr;
-    if (doc_off[0] != 0) return fail(TK_ERR_INVALID_ARGUMENT, "document offsets must start at 0, be non-decreasing and end at the text length");
+    {
+        // the chunk plan below slices the caller's buffers by these offsets: check them before anything is copied
+        uint64_t bad = doc_off[0] != 0;
+        for (size_t d = 0; d < n_docs; ++d) bad |= (uint64_t)(doc_off[d + 1] < doc_off[d]);
+        if (bad) return fail(TK_ERR_INVALID_ARGUMENT, "document offsets must start at 0, be non-decreasing and end at the text length");
+    }
     const uint64_t total = doc_off[n_docs];
     if (!data && total) return fail(TK_ERR_INVALID_ARGUMENT, "null text");
     tk_tokenizer* t = const_cast<tk_tokenizer*>(tc);
@@ -870,6 +934,20 @@ extern "C" uint64_t tk_kernel_launch_count(void) { return tkk::launch_count(); }
 
 extern "C" void tk_set_stage_timing(tk_tokenizer* t, int enabled) {
     if (t) t->timing = enabled != 0;
+}
+
+extern "C" size_t tk_last_encode_counters(const tk_tokenizer* t, uint64_t* out, size_t cap) {
+    if (!t || !out || !t->dev_slot.h_small) return 0;
+    const uint32_t* small = t->dev_slot.h_small;
+    uint64_t v[TKK_N_CLASSES + 4];
+    for (int c = 0; c < TKK_N_CLASSES; ++c) v[c] = small[tkk::TKK_S_QN + c];
+    v[TKK_N_CLASSES] = small[tkk::TKK_S_NLONG];
+    v[TKK_N_CLASSES + 1] = small[tkk::TKK_S_NHUGE];
+    memcpy(&v[TKK_N_CLASSES + 2], small + tkk::TKK_S_PAIRLOOK, 8);
+    memcpy(&v[TKK_N_CLASSES + 3], small + tkk::TKK_S_BPLOOK, 8);
+    const size_t n = std::min(cap, (size_t)(TKK_N_CLASSES + 4));
+    for (size_t i = 0; i < n; ++i) out[i] = v[i];
+    return n;
 }
 
 extern "C" size_t tk_last_stage_times(const tk_tokenizer* t, const char** names, float* ms, size_t cap) {

@@ -217,7 +217,7 @@ __device__ __forceinline__ uint32_t tk_popc_m(tk_u128 m) {
 #define TK_KEY_SHIFT 7u                                  // key = rank << TK_KEY_SHIFT | offset; offsets < 128
 
 template <class M, int MAXLEN>
-__device__ __forceinline__ M tk_bpe_merge_loop(const TkDeviceTables& T, uint32_t len, uint32_t* id, uint32_t* key) {
+__device__ __forceinline__ M tk_bpe_merge_loop(const TkDeviceTables& T, uint32_t len, uint32_t* id, uint32_t* key, uint32_t& lookups) {
     constexpr uint32_t kBits = sizeof(M) * 8;
     static_assert(MAXLEN % 4 == 0 && MAXLEN <= (int)kBits, "scan is unrolled by four; one live bit per offset");
     const M one = 1;
@@ -246,6 +246,7 @@ __device__ __forceinline__ M tk_bpe_merge_loop(const TkDeviceTables& T, uint32_t
         const uint32_t rgt = nn != 0xFFFFFFFFu ? id[nn] : TK_INF;
         uint32_t r0, r1;
         tk_pair_rank2(T, lft, rank, rank, rgt, &r0, &r1);
+        lookups += (lft != TK_INF ? 1u : 0u) + (rgt != TK_INF ? 1u : 0u);
         if (pv != 0xFFFFFFFFu) key[pv] = r0 == TK_INF ? TK_INF : ((r0 << TK_KEY_SHIFT) | pv);
         key[bp] = r1 == TK_INF ? TK_INF : ((r1 << TK_KEY_SHIFT) | bp);
     }

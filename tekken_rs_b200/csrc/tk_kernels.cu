@@ -69,6 +69,9 @@ __global__ void docmark_kernel(const uint64_t* __restrict__ doc_off, uint64_t of
                                uint32_t* __restrict__ flags) {
     uint64_t d = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (d > n_docs) return;
+    // the end-of-data sentinel does not depend on the offsets being valid: every later kernel that walks the
+    // piece-start mask to "the next set bit" relies on it, also when the call is about to fail with bad offsets
+    if (d == n_docs) atomicOr(ds_mask + (total >> 5), 1u << (total & 31));
     uint64_t o = doc_off[d] - off_base;      // offsets may be a slice of a larger batch (off_base = its first entry)
     bool ok = doc_off[d] >= off_base && o <= total;
     if (d == 0 && o != 0) ok = false;
@@ -457,15 +460,17 @@ __global__ void longmark_kernel(const uint32_t* __restrict__ start_mask, uint64_
 // =====================================================================================================
 #define LM_WARPS 4
 
-__device__ __forceinline__ uint64_t piece_end(const uint32_t* __restrict__ start_mask, uint64_t pos) {
-    // position of the next set bit after pos (the sentinel at n guarantees there is one)
+__device__ __forceinline__ uint64_t piece_end(const uint32_t* __restrict__ start_mask, uint64_t pos, uint64_t n_windows, uint64_t n) {
+    // position of the next set bit after pos (the sentinel at n guarantees there is one; the walk is bounded by
+    // the mask's length all the same, so that a damaged mask cannot send it into the neighbouring arrays)
     const uint32_t lane = threadIdx.x & 31u;
     uint64_t w = pos >> 5;
     uint32_t first = start_mask[w] & ~((2u << (pos & 31)) - 1u);
     if ((pos & 31) == 31) first = 0;
     if (first) return w * 32u + (uint32_t)(__ffs((int)first) - 1);
     for (w += 1;; w += 32) {
-        const uint32_t m = start_mask[w + lane];
+        if (w >= n_windows) return n;
+        const uint32_t m = w + lane < n_windows ? start_mask[w + lane] : 0u;
         const uint32_t any = __ballot_sync(0xFFFFFFFFu, m != 0);
         if (any) {
             const int l = __ffs((int)any) - 1;
@@ -482,9 +487,11 @@ __global__ void __launch_bounds__(LM_WARPS * 32) longmerge_warp_kernel(const uin
                                                                        unsigned long long* __restrict__ pool_cursor,
                                                                        uint32_t* __restrict__ huge_list, uint32_t* __restrict__ n_huge,
                                                                        uint32_t* __restrict__ work_counter,
-                                                                       unsigned long long* __restrict__ tile_count) {
+                                                                       unsigned long long* __restrict__ tile_count,
+                                                                       uint64_t n_windows, uint64_t n, const uint32_t* __restrict__ flags) {
     __shared__ TkWarpBpeSmem S[LM_WARPS];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    if (*flags & TKK_FLAG_BAD_OFFSETS) return;          // the call fails; the masks describe no valid batch
     const uint32_t total = *n_long;
     for (;;) {
         uint32_t r = 0;
@@ -492,7 +499,7 @@ __global__ void __launch_bounds__(LM_WARPS * 32) longmerge_warp_kernel(const uin
         r = __shfl_sync(0xFFFFFFFFu, r, 0);
         if (r >= total) break;
         const uint64_t pos = recs[r].start;
-        const uint64_t end = piece_end(start_mask, pos);
+        const uint64_t end = piece_end(start_mask, pos, n_windows, n);
         const uint64_t len = end - pos;
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(pool_cursor, (unsigned long long)len);
@@ -571,7 +578,7 @@ __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __
         if (s_rec >= total) break;
         const uint32_t r = huge_list[s_rec];
         const uint64_t pos = recs[r].start;
-        const uint32_t n = (uint32_t)recs[r].len;   // pieces are < 4 GiB (checked by the host)
+        const uint32_t n = (uint32_t)recs[r].len;   // a call holds < 4 GiB of text (tk_api.cu encode_issue), so does a piece
         if (t == 0) s_base = atomicAdd(scratch_cursor, (unsigned long long)HG_ARRAYS * n);   // the cursor also tells the host how much is needed
         __syncthreads();
         if (s_base + (unsigned long long)HG_ARRAYS * n > scratch_cap) {
@@ -961,7 +968,8 @@ template <int MAXLEN, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) lanemerge_kernel(const uint8_t* __restrict__ data, uint64_t n, TkDeviceTables T,
                                                             const unsigned long long* __restrict__ queue,
                                                             const uint32_t* __restrict__ q_n, uint32_t* __restrict__ q_w,
-                                                            uint32_t* __restrict__ stream, unsigned long long* __restrict__ tile_count) {
+                                                            uint32_t* __restrict__ stream, unsigned long long* __restrict__ tile_count,
+                                                            unsigned long long* __restrict__ stats) {
     constexpr int STRIDE = MAXLEN + 1;      // odd: lane i's arrays start at bank i (no conflicts when lanes sweep together)
     extern __shared__ __align__(16) uint32_t lm_raw[];
     uint32_t* id = lm_raw + threadIdx.x * STRIDE;
@@ -1002,6 +1010,7 @@ __global__ void __launch_bounds__(THREADS, MINB) lanemerge_kernel(const uint8_t*
                                             (uint32_t)(e1 >> QE_START_BITS) & ((1u << QE_LEN_BITS) - 1u), w1);
     uint32_t k2 = next_batch(k1);
     unsigned long long e2 = entry_of(k2);
+    uint32_t n_pair = 0, n_bp = 0;                          // table lookups issued by this lane (reported by bench.py)
     while (k1 < total) {
         const unsigned long long e = e1;
         uint32_t w[kWordsAhead ? NW : 1];
@@ -1048,7 +1057,8 @@ __global__ void __launch_bounds__(THREADS, MINB) lanemerge_kernel(const uint8_t*
             }
             using Mask = typename std::conditional<(MAXLEN <= 32), uint32_t,
                                                    typename std::conditional<(MAXLEN <= 64), unsigned long long, tk_u128>::type>::type;
-            Mask live = tk_bpe_merge_loop<Mask, MAXLEN>(T, len, id, key);
+            n_bp += len - 1u;
+            Mask live = tk_bpe_merge_loop<Mask, MAXLEN>(T, len, id, key, n_pair);
             {
                 // the ranks go to consecutive byte positions from `start`: count them for the tile each one lands in
                 const uint32_t cnt = tk_popc_m(live);
@@ -1067,6 +1077,9 @@ __global__ void __launch_bounds__(THREADS, MINB) lanemerge_kernel(const uint8_t*
         }
         __syncwarp();
     }
+    n_pair = __reduce_add_sync(0xFFFFFFFFu, n_pair);
+    n_bp = __reduce_add_sync(0xFFFFFFFFu, n_bp);
+    if (lane == 0 && (n_pair | n_bp)) { atomicAdd(stats, (unsigned long long)n_pair); atomicAdd(stats + 1, (unsigned long long)n_bp); }
 }
 
 // =====================================================================================================
@@ -1451,7 +1464,7 @@ cudaError_t publish_counters(const void* d_ws, const EncodeLayout& L, uint32_t* 
 template <int MAXLEN, int THREADS, int MINB>
 static cudaError_t launch_lanemerge(int blocks_per_sm, int sm_count, const uint8_t* d_data, uint64_t n, const TkDeviceTables& T,
                                     const unsigned long long* queue, const uint32_t* q_n, uint32_t* q_w, uint32_t* stream,
-                                    unsigned long long* tile_count, cudaStream_t st) {
+                                    unsigned long long* tile_count, unsigned long long* stats, const HotTables* hot, cudaStream_t st) {
     const size_t smem = (size_t)2 * THREADS * (MAXLEN + 1) * sizeof(uint32_t);
     static std::atomic<uint64_t> attr_set{0};   // bit per device ordinal
     int dev = 0;
@@ -1460,7 +1473,28 @@ static cudaError_t launch_lanemerge(int blocks_per_sm, int sm_count, const uint8
         CK(cudaFuncSetAttribute(lanemerge_kernel<MAXLEN, THREADS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set.fetch_or(1ull << (dev & 63));
     }
-    lanemerge_kernel<MAXLEN, THREADS, MINB><<<(unsigned)(sm_count * blocks_per_sm), THREADS, smem, st>>>(d_data, n, T, queue, q_n, q_w, stream, tile_count);
+    // Launch attribute: an L2 access-policy window over the pair + byte-pair tables (persisting), everything else this
+    // kernel touches (queue entries, piece bytes, stream words: each used once) streaming.  Per launch, so the
+    // caller's stream keeps its own attributes.  TEKKEN_B200_L2PIN=0 switches it off (A/B measurements).
+    static const bool pin = [] { const char* e = getenv("TEKKEN_B200_L2PIN"); return !e || atoi(e) != 0; }();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(sm_count * blocks_per_sm));
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    cfg.attrs = attr;
+    cfg.numAttrs = 0;
+    if (pin && hot && hot->enabled) {
+        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[0].val.accessPolicyWindow.base_ptr = hot->ptr;
+        attr[0].val.accessPolicyWindow.num_bytes = hot->bytes;
+        attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
+        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cfg.numAttrs = 1;
+    }
+    CK(cudaLaunchKernelEx(&cfg, lanemerge_kernel<MAXLEN, THREADS, MINB>, d_data, n, T, queue, q_n, (uint32_t*)q_w, stream, tile_count, stats));
     count_launch();
     return cudaSuccess;
 }
@@ -1468,7 +1502,7 @@ static cudaError_t launch_lanemerge(int blocks_per_sm, int sm_count, const uint8
 cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const uint64_t* d_doc_off, uint64_t off_base,
                           uint64_t n_docs, uint64_t n, int add_bos, int add_eos, uint32_t* d_out, uint64_t out_cap, uint64_t* d_tok_off,
                           void* d_ws, const EncodeLayout& L, uint32_t* d_scratch, uint64_t scratch_cap, int sm_count,
-                          cudaStream_t st, StageTimer* timer) {
+                          cudaStream_t st, StageTimer* timer, const HotTables* hot) {
     unsigned char* ws = (unsigned char*)d_ws;
     uint32_t* small = (uint32_t*)(ws + L.off_small);
     uint32_t* ds = (uint32_t*)(ws + L.off_ds);
@@ -1539,7 +1573,7 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
         const uint64_t cap = (uint64_t)sm_count * 12;
         if (blocks > cap) blocks = cap;
         longmerge_warp_kernel<<<(unsigned)blocks, LM_WARPS * 32, 0, st>>>(d_data, start, T, recs, n_long, pool, pool_cursor, huge,
-                                                                        n_huge, wc_long, tile_count);
+                                                                        n_huge, wc_long, tile_count, L.n_windows, n, flags);
         TK_LAUNCHED();
         uint64_t hb = L.max_long < (uint64_t)(2 * sm_count) ? L.max_long : (uint64_t)(2 * sm_count);
         longmerge_block_kernel<<<(unsigned)hb, HG_T, 0, st>>>(d_data, T, recs, huge, n_huge, pool, d_scratch, scratch_cap,
@@ -1569,7 +1603,7 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
 #define TK_LANEMERGE(MAXLEN, THREADS, MINB, CLS, NAME)                                                                            \
     if (timer) timer->mark(st, NAME);                                                                                             \
     CK((launch_lanemerge<MAXLEN, THREADS, MINB>(bps[TKK_N_CLASSES - 1 - CLS], sm_count, d_data, n, T, queues + L.queues.off[CLS],     \
-                                                q_n + CLS, q_w + CLS, stream, tile_count, st)));
+                                                q_n + CLS, q_w + CLS, stream, tile_count, (unsigned long long*)(small + TKK_S_PAIRLOOK), hot, st)));
     // MINB (the resident blocks the compiler plans registers for) is set from measurements: capping the 12- and
     // 16-byte classes at 32 / 40 registers for more resident warps made them 1.4x slower
     TK_LANEMERGE(96, 64, 1, 8, "lanemerge96")

@@ -34,6 +34,8 @@ enum {
     TKK_S_BADDOC = 16,   // u64 (decode)
     TKK_S_QN = 20,       // TKK_N_CLASSES counters: queued pieces per length class
     TKK_S_QW = 30,       // TKK_N_CLASSES work counters
+    TKK_S_PAIRLOOK = 40, // u64: pair-table lookups issued by the lane-merge kernels (two per merge, minus piece edges)
+    TKK_S_BPLOOK = 42,   // u64: byte-pair table lookups (first round of every queued piece)
 };
 
 #define TKK_N_CLASSES 9
@@ -77,11 +79,18 @@ struct StageTimer {
     ~StageTimer();
 };
 
+// the allocation that holds the merge kernels' tables (pair table, then byte-pair table)
+struct HotTables {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+    bool enabled = false;     // the device accepted a persisting-L2 carve-out that covers it
+};
+
 size_t encode_workspace_bytes(uint64_t n, uint64_t n_docs, EncodeLayout* L);
 cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const uint64_t* d_doc_off, uint64_t off_base,
                           uint64_t n_docs, uint64_t n, int add_bos, int add_eos, uint32_t* d_out, uint64_t out_cap, uint64_t* d_tok_off,
                           void* d_ws, const EncodeLayout& L, uint32_t* d_scratch, uint64_t scratch_cap, int sm_count,
-                          cudaStream_t st, StageTimer* timer);
+                          cudaStream_t st, StageTimer* timer, const HotTables* hot = nullptr);
 
 cudaError_t publish_counters(const void* d_ws, const EncodeLayout& L, uint32_t* mapped_dev, cudaStream_t st);
 

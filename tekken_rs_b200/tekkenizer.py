@@ -292,10 +292,20 @@ class Tekkenizer:
         self._lib.tk_set_stage_timing(self._h, int(enabled))
 
     def last_stage_times(self) -> dict:
-        names = (ctypes.c_char_p * 16)()
-        ms = (ctypes.c_float * 16)()
-        n = self._lib.tk_last_stage_times(self._h, names, ms, 16)
+        names = (ctypes.c_char_p * 32)()
+        ms = (ctypes.c_float * 32)()
+        n = self._lib.tk_last_stage_times(self._h, names, ms, 32)
         return {names[i].decode(): float(ms[i]) for i in range(n)}
+
+    def last_encode_counters(self) -> dict:
+        """Work counters of the last device-pointer encode call (pieces per merge class, table lookups)."""
+        v = (ctypes.c_uint64 * 16)()
+        n = self._lib.tk_last_encode_counters(self._h, v, 16)
+        if n < 13:
+            return {}
+        by_class = [int(v[i]) for i in range(9)]
+        return {"by_class": by_class, "pieces_queued": sum(by_class), "n_long": int(v[9]), "n_huge": int(v[10]),
+                "pair_lookups": int(v[11]), "byte_pair_lookups": int(v[12])}
 
 
 def shard_plan(doc_off, n_shards: int) -> np.ndarray:

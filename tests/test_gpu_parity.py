@@ -295,6 +295,93 @@ def test_config4_adversarial_long_pieces(gpu_tok, oracle):
         assert gpu_tok.decode_bytes(ids) == data.tobytes()
 
 
+def test_config4_full_256_pieces(gpu_tok, oracle):
+    # BASELINE configs[3] at its named size: 256 single pre-tokens x 64 KiB (16 MiB, one document); the oracle's
+    # heap variant of the merge loop (cross-checked against the literal loop in tests/test_oracle.py) takes seconds
+    data, off = one_doc(corpus.adversarial_pieces(256, 1 << 16))
+    ids, _ = assert_same_batch(gpu_tok, oracle, data, off, False, False, n_threads=1)
+    assert gpu_tok.decode_bytes(ids) == data.tobytes()
+
+
+def test_config5_sharded_roundtrip_reduced_scale(gpu_tok, oracle):
+    # BASELINE configs[4] at reduced scale: 8 shards x 65,536 documents of the 64-shard corpus' generator.  Every shard:
+    # decode(encode(x)) == x compared ON THE DEVICE; ids identical whether the corpus goes through as 1 shard plan or 8
+    # (checksum of checksums + concatenation); oracle on every 16th document.
+    import torch
+    n_shards, per = 8, 1 << 16
+    datas, offs = [], []
+    for s in range(n_shards):
+        d, o = corpus.mixed_script_docs(per, 42, first_doc=s * (1 << 20))     # the first 65,536 documents of bench.py's shard s
+        datas.append(d); offs.append(o)
+    st = torch.cuda.current_stream().cuda_stream
+    shard_ids, shard_chk = [], 0
+    for s in range(n_shards):
+        d, o = datas[s], offs[s]
+        n, nd = len(d), per
+        d_data = torch.from_numpy(np.concatenate([d, np.zeros(64, np.uint8)])).cuda()
+        d_off = torch.from_numpy(o.astype(np.int64)).cuda()
+        cap = n + 2 * nd + 2
+        d_tok = torch.empty(cap, dtype=torch.int32, device="cuda")
+        d_toff = torch.empty(nd + 1, dtype=torch.int64, device="cuda")
+        ntok = gpu_tok.encode_batch_device(d_data.data_ptr(), d_off.data_ptr(), nd, n, True, True, d_tok.data_ptr(), cap, d_toff.data_ptr(), st)
+        d_out = torch.empty(n + 64, dtype=torch.uint8, device="cuda")
+        d_boff = torch.empty(nd + 1, dtype=torch.int64, device="cuda")
+        nb = gpu_tok.decode_batch_device(d_tok.data_ptr(), d_toff.data_ptr(), nd, ntok, SpecialTokenPolicy.Ignore, d_out.data_ptr(), n + 64,
+                                         d_boff.data_ptr(), 0, st)
+        assert nb == n and bool(torch.equal(d_out[:n], d_data[:n])) and bool(torch.equal(d_boff, d_off)), "shard %d round trip" % s
+        ids = d_tok[:ntok].cpu().numpy().view(np.uint32)
+        toff = d_toff.cpu().numpy().view(np.uint64)
+        shard_ids.append(ids)
+        shard_chk ^= corpus.checksum64(ids) + 0x1000003 * s
+        sel = np.arange(0, nd, 16)
+        sub = [d[int(o[k]):int(o[k + 1])] for k in sel]
+        soff = np.zeros(len(sub) + 1, dtype=np.uint64)
+        np.cumsum([len(x) for x in sub], out=soff[1:])
+        rid, _ = oracle.encode_batch_np(np.concatenate(sub), soff, True, True, n_threads=8)
+        assert np.array_equal(np.concatenate([ids[int(toff[k]):int(toff[k + 1])] for k in sel]), rid), "shard %d oracle sample" % s
+    # the same corpus as ONE batch cut by a 1-shard and an 8-shard byte-balanced plan through the host API
+    data = np.concatenate(datas)
+    off = np.zeros(n_shards * per + 1, dtype=np.uint64)
+    np.cumsum(np.concatenate([np.diff(o.astype(np.int64)) for o in offs]), out=off[1:])
+    whole, wtoff = gpu_tok.encode_batch_np(data, off, True, True)
+    assert np.array_equal(whole, np.concatenate(shard_ids))
+    plan = shard_plan(off, 8)
+    parts, chk8 = [], 0
+    for s in range(8):
+        b, e = int(plan[s]), int(plan[s + 1])
+        sid, _ = gpu_tok.encode_batch_np(data[int(off[b]):int(off[e])], sharding.rebase_offsets(off, b, e), True, True)
+        parts.append(sid)
+    assert corpus.checksum64(np.concatenate(parts)) == corpus.checksum64(whole)
+    chk1 = 0
+    for s in range(n_shards):
+        a, b = int(wtoff[s * per]), int(wtoff[(s + 1) * per])
+        chk1 ^= corpus.checksum64(whole[a:b]) + 0x1000003 * s
+    assert chk1 == shard_chk
+
+
+def test_bad_offsets_fail_cleanly_on_the_device_path(gpu_tok):
+    # offsets that do not cover the text must come back as InvalidArgument, never as a device fault --
+    # also when the text ends in a long run of punctuation / whitespace (no natural piece start at the end)
+    import torch
+    raw = (b"word " * 50 + b"." * 5000 + b" " * 3000)
+    d_data = torch.from_numpy(np.frombuffer(raw + b"\0" * 64, dtype=np.uint8).copy()).cuda()
+    for bad in ([0, len(raw) - 7], [5, len(raw)], [0, 900, 100, len(raw)], [0, len(raw) + 9]):
+        d_off = torch.tensor(bad, dtype=torch.int64, device="cuda")
+        d_tok = torch.empty(len(raw) + 16, dtype=torch.int32, device="cuda")
+        d_toff = torch.empty(len(bad), dtype=torch.int64, device="cuda")
+        with pytest.raises(TokenizerError) as e:
+            gpu_tok.encode_batch_device(d_data.data_ptr(), d_off.data_ptr(), len(bad) - 1, len(raw), True, True, d_tok.data_ptr(),
+                                        len(raw) + 16, d_toff.data_ptr(), 0)
+        assert e.value.kind == "InvalidArgument"
+    torch.cuda.synchronize()
+    assert gpu_tok.encode("still alive", False, False) == gpu_tok.encode(b"still alive", False, False)
+    data = np.frombuffer(raw, dtype=np.uint8)
+    for bad in ([0, 900, 100, len(raw)], [0, 10**12, 5, len(raw)], [3, len(raw)]):
+        with pytest.raises(TokenizerError) as e:
+            gpu_tok.encode_batch_np(data, np.array(bad, dtype=np.uint64), False, False)
+        assert e.value.kind == "InvalidArgument"
+
+
 def test_config4_piece_length_sweep(gpu_tok, oracle):
     # every length across the lane-merge classes (one lane per piece <= 96 B, class limits 4, 8, 12, 16, 24, 32, 48,
     # 64, 96) and around the later escalation thresholds (warp <= 512 B, block beyond)
