@@ -332,7 +332,7 @@ def run_ours(args):
     if cx.world > 1:
         cx.dist.barrier()
         path = assets.ensure_tekken_json()
-    tk = Tekkenizer.from_file(path, device=cx.local)
+    tk = Tekkenizer.from_file(path, device=cx.local, split=1 if args.split == "config" else 0)
     lib = _lib.load()
     if args.workload == "roundtrip64g":
         return run_roundtrip(args, cx, tk, lib, path)
@@ -546,11 +546,13 @@ def run_ours(args):
         cb, orc, (sdata, soff) = cpu_baselines(wl, path)
         # the sample doubles as a parity check of this very run
         if wl.name in ("mixed", "english", "english1m"):
-            rid, roff = orc.encode_batch_np(sdata, soff, True, True, n_threads=host_threads())
+            rid, roff = orc.encode_batch_np(sdata, soff, True, True, n_threads=host_threads(), mode=4 if args.split == "config" else 0)
             got = d_tok[:int(roff[-1])].cpu().numpy().view(np.uint32)
             cb["ids_match_gpu_on_sample"] = bool(np.array_equal(got, rid))
             cb["sample_docs"] = len(soff) - 1
         line["cpu_baseline"] = cb
+    if args.split == "config":
+        line["config"]["split"] = "TK_SPLIT_CONFIG: the pattern stored in tekken.json (not what the reference computes; SURVEY 8f rank 1)"
     if cx.rank == 0 and cx.world == 1 and args.latency:
         line["latency"] = latency_table(tk, lib, path)
     cx.close()
@@ -803,6 +805,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--quick", action="store_true", help="skip the pageable-input and one-call-all-GPUs legs")
     ap.add_argument("--latency", action="store_true", help="add the single-string latency table (13 B .. 1 MiB)")
+    ap.add_argument("--split", default="reference", choices=["reference", "config"],
+                    help="reference = the pattern the reference hard-codes (the bench line); config = the pattern stored in tekken.json (SURVEY 8f-1)")
     ap.add_argument("--workload", default="mixed", choices=["mixed", "english1m", "single1g", "adversarial", "roundtrip64g", "english"])
     args = ap.parse_args()
     if args.gpus > 1 and "RANK" not in os.environ:

@@ -57,6 +57,12 @@ typedef enum tk_policy { TK_POLICY_IGNORE = 0, TK_POLICY_KEEP = 1, TK_POLICY_RAI
 /* src/config.rs:97-103 */
 typedef enum tk_version { TK_V3 = 3, TK_V7 = 7, TK_V11 = 11, TK_V13 = 13 } tk_version;
 
+/* Which split pattern a handle uses.  TK_SPLIT_REFERENCE: the literal hard-coded at src/tekkenizer.rs:123 -- what the
+   reference computes (it drops `config.pattern`, `_pattern` at :74).  TK_SPLIT_CONFIG: the pattern STORED in
+   tekken.json (Mistral's own Tekken regex, the one tests/test_small_vocab.rs:62 and examples/basic_usage.rs:141
+   write and `mistral_common` compiles) -- SURVEY 8(f) rank 1. */
+typedef enum tk_split_mode { TK_SPLIT_REFERENCE = 0, TK_SPLIT_CONFIG = 1 } tk_split_mode;
+
 /* src/config.rs:16-23 `TokenInfo` (token_str is display-only and not needed) */
 typedef struct tk_vocab_entry {
     uint64_t rank;
@@ -83,6 +89,14 @@ int tk_load_file(const char *path, int device, tk_tokenizer **out);
 int tk_new(const tk_vocab_entry *vocab, size_t n_vocab, const tk_special_entry *special,
            size_t n_special, const char *pattern, size_t vocab_size, size_t num_special_tokens,
            int version, int device, tk_tokenizer **out);
+
+/* The same constructors with an explicit tk_split_mode (tk_load_file / tk_new use TK_SPLIT_REFERENCE).  With
+   TK_SPLIT_CONFIG the file's / argument's pattern must be the Tekken pattern (TK_ERR_INVALID_CONFIG otherwise). */
+int tk_load_file_ex(const char *path, int device, int split_mode, tk_tokenizer **out);
+int tk_new_ex(const tk_vocab_entry *vocab, size_t n_vocab, const tk_special_entry *special,
+              size_t n_special, const char *pattern, size_t vocab_size, size_t num_special_tokens,
+              int version, int device, int split_mode, tk_tokenizer **out);
+int tk_split_mode_of(const tk_tokenizer *t); /* a tk_split_mode */
 
 /* The 20 built-in special tokens used when the file has no `special_tokens`
    (get_deprecated_special_tokens, src/tekkenizer.rs:827-930).  Returns their count. */

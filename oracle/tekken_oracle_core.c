@@ -572,12 +572,17 @@ uint64_t orc_encode_piece(const orc_t *o, const uint8_t *piece, uint64_t n, uint
    the control token is absent (TokenNotFound, src/tekkenizer.rs:335-340). */
 int64_t orc_encode(const orc_t *o, const uint8_t *text, uint64_t n, int add_bos, int add_eos,
                    uint32_t *out, int mode) {
+    /* mode bit 2 (value 4): split with the pattern STORED in tekken.json (match_at_config) instead of the
+       reference's hard-coded one; the low two bits choose the merge loop as in orc_encode_piece */
+    const int cfg = mode & 4;
+    mode &= 3;
+    if (cfg) init_classes();
     if (!orc_utf8_valid(text, n)) return -1;
     int64_t k = 0;
     if (add_bos) { if (o->bos_id < 0) return -2; out[k++] = (uint32_t)o->bos_id; }
     const uint8_t *q = text, *end = text + n;
     while (q < end) {
-        size_t len = match_at(q, end);
+        size_t len = cfg ? match_at_config(q, end) : match_at(q, end);
         uint64_t c = orc_encode_piece(o, q, len, out + k, mode);
         for (uint64_t j = 0; j < c; j++) out[k + j] += o->num_special;
         k += (int64_t)c;

@@ -29,6 +29,11 @@ PROTOTYPES = {
     "tk_new": (ctypes.c_int, [ctypes.POINTER(VocabEntry), ctypes.c_size_t, ctypes.POINTER(SpecialEntry), ctypes.c_size_t,
                               ctypes.c_char_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
                               ctypes.POINTER(c_vp)]),
+    "tk_load_file_ex": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(c_vp)]),
+    "tk_new_ex": (ctypes.c_int, [ctypes.POINTER(VocabEntry), ctypes.c_size_t, ctypes.POINTER(SpecialEntry), ctypes.c_size_t,
+                                 ctypes.c_char_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                 ctypes.POINTER(c_vp)]),
+    "tk_split_mode_of": (ctypes.c_int, [c_vp]),
     "tk_deprecated_special_tokens": (ctypes.c_size_t, [ctypes.POINTER(ctypes.POINTER(SpecialEntry))]),
     "tk_free": (None, [c_vp]),
     "tk_vocab_size": (ctypes.c_size_t, [c_vp]),

@@ -211,6 +211,9 @@ struct tk_tokenizer {
     bool timing = false;
     bool counted = false;          // included in g_live_handles
     tkk::HotTables hot;            // pair + byte-pair table allocation (L2 persistence window of the merge kernels)
+    int split_mode = TK_SPLIT_REFERENCE;
+    tkk::CfgSplitTables cfg;       // device class tables of the TK_SPLIT_CONFIG split (null pointers otherwise)
+    const tkk::CfgSplitTables* cfg_ptr() const { return split_mode == TK_SPLIT_CONFIG ? &cfg : nullptr; }
     tkk::StageTimer timer;
     std::vector<std::string> stage_names;
     std::vector<float> stage_ms;
@@ -228,8 +231,17 @@ static cudaError_t upload(tk_tokenizer* t, const V& v, const void** out) {
     return e;
 }
 
-static int finish_handle(tk_tokenizer* t, int device, tk_tokenizer** out) {
+static int finish_handle(tk_tokenizer* t, int device, int split_mode, tk_tokenizer** out) {
     t->device = device;
+    if (split_mode != TK_SPLIT_REFERENCE && split_mode != TK_SPLIT_CONFIG) {
+        delete t;
+        return fail(TK_ERR_INVALID_ARGUMENT, "unknown split mode %d", split_mode);
+    }
+    if (split_mode == TK_SPLIT_CONFIG && t->host.pattern != tk::tekken_config_pattern()) {
+        delete t;
+        return fail(TK_ERR_INVALID_CONFIG, "TK_SPLIT_CONFIG: the pattern stored in the tokenizer file is not the Tekken pattern this library implements");
+    }
+    t->split_mode = split_mode;
     if (device >= 0) {
         int count = 0;
         cudaError_t e = cudaGetDeviceCount(&count);
@@ -277,6 +289,13 @@ static int finish_handle(tk_tokenizer* t, int device, tk_tokenizer** out) {
         if (err == cudaSuccess) err = upload(t, h.vocab_off, (const void**)&T.vocab_off);
         if (err == cudaSuccess) err = upload(t, h.special_bytes, (const void**)&T.special_bytes);
         if (err == cudaSuccess) err = upload(t, h.special_off, (const void**)&T.special_off);
+        if (err == cudaSuccess && split_mode == TK_SPLIT_CONFIG) {
+            std::vector<uint16_t> s1;
+            std::vector<uint8_t> s2;
+            tk::build_cfg_unicode_tables(s1, s2);
+            err = upload(t, s1, (const void**)&t->cfg.stage1);
+            if (err == cudaSuccess) err = upload(t, s2, (const void**)&t->cfg.stage2);
+        }
         if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking);
         T.vocab_mask = (uint32_t)h.vocab_slots.size() - 1;
         T.pair_mask = (uint32_t)h.pair_slots.size() - 1;
@@ -298,6 +317,10 @@ static int finish_handle(tk_tokenizer* t, int device, tk_tokenizer** out) {
 }
 
 extern "C" int tk_load_file(const char* path, int device, tk_tokenizer** out) {
+    return tk_load_file_ex(path, device, TK_SPLIT_REFERENCE, out);
+}
+
+extern "C" int tk_load_file_ex(const char* path, int device, int split_mode, tk_tokenizer** out) {
     if (!path || !out) return fail(TK_ERR_INVALID_ARGUMENT, "null argument");
     *out = nullptr;
     tk_tokenizer* t = new tk_tokenizer();
@@ -310,12 +333,18 @@ extern "C" int tk_load_file(const char* path, int device, tk_tokenizer** out) {
         delete t;
         return fail(TK_ERR_IO, "%s", e.what());
     }
-    return finish_handle(t, device, out);
+    return finish_handle(t, device, split_mode, out);
 }
 
 extern "C" int tk_new(const tk_vocab_entry* vocab, size_t n_vocab, const tk_special_entry* special, size_t n_special,
                       const char* pattern, size_t vocab_size, size_t num_special_tokens, int version, int device,
                       tk_tokenizer** out) {
+    return tk_new_ex(vocab, n_vocab, special, n_special, pattern, vocab_size, num_special_tokens, version, device, TK_SPLIT_REFERENCE, out);
+}
+
+extern "C" int tk_new_ex(const tk_vocab_entry* vocab, size_t n_vocab, const tk_special_entry* special, size_t n_special,
+                         const char* pattern, size_t vocab_size, size_t num_special_tokens, int version, int device,
+                         int split_mode, tk_tokenizer** out) {
     if (!out || (!vocab && n_vocab) || (!special && n_special)) return fail(TK_ERR_INVALID_ARGUMENT, "null argument");
     *out = nullptr;
     if (version != TK_V3 && version != TK_V7 && version != TK_V11 && version != TK_V13)
@@ -340,7 +369,7 @@ extern "C" int tk_new(const tk_vocab_entry* vocab, size_t n_vocab, const tk_spec
         delete t;
         return fail(e.code, "%s", e.what());
     }
-    return finish_handle(t, device, out);
+    return finish_handle(t, device, split_mode, out);
 }
 
 extern "C" size_t tk_deprecated_special_tokens(const tk_special_entry** out) {
@@ -385,6 +414,7 @@ extern "C" size_t tk_vocab_size(const tk_tokenizer* t) { return t ? t->host.voca
 extern "C" size_t tk_num_special_tokens(const tk_tokenizer* t) { return t ? t->host.num_special : 0; }
 extern "C" int tk_version_of(const tk_tokenizer* t) { return t ? t->host.version : 0; }
 extern "C" int tk_device_of(const tk_tokenizer* t) { return t ? t->device : -1; }
+extern "C" int tk_split_mode_of(const tk_tokenizer* t) { return t ? t->split_mode : TK_SPLIT_REFERENCE; }
 
 extern "C" int tk_get_control_token(const tk_tokenizer* t, const char* s, uint32_t* id) {
     if (!t || !s || !id) return fail(TK_ERR_INVALID_ARGUMENT, "null argument");
@@ -503,7 +533,7 @@ static int encode_issue(tk_tokenizer* t, tk_tokenizer::EncSlot& s, const uint8_t
     if (timing) t->timer.reset();
     cudaError_t e = tkk::encode_device(t->tables, d_data, d_doc_off, off_base, n_docs, total, add_bos, add_eos, d_tokens, cap, d_tok_off,
                                        s.ws.p, s.L, (uint32_t*)s.scratch.p, s.scratch.cap / 4, t->sm_count, st,
-                                       timing ? &t->timer : nullptr, &t->hot);
+                                       timing ? &t->timer : nullptr, &t->hot, t->cfg_ptr());
     if (e != cudaSuccess) return fail(TK_ERR_CUDA, "encode launch: %s", cudaGetErrorString(e));
     CUDA_OR_FAIL(tkk::publish_counters(s.ws.p, s.L, s.d_small_map, st));
     CUDA_OR_FAIL(cudaEventRecord(s.done, st));

@@ -447,7 +447,7 @@ void build_unicode_tables(std::vector<uint16_t>& stage1, std::vector<uint8_t>& s
     }
 }
 
-// GROUNDWORK (config-driven pattern, not used by the library yet): 4-bit classes of tk_pretok_cfg.h (TK_CC_*), two-stage:
+// Class tables of the TK_SPLIT_CONFIG split: 4-bit classes of tk_pretok_cfg.h (TK_CC_*), two-stage:
 // stage1[cp >> 7] -> block, 64 bytes (128 nibbles) per block.  CR/LF are tested inline by tk_cfg_class.
 void build_cfg_unicode_tables(std::vector<uint16_t>& stage1, std::vector<uint8_t>& stage2) {
     enum { CC_O = 0, CC_U = 1, CC_LO = 2, CC_C = 3, CC_M = 4, CC_N = 5, CC_W = 6 };
@@ -504,10 +504,19 @@ struct BytesKeyHash {
     size_t operator()(const BytesKey& k) const { return (size_t)piece_hash(k.p, k.n, nullptr); }
 };
 
+// Mistral's Tekken pattern as tekken.json stores it: the one pattern the TK_SPLIT_CONFIG kernels implement
+// (tk_pretok_cfg.h).  A file with another pattern cannot be honoured and is refused in that mode.
+const char* tekken_config_pattern() {
+    return "[^\\r\\n\\p{L}\\p{N}]?[\\p{Lu}\\p{Lt}\\p{Lm}\\p{Lo}\\p{M}]*[\\p{Ll}\\p{Lm}\\p{Lo}\\p{M}]+"
+           "|[^\\r\\n\\p{L}\\p{N}]?[\\p{Lu}\\p{Lt}\\p{Lm}\\p{Lo}\\p{M}]+[\\p{Ll}\\p{Lm}\\p{Lo}\\p{M}]*"
+           "|\\p{N}| ?[^\\s\\p{L}\\p{N}]+[\\r\\n/]*|\\s*[\\r\\n]+|\\s+(?!\\S)|\\s+";
+}
+
 HostModel HostModel::build(const std::vector<VocabEntry>& vocab, const std::vector<SpecialEntry>& special,
-                           const std::string& /*pattern_ignored*/, size_t vocab_size, size_t num_special,
+                           const std::string& pattern, size_t vocab_size, size_t num_special,
                            int version) {
     HostModel m;
+    m.pattern = pattern;      // the reference drops it (`_pattern`, :74); kept for handles that ask for TK_SPLIT_CONFIG
     // src/tekkenizer.rs:80-87
     if (vocab_size > vocab.size() + num_special) {
         std::ostringstream os;

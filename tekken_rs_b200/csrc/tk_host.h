@@ -56,6 +56,7 @@ struct HostModel {
     std::vector<uint32_t> vocab_off;                          // n_vocab + 1
     std::vector<std::string> vocab_strings;                   // vocab() (:141-155), lossy UTF-8
     uint32_t max_token_len = 0;
+    std::string pattern;                                      // config.pattern as given (ignored by the reference, :74)
 
     // device table images
     std::vector<uint16_t> uni_stage1;
@@ -82,7 +83,8 @@ struct HostModel {
 };
 
 void build_unicode_tables(std::vector<uint16_t>& stage1, std::vector<uint8_t>& stage2);
-void build_cfg_unicode_tables(std::vector<uint16_t>& stage1, std::vector<uint8_t>& stage2);   // groundwork, see tk_pretok_cfg.h
+void build_cfg_unicode_tables(std::vector<uint16_t>& stage1, std::vector<uint8_t>& stage2);   // TK_SPLIT_CONFIG, see tk_pretok_cfg.h
+const char* tekken_config_pattern();                          // the stored pattern the TK_SPLIT_CONFIG kernels implement
 std::string utf8_lossy(const uint8_t* p, size_t n);  // String::from_utf8_lossy
 bool utf8_valid(const uint8_t* p, size_t n);         // String::from_utf8(..).is_ok()
 

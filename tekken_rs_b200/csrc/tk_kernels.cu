@@ -24,6 +24,7 @@
 
 #include "tk_device.cuh"
 #include "tk_pretok.h"
+#include "tk_pretok_cfg.h"
 
 namespace tkk {
 
@@ -122,6 +123,27 @@ __device__ __forceinline__ TkWin pt_load(const PtSmem& S, int i) {
     return w;
 }
 
+// stage [tile - halo, tile + 8 KiB + halo) of the text in shared memory, zero outside the text (PT_T threads)
+__device__ __forceinline__ void pt_stage_tile(uint8_t* bytes, uint32_t b, const uint8_t* __restrict__ data, uint64_t n) {
+    const int t = threadIdx.x;
+    const long long g0 = (long long)b * (PT_T * 32) - PT_HALO;
+    uint4* dst = reinterpret_cast<uint4*>(bytes);
+    for (int i = t; i < (int)((PT_HALO + PT_T * 32 + PT_HALO) / 16); i += PT_T) {
+        const long long g = g0 + 16ll * i;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (g >= 0 && (uint64_t)g + 16u <= n) v = __ldg(reinterpret_cast<const uint4*>(data + g));
+        else if (g + 16 > 0 && (uint64_t)(g < 0 ? 0 : g) < n) {
+            uint32_t x[4] = {0u, 0u, 0u, 0u};
+            for (int k = 0; k < 16; ++k) {
+                const long long q = g + k;
+                if (q >= 0 && (uint64_t)q < n) x[k >> 2] |= (uint32_t)data[q] << (8 * (k & 3));
+            }
+            v = make_uint4(x[0], x[1], x[2], x[3]);
+        }
+        dst[i] = v;
+    }
+}
+
 // classify window wi of the text from the staged tile (wl = its index inside the tile, -1 .. PT_T)
 __device__ __forceinline__ TkWin pt_classify(const PtSmem& S, const TkBytesTile& src, const uint32_t* __restrict__ ds_mask,
                                              uint64_t n_windows, long long wi, int wl, const TkDeviceTables& T) {
@@ -144,25 +166,7 @@ __device__ __forceinline__ void pretok_tile(PtSmem& S, uint32_t b, const uint8_t
     const int t = threadIdx.x;
     const long long wi = (long long)b * PT_T + t;
     const uint64_t pos = (uint64_t)wi * 32u;
-    // stage [tile - halo, tile + 8 KiB + halo) in shared memory, zero outside the text
-    {
-        const long long g0 = (long long)b * (PT_T * 32) - PT_HALO;
-        uint4* dst = reinterpret_cast<uint4*>(S.bytes);
-        for (int i = t; i < (int)(sizeof(S.bytes) / 16); i += PT_T) {
-            const long long g = g0 + 16ll * i;
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (g >= 0 && (uint64_t)g + 16u <= n) v = __ldg(reinterpret_cast<const uint4*>(data + g));
-            else if (g + 16 > 0 && (uint64_t)(g < 0 ? 0 : g) < n) {
-                uint32_t x[4] = {0u, 0u, 0u, 0u};
-                for (int k = 0; k < 16; ++k) {
-                    const long long q = g + k;
-                    if (q >= 0 && (uint64_t)q < n) x[k >> 2] |= (uint32_t)data[q] << (8 * (k & 3));
-                }
-                v = make_uint4(x[0], x[1], x[2], x[3]);
-            }
-            dst[i] = v;
-        }
-    }
+    pt_stage_tile(S.bytes, b, data, n);
     __syncthreads();
     const TkBytesTile src{S.bytes + PT_HALO, (int64_t)b * (PT_T * 32)};
     TkWin c = pt_classify(S, src, ds_mask, n_windows, wi, t, T);
@@ -404,6 +408,96 @@ __global__ void __launch_bounds__(SG_T) pretok_apply_kernel(const TkkTileSummary
             const uint32_t h = rs_unpack(s.packed).head;
             if (h) nh = h;
         }
+    }
+}
+
+// =====================================================================================================
+// K1c: the split for the pattern STORED in tekken.json (tk_pretok_cfg.h), used by handles
+// created with TK_SPLIT_CONFIG.  Two kernels replace K1/K1s/K1f; every later stage is pattern-independent.
+//   cfg_mask_kernel  one thread per 32-byte window: 4-bit classes (SWAR for ASCII, two-stage table otherwise,
+//                    strict UTF-8), then the SAFE starts as bit logic -- positions that four purely local rules
+//                    prove to be piece starts (document start, a digit, after a digit, whitespace after
+//                    non-whitespace, punctuation after a letter).  They seed the piece-start mask.
+//   cfg_walk_kernel  one lane per safe start: the sequential leftmost-first matcher from piece to piece until the
+//                    next safe start / document / end of text, marking the piece starts in between (atomicOr).
+// A walk is as long as the distance to the next safe start: a word, a camelCase identifier, a whitespace run.
+// =====================================================================================================
+struct CfgSmem {
+    uint8_t bytes[PT_HALO + PT_T * 32 + PT_HALO];
+    TkCfgWin win[PT_T + 1];                      // [0] = the window before the tile
+};
+
+__global__ void __launch_bounds__(PT_T) cfg_mask_kernel(const uint8_t* __restrict__ data, uint64_t n, const uint32_t* __restrict__ ds_mask,
+                                                        uint32_t* __restrict__ safe_mask, uint32_t* __restrict__ start_mask,
+                                                        uint64_t n_windows, TkCfgTables T, unsigned long long* __restrict__ err_pos) {
+    __shared__ __align__(16) CfgSmem S;
+    const int t = threadIdx.x;
+    const uint32_t b = blockIdx.x;
+    const long long wi = (long long)b * PT_T + t;
+    const uint64_t pos = (uint64_t)wi * 32u;
+    pt_stage_tile(S.bytes, b, data, n);
+    __syncthreads();
+    const TkBytesTile src{S.bytes + PT_HALO, (int64_t)b * (PT_T * 32)};
+    auto classify = [&](long long w, int wl) -> TkCfgWin {
+        TkCfgWin z;
+        z.lead = 0xFFFFFFFFu; z.mU = z.mLO = z.mC = z.mM = z.mN = z.mW = z.mR = z.ds = z.bad = 0;
+        if (w < 0 || (uint64_t)w >= n_windows) return z;
+        const uint4* q = reinterpret_cast<const uint4*>(S.bytes + PT_HALO + wl * 32);
+        const uint4 a = q[0], c = q[1];
+        const uint32_t words[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+        return tk_cfg_classify_window(src, (uint64_t)w * 32u, words, ds_mask[w], T);
+    };
+    const TkCfgWin c = classify(wi, t);
+    S.win[t + 1] = c;
+    if (t == 0) S.win[0] = classify((long long)b * PT_T - 1, -1);
+    __syncthreads();
+    if ((uint64_t)wi < n_windows) {
+        const uint32_t keep = (pos + 32 <= n) ? 0xFFFFFFFFu : (uint32_t)((2ull << (n - pos)) - 1ull);   // bit n: the end sentinel
+        const uint32_t safe = tk_cfg_safe_mask(S.win[t], c) & keep;
+        safe_mask[wi] = safe;
+        start_mask[wi] = safe;
+        const uint32_t valid = (pos + 32 <= n) ? 0xFFFFFFFFu : (uint32_t)((1ull << (n - pos)) - 1ull);
+        if (c.bad & valid) atomicMin(err_pos, (unsigned long long)(pos + (uint64_t)(__ffs((int)(c.bad & valid)) - 1)));
+    }
+}
+
+#define CW_T 256
+__global__ void __launch_bounds__(CW_T) cfg_walk_kernel(const uint8_t* __restrict__ data, uint64_t n, const uint32_t* __restrict__ ds_mask,
+                                                        const uint32_t* __restrict__ safe_mask, uint32_t* __restrict__ start_mask,
+                                                        uint64_t n_windows, TkCfgTables T, const unsigned long long* __restrict__ err_pos) {
+    __shared__ uint16_t list[CW_T * 32];
+    __shared__ uint32_t wsum[CW_T / 32];
+    __shared__ uint32_t n_list;
+    if (*err_pos != ~0ull) return;                    // invalid UTF-8: the call fails, and the matcher assumes valid text
+    const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    const uint64_t w = (uint64_t)blockIdx.x * CW_T + t;
+    uint32_t m = w < n_windows ? safe_mask[w] : 0u;
+    // the tile's safe starts, in order, one list entry each
+    uint32_t inc = (uint32_t)__popc(m);
+    const uint32_t mine = inc;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if (lane >= (uint32_t)d) inc += o;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    uint32_t before = inc - mine, all = 0;
+    for (uint32_t x = 0; x < CW_T / 32; ++x) { if (x < warp) before += wsum[x]; all += wsum[x]; }
+    if (t == 0) n_list = all;
+    while (m) {
+        list[before++] = (uint16_t)(t * 32u + (uint32_t)(__ffs((int)m) - 1));
+        m &= m - 1;
+    }
+    __syncthreads();
+    const uint32_t cnt = n_list;
+    const TkBytesChecked src{data, n};
+    const uint64_t tile_pos = (uint64_t)blockIdx.x * CW_T * 32u;
+    for (uint32_t k = t; k < cnt; k += CW_T) {
+        const int64_t q0 = (int64_t)(tile_pos + list[k]);
+        if ((uint64_t)q0 >= n) continue;              // the end sentinel is not a piece
+        tk_cfg_walk(src, q0, safe_mask, ds_mask, (int64_t)n, T,
+                    [&](int64_t p) { atomicOr(start_mask + (p >> 5), 1u << (p & 31)); });
     }
 }
 
@@ -1502,7 +1596,7 @@ static cudaError_t launch_lanemerge(int blocks_per_sm, int sm_count, const uint8
 cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const uint64_t* d_doc_off, uint64_t off_base,
                           uint64_t n_docs, uint64_t n, int add_bos, int add_eos, uint32_t* d_out, uint64_t out_cap, uint64_t* d_tok_off,
                           void* d_ws, const EncodeLayout& L, uint32_t* d_scratch, uint64_t scratch_cap, int sm_count,
-                          cudaStream_t st, StageTimer* timer, const HotTables* hot) {
+                          cudaStream_t st, StageTimer* timer, const HotTables* hot, const CfgSplitTables* cfg) {
     unsigned char* ws = (unsigned char*)d_ws;
     uint32_t* small = (uint32_t*)(ws + L.off_small);
     uint32_t* ds = (uint32_t*)(ws + L.off_ds);
@@ -1546,6 +1640,16 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
     docmark_kernel<<<(unsigned)ceil_div(n_docs + 1, 256), 256, 0, st>>>(d_doc_off, off_base, n_docs, n, add_bos ? 1u : 0u, add_eos ? 1u : 0u, ds, docfirst, doccnt, tile_count, flags);
     TK_LAUNCHED();
     if (timer) timer->mark(st, "pretok");
+    if (cfg) {
+        // the pattern stored in tekken.json: safe starts by bit logic, then one matcher walk per safe start.  The safe
+        // mask lives in the long-piece index array, which is not written before K2a.
+        const TkCfgTables CT{cfg->stage1, cfg->stage2};
+        cfg_mask_kernel<<<(unsigned)L.n_tiles, PT_T, 0, st>>>(d_data, n, ds, longword, start, L.n_windows, CT, err_pos);
+        TK_LAUNCHED();
+        if (timer) timer->mark(st, "pretok_walk");
+        cfg_walk_kernel<<<(unsigned)ceil_div(L.n_windows, CW_T), CW_T, 0, st>>>(d_data, n, ds, longword, start, L.n_windows, CT, err_pos);
+        TK_LAUNCHED();
+    } else {
     pretok_kernel<<<(unsigned)L.n_tiles, PT_T, 0, st>>>(d_data, n, ds, start, L.n_windows, T, summ, err_pos);
     TK_LAUNCHED();
     if (timer) timer->mark(st, "pretok_carry");
@@ -1564,6 +1668,7 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
     pretok_fix_kernel<<<(unsigned)(L.n_tiles < (uint64_t)(2 * sm_count) ? L.n_tiles : (uint64_t)(2 * sm_count)), PT_T, 0, st>>>(
         d_data, n, ds, start, L.n_windows, T, carry, worklist, work_count, err_pos);
     TK_LAUNCHED();
+    }
     if (timer) timer->mark(st, "longmark");
     longmark_kernel<<<(unsigned)ceil_div(L.n_windows, 256), 256, 0, st>>>(start, L.n_windows, n, longword, recs, n_long);
     TK_LAUNCHED();

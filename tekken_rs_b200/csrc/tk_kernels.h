@@ -86,11 +86,17 @@ struct HotTables {
     bool enabled = false;     // the device accepted a persisting-L2 carve-out that covers it
 };
 
+// class tables of the split for the pattern stored in tekken.json (tk_pretok_cfg.h); null = the reference's pattern
+struct CfgSplitTables {
+    const uint16_t* stage1 = nullptr;
+    const uint8_t* stage2 = nullptr;
+};
+
 size_t encode_workspace_bytes(uint64_t n, uint64_t n_docs, EncodeLayout* L);
 cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const uint64_t* d_doc_off, uint64_t off_base,
                           uint64_t n_docs, uint64_t n, int add_bos, int add_eos, uint32_t* d_out, uint64_t out_cap, uint64_t* d_tok_off,
                           void* d_ws, const EncodeLayout& L, uint32_t* d_scratch, uint64_t scratch_cap, int sm_count,
-                          cudaStream_t st, StageTimer* timer, const HotTables* hot = nullptr);
+                          cudaStream_t st, StageTimer* timer, const HotTables* hot = nullptr, const CfgSplitTables* cfg = nullptr);
 
 cudaError_t publish_counters(const void* d_ws, const EncodeLayout& L, uint32_t* mapped_dev, cudaStream_t st);
 

@@ -1,15 +1,15 @@
-// tk_pretok_cfg.h -- GROUNDWORK (not yet part of the library): the split for the pattern STORED in
-// tekken.json (Mistral's own Tekken regex; the reference ignores it, src/tekkenizer.rs:74,123):
+// tk_pretok_cfg.h -- the split for the pattern STORED in tekken.json (Mistral's own Tekken regex; the reference
+// ignores it, src/tekkenizer.rs:74,123), used by handles created with TK_SPLIT_CONFIG:
 //
 //   [^\r\n\p{L}\p{N}]?[\p{Lu}\p{Lt}\p{Lm}\p{Lo}\p{M}]*[\p{Ll}\p{Lm}\p{Lo}\p{M}]+
 //   | [^\r\n\p{L}\p{N}]?[\p{Lu}\p{Lt}\p{Lm}\p{Lo}\p{M}]+[\p{Ll}\p{Lm}\p{Lo}\p{M}]*
 //   | \p{N} | ?[^\s\p{L}\p{N}]+[\r\n/]* | \s*[\r\n]+ | \s+(?!\S) | \s+
 //
-// Plan: four purely local rules mark positions that are always piece starts ("safe starts":
-// tk_cfg_safe_start); between two safe starts one lane runs the sequential matcher (tk_cfg_match_end) -- the
-// lane-per-irregular-unit scheme of the merge stage.  Both functions are __host__ __device__;
-// tests/native/cfgsplit_host.cpp runs them on the CPU against the oracle (tests/test_cfgsplit_model.py).
-// No kernel includes this header yet.
+// Four purely local rules mark positions that are always piece starts ("safe starts": tk_cfg_safe_start /
+// tk_cfg_safe_mask); between two safe starts one lane runs the sequential matcher (tk_cfg_match_end, tk_cfg_walk) --
+// the lane-per-irregular-unit scheme of the merge stage.  Everything is __host__ __device__: cfg_mask_kernel and
+// cfg_walk_kernel (tk_kernels.cu) run it on the GPU, tests/native/cfgsplit_host.cpp runs the same code on the CPU
+// against the oracle (tests/test_cfgsplit_model.py).
 #pragma once
 #include "tk_common.h"
 #include "tk_pretok.h"      // SWAR helpers, byte sources, TK_FFS

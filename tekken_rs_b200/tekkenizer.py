@@ -35,6 +35,12 @@ class SpecialTokenPolicy(enum.IntEnum):
     Raise = 2
 
 
+class SplitMode(enum.IntEnum):
+    """include/tekken_b200.h tk_split_mode"""
+    Reference = 0      # the literal of src/tekkenizer.rs:123 (what the reference computes)
+    Config = 1         # the pattern stored in tekken.json
+
+
 class TokenizerVersion(enum.IntEnum):
     """src/config.rs:97-103"""
     V3 = 3
@@ -91,16 +97,17 @@ class Tekkenizer:
 
     # ---- construction -------------------------------------------------------------------
     @classmethod
-    def from_file(cls, path, device: int = 0) -> "Tekkenizer":
-        """Tekkenizer::from_file (src/tekkenizer.rs:222-248)."""
+    def from_file(cls, path, device: int = 0, split: "SplitMode" = 0) -> "Tekkenizer":
+        """Tekkenizer::from_file (src/tekkenizer.rs:222-248).  ``split`` = SplitMode.Config honours the pattern stored
+        in the file (Mistral's own) instead of the literal the reference hard-codes."""
         lib = _lib.load()
         h = ctypes.c_void_p()
-        _check(lib.tk_load_file(str(path).encode(), device, ctypes.byref(h)))
+        _check(lib.tk_load_file_ex(str(path).encode(), device, int(split), ctypes.byref(h)))
         return cls(h.value)
 
     @classmethod
     def new(cls, vocab: Sequence[dict], special_tokens: Sequence[dict], pattern: str, vocab_size: int,
-            num_special_tokens: int, version, audio_config=None, device: int = 0) -> "Tekkenizer":
+            num_special_tokens: int, version, audio_config=None, device: int = 0, split: "SplitMode" = 0) -> "Tekkenizer":
         """Tekkenizer::new (src/tekkenizer.rs:71-191).  ``pattern`` is ignored as in the reference;
         ``audio_config`` is outside the text path and must be None."""
         if audio_config is not None:
@@ -126,8 +133,8 @@ class Tekkenizer:
             sa[i].token_str = b
             sa[i].is_control = 1 if e.get("is_control", True) else 0
         h = ctypes.c_void_p()
-        _check(lib.tk_new(va, len(vocab), sa, len(special_tokens), pattern.encode("utf-8"), vocab_size,
-                          num_special_tokens, int(version), device, ctypes.byref(h)))
+        _check(lib.tk_new_ex(va, len(vocab), sa, len(special_tokens), pattern.encode("utf-8"), vocab_size,
+                             num_special_tokens, int(version), device, int(split), ctypes.byref(h)))
         return cls(h.value)
 
     def close(self):
@@ -153,6 +160,9 @@ class Tekkenizer:
 
     def device(self) -> int:
         return self._lib.tk_device_of(self._h)
+
+    def split_mode(self) -> SplitMode:
+        return SplitMode(self._lib.tk_split_mode_of(self._h))
 
     def get_control_token(self, token_str: str) -> int:
         v = ctypes.c_uint32()
