@@ -135,17 +135,26 @@ int tk_encode(const tk_tokenizer *t, const uint8_t *utf8, size_t len, int add_bo
 /* New: encode_batch.  Documents are data[doc_off[d] .. doc_off[d+1]) (n_docs+1 offsets,
    doc_off[0] == 0).  ids of all documents are returned back to back in *tokens; *tok_off
    gets n_docs+1 offsets into it.  Host buffers in, pinned host buffers out.  The batch may be
-   of any size (it is streamed through the device in chunks cut at document boundaries); one
-   document is limited to 8 GiB. */
+   of any size: it is streamed through the device in chunks cut at document boundaries, and a document larger than a
+   chunk is cut at context-free piece boundaries (an ASCII space between ASCII letters / digits), so its size is not
+   limited either unless it contains no such boundary for 4 GiB.  `data` may be pageable or page-locked memory. */
 int tk_encode_batch(const tk_tokenizer *t, const uint8_t *data, const uint64_t *doc_off,
                     size_t n_docs, int add_bos, int add_eos, uint32_t **tokens, uint64_t **tok_off);
+
+/* One call, all GPUs: the same as tk_encode_batch over `n_handles` handles of the SAME tokenizer on different
+   devices (tk_load_file(path, g, ..) for g = 0 .. n-1).  The batch's chunks are dealt to the devices, each device runs
+   its pipeline on its own host thread, and ids / offsets land in one result buffer in document order (no stitching
+   pass; no collective: documents are independent).  SURVEY 8(b) "batch calls fan out to all GPUs internally". */
+int tk_encode_batch_multi(tk_tokenizer *const *handles, size_t n_handles, const uint8_t *data,
+                          const uint64_t *doc_off, size_t n_docs, int add_bos, int add_eos,
+                          uint32_t **tokens, uint64_t **tok_off);
 
 /* Zero-copy form: every pointer is a device pointer on the handle's device, `stream` is a
    cudaStream_t (NULL = default stream).  d_tokens must hold tokens_capacity ids
    (total_bytes + 2*n_docs always suffices); d_tok_off holds n_docs+1 offsets.  The call
    synchronises the stream before returning; *n_tokens is the total id count.  On
    TK_ERR_BUFFER_TOO_SMALL *n_tokens is the capacity that would have been enough.  d_data must
-   be 16-byte aligned; total_bytes < 8 GiB and n_docs < 2^32 - 2 per call (TK_ERR_INVALID_ARGUMENT
+   be 16-byte aligned; total_bytes < 4 GiB and n_docs < 2^32 - 2 per call (TK_ERR_INVALID_ARGUMENT
    otherwise: shard the batch, tk_shard_plan). */
 int tk_encode_batch_device(const tk_tokenizer *t, const uint8_t *d_data, const uint64_t *d_doc_off,
                            size_t n_docs, uint64_t total_bytes, int add_bos, int add_eos,
@@ -187,6 +196,10 @@ int tk_shard_plan(const uint64_t *doc_off, size_t n_docs, size_t n_shards, uint6
 void tk_buffer_free(void *p);
 const char *tk_last_error(void);
 const char *tk_status_name(int status);
+/* Tuning knob of the host-buffer calls: size of the chunks a batch is streamed through the device in (process-wide;
+   0 restores the default of 48 MB, also settable with TEKKEN_B200_CHUNK_MB).  The tests use it to exercise the
+   chunk-boundary and document-slicing logic on small inputs. */
+void tk_set_chunk_bytes(uint64_t bytes);
 /* Kernel launches issued by this process so far (for benchmark accounting). */
 uint64_t tk_kernel_launch_count(void);
 /* Per-stage device time of the most recent tk_encode_batch_device call on this handle, in

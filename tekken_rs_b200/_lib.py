@@ -55,6 +55,8 @@ PROTOTYPES = {
                                  ctypes.POINTER(ctypes.c_size_t)]),
     "tk_encode_batch": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.POINTER(c_vp),
                                        ctypes.POINTER(c_vp)]),
+    "tk_encode_batch_multi": (ctypes.c_int, [ctypes.POINTER(c_vp), ctypes.c_size_t, c_vp, c_vp, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
+                                             ctypes.POINTER(c_vp), ctypes.POINTER(c_vp)]),
     "tk_encode_batch_device": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_int, ctypes.c_int,
                                               c_vp, ctypes.c_uint64, c_vp, c_u64p, c_vp]),
     "tk_decode": (ctypes.c_int, [c_vp, c_vp, ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(c_vp),
@@ -69,6 +71,7 @@ PROTOTYPES = {
     "tk_buffer_free": (None, [c_vp]),
     "tk_last_error": (ctypes.c_char_p, []),
     "tk_status_name": (ctypes.c_char_p, [ctypes.c_int]),
+    "tk_set_chunk_bytes": (None, [ctypes.c_uint64]),
     "tk_kernel_launch_count": (ctypes.c_uint64, []),
     "tk_set_stage_timing": (None, [c_vp, ctypes.c_int]),
     "tk_last_encode_counters": (ctypes.c_size_t, [c_vp, c_u64p, ctypes.c_size_t]),

@@ -14,6 +14,11 @@
 #include <cstring>
 #include <map>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <memory>
+#include <thread>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -202,12 +207,24 @@ struct tk_tokenizer {
         uint32_t* d_small_map = nullptr;   // its device address
         cudaEvent_t done = nullptr;    // recorded after the counters have been published
         cudaEvent_t ev_in = nullptr, ev_out = nullptr;   // pipeline: text has arrived / ids have left
+        uint8_t* h_stage = nullptr;    // pinned staging of pageable caller memory (offsets, then text)
+        size_t stage_cap = 0;
         tkk::EncodeLayout L;
     };
     static constexpr int kSlots = 4;
     EncSlot slot[kSlots];          // host-buffer encode: chunks of a batch pipeline through these
     cudaStream_t pipe_st[3] = {nullptr, nullptr, nullptr};   // ... on an upload, a kernel and a download stream
     EncSlot dev_slot;              // device-pointer encode (caller's stream)
+    // the latency path (tk_encode of a short text): mapped pinned in/out buffers + a stream per slot
+    struct FastSlot {
+        std::mutex mu;
+        cudaStream_t st = nullptr;
+        uint8_t* h_in = nullptr; uint8_t* d_in = nullptr;
+        uint32_t* h_out = nullptr; uint32_t* d_out = nullptr;
+        uint32_t seq = 0;
+    };
+    static constexpr int kFastSlots = 4;
+    FastSlot fast[kFastSlots];
     bool timing = false;
     bool counted = false;          // included in g_live_handles
     tkk::HotTables hot;            // pair + byte-pair table allocation (L2 persistence window of the merge kernels)
@@ -394,10 +411,16 @@ extern "C" void tk_free(tk_tokenizer* t) {
             if (s.st) { cudaStreamSynchronize(s.st); cudaStreamDestroy(s.st); }
             s.ws.release(); s.scratch.release(); s.in_data.release(); s.in_off.release(); s.out_tok.release(); s.out_off.release();
             if (s.h_small) cudaFreeHost(s.h_small);
+            if (s.h_stage) cudaFreeHost(s.h_stage);
             if (s.done) cudaEventDestroy(s.done);
             if (s.ev_in) cudaEventDestroy(s.ev_in);
             if (s.ev_out) cudaEventDestroy(s.ev_out);
         };
+        for (auto& f : t->fast) {
+            if (f.st) { cudaStreamSynchronize(f.st); cudaStreamDestroy(f.st); }
+            if (f.h_in) cudaFreeHost(f.h_in);
+            if (f.h_out) cudaFreeHost(f.h_out);
+        }
         for (auto& ps : t->pipe_st) if (ps) { cudaStreamSynchronize(ps); cudaStreamDestroy(ps); }
         for (auto& sl : t->slot) drop(sl);
         drop(t->dev_slot);
@@ -597,181 +620,521 @@ extern "C" int tk_encode_batch_device(const tk_tokenizer* tc, const uint8_t* d_d
     return fail(TK_ERR_CUDA, "huge-piece scratch could not be grown");
 }
 
-// Host buffers in, pinned host buffers out.  The batch is cut at document boundaries into chunks of
-// about kChunkBytes that flow through kSlots streams: while chunk i is being encoded, chunk i+1 is
-// on its way to the device and the ids of chunk i-1 are on their way back.
-extern "C" int tk_encode_batch(const tk_tokenizer* tc, const uint8_t* data, const uint64_t* doc_off, size_t n_docs, int add_bos,
-                               int add_eos, uint32_t** tokens, uint64_t** tok_off) {
-    int rc = check_encode_args(tc, add_bos, add_eos);
-    if (rc) return rc;
+// ------------------------------------------------------------------------------------------ host-buffer encode engine
+//
+// Host buffers in, pinned host buffers out, on one GPU or on all GPUs of the box with ONE call.
+//
+//   plan      the batch is cut at document boundaries into chunks of about kChunkBytes.  A document larger than 1.5
+//             chunks is cut INSIDE, at a context-free piece boundary: before an ASCII space that follows an ASCII
+//             letter / digit and precedes an ASCII letter -- both patterns start a piece there whatever comes before
+//             (the previous piece cannot contain the space, and " x..." matches the word alternative), and no lookahead
+//             of an earlier piece reaches past the letter / digit.  The slices are encoded as separate texts; BOS / EOS
+//             go to the first / last slice.  So a 1 GiB document pipelines like a batch and needs a chunk's workspace.
+//   deal      chunk c goes to device c mod N.  Every device runs the three-stream pipeline (upload, kernels,
+//             download; kSlots buffer slots) over its chunks on its own host thread.
+//   stitch    the id count of a chunk is known when its kernels finish; its place in the output when every earlier
+//             chunk has reported its count.  Ids are then copied straight to that place in ONE pinned result buffer
+//             (sized from the first chunk's ids-per-byte ratio; if the estimate is too small the call is repeated
+//             once with the worst-case size), token offsets likewise: no per-shard buffers, no stitching pass.
+//   pageable  caller memory that is not page-locked is staged through pinned per-slot buffers by a small pool of
+//             copy threads (a direct cudaMemcpyAsync from pageable memory is synchronous and runs at a third of the
+//             speed).
+// TEKKEN_B200_TRACE=1 prints the device timeline of every chunk on stderr.
+
+namespace {
+
+class CopyPool {
+  public:
+    static CopyPool& get() {
+        static CopyPool* p = new CopyPool();      // leaked on purpose: worker threads may outlive static destructors
+        return *p;
+    }
+    // dst/src do not overlap.  The caller copies too; returns when all n bytes are in place.
+    void parallel_memcpy(void* dst, const void* src, size_t n) {
+        constexpr size_t kPiece = 1 << 20;
+        if (n <= 2 * kPiece || threads_.empty()) { memcpy(dst, src, n); return; }
+        auto job = std::make_shared<Job>();
+        job->dst = (char*)dst; job->src = (const char*)src; job->n = n;
+        job->pieces = (n + kPiece - 1) / kPiece;
+        const size_t helpers = std::min(threads_.size(), job->pieces - 1);
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            for (size_t i = 0; i < helpers; ++i) q_.push_back(job);
+        }
+        cv_.notify_all();
+        run(*job);
+        while (job->done.load(std::memory_order_acquire) < job->pieces) std::this_thread::yield();
+    }
+
+  private:
+    struct Job {
+        char* dst; const char* src; size_t n, pieces;
+        std::atomic<size_t> next{0}, done{0};
+    };
+    static void run(Job& j) {
+        constexpr size_t kPiece = 1 << 20;
+        for (;;) {
+            const size_t p = j.next.fetch_add(1);
+            if (p >= j.pieces) return;
+            const size_t o = p * kPiece, len = std::min(kPiece, j.n - o);
+            memcpy(j.dst + o, j.src + o, len);
+            j.done.fetch_add(1, std::memory_order_release);
+        }
+    }
+    CopyPool() {
+        unsigned n = std::thread::hardware_concurrency() / 2;
+        if (const char* e = getenv("TEKKEN_B200_COPY_THREADS")) n = (unsigned)atoi(e);
+        n = std::max(1u, std::min(n, 12u));
+        for (unsigned i = 0; i + 1 < n; ++i) threads_.emplace_back([this] { loop(); });
+        for (auto& t : threads_) t.detach();
+    }
+    void loop() {
+        for (;;) {
+            std::shared_ptr<Job> j;
+            {
+                std::unique_lock<std::mutex> g(mu_);
+                cv_.wait(g, [this] { return !q_.empty(); });
+                j = q_.front();
+                q_.pop_front();
+            }
+            run(*j);
+        }
+    }
+    std::vector<std::thread> threads_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<std::shared_ptr<Job>> q_;
+};
+
+struct Chunk {
+    size_t doc_begin, n_docs;        // documents of the chunk; a slice of a big document: that document, n_docs = 1
+    uint64_t byte_begin, n_bytes;
+    bool partial, first, last;       // slice of one document; its first / last slice
+};
+
+inline bool ascii_alpha(uint8_t c) { return (uint8_t)((c | 0x20u) - 'a') < 26u; }
+inline bool ascii_alnum(uint8_t c) { return ascii_alpha(c) || (uint8_t)(c - '0') < 10u; }
+// a piece starts at byte p whatever the context (see above); p - 1 and p + 1 are inside the document
+inline bool context_free_cut(const uint8_t* d, uint64_t p) { return d[p] == ' ' && ascii_alpha(d[p + 1]) && ascii_alnum(d[p - 1]); }
+
+constexpr uint64_t kMaxDeviceCall = (1ull << 32) - (1ull << 20);     // one device call takes < 4 GiB of text
+
+int plan_chunks(const uint8_t* data, const uint64_t* doc_off, size_t n_docs, uint64_t chunk_bytes, std::vector<Chunk>& out) {
+    const uint64_t big = chunk_bytes + chunk_bytes / 2;
+    size_t d = 0;
+    while (d < n_docs) {
+        const uint64_t len_d = doc_off[d + 1] - doc_off[d];
+        if (len_d > big) {
+            uint64_t pos = doc_off[d];
+            const uint64_t end = doc_off[d + 1];
+            bool first = true;
+            while (pos < end) {
+                uint64_t cut = end;
+                if (end - pos > big) {
+                    const uint64_t target = pos + chunk_bytes, lo = pos + chunk_bytes / 2;
+                    cut = 0;
+                    for (uint64_t p = target; p > lo; --p) if (context_free_cut(data, p)) { cut = p; break; }
+                    if (!cut) {
+                        const uint64_t hi = std::min(end - 1, pos + kMaxDeviceCall);
+                        for (uint64_t p = target + 1; p < hi; ++p) if (context_free_cut(data, p)) { cut = p; break; }
+                    }
+                    if (!cut) cut = end;      // no such boundary (one endless run): the rest goes as one piece of work
+                }
+                if (cut - pos >= kMaxDeviceCall)
+                    return fail(TK_ERR_INVALID_ARGUMENT, "document %zu has no cut point within 4 GiB (a single run of that length); it cannot be encoded in one device call", d);
+                out.push_back({d, 1, pos, cut - pos, true, first, cut == end});
+                first = false;
+                pos = cut;
+            }
+            ++d;
+            continue;
+        }
+        const size_t b = d;
+        const uint64_t begin = doc_off[b];
+        size_t e = std::upper_bound(doc_off + b + 1, doc_off + n_docs + 1, begin + chunk_bytes) - doc_off;   // first doc END beyond the target
+        if (e > n_docs) e = n_docs;
+        if (e <= b) e = b + 1;
+        // a big document is never part of an ordinary chunk (it is sliced above)
+        for (size_t k = (e - b > 4 ? e - 2 : b); k < e; ++k)
+            if (doc_off[k + 1] - doc_off[k] > big) { e = k > b ? k : b + 1; break; }
+        out.push_back({b, e - b, begin, doc_off[e] - begin, false, true, true});
+        d = e;
+    }
+    if (out.empty()) out.push_back({0, 0, 0, 0, false, true, true});
+    return TK_OK;
+}
+
+struct EncodeJob {
+    const uint8_t* data = nullptr;
+    const uint64_t* doc_off = nullptr;
+    size_t n_docs = 0;
+    uint64_t total = 0;
+    int add_bos = 0, add_eos = 0;
+    bool pageable = false;
+    std::vector<Chunk> chunks;
+    uint64_t forced_cap = 0;          // second attempt: worst-case output size
+    // progress shared by the device workers
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<int64_t> ntok;        // id count per chunk, -1 = not known yet
+    std::vector<uint64_t> prefix;     // prefix[c] = ids before chunk c, valid for c <= known
+    size_t known = 0;
+    uint32_t* h_tok = nullptr;
+    uint64_t h_cap = 0;
+    uint64_t* h_off = nullptr;
+    bool alloc_failed = false;
+    std::atomic<bool> abort{false};
+    bool overflow = false;            // the estimate was too small: repeat with the worst-case size
+    int rc = TK_OK;
+    std::string err;
+
+    void fail_with(int code, const std::string& msg) {
+        std::lock_guard<std::mutex> g(mu);
+        if (rc == TK_OK) { rc = code; err = msg; }
+        abort.store(true);
+        cv.notify_all();
+    }
+};
+
+const uint64_t kDefaultChunkBytes = [] {
+    const char* e = getenv("TEKKEN_B200_CHUNK_MB");          // tuning knob; default 48 MB
+    const long mb = e ? atol(e) : 0;
+    return (uint64_t)(mb > 0 ? mb : 48) << 20;
+}();
+std::atomic<uint64_t> g_chunk_bytes{0};                     // tk_set_chunk_bytes; 0 = the default
+
+}  // namespace
+
+// One device's share of an encode job: chunks g, g + stride, ...  Runs on its own host thread (the caller's for
+// device 0).  Returns TK_OK or the status it also stored in the job.
+static int encode_worker(tk_tokenizer* t, EncodeJob& J, size_t g, size_t stride) {
+    std::lock_guard<std::mutex> lock(t->mu);
+    DeviceGuard dg(t->device);
+    auto bail = [&](int code) {
+        J.fail_with(code, g_last_error);
+        for (auto& ps : t->pipe_st) if (ps) cudaStreamSynchronize(ps);
+        return code;
+    };
+    if (!dg.ok) return bail(fail(TK_ERR_CUDA, "cudaSetDevice(%d) failed", t->device));
+#define W_CUDA(x)                                                                                          \
+    do {                                                                                                   \
+        cudaError_t e_ = (x);                                                                              \
+        if (e_ != cudaSuccess) return bail(fail(TK_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)));         \
+    } while (0)
+    for (auto& ps : t->pipe_st) if (!ps) W_CUDA(cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
+    cudaStream_t st_up = t->pipe_st[0], st_k = t->pipe_st[1], st_down = t->pipe_st[2];
+    std::vector<size_t> mine;
+    for (size_t c = g; c < J.chunks.size(); c += stride) mine.push_back(c);
+    const size_t n_mine = mine.size();
+
+    static const bool kTrace = getenv("TEKKEN_B200_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    std::vector<double> thost;
+    const auto host_now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    if (kTrace) {
+        tev.resize(n_mine * 6 + 1);
+        thost.resize(n_mine * 3 + 1);
+        for (auto& e : tev) cudaEventCreate(&e);
+        cudaEventRecord(tev[0], st_up);
+        thost[0] = host_now();
+    }
+    struct TraceGuard {
+        std::vector<cudaEvent_t>& ev;
+        ~TraceGuard() { for (auto& e : ev) cudaEventDestroy(e); }
+    } trace_guard{tev};
+    auto mark = [&](size_t i, int k, cudaStream_t st) { if (kTrace) cudaEventRecord(tev[1 + i * 6 + k], st); };
+
+    auto caps = [&](const Chunk& c) { return c.n_bytes + 2 * (uint64_t)c.n_docs + 2; };
+    auto bos_of = [&](const Chunk& c) { return J.add_bos && c.first ? 1 : 0; };
+    auto eos_of = [&](const Chunk& c) { return J.add_eos && c.last ? 1 : 0; };
+    auto launch = [&](size_t i) -> int {      // the kernels of my i-th chunk (its text is on the device or on its way)
+        tk_tokenizer::EncSlot& s = t->slot[i % tk_tokenizer::kSlots];
+        const Chunk& c = J.chunks[mine[i]];
+        return encode_issue(t, s, (const uint8_t*)s.in_data.p, (const uint64_t*)s.in_off.p, c.partial ? 0 : c.byte_begin, c.n_docs, c.n_bytes,
+                            bos_of(c), eos_of(c), (uint32_t*)s.out_tok.p, caps(c), (uint64_t*)s.out_off.p, st_k, false);
+    };
+    auto issue = [&](size_t i) -> int {
+        tk_tokenizer::EncSlot& s = t->slot[i % tk_tokenizer::kSlots];
+        const Chunk& c = J.chunks[mine[i]];
+        if (!s.ev_in) {
+            CUDA_OR_FAIL(cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
+            CUDA_OR_FAIL(cudaEventCreateWithFlags(&s.ev_out, cudaEventDisableTiming));
+        }
+        if (kTrace) thost[1 + i * 3] = host_now();
+        const size_t off_bytes = (c.n_docs + 1) * 8;
+        CUDA_OR_FAIL(s.in_data.ensure(c.n_bytes + 64));
+        CUDA_OR_FAIL(s.in_off.ensure(off_bytes));
+        CUDA_OR_FAIL(s.out_tok.ensure(caps(c) * 4));
+        CUDA_OR_FAIL(s.out_off.ensure(off_bytes));
+        const uint8_t* src = J.data + c.byte_begin;
+        const uint64_t* src_off = J.doc_off + c.doc_begin;
+        if (J.pageable || c.partial) {
+            // pinned staging: [offsets | text]; the previous upload from it has long finished (kSlots chunks ago), but say so
+            const size_t need = ((off_bytes + 63) & ~(size_t)63) + (J.pageable ? c.n_bytes : 0) + 64;
+            if (s.stage_cap < need) {
+                if (s.h_stage) { cudaStreamSynchronize(st_up); cudaFreeHost(s.h_stage); }
+                s.h_stage = nullptr; s.stage_cap = 0;
+                CUDA_OR_FAIL(cudaHostAlloc((void**)&s.h_stage, need + need / 8, cudaHostAllocDefault));
+                s.stage_cap = need + need / 8;
+            } else if (i >= (size_t)tk_tokenizer::kSlots) CUDA_OR_FAIL(cudaEventSynchronize(s.ev_in));
+            uint64_t* so = (uint64_t*)s.h_stage;
+            if (c.partial) { so[0] = 0; so[1] = c.n_bytes; }
+            else memcpy(so, src_off, off_bytes);
+            src_off = so;
+            if (J.pageable) {
+                uint8_t* sd = s.h_stage + ((off_bytes + 63) & ~(size_t)63);
+                CopyPool::get().parallel_memcpy(sd, src, c.n_bytes);
+                src = sd;
+            }
+        }
+        if (i >= (size_t)tk_tokenizer::kSlots) CUDA_OR_FAIL(cudaStreamWaitEvent(st_up, s.done, 0));
+        mark(i, 0, st_up);
+        if (c.n_bytes) CUDA_OR_FAIL(cudaMemcpyAsync(s.in_data.p, src, c.n_bytes, cudaMemcpyHostToDevice, st_up));
+        CUDA_OR_FAIL(cudaMemcpyAsync(s.in_off.p, src_off, off_bytes, cudaMemcpyHostToDevice, st_up));
+        mark(i, 1, st_up);
+        CUDA_OR_FAIL(cudaEventRecord(s.ev_in, st_up));
+        CUDA_OR_FAIL(cudaStreamWaitEvent(st_k, s.ev_in, 0));
+        if (i >= (size_t)tk_tokenizer::kSlots) CUDA_OR_FAIL(cudaStreamWaitEvent(st_k, s.ev_out, 0));
+        mark(i, 2, st_k);
+        const int r = launch(i);
+        mark(i, 3, st_k);
+        if (kTrace) thost[2 + i * 3] = host_now();
+        return r;
+    };
+
+    // kAhead chunks are always queued ahead, so this thread sits in the wait for chunk i when it completes and its
+    // ids start their way back at once
+    constexpr size_t kAhead = tk_tokenizer::kSlots - 1;
+    int rc = TK_OK;
+    for (size_t i = 0; i < kAhead && i < n_mine; ++i) { rc = issue(i); if (rc) return bail(rc); }
+    for (size_t i = 0; i < n_mine; ++i) {
+        if (J.abort.load()) return bail(J.rc ? J.rc : TK_ERR_CUDA);
+        tk_tokenizer::EncSlot& s = t->slot[i % tk_tokenizer::kSlots];
+        const size_t ci = mine[i];
+        const Chunk& c = J.chunks[ci];
+        uint64_t n_tok = 0;
+        for (int attempt = 0;; ++attempt) {
+            bool retry = false;
+            rc = encode_finish(t, s, st_k, c.n_bytes, caps(c), c.byte_begin, &n_tok, &retry, false);
+            if (rc) return bail(rc);
+            if (!retry) break;
+            if (attempt) return bail(fail(TK_ERR_CUDA, "huge-piece scratch could not be grown"));
+            rc = launch(i);
+            if (rc) return bail(rc);
+        }
+        uint64_t my_prefix = 0;
+        {
+            std::unique_lock<std::mutex> lk(J.mu);
+            J.ntok[ci] = (int64_t)n_tok;
+            while (J.known < J.chunks.size() && J.ntok[J.known] >= 0) { J.prefix[J.known + 1] = J.prefix[J.known] + (uint64_t)J.ntok[J.known]; ++J.known; }
+            if (ci == 0 && !J.h_tok) {
+                // the result buffer, sized from the first chunk's ids per byte (the worst case on the second attempt)
+                const uint64_t worst = J.total + 2 * (uint64_t)J.n_docs + 2;
+                uint64_t cap = worst;
+                if (!J.forced_cap && J.chunks.size() > 1) {
+                    const double ratio = (double)n_tok / (double)std::max<uint64_t>(1, c.n_bytes);
+                    cap = std::min(worst, (uint64_t)(ratio * 1.25 * (double)J.total) + 2 * (uint64_t)J.n_docs + (1u << 16));
+                }
+                if (J.chunks.size() == 1) cap = n_tok + 2;
+                lk.unlock();
+                uint32_t* p = (uint32_t*)g_pool.get(std::max<uint64_t>(cap, 1) * 4);
+                lk.lock();
+                if (!p) J.alloc_failed = true;
+                J.h_tok = p;
+                J.h_cap = cap;
+            }
+            J.cv.notify_all();
+            J.cv.wait(lk, [&] { return J.abort.load() || ((J.known >= ci) && (J.h_tok || J.alloc_failed)); });
+            if (J.alloc_failed) { lk.unlock(); return bail(fail(TK_ERR_CUDA, "out of pinned host memory")); }
+            if (J.abort.load()) { lk.unlock(); return bail(J.rc ? J.rc : TK_ERR_CUDA); }
+            my_prefix = J.prefix[ci];
+            if (my_prefix + n_tok > J.h_cap) {
+                J.overflow = true;
+                lk.unlock();
+                J.fail_with(TK_ERR_BUFFER_TOO_SMALL, "result estimate too small");
+                for (auto& ps : t->pipe_st) if (ps) cudaStreamSynchronize(ps);
+                return TK_ERR_BUFFER_TOO_SMALL;
+            }
+        }
+        cudaError_t e = cudaSuccess;
+        if (kTrace) thost[3 + i * 3] = host_now();
+        mark(i, 4, st_down);
+        if (n_tok) e = cudaMemcpyAsync(J.h_tok + my_prefix, s.out_tok.p, n_tok * 4, cudaMemcpyDeviceToHost, st_down);
+        if (e == cudaSuccess && !c.partial && c.n_docs)
+            e = cudaMemcpyAsync(J.h_off + c.doc_begin, s.out_off.p, c.n_docs * 8, cudaMemcpyDeviceToHost, st_down);
+        mark(i, 5, st_down);
+        if (e == cudaSuccess) e = cudaEventRecord(s.ev_out, st_down);
+        if (e != cudaSuccess) return bail(fail(TK_ERR_CUDA, "copying ids back: %s", cudaGetErrorString(e)));
+        if (i + kAhead < n_mine) { rc = issue(i + kAhead); if (rc) return bail(rc); }
+    }
+    {
+        cudaError_t e = cudaStreamSynchronize(st_down);
+        if (e != cudaSuccess) return bail(fail(TK_ERR_CUDA, "copying ids back: %s", cudaGetErrorString(e)));
+    }
+    // chunk-local token offsets -> batch offsets (every prefix is known by now: my last chunk waited for them)
+    for (size_t i = 0; i < n_mine; ++i) {
+        const Chunk& c = J.chunks[mine[i]];
+        const uint64_t add = J.prefix[mine[i]];
+        if (c.partial) { if (c.first) J.h_off[c.doc_begin] = add; }
+        else if (add) for (size_t d = c.doc_begin; d < c.doc_begin + c.n_docs; ++d) J.h_off[d] += add;
+    }
+    if (kTrace) {
+        fprintf(stderr, "[tekken_b200 trace] device %d chunk: host issue..issued | h2d begin..end | kernels begin..end | host saw done | d2h begin..end  (ms)\n", t->device);
+        for (size_t i = 0; i < n_mine; ++i) {
+            float v[6];
+            for (int k = 0; k < 6; ++k) cudaEventElapsedTime(&v[k], tev[0], tev[1 + i * 6 + k]);
+            fprintf(stderr, "[tekken_b200 trace] %d/%3zu: %7.2f..%7.2f | %7.2f..%7.2f | %7.2f..%7.2f | %7.2f | %7.2f..%7.2f\n", t->device, mine[i],
+                    thost[1 + i * 3] - thost[0], thost[2 + i * 3] - thost[0], v[0], v[1], v[2], v[3], thost[3 + i * 3] - thost[0], v[4], v[5]);
+        }
+        fprintf(stderr, "[tekken_b200 trace] device %d: all copies done at host %.2f ms\n", t->device, host_now() - thost[0]);
+    }
+#undef W_CUDA
+    return TK_OK;
+}
+
+static int encode_batch_engine(tk_tokenizer* const* handles, size_t n_handles, const uint8_t* data, const uint64_t* doc_off, size_t n_docs,
+                               int add_bos, int add_eos, uint32_t** tokens, uint64_t** tok_off) {
     if (!doc_off || !tokens || !tok_off) return fail(TK_ERR_INVALID_ARGUMENT, "null argument");
     *tokens = nullptr;
     *tok_off = nullptr;
     {
-        // the chunk plan below slices the caller's buffers by these offsets: check them before anything is copied
+        // the chunk plan slices the caller's buffers by these offsets: check them before anything is copied
         uint64_t bad = doc_off[0] != 0;
         for (size_t d = 0; d < n_docs; ++d) bad |= (uint64_t)(doc_off[d + 1] < doc_off[d]);
         if (bad) return fail(TK_ERR_INVALID_ARGUMENT, "document offsets must start at 0, be non-decreasing and end at the text length");
     }
     const uint64_t total = doc_off[n_docs];
     if (!data && total) return fail(TK_ERR_INVALID_ARGUMENT, "null text");
+    bool pageable = false;
+    if (total) {
+        DeviceGuard dg(handles[0]->device);
+        cudaPointerAttributes pa{};
+        if (cudaPointerGetAttributes(&pa, data) != cudaSuccess) { cudaGetLastError(); pageable = true; }
+        else pageable = pa.type == cudaMemoryTypeUnregistered;
+    }
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        EncodeJob J;
+        J.data = data; J.doc_off = doc_off; J.n_docs = n_docs; J.total = total; J.add_bos = add_bos; J.add_eos = add_eos;
+        J.pageable = pageable && total >= (1u << 16);       // small inputs: the driver's own staging is as good
+        J.forced_cap = attempt ? total + 2 * (uint64_t)n_docs + 2 : 0;
+        // chunks small enough that every device gets several, large enough to keep the launch overhead low
+        uint64_t chunk = g_chunk_bytes.load() ? g_chunk_bytes.load() : kDefaultChunkBytes;
+        if (n_handles > 1) chunk = std::max<uint64_t>(4u << 20, std::min<uint64_t>(chunk, total / (n_handles * 4) + 1));
+        int rc = plan_chunks(data, doc_off, n_docs, chunk, J.chunks);
+        if (rc) return rc;
+        J.ntok.assign(J.chunks.size(), -1);
+        J.prefix.assign(J.chunks.size() + 1, 0);
+        J.h_off = (uint64_t*)g_pool.get((n_docs + 1) * 8);
+        if (!J.h_off) return fail(TK_ERR_CUDA, "out of pinned host memory");
+        const size_t n_dev = std::min(n_handles, J.chunks.size());
+        std::vector<std::thread> th;
+        for (size_t g = 1; g < n_dev; ++g) th.emplace_back([&, g] { encode_worker(handles[g], J, g, n_dev); });
+        encode_worker(handles[0], J, 0, n_dev);
+        for (auto& x : th) x.join();
+        if (J.rc == TK_OK) {
+            J.h_off[n_docs] = J.prefix[J.chunks.size()];
+            if (!J.h_tok) J.h_tok = (uint32_t*)g_pool.get(4);      // (not reached: chunk 0 always allocates)
+            *tokens = J.h_tok;
+            *tok_off = J.h_off;
+            return TK_OK;
+        }
+        g_pool.put(J.h_tok);
+        g_pool.put(J.h_off);
+        if (!(J.overflow && attempt == 0)) return fail(J.rc, "%s", J.err.c_str());
+    }
+    return fail(TK_ERR_CUDA, "result buffer could not be sized");
+}
+
+extern "C" int tk_encode_batch(const tk_tokenizer* tc, const uint8_t* data, const uint64_t* doc_off, size_t n_docs, int add_bos,
+                               int add_eos, uint32_t** tokens, uint64_t** tok_off) {
+    int rc = check_encode_args(tc, add_bos, add_eos);
+    if (rc) return rc;
     tk_tokenizer* t = const_cast<tk_tokenizer*>(tc);
-    std::lock_guard<std::mutex> g(t->mu);
+    return encode_batch_engine(&t, 1, data, doc_off, n_docs, add_bos, add_eos, tokens, tok_off);
+}
+
+extern "C" int tk_encode_batch_multi(tk_tokenizer* const* handles, size_t n_handles, const uint8_t* data, const uint64_t* doc_off,
+                                     size_t n_docs, int add_bos, int add_eos, uint32_t** tokens, uint64_t** tok_off) {
+    if (!handles || n_handles == 0) return fail(TK_ERR_INVALID_ARGUMENT, "no tokenizer handles");
+    for (size_t g = 0; g < n_handles; ++g) {
+        int rc = check_encode_args(handles[g], add_bos, add_eos);
+        if (rc) return rc;
+        const tk_tokenizer* a = handles[0];
+        const tk_tokenizer* b = handles[g];
+        if (b->host.vocab_size != a->host.vocab_size || b->host.num_special != a->host.num_special || b->split_mode != a->split_mode ||
+            b->host.vocab_bytes != a->host.vocab_bytes)
+            return fail(TK_ERR_INVALID_ARGUMENT, "handle %zu was not created from the same tokenizer as handle 0", g);
+        for (size_t k = 0; k < g; ++k)      // (two handles on one device work -- separate streams and workspaces -- but gain nothing)
+            if (handles[k] == handles[g]) return fail(TK_ERR_INVALID_ARGUMENT, "handle %zu is passed twice; pass one handle per GPU", g);
+    }
+    return encode_batch_engine(handles, n_handles, data, doc_off, n_docs, add_bos, add_eos, tokens, tok_off);
+}
+
+static inline void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+}
+
+// The latency path: a text of at most kSmallMaxBytes goes through ONE single-block kernel that reads it from mapped
+// pinned memory and writes the ids + a completion word back to mapped pinned memory, which this thread polls.
+// *fallback is set when the text has a piece only the batch path's long-piece kernels handle.
+static int encode_small_text(tk_tokenizer* t, const uint8_t* utf8, size_t len, int add_bos, int add_eos, uint32_t** out, size_t* n_out,
+                             bool* fallback) {
+    *fallback = false;
+    tk_tokenizer::FastSlot* s = nullptr;
+    for (auto& f : t->fast) if (f.mu.try_lock()) { s = &f; break; }
+    if (!s) { s = &t->fast[0]; s->mu.lock(); }
+    std::lock_guard<std::mutex> g(s->mu, std::adopt_lock);
     DeviceGuard dg(t->device);
     if (!dg.ok) return fail(TK_ERR_CUDA, "cudaSetDevice(%d) failed", t->device);
-
-    // chunk plan: [begin doc, end doc)
-    static const uint64_t kChunkBytes = [] {
-        const char* e = getenv("TEKKEN_B200_CHUNK_MB");          // tuning knob; default 48 MB
-        const long mb = e ? atol(e) : 0;
-        return (uint64_t)(mb > 0 ? mb : 48) << 20;
-    }();
-    std::vector<size_t> cut{0};
-    while (cut.back() < n_docs) {
-        const size_t b = cut.back();
-        const uint64_t target = doc_off[b] + kChunkBytes;
-        size_t e = std::upper_bound(doc_off + b + 1, doc_off + n_docs + 1, target) - doc_off;   // first doc END beyond the target
-        if (e > n_docs) e = n_docs;
-        if (e <= b) e = b + 1;
-        if (doc_off[e] < doc_off[b]) return fail(TK_ERR_INVALID_ARGUMENT, "document offsets must start at 0, be non-decreasing and end at the text length");
-        cut.push_back(e);
+    if (!s->st) {
+        CUDA_OR_FAIL(cudaHostAlloc((void**)&s->h_in, tkk::kSmallMaxBytes + 128, cudaHostAllocMapped));
+        CUDA_OR_FAIL(cudaHostAlloc((void**)&s->h_out, tkk::kSmallOutWords * 4, cudaHostAllocMapped));
+        CUDA_OR_FAIL(cudaHostGetDevicePointer((void**)&s->d_in, s->h_in, 0));
+        CUDA_OR_FAIL(cudaHostGetDevicePointer((void**)&s->d_out, s->h_out, 0));
+        memset(s->h_out, 0, 64);
+        CUDA_OR_FAIL(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
     }
-    if (n_docs == 0) cut.push_back(0);
-    const size_t n_chunks = cut.size() - 1;
-
-    // result buffers: the id count is not known in advance; start from an estimate and grow if needed
-    uint64_t h_cap = total / 2 + 2 * (uint64_t)n_docs + 4096;
-    uint32_t* h_tok = (uint32_t*)g_pool.get(h_cap * 4);
-    uint64_t* h_off = (uint64_t*)g_pool.get((n_docs + 1) * 8);
-    if (!h_tok || !h_off) { g_pool.put(h_tok); g_pool.put(h_off); return fail(TK_ERR_CUDA, "out of pinned host memory"); }
-    auto bail = [&](int code) {
-        for (auto& ps : t->pipe_st) if (ps) cudaStreamSynchronize(ps);
-        g_pool.put(h_tok); g_pool.put(h_off);
-        return code;
-    };
-    struct Chunk { uint64_t byte_begin, n_bytes, cap; size_t doc_begin, n; };
-    auto chunk_of = [&](size_t i) {
-        Chunk c;
-        c.doc_begin = cut[i]; c.n = cut[i + 1] - cut[i];
-        c.byte_begin = n_docs ? doc_off[cut[i]] : 0; c.n_bytes = n_docs ? doc_off[cut[i + 1]] - c.byte_begin : 0;
-        c.cap = c.n_bytes + 2 * (uint64_t)c.n + 2;
-        return c;
-    };
-    // Three role streams: text goes up on one, the kernels of successive chunks run back to back on the
-    // second, ids come down on the third.  Events order them per slot: kernels(i) after H2D(i) and after
-    // D2H(i - kSlots) has emptied the slot's id buffer; H2D(i) after kernels(i - kSlots) have read the
-    // slot's text.  TEKKEN_B200_TRACE=1 prints the device timeline of every chunk on stderr.
-    for (auto& ps : t->pipe_st) if (!ps) CUDA_OR_FAIL(cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
-    cudaStream_t st_up = t->pipe_st[0], st_k = t->pipe_st[1], st_down = t->pipe_st[2];
-    static const bool kTrace = getenv("TEKKEN_B200_TRACE") != nullptr;
-    std::vector<cudaEvent_t> tev;
-    std::vector<double> thost;
-    const auto host_now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    if (kTrace) {
-        tev.resize(n_chunks * 6 + 1);
-        thost.resize(n_chunks * 3 + 1);
-        for (auto& e : tev) cudaEventCreate(&e);
-        cudaEventRecord(tev[0], st_up);
-        thost[0] = host_now();
-    }
-    auto mark = [&](size_t i, int k, cudaStream_t st) { if (kTrace) cudaEventRecord(tev[1 + i * 6 + k], st); };
-    auto issue = [&](size_t i) -> int {
-        tk_tokenizer::EncSlot& s = t->slot[i % tk_tokenizer::kSlots];
-        const Chunk c = chunk_of(i);
-        if (!s.ev_in) {
-            CUDA_OR_FAIL(cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
-            CUDA_OR_FAIL(cudaEventCreateWithFlags(&s.ev_out, cudaEventDisableTiming));
+    if (len) memcpy(s->h_in, utf8, len);
+    const uint32_t seq = ++s->seq ? s->seq : ++s->seq;            // never 0: the cleared header reads as "not done"
+    cudaError_t e = tkk::encode_small(t->tables, s->d_in, (uint32_t)len, add_bos, add_eos, s->d_out, seq, s->st);
+    if (e != cudaSuccess) return fail(TK_ERR_CUDA, "encode launch: %s", cudaGetErrorString(e));
+    volatile uint32_t* hdr = s->h_out;
+    for (uint32_t spin = 1;; ++spin) {
+        if (hdr[4] == seq) break;
+        if ((spin & 4095u) == 0u) {
+            // the kernel cannot finish without setting the word: a finished (or failed) stream without it is an error
+            const cudaError_t q = cudaStreamQuery(s->st);
+            if (q == cudaSuccess) { if (hdr[4] == seq) break; return fail(TK_ERR_CUDA, "single-block encode kernel ended without a result"); }
+            if (q != cudaErrorNotReady) return fail(TK_ERR_CUDA, "single-block encode kernel: %s", cudaGetErrorString(q));
         }
-        if (kTrace) thost[1 + i * 3] = host_now();
-        CUDA_OR_FAIL(s.in_data.ensure(c.n_bytes + 64));
-        CUDA_OR_FAIL(s.in_off.ensure((c.n + 1) * 8));
-        CUDA_OR_FAIL(s.out_tok.ensure(c.cap * 4));
-        CUDA_OR_FAIL(s.out_off.ensure((c.n + 1) * 8));
-        if (i >= (size_t)tk_tokenizer::kSlots) CUDA_OR_FAIL(cudaStreamWaitEvent(st_up, s.done, 0));
-        mark(i, 0, st_up);
-        if (c.n_bytes) CUDA_OR_FAIL(cudaMemcpyAsync(s.in_data.p, data + c.byte_begin, c.n_bytes, cudaMemcpyHostToDevice, st_up));
-        CUDA_OR_FAIL(cudaMemcpyAsync(s.in_off.p, doc_off + c.doc_begin, (c.n + 1) * 8, cudaMemcpyHostToDevice, st_up));
-        mark(i, 1, st_up);
-        CUDA_OR_FAIL(cudaEventRecord(s.ev_in, st_up));
-        CUDA_OR_FAIL(cudaStreamWaitEvent(st_k, s.ev_in, 0));
-        if (i >= (size_t)tk_tokenizer::kSlots) CUDA_OR_FAIL(cudaStreamWaitEvent(st_k, s.ev_out, 0));
-        mark(i, 2, st_k);
-        const int r = encode_issue(t, s, (const uint8_t*)s.in_data.p, (const uint64_t*)s.in_off.p, c.byte_begin, c.n, c.n_bytes, add_bos, add_eos,
-                                   (uint32_t*)s.out_tok.p, c.cap, (uint64_t*)s.out_off.p, st_k, false);
-        mark(i, 3, st_k);
-        if (kTrace) thost[2 + i * 3] = host_now();
-        return r;
-    };
-    std::vector<uint64_t> prefix(n_chunks + 1, 0);
-    // kAhead chunks are always queued ahead, so the host sits in the wait for chunk i when it completes
-    // and its ids start their way back at once
-    constexpr size_t kAhead = tk_tokenizer::kSlots - 1;
-    for (size_t i = 0; i < kAhead && i < n_chunks; ++i) { rc = issue(i); if (rc) return bail(rc); }
-    for (size_t i = 0; i < n_chunks; ++i) {
-        tk_tokenizer::EncSlot& s = t->slot[i % tk_tokenizer::kSlots];
-        const Chunk c = chunk_of(i);
-        uint64_t n_tok = 0;
-        for (int attempt = 0;; ++attempt) {
-            bool retry = false;
-            rc = encode_finish(t, s, st_k, c.n_bytes, c.cap, c.byte_begin, &n_tok, &retry, false);
-            if (rc) return bail(rc);
-            if (!retry) break;
-            if (attempt) return bail(fail(TK_ERR_CUDA, "huge-piece scratch could not be grown"));
-            rc = encode_issue(t, s, (const uint8_t*)s.in_data.p, (const uint64_t*)s.in_off.p, c.byte_begin, c.n, c.n_bytes, add_bos, add_eos,
-                              (uint32_t*)s.out_tok.p, c.cap, (uint64_t*)s.out_off.p, st_k, false);
-            if (rc) return bail(rc);
-        }
-        if (prefix[i] + n_tok > h_cap) {
-            // estimate too small: finish the copies into the old buffer, move to a bigger one
-            CUDA_OR_FAIL(cudaStreamSynchronize(st_down));
-            uint64_t want = std::max(2 * h_cap, prefix[i] + n_tok + (total - c.byte_begin - c.n_bytes) + 2 * (uint64_t)(n_docs - c.doc_begin) + 4096);
-            uint32_t* bigger = (uint32_t*)g_pool.get(want * 4);
-            if (!bigger) return bail(fail(TK_ERR_CUDA, "out of pinned host memory"));
-            memcpy(bigger, h_tok, prefix[i] * 4);
-            g_pool.put(h_tok);
-            h_tok = bigger;
-            h_cap = want;
-        }
-        cudaError_t e = cudaSuccess;
-        if (kTrace) thost[3 + i * 3] = host_now();
-        mark(i, 4, st_down);
-        if (n_tok) e = cudaMemcpyAsync(h_tok + prefix[i], s.out_tok.p, n_tok * 4, cudaMemcpyDeviceToHost, st_down);
-        if (e == cudaSuccess && c.n) e = cudaMemcpyAsync(h_off + c.doc_begin, s.out_off.p, c.n * 8, cudaMemcpyDeviceToHost, st_down);
-        mark(i, 5, st_down);
-        if (e == cudaSuccess) e = cudaEventRecord(s.ev_out, st_down);
-        if (e != cudaSuccess) return bail(fail(TK_ERR_CUDA, "copying ids back: %s", cudaGetErrorString(e)));
-        prefix[i + 1] = prefix[i] + n_tok;
-        if (i + kAhead < n_chunks) { rc = issue(i + kAhead); if (rc) return bail(rc); }
+        cpu_relax();
     }
-    {
-        cudaError_t e = cudaStreamSynchronize(st_down);
-        if (e != cudaSuccess) return bail(fail(TK_ERR_CUDA, "copying ids back: %s", cudaGetErrorString(e)));
-    }
-    if (kTrace) {
-        fprintf(stderr, "[tekken_b200 trace] chunk: host issue..issued | h2d begin..end | kernels begin..end | host saw done | d2h begin..end  (ms)\n");
-        for (size_t i = 0; i < n_chunks; ++i) {
-            float v[6];
-            for (int k = 0; k < 6; ++k) cudaEventElapsedTime(&v[k], tev[0], tev[1 + i * 6 + k]);
-            fprintf(stderr, "[tekken_b200 trace] %3zu: %7.2f..%7.2f | %7.2f..%7.2f | %7.2f..%7.2f | %7.2f | %7.2f..%7.2f\n", i,
-                    thost[1 + i * 3] - thost[0], thost[2 + i * 3] - thost[0], v[0], v[1], v[2], v[3], thost[3 + i * 3] - thost[0], v[4], v[5]);
-        }
-        fprintf(stderr, "[tekken_b200 trace] all copies done at host %.2f ms\n", host_now() - thost[0]);
-        for (auto& e : tev) cudaEventDestroy(e);
-    }
-    // chunk-local token offsets -> batch offsets
-    for (size_t i = 1; i < n_chunks; ++i) {
-        const uint64_t add = prefix[i];
-        for (size_t d = cut[i]; d < cut[i + 1]; ++d) h_off[d] += add;
-    }
-    h_off[n_docs] = prefix[n_chunks];
-    *tokens = h_tok;
-    *tok_off = h_off;
+    std::atomic_thread_fence(std::memory_order_acquire);
+    const uint32_t n_ids = hdr[0], flags = hdr[1], err_pos = hdr[2];
+    if (flags & tkk::kSmallBadUtf8) return fail(TK_ERR_INVALID_UTF8, "input is not valid UTF-8 at byte %u", err_pos);
+    if (flags & tkk::kSmallNeedBatch) { *fallback = true; return TK_OK; }
+    uint32_t* ids = (uint32_t*)g_pool.get((size_t)n_ids * 4 + 4, false);
+    if (!ids) return fail(TK_ERR_CUDA, "out of host memory");
+    if (n_ids) memcpy(ids, s->h_out + 8, (size_t)n_ids * 4);
+    *out = ids;
+    *n_out = n_ids;
     return TK_OK;
 }
 
 extern "C" int tk_encode(const tk_tokenizer* t, const uint8_t* utf8, size_t len, int add_bos, int add_eos, uint32_t** out,
                          size_t* n_out) {
     if (!out || !n_out) return fail(TK_ERR_INVALID_ARGUMENT, "null argument");
+    static const bool kNoFast = getenv("TEKKEN_B200_NO_FAST") != nullptr;      // measurements: force the batch path
+    if (t && t->device >= 0 && len <= tkk::kSmallMaxBytes && t->split_mode == TK_SPLIT_REFERENCE && !kNoFast) {
+        int rc = check_encode_args(t, add_bos, add_eos);
+        if (rc) return rc;
+        if (!utf8 && len) return fail(TK_ERR_INVALID_ARGUMENT, "null text");
+        bool fallback = false;
+        rc = encode_small_text(const_cast<tk_tokenizer*>(t), utf8, len, add_bos, add_eos, out, n_out, &fallback);
+        if (rc || !fallback) return rc;
+    }
     uint64_t off[2] = {0, len};
     uint64_t* tok_off = nullptr;
     int rc = tk_encode_batch(t, utf8, off, 1, add_bos, add_eos, out, &tok_off);
@@ -959,6 +1322,8 @@ extern "C" int tk_shard_plan(const uint64_t* doc_off, size_t n_docs, size_t n_sh
     shard_begin[n_shards] = n_docs;
     return TK_OK;
 }
+
+extern "C" void tk_set_chunk_bytes(uint64_t bytes) { g_chunk_bytes.store(bytes ? std::max<uint64_t>(bytes, 4096) : 0); }
 
 extern "C" uint64_t tk_kernel_launch_count(void) { return tkk::launch_count(); }
 

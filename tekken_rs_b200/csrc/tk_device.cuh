@@ -276,13 +276,13 @@ __device__ __forceinline__ uint32_t tk_slice_min(const uint32_t* rk, uint32_t lo
     return best;
 }
 
-// src: the piece bytes (global).  out: global buffer for up to n ranks.  Returns the count
+// src: the piece bytes (global or shared).  out: buffer for up to n ranks (global or shared).  Returns the count
 // (same value on all lanes).  Must be called by all 32 lanes.
 __device__ inline uint32_t tk_bpe_warp(const TkDeviceTables& T, TkWarpBpeSmem& S, const uint8_t* src, uint32_t n,
                                        uint32_t* out) {
     const uint32_t lane = threadIdx.x & 31u;
     for (uint32_t i = lane; i < n; i += 32) {
-        S.id[i] = __ldg(src + i);
+        S.id[i] = src[i];                // plain load: src is global text in the batch path, shared memory in the single-block kernel
         S.nx[i] = (uint16_t)(i + 1);
         S.pv[i] = (uint16_t)(i - 1);   // 0xFFFF for i == 0
     }

@@ -1496,6 +1496,8 @@ __global__ void __launch_bounds__(E3_T, E3_MINB) emit_kernel(const uint32_t* __r
     }
 }
 
+#include "tk_small.cuh"
+
 // =====================================================================================================
 // launch sequence
 // =====================================================================================================
@@ -1737,6 +1739,11 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
     TK_LAUNCHED();
     if (timer) timer->mark(st, "end");
     return cudaGetLastError();
+}
+
+cudaError_t encode_small(const TkDeviceTables& T, const uint8_t* d_text, uint32_t n, int add_bos, int add_eos, uint32_t* d_out,
+                         uint32_t seq, cudaStream_t st) {
+    return encode_small_launch(T, d_text, n, add_bos, add_eos, d_out, seq, st);
 }
 
 }  // namespace tkk

@@ -98,6 +98,15 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
                           void* d_ws, const EncodeLayout& L, uint32_t* d_scratch, uint64_t scratch_cap, int sm_count,
                           cudaStream_t st, StageTimer* timer, const HotTables* hot = nullptr, const CfgSplitTables* cfg = nullptr);
 
+// The latency path (tk_small.cuh): one single-block kernel encodes one text of at most kSmallMaxBytes.  d_text (16-byte
+// aligned) and d_out may be mapped pinned host memory.  d_out: 8 header words {n_ids, flags, err_pos, -, done, ...},
+// ids from word 8; `done` becomes `seq` when everything is visible to the host.
+constexpr uint32_t kSmallMaxBytes = 256 * 32 - 64;
+constexpr uint32_t kSmallOutWords = 8 + kSmallMaxBytes + 2 + 6;
+constexpr uint32_t kSmallNeedBatch = 1u, kSmallBadUtf8 = 2u;
+cudaError_t encode_small(const TkDeviceTables& T, const uint8_t* d_text, uint32_t n, int add_bos, int add_eos, uint32_t* d_out,
+                         uint32_t seq, cudaStream_t st);
+
 cudaError_t publish_counters(const void* d_ws, const EncodeLayout& L, uint32_t* mapped_dev, cudaStream_t st);
 
 size_t decode_workspace_bytes(uint64_t n_ids, uint64_t n_docs, uint64_t out_cap, DecodeLayout* L);

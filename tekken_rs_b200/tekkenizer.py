@@ -327,5 +327,25 @@ def shard_plan(doc_off, n_shards: int) -> np.ndarray:
     return out
 
 
+def encode_batch_multi(tokenizers: Sequence["Tekkenizer"], data, doc_off, add_bos: bool, add_eos: bool):
+    """One call over several handles of the same tokenizer (one per GPU): chunks of the batch are dealt to the devices,
+    ids and offsets come back in document order in one buffer.  Returns (ids uint32, tok_off uint64[n_docs+1])."""
+    lib = _lib.load()
+    a = _u8(data)
+    off = np.ascontiguousarray(doc_off, dtype=np.uint64)
+    n_docs = len(off) - 1
+    arr = (ctypes.c_void_p * len(tokenizers))(*[t._h for t in tokenizers])
+    tok, toff = ctypes.c_void_p(), ctypes.c_void_p()
+    _check(lib.tk_encode_batch_multi(arr, len(tokenizers), a.ctypes.data if len(a) else None, off.ctypes.data, n_docs,
+                                     int(add_bos), int(add_eos), ctypes.byref(tok), ctypes.byref(toff)))
+    tok_off = _take(toff.value, (n_docs + 1) * 8, np.uint64)
+    return _take(tok.value, int(tok_off[-1]) * 4, np.uint32), tok_off
+
+
+def set_chunk_bytes(n: int):
+    """Tuning knob: chunk size of the host-buffer calls (0 = default 48 MB)."""
+    _lib.load().tk_set_chunk_bytes(int(n))
+
+
 def kernel_launch_count() -> int:
     return int(_lib.load().tk_kernel_launch_count())

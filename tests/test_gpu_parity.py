@@ -104,6 +104,74 @@ def test_basic_tokenizer_example(gpu_tok):
     assert gpu_tok.encode("का", False, False) == [2622, 1658]      # the hard-coded pattern, not Mistral's
 
 
+def test_single_text_latency_path(gpu_tok, oracle):
+    # tk_encode of a text <= 8128 bytes runs the single-block kernel (tk_small.cuh), longer texts and texts with a piece
+    # > 512 bytes the batch pipeline: both must give the oracle's ids, at every length around the switch
+    rng = random.Random(17)
+    from oracle.tools.make_golden_fixtures import FUZZ_ALPHABET
+    texts = ["", " ", "a", "\n", "  \n  ", "x \n \t", "tail ws   ", "12345678901", "it's we'LL", "\r\n\r\n", "é" * 300, "q" * 512, "q" * 513,
+             " " * 700, "ab" * 3000, "😀" * 1500, "z" * 8128, "word " * 1625, "word " * 1626, ("x" * 31 + " ") * 254]
+    for L in (1, 31, 32, 33, 95, 96, 97, 511, 512, 513, 4095, 4096, 4097, 8100, 8127, 8128, 8129, 8192, 9000):
+        texts.append("".join(rng.choice("abc de.\n1'") for _ in range(L)))
+        t = "".join(rng.choice(FUZZ_ALPHABET) for _ in range(L))
+        while len(t.encode()) > L:
+            t = t[:-1]
+        texts.append(t)
+    for t in texts:
+        for bos, eos in ((True, True), (False, False), (True, False)):
+            assert gpu_tok.encode(t, bos, eos) == oracle.encode(t, bos, eos), (len(t), t[:60])
+    # random short strings: single-text path == batch path == oracle
+    fz = _fuzz_texts(4000, 23, [0, 1, 2, 3, 5, 8, 13, 30, 64, 200, 700, 3000])
+    data, off = _pack(fz)
+    ids, toff = assert_same_batch(gpu_tok, oracle, data, off, True, True)
+    for k in range(0, len(fz), 7):
+        assert gpu_tok.encode(fz[k], True, True) == ids[int(toff[k]):int(toff[k + 1])].tolist(), fz[k][:60]
+    for bad in (b"ab\xff", b"x" * 5000 + b"\xe4\xb8", b"\x80"):
+        with pytest.raises(TokenizerError) as e:
+            gpu_tok.encode(bad, True, True)
+        assert e.value.kind == "InvalidUtf8"
+
+
+def test_host_engine_chunks_slices_and_devices(gpu_tok, oracle, tekken_json):
+    # the host-buffer engine (tk_api.cu): chunks cut at document boundaries, documents larger than a chunk sliced at
+    # context-free piece boundaries, chunks dealt to several handles with the ids landing in document order, pageable
+    # and page-locked callers.  Small chunk sizes make all of that happen on a few MB.
+    import torch
+    from tekken_rs_b200 import encode_batch_multi, set_chunk_bytes
+    rng = random.Random(5)
+    big = corpus.english_like(3 << 20, 99)                                   # sliced (many cut points)
+    nocut = ("x" * 700000).encode()                                          # no cut point at all: one piece of work
+    cjk = "".join(chr(rng.randint(0x4E00, 0x9FA5)) for _ in range(120000)).encode()   # no ASCII: no cut point
+    mixed, moff = corpus.mixed_script_docs(3000, 3)
+    docs = [bytes(mixed[int(moff[i]):int(moff[i + 1])]) for i in range(3000)]
+    docs[10:10] = [big, b"", nocut, b"tiny", cjk, corpus.single_long_document(1 << 20, 3)]
+    data, off = _pack(docs)
+    want, woff = oracle.encode_batch_np(data, off, True, True, n_threads=8)
+    others = [Tekkenizer.from_file(tekken_json, device=0) for _ in range(2)]
+    try:
+        for chunk in (64 << 10, 300 << 10, 1 << 20, 0):
+            set_chunk_bytes(chunk)
+            ids, toff = gpu_tok.encode_batch_np(data, off, True, True)                       # pageable caller memory
+            assert np.array_equal(toff, woff) and np.array_equal(ids, want), "chunk %d" % chunk
+            ids, toff = encode_batch_multi([gpu_tok] + others, data, off, True, True)       # three pipelines, one result
+            assert np.array_equal(toff, woff) and np.array_equal(ids, want), "multi, chunk %d" % chunk
+            pinned = torch.from_numpy(np.concatenate([data, np.zeros(64, np.uint8)])).pin_memory()
+            ids, toff = gpu_tok.encode_batch_np(pinned.numpy()[:len(data)], off, True, True)   # page-locked caller memory
+            assert np.array_equal(toff, woff) and np.array_equal(ids, want), "pinned, chunk %d" % chunk
+            for bos, eos in ((False, False), (True, False)):
+                one, _ = gpu_tok.encode_batch_np(np.frombuffer(big, dtype=np.uint8), np.array([0, len(big)], dtype=np.uint64), bos, eos)
+                assert one.tolist() == oracle.encode(big, bos, eos)
+        # a tiny estimate for the result buffer: the first chunk has few ids per byte, the rest many (forces the repeat)
+        set_chunk_bytes(64 << 10)
+        skew = [b" " * 60000 + b"x"] + ["".join(chr(rng.randint(0x4E00, 0x9FA5)) for _ in range(300)).encode() for _ in range(2000)]
+        sdata, soff = _pack(skew)
+        assert_same_batch(gpu_tok, oracle, sdata, soff, True, True)
+    finally:
+        set_chunk_bytes(0)
+        for t in others:
+            t.close()
+
+
 # ------------------------------------------------------------------------------------------ differential fuzz
 
 def _fuzz_texts(n, seed, lengths):
