@@ -213,6 +213,16 @@ struct tk_tokenizer {
     };
     static constexpr int kSlots = 4;
     EncSlot slot[kSlots];          // host-buffer encode: chunks of a batch pipeline through these
+    struct DecSlot {
+        DevBuf ids, off, out, boff, status, ws;
+        uint32_t* h_small = nullptr;
+        uint32_t* d_small_map = nullptr;
+        cudaEvent_t done = nullptr, ev_in = nullptr, ev_out = nullptr;
+        uint8_t* h_stage = nullptr;
+        size_t stage_cap = 0;
+        tkk::DecodeLayout L;
+    };
+    DecSlot dslot[kSlots];         // host-buffer decode
     cudaStream_t pipe_st[3] = {nullptr, nullptr, nullptr};   // ... on an upload, a kernel and a download stream
     EncSlot dev_slot;              // device-pointer encode (caller's stream)
     // the latency path (tk_encode of a short text): mapped pinned in/out buffers + a stream per slot
@@ -280,17 +290,21 @@ static int finish_handle(tk_tokenizer* t, int device, int split_mode, tk_tokeniz
             // the merge kernels' tables (pair table + byte-pair table, 8.25 MB for the Tekken vocabulary) live in ONE
             // allocation so that one L2 access-policy window can keep them resident while text / queue / stream
             // traffic passes through (tk_kernels.cu launch_lanemerge)
-            const size_t pb = h.pair_slots.size() * sizeof(uint64_t), bb = h.byte_pair.size() * sizeof(uint32_t);
+            const size_t pb = h.pair_slots.size() * sizeof(uint64_t), bb = h.byte_pair.size() * sizeof(uint32_t),
+                         kb = h.pair_buckets.size() * sizeof(uint64_t);
             void* hot = nullptr;
-            err = cudaMalloc(&hot, pb + bb);
+            err = cudaMalloc(&hot, pb + bb + kb + 32);
             if (err == cudaSuccess) {
                 t->table_allocs.push_back(hot);
                 err = cudaMemcpy(hot, h.pair_slots.data(), pb, cudaMemcpyHostToDevice);
                 if (err == cudaSuccess) err = cudaMemcpy((char*)hot + pb, h.byte_pair.data(), bb, cudaMemcpyHostToDevice);
+                if (err == cudaSuccess && kb) err = cudaMemcpy((char*)hot + pb + bb, h.pair_buckets.data(), kb, cudaMemcpyHostToDevice);
                 T.pair_slots = (const uint64_t*)hot;
                 T.byte_pair = (const uint32_t*)((const char*)hot + pb);
+                T.pair_buckets = kb ? (const uint64_t*)((const char*)hot + pb + bb) : nullptr;     // pb, bb: multiples of 32 bytes
+                T.bucket_mask = h.bucket_mask;
                 t->hot.ptr = hot;
-                t->hot.bytes = pb + bb;
+                t->hot.bytes = pb + bb + kb;
                 int max_persist = 0, max_window = 0;
                 cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
                 cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device);
@@ -315,7 +329,7 @@ static int finish_handle(tk_tokenizer* t, int device, int split_mode, tk_tokeniz
         }
         if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking);
         T.vocab_mask = (uint32_t)h.vocab_slots.size() - 1;
-        T.pair_mask = (uint32_t)h.pair_slots.size() - 1;
+        T.pair_mask = h.pair_mask;
         T.n_vocab = (uint32_t)h.n_vocab();
         T.num_special = (uint32_t)h.num_special;
         T.max_token_len = h.max_token_len;
@@ -423,6 +437,14 @@ extern "C" void tk_free(tk_tokenizer* t) {
         }
         for (auto& ps : t->pipe_st) if (ps) { cudaStreamSynchronize(ps); cudaStreamDestroy(ps); }
         for (auto& sl : t->slot) drop(sl);
+        for (auto& d : t->dslot) {
+            d.ids.release(); d.off.release(); d.out.release(); d.boff.release(); d.status.release(); d.ws.release();
+            if (d.h_small) cudaFreeHost(d.h_small);
+            if (d.h_stage) cudaFreeHost(d.h_stage);
+            if (d.done) cudaEventDestroy(d.done);
+            if (d.ev_in) cudaEventDestroy(d.ev_in);
+            if (d.ev_out) cudaEventDestroy(d.ev_out);
+        }
         drop(t->dev_slot);
         if (t->stream) cudaStreamDestroy(t->stream);
     }
@@ -719,10 +741,16 @@ inline bool context_free_cut(const uint8_t* d, uint64_t p) { return d[p] == ' ' 
 
 constexpr uint64_t kMaxDeviceCall = (1ull << 32) - (1ull << 20);     // one device call takes < 4 GiB of text
 
-int plan_chunks(const uint8_t* data, const uint64_t* doc_off, size_t n_docs, uint64_t chunk_bytes, std::vector<Chunk>& out) {
-    const uint64_t big = chunk_bytes + chunk_bytes / 2;
+int plan_chunks(const uint8_t* data, const uint64_t* doc_off, size_t n_docs, uint64_t full_chunk, size_t n_devices, std::vector<Chunk>& out) {
+    const uint64_t big = full_chunk + full_chunk / 2;
+    // The first chunks are small and double up to the full size: the download engine -- the resource that limits a
+    // large call (4 bytes come back for every 2.4 that go up) -- starts after a fraction of a millisecond instead of
+    // after a full chunk's upload and kernels.
+    const uint64_t total = doc_off[n_docs];
+    uint64_t chunk_bytes = total > 4 * full_chunk * n_devices ? std::max<uint64_t>(full_chunk / 8, 1u << 20) : full_chunk;
     size_t d = 0;
     while (d < n_docs) {
+        if (!out.empty() && out.size() % n_devices == 0) chunk_bytes = std::min(full_chunk, chunk_bytes * 2);
         const uint64_t len_d = doc_off[d + 1] - doc_off[d];
         if (len_d > big) {
             uint64_t pos = doc_off[d];
@@ -1020,7 +1048,7 @@ static int encode_batch_engine(tk_tokenizer* const* handles, size_t n_handles, c
         // chunks small enough that every device gets several, large enough to keep the launch overhead low
         uint64_t chunk = g_chunk_bytes.load() ? g_chunk_bytes.load() : kDefaultChunkBytes;
         if (n_handles > 1) chunk = std::max<uint64_t>(4u << 20, std::min<uint64_t>(chunk, total / (n_handles * 4) + 1));
-        int rc = plan_chunks(data, doc_off, n_docs, chunk, J.chunks);
+        int rc = plan_chunks(data, doc_off, n_docs, chunk, n_handles, J.chunks);
         if (rc) return rc;
         J.ntok.assign(J.chunks.size(), -1);
         J.prefix.assign(J.chunks.size() + 1, 0);
@@ -1156,7 +1184,7 @@ static int run_decode(tk_tokenizer* t, const uint32_t* d_ids, const uint64_t* d_
     tkk::DecodeLayout L;
     size_t ws_bytes = tkk::decode_workspace_bytes(n_ids, n_docs, cap, &L);
     CUDA_OR_FAIL(t->ws.ensure(ws_bytes));
-    cudaError_t e = tkk::decode_device(t->tables, d_ids, d_tok_off, n_docs, n_ids, policy, d_out, cap, d_byte_off, d_status, t->ws.p,
+    cudaError_t e = tkk::decode_device(t->tables, d_ids, d_tok_off, 0, n_docs, n_ids, policy, d_out, cap, d_byte_off, d_status, t->ws.p,
                                        L, st);
     if (e != cudaSuccess) return fail(TK_ERR_CUDA, "decode launch: %s", cudaGetErrorString(e));
     uint32_t small[64];
@@ -1209,6 +1237,239 @@ extern "C" int tk_decode_batch_device(const tk_tokenizer* tc, const uint32_t* d_
                       (cudaStream_t)stream);
 }
 
+// ------------------------------------------------------------------------------------------ host-buffer decode engine
+//
+// tk_decode_batch: ids in host memory (pageable or pinned), text out in pinned host memory.  The batch is cut at
+// sequence boundaries into chunks of about kChunkBytes / 4 ids that flow through kSlots buffer slots on the
+// upload / kernel / download streams, like the encode engine.  A sequence larger than 1.5 chunks is cut inside,
+// before an id whose bytes start with an ASCII byte (or before a special id): the bytes before such a cut must end a
+// character for the run to be valid UTF-8, so validating the slices separately is validating the run.  The size of
+// the text is not known in advance: the result buffer is sized from the first chunk's bytes per id, and if that
+// turns out too small the call is repeated with the exact size (a host walk over the ids).  Nothing else walks the
+// ids on the host.
+
+namespace {
+
+struct DChunk {
+    size_t seq_begin, n_seqs;
+    uint64_t id_begin, n_ids;
+    bool partial, first, last;
+};
+
+// may the id sequence be cut BEFORE position p (see above)?
+inline bool decode_cut_ok(const tk::HostModel& h, uint32_t id) {
+    if (id < h.num_special) return true;
+    const size_t r = id - h.num_special;
+    if (r >= h.n_vocab()) return true;                         // unknown id: the sequence fails anyway
+    const uint32_t a = h.vocab_off[r], b = h.vocab_off[r + 1];
+    return b > a && h.vocab_bytes[a] < 0x80u;
+}
+
+int plan_decode_chunks(const tk::HostModel& h, const uint32_t* ids, const uint64_t* tok_off, size_t n_seqs, uint64_t chunk_ids,
+                       std::vector<DChunk>& out) {
+    const uint64_t big = chunk_ids + chunk_ids / 2, kMaxIds = (1ull << 31);
+    size_t d = 0;
+    while (d < n_seqs) {
+        const uint64_t len_d = tok_off[d + 1] - tok_off[d];
+        if (len_d > big) {
+            uint64_t pos = tok_off[d];
+            const uint64_t end = tok_off[d + 1];
+            bool first = true;
+            while (pos < end) {
+                uint64_t cut = end;
+                if (end - pos > big) {
+                    const uint64_t target = pos + chunk_ids, lo = pos + chunk_ids / 2;
+                    cut = 0;
+                    for (uint64_t p = target; p > lo; --p) if (decode_cut_ok(h, ids[p])) { cut = p; break; }
+                    if (!cut) {
+                        const uint64_t hi = std::min(end, pos + kMaxIds);
+                        for (uint64_t p = target + 1; p < hi; ++p) if (decode_cut_ok(h, ids[p])) { cut = p; break; }
+                    }
+                    if (!cut) cut = end;
+                }
+                if (cut - pos >= kMaxIds) return fail(TK_ERR_INVALID_ARGUMENT, "sequence %zu has no cut point within 2^31 ids", d);
+                out.push_back({d, 1, pos, cut - pos, true, first, cut == end});
+                first = false;
+                pos = cut;
+            }
+            ++d;
+            continue;
+        }
+        const size_t b = d;
+        const uint64_t begin = tok_off[b];
+        size_t e = std::upper_bound(tok_off + b + 1, tok_off + n_seqs + 1, begin + chunk_ids) - tok_off;
+        if (e > n_seqs) e = n_seqs;
+        if (e <= b) e = b + 1;
+        for (size_t k = (e - b > 4 ? e - 2 : b); k < e; ++k)
+            if (tok_off[k + 1] - tok_off[k] > big) { e = k > b ? k : b + 1; break; }
+        out.push_back({b, e - b, begin, tok_off[e] - begin, false, true, true});
+        d = e;
+    }
+    if (out.empty()) out.push_back({0, 0, 0, 0, false, true, true});
+    return TK_OK;
+}
+
+}  // namespace
+
+static int decode_batch_engine(tk_tokenizer* t, const uint32_t* ids, const uint64_t* tok_off, size_t n_seqs, int policy, uint8_t** out,
+                               uint64_t** byte_off, uint64_t* bad_doc, uint64_t forced_cap) {
+    const uint64_t n_ids = tok_off[n_seqs];
+    std::lock_guard<std::mutex> lock(t->mu);
+    DeviceGuard dg(t->device);
+    if (!dg.ok) return fail(TK_ERR_CUDA, "cudaSetDevice(%d) failed", t->device);
+    bool pageable = false;
+    if (n_ids) {
+        cudaPointerAttributes pa{};
+        if (cudaPointerGetAttributes(&pa, ids) != cudaSuccess) { cudaGetLastError(); pageable = true; }
+        else pageable = pa.type == cudaMemoryTypeUnregistered;
+    }
+    if (n_ids * 4 < (1u << 16)) pageable = false;
+    std::vector<DChunk> chunks;
+    const uint64_t chunk_ids = std::max<uint64_t>(1024, (g_chunk_bytes.load() ? g_chunk_bytes.load() : kDefaultChunkBytes) / 4);
+    int rc = plan_decode_chunks(t->host, ids, tok_off, n_seqs, chunk_ids, chunks);
+    if (rc) return rc;
+    const size_t n_chunks = chunks.size();
+    for (auto& ps : t->pipe_st) if (!ps) CUDA_OR_FAIL(cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
+    cudaStream_t st_up = t->pipe_st[0], st_k = t->pipe_st[1], st_down = t->pipe_st[2];
+
+    uint8_t* h_out = nullptr;
+    uint64_t h_cap = 0;
+    uint64_t* h_boff = (uint64_t*)g_pool.get((n_seqs + 1) * 8);
+    if (!h_boff) return fail(TK_ERR_CUDA, "out of pinned host memory");
+    auto bail = [&](int code) {
+        for (auto& ps : t->pipe_st) if (ps) cudaStreamSynchronize(ps);
+        g_pool.put(h_out); g_pool.put(h_boff);
+        return code;
+    };
+    auto launch = [&](size_t i) -> int {
+        tk_tokenizer::DecSlot& s = t->dslot[i % tk_tokenizer::kSlots];
+        const DChunk& c = chunks[i];
+        size_t ws_bytes = tkk::decode_workspace_bytes(c.n_ids, c.n_seqs, s.out.cap, &s.L);
+        CUDA_OR_FAIL(s.ws.ensure(ws_bytes));
+        cudaError_t e = tkk::decode_device(t->tables, (const uint32_t*)s.ids.p, (const uint64_t*)s.off.p, c.partial ? 0 : c.id_begin, c.n_seqs, c.n_ids,
+                                           policy, (uint8_t*)s.out.p, s.out.cap, (uint64_t*)s.boff.p, (int32_t*)s.status.p, s.ws.p, s.L, st_k);
+        if (e != cudaSuccess) return fail(TK_ERR_CUDA, "decode launch: %s", cudaGetErrorString(e));
+        CUDA_OR_FAIL(tkk::publish_small((const unsigned char*)s.ws.p + s.L.off_small, s.d_small_map, st_k));
+        CUDA_OR_FAIL(cudaEventRecord(s.done, st_k));
+        return TK_OK;
+    };
+    auto issue = [&](size_t i) -> int {
+        tk_tokenizer::DecSlot& s = t->dslot[i % tk_tokenizer::kSlots];
+        const DChunk& c = chunks[i];
+        if (!s.h_small) {
+            CUDA_OR_FAIL(cudaHostAlloc((void**)&s.h_small, 256, cudaHostAllocMapped));
+            CUDA_OR_FAIL(cudaHostGetDevicePointer((void**)&s.d_small_map, s.h_small, 0));
+            CUDA_OR_FAIL(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+            CUDA_OR_FAIL(cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
+            CUDA_OR_FAIL(cudaEventCreateWithFlags(&s.ev_out, cudaEventDisableTiming));
+        }
+        const size_t off_bytes = (c.n_seqs + 1) * 8;
+        CUDA_OR_FAIL(s.ids.ensure(c.n_ids * 4 + 64));
+        CUDA_OR_FAIL(s.off.ensure(off_bytes));
+        CUDA_OR_FAIL(s.boff.ensure(off_bytes));
+        CUDA_OR_FAIL(s.status.ensure((c.n_seqs + 1) * 4));
+        CUDA_OR_FAIL(s.out.ensure(std::max<uint64_t>(s.out.cap, c.n_ids * 6 + (1u << 16))));
+        const uint32_t* src = ids + c.id_begin;
+        const uint64_t* src_off = tok_off + c.seq_begin;
+        if (pageable || c.partial) {
+            const size_t need = ((off_bytes + 63) & ~(size_t)63) + (pageable ? c.n_ids * 4 : 0) + 64;
+            if (s.stage_cap < need) {
+                if (s.h_stage) { cudaStreamSynchronize(st_up); cudaFreeHost(s.h_stage); }
+                s.h_stage = nullptr; s.stage_cap = 0;
+                CUDA_OR_FAIL(cudaHostAlloc((void**)&s.h_stage, need + need / 8, cudaHostAllocDefault));
+                s.stage_cap = need + need / 8;
+            } else if (i >= (size_t)tk_tokenizer::kSlots) CUDA_OR_FAIL(cudaEventSynchronize(s.ev_in));
+            uint64_t* so = (uint64_t*)s.h_stage;
+            if (c.partial) { so[0] = 0; so[1] = c.n_ids; }
+            else memcpy(so, src_off, off_bytes);
+            src_off = so;
+            if (pageable) {
+                uint8_t* sd = s.h_stage + ((off_bytes + 63) & ~(size_t)63);
+                CopyPool::get().parallel_memcpy(sd, src, c.n_ids * 4);
+                src = (const uint32_t*)sd;
+            }
+        }
+        if (i >= (size_t)tk_tokenizer::kSlots) CUDA_OR_FAIL(cudaStreamWaitEvent(st_up, s.done, 0));
+        if (c.n_ids) CUDA_OR_FAIL(cudaMemcpyAsync(s.ids.p, src, c.n_ids * 4, cudaMemcpyHostToDevice, st_up));
+        CUDA_OR_FAIL(cudaMemcpyAsync(s.off.p, src_off, off_bytes, cudaMemcpyHostToDevice, st_up));
+        CUDA_OR_FAIL(cudaEventRecord(s.ev_in, st_up));
+        CUDA_OR_FAIL(cudaStreamWaitEvent(st_k, s.ev_in, 0));
+        if (i >= (size_t)tk_tokenizer::kSlots) CUDA_OR_FAIL(cudaStreamWaitEvent(st_k, s.ev_out, 0));
+        return launch(i);
+    };
+    std::vector<uint64_t> prefix(n_chunks + 1, 0);
+    constexpr size_t kAhead = tk_tokenizer::kSlots - 1;
+    for (size_t i = 0; i < kAhead && i < n_chunks; ++i) { rc = issue(i); if (rc) return bail(rc); }
+    for (size_t i = 0; i < n_chunks; ++i) {
+        tk_tokenizer::DecSlot& s = t->dslot[i % tk_tokenizer::kSlots];
+        const DChunk& c = chunks[i];
+        uint64_t n_bytes = 0;
+        for (int attempt = 0;; ++attempt) {
+            cudaError_t e = cudaEventSynchronize(s.done);
+            if (e != cudaSuccess) return bail(fail(TK_ERR_CUDA, "decode: %s", cudaGetErrorString(e)));
+            const uint32_t flags = s.h_small[tkk::TKK_S_FLAGS];
+            uint64_t first_bad;
+            memcpy(&n_bytes, s.h_small + tkk::TKK_S_TOTAL, 8);
+            memcpy(&first_bad, s.h_small + tkk::TKK_S_BADDOC, 8);
+            if (flags & tkk::TKK_FLAG_BAD_OFFSETS)
+                return bail(fail(TK_ERR_INVALID_ARGUMENT, "id offsets must start at 0, be non-decreasing and end at the id count"));
+            if (flags & tkk::TKK_FLAG_OUT_FULL) {
+                // this chunk's text is longer than the slot's buffer: the kernel reported the size, grow and run it again
+                if (attempt) return bail(fail(TK_ERR_CUDA, "decode buffer could not be grown"));
+                cudaError_t g = s.out.ensure(n_bytes + 4096);
+                if (g != cudaSuccess) return bail(fail(TK_ERR_CUDA, "decode buffer: %s", cudaGetErrorString(g)));
+                rc = launch(i);
+                if (rc) return bail(rc);
+                continue;
+            }
+            if (first_bad != ~0ull) {
+                int32_t st = 0;
+                e = cudaMemcpy(&st, (int32_t*)s.status.p + first_bad, 4, cudaMemcpyDeviceToHost);
+                if (e != cudaSuccess) return bail(fail(TK_ERR_CUDA, "decode: %s", cudaGetErrorString(e)));
+                const uint64_t bad = c.seq_begin + first_bad;
+                if (bad_doc) *bad_doc = bad;
+                if (st == TK_ERR_SPECIAL_TOKEN_POLICY)
+                    return bail(fail(TK_ERR_SPECIAL_TOKEN_POLICY, "Decoding tokens that contain special tokens is not allowed (sequence %llu)",
+                                     (unsigned long long)bad));
+                return bail(fail(TK_ERR_TOKENIZERS, "decode failed for sequence %llu: unknown token id or the bytes of an ordinary run are not valid UTF-8",
+                                 (unsigned long long)bad));
+            }
+            break;
+        }
+        if (i == 0) {
+            uint64_t cap = forced_cap;
+            if (!cap) cap = n_chunks == 1 ? n_bytes : (uint64_t)((double)n_bytes / (double)std::max<uint64_t>(1, c.n_ids) * 1.25 * (double)n_ids) + (1u << 16);
+            h_out = (uint8_t*)g_pool.get(cap + 1);
+            if (!h_out) return bail(fail(TK_ERR_CUDA, "out of pinned host memory"));
+            h_cap = cap;
+        }
+        if (prefix[i] + n_bytes > h_cap) { bail(TK_OK); return TK_ERR_BUFFER_TOO_SMALL; }     // caller repeats with the exact size
+        cudaError_t e = cudaSuccess;
+        if (n_bytes) e = cudaMemcpyAsync(h_out + prefix[i], s.out.p, n_bytes, cudaMemcpyDeviceToHost, st_down);
+        if (e == cudaSuccess && !c.partial && c.n_seqs) e = cudaMemcpyAsync(h_boff + c.seq_begin, s.boff.p, c.n_seqs * 8, cudaMemcpyDeviceToHost, st_down);
+        if (e == cudaSuccess) e = cudaEventRecord(s.ev_out, st_down);
+        if (e != cudaSuccess) return bail(fail(TK_ERR_CUDA, "copying text back: %s", cudaGetErrorString(e)));
+        prefix[i + 1] = prefix[i] + n_bytes;
+        if (i + kAhead < n_chunks) { rc = issue(i + kAhead); if (rc) return bail(rc); }
+    }
+    {
+        cudaError_t e = cudaStreamSynchronize(st_down);
+        if (e != cudaSuccess) return bail(fail(TK_ERR_CUDA, "copying text back: %s", cudaGetErrorString(e)));
+    }
+    for (size_t i = 0; i < n_chunks; ++i) {
+        const DChunk& c = chunks[i];
+        const uint64_t add = prefix[i];
+        if (c.partial) { if (c.first) h_boff[c.seq_begin] = add; }
+        else if (add) for (size_t d = c.seq_begin; d < c.seq_begin + c.n_seqs; ++d) h_boff[d] += add;
+    }
+    h_boff[n_seqs] = prefix[n_chunks];
+    if (!h_out) { h_out = (uint8_t*)g_pool.get(1); if (!h_out) return bail(fail(TK_ERR_CUDA, "out of host memory")); }
+    h_out[prefix[n_chunks]] = 0;
+    *out = h_out;
+    *byte_off = h_boff;
+    return TK_OK;
+}
+
 extern "C" int tk_decode_batch(const tk_tokenizer* tc, const uint32_t* ids, const uint64_t* tok_off, size_t n_docs, int policy,
                                uint8_t** out, uint64_t** byte_off, uint64_t* bad_doc) {
     int rc = check_encode_args(tc, 0, 0);
@@ -1216,45 +1477,28 @@ extern "C" int tk_decode_batch(const tk_tokenizer* tc, const uint32_t* ids, cons
     if (!tok_off || !out || !byte_off) return fail(TK_ERR_INVALID_ARGUMENT, "null argument");
     *out = nullptr;
     *byte_off = nullptr;
+    if (policy != TK_POLICY_IGNORE && policy != TK_POLICY_KEEP && policy != TK_POLICY_RAISE)
+        return fail(TK_ERR_INVALID_ARGUMENT, "unknown special token policy %d", policy);
+    {
+        uint64_t bad = tok_off[0] != 0;
+        for (size_t d = 0; d < n_docs; ++d) bad |= (uint64_t)(tok_off[d + 1] < tok_off[d]);
+        if (bad) return fail(TK_ERR_INVALID_ARGUMENT, "id offsets must start at 0, be non-decreasing and end at the id count");
+    }
     const uint64_t n_ids = tok_off[n_docs];
     if (!ids && n_ids) return fail(TK_ERR_INVALID_ARGUMENT, "null ids");
+    if (((uintptr_t)ids & 3u) != 0) return fail(TK_ERR_INVALID_ARGUMENT, "id pointer must be 4-byte aligned");
     tk_tokenizer* t = const_cast<tk_tokenizer*>(tc);
+    rc = decode_batch_engine(t, ids, tok_off, n_docs, policy, out, byte_off, bad_doc, 0);
+    if (rc != TK_ERR_BUFFER_TOO_SMALL) return rc;
+    // the estimate of the text size was too small: the exact size from the host tables, once
     const tk::HostModel& h = t->host;
-    // exact output size from the host tables (a length sum over ids; the bytes themselves are
-    // gathered on the device)
     uint64_t cap = 0;
     for (uint64_t i = 0; i < n_ids; ++i) {
         const uint32_t v = ids[i];
         if (v < h.num_special) { if (policy == TK_POLICY_KEEP) cap += h.special_off[v + 1] - h.special_off[v]; }
         else if (v - h.num_special < h.n_vocab()) cap += h.vocab_off[v - h.num_special + 1] - h.vocab_off[v - h.num_special];
     }
-    std::lock_guard<std::mutex> g(t->mu);
-    DeviceGuard dg(t->device);
-    if (!dg.ok) return fail(TK_ERR_CUDA, "cudaSetDevice(%d) failed", t->device);
-    cudaStream_t st = t->stream;
-    CUDA_OR_FAIL(t->in_data.ensure(n_ids * 4 + 64));
-    CUDA_OR_FAIL(t->in_off.ensure((n_docs + 1) * 8));
-    CUDA_OR_FAIL(t->out_a.ensure(cap + 64));
-    CUDA_OR_FAIL(t->out_b.ensure((n_docs + 1) * 8));
-    CUDA_OR_FAIL(t->status.ensure((n_docs + 1) * 4));
-    if (n_ids) CUDA_OR_FAIL(cudaMemcpyAsync(t->in_data.p, ids, n_ids * 4, cudaMemcpyHostToDevice, st));
-    CUDA_OR_FAIL(cudaMemcpyAsync(t->in_off.p, tok_off, (n_docs + 1) * 8, cudaMemcpyHostToDevice, st));
-    uint64_t n_bytes = 0;
-    rc = run_decode(t, (const uint32_t*)t->in_data.p, (const uint64_t*)t->in_off.p, n_docs, n_ids, policy, (uint8_t*)t->out_a.p, cap,
-                    (uint64_t*)t->out_b.p, (int32_t*)t->status.p, &n_bytes, bad_doc, st);
-    if (rc) return rc;
-    uint8_t* h_out = (uint8_t*)g_pool.get(n_bytes + 1);
-    uint64_t* h_off = (uint64_t*)g_pool.get((n_docs + 1) * 8);
-    if (!h_out || !h_off) { g_pool.put(h_out); g_pool.put(h_off); return fail(TK_ERR_CUDA, "out of pinned host memory"); }
-    cudaError_t e = cudaSuccess;
-    if (n_bytes) e = cudaMemcpyAsync(h_out, t->out_a.p, n_bytes, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(h_off, t->out_b.p, (n_docs + 1) * 8, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) { g_pool.put(h_out); g_pool.put(h_off); return fail(TK_ERR_CUDA, "copying text back: %s", cudaGetErrorString(e)); }
-    h_out[n_bytes] = 0;
-    *out = h_out;
-    *byte_off = h_off;
-    return TK_OK;
+    return decode_batch_engine(t, ids, tok_off, n_docs, policy, out, byte_off, bad_doc, cap + 1);
 }
 
 extern "C" int tk_decode(const tk_tokenizer* t, const uint32_t* ids, size_t n, int policy, uint8_t** out, size_t* n_out) {

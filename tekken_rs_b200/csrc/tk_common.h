@@ -73,6 +73,22 @@ struct TkPieceHasher {
 // ---- pair table: (left id, right id) -> rank of the concatenation ------------------------------
 // One u64 per slot: bit 63 = occupied, bits 42..62 = left id, 21..41 = right id, 0..20 = rank.
 // Ids are < 2^21 (checked at load).
+// Layout (TK_PAIR_BUCKETED, the default): BUCKETS of four slots = one 32-byte sector, fetched with two
+// 16-byte loads; a key lives in the bucket its hash names, slots of a bucket fill front to back, and only the
+// entries that find their bucket full spill into the next one -- so a lookup (hit or miss) ends in its first
+// bucket unless that bucket is full (well under 1 % of the buckets at the load factor the builder keeps).
+// The merge kernels run one lane per piece: a warp-wide round of lookups takes as many dependent round trips
+// to L2 as its unluckiest lane, and with one slot per probe (the round-1 layout, kept under TK_PAIR_BUCKETED=0)
+// that was two to four per round; with buckets it is one.
+// Both layouts are resident (TK_PAIR_BUCKETED=1, the default; 8 MB + 16 MB for the Tekken vocabulary): measured on
+// the bench corpus, the classes of 17..96-byte pieces -- low occupancy, bound by the latency of the dependent
+// round trips -- run 1.1-1.35x faster on buckets, while the classes up to 16 bytes -- bound by the L1TEX pipe,
+// where a fully divergent load costs one cycle per lane and two 16-byte loads cost twice one 8-byte load -- are
+// 1.1-1.3x faster on the one-slot table (r02d A/B in profiles/).  Kernels pick by a template flag.
+#ifndef TK_PAIR_BUCKETED
+#define TK_PAIR_BUCKETED 1
+#endif
+#define TK_PAIR_BUCKET_SLOTS 4u
 #define TK_ID_BITS 21u
 #define TK_ID_MASK ((1u << TK_ID_BITS) - 1u)
 
@@ -94,8 +110,10 @@ struct TkDeviceTables {
     const uint8_t* uni_stage2;     // n_blocks * 32 bytes
     const TkVocabSlot* vocab_slots;
     uint32_t vocab_mask;           // capacity - 1
-    const uint64_t* pair_slots;
-    uint32_t pair_mask;
+    const uint64_t* pair_slots;    // one-slot open addressing (linear probing)
+    uint32_t pair_mask;            // slot count - 1
+    const uint64_t* pair_buckets;  // the same entries in four-slot buckets (null with TK_PAIR_BUCKETED=0)
+    uint32_t bucket_mask;          // bucket count - 1
     const uint32_t* byte_pair;     // [b0 << 8 | b1] -> rank of the two-byte token, TK_INF if none
     const uint4* vocab_pad16;      // token bytes zero-padded to 16 (tokens longer than that: first 16 bytes)
     const uint8_t* vocab_len;      // token length, 255 = look at vocab_off

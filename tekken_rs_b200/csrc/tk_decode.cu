@@ -26,12 +26,12 @@ struct DocErr {
     unsigned long long unk_tok, sp_tok, sp_byte, utf_byte;
 };
 
-__global__ void tokmark_kernel(const uint64_t* __restrict__ tok_off, uint64_t n_docs, uint64_t total,
+__global__ void tokmark_kernel(const uint64_t* __restrict__ tok_off, uint64_t off_base, uint64_t n_docs, uint64_t total,
                                uint32_t* __restrict__ tds, uint32_t* __restrict__ seq_first, uint32_t* __restrict__ flags) {
     uint64_t d = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (d > n_docs) return;
-    uint64_t o = tok_off[d];
-    bool ok = o <= total;
+    uint64_t o = tok_off[d] - off_base;      // offsets may be a slice of a larger batch (off_base = its first entry)
+    bool ok = tok_off[d] >= off_base && o <= total;
     if (d == 0 && o != 0) ok = false;
     if (d == n_docs && o != total) ok = false;
     if (d < n_docs && tok_off[d + 1] < o) ok = false;
@@ -41,11 +41,11 @@ __global__ void tokmark_kernel(const uint64_t* __restrict__ tok_off, uint64_t n_
 }
 
 // index of the sequence that contains position i (last d < n_docs with off[d] <= i)
-__device__ __forceinline__ uint64_t seq_of(const uint64_t* __restrict__ off, uint64_t n_docs, uint64_t i) {
+__device__ __forceinline__ uint64_t seq_of(const uint64_t* __restrict__ off, uint64_t off_base, uint64_t n_docs, uint64_t i) {
     uint64_t lo = 0, hi = n_docs;   // find first d with off[d] > i
     while (lo < hi) {
         uint64_t mid = (lo + hi) >> 1;
-        if (off[mid] <= i) lo = mid + 1; else hi = mid;
+        if (off[mid] - off_base <= i) lo = mid + 1; else hi = mid;
     }
     return lo ? lo - 1 : 0;
 }
@@ -70,7 +70,7 @@ __device__ __forceinline__ void dc_put(uint8_t* __restrict__ buf, bool fits, uin
 #define DC_MINB 8      // 32 registers (measured: 5.4 ms; 5.8 ms at 40 registers, 7.8 ms uncapped at 71)
 #endif
 __global__ void __launch_bounds__(DC_T, DC_MINB) decode_gather_kernel(const uint32_t* __restrict__ ids, uint64_t n_ids,
-                                                             const uint64_t* __restrict__ tok_off, uint64_t n_docs,
+                                                             const uint64_t* __restrict__ tok_off, uint64_t off_base, uint64_t n_docs,
                                                              const uint32_t* __restrict__ tds, const uint32_t* __restrict__ seq_first,
                                                              int policy, TkDeviceTables T,
                                                              uint8_t* __restrict__ out, uint64_t out_cap,
@@ -184,8 +184,8 @@ __global__ void __launch_bounds__(DC_T, DC_MINB) decode_gather_kernel(const uint
         const uint64_t ok = o + pre;
         const uint32_t pk = p + pre;
         if ((tw >> k) & 1u) {
-            while (tok_off[seq] < i) ++seq;              // sequences that start earlier in the group
-            for (; seq <= n_docs && tok_off[seq] == i; ++seq) byte_off[seq] = ok;
+            while (tok_off[seq] - off_base < i) ++seq;   // sequences that start earlier in the group
+            for (; seq <= n_docs && tok_off[seq] - off_base == i; ++seq) byte_off[seq] = ok;
             mark_boundary(bmask, ok, out_cap);
         }
         if (i == n_ids) break;
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(DC_T, DC_MINB) decode_gather_kernel(const uint
             // a special id ends the ordinary run before it and starts a new one after it
             mark_boundary(bmask, ok, out_cap);
             if (policy == TK_POLICY_RAISE) {
-                const uint64_t d = seq_of(tok_off, n_docs, i);
+                const uint64_t d = seq_of(tok_off, off_base, n_docs, i);
                 atomicMin(&docerr[d].sp_tok, (unsigned long long)i);
                 atomicMin(&docerr[d].sp_byte, (unsigned long long)ok);
             } else if (policy == TK_POLICY_KEEP) {
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(DC_T, DC_MINB) decode_gather_kernel(const uint
         } else {
             const uint32_t r = v - T.num_special;
             if (r >= T.n_vocab) {
-                const uint64_t d = seq_of(tok_off, n_docs, i);
+                const uint64_t d = seq_of(tok_off, off_base, n_docs, i);
                 atomicMin(&docerr[d].unk_tok, (unsigned long long)i);
             } else {
                 dc_put(buf, fits, pk, out, ok, out_cap, T.vocab_bytes + T.vocab_off[r], l);
@@ -344,7 +344,7 @@ size_t decode_workspace_bytes(uint64_t n_ids, uint64_t n_docs, uint64_t out_cap,
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
 
-cudaError_t decode_device(const TkDeviceTables& T, const uint32_t* d_ids, const uint64_t* d_tok_off, uint64_t n_docs,
+cudaError_t decode_device(const TkDeviceTables& T, const uint32_t* d_ids, const uint64_t* d_tok_off, uint64_t off_base, uint64_t n_docs,
                           uint64_t n_ids, int policy, uint8_t* d_out, uint64_t out_cap, uint64_t* d_byte_off,
                           int32_t* d_doc_status, void* d_ws, const DecodeLayout& L, cudaStream_t st) {
     unsigned char* ws = (unsigned char*)d_ws;
@@ -365,9 +365,9 @@ cudaError_t decode_device(const TkDeviceTables& T, const uint32_t* d_ids, const 
     CK(cudaMemsetAsync(bmask, 0, L.mask_words_out * 4, st));
     CK(cudaMemsetAsync(tilestate, 0, L.n_tiles * 8, st));
     CK(cudaMemsetAsync(docerr, 0xFF, (n_docs + 1) * sizeof(DocErr), st));
-    tokmark_kernel<<<(unsigned)ceil_div(n_docs + 1, 256), 256, 0, st>>>(d_tok_off, n_docs, n_ids, tds, seq_first, flags);
+    tokmark_kernel<<<(unsigned)ceil_div(n_docs + 1, 256), 256, 0, st>>>(d_tok_off, off_base, n_docs, n_ids, tds, seq_first, flags);
     count_launch();
-    decode_gather_kernel<<<(unsigned)L.n_tiles, DC_T, 0, st>>>(d_ids, n_ids, d_tok_off, n_docs, tds, seq_first, policy, T, d_out, out_cap,
+    decode_gather_kernel<<<(unsigned)L.n_tiles, DC_T, 0, st>>>(d_ids, n_ids, d_tok_off, off_base, n_docs, tds, seq_first, policy, T, d_out, out_cap,
                                                              d_byte_off, bmask, docerr, tilestate, ticket, total_out, flags);
     count_launch();
     {

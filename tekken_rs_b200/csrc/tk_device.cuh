@@ -13,6 +13,7 @@
 
 __device__ __forceinline__ uint64_t tk_ldg64(const uint64_t* p) { return __ldg((const unsigned long long*)p); }
 
+// ---- pair table, one-slot layout (linear probing) -----------------------------------------------
 // rank of bytes(l)+bytes(r), TK_INF if it is not a vocabulary entry
 __device__ __forceinline__ uint32_t tk_pair_rank(const TkDeviceTables& T, uint32_t l, uint32_t r) {
     uint32_t i = tk_pair_hash(l, r) & T.pair_mask;
@@ -27,8 +28,8 @@ __device__ __forceinline__ uint32_t tk_pair_rank(const TkDeviceTables& T, uint32
 
 // Two independent pair lookups with their first probes in flight together (a merge creates two
 // new adjacent pairs; their ranks do not depend on each other).  l == TK_INF skips a lookup.
-__device__ __forceinline__ void tk_pair_rank2(const TkDeviceTables& T, uint32_t l0, uint32_t r0, uint32_t l1, uint32_t r1,
-                                              uint32_t* out0, uint32_t* out1) {
+__device__ __forceinline__ void tk_pair_rank2_slots(const TkDeviceTables& T, uint32_t l0, uint32_t r0, uint32_t l1, uint32_t r1,
+                                                    uint32_t* out0, uint32_t* out1) {
     const bool h0 = l0 != TK_INF && r0 != TK_INF, h1 = l1 != TK_INF && r1 != TK_INF;
     uint32_t i0 = tk_pair_hash(l0, r0) & T.pair_mask, i1 = tk_pair_hash(l1, r1) & T.pair_mask;
     const uint64_t k0 = tk_pair_key(l0, r0), k1 = tk_pair_key(l1, r1);
@@ -48,6 +49,66 @@ __device__ __forceinline__ void tk_pair_rank2(const TkDeviceTables& T, uint32_t 
     }
     *out0 = a;
     *out1 = b;
+}
+
+#if TK_PAIR_BUCKETED
+// ---- pair table, bucket layout: one bucket = four slots = one 32-byte sector, read with two 16-byte loads ----
+struct TkPairBucket {
+    uint4 a, b;
+    __device__ __forceinline__ uint64_t slot(int k) const {
+        return k == 0 ? ((uint64_t)a.y << 32 | a.x) : k == 1 ? ((uint64_t)a.w << 32 | a.z) : k == 2 ? ((uint64_t)b.y << 32 | b.x) : ((uint64_t)b.w << 32 | b.z);
+    }
+};
+__device__ __forceinline__ TkPairBucket tk_pair_bucket_load(const TkDeviceTables& T, uint32_t bucket) {
+    const uint4* p = reinterpret_cast<const uint4*>(T.pair_buckets) + 2u * bucket;
+    TkPairBucket B;
+    B.a = __ldg(p);
+    B.b = __ldg(p + 1);
+    return B;
+}
+// the rank stored for key (slot >> TK_ID_BITS == key | occupied bit) in bucket B, TK_INF if it is not there;
+// *full = the bucket has no free slot (the key may then have spilled into the next bucket)
+__device__ __forceinline__ uint32_t tk_pair_bucket_find(const TkPairBucket& B, uint64_t tag, bool* full) {
+    uint32_t r = TK_INF;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint64_t s = B.slot(k);
+        if ((s >> TK_ID_BITS) == tag) r = (uint32_t)s & TK_ID_MASK;
+    }
+    *full = B.slot(3) != 0;
+    return r;
+}
+__device__ __forceinline__ void tk_pair_rank2_buckets(const TkDeviceTables& T, uint32_t l0, uint32_t r0, uint32_t l1, uint32_t r1,
+                                                      uint32_t* out0, uint32_t* out1) {
+    const bool h0 = l0 != TK_INF && r0 != TK_INF, h1 = l1 != TK_INF && r1 != TK_INF;
+    uint32_t b0 = tk_pair_hash(l0, r0) & T.bucket_mask, b1 = tk_pair_hash(l1, r1) & T.bucket_mask;
+    const uint64_t t0 = (1ull << (63u - TK_ID_BITS)) | tk_pair_key(l0, r0), t1 = (1ull << (63u - TK_ID_BITS)) | tk_pair_key(l1, r1);
+    TkPairBucket B0, B1;
+    B0.a = B0.b = B1.a = B1.b = make_uint4(0u, 0u, 0u, 0u);
+    if (h0) B0 = tk_pair_bucket_load(T, b0);
+    if (h1) B1 = tk_pair_bucket_load(T, b1);
+    bool f0, f1;
+    uint32_t a = tk_pair_bucket_find(B0, t0, &f0), b = tk_pair_bucket_find(B1, t1, &f1);
+    while (a == TK_INF && f0) {                    // rare: the first bucket is full
+        b0 = (b0 + 1) & T.bucket_mask;
+        a = tk_pair_bucket_find(tk_pair_bucket_load(T, b0), t0, &f0);
+    }
+    while (b == TK_INF && f1) {
+        b1 = (b1 + 1) & T.bucket_mask;
+        b = tk_pair_bucket_find(tk_pair_bucket_load(T, b1), t1, &f1);
+    }
+    *out0 = a;
+    *out1 = b;
+}
+#endif
+
+template <bool BUCKETS>
+__device__ __forceinline__ void tk_pair_rank2(const TkDeviceTables& T, uint32_t l0, uint32_t r0, uint32_t l1, uint32_t r1,
+                                              uint32_t* out0, uint32_t* out1) {
+#if TK_PAIR_BUCKETED
+    if (BUCKETS) { tk_pair_rank2_buckets(T, l0, r0, l1, r1, out0, out1); return; }
+#endif
+    tk_pair_rank2_slots(T, l0, r0, l1, r1, out0, out1);
 }
 
 // ---- decoupled look-back over tiles (single-pass prefix sum) -------------------------------------
@@ -216,6 +277,9 @@ __device__ __forceinline__ uint32_t tk_popc_m(tk_u128 m) {
 }
 #define TK_KEY_SHIFT 7u                                  // key = rank << TK_KEY_SHIFT | offset; offsets < 128
 
+#ifndef TK_BUCKET_ABOVE
+#define TK_BUCKET_ABOVE 16      // lane-merge classes of pieces longer than this use the bucket layout of the pair table
+#endif
 template <class M, int MAXLEN>
 __device__ __forceinline__ M tk_bpe_merge_loop(const TkDeviceTables& T, uint32_t len, uint32_t* id, uint32_t* key, uint32_t& lookups) {
     constexpr uint32_t kBits = sizeof(M) * 8;
@@ -245,7 +309,7 @@ __device__ __forceinline__ M tk_bpe_merge_loop(const TkDeviceTables& T, uint32_t
         const uint32_t lft = pv != 0xFFFFFFFFu ? id[pv] : TK_INF;
         const uint32_t rgt = nn != 0xFFFFFFFFu ? id[nn] : TK_INF;
         uint32_t r0, r1;
-        tk_pair_rank2(T, lft, rank, rank, rgt, &r0, &r1);
+        tk_pair_rank2<(MAXLEN > TK_BUCKET_ABOVE)>(T, lft, rank, rank, rgt, &r0, &r1);
         lookups += (lft != TK_INF ? 1u : 0u) + (rgt != TK_INF ? 1u : 0u);
         if (pv != 0xFFFFFFFFu) key[pv] = r0 == TK_INF ? TK_INF : ((r0 << TK_KEY_SHIFT) | pv);
         key[bp] = r1 == TK_INF ? TK_INF : ((r1 << TK_KEY_SHIFT) | bp);

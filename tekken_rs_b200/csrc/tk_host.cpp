@@ -652,15 +652,40 @@ HostModel HostModel::build(const std::vector<VocabEntry>& vocab, const std::vect
             }
         }
         m.n_pairs = entries.size();
-        uint32_t cap = 1024;
-        while (cap < 3 * entries.size()) cap <<= 1;
-        m.pair_slots.assign(cap, 0);
-        for (uint64_t e : entries) {
-            uint32_t l = (uint32_t)((e >> (2 * TK_ID_BITS)) & TK_ID_MASK), r = (uint32_t)((e >> TK_ID_BITS) & TK_ID_MASK);
-            uint32_t i = tk_pair_hash(l, r) & (cap - 1);
-            while (m.pair_slots[i] != 0) i = (i + 1) & (cap - 1);
-            m.pair_slots[i] = e;
+        {
+            uint32_t cap = 1024;
+            while (cap < 3 * entries.size()) cap <<= 1;
+            m.pair_slots.assign(cap, 0);
+            for (uint64_t e : entries) {
+                uint32_t l = (uint32_t)((e >> (2 * TK_ID_BITS)) & TK_ID_MASK), r = (uint32_t)((e >> TK_ID_BITS) & TK_ID_MASK);
+                uint32_t i = tk_pair_hash(l, r) & (cap - 1);
+                while (m.pair_slots[i] != 0) i = (i + 1) & (cap - 1);
+                m.pair_slots[i] = e;
+            }
+            m.pair_mask = cap - 1;
         }
+#if TK_PAIR_BUCKETED
+        {
+            // buckets of four slots, on average at most 0.55 entries per bucket: about 0.2 % of the buckets are full
+            uint32_t nb = 256;
+            while ((double)nb * 0.55 < (double)entries.size()) nb <<= 1;
+            if (const char* e = getenv("TEKKEN_B200_PAIR_BUCKETS_LOG2")) { const int k = atoi(e); if (k >= 8 && k <= 26) nb = 1u << k; }
+            while ((uint64_t)nb * TK_PAIR_BUCKET_SLOTS < 2 * entries.size()) nb <<= 1;      // never more than half full
+            m.pair_buckets.assign((size_t)nb * TK_PAIR_BUCKET_SLOTS, 0);
+            for (uint64_t e : entries) {
+                uint32_t l = (uint32_t)((e >> (2 * TK_ID_BITS)) & TK_ID_MASK), r = (uint32_t)((e >> TK_ID_BITS) & TK_ID_MASK);
+                uint32_t b = tk_pair_hash(l, r) & (nb - 1);
+                for (;;) {
+                    uint64_t* slot = &m.pair_buckets[(size_t)b * TK_PAIR_BUCKET_SLOTS];
+                    uint32_t k = 0;
+                    while (k < TK_PAIR_BUCKET_SLOTS && slot[k] != 0) ++k;
+                    if (k < TK_PAIR_BUCKET_SLOTS) { slot[k] = e; break; }
+                    b = (b + 1) & (nb - 1);
+                }
+            }
+            m.bucket_mask = nb - 1;
+        }
+#endif
     }
     // decode's gather source: every token in an aligned 16-byte cell + its length in a byte
     {

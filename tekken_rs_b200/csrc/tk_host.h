@@ -63,6 +63,9 @@ struct HostModel {
     std::vector<uint8_t> uni_stage2;
     std::vector<TkVocabSlot> vocab_slots;
     std::vector<uint64_t> pair_slots;
+    uint32_t pair_mask = 0;                                   // slot count - 1
+    std::vector<uint64_t> pair_buckets;                       // the same entries in four-slot buckets (see tk_common.h)
+    uint32_t bucket_mask = 0;
     std::vector<uint32_t> byte_pair;                          // 65536 entries, direct-indexed
     std::vector<uint8_t> vocab_pad16;                         // 16 bytes per rank (decode's gather source)
     std::vector<uint8_t> vocab_len8;                          // length per rank, 255 = longer than 254

@@ -741,7 +741,7 @@ __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __
                 const uint32_t lf = i == 0 ? TK_INF : (i >= 2 && rL[i - 2] != HG_UNSEL) ? mn : id[i - 1];
                 const uint32_t rt = i + 2 < m ? id[i + 2] : TK_INF;
                 uint32_t x, y;
-                tk_pair_rank2(T, lf, mn, mn, rt, &x, &y);
+                tk_pair_rank2<true>(T, lf, mn, mn, rt, &x, &y);
                 rR[i] = y;
                 rL[i] = x == HG_UNSEL ? TK_INF : x;           // (ranks are < 2^21: never equal to the marker)
                 if (x <= mn || y <= mn) hazard = min(hazard, i);
@@ -1058,6 +1058,16 @@ __device__ __forceinline__ void lm_load_words(const uint8_t* __restrict__ data, 
     }
 }
 
+// register budgets of the three short classes (resident blocks the compiler plans for), from A/B builds
+#ifndef LM_MINB_12
+#define LM_MINB_12 6
+#endif
+#ifndef LM_MINB_8
+#define LM_MINB_8 8
+#endif
+#ifndef LM_MINB_4
+#define LM_MINB_4 6
+#endif
 template <int MAXLEN, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) lanemerge_kernel(const uint8_t* __restrict__ data, uint64_t n, TkDeviceTables T,
                                                             const unsigned long long* __restrict__ queue,
@@ -1551,6 +1561,11 @@ __global__ void publish_kernel(const uint32_t* __restrict__ small, uint32_t* __r
     mapped[threadIdx.x] = small[threadIdx.x];
     __threadfence_system();
 }
+cudaError_t publish_small(const void* d_small, uint32_t* mapped_dev, cudaStream_t st) {
+    publish_kernel<<<1, 64, 0, st>>>((const uint32_t*)d_small, mapped_dev);
+    count_launch();
+    return cudaGetLastError();
+}
 cudaError_t publish_counters(const void* d_ws, const EncodeLayout& L, uint32_t* mapped_dev, cudaStream_t st) {
     publish_kernel<<<1, 64, 0, st>>>((const uint32_t*)((const unsigned char*)d_ws + L.off_small), mapped_dev);
     count_launch();
@@ -1719,9 +1734,9 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
     TK_LANEMERGE(32, 256, 1, 5, "lanemerge32")
     TK_LANEMERGE(24, 256, 1, 4, "lanemerge24")
     TK_LANEMERGE(16, 256, 1, 3, "lanemerge16")
-    TK_LANEMERGE(12, 256, 6, 2, "lanemerge12")
-    TK_LANEMERGE(8, 256, 8, 1, "lanemerge8")
-    TK_LANEMERGE(4, 256, 6, 0, "lanemerge4")
+    TK_LANEMERGE(12, 256, LM_MINB_12, 2, "lanemerge12")
+    TK_LANEMERGE(8, 256, LM_MINB_8, 1, "lanemerge8")
+    TK_LANEMERGE(4, 256, LM_MINB_4, 0, "lanemerge4")
 #undef TK_LANEMERGE
     if (timer) timer->mark(st, "emit");
     {

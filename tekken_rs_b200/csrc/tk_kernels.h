@@ -108,9 +108,10 @@ cudaError_t encode_small(const TkDeviceTables& T, const uint8_t* d_text, uint32_
                          uint32_t seq, cudaStream_t st);
 
 cudaError_t publish_counters(const void* d_ws, const EncodeLayout& L, uint32_t* mapped_dev, cudaStream_t st);
+cudaError_t publish_small(const void* d_small, uint32_t* mapped_dev, cudaStream_t st);     // any 256-byte counter block
 
 size_t decode_workspace_bytes(uint64_t n_ids, uint64_t n_docs, uint64_t out_cap, DecodeLayout* L);
-cudaError_t decode_device(const TkDeviceTables& T, const uint32_t* d_ids, const uint64_t* d_tok_off, uint64_t n_docs,
+cudaError_t decode_device(const TkDeviceTables& T, const uint32_t* d_ids, const uint64_t* d_tok_off, uint64_t off_base, uint64_t n_docs,
                           uint64_t n_ids, int policy, uint8_t* d_out, uint64_t out_cap, uint64_t* d_byte_off,
                           int32_t* d_doc_status, void* d_ws, const DecodeLayout& L, cudaStream_t st);
 

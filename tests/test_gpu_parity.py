@@ -161,6 +161,22 @@ def test_host_engine_chunks_slices_and_devices(gpu_tok, oracle, tekken_json):
             for bos, eos in ((False, False), (True, False)):
                 one, _ = gpu_tok.encode_batch_np(np.frombuffer(big, dtype=np.uint8), np.array([0, len(big)], dtype=np.uint64), bos, eos)
                 assert one.tolist() == oracle.encode(big, bos, eos)
+            # the decode engine on the same ids: chunks of ids, sequences larger than a chunk sliced before an id that
+            # starts with an ASCII byte (the CJK document has no such id for 100 k ids), Keep and Ignore
+            back, boff = gpu_tok.decode_batch_np(want, woff, SpecialTokenPolicy.Ignore)
+            assert np.array_equal(boff, off) and np.array_equal(back, data), "decode, chunk %d" % chunk
+            kept, koff = gpu_tok.decode_batch_np(want, woff, SpecialTokenPolicy.Keep)
+            assert len(kept) == len(data) + 7 * len(docs) and bytes(kept[:3]) == b"<s>" and bytes(kept[-4:]) == b"</s>"
+            assert np.array_equal(koff, off + np.arange(len(off), dtype=np.uint64) * np.uint64(7))
+            broken = want.copy()
+            k = int(woff[len(docs) - 5]) + 1
+            broken[k], broken[k + 1] = 1000 + 0xE4, 1000 + 0x41     # a lead byte followed by 'A' in a late sequence
+            with pytest.raises(TokenizerError) as e:
+                gpu_tok.decode_batch_np(broken, woff, SpecialTokenPolicy.Ignore)
+            assert e.value.kind == "Tokenizers" and "sequence %d" % (len(docs) - 5) in e.value.msg
+            with pytest.raises(TokenizerError) as e:
+                gpu_tok.decode_batch_np(want, woff, SpecialTokenPolicy.Raise)
+            assert e.value.kind == "SpecialTokenPolicy" and "sequence 0)" in e.value.msg
         # a tiny estimate for the result buffer: the first chunk has few ids per byte, the rest many (forces the repeat)
         set_chunk_bytes(64 << 10)
         skew = [b" " * 60000 + b"x"] + ["".join(chr(rng.randint(0x4E00, 0x9FA5)) for _ in range(300)).encode() for _ in range(2000)]
