@@ -185,11 +185,52 @@ int tk_decode_batch_device(const tk_tokenizer *t, const uint32_t *d_ids, const u
                            uint64_t out_capacity, uint64_t *d_byte_off, int32_t *d_doc_status,
                            uint64_t *n_bytes, uint64_t *bad_doc, void *stream);
 
+/* ---- audio token counting: AudioEncoder::encode, the token part (src/audio.rs:555-591) ---- */
+
+/* AudioConfig + AudioSpectrogramConfig (src/audio.rs:18-22, 86-91).  chunk_length_s <= 0 means None. */
+typedef struct tk_audio_config {
+    uint64_t sampling_rate;
+    double frame_rate;
+    uint64_t num_mel_bins, hop_length, window_size;
+    double chunk_length_s;
+} tk_audio_config;
+
+int tk_has_audio_support(const tk_tokenizer *t);                      /* src/tekkenizer.rs:746-748 */
+int tk_audio_config_of(const tk_tokenizer *t, tk_audio_config *out);  /* :757-759; TK_ERR_AUDIO when the file has no `audio` */
+/* Samples after Audio::pad (:439-463) and the number of [AUDIO] ids (:563-584) for a clip of n_samples samples at
+   cfg->sampling_rate (i.e. after the resampling of :557).  Host arithmetic, O(1). */
+int tk_audio_token_count(const tk_audio_config *cfg, uint64_t n_samples, uint64_t *padded_samples,
+                         uint64_t *n_audio_tokens);
+/* AudioEncoding::tokens of encode_audio (src/tekkenizer.rs:728-735): [BEGIN_AUDIO] then one [AUDIO] per frame group,
+   ready to be spliced between text ids (examples/audio_tokenization_test.rs:52-62).  TK_ERR_AUDIO without audio config. */
+int tk_encode_audio_tokens(const tk_tokenizer *t, uint64_t n_samples, uint32_t **out, size_t *n_out);
+
 /* ---- multi-GPU sharding (documents are independent: no collective) -------------------- */
 
 /* Byte-balanced contiguous document ranges: shard s gets documents
    [shard_begin[s], shard_begin[s+1]).  shard_begin has n_shards+1 entries. */
 int tk_shard_plan(const uint64_t *doc_off, size_t n_docs, size_t n_shards, uint64_t *shard_begin);
+
+/* ---- streaming: text file in, id shards out ------------------------- */
+
+typedef enum tk_shard_format {
+    TK_SHARDS_RAW_U32 = 0, /* ids: little-endian u32, back to back (the usual training `.bin`); offsets: u64 */
+    TK_SHARDS_NPY = 1      /* the same data behind a NumPy .npy header (1-D '<u4' / '<u8') */
+} tk_shard_format;
+
+typedef struct tk_file_stats {
+    uint64_t n_docs, n_bytes, n_tokens;
+    double seconds;
+} tk_file_stats;
+
+/* Encode a UTF-8 text file into a shard of ids.  The file is memory-mapped and cut into documents at `delimiter` (a
+   byte value such as '\n' or 0; every document includes its delimiter; -1: the whole file is one document), encoded
+   window by window on all `n_handles` devices (handles of one tokenizer, as for tk_encode_batch_multi) while the
+   previous window's ids are written out, so memory use does not grow with the file.  `offsets_path` (may be NULL)
+   receives n_docs + 1 token offsets. */
+int tk_encode_file(tk_tokenizer *const *handles, size_t n_handles, const char *text_path, int delimiter,
+                   int add_bos, int add_eos, const char *tokens_path, const char *offsets_path,
+                   int format, tk_file_stats *stats);
 
 /* ---- misc ---------------------------------------------------------------------------- */
 

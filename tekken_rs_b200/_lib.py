@@ -19,6 +19,15 @@ class VocabEntry(ctypes.Structure):
     _fields_ = [("rank", ctypes.c_uint64), ("token_bytes_b64", ctypes.c_char_p)]
 
 
+class AudioConfig(ctypes.Structure):
+    _fields_ = [("sampling_rate", ctypes.c_uint64), ("frame_rate", ctypes.c_double), ("num_mel_bins", ctypes.c_uint64),
+                ("hop_length", ctypes.c_uint64), ("window_size", ctypes.c_uint64), ("chunk_length_s", ctypes.c_double)]
+
+
+class FileStats(ctypes.Structure):
+    _fields_ = [("n_docs", ctypes.c_uint64), ("n_bytes", ctypes.c_uint64), ("n_tokens", ctypes.c_uint64), ("seconds", ctypes.c_double)]
+
+
 class SpecialEntry(ctypes.Structure):
     _fields_ = [("rank", ctypes.c_uint64), ("token_str", ctypes.c_char_p), ("is_control", ctypes.c_int)]
 
@@ -67,6 +76,12 @@ PROTOTYPES = {
                                        ctypes.POINTER(c_vp), c_u64p]),
     "tk_decode_batch_device": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_int, c_vp,
                                               ctypes.c_uint64, c_vp, c_vp, c_u64p, c_u64p, c_vp]),
+    "tk_encode_file": (ctypes.c_int, [ctypes.POINTER(c_vp), ctypes.c_size_t, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                      ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(FileStats)]),
+    "tk_has_audio_support": (ctypes.c_int, [c_vp]),
+    "tk_audio_config_of": (ctypes.c_int, [c_vp, ctypes.POINTER(AudioConfig)]),
+    "tk_audio_token_count": (ctypes.c_int, [ctypes.POINTER(AudioConfig), ctypes.c_uint64, c_u64p, c_u64p]),
+    "tk_encode_audio_tokens": (ctypes.c_int, [c_vp, ctypes.c_uint64, ctypes.POINTER(c_vp), ctypes.POINTER(ctypes.c_size_t)]),
     "tk_shard_plan": (ctypes.c_int, [c_vp, ctypes.c_size_t, ctypes.c_size_t, c_vp]),
     "tk_buffer_free": (None, [c_vp]),
     "tk_last_error": (ctypes.c_char_p, []),

@@ -6,8 +6,13 @@
 // All arithmetic of the path runs in the kernels (tk_kernels.cu, tk_decode.cu); there is no CPU
 // implementation of encode or decode in this library.
 #include <cuda_runtime.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
+#include <cerrno>
 #include <atomic>
 #include <cstdarg>
 #include <cstdlib>
@@ -1542,6 +1547,210 @@ extern "C" int tk_decode_all(const tk_tokenizer* t, const uint32_t* ids, size_t 
     if (!ends.empty()) memcpy(pe, ends.data(), ends.size() * 8);
     *part_end = pe;
     *n_parts = ends.size();
+    return TK_OK;
+}
+
+// ------------------------------------------------------------------------------------------ streaming: text file in, id shards out
+//
+// the step either side of the path -- corpus bytes in, token shards out.  The text file is
+// memory-mapped (pageable memory: the engine stages it through pinned buffers with its copy threads), cut into
+// documents at a delimiter byte, and encoded window by window (about 1 GiB of text per window, whole documents)
+// with the host-buffer engine on all given devices; the ids of window i are written to the shard file by a writer
+// thread while window i + 1 is being encoded.  Memory stays bounded by two windows' results whatever the file size.
+
+namespace {
+
+struct OutFile {
+    int fd = -1;
+    bool npy = false;
+    char dtype = '4';
+    uint64_t count = 0;
+    static constexpr size_t kHeader = 128;
+    int open_for(const char* path, bool as_npy, char dt) {
+        fd = ::open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+        if (fd < 0) return fail(TK_ERR_IO, "cannot create %s: %s", path, strerror(errno));
+        npy = as_npy; dtype = dt;
+        if (npy) return write_header();           // placeholder: the element count is patched in by close()
+        return TK_OK;
+    }
+    int write_header() {
+        char h[kHeader];
+        memset(h, ' ', sizeof h);
+        memcpy(h, "\x93NUMPY\x01\x00", 8);
+        const uint16_t hl = kHeader - 10;
+        h[8] = (char)(hl & 0xFF); h[9] = (char)(hl >> 8);
+        char d[96];
+        const int n = snprintf(d, sizeof d, "{'descr': '<u%c', 'fortran_order': False, 'shape': (%llu,), }", dtype, (unsigned long long)count);
+        memcpy(h + 10, d, (size_t)n);
+        h[kHeader - 1] = '\n';
+        if (::pwrite(fd, h, kHeader, 0) != (ssize_t)kHeader) return fail(TK_ERR_IO, "write failed: %s", strerror(errno));
+        if (::lseek(fd, 0, SEEK_END) < (off_t)kHeader) ::lseek(fd, kHeader, SEEK_SET);
+        return TK_OK;
+    }
+    int append(const void* p, size_t bytes, size_t elems) {
+        const char* c = (const char*)p;
+        while (bytes) {
+            const ssize_t w = ::write(fd, c, std::min<size_t>(bytes, (size_t)1 << 30));
+            if (w < 0) { if (errno == EINTR) continue; return fail(TK_ERR_IO, "write failed: %s", strerror(errno)); }
+            c += w; bytes -= (size_t)w;
+        }
+        count += elems;
+        return TK_OK;
+    }
+    int close_file() {
+        int rc = TK_OK;
+        if (fd >= 0) {
+            if (npy) rc = write_header();
+            if (::close(fd) != 0 && rc == TK_OK) rc = fail(TK_ERR_IO, "close failed: %s", strerror(errno));
+            fd = -1;
+        }
+        return rc;
+    }
+    ~OutFile() { if (fd >= 0) ::close(fd); }
+};
+
+}  // namespace
+
+extern "C" int tk_encode_file(tk_tokenizer* const* handles, size_t n_handles, const char* text_path, int delimiter, int add_bos, int add_eos,
+                              const char* tokens_path, const char* offsets_path, int format, tk_file_stats* stats) {
+    if (!handles || n_handles == 0 || !text_path || !tokens_path) return fail(TK_ERR_INVALID_ARGUMENT, "null argument");
+    if (format != TK_SHARDS_RAW_U32 && format != TK_SHARDS_NPY) return fail(TK_ERR_INVALID_ARGUMENT, "unknown shard format %d", format);
+    if (delimiter < -1 || delimiter > 255) return fail(TK_ERR_INVALID_ARGUMENT, "delimiter must be a byte value or -1");
+    for (size_t g = 0; g < n_handles; ++g) {
+        int rc = check_encode_args(handles[g], add_bos, add_eos);
+        if (rc) return rc;
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    const int fd = ::open(text_path, O_RDONLY);
+    if (fd < 0) return fail(TK_ERR_IO, "cannot open %s: %s", text_path, strerror(errno));
+    struct stat sb;
+    if (fstat(fd, &sb) != 0) { ::close(fd); return fail(TK_ERR_IO, "cannot stat %s: %s", text_path, strerror(errno)); }
+    const uint64_t n = (uint64_t)sb.st_size;
+    const uint8_t* data = nullptr;
+    if (n) {
+        void* m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m == MAP_FAILED) { ::close(fd); return fail(TK_ERR_IO, "cannot map %s: %s", text_path, strerror(errno)); }
+        madvise(m, n, MADV_SEQUENTIAL);
+        data = (const uint8_t*)m;
+    }
+    ::close(fd);
+    struct Unmap { const uint8_t* p; uint64_t n; ~Unmap() { if (p) munmap((void*)p, n); } } unmap{data, n};
+    // documents: every document ends with (and includes) its delimiter; a last one without delimiter is kept
+    std::vector<uint64_t> off{0};
+    if (delimiter < 0) { if (n) off.push_back(n); }
+    else {
+        const uint8_t* p = data;
+        const uint8_t* end = data + n;
+        while (p < end) {
+            const uint8_t* q = (const uint8_t*)memchr(p, delimiter, (size_t)(end - p));
+            p = q ? q + 1 : end;
+            off.push_back((uint64_t)(p - data));
+        }
+    }
+    const size_t n_docs = off.size() - 1;
+    OutFile ftok, foff;
+    int rc = ftok.open_for(tokens_path, format == TK_SHARDS_NPY, '4');
+    if (rc) return rc;
+    if (offsets_path) { rc = foff.open_for(offsets_path, format == TK_SHARDS_NPY, '8'); if (rc) return rc; }
+    static const uint64_t kWindow = [] { const char* e = getenv("TEKKEN_B200_FILE_WINDOW_MB"); const long mb = e ? atol(e) : 0; return (uint64_t)(mb > 0 ? mb : 1024) << 20; }();
+    // writer thread state: the result of the previous window
+    std::thread writer;
+    int writer_rc = TK_OK;
+    std::string writer_err;
+    uint64_t tok_base = 0;
+    auto join_writer = [&]() -> int {
+        if (writer.joinable()) writer.join();
+        if (writer_rc) return fail(writer_rc, "%s", writer_err.c_str());
+        return TK_OK;
+    };
+    size_t a = 0;
+    std::vector<uint64_t> local;
+    while (a < n_docs || (n_docs == 0 && a == 0)) {
+        size_t b = a;
+        while (b < n_docs && (b == a || off[b + 1] - off[a] <= kWindow)) ++b;
+        local.resize(b - a + 1);
+        for (size_t d = a; d <= b; ++d) local[d - a] = off[d] - off[a];
+        uint32_t* ids = nullptr;
+        uint64_t* toff = nullptr;
+        rc = encode_batch_engine(handles, n_handles, data ? data + off[a] : nullptr, local.data(), b - a, add_bos, add_eos, &ids, &toff);
+        if (rc) { join_writer(); return rc; }
+        rc = join_writer();                      // the previous window is on disk (its buffers went back to the pool)
+        if (rc) { g_pool.put(ids); g_pool.put(toff); return rc; }
+        const uint64_t n_tok = toff[b - a], base = tok_base;
+        const size_t nd = b - a;
+        const bool last = b >= n_docs;
+        writer = std::thread([&, ids, toff, n_tok, base, nd, last] {
+            int r = ftok.append(ids, (size_t)n_tok * 4, (size_t)n_tok);
+            if (r == TK_OK && foff.fd >= 0) {
+                for (size_t d = 0; d <= nd; ++d) toff[d] += base;
+                r = foff.append(toff, (nd + (last ? 1 : 0)) * 8, nd + (last ? 1 : 0));      // the closing offset once, at the very end
+            }
+            if (r) { writer_rc = r; writer_err = g_last_error; }
+            g_pool.put(ids);
+            g_pool.put(toff);
+        });
+        tok_base += n_tok;
+        a = b;
+        if (n_docs == 0) break;
+    }
+    rc = join_writer();
+    if (rc) return rc;
+    rc = ftok.close_file();
+    if (rc == TK_OK) rc = foff.close_file();
+    if (rc) return rc;
+    if (stats) {
+        stats->n_docs = n_docs; stats->n_bytes = n; stats->n_tokens = tok_base;
+        stats->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
+    return TK_OK;
+}
+
+// ------------------------------------------------------------------------------------------ audio token counting
+
+// the text-side half of Tekkenizer::encode_audio (src/tekkenizer.rs:728-735 -> AudioEncoder::encode,
+// src/audio.rs:555-591): how many [AUDIO] ids a clip turns into.  O(1) integer / f64 arithmetic per clip on the host --
+// there is nothing for a GPU to do; resampling and the mel spectrogram are outside this library.
+extern "C" int tk_has_audio_support(const tk_tokenizer* t) { return t && t->host.audio.present; }
+
+extern "C" int tk_audio_config_of(const tk_tokenizer* t, tk_audio_config* out) {
+    if (!t || !out) return fail(TK_ERR_INVALID_ARGUMENT, "null argument");
+    const tk::AudioConfigData& a = t->host.audio;
+    if (!a.present) return fail(TK_ERR_AUDIO, "Audio encoder not configured");
+    out->sampling_rate = a.sampling_rate; out->frame_rate = a.frame_rate; out->num_mel_bins = a.num_mel_bins;
+    out->hop_length = a.hop_length; out->window_size = a.window_size; out->chunk_length_s = a.chunk_length_s;
+    return TK_OK;
+}
+
+extern "C" int tk_audio_token_count(const tk_audio_config* cfg, uint64_t n_samples, uint64_t* padded_samples, uint64_t* n_audio_tokens) {
+    if (!cfg || !n_audio_tokens) return fail(TK_ERR_INVALID_ARGUMENT, "null argument");
+    tk::AudioConfigData a;
+    a.present = true; a.sampling_rate = cfg->sampling_rate; a.frame_rate = cfg->frame_rate; a.num_mel_bins = cfg->num_mel_bins;
+    a.hop_length = cfg->hop_length; a.window_size = cfg->window_size; a.chunk_length_s = cfg->chunk_length_s;
+    uint64_t padded = 0;
+    try {
+        tk::audio_token_count(a, n_samples, &padded, n_audio_tokens);
+    } catch (const tk::Error& e) {
+        return fail(e.code, "%s", e.what());
+    }
+    if (padded_samples) *padded_samples = padded;
+    return TK_OK;
+}
+
+extern "C" int tk_encode_audio_tokens(const tk_tokenizer* t, uint64_t n_samples, uint32_t** out, size_t* n_out) {
+    if (!t || !out || !n_out) return fail(TK_ERR_INVALID_ARGUMENT, "null argument");
+    if (!t->host.audio.present) return fail(TK_ERR_AUDIO, "Audio encoder not configured");        // src/tekkenizer.rs:731-734
+    uint64_t padded = 0, n = 0;
+    try {
+        tk::audio_token_count(t->host.audio, n_samples, &padded, &n);
+    } catch (const tk::Error& e) {
+        return fail(e.code, "%s", e.what());
+    }
+    uint32_t* ids = (uint32_t*)g_pool.get((size_t)(n + 1) * 4, false);
+    if (!ids) return fail(TK_ERR_CUDA, "out of host memory");
+    ids[0] = t->host.begin_audio_token_id;                                                         // src/audio.rs:586-587
+    for (uint64_t i = 0; i < n; ++i) ids[1 + i] = t->host.audio_token_id;
+    *out = ids;
+    *n_out = (size_t)(n + 1);
     return TK_OK;
 }
 

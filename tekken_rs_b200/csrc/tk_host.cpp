@@ -11,6 +11,7 @@
 #include "tk_host.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <fstream>
 #include <sstream>
@@ -135,6 +136,15 @@ struct JsonReader {
         if (p < end && (*p == '.' || *p == 'e' || *p == 'E')) { p = s; fail("invalid type: floating point, expected usize"); }
         if (p - s > 1 && *s == '0') { p = s; fail("invalid number"); }
         return v;
+    }
+    // serde `f64`: any JSON number
+    double f64() {
+        ws();
+        const char* s = p;
+        if (p < end && *p == '-') ++p;
+        if (p >= end || *p < '0' || *p > '9') { p = s; fail("invalid type: expected f64"); }
+        while (p < end && ((*p >= '0' && *p <= '9') || *p == '.' || *p == 'e' || *p == 'E' || *p == '+' || *p == '-')) ++p;
+        return strtod(std::string(s, p).c_str(), nullptr);
     }
     bool boolean() {
         ws();
@@ -270,9 +280,37 @@ ModelData parse_tekken_json(const std::string& text) {
             if (!c_dvs) r.fail("missing field `default_vocab_size`");
             if (!c_dnst) r.fail("missing field `default_num_special_tokens`");
             if (!c_version) r.fail("missing field `version`");
+        } else if (key == "audio") {
+            // ModelData::audio: Option<AudioConfig> (src/config.rs:81, src/audio.rs:86-91).  Only the token COUNT of
+            // an audio clip is on this library's path; the waveform processing is not.
+            if (r.null()) { md.audio.present = false; return; }
+            md.audio = AudioConfigData{};
+            md.audio.present = true;
+            bool a_sr = false, a_fr = false, a_enc = false;
+            r.object([&](const std::string& k) {
+                if (k == "sampling_rate") { md.audio.sampling_rate = r.usize(); a_sr = true; }
+                else if (k == "frame_rate") { md.audio.frame_rate = r.f64(); a_fr = true; }
+                else if (k == "chunk_length_s") { if (r.null()) md.audio.chunk_length_s = -1.0; else md.audio.chunk_length_s = r.f64(); }
+                else if (k == "audio_encoding_config") {
+                    a_enc = true;
+                    bool e_m = false, e_h = false, e_w = false;
+                    r.object([&](const std::string& k2) {
+                        if (k2 == "num_mel_bins") { md.audio.num_mel_bins = r.usize(); e_m = true; }
+                        else if (k2 == "hop_length") { md.audio.hop_length = r.usize(); e_h = true; }
+                        else if (k2 == "window_size") { md.audio.window_size = r.usize(); e_w = true; }
+                        else r.skip_value();
+                    });
+                    if (!e_m) r.fail("missing field `num_mel_bins`");
+                    if (!e_h) r.fail("missing field `hop_length`");
+                    if (!e_w) r.fail("missing field `window_size`");
+                }
+                else r.skip_value();
+            });
+            if (!a_sr) r.fail("missing field `sampling_rate`");
+            if (!a_fr) r.fail("missing field `frame_rate`");
+            if (!a_enc) r.fail("missing field `audio_encoding_config`");
         } else {
-            // `audio` (src/audio.rs) is outside the text path; `image`/other keys are ignored by
-            // the reference's serde model too.
+            // `image` / other keys are ignored by the reference's serde model too
             r.skip_value();
         }
     });
@@ -729,7 +767,48 @@ HostModel HostModel::from_file(const std::string& path) {
     int version = parse_version(md.version);
     if (!version) throw Error(TK_ERR_INVALID_CONFIG, "Unknown version: " + md.version);
     const std::vector<SpecialEntry>& sp = md.has_special_tokens ? md.special_tokens : deprecated_special_tokens();
-    return build(md.vocab, sp, md.pattern, md.default_vocab_size, md.default_num_special_tokens, version);
+    HostModel m = build(md.vocab, sp, md.pattern, md.default_vocab_size, md.default_num_special_tokens, version);
+    m.set_audio(md.audio);
+    return m;
+}
+
+// Tekkenizer::new with Some(audio_config) (src/tekkenizer.rs:157-178): the audio special tokens must exist
+void HostModel::set_audio(const AudioConfigData& a) {
+    audio = a;
+    if (!a.present) return;
+    if (!has_control_token("[AUDIO]")) throw Error(TK_ERR_TOKEN_NOT_FOUND, "Audio token not found");
+    if (!has_control_token("[BEGIN_AUDIO]")) throw Error(TK_ERR_TOKEN_NOT_FOUND, "BeginAudio token not found");
+    audio_token_id = control_token("[AUDIO]");
+    begin_audio_token_id = control_token("[BEGIN_AUDIO]");
+}
+
+// The token count of AudioEncoder::encode (src/audio.rs:555-591) for a clip of n_samples samples at the configured
+// sampling rate: Audio::pad (:439-463), the spectrogram length (:563-578), ceil(length / audio_length_per_tok) (:584,
+// :188-199).  Same integer / f64 arithmetic as the reference.
+void audio_token_count(const AudioConfigData& c, uint64_t n_samples, uint64_t* padded, uint64_t* n_tokens) {
+    if (c.sampling_rate == 0) throw Error(TK_ERR_INVALID_CONFIG, "sampling_rate must be > 0");
+    if (!(c.frame_rate > 0.0)) throw Error(TK_ERR_INVALID_CONFIG, "frame_rate must be > 0");
+    if (c.hop_length == 0) throw Error(TK_ERR_INVALID_CONFIG, "hop_length must be > 0");
+    if (c.window_size == 0) throw Error(TK_ERR_INVALID_CONFIG, "window_size must be > 0");
+    uint64_t len = n_samples;
+    if (c.chunk_length_s > 0.0) {
+        const uint64_t chunk_frames = (uint64_t)(c.chunk_length_s * (double)c.sampling_rate);      // :157-175
+        if (chunk_frames == 0) throw Error(TK_ERR_INVALID_CONFIG, "chunk_length_s too small");
+        len = (len + chunk_frames - 1) / chunk_frames * chunk_frames;                                // div_ceil * chunk_frames
+    } else if (len < c.window_size) {
+        len = c.window_size;
+    }
+    *padded = len;
+    uint64_t sig;
+    if (len % c.hop_length != 0) {
+        const double v = std::ceil((double)len / (double)c.hop_length - 1.0);
+        sig = v <= 0.0 ? 0 : (uint64_t)v;                                                            // `as usize` saturates at 0
+    } else sig = len / c.hop_length;
+    double f = (double)c.sampling_rate / c.frame_rate;
+    f /= (double)c.hop_length;
+    const uint64_t per_tok = f <= 0.0 ? 0 : (uint64_t)f;                                             // audio_length_per_tok
+    if (per_tok == 0) throw Error(TK_ERR_INVALID_CONFIG, "frame_rate * hop_length exceeds sampling_rate: audio_length_per_tok is 0");
+    *n_tokens = (uint64_t)std::ceil((double)sig / (double)per_tok);
 }
 
 }  // namespace tk

@@ -28,6 +28,15 @@ struct SpecialEntry {
     bool is_control;
 };
 
+// AudioConfig + AudioSpectrogramConfig (src/audio.rs:18-22, 86-91), as far as token counting needs them
+struct AudioConfigData {
+    bool present = false;
+    uint64_t sampling_rate = 0;
+    double frame_rate = 0.0;
+    uint64_t num_mel_bins = 0, hop_length = 0, window_size = 0;
+    double chunk_length_s = -1.0;      // <= 0: None
+};
+
 // What Tekkenizer::from_file reads from the file (src/config.rs:73-82).
 struct ModelData {
     std::vector<VocabEntry> vocab;
@@ -38,6 +47,7 @@ struct ModelData {
     uint64_t default_vocab_size = 0;
     uint64_t default_num_special_tokens = 0;
     std::string version;
+    AudioConfigData audio;
 };
 
 ModelData parse_tekken_json(const std::string& text);           // throws Error(TK_ERR_JSON)
@@ -57,6 +67,9 @@ struct HostModel {
     std::vector<std::string> vocab_strings;                   // vocab() (:141-155), lossy UTF-8
     uint32_t max_token_len = 0;
     std::string pattern;                                      // config.pattern as given (ignored by the reference, :74)
+    AudioConfigData audio;                                    // :42 audio_config
+    uint32_t audio_token_id = 0, begin_audio_token_id = 0;    // :158-175 (valid when audio.present)
+    void set_audio(const AudioConfigData& a);                 // throws TokenNotFound like Tekkenizer::new(.., Some(cfg))
 
     // device table images
     std::vector<uint16_t> uni_stage1;
@@ -85,6 +98,7 @@ struct HostModel {
     static HostModel from_file(const std::string& path);
 };
 
+void audio_token_count(const AudioConfigData& c, uint64_t n_samples, uint64_t* padded, uint64_t* n_tokens);   // src/audio.rs:555-584
 void build_unicode_tables(std::vector<uint16_t>& stage1, std::vector<uint8_t>& stage2);
 void build_cfg_unicode_tables(std::vector<uint16_t>& stage1, std::vector<uint8_t>& stage2);   // TK_SPLIT_CONFIG, see tk_pretok_cfg.h
 const char* tekken_config_pattern();                          // the stored pattern the TK_SPLIT_CONFIG kernels implement

@@ -297,6 +297,23 @@ class Tekkenizer:
                                                 d_out, capacity, d_byte_off, d_status, ctypes.byref(n), ctypes.byref(bad), stream))
         return n.value
 
+    # ---- audio token counting (src/audio.rs:555-591, src/tekkenizer.rs:728-760) ----------------------
+    def has_audio_support(self) -> bool:
+        return bool(self._lib.tk_has_audio_support(self._h))
+
+    def audio_config(self) -> Optional[dict]:
+        c = _lib.AudioConfig()
+        if self._lib.tk_audio_config_of(self._h, ctypes.byref(c)) != 0:
+            return None
+        return {"sampling_rate": c.sampling_rate, "frame_rate": c.frame_rate, "chunk_length_s": c.chunk_length_s if c.chunk_length_s > 0 else None,
+                "audio_encoding_config": {"num_mel_bins": c.num_mel_bins, "hop_length": c.hop_length, "window_size": c.window_size}}
+
+    def encode_audio_tokens(self, n_samples: int) -> List[int]:
+        """AudioEncoding.tokens for a clip of n_samples samples at the configured sampling rate."""
+        out, n = ctypes.c_void_p(), ctypes.c_size_t()
+        _check(self._lib.tk_encode_audio_tokens(self._h, int(n_samples), ctypes.byref(out), ctypes.byref(n)))
+        return _take(out.value, n.value * 4, np.uint32).tolist()
+
     # ---- instrumentation ----------------------------------------------------------------------
     def set_stage_timing(self, enabled: bool):
         self._lib.tk_set_stage_timing(self._h, int(enabled))
@@ -342,9 +359,31 @@ def encode_batch_multi(tokenizers: Sequence["Tekkenizer"], data, doc_off, add_bo
     return _take(tok.value, int(tok_off[-1]) * 4, np.uint32), tok_off
 
 
+def encode_file(tokenizers: Sequence["Tekkenizer"], text_path: str, tokens_path: str, offsets_path: Optional[str] = None,
+                delimiter: Optional[int] = 10, add_bos: bool = True, add_eos: bool = True, npy: bool = False) -> dict:
+    """Text file -> shard of u32 ids (+ u64 token offsets), streamed through the GPU(s) window by window."""
+    lib = _lib.load()
+    arr = (ctypes.c_void_p * len(tokenizers))(*[t._h for t in tokenizers])
+    st = _lib.FileStats()
+    _check(lib.tk_encode_file(arr, len(tokenizers), str(text_path).encode(), -1 if delimiter is None else int(delimiter), int(add_bos), int(add_eos),
+                              str(tokens_path).encode(), str(offsets_path).encode() if offsets_path else None, 1 if npy else 0, ctypes.byref(st)))
+    return {"n_docs": st.n_docs, "n_bytes": st.n_bytes, "n_tokens": st.n_tokens, "seconds": st.seconds}
+
+
 def set_chunk_bytes(n: int):
     """Tuning knob: chunk size of the host-buffer calls (0 = default 48 MB)."""
     _lib.load().tk_set_chunk_bytes(int(n))
+
+
+def audio_token_count(cfg: dict, n_samples: int):
+    """(padded samples, number of [AUDIO] ids) for a clip under an AudioConfig given as the tekken.json `audio` dict."""
+    lib = _lib.load()
+    e = cfg["audio_encoding_config"]
+    c = _lib.AudioConfig(int(cfg["sampling_rate"]), float(cfg["frame_rate"]), int(e["num_mel_bins"]), int(e["hop_length"]), int(e["window_size"]),
+                         float(cfg["chunk_length_s"]) if cfg.get("chunk_length_s") else -1.0)
+    p, n = ctypes.c_uint64(), ctypes.c_uint64()
+    _check(lib.tk_audio_token_count(ctypes.byref(c), int(n_samples), ctypes.byref(p), ctypes.byref(n)))
+    return p.value, n.value
 
 
 def kernel_launch_count() -> int:

@@ -188,6 +188,36 @@ def test_host_engine_chunks_slices_and_devices(gpu_tok, oracle, tekken_json):
             t.close()
 
 
+def test_encode_file_streams_shards(gpu_tok, oracle, tmp_path, monkeypatch):
+    # text file in, u32 id shard + u64 offsets out, window by window (1 MiB windows here), raw and .npy
+    import os
+    from tekken_rs_b200 import encode_file
+    monkeypatch.setenv("TEKKEN_B200_FILE_WINDOW_MB", "1")
+    data, off = corpus.mixed_script_docs(6000, 11)
+    lines = [bytes(data[int(off[i]):int(off[i + 1])]).replace(b"\n", b" ").replace(b"\r", b" ") + b"\n" for i in range(6000)]
+    lines.append(b"last line without a newline")
+    text = b"".join(lines)
+    src = tmp_path / "corpus.txt"
+    src.write_bytes(text)
+    ldata, loff = _pack(lines)
+    want, woff = oracle.encode_batch_np(ldata, loff, True, True, n_threads=8)
+    st = encode_file([gpu_tok], str(src), str(tmp_path / "ids.bin"), str(tmp_path / "ids.idx"), delimiter=10)
+    assert st["n_docs"] == len(lines) and st["n_bytes"] == len(text) and st["n_tokens"] == len(want)
+    assert np.array_equal(np.fromfile(tmp_path / "ids.bin", dtype=np.uint32), want)
+    assert np.array_equal(np.fromfile(tmp_path / "ids.idx", dtype=np.uint64), woff)
+    st = encode_file([gpu_tok], str(src), str(tmp_path / "ids.npy"), str(tmp_path / "off.npy"), delimiter=10, npy=True)
+    assert np.array_equal(np.load(tmp_path / "ids.npy"), want) and np.array_equal(np.load(tmp_path / "off.npy"), woff)
+    # the whole file as one document, no offsets file; an empty file
+    st = encode_file([gpu_tok], str(src), str(tmp_path / "one.bin"), None, delimiter=None, add_bos=False, add_eos=False)
+    assert np.fromfile(tmp_path / "one.bin", dtype=np.uint32).tolist() == oracle.encode(text, False, False) and st["n_docs"] == 1
+    (tmp_path / "empty.txt").write_bytes(b"")
+    st = encode_file([gpu_tok], str(tmp_path / "empty.txt"), str(tmp_path / "e.bin"), str(tmp_path / "e.idx"))
+    assert st["n_tokens"] == 0 and os.path.getsize(tmp_path / "e.bin") == 0 and np.fromfile(tmp_path / "e.idx", dtype=np.uint64).tolist() == [0]
+    with pytest.raises(TokenizerError) as e:
+        encode_file([gpu_tok], str(tmp_path / "missing.txt"), str(tmp_path / "x.bin"))
+    assert e.value.kind == "Io"
+
+
 # ------------------------------------------------------------------------------------------ differential fuzz
 
 def _fuzz_texts(n, seed, lengths):

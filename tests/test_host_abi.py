@@ -181,3 +181,50 @@ def test_status_names():
     p = ctypes.POINTER(_lib.SpecialEntry)()
     n = lib.tk_deprecated_special_tokens(ctypes.byref(p))
     assert n == 20 and p[1].token_str == b"<s>" and p[19].token_str == b"[TOOL_CONTENT]"
+
+
+def test_audio_token_counting(host_tok, tekken_json):
+    # AudioEncoder::encode's token count (src/audio.rs:555-591) -- host arithmetic, no GPU involved
+    import json
+    import random
+    from oracle import tekken_oracle as TO
+    from tekken_rs_b200 import audio_token_count
+    cfg = json.load(open(tekken_json))["audio"]
+    assert host_tok.has_audio_support() and host_tok.audio_config() == cfg
+    # by hand: 16 kHz, 12.5 frames/s, hop 160, chunks of 30 s = 480,000 samples -> 3,000 frames / 8 per token = 375
+    assert audio_token_count(cfg, 16000) == (480000, 375)
+    assert audio_token_count(cfg, 480001) == (960000, 750)
+    assert audio_token_count(cfg, 0) == (0, 0)
+    toks = host_tok.encode_audio_tokens(16000)
+    assert toks[0] == host_tok.get_control_token("[BEGIN_AUDIO]") and toks[1:] == [host_tok.get_control_token("[AUDIO]")] * 375
+    # no chunking: short clips are padded to the window; lengths that are not a multiple of the hop lose a frame
+    nochunk = dict(cfg, chunk_length_s=None)
+    assert audio_token_count(nochunk, 100) == (400, 1)          # 400 / 160 = 2.5 -> ceil(1.5) = 2 frames -> ceil(2 / 8) = 1
+    assert audio_token_count(nochunk, 16000) == (16000, 13)     # 100 frames -> ceil(12.5)
+    assert audio_token_count(nochunk, 16001) == (16001, 13)     # ceil(100.006 - 1) = 100 frames
+    rng = random.Random(3)
+    for _ in range(3000):
+        c = {"sampling_rate": rng.choice([8000, 16000, 22050, 44100, 48000]), "frame_rate": rng.choice([12.5, 25.0, 50.0, 7.5, 100.0]),
+             "chunk_length_s": rng.choice([None, None, 30.0, 0.5, 10.25]),
+             "audio_encoding_config": {"num_mel_bins": 128, "hop_length": rng.choice([128, 160, 200, 256]), "window_size": rng.choice([400, 512, 1024])}}
+        if int(c["sampling_rate"] / c["frame_rate"] / c["audio_encoding_config"]["hop_length"]) == 0:
+            continue
+        n = rng.choice([0, 1, 399, 400, 401, rng.randrange(1, 10**7)])
+        assert audio_token_count(c, n) == TO.audio_token_count(c, n), (c, n)
+    # a file without an `audio` block: Audio error, as src/tekkenizer.rs:731-734; with one but without the tokens: TokenNotFound (:158-170)
+    src = json.load(open(tekken_json))
+    import os
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        a = dict(src); a.pop("audio")
+        p = os.path.join(d, "noaudio.json"); json.dump(a, open(p, "w"))
+        t = Tekkenizer.from_file(p, device=-1)
+        assert not t.has_audio_support() and t.audio_config() is None
+        with pytest.raises(TokenizerError) as e:
+            t.encode_audio_tokens(16000)
+        assert e.value.kind == "Audio"
+        b = dict(src); b["special_tokens"] = [x for x in src["special_tokens"] if x["token_str"] != "[AUDIO]"]
+        p = os.path.join(d, "notoken.json"); json.dump(b, open(p, "w"))
+        with pytest.raises(TokenizerError) as e:
+            Tekkenizer.from_file(p, device=-1)
+        assert e.value.kind == "TokenNotFound"
