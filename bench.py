@@ -416,10 +416,10 @@ def run_ours(args):
         lib.tk_buffer_free(tok)
         return last, first
 
-    e2e_steps = max(1, min(args.steps, 10))
-    for _ in range(2):
+    e2e_steps = max(1, min(args.steps, 10)) if not args.no_e2e else 1
+    for _ in range(2 if not args.no_e2e else 0):
         n_e2e, first = step_host()
-    assert n_e2e == n_tokens and first == 1, (n_e2e, n_tokens, first)
+        assert n_e2e == n_tokens and first == 1, (n_e2e, n_tokens, first)
     cx.barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -432,7 +432,9 @@ def run_ours(args):
            "d2h_bytes_per_step": int(4 * n_tokens + 8 * (n_docs + 1)), "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
            "tokens_per_s": total_tokens * e2e_steps / e2e_s,
            "api": "tk_encode (one text, pinned host in, host ids out)" if wl.single_doc else "tk_encode_batch (pinned host text in, pinned host ids out)"}
-    if not wl.single_doc and not args.quick:
+    if args.no_e2e:
+        e2e["note"] = "--no-e2e (profiling run): one unwarmed call, not a measurement"
+    if not wl.single_doc and not args.quick and not args.no_e2e:
         # the same call on PAGEABLE caller memory (what a Rust &str / Vec<u8> is): the library stages it itself
         pg = np.empty(n_bytes + 64, dtype=np.uint8)
         pg[:n_bytes] = h_view
@@ -804,6 +806,7 @@ def main():
     ap.add_argument("--shards", type=int, default=64, help="roundtrip64g: shards of 2^20 documents in all")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--quick", action="store_true", help="skip the pageable-input and one-call-all-GPUs legs")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs: a single host-buffer call instead of the timed e2e loop")
     ap.add_argument("--latency", action="store_true", help="add the single-string latency table (13 B .. 1 MiB)")
     ap.add_argument("--split", default="reference", choices=["reference", "config"],
                     help="reference = the pattern the reference hard-codes (the bench line); config = the pattern stored in tekken.json (SURVEY 8f-1)")

@@ -238,7 +238,7 @@ void tk_buffer_free(void *p);
 const char *tk_last_error(void);
 const char *tk_status_name(int status);
 /* Tuning knob of the host-buffer calls: size of the chunks a batch is streamed through the device in (process-wide;
-   0 restores the default of 48 MB, also settable with TEKKEN_B200_CHUNK_MB).  The tests use it to exercise the
+   0 restores the default of 128 MB, also settable with TEKKEN_B200_CHUNK_MB).  The tests use it to exercise the
    chunk-boundary and document-slicing logic on small inputs. */
 void tk_set_chunk_bytes(uint64_t bytes);
 /* Kernel launches issued by this process so far (for benchmark accounting). */

@@ -24,8 +24,20 @@ struct TkCfgTables {
     const uint8_t* stage2;
 };
 
+// ASCII without the table (the matcher walks character by character: two dependent table loads per ASCII
+// character were most of its time).  \s in ASCII is 9..13 and 32; tests/test_cfgsplit_model.py checks this
+// function against the table for all 128 values.
+TK_HD uint32_t tk_cfg_class_ascii(uint32_t c) {
+    if (c - 0x61u < 26u) return TK_CC_LO;
+    if (c - 0x41u < 26u) return TK_CC_U;
+    if (c - 0x30u < 10u) return TK_CC_N;
+    if (c == 0x0Au || c == 0x0Du) return TK_CC_R;
+    if (c == 0x20u || c - 9u < 5u) return TK_CC_W;
+    return TK_CC_O;
+}
+
 TK_HD uint32_t tk_cfg_class(const TkCfgTables& T, uint32_t cp) {
-    if (cp == 0x0Au || cp == 0x0Du) return TK_CC_R;
+    if (cp < 0x80u) return tk_cfg_class_ascii(cp);
     const uint32_t blk = T.stage1[cp >> 7];
     const uint32_t b = T.stage2[blk * 64u + ((cp & 127u) >> 1)];
     return (b >> ((cp & 1u) * 4u)) & 15u;
@@ -302,6 +314,48 @@ TK_HD uint32_t tk_cfg_safe_mask(const TkCfgWin& p, const TkCfgWin& c) {
     const uint32_t P_letter = tk_shl(c.mU | c.mLO | c.mC, p.mU | p.mLO | p.mC, 1);
     const uint32_t mO = ~(c.mU | c.mLO | c.mC | c.mM | c.mN | c.mW | c.mR);
     return c.lead & (c.ds | c.mN | P_N | (c.mW & ~(P_W | P_R)) | (mO & P_letter));
+}
+
+// The text as a kernel's walk sees it: a shared-memory copy of the tile around the walk's start (zero outside the
+// text), the text itself beyond it (a walk is as long as the distance to the next safe start: usually a word).
+struct TkBytesTileOrGlobal {
+    const uint8_t* sm;        // sm[pos - origin] for lo <= pos < hi
+    int64_t origin, lo, hi;
+    const uint8_t* data;
+    uint64_t n;
+    TK_HD uint32_t at(int64_t pos) const {
+        if (pos >= lo && pos < hi) return (uint32_t)sm[pos - origin];
+        return (pos >= 0 && (uint64_t)pos < n) ? (uint32_t)data[pos] : 0u;
+    }
+    TK_HD bool past_end(int64_t end) const { return (uint64_t)end > n; }
+};
+// a bitmask (document starts, safe starts) with the words [w_lo, w_hi) staged in shared memory
+struct TkMaskTileOrGlobal {
+    const uint32_t* sm;       // sm[w - w_lo]
+    int64_t w_lo, w_hi;
+    const uint32_t* g;
+    TK_HD uint32_t bit(int64_t pos) const {
+        const int64_t w = pos >> 5;
+        const uint32_t m = (w >= w_lo && w < w_hi) ? sm[w - w_lo] : g[w];
+        return (m >> (pos & 31)) & 1u;
+    }
+};
+struct TkCfgEndMaskTile {
+    TkMaskTileOrGlobal ds;
+    int64_t n, own_start;
+    TK_HD bool at_end(int64_t pos) const { return pos >= n || (pos > own_start && ds.bit(pos)); }
+};
+
+// The walk in its general form: `stop` says where the document ends, `is_safe(pos)` whether pos is a safe start.
+template <class B, class E, class S, class F>
+TK_HD void tk_cfg_walk_from(const B& src, int64_t q0, const S& is_safe, const E& stop, int64_t n, const TkCfgTables& T, F set_bit) {
+    int64_t q = q0;
+    for (;;) {
+        const int64_t e = tk_cfg_match_end(src, q, stop, T);
+        if (e >= n || is_safe(e)) return;                                   // the next segment's lane takes over
+        set_bit(e);
+        q = e;
+    }
 }
 
 // What one lane of the walk kernel does for one safe start at byte q0: run the matcher from piece to piece and mark

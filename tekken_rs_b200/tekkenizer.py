@@ -371,7 +371,7 @@ def encode_file(tokenizers: Sequence["Tekkenizer"], text_path: str, tokens_path:
 
 
 def set_chunk_bytes(n: int):
-    """Tuning knob: chunk size of the host-buffer calls (0 = default 48 MB)."""
+    """Tuning knob: chunk size of the host-buffer calls (0 = default 128 MB)."""
     _lib.load().tk_set_chunk_bytes(int(n))
 
 

@@ -22,6 +22,13 @@ extern "C" int64_t cfgsplit_use_library_tables(const uint8_t* cls_flat) {
     int64_t diff = 0;
     for (uint32_t c = 0; c < 0x110000u; ++c)
         if (c != 0x0A && c != 0x0D && tk_cfg_class(T, c) != cls_flat[c]) ++diff;
+    // the table-free ASCII classes must be the table's
+    for (uint32_t c = 0; c < 0x80u; ++c) {
+        if (c == 0x0A || c == 0x0D) { if (tk_cfg_class_ascii(c) != TK_CC_R) ++diff; continue; }
+        const uint32_t blk = T.stage1[c >> 7];
+        const uint32_t b = T.stage2[blk * 64u + ((c & 127u) >> 1)];
+        if (((b >> ((c & 1u) * 4u)) & 15u) != tk_cfg_class_ascii(c)) ++diff;
+    }
     return diff;
 }
 
