@@ -108,9 +108,11 @@ struct HostPool {
         void* p = nullptr;
         // capacities come in steps of 1/8 of the size's power of two, so that the slightly different result sizes of
         // successive batches of one corpus reuse each other's buffers instead of pinning a new 2 GB every call
+        // (plus a tenth of headroom when a new buffer has to be pinned: estimates of one corpus scatter by a few per cent)
         size_t step = 4096;
         while (step * 16 <= bytes) step <<= 1;
-        size_t cap = (bytes + step - 1) / step * step;
+        const size_t want = bytes >= ((size_t)64 << 20) ? bytes + bytes / 10 : bytes;
+        size_t cap = (want + step - 1) / step * step;
         if (cudaHostAlloc(&p, cap, cudaHostAllocPortable) != cudaSuccess) {
             cudaGetLastError();
             // no CUDA context (host-only handle): plain memory
@@ -222,6 +224,17 @@ struct tk_tokenizer {
     };
     static constexpr int kSlots = 4;
     EncSlot slot[kSlots];          // host-buffer encode: chunks of a batch pipeline through these
+    // ids of a chunk wait here for their download.  There are more of these than of the slots above: the download
+    // engine is the slowest stage of a large call (4 bytes come back per id), and with as many id buffers as text
+    // buffers the kernels -- and behind them the uploads -- were paced by it for the whole call, so uploads and
+    // downloads shared the bus from start to end.  With the kernels free to run ahead the text is up after half the
+    // call and the ids have the bus to themselves for the rest.
+    struct OutSlot {
+        DevBuf tok, off;
+        cudaEvent_t ev_out = nullptr;      // the slot's ids have left
+    };
+    static constexpr int kOutSlots = 12;
+    OutSlot oslot[kOutSlots];
     struct DecSlot {
         DevBuf ids, off, out, boff, status, ws;
         uint32_t* h_small = nullptr;
@@ -446,6 +459,10 @@ extern "C" void tk_free(tk_tokenizer* t) {
         }
         for (auto& ps : t->pipe_st) if (ps) { cudaStreamSynchronize(ps); cudaStreamDestroy(ps); }
         for (auto& sl : t->slot) drop(sl);
+        for (auto& o : t->oslot) {
+            o.tok.release(); o.off.release();
+            if (o.ev_out) cudaEventDestroy(o.ev_out);
+        }
         for (auto& d : t->dslot) {
             d.ids.release(); d.off.release(); d.out.release(); d.boff.release(); d.status.release(); d.ws.release();
             if (d.h_small) cudaFreeHost(d.h_small);
@@ -889,23 +906,25 @@ static int encode_worker(tk_tokenizer* t, EncodeJob& J, size_t g, size_t stride)
     auto eos_of = [&](const Chunk& c) { return J.add_eos && c.last ? 1 : 0; };
     auto launch = [&](size_t i) -> int {      // the kernels of my i-th chunk (its text is on the device or on its way)
         tk_tokenizer::EncSlot& s = t->slot[i % tk_tokenizer::kSlots];
+        tk_tokenizer::OutSlot& o = t->oslot[i % tk_tokenizer::kOutSlots];
         const Chunk& c = J.chunks[mine[i]];
         return encode_issue(t, s, (const uint8_t*)s.in_data.p, (const uint64_t*)s.in_off.p, c.partial ? 0 : c.byte_begin, c.n_docs, c.n_bytes,
-                            bos_of(c), eos_of(c), (uint32_t*)s.out_tok.p, caps(c), (uint64_t*)s.out_off.p, st_k, false);
+                            bos_of(c), eos_of(c), (uint32_t*)o.tok.p, caps(c), (uint64_t*)o.off.p, st_k, false);
     };
     auto issue = [&](size_t i) -> int {
         tk_tokenizer::EncSlot& s = t->slot[i % tk_tokenizer::kSlots];
+        tk_tokenizer::OutSlot& o = t->oslot[i % tk_tokenizer::kOutSlots];
         const Chunk& c = J.chunks[mine[i]];
-        if (!s.ev_in) {
-            CUDA_OR_FAIL(cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
-            CUDA_OR_FAIL(cudaEventCreateWithFlags(&s.ev_out, cudaEventDisableTiming));
-        }
+        if (!s.ev_in) CUDA_OR_FAIL(cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
+        if (!o.ev_out) CUDA_OR_FAIL(cudaEventCreateWithFlags(&o.ev_out, cudaEventDisableTiming));
         if (kTrace) thost[1 + i * 3] = host_now();
         const size_t off_bytes = (c.n_docs + 1) * 8;
         CUDA_OR_FAIL(s.in_data.ensure(c.n_bytes + 64));
         CUDA_OR_FAIL(s.in_off.ensure(off_bytes));
-        CUDA_OR_FAIL(s.out_tok.ensure(caps(c) * 4));
-        CUDA_OR_FAIL(s.out_off.ensure(off_bytes));
+        if (i >= (size_t)tk_tokenizer::kOutSlots && (o.tok.cap < caps(c) * 4 || o.off.cap < off_bytes))
+            CUDA_OR_FAIL(cudaEventSynchronize(o.ev_out));      // about to reallocate a buffer whose ids may still be leaving
+        CUDA_OR_FAIL(o.tok.ensure(caps(c) * 4));
+        CUDA_OR_FAIL(o.off.ensure(off_bytes));
         const uint8_t* src = J.data + c.byte_begin;
         const uint64_t* src_off = J.doc_off + c.doc_begin;
         if (J.pageable || c.partial) {
@@ -934,7 +953,7 @@ static int encode_worker(tk_tokenizer* t, EncodeJob& J, size_t g, size_t stride)
         mark(i, 1, st_up);
         CUDA_OR_FAIL(cudaEventRecord(s.ev_in, st_up));
         CUDA_OR_FAIL(cudaStreamWaitEvent(st_k, s.ev_in, 0));
-        if (i >= (size_t)tk_tokenizer::kSlots) CUDA_OR_FAIL(cudaStreamWaitEvent(st_k, s.ev_out, 0));
+        if (i >= (size_t)tk_tokenizer::kOutSlots) CUDA_OR_FAIL(cudaStreamWaitEvent(st_k, o.ev_out, 0));
         mark(i, 2, st_k);
         const int r = launch(i);
         mark(i, 3, st_k);
@@ -999,11 +1018,12 @@ static int encode_worker(tk_tokenizer* t, EncodeJob& J, size_t g, size_t stride)
         cudaError_t e = cudaSuccess;
         if (kTrace) thost[3 + i * 3] = host_now();
         mark(i, 4, st_down);
-        if (n_tok) e = cudaMemcpyAsync(J.h_tok + my_prefix, s.out_tok.p, n_tok * 4, cudaMemcpyDeviceToHost, st_down);
+        tk_tokenizer::OutSlot& o = t->oslot[i % tk_tokenizer::kOutSlots];
+        if (n_tok) e = cudaMemcpyAsync(J.h_tok + my_prefix, o.tok.p, n_tok * 4, cudaMemcpyDeviceToHost, st_down);
         if (e == cudaSuccess && !c.partial && c.n_docs)
-            e = cudaMemcpyAsync(J.h_off + c.doc_begin, s.out_off.p, c.n_docs * 8, cudaMemcpyDeviceToHost, st_down);
+            e = cudaMemcpyAsync(J.h_off + c.doc_begin, o.off.p, c.n_docs * 8, cudaMemcpyDeviceToHost, st_down);
         mark(i, 5, st_down);
-        if (e == cudaSuccess) e = cudaEventRecord(s.ev_out, st_down);
+        if (e == cudaSuccess) e = cudaEventRecord(o.ev_out, st_down);
         if (e != cudaSuccess) return bail(fail(TK_ERR_CUDA, "copying ids back: %s", cudaGetErrorString(e)));
         if (i + kAhead < n_mine) { rc = issue(i + kAhead); if (rc) return bail(rc); }
     }
