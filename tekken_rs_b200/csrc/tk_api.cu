@@ -911,22 +911,23 @@ static int encode_worker(tk_tokenizer* t, EncodeJob& J, size_t g, size_t stride)
         return encode_issue(t, s, (const uint8_t*)s.in_data.p, (const uint64_t*)s.in_off.p, c.partial ? 0 : c.byte_begin, c.n_docs, c.n_bytes,
                             bos_of(c), eos_of(c), (uint32_t*)o.tok.p, caps(c), (uint64_t*)o.off.p, st_k, false);
     };
-    auto issue = [&](size_t i) -> int {
+    // upload(i): the text and offsets of my i-th chunk on their way to the device (staged through pinned memory when
+    // the caller's memory is pageable, 16 MB at a time so that the copy of one piece overlaps the staging of the next).
+    // kick(i): its kernels queued behind the upload.  With pageable input a stager thread runs the uploads ahead of
+    // this thread, which then only queues kernels, waits for results and starts downloads.
+    std::vector<std::atomic<int>> up_state(n_mine), kicked(n_mine);
+    for (size_t i = 0; i < n_mine; ++i) { up_state[i].store(0); kicked[i].store(0); }
+    auto upload = [&](size_t i) -> int {
         tk_tokenizer::EncSlot& s = t->slot[i % tk_tokenizer::kSlots];
-        tk_tokenizer::OutSlot& o = t->oslot[i % tk_tokenizer::kOutSlots];
         const Chunk& c = J.chunks[mine[i]];
         if (!s.ev_in) CUDA_OR_FAIL(cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
-        if (!o.ev_out) CUDA_OR_FAIL(cudaEventCreateWithFlags(&o.ev_out, cudaEventDisableTiming));
         if (kTrace) thost[1 + i * 3] = host_now();
         const size_t off_bytes = (c.n_docs + 1) * 8;
         CUDA_OR_FAIL(s.in_data.ensure(c.n_bytes + 64));
         CUDA_OR_FAIL(s.in_off.ensure(off_bytes));
-        if (i >= (size_t)tk_tokenizer::kOutSlots && (o.tok.cap < caps(c) * 4 || o.off.cap < off_bytes))
-            CUDA_OR_FAIL(cudaEventSynchronize(o.ev_out));      // about to reallocate a buffer whose ids may still be leaving
-        CUDA_OR_FAIL(o.tok.ensure(caps(c) * 4));
-        CUDA_OR_FAIL(o.off.ensure(off_bytes));
         const uint8_t* src = J.data + c.byte_begin;
         const uint64_t* src_off = J.doc_off + c.doc_begin;
+        uint8_t* sd = nullptr;
         if (J.pageable || c.partial) {
             // pinned staging: [offsets | text]; the previous upload from it has long finished (kSlots chunks ago), but say so
             const size_t need = ((off_bytes + 63) & ~(size_t)63) + (J.pageable ? c.n_bytes : 0) + 64;
@@ -940,25 +941,78 @@ static int encode_worker(tk_tokenizer* t, EncodeJob& J, size_t g, size_t stride)
             if (c.partial) { so[0] = 0; so[1] = c.n_bytes; }
             else memcpy(so, src_off, off_bytes);
             src_off = so;
-            if (J.pageable) {
-                uint8_t* sd = s.h_stage + ((off_bytes + 63) & ~(size_t)63);
-                CopyPool::get().parallel_memcpy(sd, src, c.n_bytes);
-                src = sd;
-            }
+            if (J.pageable) sd = s.h_stage + ((off_bytes + 63) & ~(size_t)63);
         }
         if (i >= (size_t)tk_tokenizer::kSlots) CUDA_OR_FAIL(cudaStreamWaitEvent(st_up, s.done, 0));
         mark(i, 0, st_up);
-        if (c.n_bytes) CUDA_OR_FAIL(cudaMemcpyAsync(s.in_data.p, src, c.n_bytes, cudaMemcpyHostToDevice, st_up));
+        if (sd) {
+            constexpr uint64_t kPiece = 16u << 20;
+            for (uint64_t o = 0; o < c.n_bytes; o += kPiece) {
+                const uint64_t len = std::min<uint64_t>(kPiece, c.n_bytes - o);
+                CopyPool::get().parallel_memcpy(sd + o, src + o, len);
+                CUDA_OR_FAIL(cudaMemcpyAsync((uint8_t*)s.in_data.p + o, sd + o, len, cudaMemcpyHostToDevice, st_up));
+            }
+        } else if (c.n_bytes) CUDA_OR_FAIL(cudaMemcpyAsync(s.in_data.p, src, c.n_bytes, cudaMemcpyHostToDevice, st_up));
         CUDA_OR_FAIL(cudaMemcpyAsync(s.in_off.p, src_off, off_bytes, cudaMemcpyHostToDevice, st_up));
         mark(i, 1, st_up);
         CUDA_OR_FAIL(cudaEventRecord(s.ev_in, st_up));
+        return TK_OK;
+    };
+    auto kick = [&](size_t i) -> int {
+        tk_tokenizer::EncSlot& s = t->slot[i % tk_tokenizer::kSlots];
+        tk_tokenizer::OutSlot& o = t->oslot[i % tk_tokenizer::kOutSlots];
+        const Chunk& c = J.chunks[mine[i]];
+        const size_t off_bytes = (c.n_docs + 1) * 8;
+        if (!o.ev_out) CUDA_OR_FAIL(cudaEventCreateWithFlags(&o.ev_out, cudaEventDisableTiming));
+        if (i >= (size_t)tk_tokenizer::kOutSlots && (o.tok.cap < caps(c) * 4 || o.off.cap < off_bytes))
+            CUDA_OR_FAIL(cudaEventSynchronize(o.ev_out));      // about to reallocate a buffer whose ids may still be leaving
+        CUDA_OR_FAIL(o.tok.ensure(caps(c) * 4));
+        CUDA_OR_FAIL(o.off.ensure(off_bytes));
         CUDA_OR_FAIL(cudaStreamWaitEvent(st_k, s.ev_in, 0));
         if (i >= (size_t)tk_tokenizer::kOutSlots) CUDA_OR_FAIL(cudaStreamWaitEvent(st_k, o.ev_out, 0));
         mark(i, 2, st_k);
         const int r = launch(i);
         mark(i, 3, st_k);
         if (kTrace) thost[2 + i * 3] = host_now();
+        kicked[i].store(1, std::memory_order_release);
         return r;
+    };
+    // the stager (pageable input only): uploads in order, at most kSlots chunks ahead of the kernels
+    std::thread stager;
+    struct StagerJoin {
+        std::thread& th; EncodeJob& J; bool failed_flag = false;
+        ~StagerJoin() { if (th.joinable()) { if (std::uncaught_exceptions() || failed_flag) J.abort.store(true); th.join(); } }
+    } stager_join{stager, J};
+    const bool use_stager = J.pageable && n_mine > 1;
+    if (use_stager) {
+        stager = std::thread([&] {
+            DeviceGuard g2(t->device);
+            for (size_t i = 0; i < n_mine; ++i) {
+                if (i >= (size_t)tk_tokenizer::kSlots)      // the slot's previous chunk must have its kernels queued (they record s.done)
+                    while (!kicked[i - tk_tokenizer::kSlots].load(std::memory_order_acquire)) {
+                        if (J.abort.load()) { up_state[i].store(-1); return; }
+                        std::this_thread::yield();
+                    }
+                if (J.abort.load()) { up_state[i].store(-1); return; }
+                const int r = upload(i);
+                if (r) { J.fail_with(r, g_last_error); for (size_t k = i; k < n_mine; ++k) up_state[k].store(-1); return; }
+                up_state[i].store(1, std::memory_order_release);
+            }
+        });
+    }
+    auto issue = [&](size_t i) -> int {
+        if (use_stager) {
+            int st;
+            while ((st = up_state[i].load(std::memory_order_acquire)) == 0) {
+                if (J.abort.load()) return J.rc ? J.rc : TK_ERR_CUDA;
+                std::this_thread::yield();
+            }
+            if (st < 0) return fail(J.rc ? J.rc : TK_ERR_CUDA, "%s", J.err.c_str());
+        } else {
+            const int r = upload(i);
+            if (r) return r;
+        }
+        return kick(i);
     };
 
     // kAhead chunks are always queued ahead, so this thread sits in the wait for chunk i when it completes and its
