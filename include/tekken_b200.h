@@ -241,6 +241,10 @@ const char *tk_status_name(int status);
    0 restores the default of 128 MB, also settable with TEKKEN_B200_CHUNK_MB).  The tests use it to exercise the
    chunk-boundary and document-slicing logic on small inputs. */
 void tk_set_chunk_bytes(uint64_t bytes);
+/* Bounds-checked debug build (compile the library with -DTK_DEBUG_BOUNDS; compute-sanitizer substitute): number of
+   out-of-range stores the encode kernels of the handle's device refused since the last call of this function, with
+   detail4 = {count, source line, index, limit} of the first one.  -1 in a regular build (the checks compile away). */
+long long tk_debug_bounds_violations(const tk_tokenizer *t, uint64_t *detail4);
 /* Kernel launches issued by this process so far (for benchmark accounting). */
 uint64_t tk_kernel_launch_count(void);
 /* Per-stage device time of the most recent tk_encode_batch_device call on this handle, in

@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 # TEKKEN_B200_LIB: load (and build into) another file, e.g. an experimental build with TEKKEN_B200_NVCC_FLAGS="-DPT_MINB=5"
 LIB = os.environ.get("TEKKEN_B200_LIB") or os.path.join(HERE, "libtekken_b200.so")
 SOURCES = ["tk_kernels.cu", "tk_decode.cu", "tk_api.cu", "tk_host.cpp"]
-HEADERS = ["tk_common.h", "tk_host.h", "tk_pretok.h", "tk_device.cuh", "tk_kernels.h", "unicode_ranges.inc", "unicode_subclasses.inc",
+HEADERS = ["tk_common.h", "tk_host.h", "tk_pretok.h", "tk_pretok_cfg.h", "tk_small.cuh", "tk_device.cuh", "tk_kernels.h", "unicode_ranges.inc", "unicode_subclasses.inc",
            os.path.join("..", "..", "include", "tekken_b200.h")]
 
 
@@ -44,3 +44,19 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 if __name__ == "__main__":
     print(build(force=True, verbose=True))
+
+
+DEBUG_LIB = os.path.join(HERE, "libtekken_b200_dbg.so")
+
+
+def build_debug(force: bool = False) -> str:
+    """The bounds-checked variant (-DTK_DEBUG_BOUNDS, see tk_kernels.cu): libtekken_b200_dbg.so next to the library.
+    tests/test_gpu_debug_bounds.py runs the parity corpus through it (compute-sanitizer is closed on the GPU pool)."""
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
+    if not force and os.path.exists(DEBUG_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(DEBUG_LIB) for d in deps if os.path.exists(d)):
+        return DEBUG_LIB
+    cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-DTK_DEBUG_BOUNDS",
+           "-Xcompiler", "-fPIC", "-shared", "-o", DEBUG_LIB + ".tmp"] + [os.path.join(CSRC, s) for s in SOURCES]
+    subprocess.check_call(cmd)
+    os.replace(DEBUG_LIB + ".tmp", DEBUG_LIB)
+    return DEBUG_LIB

@@ -13,6 +13,9 @@
 
 #include <algorithm>
 #include <cerrno>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 #include <atomic>
 #include <cstdarg>
 #include <cstdlib>
@@ -700,7 +703,7 @@ class CopyPool {
     // dst/src do not overlap.  The caller copies too; returns when all n bytes are in place.
     void parallel_memcpy(void* dst, const void* src, size_t n) {
         constexpr size_t kPiece = 1 << 20;
-        if (n <= 2 * kPiece || threads_.empty()) { memcpy(dst, src, n); return; }
+        if (n <= 2 * kPiece || threads_.empty()) { copy_piece((char*)dst, (const char*)src, n); return; }
         auto job = std::make_shared<Job>();
         job->dst = (char*)dst; job->src = (const char*)src; job->n = n;
         job->pieces = (n + kPiece - 1) / kPiece;
@@ -719,13 +722,42 @@ class CopyPool {
         char* dst; const char* src; size_t n, pieces;
         std::atomic<size_t> next{0}, done{0};
     };
+    // The destination is a pinned staging buffer that the DMA engine reads next and the CPU never reads back: write it
+    // with non-temporal stores (no read-for-ownership of the destination lines, no cache pollution).  glibc's memcpy
+    // only switches to them far above the 1 MB pieces used here.
+#if defined(__x86_64__)
+    __attribute__((target("avx2"))) static void copy_nt_avx2(char* dst, const char* src, size_t n) {
+        size_t head = (64 - ((uintptr_t)dst & 63)) & 63;
+        if (head > n) head = n;
+        memcpy(dst, src, head);
+        dst += head; src += head; n -= head;
+        size_t i = 0;
+        for (; i + 128 <= n; i += 128) {
+            const __m256i a = _mm256_loadu_si256((const __m256i*)(src + i)), b = _mm256_loadu_si256((const __m256i*)(src + i + 32));
+            const __m256i c = _mm256_loadu_si256((const __m256i*)(src + i + 64)), d = _mm256_loadu_si256((const __m256i*)(src + i + 96));
+            _mm256_stream_si256((__m256i*)(dst + i), a);
+            _mm256_stream_si256((__m256i*)(dst + i + 32), b);
+            _mm256_stream_si256((__m256i*)(dst + i + 64), c);
+            _mm256_stream_si256((__m256i*)(dst + i + 96), d);
+        }
+        _mm_sfence();
+        memcpy(dst + i, src + i, n - i);
+    }
+#endif
+    static void copy_piece(char* dst, const char* src, size_t n) {
+#if defined(__x86_64__)
+        static const bool avx2 = __builtin_cpu_supports("avx2") && !getenv("TEKKEN_B200_NO_NT_COPY");
+        if (avx2) { copy_nt_avx2(dst, src, n); return; }
+#endif
+        memcpy(dst, src, n);
+    }
     static void run(Job& j) {
         constexpr size_t kPiece = 1 << 20;
         for (;;) {
             const size_t p = j.next.fetch_add(1);
             if (p >= j.pieces) return;
             const size_t o = p * kPiece, len = std::min(kPiece, j.n - o);
-            memcpy(j.dst + o, j.src + o, len);
+            copy_piece(j.dst + o, j.src + o, len);
             j.done.fetch_add(1, std::memory_order_release);
         }
     }
@@ -988,8 +1020,9 @@ static int encode_worker(tk_tokenizer* t, EncodeJob& J, size_t g, size_t stride)
         stager = std::thread([&] {
             DeviceGuard g2(t->device);
             for (size_t i = 0; i < n_mine; ++i) {
-                if (i >= (size_t)tk_tokenizer::kSlots)      // the slot's previous chunk must have its kernels queued (they record s.done)
-                    while (!kicked[i - tk_tokenizer::kSlots].load(std::memory_order_acquire)) {
+                if (i >= (size_t)tk_tokenizer::kSlots)      // the slot's previous chunk must be through its kernels (a re-run after
+                                                            // growing the long-piece scratch reads the slot's text again)
+                    while (kicked[i - tk_tokenizer::kSlots].load(std::memory_order_acquire) < 2) {
                         if (J.abort.load()) { up_state[i].store(-1); return; }
                         std::this_thread::yield();
                     }
@@ -1035,6 +1068,7 @@ static int encode_worker(tk_tokenizer* t, EncodeJob& J, size_t g, size_t stride)
             rc = launch(i);
             if (rc) return bail(rc);
         }
+        kicked[i].store(2, std::memory_order_release);       // the slot's text buffers may be refilled
         uint64_t my_prefix = 0;
         {
             std::unique_lock<std::mutex> lk(J.mu);
@@ -1858,6 +1892,16 @@ extern "C" int tk_shard_plan(const uint64_t* doc_off, size_t n_docs, size_t n_sh
 }
 
 extern "C" void tk_set_chunk_bytes(uint64_t bytes) { g_chunk_bytes.store(bytes ? std::max<uint64_t>(bytes, 4096) : 0); }
+
+extern "C" long long tk_debug_bounds_violations(const tk_tokenizer* t, uint64_t* detail4) {
+    if (!t || t->device < 0) return -1;
+    DeviceGuard dg(t->device);
+    cudaDeviceSynchronize();
+    unsigned long long d[4] = {0, 0, 0, 0};
+    const long long n = tkk::debug_bounds_violations(d);
+    if (detail4) for (int i = 0; i < 4; ++i) detail4[i] = d[i];
+    return n;
+}
 
 extern "C" uint64_t tk_kernel_launch_count(void) { return tkk::launch_count(); }
 

@@ -30,6 +30,28 @@ namespace tkk {
 
 #define TKK_COUNT_TILE 4096u      // tokens are counted per 4 KiB of text (= lookup / emit tile)
 
+// ---- bounds-checked debug build (-DTK_DEBUG_BOUNDS) ------------------------------------------------
+// compute-sanitizer is not available on the GPU pool this library is developed on, so the kernels carry their own
+// checks: in a debug build every store into a workspace / output array first compares its index with the array's
+// size (the host publishes the sizes of the call in g_dbg before the launches); a violation is skipped and recorded
+// (source line, index) in g_dbg_hit, which tk_debug_bounds_violations() reads.  tests/test_gpu_debug_bounds.py
+// builds this variant and runs the parity corpus through it.  A regular build compiles the checks away.
+struct DbgLimits {
+    unsigned long long mask_words, stream_words, queue_words, pool_words, scratch_words, count_tiles, out_cap, n_docs, max_long;
+};
+#ifdef TK_DEBUG_BOUNDS
+__device__ DbgLimits g_dbg;
+__device__ unsigned long long g_dbg_hit[4];      // violations, first line, its index, its limit
+__device__ __forceinline__ bool dbg_in(unsigned long long i, unsigned long long n, int line) {
+    if (i < n) return true;
+    if (atomicAdd(&g_dbg_hit[0], 1ull) == 0ull) { g_dbg_hit[1] = (unsigned long long)line; g_dbg_hit[2] = i; g_dbg_hit[3] = n; }
+    return false;
+}
+#define TK_DBG(index, field) dbg_in((unsigned long long)(index), g_dbg.field, __LINE__)
+#else
+#define TK_DBG(index, field) true
+#endif
+
 static std::atomic<uint64_t> g_launches{0};
 uint64_t launch_count() { return g_launches.load(); }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
@@ -72,19 +94,20 @@ __global__ void docmark_kernel(const uint64_t* __restrict__ doc_off, uint64_t of
     if (d > n_docs) return;
     // the end-of-data sentinel does not depend on the offsets being valid: every later kernel that walks the
     // piece-start mask to "the next set bit" relies on it, also when the call is about to fail with bad offsets
-    if (d == n_docs) atomicOr(ds_mask + (total >> 5), 1u << (total & 31));
+    if (d == n_docs && TK_DBG(total >> 5, mask_words)) atomicOr(ds_mask + (total >> 5), 1u << (total & 31));
     uint64_t o = doc_off[d] - off_base;      // offsets may be a slice of a larger batch (off_base = its first entry)
     bool ok = doc_off[d] >= off_base && o <= total;
     if (d == 0 && o != 0) ok = false;
     if (d == n_docs && o != total) ok = false;
     if (d < n_docs && doc_off[d + 1] < doc_off[d]) ok = false;
     if (!ok) { atomicOr(flags, TKK_FLAG_BAD_OFFSETS); return; }
+    if (!TK_DBG(o >> 5, mask_words)) return;
     atomicOr(ds_mask + (o >> 5), 1u << (o & 31));
     atomicMin(doc_first + (o >> 5), (uint32_t)d);     // first document that starts in this 32-byte window
     atomicAdd(doc_cnt + (o >> 5), 1u);                // ... and how many do
     // the EOS of the document before and the BOS of this one count towards the tile this document starts in
     const unsigned long long sp = (d > 0 ? add_eos : 0u) + (d < n_docs ? add_bos : 0u);
-    if (sp) atomicAdd(tile_count + o / TKK_COUNT_TILE, sp);
+    if (sp && TK_DBG(o / TKK_COUNT_TILE, count_tiles)) atomicAdd(tile_count + o / TKK_COUNT_TILE, sp);
 }
 
 // =====================================================================================================
@@ -234,7 +257,7 @@ __device__ __forceinline__ void pretok_tile(PtSmem& S, uint32_t b, const uint8_t
     }
     if ((uint64_t)wi < n_windows) {
         const uint32_t keep = (pos + 32 <= n) ? 0xFFFFFFFFu : (uint32_t)((2ull << (n - pos)) - 1ull);
-        start_mask[wi] = start & keep;
+        if (TK_DBG(wi, mask_words)) start_mask[wi] = start & keep;
         const uint32_t valid = (pos + 32 <= n) ? 0xFFFFFFFFu : (uint32_t)((1ull << (n - pos)) - 1ull);
         if (c.bad & valid) atomicMin(err_pos, (unsigned long long)(pos + (uint64_t)(__ffs((int)(c.bad & valid)) - 1)));
     }
@@ -455,7 +478,7 @@ __global__ void __launch_bounds__(PT_T) cfg_mask_kernel(const uint8_t* __restric
         const uint32_t keep = (pos + 32 <= n) ? 0xFFFFFFFFu : (uint32_t)((2ull << (n - pos)) - 1ull);   // bit n: the end sentinel
         const uint32_t safe = tk_cfg_safe_mask(S.win[t], c) & keep;
         safe_mask[wi] = safe;
-        start_mask[wi] = safe;
+        if (TK_DBG(wi, mask_words)) start_mask[wi] = safe;
         const uint32_t valid = (pos + 32 <= n) ? 0xFFFFFFFFu : (uint32_t)((1ull << (n - pos)) - 1ull);
         if (c.bad & valid) atomicMin(err_pos, (unsigned long long)(pos + (uint64_t)(__ffs((int)(c.bad & valid)) - 1)));
     }
@@ -546,7 +569,7 @@ __global__ void longmark_kernel(const uint32_t* __restrict__ start_mask, uint64_
     if (need) {
         TkkLongRec r;
         r.start = pos; r.len = 0; r.count = 0; r.tok_base = 0; r.pad = 0;
-        recs[slot] = r;
+        if (TK_DBG(slot, max_long)) recs[slot] = r;
     }
     if (w < n_windows) long_of_word[w] = need ? slot + 1u : 0u;
 }
@@ -610,13 +633,13 @@ __global__ void __launch_bounds__(LM_WARPS * 32) longmerge_warp_kernel(const uin
                 whole = __shfl_sync(0xFFFFFFFFu, whole, 0);
             }
             if (whole != TK_INF) {
-                if (lane == 0) pool[base] = whole;
+                if (lane == 0 && TK_DBG(base, pool_words)) pool[base] = whole;
                 count = 1;
             } else {
                 count = tk_bpe_warp(T, S[warp], data + pos, (uint32_t)len, pool + base);
             }
         } else if (lane == 0) {
-            huge_list[atomicAdd(n_huge, 1u)] = r;
+            { const uint32_t hslot = atomicAdd(n_huge, 1u); if (TK_DBG(hslot, max_long)) huge_list[hslot] = r; }
         }
         if (lane == 0) {
             recs[r].len = len;
@@ -857,12 +880,12 @@ __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __
                 __syncthreads();
                 uint32_t before = 0, all = 0;
                 for (uint32_t w = 0; w < HG_T / 32; ++w) { if (w < warp) before += s_cnt[w]; all += s_cnt[w]; }
-                if (v != TK_DEAD) out[outn + before + __popc(alive & ((1u << lane) - 1u))] = v;
+                if (v != TK_DEAD && TK_DBG(recs[r].tok_base + outn + before + __popc(alive & ((1u << lane) - 1u)), pool_words)) out[outn + before + __popc(alive & ((1u << lane) - 1u))] = v;
                 outn += all;
                 __syncthreads();
             }
         } else {
-            for (uint32_t i = t; i < m; i += HG_T) out[i] = id[i];
+            for (uint32_t i = t; i < m; i += HG_T) if (TK_DBG(recs[r].tok_base + i, pool_words)) out[i] = id[i];
         }
         if (t == 0) { recs[r].count = outn; atomicAdd(tile_count + pos / TKK_COUNT_TILE, (unsigned long long)outn); }
     }
@@ -983,7 +1006,7 @@ __global__ void __launch_bounds__(LK_T, LK_MINB) lookup_kernel(const uint8_t* __
     {
         const uint4 inv = make_uint4(EN_INVALID, EN_INVALID, EN_INVALID, EN_INVALID);
         uint4* d4 = reinterpret_cast<uint4*>(dst);
-        for (uint32_t i = t; i < LK_TILE / 4; i += LK_T) d4[i] = inv;
+        for (uint32_t i = t; i < LK_TILE / 4; i += LK_T) if (TK_DBG(tile_pos + 4u * i + 3u, stream_words)) d4[i] = inv;
     }
     __threadfence_block();
     __syncthreads();
@@ -1001,10 +1024,11 @@ __global__ void __launch_bounds__(LK_T, LK_MINB) lookup_kernel(const uint8_t* __
                 if (e != 0xFFFFFFFFu && e - s <= TK_LANE_MAX) {
                     len = e - s;
                     const uint32_t whole = tk_vocab_lookup_w32(T, S.bytes, s, len);
-                    if (whole != TK_INF) { dst[s] = whole; hit = true; }
+                    if (!TK_DBG(tile_pos + s, stream_words)) { }
+                    else if (whole != TK_INF) { dst[s] = whole; hit = true; }
                     else if (len == 1) { dst[s] = (uint32_t)S.bytes[s]; hit = true; }
                     else cls = lane_class(len);
-                } else dst[s] = EN_LONGREF;                           // longer pieces: K3
+                } else if (TK_DBG(tile_pos + s, stream_words)) dst[s] = EN_LONGREF;      // longer pieces: K3
             }
         }
         const uint32_t hm = __ballot_sync(0xFFFFFFFFu, hit);
@@ -1038,7 +1062,7 @@ __global__ void __launch_bounds__(LK_T, LK_MINB) lookup_kernel(const uint8_t* __
             if ((int)lane == leader) base = atomicAdd(&S.cls_pos[cls], (uint32_t)__popc(peers));
             base = __shfl_sync(peers, base, leader);
             const uint32_t pos = S.cls_base[cls] + base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
-            queues[Q.off[cls] + pos] = (tile_pos + (e & 4095u)) | ((unsigned long long)(e >> 12) << QE_START_BITS);
+            if (TK_DBG(Q.off[cls] + pos, queue_words)) queues[Q.off[cls] + pos] = (tile_pos + (e & 4095u)) | ((unsigned long long)(e >> 12) << QE_START_BITS);
         }
     }
 }
@@ -1179,7 +1203,8 @@ __global__ void __launch_bounds__(THREADS, MINB) lanemerge_kernel(const uint8_t*
             while (live) {
                 const uint32_t j = tk_ffs_m(live) - 1u;
                 live &= live - 1;
-                *dst++ = id[j];
+                if (TK_DBG(dst - stream, stream_words)) *dst = id[j];
+                ++dst;
             }
         }
         __syncwarp();
@@ -1468,7 +1493,7 @@ __global__ void __launch_bounds__(E3_T, E3_MINB) emit_kernel(const uint32_t* __r
             unsigned long long o = base + (unsigned long long)__popc(m & (le_mask >> 1));
             for (uint64_t x = d0; x < d0 + nd; ++x) {
                 if (x > 0 && add_eos) { if (o < out_cap) out[o] = eos_id; ++o; }
-                tok_off[x] = o;
+                if (TK_DBG(x, n_docs)) tok_off[x] = o;
                 if (x < n_docs && add_bos) { if (o < out_cap) out[o] = bos_id; ++o; }
             }
         }
@@ -1544,6 +1569,7 @@ size_t encode_workspace_bytes(uint64_t n, uint64_t n_docs, EncodeLayout* L) {
         const uint32_t shortest[TKK_N_CLASSES] = {2, 5, 9, 13, 17, 25, 33, 49, 65};
         uint64_t e = 0;
         for (int c = 0; c < TKK_N_CLASSES; ++c) { l.queues.off[c] = e; e += n / shortest[c] + 32; }
+        l.queue_words = e;
         l.off_queues = take(e * 8);
     }
     l.max_long = n / (TK_LANE_MAX + 1) + 2;
@@ -1649,6 +1675,15 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
     unsigned long long* scratch_cursor = (unsigned long long*)(small + TKK_S_SCRCUR);
     unsigned long long* total_out = (unsigned long long*)(small + TKK_S_TOTAL);
 
+#ifdef TK_DEBUG_BOUNDS
+    {
+        DbgLimits lim{};
+        lim.mask_words = L.mask_words; lim.stream_words = L.n_ltiles * (unsigned long long)LK_TILE + TK_LANE_MAX + 64;
+        lim.queue_words = L.queue_words; lim.pool_words = n + 16; lim.scratch_words = scratch_cap; lim.count_tiles = L.n_ltiles + 1;
+        lim.out_cap = out_cap; lim.n_docs = n_docs + 1; lim.max_long = L.max_long;
+        CK(cudaMemcpyToSymbolAsync(g_dbg, &lim, sizeof lim, 0, cudaMemcpyHostToDevice, st));
+    }
+#endif
     if (timer) timer->mark(st, "setup");
     CK(cudaMemsetAsync(small, 0, 256, st));
     CK(cudaMemsetAsync(err_pos, 0xFF, 8, st));
@@ -1757,6 +1792,20 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
     TK_LAUNCHED();
     if (timer) timer->mark(st, "end");
     return cudaGetLastError();
+}
+
+// (debug build) violations recorded by the kernels of this device since the last call; out: {count, line, index, limit}
+long long debug_bounds_violations(unsigned long long* out4) {
+#ifdef TK_DEBUG_BOUNDS
+    unsigned long long h[4] = {0, 0, 0, 0}, z[4] = {0, 0, 0, 0};
+    if (cudaMemcpyFromSymbol(h, g_dbg_hit, sizeof h) != cudaSuccess) return -2;
+    cudaMemcpyToSymbol(g_dbg_hit, z, sizeof z);
+    if (out4) for (int i = 0; i < 4; ++i) out4[i] = h[i];
+    return (long long)h[0];
+#else
+    (void)out4;
+    return -1;
+#endif
 }
 
 cudaError_t encode_small(const TkDeviceTables& T, const uint8_t* d_text, uint32_t n, int add_bos, int add_eos, uint32_t* d_out,

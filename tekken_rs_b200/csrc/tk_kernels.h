@@ -58,7 +58,7 @@ struct TkkLongRec {
 };
 
 struct EncodeLayout {
-    uint64_t n_windows, n_tiles, n_ltiles, mask_words, max_long;
+    uint64_t n_windows, n_tiles, n_ltiles, mask_words, max_long, queue_words;
     TkkQueueLayout queues;
     size_t off_small, off_ds, off_start, off_longword, off_docfirst, off_doccnt, off_summ, off_carry, off_worklist, off_seg, off_tilecount, off_tilebase, off_bsum, off_recs,
         off_huge, off_pool, off_stream, off_queues, total;
@@ -115,6 +115,7 @@ cudaError_t decode_device(const TkDeviceTables& T, const uint32_t* d_ids, const 
                           uint64_t n_ids, int policy, uint8_t* d_out, uint64_t out_cap, uint64_t* d_byte_off,
                           int32_t* d_doc_status, void* d_ws, const DecodeLayout& L, cudaStream_t st);
 
+long long debug_bounds_violations(unsigned long long* out4);   // -1: not a -DTK_DEBUG_BOUNDS build
 uint64_t launch_count();
 void count_launch();
 
