@@ -317,6 +317,41 @@ __device__ __forceinline__ M tk_bpe_merge_loop(const TkDeviceTables& T, uint32_t
     return live;
 }
 
+// ---- pieces of 2..4 bytes that are not vocabulary entries: the merge loop written out -------------------
+// With at most four parts the loop has at most two steps, and its LAST possible pair is always the whole piece,
+// which is known not to be a token (the caller's whole-piece lookup missed): 0, 2 or 3 byte-pair lookups and at most
+// two pair-table lookups, no scratch, no loop.  The lookup kernel runs this inline for such pieces instead of queueing
+// them (a third of all queued pieces on mixed text; every 3-digit group of a long number).  out: up to 4 ranks.
+__device__ __forceinline__ uint32_t tk_bpe_tiny(const TkDeviceTables& T, uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3, uint32_t len,
+                                                uint32_t* out) {
+    if (len == 2) { out[0] = b0; out[1] = b1; return 2; }                 // its only pair is the whole piece
+    const uint32_t r0 = __ldg(T.byte_pair + ((b0 << 8) | b1)), r1 = __ldg(T.byte_pair + ((b1 << 8) | b2));
+    if (len == 3) {
+        if (r0 == TK_INF && r1 == TK_INF) { out[0] = b0; out[1] = b1; out[2] = b2; return 3; }
+        if (r0 <= r1) { out[0] = r0; out[1] = b2; }                       // leftmost on ties
+        else { out[0] = b0; out[1] = r1; }
+        return 2;
+    }
+    const uint32_t r2 = __ldg(T.byte_pair + ((b2 << 8) | b3));
+    const uint32_t m = min(r0, min(r1, r2));
+    if (m == TK_INF) { out[0] = b0; out[1] = b1; out[2] = b2; out[3] = b3; return 4; }
+    uint32_t p0, p1;
+    if (r0 == m) {                                                        // (a b) c d
+        p0 = tk_pair_rank(T, r0, b2); p1 = r2;
+        if (p0 == TK_INF && p1 == TK_INF) { out[0] = r0; out[1] = b2; out[2] = b3; return 3; }
+        if (p0 <= p1) { out[0] = p0; out[1] = b3; } else { out[0] = r0; out[1] = p1; }
+    } else if (r1 == m) {                                                 // a (b c) d
+        tk_pair_rank2<false>(T, b0, r1, r1, b3, &p0, &p1);
+        if (p0 == TK_INF && p1 == TK_INF) { out[0] = b0; out[1] = r1; out[2] = b3; return 3; }
+        if (p0 <= p1) { out[0] = p0; out[1] = b3; } else { out[0] = b0; out[1] = p1; }
+    } else {                                                              // a b (c d)
+        p0 = r0; p1 = tk_pair_rank(T, b1, r2);
+        if (p0 == TK_INF && p1 == TK_INF) { out[0] = b0; out[1] = b1; out[2] = r2; return 3; }
+        if (p0 <= p1) { out[0] = p0; out[1] = r2; } else { out[0] = b0; out[1] = p1; }
+    }
+    return 2;
+}
+
 // ---- one warp, one medium piece ------------------------------------------------------------------
 // Same loop, parts in shared memory (TK_MED_MAX entries per warp), each lane caching the minimum
 // of its own slice so a merge step costs one warp-wide min + a rescan by the lanes it touched.

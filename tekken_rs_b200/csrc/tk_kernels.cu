@@ -1016,7 +1016,7 @@ __global__ void __launch_bounds__(LK_T, LK_MINB) lookup_kernel(const uint8_t* __
     for (uint32_t k0 = 0; k0 < np; k0 += LK_T) {
         const uint32_t k = k0 + t;
         uint32_t s = 0, len = 0, cls = 0xFFFFFFFFu;
-        bool hit = false;
+        uint32_t hit = 0;                                  // ranks this lane stored (1 for a vocabulary entry, 2..4 for a tiny piece)
         if (k < np) {
             s = S.list[k];
             if (tile_pos + s < n) {                        // the end-of-data sentinel is not a piece
@@ -1025,14 +1025,23 @@ __global__ void __launch_bounds__(LK_T, LK_MINB) lookup_kernel(const uint8_t* __
                     len = e - s;
                     const uint32_t whole = tk_vocab_lookup_w32(T, S.bytes, s, len);
                     if (!TK_DBG(tile_pos + s, stream_words)) { }
-                    else if (whole != TK_INF) { dst[s] = whole; hit = true; }
-                    else if (len == 1) { dst[s] = (uint32_t)S.bytes[s]; hit = true; }
+                    else if (whole != TK_INF) { dst[s] = whole; hit = 1; }
+                    else if (len == 1) { dst[s] = (uint32_t)S.bytes[s]; hit = 1; }
+                    else if (len <= 4u && s + len <= LK_TILE) {
+                        // 2..4 bytes: the merge loop written out (tk_bpe_tiny), ranks straight into the piece's own positions
+                        // (a piece that reaches into the next tile's words is queued: that tile's block clears them)
+                        uint32_t r[4];
+                        hit = tk_bpe_tiny(T, S.bytes[s], S.bytes[s + 1], S.bytes[s + 2], S.bytes[s + 3], len, r);
+                        dst[s] = r[0]; dst[s + 1] = r[1];
+                        if (hit > 2u) dst[s + 2] = r[2];
+                        if (hit > 3u) dst[s + 3] = r[3];
+                    }
                     else cls = lane_class(len);
                 } else if (TK_DBG(tile_pos + s, stream_words)) dst[s] = EN_LONGREF;      // longer pieces: K3
             }
         }
-        const uint32_t hm = __ballot_sync(0xFFFFFFFFu, hit);
-        if (lane == 0 && hm) atomicAdd(&S.n_hit, (uint32_t)__popc(hm));
+        const uint32_t hm = __reduce_add_sync(0xFFFFFFFFu, hit);
+        if (lane == 0 && hm) atomicAdd(&S.n_hit, hm);
         const uint32_t mm = __ballot_sync(0xFFFFFFFFu, cls != 0xFFFFFFFFu);
         if (mm) {
             uint32_t base = 0;
