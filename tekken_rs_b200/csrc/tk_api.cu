@@ -260,6 +260,7 @@ struct tk_tokenizer {
     };
     static constexpr int kFastSlots = 4;
     FastSlot fast[kFastSlots];
+    std::atomic<float> ratio_hint{0.f};   // ids per text byte of recent large host-buffer calls (sizes the next result buffer)
     bool timing = false;
     bool counted = false;          // included in g_live_handles
     tkk::HotTables hot;            // pair + byte-pair table allocation (L2 persistence window of the merge kernels)
@@ -859,6 +860,7 @@ struct EncodeJob {
     bool pageable = false;
     std::vector<Chunk> chunks;
     uint64_t forced_cap = 0;          // second attempt: worst-case output size
+    float ratio_hint = 0.f;           // ids per byte recent calls on this handle needed
     // progress shared by the device workers
     std::mutex mu;
     std::condition_variable cv;
@@ -1079,7 +1081,9 @@ static int encode_worker(tk_tokenizer* t, EncodeJob& J, size_t g, size_t stride)
                 const uint64_t worst = J.total + 2 * (uint64_t)J.n_docs + 2;
                 uint64_t cap = worst;
                 if (!J.forced_cap && J.chunks.size() > 1) {
-                    const double ratio = (double)n_tok / (double)std::max<uint64_t>(1, c.n_bytes);
+                    // the first chunk's ids per byte, or what recent calls on this handle needed if that was more (a
+                    // document whose first megabytes are not typical of the rest would otherwise overflow every time)
+                    const double ratio = std::max((double)n_tok / (double)std::max<uint64_t>(1, c.n_bytes), (double)J.ratio_hint);
                     cap = std::min(worst, (uint64_t)(ratio * 1.25 * (double)J.total) + 2 * (uint64_t)J.n_docs + (1u << 16));
                 }
                 if (J.chunks.size() == 1) cap = n_tok + 2;
@@ -1165,6 +1169,7 @@ static int encode_batch_engine(tk_tokenizer* const* handles, size_t n_handles, c
         J.data = data; J.doc_off = doc_off; J.n_docs = n_docs; J.total = total; J.add_bos = add_bos; J.add_eos = add_eos;
         J.pageable = pageable && total >= (1u << 16);       // small inputs: the driver's own staging is as good
         J.forced_cap = attempt ? total + 2 * (uint64_t)n_docs + 2 : 0;
+        J.ratio_hint = handles[0]->ratio_hint.load();
         // chunks small enough that every device gets several, large enough to keep the launch overhead low
         uint64_t chunk = g_chunk_bytes.load() ? g_chunk_bytes.load() : kDefaultChunkBytes;
         if (n_handles > 1) chunk = std::max<uint64_t>(4u << 20, std::min<uint64_t>(chunk, total / (n_handles * 4) + 1));
@@ -1180,6 +1185,10 @@ static int encode_batch_engine(tk_tokenizer* const* handles, size_t n_handles, c
         encode_worker(handles[0], J, 0, n_dev);
         for (auto& x : th) x.join();
         if (J.rc == TK_OK) {
+            if (total >= (64u << 20)) {
+                const float r = (float)((double)J.prefix[J.chunks.size()] / (double)total), old = handles[0]->ratio_hint.load();
+                handles[0]->ratio_hint.store(std::max(r, old * 0.9f));
+            }
             J.h_off[n_docs] = J.prefix[J.chunks.size()];
             if (!J.h_tok) J.h_tok = (uint32_t*)g_pool.get(4);      // (not reached: chunk 0 always allocates)
             *tokens = J.h_tok;

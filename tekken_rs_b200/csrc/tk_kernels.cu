@@ -82,6 +82,76 @@ void StageTimer::reset() {
 }
 StageTimer::~StageTimer() { reset(); }
 
+// ---- programmatic dependent launch ---------------------------------------------------------------------
+// The encode path is a chain of two dozen dependent launches on one stream.  They are launched with the
+// programmatic-stream-serialization attribute: a kernel's blocks may be set up on the SMs while the kernel before it
+// drains, and every kernel begins with pdl_wait() (griddepcontrol.wait), which returns when the preceding kernel's
+// memory is visible -- so nothing is read early, and the launch latency of each link overlaps the tail of the one
+// before.  TEKKEN_B200_PDL=0 launches the plain way (A/B measurements).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+static bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("TEKKEN_B200_PDL"); return !e || atoi(e) != 0; }();
+    return on;
+}
+template <class... KArgs, class... Args>
+static cudaError_t launch_chain(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    count_launch();
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// ---- bulk copy of a tile's text into shared memory (TMA, 1-D: cp.async.bulk + mbarrier) ---------------------
+// One thread issues the copy of the whole tile; the block's threads do other work (mask words, piece lists) and meet
+// at the mbarrier before they read the bytes.  Source and destination 16-byte aligned, size a multiple of 16.
+__device__ __forceinline__ void bulk_tile_begin(void* smem_dst, const void* gmem_src, uint32_t bytes, unsigned long long* mbar) {
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(mbar), dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(gmem_src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_tile_wait(unsigned long long* mbar) {
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(mbar);
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(bar) : "memory");
+    }
+}
+
+// K0a: everything the later kernels expect cleared, in one launch (it was seven memsets): the counter block, the
+// document masks / tables, the padding of the piece-start mask, the per-tile token counts.
+struct SetupArgs {
+    uint32_t* small;                 // 64 words: 0, except err_pos = ~0
+    uint4* zero0; uint64_t n0;       // ds mask           (16-byte units)
+    uint4* ones;  uint64_t n1;       // first-document table: 0xFF
+    uint4* zero1; uint64_t n2;       // document counts
+    uint32_t* tail; uint64_t n3;     // piece-start mask padding (words)
+    unsigned long long* counts; uint64_t n4;
+};
+__global__ void __launch_bounds__(256) setup_kernel(SetupArgs a) {
+    pdl_wait();
+    const uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, step = (uint64_t)gridDim.x * blockDim.x;
+    if (i0 < 64) a.small[i0] = (i0 == TKK_S_ERRPOS || i0 == TKK_S_ERRPOS + 1) ? 0xFFFFFFFFu : 0u;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u), f = make_uint4(~0u, ~0u, ~0u, ~0u);
+    for (uint64_t i = i0; i < a.n0; i += step) a.zero0[i] = z;
+    for (uint64_t i = i0; i < a.n1; i += step) a.ones[i] = f;
+    for (uint64_t i = i0; i < a.n2; i += step) a.zero1[i] = z;
+    for (uint64_t i = i0; i < a.n3; i += step) a.tail[i] = 0u;
+    for (uint64_t i = i0; i < a.n4; i += step) a.counts[i] = 0ull;
+}
+
 // =====================================================================================================
 // K0: document-start bitmask.  Bit p is set iff some document starts at byte p; bit `total` is
 // the end-of-data sentinel.  Also validates the offsets.
@@ -90,6 +160,7 @@ __global__ void docmark_kernel(const uint64_t* __restrict__ doc_off, uint64_t of
                                uint32_t add_bos, uint32_t add_eos, uint32_t* __restrict__ ds_mask, uint32_t* __restrict__ doc_first,
                                uint32_t* __restrict__ doc_cnt, unsigned long long* __restrict__ tile_count,
                                uint32_t* __restrict__ flags) {
+    pdl_wait();
     uint64_t d = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (d > n_docs) return;
     // the end-of-data sentinel does not depend on the offsets being valid: every later kernel that walks the
@@ -133,6 +204,7 @@ struct PtSmem {
     uint32_t head[PT_T + 1];
     uint32_t wtot[PT_T / 32];
     long long pend;
+    unsigned long long mbar;           // mbarrier of the tile's bulk copy
 };
 
 __device__ __forceinline__ void pt_store(PtSmem& S, int i, const TkWin& w) {
@@ -146,10 +218,18 @@ __device__ __forceinline__ TkWin pt_load(const PtSmem& S, int i) {
     return w;
 }
 
-// stage [tile - halo, tile + 8 KiB + halo) of the text in shared memory, zero outside the text (PT_T threads)
-__device__ __forceinline__ void pt_stage_tile(uint8_t* bytes, uint32_t b, const uint8_t* __restrict__ data, uint64_t n) {
+// stage [tile - halo, tile + 8 KiB + halo) of the text in shared memory, zero outside the text (PT_T threads).
+// With `mbar`, a tile that lies inside the text goes by ONE bulk copy issued by thread 0 (returns true: the caller
+// waits on the mbarrier after its next __syncthreads); tiles at the edges of the text take the loop.
+__device__ __forceinline__ bool pt_stage_tile(uint8_t* bytes, uint32_t b, const uint8_t* __restrict__ data, uint64_t n,
+                                              unsigned long long* mbar = nullptr) {
     const int t = threadIdx.x;
     const long long g0 = (long long)b * (PT_T * 32) - PT_HALO;
+    constexpr uint32_t kBytes = PT_HALO + PT_T * 32 + PT_HALO;
+    if (mbar && g0 >= 0 && (uint64_t)g0 + kBytes <= n && (((uintptr_t)data) & 15u) == 0) {
+        if (t == 0) bulk_tile_begin(bytes, data + g0, kBytes, mbar);
+        return true;
+    }
     uint4* dst = reinterpret_cast<uint4*>(bytes);
     for (int i = t; i < (int)((PT_HALO + PT_T * 32 + PT_HALO) / 16); i += PT_T) {
         const long long g = g0 + 16ll * i;
@@ -165,6 +245,7 @@ __device__ __forceinline__ void pt_stage_tile(uint8_t* bytes, uint32_t b, const 
         }
         dst[i] = v;
     }
+    return false;
 }
 
 // classify window wi of the text from the staged tile (wl = its index inside the tile, -1 .. PT_T)
@@ -189,8 +270,9 @@ __device__ __forceinline__ void pretok_tile(PtSmem& S, uint32_t b, const uint8_t
     const int t = threadIdx.x;
     const long long wi = (long long)b * PT_T + t;
     const uint64_t pos = (uint64_t)wi * 32u;
-    pt_stage_tile(S.bytes, b, data, n);
+    const bool bulk = pt_stage_tile(S.bytes, b, data, n, FIX ? nullptr : &S.mbar);    // (the fix pass re-uses its block for many tiles)
     __syncthreads();
+    if (bulk) bulk_tile_wait(&S.mbar);
     const TkBytesTile src{S.bytes + PT_HALO, (int64_t)b * (PT_T * 32)};
     TkWin c = pt_classify(S, src, ds_mask, n_windows, wi, t, T);
     pt_store(S, t + 1, c);
@@ -280,6 +362,7 @@ __global__ void __launch_bounds__(PT_T, PT_MINB) pretok_kernel(const uint8_t* __
                                                       const uint32_t* __restrict__ ds_mask, uint32_t* __restrict__ start_mask,
                                                       uint64_t n_windows, TkDeviceTables T, TkkTileSummary* __restrict__ summ,
                                                       unsigned long long* __restrict__ err_pos) {
+    pdl_wait();
     __shared__ __align__(16) PtSmem S;
     pretok_tile<false>(S, blockIdx.x, data, n, ds_mask, start_mask, n_windows, T, summ, nullptr, err_pos);
 }
@@ -289,6 +372,7 @@ __global__ void __launch_bounds__(PT_T) pretok_fix_kernel(const uint8_t* __restr
                                                           uint64_t n_windows, TkDeviceTables T, const uint32_t* __restrict__ carry,
                                                           const uint32_t* __restrict__ worklist, const uint32_t* __restrict__ work_count,
                                                           unsigned long long* __restrict__ err_pos) {
+    pdl_wait();
     __shared__ __align__(16) PtSmem S;
     const uint32_t cnt = *work_count;
     for (uint32_t w = blockIdx.x; w < cnt; w += gridDim.x) {
@@ -313,6 +397,7 @@ __device__ __forceinline__ void rs_step(uint32_t& nst, uint32_t& ast, const TkRu
 
 __global__ void __launch_bounds__(SG_T) pretok_seg_kernel(const TkkTileSummary* __restrict__ summ, uint32_t n_tiles,
                                                           uint32_t* __restrict__ seg_packed) {
+    pdl_wait();
     __shared__ uint32_t f_chunk[SG_T];
     const uint32_t t = threadIdx.x;
     const uint64_t lo0 = (uint64_t)blockIdx.x * SG_TILES + (uint64_t)t * SG_PER;
@@ -337,6 +422,7 @@ __global__ void __launch_bounds__(SG_T) pretok_seg_kernel(const TkkTileSummary* 
 
 __global__ void __launch_bounds__(SC_T) pretok_segscan_kernel(const uint32_t* __restrict__ seg_packed, uint32_t n_seg,
                                                               uint32_t* __restrict__ seg_in, uint32_t* __restrict__ seg_after) {
+    pdl_wait();
     __shared__ uint32_t f_chunk[SC_T], in_state[SC_T], h_chunk[SC_T], h_after[SC_T];
     const uint32_t t = threadIdx.x;
     const uint32_t per = (n_seg + SC_T - 1) / SC_T;
@@ -380,6 +466,7 @@ __global__ void __launch_bounds__(SG_T) pretok_apply_kernel(const TkkTileSummary
                                                             const uint32_t* __restrict__ seg_in, const uint32_t* __restrict__ seg_after,
                                                             uint32_t* __restrict__ carry, uint32_t* __restrict__ worklist,
                                                             uint32_t* __restrict__ work_count, uint32_t* __restrict__ start_mask) {
+    pdl_wait();
     __shared__ uint32_t f_chunk[SG_T];     // composite of each thread's tiles
     __shared__ uint32_t in_state[SG_T];    // n | abs<<2 entering each thread's tiles
     __shared__ uint32_t h_after[SG_T];     // first head event after each thread's tiles
@@ -453,6 +540,7 @@ struct CfgSmem {
 __global__ void __launch_bounds__(PT_T) cfg_mask_kernel(const uint8_t* __restrict__ data, uint64_t n, const uint32_t* __restrict__ ds_mask,
                                                         uint32_t* __restrict__ safe_mask, uint32_t* __restrict__ start_mask,
                                                         uint64_t n_windows, TkCfgTables T, unsigned long long* __restrict__ err_pos) {
+    pdl_wait();
     __shared__ __align__(16) CfgSmem S;
     const int t = threadIdx.x;
     const uint32_t b = blockIdx.x;
@@ -491,6 +579,7 @@ __global__ void __launch_bounds__(PT_T) cfg_mask_kernel(const uint8_t* __restric
 __global__ void __launch_bounds__(CW_T) cfg_walk_kernel(const uint8_t* __restrict__ data, uint64_t n, const uint32_t* __restrict__ ds_mask,
                                                         const uint32_t* __restrict__ safe_mask, uint32_t* __restrict__ start_mask,
                                                         uint64_t n_windows, TkCfgTables T, const unsigned long long* __restrict__ err_pos) {
+    pdl_wait();
     __shared__ uint16_t list[CW_T * 32];
     __shared__ uint32_t wsum[CW_T / 32];
     __shared__ uint32_t n_list;
@@ -546,6 +635,7 @@ __device__ __forceinline__ uint32_t warp_claim(uint32_t* counter, bool pred) {
 __global__ void longmark_kernel(const uint32_t* __restrict__ start_mask, uint64_t n_windows, uint64_t n,
                                 uint32_t* __restrict__ long_of_word, TkkLongRec* __restrict__ recs,
                                 uint32_t* __restrict__ n_long) {
+    pdl_wait();
     const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;     // blockDim.x is a multiple of 32
     const uint32_t m = w < n_windows ? start_mask[w] : 0u;
     bool need = false;
@@ -609,6 +699,7 @@ __global__ void __launch_bounds__(LM_WARPS * 32) longmerge_warp_kernel(const uin
                                                                        uint32_t* __restrict__ work_counter,
                                                                        unsigned long long* __restrict__ tile_count,
                                                                        uint64_t n_windows, uint64_t n, const uint32_t* __restrict__ flags) {
+    pdl_wait();
     __shared__ TkWarpBpeSmem S[LM_WARPS];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     if (*flags & TKK_FLAG_BAD_OFFSETS) return;          // the call fails; the masks describe no valid batch
@@ -682,6 +773,7 @@ __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __
                                                                unsigned long long* __restrict__ scratch_cursor,
                                                                uint32_t* __restrict__ work_counter, uint32_t* __restrict__ flags,
                                                                unsigned long long* __restrict__ tile_count) {
+    pdl_wait();
     __shared__ uint32_t s_tmp[HG_T / 32];
     __shared__ uint32_t s_par[HG_T / 32];      // run-parity summaries of the warps
     __shared__ uint32_t s_cnt[HG_T / 32];
@@ -929,6 +1021,7 @@ struct LkSmem {
     uint32_t wsum[LK_T / 32];
     uint32_t cls_n[TKK_N_CLASSES], cls_base[TKK_N_CLASSES], cls_pos[TKK_N_CLASSES];
     uint32_t n_pieces, n_miss, n_hit;
+    unsigned long long mbar;           // mbarrier of the tile's bulk copy
 };
 
 // tile-relative end of the piece that starts at tile-relative byte s (the next set bit of the start
@@ -972,6 +1065,7 @@ __global__ void __launch_bounds__(LK_T, LK_MINB) lookup_kernel(const uint8_t* __
                                                       uint32_t* __restrict__ stream, unsigned long long* __restrict__ queues,
                                                       TkkQueueLayout Q, uint32_t* __restrict__ q_n,
                                                       unsigned long long* __restrict__ tile_count) {
+    pdl_wait();
     static_assert(LK_TILE == TKK_COUNT_TILE, "token counts are kept per lookup tile");
     __shared__ __align__(16) LkSmem S;
     const uint32_t t = threadIdx.x, lane = t & 31u;
@@ -981,14 +1075,21 @@ __global__ void __launch_bounds__(LK_T, LK_MINB) lookup_kernel(const uint8_t* __
     if (t < TKK_N_CLASSES) { S.cls_n[t] = 0; S.cls_pos[t] = 0; }
     if (t == 0) { S.n_miss = 0; S.n_hit = 0; }
     // ---- A: stage bytes and mask words; list the piece starts ----
+    bool bulk;
     {
         const uint64_t avail = n > tile_pos ? n - tile_pos : 0;
-        const uint32_t want = LK_TILE + TK_LANE_MAX + 16;
-        const uint32_t full16 = (uint32_t)((avail < want ? avail : want) / 16);
-        uint4* dst = reinterpret_cast<uint4*>(S.bytes);
-        const uint4* src = reinterpret_cast<const uint4*>(data + tile_pos);
-        for (uint32_t i = t; i < full16; i += LK_T) dst[i] = __ldg(src + i);
-        for (uint32_t i = full16 * 16 + t; i < want; i += LK_T) S.bytes[i] = (tile_pos + i < n) ? data[tile_pos + i] : 0;
+        constexpr uint32_t want = LK_TILE + TK_LANE_MAX + 16;
+        static_assert(want % 16 == 0, "bulk copies move multiples of 16 bytes");
+        bulk = avail >= want;                              // a tile inside the text: one bulk copy (TMA), issued by thread 0,
+        if (bulk) {                                        // in flight while the block lists the piece starts
+            if (t == 0) bulk_tile_begin(S.bytes, data + tile_pos, want, &S.mbar);
+        } else {
+            const uint32_t full16 = (uint32_t)(avail / 16);
+            uint4* dst = reinterpret_cast<uint4*>(S.bytes);
+            const uint4* src = reinterpret_cast<const uint4*>(data + tile_pos);
+            for (uint32_t i = t; i < full16; i += LK_T) dst[i] = __ldg(src + i);
+            for (uint32_t i = full16 * 16 + t; i < want; i += LK_T) S.bytes[i] = (tile_pos + i < n) ? data[tile_pos + i] : 0;
+        }
         uint32_t m = 0;
         if (t < LK_WINS + 4) { m = start_mask[win0 + t]; S.mask[t] = m; }
         if (t >= LK_WINS) m = 0;
@@ -1010,6 +1111,7 @@ __global__ void __launch_bounds__(LK_T, LK_MINB) lookup_kernel(const uint8_t* __
     }
     __threadfence_block();
     __syncthreads();
+    if (bulk) bulk_tile_wait(&S.mbar);
     const uint32_t np = S.n_pieces;
 
     // ---- B: one lane per piece: whole-piece vocabulary lookup; entries written, misses collected ----
@@ -1110,6 +1212,7 @@ __global__ void __launch_bounds__(THREADS, MINB) lanemerge_kernel(const uint8_t*
                                                             const uint32_t* __restrict__ q_n, uint32_t* __restrict__ q_w,
                                                             uint32_t* __restrict__ stream, unsigned long long* __restrict__ tile_count,
                                                             unsigned long long* __restrict__ stats) {
+    pdl_wait();
     constexpr int STRIDE = MAXLEN + 1;      // odd: lane i's arrays start at bank i (no conflicts when lanes sweep together)
     extern __shared__ __align__(16) uint32_t lm_raw[];
     uint32_t* id = lm_raw + threadIdx.x * STRIDE;
@@ -1252,6 +1355,7 @@ __device__ __forceinline__ unsigned long long ts_block_excl(unsigned long long v
 
 __global__ void __launch_bounds__(TS_T) tilesum_kernel(const unsigned long long* __restrict__ tile_count, uint32_t n_tiles,
                                                        unsigned long long* __restrict__ bsum) {
+    pdl_wait();
     __shared__ unsigned long long wsum[TS_T / 32];
     unsigned long long v = 0;
 #pragma unroll
@@ -1266,6 +1370,7 @@ __global__ void __launch_bounds__(TS_T) tilesum_kernel(const unsigned long long*
 
 __global__ void __launch_bounds__(TS_T) tilescan_kernel(unsigned long long* __restrict__ bsum, uint32_t n_blocks, uint64_t out_cap,
                                                         unsigned long long* __restrict__ total_out, uint32_t* __restrict__ flags) {
+    pdl_wait();
     __shared__ unsigned long long wsum[TS_T / 32];
     unsigned long long run = 0;
     for (uint32_t b0 = 0; b0 < n_blocks; b0 += TS_T) {
@@ -1285,6 +1390,7 @@ __global__ void __launch_bounds__(TS_T) tilescan_kernel(unsigned long long* __re
 __global__ void __launch_bounds__(TS_T) tileapply_kernel(const unsigned long long* __restrict__ tile_count, uint32_t n_tiles,
                                                          const unsigned long long* __restrict__ bbase,
                                                          unsigned long long* __restrict__ tile_base) {
+    pdl_wait();
     __shared__ unsigned long long wsum[TS_T / 32];
     unsigned long long run = bbase[blockIdx.x];
 #pragma unroll
@@ -1391,6 +1497,7 @@ __global__ void __launch_bounds__(E3_T, E3_MINB) emit_kernel(const uint32_t* __r
                                                     uint32_t add_bos, uint32_t add_eos, uint32_t nsp, uint32_t bos_id, uint32_t eos_id,
                                                     uint32_t* __restrict__ out, uint64_t out_cap, uint64_t* __restrict__ tok_off,
                                                     const unsigned long long* __restrict__ tile_base) {
+    pdl_wait();
     static_assert(E3_T * E3_PER == LK_TILE && E3_PER == 16, "one emit block per lookup tile, 16 windows per warp");
     __shared__ unsigned long long wsum[E3_T / 32];
     __shared__ E3Long longs[E3_LONGCAP];
@@ -1596,18 +1703,15 @@ size_t encode_workspace_bytes(uint64_t n, uint64_t n_docs, EncodeLayout* L) {
 // The 256-byte counter block goes to mapped pinned host memory with a kernel, not a copy: a copy
 // would queue behind the large id transfers of other chunks on the device-to-host copy engine.
 __global__ void publish_kernel(const uint32_t* __restrict__ small, uint32_t* __restrict__ mapped) {
+    pdl_wait();
     mapped[threadIdx.x] = small[threadIdx.x];
     __threadfence_system();
 }
 cudaError_t publish_small(const void* d_small, uint32_t* mapped_dev, cudaStream_t st) {
-    publish_kernel<<<1, 64, 0, st>>>((const uint32_t*)d_small, mapped_dev);
-    count_launch();
-    return cudaGetLastError();
+    return launch_chain(publish_kernel, 1, 64, 0, st, (const uint32_t*)d_small, mapped_dev);
 }
 cudaError_t publish_counters(const void* d_ws, const EncodeLayout& L, uint32_t* mapped_dev, cudaStream_t st) {
-    publish_kernel<<<1, 64, 0, st>>>((const uint32_t*)((const unsigned char*)d_ws + L.off_small), mapped_dev);
-    count_launch();
-    return cudaGetLastError();
+    return launch_chain(publish_kernel, 1, 64, 0, st, (const uint32_t*)((const unsigned char*)d_ws + L.off_small), mapped_dev);
 }
 
 template <int MAXLEN, int THREADS, int MINB>
@@ -1631,7 +1735,7 @@ static cudaError_t launch_lanemerge(int blocks_per_sm, int sm_count, const uint8
     cfg.blockDim = dim3(THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     cfg.attrs = attr;
     cfg.numAttrs = 0;
     if (pin && hot && hot->enabled) {
@@ -1642,6 +1746,11 @@ static cudaError_t launch_lanemerge(int blocks_per_sm, int sm_count, const uint8
         attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
         attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
         cfg.numAttrs = 1;
+    }
+    if (pdl_enabled()) {
+        attr[cfg.numAttrs].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[cfg.numAttrs].val.programmaticStreamSerializationAllowed = 1;
+        ++cfg.numAttrs;
     }
     CK(cudaLaunchKernelEx(&cfg, lanemerge_kernel<MAXLEN, THREADS, MINB>, d_data, n, T, queue, q_n, (uint32_t*)q_w, stream, tile_count, stats));
     count_launch();
@@ -1694,65 +1803,57 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
     }
 #endif
     if (timer) timer->mark(st, "setup");
-    CK(cudaMemsetAsync(small, 0, 256, st));
-    CK(cudaMemsetAsync(err_pos, 0xFF, 8, st));
-    CK(cudaMemsetAsync(ds, 0, L.mask_words * 4, st));
-    CK(cudaMemsetAsync(docfirst, 0xFF, L.mask_words * 4, st));
-    CK(cudaMemsetAsync(doccnt, 0, L.mask_words * 4, st));
-    CK(cudaMemsetAsync(start + L.n_windows, 0, (L.mask_words - L.n_windows) * 4, st));
-    CK(cudaMemsetAsync(tile_count, 0, (L.n_ltiles + 1) * 8, st));
-    docmark_kernel<<<(unsigned)ceil_div(n_docs + 1, 256), 256, 0, st>>>(d_doc_off, off_base, n_docs, n, add_bos ? 1u : 0u, add_eos ? 1u : 0u, ds, docfirst, doccnt, tile_count, flags);
-    TK_LAUNCHED();
+    {
+        SetupArgs sa;
+        sa.small = small;
+        sa.zero0 = (uint4*)ds; sa.n0 = L.mask_words / 4;                   // mask_words is a multiple of 64
+        sa.ones = (uint4*)docfirst; sa.n1 = L.mask_words / 4;
+        sa.zero1 = (uint4*)doccnt; sa.n2 = L.mask_words / 4;
+        sa.tail = start + L.n_windows; sa.n3 = L.mask_words - L.n_windows;
+        sa.counts = tile_count; sa.n4 = L.n_ltiles + 1;
+        const uint64_t work = L.mask_words / 4 + 64;
+        const unsigned grid = (unsigned)std::min<uint64_t>(ceil_div(work, 256), (uint64_t)sm_count * 8);
+        CK(launch_chain(setup_kernel, grid, 256, 0, st, sa));
+    }
+    CK(launch_chain(docmark_kernel, (unsigned)ceil_div(n_docs + 1, 256), 256, 0, st, d_doc_off, off_base, n_docs, n, add_bos ? 1u : 0u, add_eos ? 1u : 0u, ds, docfirst, doccnt, tile_count, flags));
     if (timer) timer->mark(st, "pretok");
     if (cfg) {
         // the pattern stored in tekken.json: safe starts by bit logic, then one matcher walk per safe start.  The safe
         // mask lives in the long-piece index array, which is not written before K2a.
         const TkCfgTables CT{cfg->stage1, cfg->stage2};
-        cfg_mask_kernel<<<(unsigned)L.n_tiles, PT_T, 0, st>>>(d_data, n, ds, longword, start, L.n_windows, CT, err_pos);
-        TK_LAUNCHED();
+        CK(launch_chain(cfg_mask_kernel, (unsigned)L.n_tiles, PT_T, 0, st, d_data, n, ds, longword, start, L.n_windows, CT, err_pos));
         if (timer) timer->mark(st, "pretok_walk");
-        cfg_walk_kernel<<<(unsigned)ceil_div(L.n_windows, CW_T), CW_T, 0, st>>>(d_data, n, ds, longword, start, L.n_windows, CT, err_pos);
-        TK_LAUNCHED();
+        CK(launch_chain(cfg_walk_kernel, (unsigned)ceil_div(L.n_windows, CW_T), CW_T, 0, st, d_data, n, ds, longword, start, L.n_windows, CT, err_pos));
     } else {
-    pretok_kernel<<<(unsigned)L.n_tiles, PT_T, 0, st>>>(d_data, n, ds, start, L.n_windows, T, summ, err_pos);
-    TK_LAUNCHED();
+    CK(launch_chain(pretok_kernel, (unsigned)L.n_tiles, PT_T, 0, st, d_data, n, ds, start, L.n_windows, T, summ, err_pos));
     if (timer) timer->mark(st, "pretok_carry");
     {
         const uint32_t n_seg = (uint32_t)ceil_div(L.n_tiles, SG_TILES);
         uint32_t* seg_packed = (uint32_t*)(ws + L.off_seg);
         uint32_t* seg_in = seg_packed + n_seg;
         uint32_t* seg_after = seg_in + n_seg;
-        pretok_seg_kernel<<<n_seg, SG_T, 0, st>>>(summ, (uint32_t)L.n_tiles, seg_packed);
-        TK_LAUNCHED();
-        pretok_segscan_kernel<<<1, SC_T, 0, st>>>(seg_packed, n_seg, seg_in, seg_after);
-        TK_LAUNCHED();
-        pretok_apply_kernel<<<n_seg, SG_T, 0, st>>>(summ, (uint32_t)L.n_tiles, seg_in, seg_after, carry, worklist, work_count, start);
-        TK_LAUNCHED();
+        CK(launch_chain(pretok_seg_kernel, n_seg, SG_T, 0, st, summ, (uint32_t)L.n_tiles, seg_packed));
+        CK(launch_chain(pretok_segscan_kernel, 1, SC_T, 0, st, seg_packed, n_seg, seg_in, seg_after));
+        CK(launch_chain(pretok_apply_kernel, n_seg, SG_T, 0, st, summ, (uint32_t)L.n_tiles, seg_in, seg_after, carry, worklist, work_count, start));
     }
-    pretok_fix_kernel<<<(unsigned)(L.n_tiles < (uint64_t)(2 * sm_count) ? L.n_tiles : (uint64_t)(2 * sm_count)), PT_T, 0, st>>>(
-        d_data, n, ds, start, L.n_windows, T, carry, worklist, work_count, err_pos);
-    TK_LAUNCHED();
+    CK(launch_chain(pretok_fix_kernel, (unsigned)(L.n_tiles < (uint64_t)(2 * sm_count) ? L.n_tiles : (uint64_t)(2 * sm_count)), PT_T, 0, st, d_data, n, ds, start, L.n_windows, T, carry, worklist, work_count, err_pos));
     }
     if (timer) timer->mark(st, "longmark");
-    longmark_kernel<<<(unsigned)ceil_div(L.n_windows, 256), 256, 0, st>>>(start, L.n_windows, n, longword, recs, n_long);
-    TK_LAUNCHED();
+    CK(launch_chain(longmark_kernel, (unsigned)ceil_div(L.n_windows, 256), 256, 0, st, start, L.n_windows, n, longword, recs, n_long));
     if (timer) timer->mark(st, "longmerge");
     {
         uint64_t blocks = ceil_div(L.max_long, LM_WARPS);
         const uint64_t cap = (uint64_t)sm_count * 12;
         if (blocks > cap) blocks = cap;
-        longmerge_warp_kernel<<<(unsigned)blocks, LM_WARPS * 32, 0, st>>>(d_data, start, T, recs, n_long, pool, pool_cursor, huge,
-                                                                        n_huge, wc_long, tile_count, L.n_windows, n, flags);
-        TK_LAUNCHED();
+        CK(launch_chain(longmerge_warp_kernel, (unsigned)blocks, LM_WARPS * 32, 0, st, d_data, start, T, recs, n_long, pool, pool_cursor, huge,
+                                                                        n_huge, wc_long, tile_count, L.n_windows, n, flags));
         uint64_t hb = L.max_long < (uint64_t)(2 * sm_count) ? L.max_long : (uint64_t)(2 * sm_count);
-        longmerge_block_kernel<<<(unsigned)hb, HG_T, 0, st>>>(d_data, T, recs, huge, n_huge, pool, d_scratch, scratch_cap,
-                                                             scratch_cursor, wc_huge, flags, tile_count);
-        TK_LAUNCHED();
+        CK(launch_chain(longmerge_block_kernel, (unsigned)hb, HG_T, 0, st, d_data, T, recs, huge, n_huge, pool, d_scratch, scratch_cap,
+                                                             scratch_cursor, wc_huge, flags, tile_count));
     }
     if (timer) timer->mark(st, "lookup");
     {
-        lookup_kernel<<<(unsigned)L.n_ltiles, LK_T, 0, st>>>(d_data, n, start, T, stream, queues, L.queues, q_n, tile_count);
-        TK_LAUNCHED();
+        CK(launch_chain(lookup_kernel, (unsigned)L.n_ltiles, LK_T, 0, st, d_data, n, start, T, stream, queues, L.queues, q_n, tile_count));
     }
     // resident blocks per SM of the lane-merge launches, longest class first (what shared memory allows;
     // tuning knob: TEKKEN_B200_LM_BPS="a,b,...")
@@ -1788,17 +1889,13 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
     if (timer) timer->mark(st, "emit");
     {
         const uint32_t nb = (uint32_t)ceil_div(L.n_ltiles, TS_BLOCK);
-        tilesum_kernel<<<nb, TS_T, 0, st>>>(tile_count, (uint32_t)L.n_ltiles, bsum);
-        TK_LAUNCHED();
-        tilescan_kernel<<<1, TS_T, 0, st>>>(bsum, nb, out_cap, total_out, flags);
-        TK_LAUNCHED();
-        tileapply_kernel<<<nb, TS_T, 0, st>>>(tile_count, (uint32_t)L.n_ltiles, bsum, tile_base);
-        TK_LAUNCHED();
+        CK(launch_chain(tilesum_kernel, nb, TS_T, 0, st, tile_count, (uint32_t)L.n_ltiles, bsum));
+        CK(launch_chain(tilescan_kernel, 1, TS_T, 0, st, bsum, nb, out_cap, total_out, flags));
+        CK(launch_chain(tileapply_kernel, nb, TS_T, 0, st, tile_count, (uint32_t)L.n_ltiles, bsum, tile_base));
     }
-    emit_kernel<<<(unsigned)L.n_ltiles, E3_T, 0, st>>>(stream, ds, docfirst, doccnt, longword, recs, pool, d_doc_off, off_base, n_docs,
+    CK(launch_chain(emit_kernel, (unsigned)L.n_ltiles, E3_T, 0, st, stream, ds, docfirst, doccnt, longword, recs, pool, d_doc_off, off_base, n_docs,
                                                       add_bos ? 1u : 0u, add_eos ? 1u : 0u, T.num_special, T.bos_id, T.eos_id, d_out,
-                                                      out_cap, d_tok_off, tile_base);
-    TK_LAUNCHED();
+                                                      out_cap, d_tok_off, tile_base));
     if (timer) timer->mark(st, "end");
     return cudaGetLastError();
 }
