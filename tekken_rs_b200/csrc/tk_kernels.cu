@@ -750,9 +750,15 @@ __global__ void __launch_bounds__(LM_WARPS * 32) longmerge_warp_kernel(const uin
 // <= m the sequential loop would turn to that pair next: the round applies the selected merges up to and
 // including the leftmost such pair and drops the rest.  Parts and pair ranks live in compact arrays in
 // global scratch (L2-resident for pieces of tens of KiB) and are rebuilt each round with a block scan.
-// A run of thousands of spaces takes a handful of rounds instead of thousands of dependent steps.
+// A run of thousands of spaces takes a handful of rounds instead of thousands of dependent steps.  Text without
+// repetition (random letters, CJK: every rank occurs a handful of times) would need a round per rank; there MULTI-RANK
+// rounds take over: all pairs of rank <= a threshold are candidates, the ones the sequential loop would merge are
+// selected by key order ((rank, position): a candidate merges unless an overlapping neighbour with a smaller key did),
+// each computes the pairs its merge creates at its time, and the round is cut at the first created pair that could
+// overtake a later candidate.  64 KiB of random letters: 15-30 rounds instead of 40,000 dependent merges
+// (verified against the literal loop in oracle/research/multirank_rounds.py, incl. shuffled-rank vocabularies).
 #define HG_T 512
-#define HG_ARRAYS 6                 // id / rank, double-buffered, + the two new-rank arrays of a round
+#define HG_ARRAYS 7                 // id / rank, double-buffered, + the two new-rank arrays of a round + the selection state
 #define HG_UNSEL 0xFFFFFFFEu        // rL marker: pair not selected this round
 
 __device__ __forceinline__ uint32_t hg_block_min(uint32_t v, uint32_t* s_tmp) {
@@ -766,6 +772,32 @@ __device__ __forceinline__ uint32_t hg_block_min(uint32_t v, uint32_t* s_tmp) {
     return r;
 }
 
+// block-wide minimum of a 64-bit key (rank << 32 | position)
+__device__ __forceinline__ unsigned long long hg_block_min64(unsigned long long v, unsigned long long* s_tmp64) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, v, d);
+        v = o < v ? o : v;
+    }
+    __syncthreads();
+    if (lane == 0) s_tmp64[warp] = v;
+    __syncthreads();
+    unsigned long long r = s_tmp64[lane < HG_T / 32 ? lane : 0];
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, r, d);
+        r = o < r ? o : r;
+    }
+    return r;
+}
+// selection state of a pair in a multi-rank round
+#define HG_ST_NONE 0u
+#define HG_ST_UND 1u
+#define HG_ST_SEL 2u
+#define HG_ST_NOT 3u
+#define HG_PASSES 4
+
 __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __restrict__ data, TkDeviceTables T,
                                                                TkkLongRec* __restrict__ recs, const uint32_t* __restrict__ huge_list,
                                                                const uint32_t* __restrict__ n_huge, uint32_t* __restrict__ pool,
@@ -778,7 +810,6 @@ __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __
     __shared__ uint32_t s_par[HG_T / 32];      // run-parity summaries of the warps
     __shared__ uint32_t s_cnt[HG_T / 32];
     __shared__ unsigned long long s_key[HG_T / 32];
-    __shared__ unsigned long long s_best;
     __shared__ uint32_t s_rec;
     __shared__ unsigned long long s_base;
     const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
@@ -813,6 +844,7 @@ __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __
         uint32_t* rk2 = id2 + n;
         uint32_t* rL = rk2 + n;
         uint32_t* rR = rL + n;
+        uint32_t* sel = rR + n;
         for (uint32_t i = t; i < n; i += HG_T) {
             const uint32_t b0 = data[pos + i];
             id[i] = b0;
@@ -820,7 +852,11 @@ __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __
         }
         __syncthreads();
         uint32_t m = n;
-        bool sequential = false;
+        // Width of the window of ranks a round may merge: 0 = only the lowest rank (the rounds above: they handle runs
+        // of equal pairs -- repeated characters, thousands of spaces -- by parity).  When such a round applies only a
+        // few merges (text without repetition: every rank occurs a handful of times) the window opens and MULTI-RANK
+        // rounds take over; a round that had to be cut narrows it again.
+        uint32_t delta = 0;
         for (;;) {
             const uint32_t c = (m + HG_T - 1) / HG_T;
             const uint32_t lo = (uint64_t)t * c < m ? t * c : m, hi = (uint64_t)lo + c < m ? lo + c : m;
@@ -829,6 +865,104 @@ __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __
             for (uint32_t i = lo; i < hi; ++i) mine = min(mine, rk[i]);
             const uint32_t mn = hg_block_min(mine, s_tmp);
             if (mn == TK_INF) break;
+            if (delta) {
+                // ---- multi-rank round (oracle/research/multirank_rounds.py is the verified statement of this) ----
+                // candidates: pairs of rank <= thr; their order in the sequential loop is (rank, position)
+                const uint32_t thr = mn + delta < TK_ID_MASK ? mn + delta : TK_ID_MASK;
+                for (uint32_t i = lo; i < hi; ++i) sel[i] = rk[i] <= thr ? HG_ST_UND : HG_ST_NONE;
+                __syncthreads();
+                // selection = what the sequential loop merges if no merge creates a pair of rank <= thr: by key order, a
+                // candidate merges unless a neighbouring candidate (they share a part) with a smaller key merged.
+                // Passes of the local rule; a state only moves from undecided to decided, so reading a neighbour's
+                // state a pass early or late changes how soon a pair is decided, never what is decided.
+#pragma unroll 1
+                for (int pass = 0; pass < HG_PASSES; ++pass) {
+                    for (uint32_t i = lo; i < hi; ++i) {
+                        if (sel[i] != HG_ST_UND) continue;
+                        const uint32_t r = rk[i];
+                        bool lower_sel = false, lower_open = false;
+                        if (i > 0) {
+                            const uint32_t sj = sel[i - 1];
+                            if (sj != HG_ST_NONE && rk[i - 1] <= r) {                    // left neighbour: smaller key on ties
+                                lower_sel |= sj == HG_ST_SEL; lower_open |= sj == HG_ST_UND;
+                            }
+                        }
+                        if (i + 1 < m) {
+                            const uint32_t sj = sel[i + 1];
+                            if (sj != HG_ST_NONE && rk[i + 1] < r) {
+                                lower_sel |= sj == HG_ST_SEL; lower_open |= sj == HG_ST_UND;
+                            }
+                        }
+                        if (lower_sel) sel[i] = HG_ST_NOT;
+                        else if (!lower_open) sel[i] = HG_ST_SEL;
+                    }
+                    __syncthreads();
+                }
+                // candidates still undecided cut the round at their key
+                unsigned long long kcut = ~0ull;
+                for (uint32_t i = lo; i < hi; ++i)
+                    if (sel[i] == HG_ST_UND) { const unsigned long long k = (unsigned long long)rk[i] << 32 | i; kcut = k < kcut ? k : kcut; }
+                kcut = hg_block_min64(kcut, s_key);
+                // the two pairs every selected merge creates AT ITS TIME: a neighbour two positions away is already merged
+                // iff it is selected with a smaller key.  A created pair of rank <= thr is a hazard.
+                unsigned long long khaz = ~0ull;
+                for (uint32_t i = lo; i < hi; ++i) {
+                    if (sel[i] != HG_ST_SEL) continue;
+                    const uint32_t r = rk[i];
+                    const unsigned long long k = (unsigned long long)r << 32 | i;
+                    if (k >= kcut) continue;
+                    uint32_t lf = TK_INF, rt = TK_INF;
+                    if (i >= 1) lf = (i >= 2 && sel[i - 2] == HG_ST_SEL && rk[i - 2] <= r) ? rk[i - 2] : id[i - 1];
+                    if (i + 2 < m) rt = (sel[i + 2] == HG_ST_SEL && rk[i + 2] < r) ? rk[i + 2] : id[i + 2];
+                    uint32_t x, y;
+                    tk_pair_rank2<true>(T, lf, r, r, rt, &x, &y);
+                    rL[i] = x;
+                    rR[i] = y;
+                    if (x <= thr || y <= thr) khaz = k < khaz ? k : khaz;
+                }
+                khaz = hg_block_min64(khaz, s_key);
+                // apply: selected, before the cut, up to and including the first hazard
+                auto applied = [&](uint32_t j) -> bool {
+                    if (sel[j] != HG_ST_SEL) return false;
+                    const unsigned long long k = (unsigned long long)rk[j] << 32 | j;
+                    return k < kcut && k <= khaz;
+                };
+                uint32_t napp = 0, nsel = 0;
+                for (uint32_t i = lo; i < hi; ++i) { nsel += sel[i] == HG_ST_SEL ? 1u : 0u; napp += applied(i) ? 1u : 0u; }
+                uint32_t inc = napp, incs = nsel;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d), os = __shfl_up_sync(0xFFFFFFFFu, incs, d);
+                    if (lane >= (uint32_t)d) { inc += o; incs += os; }
+                }
+                if (lane == 31) { s_cnt[warp] = inc; s_par[warp] = incs; }
+                __syncthreads();
+                uint32_t before = inc - napp, all_app = 0, all_sel = 0;
+                for (uint32_t w = 0; w < HG_T / 32; ++w) { if (w < warp) before += s_cnt[w]; all_app += s_cnt[w]; all_sel += s_par[w]; }
+                for (uint32_t j = lo; j < hi; ++j) {
+                    if (j > 0 && applied(j - 1)) continue;                               // right part of an applied merge: gone
+                    const uint32_t q = j - before;
+                    uint32_t nr;
+                    if (applied(j)) {
+                        id2[q] = rk[j];
+                        if (j + 2 >= m) nr = TK_INF;
+                        else if (applied(j + 2)) nr = rk[j + 2] >= rk[j] ? rL[j + 2] : rR[j];   // the later of the two merges saw the other's result
+                        else nr = rR[j];
+                        ++before;
+                    } else {
+                        id2[q] = id[j];
+                        if (j + 1 >= m) nr = TK_INF;
+                        else nr = applied(j + 1) ? rL[j + 1] : rk[j];
+                    }
+                    rk2[q] = nr;
+                }
+                m -= all_app;
+                { uint32_t* z = id; id = id2; id2 = z; z = rk; rk = rk2; rk2 = z; }
+                __syncthreads();
+                if (all_app == all_sel) delta = delta < (1u << 19) ? delta * 2u : delta;    // went through: widen
+                else delta >>= 2;                                                            // cut: narrow (0 = single-rank rounds)
+                continue;
+            }
             // 2. selection: in every maximal run of adjacent rank-mn pairs take the 1st, 3rd, ...  A chunk's
             //    summary: all = every pair of the chunk has rank mn; par = parity of the run that ends the chunk
             uint32_t all = 1, par = 0;
@@ -899,86 +1033,11 @@ __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __
             m -= all_app;
             { uint32_t* x = id; id = id2; id2 = x; x = rk; rk = rk2; rk2 = x; }
             __syncthreads();
-            // A round costs a few passes over the m parts; a single merge of the sequential loop below costs a
-            // block-wide minimum.  Once a round applies only a handful of merges (text without repetition) the
-            // sequential loop is cheaper -- and pair ranks only get more distinct from here on.
-            if (m >= 16384u && all_app < (m >> 12)) { sequential = true; break; }
+            // a single-rank round that applies only a few merges (text without repetition): open the window of ranks
+            if (all_app * 64u < m) delta = 64u;
         }
-        uint32_t outn = m;
-        if (sequential) {
-            // the sequential definition on the compact arrays: parts become a linked list (nx / pv), a merged-away
-            // part is marked TK_DEAD, every thread caches the minimum of its slice
-            uint32_t* nx = id2;
-            uint32_t* pv = rk2;
-            for (uint32_t i = t; i < m; i += HG_T) { nx[i] = i + 1; pv[i] = i - 1; }
-            __syncthreads();
-            const uint32_t k = (m + HG_T - 1) / HG_T;
-            const uint32_t lo = (uint64_t)t * k < m ? t * k : m, hi = (uint64_t)(t + 1) * k < m ? (t + 1) * k : m;
-            unsigned long long mine = ~0ull;
-            for (uint32_t i = lo; i < hi; ++i) {
-                const uint32_t v = rk[i];
-                if (v != TK_INF) { unsigned long long key = (unsigned long long)v << 32 | i; mine = key < mine ? key : mine; }
-            }
-            for (;;) {
-                // block-wide minimum of (rank, position)
-                unsigned long long mm = mine;
-#pragma unroll
-                for (int d = 16; d; d >>= 1) {
-                    unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, mm, d);
-                    mm = o < mm ? o : mm;
-                }
-                if (lane == 0) s_key[warp] = mm;
-                __syncthreads();
-                if (warp == 0) {
-                    unsigned long long v = lane < HG_T / 32 ? s_key[lane] : ~0ull;
-#pragma unroll
-                    for (int d = 16; d; d >>= 1) {
-                        unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, v, d);
-                        v = o < v ? o : v;
-                    }
-                    if (lane == 0) s_best = v;
-                }
-                __syncthreads();
-                const unsigned long long g = s_best;
-                if (g == ~0ull) break;
-                const uint32_t p0 = (uint32_t)g, rnk = (uint32_t)(g >> 32);
-                const uint32_t j = nx[p0], pp = pv[p0];
-                const uint32_t nn = nx[j];
-                __syncthreads();
-                if (t == 0) {
-                    id[p0] = rnk; id[j] = TK_DEAD; rk[j] = TK_INF; nx[p0] = nn;
-                    if (nn < m) pv[nn] = p0;
-                    rk[p0] = nn < m ? tk_pair_rank(T, rnk, id[nn]) : TK_INF;
-                } else if (t == 32) {
-                    if (pp != 0xFFFFFFFFu) rk[pp] = tk_pair_rank(T, id[pp], rnk);
-                }
-                __syncthreads();
-                const bool touched = (p0 >= lo && p0 < hi) || (j >= lo && j < hi) || (pp != 0xFFFFFFFFu && pp >= lo && pp < hi);
-                if (touched) {
-                    mine = ~0ull;
-                    for (uint32_t i = lo; i < hi; ++i) {
-                        const uint32_t v = rk[i];
-                        if (v != TK_INF) { unsigned long long key = (unsigned long long)v << 32 | i; mine = key < mine ? key : mine; }
-                    }
-                }
-            }
-            // compaction of the surviving ids into the output
-            outn = 0;
-            for (uint32_t basei = 0; basei < m; basei += HG_T) {
-                const uint32_t i = basei + t;
-                const uint32_t v = i < m ? id[i] : TK_DEAD;
-                const uint32_t alive = __ballot_sync(0xFFFFFFFFu, v != TK_DEAD);
-                if (lane == 0) s_cnt[warp] = __popc(alive);
-                __syncthreads();
-                uint32_t before = 0, all = 0;
-                for (uint32_t w = 0; w < HG_T / 32; ++w) { if (w < warp) before += s_cnt[w]; all += s_cnt[w]; }
-                if (v != TK_DEAD && TK_DBG(recs[r].tok_base + outn + before + __popc(alive & ((1u << lane) - 1u)), pool_words)) out[outn + before + __popc(alive & ((1u << lane) - 1u))] = v;
-                outn += all;
-                __syncthreads();
-            }
-        } else {
-            for (uint32_t i = t; i < m; i += HG_T) if (TK_DBG(recs[r].tok_base + i, pool_words)) out[i] = id[i];
-        }
+        const uint32_t outn = m;
+        for (uint32_t i = t; i < m; i += HG_T) if (TK_DBG(recs[r].tok_base + i, pool_words)) out[i] = id[i];
         if (t == 0) { recs[r].count = outn; atomicAdd(tile_count + pos / TKK_COUNT_TILE, (unsigned long long)outn); }
     }
 }
