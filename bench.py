@@ -528,13 +528,18 @@ def run_ours(args):
                  "hash_probes_per_s": (counters["pair_lookups"] + counters["byte_pair_lookups"]) / s,
                  "pieces_per_s": counters["pieces_queued"] / s, "lanemerge_ms": fam["lanemerge"],
                  "l2": "see profiles/ (lts__t_sector_hit_rate of the lane-merge launches)"}
+    if counters and counters.get("long_piece_rounds") and counters["n_huge"]:
+        line_extra = {"pieces_over_512_bytes": counters["n_huge"], **counters["long_piece_rounds"]}
+    else:
+        line_extra = None
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": cx.world, "steps": args.steps, "warmup": warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8->u32",
         "data": "synthetic", "tokens_per_s": total_tokens / (ms_per_step * 1e-3),
         "config": wl.config(cx.world, int(total_docs), int(total_bytes), need_flush),
-        "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "merge_stage": merge, "decode": decode,
+        "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "merge_stage": merge,
+        "long_piece_stage": line_extra, "decode": decode,
         "tokens_per_step": int(total_tokens), "bytes_per_token": total_bytes / max(total_tokens, 1.0),
     }
     if cx.numa:

@@ -257,7 +257,8 @@ size_t tk_last_stage_times(const tk_tokenizer *t, const char **names, float *ms,
    north star asks for hash probes/s of the merge stage).  out[0..8] = pieces sent to the merge kernels per
    length class (2-4, 5-8, 9-12, 13-16, 17-24, 25-32, 33-48, 49-64, 65-96 bytes); out[9] = pieces longer than
    96 bytes; out[10] = of those, longer than 512 bytes; out[11] = pair-table lookups; out[12] = byte-pair table
-   lookups.  Returns the number of entries written (at most `cap`). */
+   lookups; out[13..16] = rounds of the block-level long-piece kernel: single-rank rounds, multi-rank rounds, multi-rank
+   rounds that were cut, merges applied by multi-rank rounds.  Returns the number of entries written (at most `cap`). */
 size_t tk_last_encode_counters(const tk_tokenizer *t, uint64_t *out, size_t cap);
 
 #ifdef __cplusplus

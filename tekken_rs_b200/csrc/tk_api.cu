@@ -1921,13 +1921,15 @@ extern "C" void tk_set_stage_timing(tk_tokenizer* t, int enabled) {
 extern "C" size_t tk_last_encode_counters(const tk_tokenizer* t, uint64_t* out, size_t cap) {
     if (!t || !out || !t->dev_slot.h_small) return 0;
     const uint32_t* small = t->dev_slot.h_small;
-    uint64_t v[TKK_N_CLASSES + 4];
+    uint64_t v[TKK_N_CLASSES + 8];
     for (int c = 0; c < TKK_N_CLASSES; ++c) v[c] = small[tkk::TKK_S_QN + c];
     v[TKK_N_CLASSES] = small[tkk::TKK_S_NLONG];
     v[TKK_N_CLASSES + 1] = small[tkk::TKK_S_NHUGE];
     memcpy(&v[TKK_N_CLASSES + 2], small + tkk::TKK_S_PAIRLOOK, 8);
     memcpy(&v[TKK_N_CLASSES + 3], small + tkk::TKK_S_BPLOOK, 8);
-    const size_t n = std::min(cap, (size_t)(TKK_N_CLASSES + 4));
+    v[TKK_N_CLASSES + 4] = small[tkk::TKK_S_ROUNDS1]; v[TKK_N_CLASSES + 5] = small[tkk::TKK_S_ROUNDSM];
+    v[TKK_N_CLASSES + 6] = small[tkk::TKK_S_ROUNDSCUT]; v[TKK_N_CLASSES + 7] = small[tkk::TKK_S_APPLIEDM];
+    const size_t n = std::min(cap, (size_t)(TKK_N_CLASSES + 8));
     for (size_t i = 0; i < n; ++i) out[i] = v[i];
     return n;
 }

@@ -867,9 +867,15 @@ __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __
             if (mn == TK_INF) break;
             if (delta) {
                 // ---- multi-rank round (oracle/research/multirank_rounds.py is the verified statement of this) ----
+                // Layout: every warp owns a contiguous region of the parts and walks it in rows of 32 (lane = position in
+                // the row): all loads are coalesced and a pair's neighbours sit in the adjacent lanes' cache lines.  (With one
+                // contiguous chunk per THREAD, as in the single-rank rounds above, a round over 64 K parts took 0.7 ms.)
+                constexpr uint32_t NW = HG_T / 32;
+                const uint32_t wsz = ((m + NW * 32u - 1u) / (NW * 32u)) * 32u;
+                const uint32_t wlo = warp * wsz < m ? warp * wsz : m, whi = wlo + wsz < m ? wlo + wsz : m;
                 // candidates: pairs of rank <= thr; their order in the sequential loop is (rank, position)
                 const uint32_t thr = mn + delta < TK_ID_MASK ? mn + delta : TK_ID_MASK;
-                for (uint32_t i = lo; i < hi; ++i) sel[i] = rk[i] <= thr ? HG_ST_UND : HG_ST_NONE;
+                for (uint32_t i = wlo + lane; i < whi; i += 32) sel[i] = rk[i] <= thr ? HG_ST_UND : HG_ST_NONE;
                 __syncthreads();
                 // selection = what the sequential loop merges if no merge creates a pair of rank <= thr: by key order, a
                 // candidate merges unless a neighbouring candidate (they share a part) with a smaller key merged.
@@ -877,7 +883,7 @@ __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __
                 // state a pass early or late changes how soon a pair is decided, never what is decided.
 #pragma unroll 1
                 for (int pass = 0; pass < HG_PASSES; ++pass) {
-                    for (uint32_t i = lo; i < hi; ++i) {
+                    for (uint32_t i = wlo + lane; i < whi; i += 32) {
                         if (sel[i] != HG_ST_UND) continue;
                         const uint32_t r = rk[i];
                         bool lower_sel = false, lower_open = false;
@@ -900,13 +906,13 @@ __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __
                 }
                 // candidates still undecided cut the round at their key
                 unsigned long long kcut = ~0ull;
-                for (uint32_t i = lo; i < hi; ++i)
+                for (uint32_t i = wlo + lane; i < whi; i += 32)
                     if (sel[i] == HG_ST_UND) { const unsigned long long k = (unsigned long long)rk[i] << 32 | i; kcut = k < kcut ? k : kcut; }
                 kcut = hg_block_min64(kcut, s_key);
                 // the two pairs every selected merge creates AT ITS TIME: a neighbour two positions away is already merged
                 // iff it is selected with a smaller key.  A created pair of rank <= thr is a hazard.
                 unsigned long long khaz = ~0ull;
-                for (uint32_t i = lo; i < hi; ++i) {
+                for (uint32_t i = wlo + lane; i < whi; i += 32) {
                     if (sel[i] != HG_ST_SEL) continue;
                     const uint32_t r = rk[i];
                     const unsigned long long k = (unsigned long long)r << 32 | i;
@@ -927,38 +933,52 @@ __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __
                     const unsigned long long k = (unsigned long long)rk[j] << 32 | j;
                     return k < kcut && k <= khaz;
                 };
-                uint32_t napp = 0, nsel = 0;
-                for (uint32_t i = lo; i < hi; ++i) { nsel += sel[i] == HG_ST_SEL ? 1u : 0u; napp += applied(i) ? 1u : 0u; }
-                uint32_t inc = napp, incs = nsel;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d), os = __shfl_up_sync(0xFFFFFFFFu, incs, d);
-                    if (lane >= (uint32_t)d) { inc += o; incs += os; }
+                // parts that survive the round (everything but the right part of an applied merge), counted per warp ...
+                uint32_t kept_w = 0, napp_w = 0, nsel_w = 0;
+                for (uint32_t i0 = wlo; i0 < whi; i0 += 32) {
+                    const uint32_t i = i0 + lane;
+                    const bool in = i < whi;
+                    const bool ap = in && applied(i);
+                    const bool keep = in && !(i > 0 && applied(i - 1));
+                    kept_w += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, keep));
+                    napp_w += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, ap));
+                    nsel_w += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, in && sel[i] == HG_ST_SEL));
                 }
-                if (lane == 31) { s_cnt[warp] = inc; s_par[warp] = incs; }
+                if (lane == 0) { s_cnt[warp] = kept_w; s_par[warp] = nsel_w; s_tmp[warp] = napp_w; }
                 __syncthreads();
-                uint32_t before = inc - napp, all_app = 0, all_sel = 0;
-                for (uint32_t w = 0; w < HG_T / 32; ++w) { if (w < warp) before += s_cnt[w]; all_app += s_cnt[w]; all_sel += s_par[w]; }
-                for (uint32_t j = lo; j < hi; ++j) {
-                    if (j > 0 && applied(j - 1)) continue;                               // right part of an applied merge: gone
-                    const uint32_t q = j - before;
-                    uint32_t nr;
-                    if (applied(j)) {
-                        id2[q] = rk[j];
-                        if (j + 2 >= m) nr = TK_INF;
-                        else if (applied(j + 2)) nr = rk[j + 2] >= rk[j] ? rL[j + 2] : rR[j];   // the later of the two merges saw the other's result
-                        else nr = rR[j];
-                        ++before;
-                    } else {
-                        id2[q] = id[j];
-                        if (j + 1 >= m) nr = TK_INF;
-                        else nr = applied(j + 1) ? rL[j + 1] : rk[j];
+                uint32_t run = 0, all_app = 0, all_sel = 0, all_kept = 0;
+                for (uint32_t w = 0; w < NW; ++w) { if (w < warp) run += s_cnt[w]; all_kept += s_cnt[w]; all_sel += s_par[w]; all_app += s_tmp[w]; }
+                // ... and written to their new places
+                for (uint32_t i0 = wlo; i0 < whi; i0 += 32) {
+                    const uint32_t j = i0 + lane;
+                    const bool in = j < whi;
+                    const bool keep = in && !(j > 0 && applied(j - 1));
+                    const uint32_t km = __ballot_sync(0xFFFFFFFFu, keep);
+                    if (keep) {
+                        const uint32_t q = run + (uint32_t)__popc(km & ((1u << lane) - 1u));
+                        uint32_t nr;
+                        if (applied(j)) {
+                            id2[q] = rk[j];
+                            if (j + 2 >= m) nr = TK_INF;
+                            else if (applied(j + 2)) nr = rk[j + 2] >= rk[j] ? rL[j + 2] : rR[j];   // the later of the two merges saw the other's result
+                            else nr = rR[j];
+                        } else {
+                            id2[q] = id[j];
+                            if (j + 1 >= m) nr = TK_INF;
+                            else nr = applied(j + 1) ? rL[j + 1] : rk[j];
+                        }
+                        rk2[q] = nr;
                     }
-                    rk2[q] = nr;
+                    run += (uint32_t)__popc(km);
                 }
-                m -= all_app;
+                m = all_kept;
                 { uint32_t* z = id; id = id2; id2 = z; z = rk; rk = rk2; rk2 = z; }
                 __syncthreads();
+                if (t == 0) {
+                    atomicAdd(flags + (TKK_S_ROUNDSM - TKK_S_FLAGS), 1u);
+                    atomicAdd(flags + (TKK_S_APPLIEDM - TKK_S_FLAGS), all_app);
+                    if (all_app != all_sel) atomicAdd(flags + (TKK_S_ROUNDSCUT - TKK_S_FLAGS), 1u);
+                }
                 if (all_app == all_sel) delta = delta < (1u << 19) ? delta * 2u : delta;    // went through: widen
                 else delta >>= 2;                                                            // cut: narrow (0 = single-rank rounds)
                 continue;
@@ -1034,6 +1054,7 @@ __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __
             { uint32_t* x = id; id = id2; id2 = x; x = rk; rk = rk2; rk2 = x; }
             __syncthreads();
             // a single-rank round that applies only a few merges (text without repetition): open the window of ranks
+            if (t == 0) atomicAdd(flags + (TKK_S_ROUNDS1 - TKK_S_FLAGS), 1u);
             if (all_app * 64u < m) delta = 64u;
         }
         const uint32_t outn = m;

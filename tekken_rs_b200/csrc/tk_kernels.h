@@ -36,6 +36,10 @@ enum {
     TKK_S_QW = 30,       // TKK_N_CLASSES work counters
     TKK_S_PAIRLOOK = 40, // u64: pair-table lookups issued by the lane-merge kernels (two per merge, minus piece edges)
     TKK_S_BPLOOK = 42,   // u64: byte-pair table lookups (first round of every queued piece)
+    TKK_S_ROUNDS1 = 44,  // block-level long-piece kernel: single-rank rounds
+    TKK_S_ROUNDSM = 45,  // ... multi-rank rounds
+    TKK_S_ROUNDSCUT = 46, // ... multi-rank rounds that were cut (undecided chain or hazard)
+    TKK_S_APPLIEDM = 47, // ... merges applied by multi-rank rounds
 };
 
 #define TKK_N_CLASSES 9

@@ -326,13 +326,17 @@ class Tekkenizer:
 
     def last_encode_counters(self) -> dict:
         """Work counters of the last device-pointer encode call (pieces per merge class, table lookups)."""
-        v = (ctypes.c_uint64 * 16)()
-        n = self._lib.tk_last_encode_counters(self._h, v, 16)
+        v = (ctypes.c_uint64 * 20)()
+        n = self._lib.tk_last_encode_counters(self._h, v, 20)
         if n < 13:
             return {}
         by_class = [int(v[i]) for i in range(9)]
-        return {"by_class": by_class, "pieces_queued": sum(by_class), "n_long": int(v[9]), "n_huge": int(v[10]),
-                "pair_lookups": int(v[11]), "byte_pair_lookups": int(v[12])}
+        out = {"by_class": by_class, "pieces_queued": sum(by_class), "n_long": int(v[9]), "n_huge": int(v[10]),
+               "pair_lookups": int(v[11]), "byte_pair_lookups": int(v[12])}
+        if n >= 17:
+            out["long_piece_rounds"] = {"single_rank": int(v[13]), "multi_rank": int(v[14]), "multi_rank_cut": int(v[15]),
+                                        "merges_by_multi_rank": int(v[16])}
+        return out
 
 
 def shard_plan(doc_off, n_shards: int) -> np.ndarray:
