@@ -852,210 +852,146 @@ __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __
         }
         __syncthreads();
         uint32_t m = n;
-        // Width of the window of ranks a round may merge: 0 = only the lowest rank (the rounds above: they handle runs
-        // of equal pairs -- repeated characters, thousands of spaces -- by parity).  When such a round applies only a
-        // few merges (text without repetition: every rank occurs a handful of times) the window opens and MULTI-RANK
-        // rounds take over; a round that had to be cut narrows it again.
+        // Width of the window of ranks a round may merge on top of the lowest rank present.  It starts at 0 (one rank per
+        // round: runs of equal pairs -- repeated characters, thousands of spaces -- halve every round), opens while rounds go
+        // through with few candidates (text without repetition: every rank occurs a handful of times) and narrows again
+        // after a round that had to be cut.
         uint32_t delta = 0;
+        constexpr uint32_t NW = HG_T / 32;
         for (;;) {
-            const uint32_t c = (m + HG_T - 1) / HG_T;
-            const uint32_t lo = (uint64_t)t * c < m ? t * c : m, hi = (uint64_t)lo + c < m ? lo + c : m;
+            // Layout: every warp owns a contiguous region of the parts and walks it in rows of 32 (lane = position in the
+            // row): all loads are coalesced and a pair's neighbours sit in the adjacent lanes.  (With one contiguous chunk
+            // per THREAD, as in round 1, a round over 64 K parts took 0.7 ms.)
+            const uint32_t wsz = ((m + NW * 32u - 1u) / (NW * 32u)) * 32u;
+            const uint32_t wlo = warp * wsz < m ? warp * wsz : m, whi = wlo + wsz < m ? wlo + wsz : m;
             // 1. lowest pair rank of the piece
             uint32_t mine = TK_INF;
-            for (uint32_t i = lo; i < hi; ++i) mine = min(mine, rk[i]);
+            for (uint32_t i = wlo + lane; i < whi; i += 32) mine = min(mine, rk[i]);
             const uint32_t mn = hg_block_min(mine, s_tmp);
             if (mn == TK_INF) break;
-            if (delta) {
-                // ---- multi-rank round (oracle/research/multirank_rounds.py is the verified statement of this) ----
-                // Layout: every warp owns a contiguous region of the parts and walks it in rows of 32 (lane = position in
-                // the row): all loads are coalesced and a pair's neighbours sit in the adjacent lanes' cache lines.  (With one
-                // contiguous chunk per THREAD, as in the single-rank rounds above, a round over 64 K parts took 0.7 ms.)
-                constexpr uint32_t NW = HG_T / 32;
-                const uint32_t wsz = ((m + NW * 32u - 1u) / (NW * 32u)) * 32u;
-                const uint32_t wlo = warp * wsz < m ? warp * wsz : m, whi = wlo + wsz < m ? wlo + wsz : m;
-                // candidates: pairs of rank <= thr; their order in the sequential loop is (rank, position)
-                const uint32_t thr = mn + delta < TK_ID_MASK ? mn + delta : TK_ID_MASK;
-                for (uint32_t i = wlo + lane; i < whi; i += 32) sel[i] = rk[i] <= thr ? HG_ST_UND : HG_ST_NONE;
-                __syncthreads();
-                // selection = what the sequential loop merges if no merge creates a pair of rank <= thr: by key order, a
-                // candidate merges unless a neighbouring candidate (they share a part) with a smaller key merged.
-                // Passes of the local rule; a state only moves from undecided to decided, so reading a neighbour's
-                // state a pass early or late changes how soon a pair is decided, never what is decided.
+            // 2. candidates: pairs of rank <= thr.  The sequential loop would take them in the order of their keys
+            //    (rank, position).
+            const uint32_t thr = mn + delta < TK_ID_MASK ? mn + delta : TK_ID_MASK;
+            for (uint32_t i = wlo + lane; i < whi; i += 32) sel[i] = rk[i] <= thr ? HG_ST_UND : HG_ST_NONE;
+            __syncthreads();
+            // 3. selection = what the sequential loop merges if no merge creates a pair of rank <= thr: by key order, a
+            //    candidate merges unless a neighbouring candidate (they share a part) with a smaller key merged.  A local
+            //    rule iterated to its fixed point inside every row (registers + shuffles), rows of a region in order, a
+            //    few passes over the regions: chains of dependent candidates -- a run of equal pairs is one, left to
+            //    right -- resolve across a whole region per pass.  A state only moves from undecided to decided, so
+            //    reading a neighbour's state early or late changes how soon a pair is decided, never what is decided.
 #pragma unroll 1
-                for (int pass = 0; pass < HG_PASSES; ++pass) {
-                    for (uint32_t i = wlo + lane; i < whi; i += 32) {
-                        if (sel[i] != HG_ST_UND) continue;
-                        const uint32_t r = rk[i];
-                        bool lower_sel = false, lower_open = false;
-                        if (i > 0) {
-                            const uint32_t sj = sel[i - 1];
-                            if (sj != HG_ST_NONE && rk[i - 1] <= r) {                    // left neighbour: smaller key on ties
-                                lower_sel |= sj == HG_ST_SEL; lower_open |= sj == HG_ST_UND;
-                            }
-                        }
-                        if (i + 1 < m) {
-                            const uint32_t sj = sel[i + 1];
-                            if (sj != HG_ST_NONE && rk[i + 1] < r) {
-                                lower_sel |= sj == HG_ST_SEL; lower_open |= sj == HG_ST_UND;
-                            }
-                        }
-                        if (lower_sel) sel[i] = HG_ST_NOT;
-                        else if (!lower_open) sel[i] = HG_ST_SEL;
-                    }
-                    __syncthreads();
-                }
-                // candidates still undecided cut the round at their key
-                unsigned long long kcut = ~0ull;
-                for (uint32_t i = wlo + lane; i < whi; i += 32)
-                    if (sel[i] == HG_ST_UND) { const unsigned long long k = (unsigned long long)rk[i] << 32 | i; kcut = k < kcut ? k : kcut; }
-                kcut = hg_block_min64(kcut, s_key);
-                // the two pairs every selected merge creates AT ITS TIME: a neighbour two positions away is already merged
-                // iff it is selected with a smaller key.  A created pair of rank <= thr is a hazard.
-                unsigned long long khaz = ~0ull;
-                for (uint32_t i = wlo + lane; i < whi; i += 32) {
-                    if (sel[i] != HG_ST_SEL) continue;
-                    const uint32_t r = rk[i];
-                    const unsigned long long k = (unsigned long long)r << 32 | i;
-                    if (k >= kcut) continue;
-                    uint32_t lf = TK_INF, rt = TK_INF;
-                    if (i >= 1) lf = (i >= 2 && sel[i - 2] == HG_ST_SEL && rk[i - 2] <= r) ? rk[i - 2] : id[i - 1];
-                    if (i + 2 < m) rt = (sel[i + 2] == HG_ST_SEL && rk[i + 2] < r) ? rk[i + 2] : id[i + 2];
-                    uint32_t x, y;
-                    tk_pair_rank2<true>(T, lf, r, r, rt, &x, &y);
-                    rL[i] = x;
-                    rR[i] = y;
-                    if (x <= thr || y <= thr) khaz = k < khaz ? k : khaz;
-                }
-                khaz = hg_block_min64(khaz, s_key);
-                // apply: selected, before the cut, up to and including the first hazard
-                auto applied = [&](uint32_t j) -> bool {
-                    if (sel[j] != HG_ST_SEL) return false;
-                    const unsigned long long k = (unsigned long long)rk[j] << 32 | j;
-                    return k < kcut && k <= khaz;
-                };
-                // parts that survive the round (everything but the right part of an applied merge), counted per warp ...
-                uint32_t kept_w = 0, napp_w = 0, nsel_w = 0;
+            for (int pass = 0; pass < HG_PASSES; ++pass) {
                 for (uint32_t i0 = wlo; i0 < whi; i0 += 32) {
                     const uint32_t i = i0 + lane;
                     const bool in = i < whi;
-                    const bool ap = in && applied(i);
-                    const bool keep = in && !(i > 0 && applied(i - 1));
-                    kept_w += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, keep));
-                    napp_w += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, ap));
-                    nsel_w += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, in && sel[i] == HG_ST_SEL));
-                }
-                if (lane == 0) { s_cnt[warp] = kept_w; s_par[warp] = nsel_w; s_tmp[warp] = napp_w; }
-                __syncthreads();
-                uint32_t run = 0, all_app = 0, all_sel = 0, all_kept = 0;
-                for (uint32_t w = 0; w < NW; ++w) { if (w < warp) run += s_cnt[w]; all_kept += s_cnt[w]; all_sel += s_par[w]; all_app += s_tmp[w]; }
-                // ... and written to their new places
-                for (uint32_t i0 = wlo; i0 < whi; i0 += 32) {
-                    const uint32_t j = i0 + lane;
-                    const bool in = j < whi;
-                    const bool keep = in && !(j > 0 && applied(j - 1));
-                    const uint32_t km = __ballot_sync(0xFFFFFFFFu, keep);
-                    if (keep) {
-                        const uint32_t q = run + (uint32_t)__popc(km & ((1u << lane) - 1u));
-                        uint32_t nr;
-                        if (applied(j)) {
-                            id2[q] = rk[j];
-                            if (j + 2 >= m) nr = TK_INF;
-                            else if (applied(j + 2)) nr = rk[j + 2] >= rk[j] ? rL[j + 2] : rR[j];   // the later of the two merges saw the other's result
-                            else nr = rR[j];
-                        } else {
-                            id2[q] = id[j];
-                            if (j + 1 >= m) nr = TK_INF;
-                            else nr = applied(j + 1) ? rL[j + 1] : rk[j];
+                    const uint32_t r = in ? rk[i] : TK_INF;
+                    uint32_t st = in ? sel[i] : HG_ST_NONE;
+                    // the neighbours outside the row: fixed while the row settles
+                    uint32_t eL_st = HG_ST_NONE, eL_r = 0, eR_st = HG_ST_NONE, eR_r = 0;
+                    if (lane == 0 && i0 > 0) { eL_st = sel[i0 - 1]; eL_r = rk[i0 - 1]; }
+                    if (lane == 31 && i0 + 32 < m) { eR_st = sel[i0 + 32]; eR_r = rk[i0 + 32]; }
+                    for (;;) {
+                        uint32_t sl = __shfl_up_sync(0xFFFFFFFFu, st, 1), rl = __shfl_up_sync(0xFFFFFFFFu, r, 1);
+                        uint32_t sr = __shfl_down_sync(0xFFFFFFFFu, st, 1), rr = __shfl_down_sync(0xFFFFFFFFu, r, 1);
+                        if (lane == 0) { sl = eL_st; rl = eL_r; }
+                        if (lane == 31) { sr = eR_st; rr = eR_r; }
+                        uint32_t nst = st;
+                        if (st == HG_ST_UND) {
+                            const bool lowL = sl != HG_ST_NONE && rl <= r, lowR = sr != HG_ST_NONE && rr < r;   // smaller key: left wins ties
+                            if ((lowL && sl == HG_ST_SEL) || (lowR && sr == HG_ST_SEL)) nst = HG_ST_NOT;
+                            else if (!((lowL && sl == HG_ST_UND) || (lowR && sr == HG_ST_UND))) nst = HG_ST_SEL;
                         }
-                        rk2[q] = nr;
+                        const bool changed = nst != st;
+                        st = nst;
+                        if (!__any_sync(0xFFFFFFFFu, changed)) break;
                     }
-                    run += (uint32_t)__popc(km);
+                    if (in) sel[i] = st;
+                    __syncwarp();
                 }
-                m = all_kept;
-                { uint32_t* z = id; id = id2; id2 = z; z = rk; rk = rk2; rk2 = z; }
                 __syncthreads();
-                if (t == 0) {
-                    atomicAdd(flags + (TKK_S_ROUNDSM - TKK_S_FLAGS), 1u);
-                    atomicAdd(flags + (TKK_S_APPLIEDM - TKK_S_FLAGS), all_app);
-                    if (all_app != all_sel) atomicAdd(flags + (TKK_S_ROUNDSCUT - TKK_S_FLAGS), 1u);
-                }
-                if (all_app == all_sel) delta = delta < (1u << 19) ? delta * 2u : delta;    // went through: widen
-                else delta >>= 2;                                                            // cut: narrow (0 = single-rank rounds)
-                continue;
             }
-            // 2. selection: in every maximal run of adjacent rank-mn pairs take the 1st, 3rd, ...  A chunk's
-            //    summary: all = every pair of the chunk has rank mn; par = parity of the run that ends the chunk
-            uint32_t all = 1, par = 0;
-            for (uint32_t i = lo; i < hi; ++i) { if (rk[i] == mn) par ^= 1u; else { par = 0; all = 0; } }
-            // exclusive scan of (all, par) over the threads: parity of the run that reaches my chunk
-            uint32_t a = all, p = par;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t oa = __shfl_up_sync(0xFFFFFFFFu, a, d), op = __shfl_up_sync(0xFFFFFFFFu, p, d);
-                if (lane >= (uint32_t)d) { p = a ? (p ^ op) : p; a &= oa; }
-            }
-            if (lane == 31) s_par[warp] = a | (p << 1);
-            uint32_t ea = __shfl_up_sync(0xFFFFFFFFu, a, 1), ep = __shfl_up_sync(0xFFFFFFFFu, p, 1);   // exclusive within the warp
-            if (lane == 0) { ea = 1; ep = 0; }
-            __syncthreads();
-            uint32_t wp = 0;                                   // parity of the run that reaches my warp
-            for (uint32_t w = 0; w < warp; ++w) { const uint32_t x = s_par[w]; wp = (x & 1u) ? (wp ^ (x >> 1)) : (x >> 1); }
-            uint32_t entry = ea ? (ep ^ wp) : ep;
-            for (uint32_t i = lo; i < hi; ++i) {
-                if (rk[i] == mn) { rL[i] = entry ? HG_UNSEL : TK_INF; entry ^= 1u; }   // TK_INF: selected, new rank filled in below
-                else { rL[i] = HG_UNSEL; entry = 0; }
-            }
-            __syncthreads();
-            // 3. the two pairs every selected merge creates, as the sequential order would see them
-            uint32_t hazard = TK_INF;
-            for (uint32_t i = lo; i < hi; ++i) {
-                if (rL[i] == HG_UNSEL) continue;
-                const uint32_t lf = i == 0 ? TK_INF : (i >= 2 && rL[i - 2] != HG_UNSEL) ? mn : id[i - 1];
-                const uint32_t rt = i + 2 < m ? id[i + 2] : TK_INF;
+            // candidates still undecided cut the round at their key
+            unsigned long long kcut = ~0ull;
+            for (uint32_t i = wlo + lane; i < whi; i += 32)
+                if (sel[i] == HG_ST_UND) { const unsigned long long k = (unsigned long long)rk[i] << 32 | i; kcut = k < kcut ? k : kcut; }
+            kcut = hg_block_min64(kcut, s_key);
+            // 4. the two pairs every selected merge creates AT ITS TIME: a neighbour two positions away is already merged
+            //    iff it is selected with a smaller key.  A created pair of rank <= thr is a hazard: the sequential loop might
+            //    take it before a later candidate.
+            unsigned long long khaz = ~0ull;
+            for (uint32_t i = wlo + lane; i < whi; i += 32) {
+                if (sel[i] != HG_ST_SEL) continue;
+                const uint32_t r = rk[i];
+                const unsigned long long k = (unsigned long long)r << 32 | i;
+                if (k >= kcut) continue;
+                uint32_t lf = TK_INF, rt = TK_INF;
+                if (i >= 1) lf = (i >= 2 && sel[i - 2] == HG_ST_SEL && rk[i - 2] <= r) ? rk[i - 2] : id[i - 1];
+                if (i + 2 < m) rt = (sel[i + 2] == HG_ST_SEL && rk[i + 2] < r) ? rk[i + 2] : id[i + 2];
                 uint32_t x, y;
-                tk_pair_rank2<true>(T, lf, mn, mn, rt, &x, &y);
+                tk_pair_rank2<true>(T, lf, r, r, rt, &x, &y);
+                rL[i] = x;
                 rR[i] = y;
-                rL[i] = x == HG_UNSEL ? TK_INF : x;           // (ranks are < 2^21: never equal to the marker)
-                if (x <= mn || y <= mn) hazard = min(hazard, i);
+                if (x <= thr || y <= thr) khaz = k < khaz ? k : khaz;
             }
-            // NOTE: rL[i - 2] of a neighbouring chunk may already hold its new rank instead of TK_INF; both mean "selected"
-            const uint32_t cut = hg_block_min(hazard, s_tmp);    // merges after the leftmost hazard wait for the next round
-            // 4. apply the merges at positions <= cut and rebuild the compact arrays
-            uint32_t napp = 0;
-            for (uint32_t i = lo; i < hi; ++i) napp += (rL[i] != HG_UNSEL && i <= cut) ? 1u : 0u;
-            uint32_t inc = napp;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-                if (lane >= (uint32_t)d) inc += o;
+            khaz = hg_block_min64(khaz, s_key);
+            // 5. apply the selected merges before the cut, up to and including the first hazard, and rebuild the compact
+            //    arrays: the parts that survive (everything but the right part of an applied merge) are counted per warp ...
+            auto applied = [&](uint32_t j) -> bool {
+                if (sel[j] != HG_ST_SEL) return false;
+                const unsigned long long k = (unsigned long long)rk[j] << 32 | j;
+                return k < kcut && k <= khaz;
+            };
+            uint32_t kept_w = 0, napp_w = 0, nsel_w = 0;
+            for (uint32_t i0 = wlo; i0 < whi; i0 += 32) {
+                const uint32_t i = i0 + lane;
+                const bool in = i < whi;
+                const bool ap = in && applied(i);
+                const bool keep = in && !(i > 0 && applied(i - 1));
+                kept_w += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, keep));
+                napp_w += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, ap));
+                nsel_w += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, in && sel[i] != HG_ST_NONE));
             }
-            if (lane == 31) s_cnt[warp] = inc;
+            if (lane == 0) { s_cnt[warp] = kept_w; s_par[warp] = nsel_w; s_tmp[warp] = napp_w; }
             __syncthreads();
-            uint32_t before = inc - napp, all_app = 0;
-            for (uint32_t w = 0; w < HG_T / 32; ++w) { if (w < warp) before += s_cnt[w]; all_app += s_cnt[w]; }
-            for (uint32_t j = lo; j < hi; ++j) {
-                const bool app = rL[j] != HG_UNSEL && j <= cut;
-                if (j > 0 && rL[j - 1] != HG_UNSEL && j - 1 <= cut) continue;      // right part of an applied merge: gone
-                const uint32_t q = j - before;
-                uint32_t nr;
-                if (app) {
-                    id2[q] = mn;
-                    if (j + 2 >= m) nr = TK_INF;
-                    else nr = (rL[j + 2] != HG_UNSEL && j + 2 <= cut) ? rL[j + 2] : rR[j];
-                    ++before;
-                } else {
-                    id2[q] = id[j];
-                    if (j + 1 >= m) nr = TK_INF;
-                    else nr = (rL[j + 1] != HG_UNSEL && j + 1 <= cut) ? rL[j + 1] : rk[j];
+            uint32_t run = 0, all_app = 0, all_cand = 0, all_kept = 0;
+            for (uint32_t w = 0; w < NW; ++w) { if (w < warp) run += s_cnt[w]; all_kept += s_cnt[w]; all_cand += s_par[w]; all_app += s_tmp[w]; }
+            // ... and written to their new places
+            for (uint32_t i0 = wlo; i0 < whi; i0 += 32) {
+                const uint32_t j = i0 + lane;
+                const bool in = j < whi;
+                const bool keep = in && !(j > 0 && applied(j - 1));
+                const uint32_t km = __ballot_sync(0xFFFFFFFFu, keep);
+                if (keep) {
+                    const uint32_t q = run + (uint32_t)__popc(km & ((1u << lane) - 1u));
+                    uint32_t nr;
+                    if (applied(j)) {
+                        id2[q] = rk[j];
+                        if (j + 2 >= m) nr = TK_INF;
+                        else if (applied(j + 2)) nr = rk[j + 2] >= rk[j] ? rL[j + 2] : rR[j];   // the later of the two merges saw the other's result
+                        else nr = rR[j];
+                    } else {
+                        id2[q] = id[j];
+                        if (j + 1 >= m) nr = TK_INF;
+                        else nr = applied(j + 1) ? rL[j + 1] : rk[j];
+                    }
+                    rk2[q] = nr;
                 }
-                rk2[q] = nr;
+                run += (uint32_t)__popc(km);
             }
-            m -= all_app;
-            { uint32_t* x = id; id = id2; id2 = x; x = rk; rk = rk2; rk2 = x; }
+            const bool was_cut = kcut != ~0ull || khaz != ~0ull;
+            if (t == 0) {
+                atomicAdd(flags + (delta ? TKK_S_ROUNDSM - TKK_S_FLAGS : TKK_S_ROUNDS1 - TKK_S_FLAGS), 1u);
+                if (delta) atomicAdd(flags + (TKK_S_APPLIEDM - TKK_S_FLAGS), all_app);
+                if (was_cut) atomicAdd(flags + (TKK_S_ROUNDSCUT - TKK_S_FLAGS), 1u);
+            }
+            m = all_kept;
+            { uint32_t* z = id; id = id2; id2 = z; z = rk; rk = rk2; rk2 = z; }
             __syncthreads();
-            // a single-rank round that applies only a few merges (text without repetition): open the window of ranks
-            if (t == 0) atomicAdd(flags + (TKK_S_ROUNDS1 - TKK_S_FLAGS), 1u);
-            if (all_app * 64u < m) delta = 64u;
+            // the window: narrow after a cut; widen when the round went through and candidates are sparse (every merge of a
+            // dense round is already a good round: a run of equal pairs halves)
+            if (was_cut) delta >>= 2;
+            else if (all_cand * 16u < m) delta = delta ? (delta < (1u << 19) ? delta * 2u : delta) : 64u;
         }
         const uint32_t outn = m;
         for (uint32_t i = t; i < m; i += HG_T) if (TK_DBG(recs[r].tok_base + i, pool_words)) out[i] = id[i];

@@ -188,6 +188,28 @@ def test_host_engine_chunks_slices_and_devices(gpu_tok, oracle, tekken_json):
             t.close()
 
 
+def test_one_call_over_all_visible_gpus(gpu_tok, oracle, tekken_json):
+    # tk_encode_batch_multi with one handle per device of the box (skipped on a one-GPU box: the same code path runs
+    # there with several handles on device 0, test_host_engine_chunks_slices_and_devices)
+    import torch
+    from tekken_rs_b200 import encode_batch_multi, set_chunk_bytes
+    n_gpu = torch.cuda.device_count()
+    if n_gpu < 2:
+        pytest.skip("one GPU visible")
+    handles = [gpu_tok] + [Tekkenizer.from_file(tekken_json, device=g) for g in range(1, n_gpu)]
+    try:
+        data, off = corpus.mixed_script_docs(60000, 9)
+        want, woff = oracle.encode_batch_np(data, off, True, True, n_threads=8)
+        for chunk in (1 << 20, 0):
+            set_chunk_bytes(chunk)
+            ids, toff = encode_batch_multi(handles, data, off, True, True)
+            assert np.array_equal(toff, woff) and np.array_equal(ids, want)
+    finally:
+        set_chunk_bytes(0)
+        for t in handles[1:]:
+            t.close()
+
+
 def test_encode_file_streams_shards(gpu_tok, oracle, tmp_path, monkeypatch):
     # text file in, u32 id shard + u64 offsets out, window by window (1 MiB windows here), raw and .npy
     import os
