@@ -880,6 +880,42 @@ __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __
             //    few passes over the regions: chains of dependent candidates -- a run of equal pairs is one, left to
             //    right -- resolve across a whole region per pass.  A state only moves from undecided to decided, so
             //    reading a neighbour's state early or late changes how soon a pair is decided, never what is decided.
+            if (delta == 0) {
+                // One rank: the keys are the positions, so in every maximal run of adjacent candidates the 1st, 3rd, ... merge.
+                // Bit arithmetic on the row's candidate mask (adding a 1 at the start of a run clears the run: runs that
+                // start on an even / odd bit keep their even / odd bits), the parity of the run that enters a row carried
+                // from row to row, the one that enters a region from a scan of (whole region in one run, parity of its
+                // trailing run) over the warps.  A run of 65,536 equal pairs is decided in this one sweep.
+                uint32_t all = 1, par = 0;
+                for (uint32_t i0 = wlo; i0 < whi; i0 += 32) {
+                    const uint32_t i = i0 + lane;
+                    const uint32_t valid = __ballot_sync(0xFFFFFFFFu, i < whi);
+                    const uint32_t B = __ballot_sync(0xFFFFFFFFu, i < whi && sel[i] != HG_ST_NONE);
+                    if (B == valid) par ^= (uint32_t)__popc(B) & 1u;
+                    else { all = 0; par = (uint32_t)(__clz((int)(valid & ~B)) - __clz((int)valid)) & 1u; }     // ones above the highest zero
+                }
+                if (lane == 0) s_par[warp] = all | (par << 1);
+                __syncthreads();
+                uint32_t c = 0;                                      // parity of the run that reaches my region
+                for (uint32_t w = 0; w < warp; ++w) { const uint32_t x = s_par[w]; c = (x & 1u) ? (c ^ (x >> 1)) : (x >> 1); }
+                for (uint32_t i0 = wlo; i0 < whi; i0 += 32) {
+                    const uint32_t i = i0 + lane;
+                    const bool in = i < whi;
+                    const uint32_t valid = __ballot_sync(0xFFFFFFFFu, in);
+                    const uint32_t B = __ballot_sync(0xFFFFFFFFu, in && sel[i] != HG_ST_NONE);
+                    uint32_t even_starts = B & ~(B << 1) & 0x55555555u;
+                    if (c && (B & 1u)) even_starts &= ~1u;           // the run continues from the row before with an odd length so far
+                    const uint32_t r_even = B & ~(B + even_starts), r_odd = B & ~r_even;
+                    const uint32_t pick = (r_even & 0x55555555u) | (r_odd & 0xAAAAAAAAu);
+                    if (in && ((B >> lane) & 1u)) sel[i] = ((pick >> lane) & 1u) ? HG_ST_SEL : HG_ST_NOT;
+                    // parity of the run that leaves the row
+                    const uint32_t top = 31u - (uint32_t)__clz((int)valid);
+                    if (!((B >> top) & 1u)) c = 0;
+                    else if (B == valid) c ^= (uint32_t)__popc(B) & 1u;
+                    else c = (uint32_t)(__clz((int)(valid & ~B)) - __clz((int)valid)) & 1u;
+                }
+                __syncthreads();
+            } else
 #pragma unroll 1
             for (int pass = 0; pass < HG_PASSES; ++pass) {
                 for (uint32_t i0 = wlo; i0 < whi; i0 += 32) {
