@@ -757,7 +757,7 @@ __global__ void __launch_bounds__(LM_WARPS * 32) longmerge_warp_kernel(const uin
 // each computes the pairs its merge creates at its time, and the round is cut at the first created pair that could
 // overtake a later candidate.  64 KiB of random letters: 15-30 rounds instead of 40,000 dependent merges
 // (verified against the literal loop in oracle/research/multirank_rounds.py, incl. shuffled-rank vocabularies).
-#define HG_T 512
+#define HG_T 1024                   // 32 warps per piece: a round is a handful of latency-bound sweeps over the parts
 #define HG_ARRAYS 7                 // id / rank, double-buffered, + the two new-rank arrays of a round + the selection state
 #define HG_UNSEL 0xFFFFFFFEu        // rL marker: pair not selected this round
 
@@ -796,6 +796,7 @@ __device__ __forceinline__ unsigned long long hg_block_min64(unsigned long long 
 #define HG_ST_UND 1u
 #define HG_ST_SEL 2u
 #define HG_ST_NOT 3u
+#define HG_ST_APP 4u                   // selected and applied this round (before the cut, up to the first hazard)
 #define HG_PASSES 4
 
 __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __restrict__ data, TkDeviceTables T,
@@ -866,13 +867,24 @@ __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __
             const uint32_t wlo = warp * wsz < m ? warp * wsz : m, whi = wlo + wsz < m ? wlo + wsz : m;
             // 1. lowest pair rank of the piece
             uint32_t mine = TK_INF;
-            for (uint32_t i = wlo + lane; i < whi; i += 32) mine = min(mine, rk[i]);
+            for (uint32_t i = wlo + lane; i < whi; i += 128) {          // four rows per trip: four loads in flight
+                const uint32_t a = rk[i], b = i + 32 < whi ? rk[i + 32] : TK_INF, c = i + 64 < whi ? rk[i + 64] : TK_INF,
+                               d = i + 96 < whi ? rk[i + 96] : TK_INF;
+                mine = min(min(mine, a), min(b, min(c, d)));
+            }
             const uint32_t mn = hg_block_min(mine, s_tmp);
             if (mn == TK_INF) break;
             // 2. candidates: pairs of rank <= thr.  The sequential loop would take them in the order of their keys
             //    (rank, position).
             const uint32_t thr = mn + delta < TK_ID_MASK ? mn + delta : TK_ID_MASK;
-            for (uint32_t i = wlo + lane; i < whi; i += 32) sel[i] = rk[i] <= thr ? HG_ST_UND : HG_ST_NONE;
+            for (uint32_t i = wlo + lane; i < whi; i += 128) {
+                const uint32_t a = rk[i], b = i + 32 < whi ? rk[i + 32] : TK_INF, c = i + 64 < whi ? rk[i + 64] : TK_INF,
+                               d = i + 96 < whi ? rk[i + 96] : TK_INF;
+                sel[i] = a <= thr ? HG_ST_UND : HG_ST_NONE;
+                if (i + 32 < whi) sel[i + 32] = b <= thr ? HG_ST_UND : HG_ST_NONE;
+                if (i + 64 < whi) sel[i + 64] = c <= thr ? HG_ST_UND : HG_ST_NONE;
+                if (i + 96 < whi) sel[i + 96] = d <= thr ? HG_ST_UND : HG_ST_NONE;
+            }
             __syncthreads();
             // 3. selection = what the sequential loop merges if no merge creates a pair of rank <= thr: by key order, a
             //    candidate merges unless a neighbouring candidate (they share a part) with a smaller key merged.  A local
@@ -949,8 +961,19 @@ __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __
             }
             // candidates still undecided cut the round at their key
             unsigned long long kcut = ~0ull;
-            for (uint32_t i = wlo + lane; i < whi; i += 32)
-                if (sel[i] == HG_ST_UND) { const unsigned long long k = (unsigned long long)rk[i] << 32 | i; kcut = k < kcut ? k : kcut; }
+            if (delta) {                                                  // (one-rank rounds decide everything)
+                for (uint32_t i = wlo + lane; i < whi; i += 128) {
+                    uint32_t st4[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) st4[u] = i + 32u * u < whi ? sel[i + 32u * u] : HG_ST_NONE;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (st4[u] == HG_ST_UND) {
+                            const unsigned long long k = (unsigned long long)rk[i + 32u * u] << 32 | (i + 32u * u);
+                            kcut = k < kcut ? k : kcut;
+                        }
+                }
+            }
             kcut = hg_block_min64(kcut, s_key);
             // 4. the two pairs every selected merge creates AT ITS TIME: a neighbour two positions away is already merged
             //    iff it is selected with a smaller key.  A created pair of rank <= thr is a hazard: the sequential loop might
@@ -971,22 +994,30 @@ __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __
                 if (x <= thr || y <= thr) khaz = k < khaz ? k : khaz;
             }
             khaz = hg_block_min64(khaz, s_key);
-            // 5. apply the selected merges before the cut, up to and including the first hazard, and rebuild the compact
-            //    arrays: the parts that survive (everything but the right part of an applied merge) are counted per warp ...
-            auto applied = [&](uint32_t j) -> bool {
-                if (sel[j] != HG_ST_SEL) return false;
-                const unsigned long long k = (unsigned long long)rk[j] << 32 | j;
-                return k < kcut && k <= khaz;
-            };
+            // 5. mark the merges that are applied: selected, before the cut, up to and including the first hazard
+            for (uint32_t i = wlo + lane; i < whi; i += 128) {
+                uint32_t st4[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) st4[u] = i + 32u * u < whi ? sel[i + 32u * u] : HG_ST_NONE;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (st4[u] == HG_ST_SEL) {
+                        const unsigned long long k = (unsigned long long)rk[i + 32u * u] << 32 | (i + 32u * u);
+                        if (k < kcut && k <= khaz) sel[i + 32u * u] = HG_ST_APP;
+                    }
+            }
+            __syncthreads();
+            // 6. rebuild the compact arrays: the parts that survive (everything but the right part of an applied merge) are
+            //    counted per warp ...
             uint32_t kept_w = 0, napp_w = 0, nsel_w = 0;
             for (uint32_t i0 = wlo; i0 < whi; i0 += 32) {
                 const uint32_t i = i0 + lane;
-                const bool in = i < whi;
-                const bool ap = in && applied(i);
-                const bool keep = in && !(i > 0 && applied(i - 1));
-                kept_w += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, keep));
-                napp_w += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, ap));
-                nsel_w += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, in && sel[i] != HG_ST_NONE));
+                const uint32_t st = i < whi ? sel[i] : HG_ST_NONE;
+                uint32_t stl = __shfl_up_sync(0xFFFFFFFFu, st, 1);
+                if (lane == 0) stl = i0 > 0 ? sel[i0 - 1] : HG_ST_NONE;
+                kept_w += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, i < whi && stl != HG_ST_APP));
+                napp_w += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, st == HG_ST_APP));
+                nsel_w += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, st != HG_ST_NONE));
             }
             if (lane == 0) { s_cnt[warp] = kept_w; s_par[warp] = nsel_w; s_tmp[warp] = napp_w; }
             __syncthreads();
@@ -996,20 +1027,26 @@ __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __
             for (uint32_t i0 = wlo; i0 < whi; i0 += 32) {
                 const uint32_t j = i0 + lane;
                 const bool in = j < whi;
-                const bool keep = in && !(j > 0 && applied(j - 1));
+                const uint32_t st = in ? sel[j] : HG_ST_NONE;
+                uint32_t stl = __shfl_up_sync(0xFFFFFFFFu, st, 1), st1 = __shfl_down_sync(0xFFFFFFFFu, st, 1), st2 = __shfl_down_sync(0xFFFFFFFFu, st, 2);
+                if (lane == 0) stl = i0 > 0 ? sel[i0 - 1] : HG_ST_NONE;
+                if (lane == 31) st1 = j + 1 < m ? sel[j + 1] : HG_ST_NONE;
+                if (lane >= 30) st2 = j + 2 < m ? sel[j + 2] : HG_ST_NONE;
+                const bool keep = in && stl != HG_ST_APP;
                 const uint32_t km = __ballot_sync(0xFFFFFFFFu, keep);
                 if (keep) {
                     const uint32_t q = run + (uint32_t)__popc(km & ((1u << lane) - 1u));
                     uint32_t nr;
-                    if (applied(j)) {
-                        id2[q] = rk[j];
+                    if (st == HG_ST_APP) {
+                        const uint32_t r = rk[j];
+                        id2[q] = r;
                         if (j + 2 >= m) nr = TK_INF;
-                        else if (applied(j + 2)) nr = rk[j + 2] >= rk[j] ? rL[j + 2] : rR[j];   // the later of the two merges saw the other's result
+                        else if (st2 == HG_ST_APP) nr = rk[j + 2] >= r ? rL[j + 2] : rR[j];   // the later of the two merges saw the other's result
                         else nr = rR[j];
                     } else {
                         id2[q] = id[j];
                         if (j + 1 >= m) nr = TK_INF;
-                        else nr = applied(j + 1) ? rL[j + 1] : rk[j];
+                        else nr = st1 == HG_ST_APP ? rL[j + 1] : rk[j];
                     }
                     rk2[q] = nr;
                 }
