@@ -930,15 +930,19 @@ __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __
             } else
 #pragma unroll 1
             for (int pass = 0; pass < HG_PASSES; ++pass) {
+                // the row being settled lives in registers; the next row is loaded before this one is settled, and the two
+                // neighbours outside a row come from registers as well (the settled lane 31 of the row before, the freshly
+                // loaded lane 0 of the row after), so a row never waits for memory
+                uint32_t cur_i = wlo + lane;
+                uint32_t r = cur_i < whi ? rk[cur_i] : TK_INF, st = cur_i < whi ? sel[cur_i] : HG_ST_NONE;
+                uint32_t eL_st = HG_ST_NONE, eL_r = 0;
+                if (wlo > 0 && wlo < whi) { eL_st = sel[wlo - 1]; eL_r = rk[wlo - 1]; }
                 for (uint32_t i0 = wlo; i0 < whi; i0 += 32) {
-                    const uint32_t i = i0 + lane;
-                    const bool in = i < whi;
-                    const uint32_t r = in ? rk[i] : TK_INF;
-                    uint32_t st = in ? sel[i] : HG_ST_NONE;
-                    // the neighbours outside the row: fixed while the row settles
-                    uint32_t eL_st = HG_ST_NONE, eL_r = 0, eR_st = HG_ST_NONE, eR_r = 0;
-                    if (lane == 0 && i0 > 0) { eL_st = sel[i0 - 1]; eL_r = rk[i0 - 1]; }
-                    if (lane == 31 && i0 + 32 < m) { eR_st = sel[i0 + 32]; eR_r = rk[i0 + 32]; }
+                    const uint32_t nxt = i0 + 32u + lane;
+                    const bool take = nxt < whi || (lane == 0 && nxt < m);      // lane 0 also looks one part past the region
+                    const uint32_t r_n = take ? rk[nxt] : TK_INF, st_n = take ? sel[nxt] : HG_ST_NONE;
+                    const uint32_t eR_st = __shfl_sync(0xFFFFFFFFu, st_n, 0), eR_r = __shfl_sync(0xFFFFFFFFu, r_n, 0);
+                    const uint32_t st_in = st;
                     for (;;) {
                         uint32_t sl = __shfl_up_sync(0xFFFFFFFFu, st, 1), rl = __shfl_up_sync(0xFFFFFFFFu, r, 1);
                         uint32_t sr = __shfl_down_sync(0xFFFFFFFFu, st, 1), rr = __shfl_down_sync(0xFFFFFFFFu, r, 1);
@@ -954,8 +958,11 @@ __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __
                         st = nst;
                         if (!__any_sync(0xFFFFFFFFu, changed)) break;
                     }
-                    if (in) sel[i] = st;
-                    __syncwarp();
+                    if (st != st_in) sel[i0 + lane] = st;
+                    eL_st = __shfl_sync(0xFFFFFFFFu, st, 31);
+                    eL_r = __shfl_sync(0xFFFFFFFFu, r, 31);
+                    r = nxt < whi ? r_n : TK_INF;
+                    st = nxt < whi ? st_n : HG_ST_NONE;
                 }
                 __syncthreads();
             }
