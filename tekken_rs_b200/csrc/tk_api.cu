@@ -816,6 +816,7 @@ int plan_chunks(const uint8_t* data, const uint64_t* doc_off, size_t n_docs, uin
             const uint64_t end = doc_off[d + 1];
             bool first = true;
             while (pos < end) {
+                if (!first && out.size() % n_devices == 0) chunk_bytes = std::min(full_chunk, chunk_bytes * 2);   // slices grow like chunks do
                 uint64_t cut = end;
                 if (end - pos > big) {
                     const uint64_t target = pos + chunk_bytes, lo = pos + chunk_bytes / 2;
@@ -1924,7 +1925,7 @@ extern "C" size_t tk_last_encode_counters(const tk_tokenizer* t, uint64_t* out, 
     uint64_t v[TKK_N_CLASSES + 8];
     for (int c = 0; c < TKK_N_CLASSES; ++c) v[c] = small[tkk::TKK_S_QN + c];
     v[TKK_N_CLASSES] = small[tkk::TKK_S_NLONG];
-    v[TKK_N_CLASSES + 1] = small[tkk::TKK_S_NHUGE];
+    v[TKK_N_CLASSES + 1] = small[tkk::TKK_S_NHUGE] + small[tkk::TKK_S_NMID];
     memcpy(&v[TKK_N_CLASSES + 2], small + tkk::TKK_S_PAIRLOOK, 8);
     memcpy(&v[TKK_N_CLASSES + 3], small + tkk::TKK_S_BPLOOK, 8);
     v[TKK_N_CLASSES + 4] = small[tkk::TKK_S_ROUNDS1]; v[TKK_N_CLASSES + 5] = small[tkk::TKK_S_ROUNDSM];

@@ -669,6 +669,7 @@ __global__ void longmark_kernel(const uint32_t* __restrict__ start_mask, uint64_
 // in shared memory (<= TK_MED_MAX bytes) or queue it for the block-level kernel.
 // =====================================================================================================
 #define LM_WARPS 4
+#define HG_SPLIT 8192u            // block-level pieces up to this many bytes get 8 warps, longer ones 32 (see longmerge_block_kernel)
 
 __device__ __forceinline__ uint64_t piece_end(const uint32_t* __restrict__ start_mask, uint64_t pos, uint64_t n_windows, uint64_t n) {
     // position of the next set bit after pos (the sentinel at n guarantees there is one; the walk is bounded by
@@ -696,6 +697,7 @@ __global__ void __launch_bounds__(LM_WARPS * 32) longmerge_warp_kernel(const uin
                                                                        const uint32_t* __restrict__ n_long, uint32_t* __restrict__ pool,
                                                                        unsigned long long* __restrict__ pool_cursor,
                                                                        uint32_t* __restrict__ huge_list, uint32_t* __restrict__ n_huge,
+                                                                       uint32_t* __restrict__ mid_list, uint32_t* __restrict__ n_mid,
                                                                        uint32_t* __restrict__ work_counter,
                                                                        unsigned long long* __restrict__ tile_count,
                                                                        uint64_t n_windows, uint64_t n, const uint32_t* __restrict__ flags) {
@@ -730,7 +732,11 @@ __global__ void __launch_bounds__(LM_WARPS * 32) longmerge_warp_kernel(const uin
                 count = tk_bpe_warp(T, S[warp], data + pos, (uint32_t)len, pool + base);
             }
         } else if (lane == 0) {
-            { const uint32_t hslot = atomicAdd(n_huge, 1u); if (TK_DBG(hslot, max_long)) huge_list[hslot] = r; }
+            {   // block-level pieces: two lists by size (the kernel that takes them runs with 8 or 32 warps per piece)
+                const bool mid = len <= HG_SPLIT;
+                const uint32_t hslot = atomicAdd(mid ? n_mid : n_huge, 1u);
+                if (TK_DBG(hslot, max_long)) (mid ? mid_list : huge_list)[hslot] = r;
+            }
         }
         if (lane == 0) {
             recs[r].len = len;
@@ -757,10 +763,15 @@ __global__ void __launch_bounds__(LM_WARPS * 32) longmerge_warp_kernel(const uin
 // each computes the pairs its merge creates at its time, and the round is cut at the first created pair that could
 // overtake a later candidate.  64 KiB of random letters: 15-30 rounds instead of 40,000 dependent merges
 // (verified against the literal loop in oracle/research/multirank_rounds.py, incl. shuffled-rank vocabularies).
-#define HG_T 1024                   // 32 warps per piece: a round is a handful of latency-bound sweeps over the parts
+// Threads per piece: a round is a handful of latency-bound sweeps over the parts, so a piece of tens of KiB gets a
+// whole SM (32 warps); pieces up to HG_SPLIT bytes -- whitespace runs, long identifiers: there can be thousands in a
+// batch -- get 8 warps each, eight pieces per SM.
+#define HG_T_BIG 1024
+#define HG_T_MID 256
 #define HG_ARRAYS 7                 // id / rank, double-buffered, + the two new-rank arrays of a round + the selection state
 #define HG_UNSEL 0xFFFFFFFEu        // rL marker: pair not selected this round
 
+template <int HG_T>
 __device__ __forceinline__ uint32_t hg_block_min(uint32_t v, uint32_t* s_tmp) {
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     v = __reduce_min_sync(0xFFFFFFFFu, v);
@@ -773,6 +784,7 @@ __device__ __forceinline__ uint32_t hg_block_min(uint32_t v, uint32_t* s_tmp) {
 }
 
 // block-wide minimum of a 64-bit key (rank << 32 | position)
+template <int HG_T>
 __device__ __forceinline__ unsigned long long hg_block_min64(unsigned long long v, unsigned long long* s_tmp64) {
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -799,6 +811,7 @@ __device__ __forceinline__ unsigned long long hg_block_min64(unsigned long long 
 #define HG_ST_APP 4u                   // selected and applied this round (before the cut, up to the first hazard)
 #define HG_PASSES 4
 
+template <int HG_T>
 __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __restrict__ data, TkDeviceTables T,
                                                                TkkLongRec* __restrict__ recs, const uint32_t* __restrict__ huge_list,
                                                                const uint32_t* __restrict__ n_huge, uint32_t* __restrict__ pool,
@@ -872,7 +885,7 @@ __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __
                                d = i + 96 < whi ? rk[i + 96] : TK_INF;
                 mine = min(min(mine, a), min(b, min(c, d)));
             }
-            const uint32_t mn = hg_block_min(mine, s_tmp);
+            const uint32_t mn = hg_block_min<HG_T>(mine, s_tmp);
             if (mn == TK_INF) break;
             // 2. candidates: pairs of rank <= thr.  The sequential loop would take them in the order of their keys
             //    (rank, position).
@@ -981,7 +994,7 @@ __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __
                         }
                 }
             }
-            kcut = hg_block_min64(kcut, s_key);
+            kcut = hg_block_min64<HG_T>(kcut, s_key);
             // 4. the two pairs every selected merge creates AT ITS TIME: a neighbour two positions away is already merged
             //    iff it is selected with a smaller key.  A created pair of rank <= thr is a hazard: the sequential loop might
             //    take it before a later candidate.
@@ -1000,7 +1013,7 @@ __global__ void __launch_bounds__(HG_T) longmerge_block_kernel(const uint8_t* __
                 rR[i] = y;
                 if (x <= thr || y <= thr) khaz = k < khaz ? k : khaz;
             }
-            khaz = hg_block_min64(khaz, s_key);
+            khaz = hg_block_min64<HG_T>(khaz, s_key);
             // 5. mark the merges that are applied: selected, before the cut, up to and including the first hazard
             for (uint32_t i = wlo + lane; i < whi; i += 128) {
                 uint32_t st4[4];
@@ -1786,7 +1799,7 @@ size_t encode_workspace_bytes(uint64_t n, uint64_t n_docs, EncodeLayout* L) {
     }
     l.max_long = n / (TK_LANE_MAX + 1) + 2;
     l.off_recs = take(l.max_long * sizeof(TkkLongRec));
-    l.off_huge = take(l.max_long * 4);
+    l.off_huge = take(l.max_long * 8);                  // two lists: pieces of more than HG_SPLIT bytes, and the others
     l.off_pool = take((n + 16) * 4);
     (void)n_docs;
     l.total = off;
@@ -1883,6 +1896,8 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
     uint32_t* n_huge = small + TKK_S_NHUGE;
     uint32_t* wc_long = small + TKK_S_WC_LONG;
     uint32_t* wc_huge = small + TKK_S_WC_HUGE;
+    uint32_t* n_mid = small + TKK_S_NMID;
+    uint32_t* wc_mid = small + TKK_S_WC_MID;
     uint32_t* q_n = small + TKK_S_QN;
     uint32_t* q_w = small + TKK_S_QW;
     unsigned long long* pool_cursor = (unsigned long long*)(small + TKK_S_POOLCUR);
@@ -1941,10 +1956,13 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
         uint64_t blocks = ceil_div(L.max_long, LM_WARPS);
         const uint64_t cap = (uint64_t)sm_count * 12;
         if (blocks > cap) blocks = cap;
+        uint32_t* mid = huge + L.max_long;
         CK(launch_chain(longmerge_warp_kernel, (unsigned)blocks, LM_WARPS * 32, 0, st, d_data, start, T, recs, n_long, pool, pool_cursor, huge,
-                                                                        n_huge, wc_long, tile_count, L.n_windows, n, flags));
+                                                                        n_huge, mid, n_mid, wc_long, tile_count, L.n_windows, n, flags));
         uint64_t hb = L.max_long < (uint64_t)(2 * sm_count) ? L.max_long : (uint64_t)(2 * sm_count);
-        CK(launch_chain(longmerge_block_kernel, (unsigned)hb, HG_T, 0, st, d_data, T, recs, huge, n_huge, pool, d_scratch, scratch_cap,
+        CK(launch_chain(longmerge_block_kernel<HG_T_MID>, (unsigned)std::min<uint64_t>(L.max_long, (uint64_t)sm_count * 8), HG_T_MID, 0, st, d_data, T, recs,
+                        mid, n_mid, pool, d_scratch, scratch_cap, scratch_cursor, wc_mid, flags, tile_count));
+        CK(launch_chain(longmerge_block_kernel<HG_T_BIG>, (unsigned)hb, HG_T_BIG, 0, st, d_data, T, recs, huge, n_huge, pool, d_scratch, scratch_cap,
                                                              scratch_cursor, wc_huge, flags, tile_count));
     }
     if (timer) timer->mark(st, "lookup");

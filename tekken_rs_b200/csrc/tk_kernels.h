@@ -26,7 +26,9 @@ enum {
     TKK_S_NHUGE = 3,
     TKK_S_WC_LONG = 4,
     TKK_S_WC_HUGE = 5,
-    TKK_S_TICKET = 6,
+    TKK_S_TICKET = 6,    // (decode)
+    TKK_S_NMID = 6,      // (encode) block-level pieces of at most HG_SPLIT bytes
+    TKK_S_WC_MID = 7,
     TKK_S_ERRPOS = 8,    // u64
     TKK_S_POOLCUR = 10,  // u64
     TKK_S_SCRCUR = 12,   // u64
