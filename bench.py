@@ -262,11 +262,24 @@ def run_reference(args):
         "e2e": {"value": gbs, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
     return 0
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
+
+_JSON_FD = None
+
+
+def emit_line(line):
+    """The one JSON line, on the process's original stdout."""
+    text = json.dumps(line) + "\n"
+    if _JSON_FD is None:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, text.encode())
+
 
 class Ctx:
     """torch / torch.distributed plumbing shared by the GPU legs."""
@@ -564,7 +577,7 @@ def run_ours(args):
         line["latency"] = latency_table(tk, lib, path)
     cx.close()
     if cx.rank == 0:
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     return 0
 
 
@@ -795,7 +808,7 @@ def run_roundtrip(args, cx, tk, lib, path):
     }
     cx.close()
     if cx.rank == 0:
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     return 0 if all_ok else 1
 
 
@@ -827,6 +840,12 @@ def main():
         s.close()
         return subprocess.call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
                                 "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:])
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        # libraries below us write to stdout (NCCL prints its version banner there): keep fd 1 for the ONE JSON line
+        global _JSON_FD
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
