@@ -341,7 +341,7 @@ static int finish_handle(tk_tokenizer* t, int device, int split_mode, tk_tokeniz
             }
         }
         if (err == cudaSuccess) err = upload(t, h.vocab_pad16, (const void**)&T.vocab_pad16);
-        if (err == cudaSuccess) err = upload(t, h.vocab_len8, (const void**)&T.vocab_len);
+        if (err == cudaSuccess) err = upload(t, h.vocab_e16, (const void**)&T.vocab_e16);
         if (err == cudaSuccess) err = upload(t, h.vocab_bytes, (const void**)&T.vocab_bytes);
         if (err == cudaSuccess) err = upload(t, h.vocab_off, (const void**)&T.vocab_off);
         if (err == cudaSuccess) err = upload(t, h.special_bytes, (const void**)&T.special_bytes);

@@ -5,10 +5,10 @@
 // (:529-544), ordinary runs are concatenated from the rank -> bytes table and must be valid UTF-8
 // as a run (CoreBPE::decode -> String::from_utf8, :552-555).  Here:
 //   D0 tokmark    sequence-start bitmask over id positions (validates tok_off)
-//   D1 gather     per 2048-id tile: lengths, block scan, decoupled look-back prefix over tiles,
-//                 byte copy, sequence byte offsets, run-boundary bits, unknown-id / Raise errors
-//   D2 validate   one thread per 32 output bytes: strict UTF-8 with run boundaries (same window
-//                 classifier the encoder uses)
+//   D1 gather     per 2048-id tile: table cells (bytes + length), block scan, text assembled in shared memory,
+//                 decoupled look-back prefix over tiles, sequence byte offsets, run-boundary bits,
+//                 unknown-id / Raise errors, word copy to the output
+//   D2 validate   one thread per 32 output bytes: strict UTF-8 with run boundaries, as flag arithmetic on words
 //   D3 status     per sequence: the error the reference would have returned first
 #include "tk_kernels.h"
 
@@ -19,8 +19,6 @@
 namespace tkk {
 
 #define DC_T 256
-#define DC_PER 8
-#define DC_TILE (DC_T * DC_PER)
 
 struct DocErr {
     unsigned long long unk_tok, sp_tok, sp_byte, utf_byte;
@@ -54,22 +52,63 @@ __device__ __forceinline__ void mark_boundary(uint32_t* __restrict__ bmask, uint
     if (o <= cap) atomicOr(bmask + (o >> 5), 1u << (o & 31));
 }
 
-#define DC_BUF 12288      // bytes of a tile's text staged in shared memory (larger tiles write straight to global memory)
+// ---- D1: gather ------------------------------------------------------------------------------------------------------
+// A tile is DC_T threads x PER consecutive ids.  Order of work inside a block:
+//   1. ids -> the first 8 bytes of one 16-byte table cell per id (length + 7 bytes): the lengths for the scan and the
+//      bytes for the copy come from the same load, issued for all of a thread's ids at once;
+//   2. block scan of the lengths; the tile's total is published for the tiles behind it;
+//   3. the text of the tile is assembled in shared memory at tile-relative positions.  A thread's tokens are adjacent in
+//      the text, so it shifts them into a 64-bit accumulator and stores whole words; the one or two words it shares with
+//      its neighbours are OR-ed into the (zeroed) buffer;
+//   4. only now warp 0 collects the prefix of the tiles before this one (decoupled look-back) -- by then it is usually
+//      there, and the other warps were not waiting for it while they assembled;
+//   5. the rare work that needs absolute positions (sequence starts, special and unknown ids) and the copy to the output
+//      in aligned words, shifted by the output's phase.
+// A tile whose text is larger than the staging buffer (more than 7 bytes per id) is written to the output byte by byte.
 
-// Copy l bytes of a token into the tile's staging buffer or, for an oversized tile, to the output.
-__device__ __forceinline__ void dc_put(uint8_t* __restrict__ buf, bool fits, uint32_t p, uint8_t* __restrict__ out, uint64_t o,
-                                       uint64_t out_cap, const uint8_t* __restrict__ src, uint32_t l) {
-    if (fits) {
-        for (uint32_t j = 0; j < l; ++j) buf[p + j] = __ldg(src + j);
-    } else if (o + l <= out_cap) {
-        for (uint32_t j = 0; j < l; ++j) out[o + j] = __ldg(src + j);
-    }
+__device__ __forceinline__ uint32_t dc_slow_len(const TkDeviceTables& T, int policy, const uint32_t* __restrict__ ids, uint64_t i,
+                                                uint64_t n_ids) {
+    if (i >= n_ids) return 0u;
+    const uint32_t v = __ldg(ids + i);
+    if (v < T.num_special) return policy == TK_POLICY_KEEP ? T.special_off[v + 1] - T.special_off[v] : 0u;
+    const uint32_t r = v - T.num_special;
+    return r < T.n_vocab ? T.vocab_off[r + 1] - T.vocab_off[r] : 0u;     // <= 65,535 (checked when the file is loaded)
 }
 
-#ifndef DC_MINB
-#define DC_MINB 8      // 32 registers (measured: 5.4 ms; 5.8 ms at 40 registers, 7.8 ms uncapped at 71)
+// bytes of a token that is not in a table cell (longer than 15 bytes, or a special string under Keep); null if none
+__device__ __forceinline__ const uint8_t* dc_slow_bytes(const TkDeviceTables& T, int policy, uint32_t v) {
+    if (v < T.num_special) return policy == TK_POLICY_KEEP ? T.special_bytes + T.special_off[v] : nullptr;
+    const uint32_t r = v - T.num_special;
+    return r < T.n_vocab ? T.vocab_bytes + T.vocab_off[r] : nullptr;
+}
+
+struct DcStream {
+    unsigned long long acc;    // bytes not stored yet, from byte `lo` of the word at wpos upwards
+    uint32_t wpos;             // tile-relative byte position of the word being filled (multiple of 4)
+    uint32_t fill;             // bytes of that word that are decided (the ones below lo belong to somebody else)
+    uint32_t lo;
+};
+__device__ __forceinline__ void dc_append(uint32_t* __restrict__ bufw, DcStream& s, uint32_t w, uint32_t nb) {
+    s.acc |= (unsigned long long)w << (8u * s.fill);
+    s.fill += nb;
+    if (s.fill >= 4u) {
+        if (s.lo) atomicOr(bufw + (s.wpos >> 2), (uint32_t)s.acc);      // shared with the thread before me
+        else bufw[s.wpos >> 2] = (uint32_t)s.acc;
+        s.wpos += 4u; s.acc >>= 32; s.fill -= 4u; s.lo = 0u;
+    }
+}
+__device__ __forceinline__ void dc_flush(uint32_t* __restrict__ bufw, const DcStream& s) {
+    if (s.fill > s.lo) atomicOr(bufw + (s.wpos >> 2), (uint32_t)s.acc);  // a partial word: the rest is somebody else's
+}
+
+#ifndef DC_PER
+#define DC_PER 8
 #endif
-__global__ void __launch_bounds__(DC_T, DC_MINB) decode_gather_kernel(const uint32_t* __restrict__ ids, uint64_t n_ids,
+#ifndef DC_MINB
+#define DC_MINB 4
+#endif
+template <int PER, int MINB>
+__global__ void __launch_bounds__(DC_T, MINB) decode_gather_kernel(const uint32_t* __restrict__ ids, uint64_t n_ids,
                                                              const uint64_t* __restrict__ tok_off, uint64_t off_base, uint64_t n_docs,
                                                              const uint32_t* __restrict__ tds, const uint32_t* __restrict__ seq_first,
                                                              int policy, TkDeviceTables T,
@@ -78,42 +117,50 @@ __global__ void __launch_bounds__(DC_T, DC_MINB) decode_gather_kernel(const uint
                                                              DocErr* __restrict__ docerr, unsigned long long* __restrict__ tile_state,
                                                              uint32_t* __restrict__ ticket, unsigned long long* __restrict__ total_out,
                                                              uint32_t* __restrict__ flags) {
-    __shared__ __align__(16) uint8_t buf[DC_BUF + 32];
+    constexpr uint32_t TILE = DC_T * PER, BUF = TILE * 7u, BUFW = BUF / 4u + 4u;
+    static_assert(BUFW % 4u == 0u && 32 % PER == 0 && PER % 4 == 0, "tile shape");
+    __shared__ __align__(16) uint32_t bufw[BUFW];
     __shared__ uint32_t wsum[DC_T / 32];
     __shared__ unsigned long long s_base;
     __shared__ uint32_t s_tile;
     const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
     if (t == 0) s_tile = atomicAdd(ticket, 1u);
+    for (uint32_t c = t; c < BUFW / 4u; c += DC_T) reinterpret_cast<uint4*>(bufw)[c] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
     const uint32_t tile = s_tile;
-    const uint64_t i0 = (uint64_t)tile * DC_TILE + (uint64_t)t * DC_PER;
-    uint32_t id[DC_PER], len[DC_PER];
-    uint32_t sum = 0;
+    const uint64_t i0 = (uint64_t)tile * TILE + (uint64_t)t * PER;
+    // 1. the first half of one table cell per id: the length and 7 bytes
+    uint2 e[PER];
     {
-        // 8 consecutive ids per thread: two 16-byte loads when they are all there
-        uint32_t raw[DC_PER];
-        if (i0 + DC_PER <= n_ids && ((uintptr_t)ids & 15u) == 0) {
-            const uint4 a = __ldg(reinterpret_cast<const uint4*>(ids + i0)), b = __ldg(reinterpret_cast<const uint4*>(ids + i0) + 1);
-            raw[0] = a.x; raw[1] = a.y; raw[2] = a.z; raw[3] = a.w; raw[4] = b.x; raw[5] = b.y; raw[6] = b.z; raw[7] = b.w;
+        uint32_t raw[PER];
+        if (i0 + PER <= n_ids && ((uintptr_t)ids & 15u) == 0) {
+#pragma unroll
+            for (int q = 0; q < PER / 4; ++q) {
+                const uint4 a = __ldg(reinterpret_cast<const uint4*>(ids + i0) + q);
+                raw[4 * q] = a.x; raw[4 * q + 1] = a.y; raw[4 * q + 2] = a.z; raw[4 * q + 3] = a.w;
+            }
         } else {
 #pragma unroll
-            for (int k = 0; k < DC_PER; ++k) raw[k] = i0 + k < n_ids ? __ldg(ids + i0 + k) : 0u;
+            for (int k = 0; k < PER; ++k) raw[k] = i0 + k < n_ids ? __ldg(ids + i0 + k) : 0u;     // 0 is a special id: no cell
         }
 #pragma unroll
-        for (int k = 0; k < DC_PER; ++k) {
-            const uint64_t i = i0 + k;
-            uint32_t l = 0;
-            const uint32_t v = raw[k];
-            if (i < n_ids) {
-                if (v < T.num_special) l = policy == TK_POLICY_KEEP ? T.special_off[v + 1] - T.special_off[v] : 0u;
-                else {
-                    const uint32_t r = v - T.num_special;
-                    l = r < T.n_vocab ? (uint32_t)__ldg(T.vocab_len + r) : 0u;
-                    if (l == 255u) l = T.vocab_off[r + 1] - T.vocab_off[r];
-                }
-            }
-            id[k] = v; len[k] = l; sum += l;
+        for (int k = 0; k < PER; ++k) {
+            const uint32_t r = raw[k] - T.num_special;
+            e[k] = make_uint2(0xFFu, 0u);
+            if (raw[k] >= T.num_special && r < T.n_vocab && i0 + k < n_ids) e[k] = __ldg(reinterpret_cast<const uint2*>(T.vocab_e16 + r));
         }
+    }
+    // 2. lengths (16 bits each), scan
+    uint32_t len16[PER / 2];
+#pragma unroll
+    for (int k = 0; k < PER / 2; ++k) len16[k] = 0u;
+    uint32_t slow = 0, sum = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        uint32_t l = e[k].x & 0xFFu;
+        if (l == 0xFFu) { slow |= 1u << k; l = dc_slow_len(T, policy, ids, i0 + k, n_ids); }
+        len16[k >> 1] |= l << (16 * (k & 1));
+        sum += l;
     }
     uint32_t inc = sum;
 #pragma unroll
@@ -126,8 +173,54 @@ __global__ void __launch_bounds__(DC_T, DC_MINB) decode_gather_kernel(const uint
     uint32_t before = 0, tile_total = 0;
 #pragma unroll
     for (int w = 0; w < DC_T / 32; ++w) { if (w < (int)warp) before += wsum[w]; tile_total += wsum[w]; }
+    if (t == 0) tk_lookback_publish(tile_state, tile, tile_total);
+    const bool fits = tile_total <= BUF;                   // block-uniform
+    const uint32_t p = before + inc - sum;                 // my first byte, tile-relative
+    // 3. assemble
+    if (fits) {
+        DcStream s;
+        s.acc = 0ull; s.wpos = p & ~3u; s.fill = s.lo = p & 3u;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            const uint32_t l = (len16[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+            if ((slow >> k) & 1u) {                        // its bytes come later (or there are none): leave room
+                if (l) {
+                    dc_flush(bufw, s);
+                    const uint32_t cur = s.wpos + s.fill + l;
+                    s.acc = 0ull; s.wpos = cur & ~3u; s.fill = s.lo = cur & 3u;
+                }
+            } else {
+                if (l) dc_append(bufw, s, e[k].x >> 8, l < 3u ? l : 3u);
+                if (l > 3u) dc_append(bufw, s, e[k].y, l < 7u ? l - 3u : 4u);
+                if (l > 7u) {                               // the second half of the cell (a fraction of a percent of the ids)
+                    const uint2 c = __ldg(reinterpret_cast<const uint2*>(T.vocab_e16 + (__ldg(ids + i0 + k) - T.num_special)) + 1);
+                    dc_append(bufw, s, c.x, l < 11u ? l - 7u : 4u);
+                    if (l > 11u) dc_append(bufw, s, c.y, l - 11u);
+                }
+            }
+        }
+        dc_flush(bufw, s);
+        uint32_t todo = slow;
+#pragma unroll 1
+        while (todo) {                                      // tokens outside the cells: byte by byte
+            const uint32_t k = (uint32_t)(__ffs((int)todo) - 1);
+            todo &= todo - 1;
+            uint32_t rel = p, l = 0;                         // where token k starts, its length
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                const uint32_t lj = (len16[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
+                rel += (uint32_t)j < k ? lj : 0u;
+                l = (uint32_t)j == k ? lj : l;
+            }
+            if (!l) continue;
+            const uint8_t* src = dc_slow_bytes(T, policy, __ldg(ids + i0 + k));
+            if (src)
+                for (uint32_t j = 0; j < l; ++j) atomicOr(bufw + ((rel + j) >> 2), (uint32_t)__ldg(src + j) << (8u * ((rel + j) & 3u)));
+        }
+    }
+    // 4. where the tile starts in the output
     if (warp == 0) {
-        const unsigned long long excl = tk_lookback(tile_state, tile, tile_total);
+        const unsigned long long excl = tk_lookback_collect(tile_state, tile, tile_total);
         if (lane == 0) {
             s_base = excl;
             if (tile == gridDim.x - 1) {
@@ -138,169 +231,208 @@ __global__ void __launch_bounds__(DC_T, DC_MINB) decode_gather_kernel(const uint
     }
     __syncthreads();
     const uint64_t base = s_base;
-    const bool fits = tile_total <= DC_BUF;              // block-uniform
-    const uint32_t shift = (uint32_t)(base & 15u);         // staging keeps the output's 16-byte phase
-    uint32_t p = shift + before + inc - sum;               // my first byte in the staging buffer
-    uint64_t o = base + before + inc - sum;
-    // sequence starts among my positions (the sentinel position n_ids included)
-    const uint32_t tw = tds[i0 >> 5] >> (i0 & 31);   // DC_PER divides 32 -> my 8 bits are in one word
-    uint64_t seq = (tw & 0xFFu) ? seq_first[i0 >> 5] : 0;   // first sequence of my group of 32 ids; advanced below
-    // Usual case, unrolled: an ordinary token of at most 16 bytes, no sequence start -> one aligned 16-byte
-    // load from the padded table.  Everything else (sequence starts, special and unknown ids, longer
-    // tokens, oversized tiles, the sentinel position) is noted in `slow` and handled by one compact loop
-    // below, so the kernel stays small enough for the instruction cache.
-    uint32_t slow = 0;
+    // 5a. positions that need more than a copy: sequence starts (the end sentinel n_ids included), special and unknown ids;
+    //     in an oversized tile every token (it is copied here)
     {
-        uint32_t pk = p;
-#pragma unroll
-        for (int k = 0; k < DC_PER; ++k) {
-            const uint64_t i = i0 + k;
-            const uint32_t v = id[k], l = len[k];
-            const uint32_t r = v - T.num_special;
-            const bool fast = fits && i < n_ids && !((tw >> k) & 1u) && v >= T.num_special && r < T.n_vocab && l <= 16u;
-            if (fast) {
-                const uint4 q = __ldg(T.vocab_pad16 + r);
-                uint32_t cur = q.x;
-                for (uint32_t j = 0; j < l; ++j) {
-                    if ((j & 3u) == 0u && j) cur = j == 4u ? q.y : j == 8u ? q.z : q.w;
-                    buf[pk + j] = (uint8_t)cur;
-                    cur >>= 8;
-                }
-            } else if (i <= n_ids) slow |= 1u << k;
-            pk += l;
-        }
-    }
+        const uint32_t tw = (tds[i0 >> 5] >> (i0 & 31)) & ((1u << PER) - 1u);   // PER divides 32: my bits are in one word
+        uint64_t seq = tw ? seq_first[i0 >> 5] : 0;         // first sequence of my group of 32 ids; advanced below
+        uint32_t todo = fits ? (tw | slow) : ((1u << PER) - 1u);
 #pragma unroll 1
-    while (slow) {
-        const uint32_t k = (uint32_t)(__ffs((int)slow) - 1);
-        slow &= slow - 1;
-        const uint64_t i = i0 + k;
-        uint32_t pre = 0, v = 0, l = 0;                      // bytes of my ids before position k; its id and length
+        while (todo) {
+            const uint32_t k = (uint32_t)(__ffs((int)todo) - 1);
+            todo &= todo - 1;
+            const uint64_t i = i0 + k;
+            if (i > n_ids) break;
+            uint32_t rel = p, l = 0;
 #pragma unroll
-        for (int j = 0; j < DC_PER; ++j) {
-            pre += (uint32_t)j < k ? len[j] : 0u;
-            if ((uint32_t)j == k) { v = id[j]; l = len[j]; }
-        }
-        const uint64_t ok = o + pre;
-        const uint32_t pk = p + pre;
-        if ((tw >> k) & 1u) {
-            while (tok_off[seq] - off_base < i) ++seq;   // sequences that start earlier in the group
-            for (; seq <= n_docs && tok_off[seq] - off_base == i; ++seq) byte_off[seq] = ok;
-            mark_boundary(bmask, ok, out_cap);
-        }
-        if (i == n_ids) break;
-        if (v < T.num_special) {
-            // a special id ends the ordinary run before it and starts a new one after it
-            mark_boundary(bmask, ok, out_cap);
-            if (policy == TK_POLICY_RAISE) {
-                const uint64_t d = seq_of(tok_off, off_base, n_docs, i);
-                atomicMin(&docerr[d].sp_tok, (unsigned long long)i);
-                atomicMin(&docerr[d].sp_byte, (unsigned long long)ok);
-            } else if (policy == TK_POLICY_KEEP) {
-                dc_put(buf, fits, pk, out, ok, out_cap, T.special_bytes + T.special_off[v], l);
-                mark_boundary(bmask, ok + l, out_cap);
+            for (int j = 0; j < PER; ++j) {
+                const uint32_t lj = (len16[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
+                rel += (uint32_t)j < k ? lj : 0u;
+                l = (uint32_t)j == k ? lj : l;
             }
-        } else {
-            const uint32_t r = v - T.num_special;
-            if (r >= T.n_vocab) {
+            const uint64_t ok = base + rel;
+            if ((tw >> k) & 1u) {
+                while (tok_off[seq] - off_base < i) ++seq;   // sequences that start earlier in the group
+                for (; seq <= n_docs && tok_off[seq] - off_base == i; ++seq) byte_off[seq] = ok;
+                mark_boundary(bmask, ok, out_cap);
+            }
+            if (i == n_ids) break;
+            const uint32_t v = __ldg(ids + i);
+            if (v < T.num_special) {
+                // a special id ends the ordinary run before it and starts a new one after it
+                mark_boundary(bmask, ok, out_cap);
+                if (policy == TK_POLICY_RAISE) {
+                    const uint64_t d = seq_of(tok_off, off_base, n_docs, i);
+                    atomicMin(&docerr[d].sp_tok, (unsigned long long)i);
+                    atomicMin(&docerr[d].sp_byte, (unsigned long long)ok);
+                } else if (policy == TK_POLICY_KEEP) {
+                    mark_boundary(bmask, ok + l, out_cap);
+                }
+            } else if (v - T.num_special >= T.n_vocab) {
                 const uint64_t d = seq_of(tok_off, off_base, n_docs, i);
                 atomicMin(&docerr[d].unk_tok, (unsigned long long)i);
-            } else {
-                dc_put(buf, fits, pk, out, ok, out_cap, T.vocab_bytes + T.vocab_off[r], l);
+            }
+            if (!fits && l && ok + l <= out_cap) {
+                const uint8_t* src = dc_slow_bytes(T, policy, v);
+                if (src)
+                    for (uint32_t j = 0; j < l; ++j) out[ok + j] = __ldg(src + j);
             }
         }
     }
     if (!fits) return;
-    __syncthreads();
-    // staging buffer -> output: aligned 16-byte stores in the middle, single bytes at the ragged ends
+    // 5b. staging buffer -> output: aligned words, the tile's text shifted by the phase of its first byte
     {
         const uint64_t lim = base + tile_total < out_cap ? base + tile_total : out_cap;   // never write past the caller's buffer
         if (lim <= base) return;
-        const uint64_t a0 = base - shift;                       // 16-byte aligned global address of buf[0]
-        const uint32_t n_chunks = (uint32_t)((lim - a0 + 15u) / 16u);
-        const bool aligned = ((uintptr_t)out & 15u) == 0;
-        for (uint32_t c = t; c < n_chunks; c += DC_T) {
-            const uint64_t g = a0 + 16ull * c;
-            if (aligned && g >= base && g + 16u <= lim) {
-                *reinterpret_cast<uint4*>(out + g) = *reinterpret_cast<const uint4*>(buf + 16u * c);
+        const uint32_t sh = (uint32_t)(((uintptr_t)out + base) & 3u);
+        const uint64_t a0 = base - sh;                          // (out + a0) is word aligned; may be "before" out for the first tile
+        const uint32_t n_words = (uint32_t)((lim - a0 + 3u) / 4u);
+        for (uint32_t j = t; j < n_words; j += DC_T) {
+            // output word j = tile bytes 4j - sh .. 4j - sh + 3
+            const uint32_t hi = bufw[j], lo = j ? bufw[j - 1] : 0u;
+            const uint32_t w = sh ? __funnelshift_r(lo, hi, 8u * (4u - sh)) : hi;
+            const uint64_t g = a0 + 4ull * j;
+            if (j && g + 4u <= lim) {                          // (j >= 1: g >= base)
+                *reinterpret_cast<uint32_t*>(out + g) = w;
             } else {
-                for (uint32_t j = 0; j < 16u; ++j)
-                    if (g + j >= base && g + j < lim) out[g + j] = buf[16u * c + j];
+#pragma unroll
+                for (uint32_t q = 0; q < 4u; ++q)
+                    if (4ull * j + q >= sh && g + q < lim) out[g + q] = (uint8_t)(w >> (8u * q));
             }
         }
     }
 }
 
-__global__ void __launch_bounds__(256) decode_validate_kernel(const uint8_t* __restrict__ out, const unsigned long long* __restrict__ total_out,
+// ---- D2: strict UTF-8 per ordinary run ----------------------------------------------------------------------------------
+// One thread per 32 output bytes, nine words (the window and the four bytes before it), flags kept where the bytes are
+// (bit 7 of every byte of a word; "the byte before" is a funnel shift by 8 across two words) -- no per-character loop
+// and no table: a window of CJK text costs what a window of Latin text costs.
+//   lead2/3/4 bytes start a chain of continuation bytes; a continuation byte ON a run boundary does not continue
+//   anything (contp);
+//   errA (charged to the run that holds the byte): a continuation byte no chain reaches, C0 C1 F5..FF, a second byte
+//     outside the range its lead allows (E0: A0..BF, ED: 80..9F, F0: 90..BF, F4: 80..8F);
+//   errB (charged to the run that holds the byte BEFORE): a chain expects a continuation byte here and there is none --
+//     the text, the run or the character just ends.
+// Which sequence an error belongs to is looked up only when there is one.
+struct DvPrev {
+    uint32_t l234, l34, l4, c1_34, c1_4, c2_4, e0, ed, f0, f4;
+};
+
+__device__ __forceinline__ uint64_t dv_seq_of_byte(const uint64_t* __restrict__ byte_off, uint64_t n_docs, uint64_t q) {
+    uint64_t lo = 0, hi = n_docs;                    // last d with byte_off[d] <= q
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (byte_off[mid] <= q) lo = mid + 1; else hi = mid;
+    }
+    return lo ? lo - 1 : 0;
+}
+
+// The nine words of one window.  REPORT = false: is anything wrong (the hot path); true: charge every error to its
+// sequence.
+template <bool REPORT>
+__device__ __forceinline__ uint32_t dv_window(const uint32_t (&w)[9], uint32_t bm, uint32_t bm0, uint64_t pos, uint64_t n,
+                                              const uint64_t* __restrict__ byte_off, uint64_t n_docs, DocErr* __restrict__ docerr) {
+    DvPrev pv = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    uint32_t any_err = 0;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+        const uint32_t x = w[j];
+        if (!((x & TK_H) | ((pv.l234 | pv.c1_34 | pv.c2_4) >> 24))) {      // ASCII, and nothing reaches into it
+            pv = DvPrev{0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            continue;
+        }
+        const uint32_t bn = j ? (bm >> (4 * (j - 1))) & 0xFu : bm0;
+        const uint32_t bnd = ((bn * 0x00204081u) & 0x01010101u) << 7;       // boundary bits -> bit 7 of their bytes
+        const uint32_t c6 = x << 1, c5 = x << 2, c4 = x << 3;
+        const uint32_t hi = x & TK_H;
+        const uint32_t cont = hi & ~c6, contp = cont & ~bnd;
+        const uint32_t a = x & c6;
+        DvPrev c;
+        c.l234 = a & TK_H;                       // >= C0
+        c.l34 = a & c5 & TK_H;                   // >= E0
+        c.l4 = c.l34 & c4;                       // >= F0
+        const uint32_t e1 = __funnelshift_l(pv.l234, c.l234, 8);
+        c.c1_34 = __funnelshift_l(pv.l34, c.l34, 8) & contp;
+        c.c1_4 = __funnelshift_l(pv.l4, c.l4, 8) & contp;
+        const uint32_t t1 = __funnelshift_l(pv.c1_34, c.c1_34, 8);
+        c.c2_4 = __funnelshift_l(pv.c1_4, c.c1_4, 8) & contp;
+        const uint32_t t2 = __funnelshift_l(pv.c2_4, c.c2_4, 8);
+        const uint32_t expect = e1 | t1 | t2;
+        uint32_t A = cont & ~(expect & contp);                              // stray continuation bytes
+        const uint32_t B = expect & ~contp;                                 // a continuation byte is missing here
+        // C0, C1: two-byte leads with bits 4..1 clear
+        A |= c.l234 & ~c5 & ~(((x & 0x1E1E1E1Eu) + 0x7F7F7F7Fu) & TK_H);
+        c.e0 = c.ed = c.f0 = c.f4 = 0u;
+        if (c.l34 | pv.e0 | pv.ed | pv.f0 | pv.f4) {
+            const uint32_t w7 = x & 0x7F7F7F7Fu;
+            c.e0 = tk_swar_eq(w7, 0x60u) & hi;
+            c.ed = tk_swar_eq(w7, 0x6Du) & hi;
+            if (c.l4) {
+                c.f0 = tk_swar_eq(w7, 0x70u) & hi;
+                c.f4 = tk_swar_eq(w7, 0x74u) & hi;
+                A |= tk_swar_ge(w7, 0x75u) & hi;                            // F5..FF
+            }
+            A |= __funnelshift_l(pv.e0, c.e0, 8) & contp & ~c5;             // E0 80..9F: overlong
+            A |= __funnelshift_l(pv.ed, c.ed, 8) & contp & c5;              // ED A0..BF: surrogates
+            A |= __funnelshift_l(pv.f0, c.f0, 8) & contp & ~c5 & ~c4;       // F0 80..8F: overlong
+            A |= __funnelshift_l(pv.f4, c.f4, 8) & contp & (c5 | c4);       // F4 90..BF: above U+10FFFF
+        }
+        pv = c;
+        if (j) {
+            any_err |= (A | B) & TK_H;
+            if (REPORT) {
+                uint32_t na = tk_swar_nib(A & TK_H), nb = tk_swar_nib(B & TK_H);
+                while (na) {
+                    const uint64_t q = pos + 4u * (uint32_t)(j - 1) + (uint32_t)(__ffs((int)na) - 1);
+                    na &= na - 1;
+                    if (q < n) atomicMin(&docerr[dv_seq_of_byte(byte_off, n_docs, q)].utf_byte, (unsigned long long)q);
+                }
+                while (nb) {
+                    const uint64_t q = pos + 4u * (uint32_t)(j - 1) + (uint32_t)(__ffs((int)nb) - 1);
+                    nb &= nb - 1;
+                    if (q >= 1 && q <= n) atomicMin(&docerr[dv_seq_of_byte(byte_off, n_docs, q - 1)].utf_byte, (unsigned long long)(q - 1));
+                }
+            }
+        }
+    }
+    return any_err;
+}
+
+__global__ void __launch_bounds__(256, 4) decode_validate_kernel(const uint8_t* __restrict__ out, const unsigned long long* __restrict__ total_out,
                                                               uint64_t out_cap, const uint32_t* __restrict__ bmask,
-                                                              const uint64_t* __restrict__ byte_off, uint64_t n_docs, TkDeviceTables T,
+                                                              const uint64_t* __restrict__ byte_off, uint64_t n_docs,
                                                               DocErr* __restrict__ docerr) {
     uint64_t n = *total_out;
     if (n > out_cap) n = out_cap;
-    const uint64_t n_windows = (n + 31) / 32;
+    const uint64_t n_windows = n / 32 + 1;           // position n itself is looked at: a character cut off by the end of the text
+    const bool aligned = ((uintptr_t)out & 15u) == 0;
     for (uint64_t wi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; wi < n_windows; wi += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t pos = wi * 32u;
-        uint32_t w[8];
-        if (pos + 32 <= n && ((uintptr_t)out & 15u) == 0) {
+        uint32_t w[9];
+        if (pos + 32 <= n && aligned) {
             const uint4 a = __ldg((const uint4*)(out + pos));
             const uint4 b = __ldg((const uint4*)(out + pos) + 1);
-            w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+            w[1] = a.x; w[2] = a.y; w[3] = a.z; w[4] = a.w; w[5] = b.x; w[6] = b.y; w[7] = b.z; w[8] = b.w;
+            w[0] = pos ? __ldg((const uint32_t*)(out + pos) - 1) : 0u;
         } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < 9; ++j) {
                 uint32_t v = 0;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    uint64_t q = pos + 4 * j + k;
-                    if (q < n) v |= (uint32_t)out[q] << (8 * k);
+                    const uint64_t q = pos + 4 * j + k;         // byte q - 4
+                    if (q >= 4 && q - 4 < n) v |= (uint32_t)out[q - 4] << (8 * k);
                 }
                 w[j] = v;
             }
         }
-        // a char must not continue across a run boundary: the classifier flags a boundary on a
-        // continuation byte and, via the byte after the window, a truncated char
-        const TkWin c = tk_classify_window(out, n, pos, w, bmask[wi], T);
-        const uint32_t valid = (pos + 32 <= n) ? 0xFFFFFFFFu : (uint32_t)((1ull << (n - pos)) - 1ull);
-        uint32_t bad = c.bad & valid;
-        // a boundary on a continuation byte: the run after it is flagged above (it starts inside a
-        // char).  The run BEFORE it is invalid too iff its last char is cut short by the boundary.
-        uint32_t split = c.ds & ~c.lead & valid;
-        while (split) {
-            const uint64_t q = pos + (uint32_t)(__ffs((int)split) - 1);
-            split &= split - 1;
-            if (q == 0) continue;
-            // lead byte of the char that contains byte q-1, without crossing an earlier boundary
-            uint64_t k = q - 1;
-            int back = 0;
-            bool crossed = false;
-            while (back < 3 && k > 0 && (out[k] & 0xC0u) == 0x80u) {
-                if ((bmask[k >> 5] >> (k & 31)) & 1u) { crossed = true; break; }
-                --k;
-                ++back;
-            }
-            if (crossed) continue;                                  // that run starts with a continuation byte: flagged already
-            const uint32_t b0 = out[k];
-            const uint32_t need = b0 < 0x80u ? 1u : b0 >= 0xF0u ? 4u : b0 >= 0xE0u ? 3u : b0 >= 0xC0u ? 2u : 0u;
-            if (need == 0u || k + need <= q) continue;              // complete (or stray bytes, flagged on their own)
-            uint64_t lo = 0, hi = n_docs;
-            while (lo < hi) {
-                uint64_t mid = (lo + hi) >> 1;
-                if (byte_off[mid] <= q - 1) lo = mid + 1; else hi = mid;
-            }
-            atomicMin(&docerr[lo ? lo - 1 : 0].utf_byte, (unsigned long long)(q - 1));
-        }
-        while (bad) {
-            const uint64_t q = pos + (uint32_t)(__ffs((int)bad) - 1);
-            bad &= bad - 1;
-            // sequence containing byte q: last d with byte_off[d] <= q
-            uint64_t lo = 0, hi = n_docs;
-            while (lo < hi) {
-                uint64_t mid = (lo + hi) >> 1;
-                if (byte_off[mid] <= q) lo = mid + 1; else hi = mid;
-            }
-            const uint64_t d = lo ? lo - 1 : 0;
-            atomicMin(&docerr[d].utf_byte, (unsigned long long)q);
-        }
+        uint32_t any = 0;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) any |= w[j];
+        if (!(any & TK_H)) continue;                             // ASCII: nothing can be wrong
+        const uint32_t bm = bmask[wi], bm0 = wi ? bmask[wi - 1] >> 28 : 0u;
+        if (!dv_window<false>(w, bm, bm0, pos, n, byte_off, n_docs, docerr)) continue;
+        dv_window<true>(w, bm, bm0, pos, n, byte_off, n_docs, docerr);         // rare: say where, and whose
     }
 }
 
@@ -328,8 +460,8 @@ size_t decode_workspace_bytes(uint64_t n_ids, uint64_t n_docs, uint64_t out_cap,
     DecodeLayout l{};
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
-    l.n_tiles = ceil_div(n_ids + 1, DC_TILE);
-    l.mask_words_tok = l.n_tiles * (DC_TILE / 32) + 8;
+    l.n_tiles = ceil_div(n_ids + 1, DC_T * DC_PER);
+    l.mask_words_tok = l.n_tiles * (DC_T * DC_PER / 32) + 8;
     l.mask_words_out = out_cap / 32 + 8;
     l.off_small = take(256);
     l.off_tds = take(l.mask_words_tok * 4);
@@ -367,14 +499,14 @@ cudaError_t decode_device(const TkDeviceTables& T, const uint32_t* d_ids, const 
     CK(cudaMemsetAsync(docerr, 0xFF, (n_docs + 1) * sizeof(DocErr), st));
     tokmark_kernel<<<(unsigned)ceil_div(n_docs + 1, 256), 256, 0, st>>>(d_tok_off, off_base, n_docs, n_ids, tds, seq_first, flags);
     count_launch();
-    decode_gather_kernel<<<(unsigned)L.n_tiles, DC_T, 0, st>>>(d_ids, n_ids, d_tok_off, off_base, n_docs, tds, seq_first, policy, T, d_out, out_cap,
+    decode_gather_kernel<DC_PER, DC_MINB><<<(unsigned)L.n_tiles, DC_T, 0, st>>>(d_ids, n_ids, d_tok_off, off_base, n_docs, tds, seq_first, policy, T, d_out, out_cap,
                                                              d_byte_off, bmask, docerr, tilestate, ticket, total_out, flags);
     count_launch();
     {
-        uint64_t blocks = ceil_div(ceil_div(out_cap, 32), 256);
+        uint64_t blocks = ceil_div(out_cap / 32 + 1, 256);
         if (blocks < 1) blocks = 1;
         if (blocks > 148 * 16) blocks = 148 * 16;
-        decode_validate_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_out, total_out, out_cap, bmask, d_byte_off, n_docs, T, docerr);
+        decode_validate_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_out, total_out, out_cap, bmask, d_byte_off, n_docs, docerr);
         count_launch();
     }
     if (n_docs) {

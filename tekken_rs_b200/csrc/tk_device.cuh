@@ -157,6 +157,39 @@ __device__ __forceinline__ unsigned long long tk_lookback(unsigned long long* __
     return excl;
 }
 
+// The two halves of tk_lookback, for a kernel that has other work to do between knowing its tile's total and needing
+// the prefix: ONE thread publishes, later ONE WARP collects.
+__device__ __forceinline__ void tk_lookback_publish(unsigned long long* __restrict__ state, uint32_t tile, unsigned long long total) {
+    tk_st_relaxed_u64(state + tile, ((tile == 0 ? 2ull : 1ull) << 62) | total);
+}
+__device__ __forceinline__ unsigned long long tk_lookback_collect(unsigned long long* __restrict__ state, uint32_t tile,
+                                                                  unsigned long long total) {
+    if (tile == 0) return 0ull;
+    const uint32_t lane = threadIdx.x & 31u;
+    const unsigned long long vmask = (1ull << 62) - 1ull;
+    unsigned long long excl = 0;
+    long long base = (long long)tile - 1;
+    for (;;) {
+        const long long j = base - (long long)lane;
+        const unsigned long long v = j >= 0 ? tk_ld_relaxed_u64(state + j) : (2ull << 62);
+        const uint32_t f = (uint32_t)(v >> 62);
+        const uint32_t m2 = __ballot_sync(0xFFFFFFFFu, f == 2u), m0 = __ballot_sync(0xFFFFFFFFu, f == 0u);
+        const uint32_t upto = m2 ? (0xFFFFFFFFu >> (32 - __ffs((int)m2))) : 0xFFFFFFFFu;
+        if (m0 & upto) {
+            __nanosleep(40);
+            continue;
+        }
+        unsigned long long c = ((upto >> lane) & 1u) ? (v & vmask) : 0ull;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, d);
+        excl += c;
+        if (m2) break;
+        base -= 32;
+    }
+    if (lane == 0) tk_st_relaxed_u64(state + tile, (2ull << 62) | (excl + total));
+    return excl;
+}
+
 // Whole-piece lookup (CoreBPE's `encoder.get(piece)` shortcut).  p may point to shared or global
 // memory; len >= 1.
 __device__ __forceinline__ uint32_t tk_vocab_lookup(const TkDeviceTables& T, const uint8_t* p, uint32_t len) {

@@ -636,6 +636,8 @@ HostModel HostModel::build(const std::vector<VocabEntry>& vocab, const std::vect
         m.vocab_off[r + 1] = m.vocab_off[r] + (uint32_t)by_rank[r]->size();
         m.max_token_len = std::max<uint32_t>(m.max_token_len, (uint32_t)by_rank[r]->size());
     }
+    if (m.max_token_len > 65535u)      // the decoder keeps token lengths in 16 bits (tk_decode.cu)
+        throw Error(TK_ERR_INVALID_CONFIG, "Vocabulary token longer than 65,535 bytes");
     m.vocab_bytes.resize(m.vocab_off[n_vocab]);
     for (size_t r = 0; r < n_vocab; ++r)
         if (!by_rank[r]->empty()) memcpy(&m.vocab_bytes[m.vocab_off[r]], by_rank[r]->data(), by_rank[r]->size());
@@ -728,11 +730,14 @@ HostModel HostModel::build(const std::vector<VocabEntry>& vocab, const std::vect
     // decode's gather source: every token in an aligned 16-byte cell + its length in a byte
     {
         m.vocab_pad16.assign(16 * std::max<size_t>(n_vocab, 1), 0);
-        m.vocab_len8.assign(std::max<size_t>(n_vocab, 1), 0);
+        m.vocab_e16.assign(16 * std::max<size_t>(n_vocab, 1), 0);
         for (size_t r = 0; r < n_vocab; ++r) {
             uint32_t len = m.vocab_off[r + 1] - m.vocab_off[r];
             memcpy(&m.vocab_pad16[16 * r], &m.vocab_bytes[m.vocab_off[r]], std::min<uint32_t>(len, 16));
-            m.vocab_len8[r] = (uint8_t)std::min<uint32_t>(len, 255);
+            // decode's cell: the length, then 15 bytes -- the first 8-byte load gives the length and 7 bytes, which is the
+            // whole token for all but a fraction of a percent of the ids in text.  0xFF = longer than 15 (see vocab_off)
+            if (len <= 15) { m.vocab_e16[16 * r] = (uint8_t)len; memcpy(&m.vocab_e16[16 * r + 1], &m.vocab_bytes[m.vocab_off[r]], len); }
+            else m.vocab_e16[16 * r] = 0xFF;
         }
     }
     // first-round pair ranks (both parts are single bytes): direct-indexed, no probing
@@ -751,6 +756,8 @@ HostModel HostModel::build(const std::vector<VocabEntry>& vocab, const std::vect
     for (size_t i = 0; i < num_special; ++i)
         m.special_off[i + 1] = m.special_off[i] + (uint32_t)m.special_tokens[i].token_str.size();
     m.special_bytes.resize(m.special_off[num_special]);
+    for (size_t i = 0; i < num_special; ++i)
+        if (m.special_off[i + 1] - m.special_off[i] > 65535u) throw Error(TK_ERR_INVALID_CONFIG, "Special token string longer than 65,535 bytes");
     for (size_t i = 0; i < num_special; ++i)
         memcpy(m.special_bytes.data() + m.special_off[i], m.special_tokens[i].token_str.data(),
                m.special_tokens[i].token_str.size());

@@ -80,8 +80,8 @@ struct HostModel {
     std::vector<uint64_t> pair_buckets;                       // the same entries in four-slot buckets (see tk_common.h)
     uint32_t bucket_mask = 0;
     std::vector<uint32_t> byte_pair;                          // 65536 entries, direct-indexed
-    std::vector<uint8_t> vocab_pad16;                         // 16 bytes per rank (decode's gather source)
-    std::vector<uint8_t> vocab_len8;                          // length per rank, 255 = longer than 254
+    std::vector<uint8_t> vocab_pad16;                         // 16 bytes per rank (the encoder's whole-piece check)
+    std::vector<uint8_t> vocab_e16;                           // 16 bytes per rank: length (0xFF = longer than 15), then 15 token bytes; decode's gather source
     std::vector<uint8_t> special_bytes;
     std::vector<uint32_t> special_off;
     size_t n_pairs = 0;
