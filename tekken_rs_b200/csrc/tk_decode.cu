@@ -57,19 +57,20 @@ __device__ __forceinline__ void mark_boundary(uint32_t* __restrict__ bmask, uint
 //   1. ids -> the first 8 bytes of one 16-byte table cell per id (length + 7 bytes): the lengths for the scan and the
 //      bytes for the copy come from the same load, issued for all of a thread's ids at once;
 //   2. block scan of the lengths; the tile's total is published for the tiles behind it;
-//   3. the text of the tile is assembled in shared memory at tile-relative positions.  A thread's tokens are adjacent in
-//      the text, so it shifts them into a 64-bit accumulator and stores whole words; the one or two words it shares with
-//      its neighbours are OR-ed into the (zeroed) buffer;
-//   4. only now warp 0 collects the prefix of the tiles before this one (decoupled look-back) -- by then it is usually
+//   3. the text of the tile is assembled in (zeroed) shared memory at tile-relative positions.  A thread's tokens are
+//      adjacent in the text: it shifts them into a two-word accumulator and stores every word it COMPLETES -- its own
+//      bytes, zeros elsewhere -- with a plain predicated store; no branch depends on a token's length (round-2 ncu: the
+//      branchy version spent 45 % of the kernel's instructions here at 5-18 active lanes);
+//   4. after a barrier the bytes that are not in a completed word are OR-ed in: every thread's last partial word and
+//      the tokens that do not come from a cell (longer than 15 bytes, special strings under Keep).  Every word has
+//      exactly one plain store or none, and all ORs come after all stores;
+//   5. only now warp 0 collects the prefix of the tiles before this one (decoupled look-back) -- by then it is usually
 //      there, and the other warps were not waiting for it while they assembled;
-//   5. the rare work that needs absolute positions (sequence starts, special and unknown ids) and the copy to the output
+//   6. the rare work that needs absolute positions (sequence starts, special and unknown ids) and the copy to the output
 //      in aligned words, shifted by the output's phase.
 // A tile whose text is larger than the staging buffer (more than 7 bytes per id) is written to the output byte by byte.
 
-__device__ __forceinline__ uint32_t dc_slow_len(const TkDeviceTables& T, int policy, const uint32_t* __restrict__ ids, uint64_t i,
-                                                uint64_t n_ids) {
-    if (i >= n_ids) return 0u;
-    const uint32_t v = __ldg(ids + i);
+__device__ __forceinline__ uint32_t dc_slow_len(const TkDeviceTables& T, int policy, uint32_t v) {
     if (v < T.num_special) return policy == TK_POLICY_KEEP ? T.special_off[v + 1] - T.special_off[v] : 0u;
     const uint32_t r = v - T.num_special;
     return r < T.n_vocab ? T.vocab_off[r + 1] - T.vocab_off[r] : 0u;     // <= 65,535 (checked when the file is loaded)
@@ -83,22 +84,42 @@ __device__ __forceinline__ const uint8_t* dc_slow_bytes(const TkDeviceTables& T,
 }
 
 struct DcStream {
-    unsigned long long acc;    // bytes not stored yet, from byte `lo` of the word at wpos upwards
-    uint32_t wpos;             // tile-relative byte position of the word being filled (multiple of 4)
-    uint32_t fill;             // bytes of that word that are decided (the ones below lo belong to somebody else)
-    uint32_t lo;
+    uint32_t a0, a1;           // bytes not stored yet: a0 = the word being filled, a1 = what spilled over
+    uint32_t wi;               // tile-relative index of that word
+    uint32_t fill;             // bytes of it that are decided (0..3 between calls)
 };
+// nb <= 4 bytes of w (the rest of w is zero); branch-free
 __device__ __forceinline__ void dc_append(uint32_t* __restrict__ bufw, DcStream& s, uint32_t w, uint32_t nb) {
-    s.acc |= (unsigned long long)w << (8u * s.fill);
+    const uint32_t sh = 8u * s.fill;
+    s.a0 |= w << sh;
+    s.a1 |= __funnelshift_l(w, 0u, sh);                     // the bytes of w that do not fit (sh = 0: none)
     s.fill += nb;
-    if (s.fill >= 4u) {
-        if (s.lo) atomicOr(bufw + (s.wpos >> 2), (uint32_t)s.acc);      // shared with the thread before me
-        else bufw[s.wpos >> 2] = (uint32_t)s.acc;
-        s.wpos += 4u; s.acc >>= 32; s.fill -= 4u; s.lo = 0u;
-    }
+    const bool full = s.fill >= 4u;
+    if (full) bufw[s.wi] = s.a0;
+    s.a0 = full ? s.a1 : s.a0;
+    s.a1 = full ? 0u : s.a1;
+    s.wi += full ? 1u : 0u;
+    s.fill -= full ? 4u : 0u;
 }
-__device__ __forceinline__ void dc_flush(uint32_t* __restrict__ bufw, const DcStream& s) {
-    if (s.fill > s.lo) atomicOr(bufw + (s.wpos >> 2), (uint32_t)s.acc);  // a partial word: the rest is somebody else's
+// l bytes that somebody else writes (zeros here)
+__device__ __forceinline__ void dc_gap(uint32_t* __restrict__ bufw, DcStream& s, uint32_t l) {
+    const uint32_t end = s.fill + l;
+    if (end >= 4u) {
+        bufw[s.wi] = s.a0;                                   // my bytes of this word; the rest of it is the gap's
+        s.a0 = 0u;
+    }
+    s.wi += end >> 2;
+    s.fill = end & 3u;
+}
+
+template <int PER>
+__device__ __forceinline__ void dc_locate(const uint32_t (&len16)[PER / 2], uint32_t k, uint32_t& rel, uint32_t& l) {
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {                          // bytes of my ids before position k; its length
+        const uint32_t lj = (len16[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
+        rel += (uint32_t)j < k ? lj : 0u;
+        l = (uint32_t)j == k ? lj : l;
+    }
 }
 
 #ifndef DC_PER
@@ -129,8 +150,10 @@ __global__ void __launch_bounds__(DC_T, MINB) decode_gather_kernel(const uint32_
     __syncthreads();
     const uint32_t tile = s_tile;
     const uint64_t i0 = (uint64_t)tile * TILE + (uint64_t)t * PER;
-    // 1. the first half of one table cell per id: the length and 7 bytes
+    // 1. the first half of one table cell per id: the length and 7 bytes.  Ids without a cell: special and unknown ids
+    //    (`spec`: no bytes unless Keep, looked at again in step 6), positions past the end.
     uint2 e[PER];
+    uint32_t spec = 0;
     {
         uint32_t raw[PER];
         if (i0 + PER <= n_ids && ((uintptr_t)ids & 15u) == 0) {
@@ -146,8 +169,10 @@ __global__ void __launch_bounds__(DC_T, MINB) decode_gather_kernel(const uint32_
 #pragma unroll
         for (int k = 0; k < PER; ++k) {
             const uint32_t r = raw[k] - T.num_special;
-            e[k] = make_uint2(0xFFu, 0u);
-            if (raw[k] >= T.num_special && r < T.n_vocab && i0 + k < n_ids) e[k] = __ldg(reinterpret_cast<const uint2*>(T.vocab_e16 + r));
+            const bool cell = raw[k] >= T.num_special && r < T.n_vocab;
+            e[k] = make_uint2(0u, 0u);
+            if (cell) e[k] = __ldg(reinterpret_cast<const uint2*>(T.vocab_e16 + r));
+            spec |= cell ? 0u : 1u << k;
         }
     }
     // 2. lengths (16 bits each), scan
@@ -158,7 +183,10 @@ __global__ void __launch_bounds__(DC_T, MINB) decode_gather_kernel(const uint32_
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
         uint32_t l = e[k].x & 0xFFu;
-        if (l == 0xFFu) { slow |= 1u << k; l = dc_slow_len(T, policy, ids, i0 + k, n_ids); }
+        if (l == 0xFFu || (policy == TK_POLICY_KEEP && ((spec >> k) & 1u))) {      // rare: the length is somewhere else
+            l = i0 + k < n_ids ? dc_slow_len(T, policy, __ldg(ids + i0 + k)) : 0u;
+            slow |= l ? 1u << k : 0u;
+        }
         len16[k >> 1] |= l << (16 * (k & 1));
         sum += l;
     }
@@ -176,49 +204,43 @@ __global__ void __launch_bounds__(DC_T, MINB) decode_gather_kernel(const uint32_
     if (t == 0) tk_lookback_publish(tile_state, tile, tile_total);
     const bool fits = tile_total <= BUF;                   // block-uniform
     const uint32_t p = before + inc - sum;                 // my first byte, tile-relative
-    // 3. assemble
+    // 3. assemble: plain stores of completed words
+    DcStream s;
+    s.a0 = s.a1 = 0u; s.wi = p >> 2; s.fill = p & 3u;
     if (fits) {
-        DcStream s;
-        s.acc = 0ull; s.wpos = p & ~3u; s.fill = s.lo = p & 3u;
 #pragma unroll
         for (int k = 0; k < PER; ++k) {
             const uint32_t l = (len16[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
-            if ((slow >> k) & 1u) {                        // its bytes come later (or there are none): leave room
-                if (l) {
-                    dc_flush(bufw, s);
-                    const uint32_t cur = s.wpos + s.fill + l;
-                    s.acc = 0ull; s.wpos = cur & ~3u; s.fill = s.lo = cur & 3u;
-                }
+            if ((slow >> k) & 1u) {                        // its bytes come in step 4
+                dc_gap(bufw, s, l);
             } else {
-                if (l) dc_append(bufw, s, e[k].x >> 8, l < 3u ? l : 3u);
-                if (l > 3u) dc_append(bufw, s, e[k].y, l < 7u ? l - 3u : 4u);
+                dc_append(bufw, s, e[k].x >> 8, l < 3u ? l : 3u);
+                dc_append(bufw, s, e[k].y, l < 3u ? 0u : (l < 7u ? l - 3u : 4u));
                 if (l > 7u) {                               // the second half of the cell (a fraction of a percent of the ids)
                     const uint2 c = __ldg(reinterpret_cast<const uint2*>(T.vocab_e16 + (__ldg(ids + i0 + k) - T.num_special)) + 1);
                     dc_append(bufw, s, c.x, l < 11u ? l - 7u : 4u);
-                    if (l > 11u) dc_append(bufw, s, c.y, l - 11u);
+                    dc_append(bufw, s, c.y, l < 11u ? 0u : l - 11u);
                 }
             }
         }
-        dc_flush(bufw, s);
+    }
+    __syncthreads();
+    // 4. OR in what is not part of a completed word
+    if (fits) {
+        if (s.fill) atomicOr(bufw + s.wi, s.a0);
         uint32_t todo = slow;
 #pragma unroll 1
         while (todo) {                                      // tokens outside the cells: byte by byte
             const uint32_t k = (uint32_t)(__ffs((int)todo) - 1);
             todo &= todo - 1;
-            uint32_t rel = p, l = 0;                         // where token k starts, its length
-#pragma unroll
-            for (int j = 0; j < PER; ++j) {
-                const uint32_t lj = (len16[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
-                rel += (uint32_t)j < k ? lj : 0u;
-                l = (uint32_t)j == k ? lj : l;
-            }
-            if (!l) continue;
+            uint32_t rel = p, l = 0;
+            dc_locate<PER>(len16, k, rel, l);
             const uint8_t* src = dc_slow_bytes(T, policy, __ldg(ids + i0 + k));
             if (src)
                 for (uint32_t j = 0; j < l; ++j) atomicOr(bufw + ((rel + j) >> 2), (uint32_t)__ldg(src + j) << (8u * ((rel + j) & 3u)));
         }
     }
-    // 4. where the tile starts in the output
+    // 5. where the tile starts in the output
     if (warp == 0) {
         const unsigned long long excl = tk_lookback_collect(tile_state, tile, tile_total);
         if (lane == 0) {
@@ -231,12 +253,12 @@ __global__ void __launch_bounds__(DC_T, MINB) decode_gather_kernel(const uint32_
     }
     __syncthreads();
     const uint64_t base = s_base;
-    // 5a. positions that need more than a copy: sequence starts (the end sentinel n_ids included), special and unknown ids;
+    // 6a. positions that need more than a copy: sequence starts (the end sentinel n_ids included), special and unknown ids;
     //     in an oversized tile every token (it is copied here)
     {
         const uint32_t tw = (tds[i0 >> 5] >> (i0 & 31)) & ((1u << PER) - 1u);   // PER divides 32: my bits are in one word
         uint64_t seq = tw ? seq_first[i0 >> 5] : 0;         // first sequence of my group of 32 ids; advanced below
-        uint32_t todo = fits ? (tw | slow) : ((1u << PER) - 1u);
+        uint32_t todo = fits ? (tw | spec) : ((1u << PER) - 1u);
 #pragma unroll 1
         while (todo) {
             const uint32_t k = (uint32_t)(__ffs((int)todo) - 1);
@@ -244,12 +266,7 @@ __global__ void __launch_bounds__(DC_T, MINB) decode_gather_kernel(const uint32_
             const uint64_t i = i0 + k;
             if (i > n_ids) break;
             uint32_t rel = p, l = 0;
-#pragma unroll
-            for (int j = 0; j < PER; ++j) {
-                const uint32_t lj = (len16[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
-                rel += (uint32_t)j < k ? lj : 0u;
-                l = (uint32_t)j == k ? lj : l;
-            }
+            dc_locate<PER>(len16, k, rel, l);
             const uint64_t ok = base + rel;
             if ((tw >> k) & 1u) {
                 while (tok_off[seq] - off_base < i) ++seq;   // sequences that start earlier in the group
@@ -280,25 +297,26 @@ __global__ void __launch_bounds__(DC_T, MINB) decode_gather_kernel(const uint32_
         }
     }
     if (!fits) return;
-    // 5b. staging buffer -> output: aligned words, the tile's text shifted by the phase of its first byte
+    // 6b. staging buffer -> output: aligned words, the tile's text shifted by the phase of its first byte
     {
         const uint64_t lim = base + tile_total < out_cap ? base + tile_total : out_cap;   // never write past the caller's buffer
         if (lim <= base) return;
         const uint32_t sh = (uint32_t)(((uintptr_t)out + base) & 3u);
-        const uint64_t a0 = base - sh;                          // (out + a0) is word aligned; may be "before" out for the first tile
-        const uint32_t n_words = (uint32_t)((lim - a0 + 3u) / 4u);
-        for (uint32_t j = t; j < n_words; j += DC_T) {
-            // output word j = tile bytes 4j - sh .. 4j - sh + 3
-            const uint32_t hi = bufw[j], lo = j ? bufw[j - 1] : 0u;
-            const uint32_t w = sh ? __funnelshift_r(lo, hi, 8u * (4u - sh)) : hi;
-            const uint64_t g = a0 + 4ull * j;
-            if (j && g + 4u <= lim) {                          // (j >= 1: g >= base)
-                *reinterpret_cast<uint32_t*>(out + g) = w;
-            } else {
-#pragma unroll
-                for (uint32_t q = 0; q < 4u; ++q)
-                    if (4ull * j + q >= sh && g + q < lim) out[g + q] = (uint8_t)(w >> (8u * q));
-            }
+        uint8_t* const o0 = out + base - sh;                    // word aligned; output word j = tile bytes 4j - sh .. 4j - sh + 3
+        const uint32_t n_bytes = (uint32_t)(lim - base) + sh;   // bytes from o0 to the end of the tile's text
+        const uint32_t n_full = n_bytes >> 2;                   // words 1 .. n_full - 1 are whole words of this tile
+        const uint32_t fs = 8u * (4u - sh);
+        uint32_t* const ow = reinterpret_cast<uint32_t*>(o0);
+        if (sh) {
+            for (uint32_t j = 1u + t; j < n_full; j += DC_T) ow[j] = __funnelshift_r(bufw[j - 1], bufw[j], fs);
+        } else {
+            for (uint32_t j = 1u + t; j < n_full; j += DC_T) ow[j] = bufw[j];
+        }
+        // the two ragged ends, byte by byte: word 0 (bytes sh..3) and the bytes after the last whole word
+        if (t < 8u) {
+            const uint32_t q = t < 4u ? t : 4u * n_full + (t - 4u);      // byte index from o0
+            const bool mine = t < 4u ? (q >= sh && q < n_bytes) : (n_full >= 1u && q < n_bytes);
+            if (mine) o0[q] = reinterpret_cast<const uint8_t*>(bufw)[q - sh];
         }
     }
 }
