@@ -116,7 +116,7 @@ struct TkDeviceTables {
     uint32_t bucket_mask;          // bucket count - 1
     const uint32_t* byte_pair;     // [b0 << 8 | b1] -> rank of the two-byte token, TK_INF if none
     const uint4* vocab_pad16;      // token bytes zero-padded to 16 (tokens longer than that: first 16 bytes)
-    const uint4* vocab_e16;        // byte 0 = token length (0xFF = longer than 15, see vocab_off), bytes 1..15 = the token, zero padded
+    const uint4* vocab_e16;        // token bytes 0..6 | length (0xFF = longer than 15, see vocab_off) | token bytes 7..14; zero padded
     const uint8_t* vocab_bytes;    // concatenated token bytes, rank order
     const uint32_t* vocab_off;     // n_vocab + 1
     const uint8_t* special_bytes;  // concatenated special strings, positional order

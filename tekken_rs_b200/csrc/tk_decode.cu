@@ -58,7 +58,7 @@ __device__ __forceinline__ void mark_boundary(uint32_t* __restrict__ bmask, uint
 //      bytes for the copy come from the same load, issued for all of a thread's ids at once;
 //   2. block scan of the lengths; the tile's total is published for the tiles behind it;
 //   3. the text of the tile is assembled in (zeroed) shared memory at tile-relative positions.  A thread's tokens are
-//      adjacent in the text: it shifts them into a two-word accumulator and stores every word it COMPLETES -- its own
+//      adjacent in the text: it shifts them into an accumulator word and stores every word it COMPLETES -- its own
 //      bytes, zeros elsewhere -- with a plain predicated store; no branch depends on a token's length (round-2 ncu: the
 //      branchy version spent 45 % of the kernel's instructions here at 5-18 active lanes);
 //   4. after a barrier the bytes that are not in a completed word are OR-ed in: every thread's last partial word and
@@ -84,22 +84,22 @@ __device__ __forceinline__ const uint8_t* dc_slow_bytes(const TkDeviceTables& T,
 }
 
 struct DcStream {
-    uint32_t a0, a1;           // bytes not stored yet: a0 = the word being filled, a1 = what spilled over
-    uint32_t wi;               // tile-relative index of that word
+    uint32_t a0;               // the word being filled: my bytes of it, zeros elsewhere
+    uint32_t wi;               // its tile-relative index
     uint32_t fill;             // bytes of it that are decided (0..3 between calls)
 };
-// nb <= 4 bytes of w (the rest of w is zero); branch-free
-__device__ __forceinline__ void dc_append(uint32_t* __restrict__ bufw, DcStream& s, uint32_t w, uint32_t nb) {
+// l <= 7 bytes in (v1:v0), zero beyond l; branch-free: up to two completed words are stored under predicates
+__device__ __forceinline__ void dc_append(uint32_t* __restrict__ bufw, DcStream& s, uint32_t v0, uint32_t v1, uint32_t l) {
     const uint32_t sh = 8u * s.fill;
-    s.a0 |= w << sh;
-    s.a1 |= __funnelshift_l(w, 0u, sh);                     // the bytes of w that do not fit (sh = 0: none)
-    s.fill += nb;
-    const bool full = s.fill >= 4u;
-    if (full) bufw[s.wi] = s.a0;
-    s.a0 = full ? s.a1 : s.a0;
-    s.a1 = full ? 0u : s.a1;
-    s.wi += full ? 1u : 0u;
-    s.fill -= full ? 4u : 0u;
+    s.a0 |= v0 << sh;
+    const uint32_t a1 = __funnelshift_l(v0, v1, sh);        // bits 32..63 of (v1:v0) << sh
+    const uint32_t a2 = __funnelshift_l(v1, 0u, sh);        // bits 64..95
+    const uint32_t end = s.fill + l, c = end >> 2;          // words completed: 0, 1 or 2
+    if (c >= 1u) bufw[s.wi] = s.a0;
+    if (c >= 2u) bufw[s.wi + 1u] = a1;
+    s.a0 = c == 0u ? s.a0 : (c == 1u ? a1 : a2);
+    s.wi += c;
+    s.fill = end & 3u;
 }
 // l bytes that somebody else writes (zeros here)
 __device__ __forceinline__ void dc_gap(uint32_t* __restrict__ bufw, DcStream& s, uint32_t l) {
@@ -179,17 +179,31 @@ __global__ void __launch_bounds__(DC_T, MINB) decode_gather_kernel(const uint32_
     uint32_t len16[PER / 2];
 #pragma unroll
     for (int k = 0; k < PER / 2; ++k) len16[k] = 0u;
-    uint32_t slow = 0, sum = 0;
+    uint32_t slow = 0;
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
-        uint32_t l = e[k].x & 0xFFu;
-        if (l == 0xFFu || (policy == TK_POLICY_KEEP && ((spec >> k) & 1u))) {      // rare: the length is somewhere else
-            l = i0 + k < n_ids ? dc_slow_len(T, policy, __ldg(ids + i0 + k)) : 0u;
-            slow |= l ? 1u << k : 0u;
-        }
-        len16[k >> 1] |= l << (16 * (k & 1));
-        sum += l;
+        const uint32_t l = e[k].y >> 24;
+        slow |= l == 0xFFu ? 1u << k : 0u;
+        len16[k >> 1] |= (l == 0xFFu ? 0u : l) << (16 * (k & 1));
     }
+    if (policy == TK_POLICY_KEEP) slow |= spec;
+    if (slow) {                                             // rare: lengths that are not in a cell
+        uint32_t todo = slow;
+        slow = 0;
+#pragma unroll 1
+        while (todo) {
+            const uint32_t k = (uint32_t)(__ffs((int)todo) - 1);
+            todo &= todo - 1;
+            const uint32_t l = i0 + k < n_ids ? dc_slow_len(T, policy, __ldg(ids + i0 + k)) : 0u;
+            if (!l) continue;
+            slow |= 1u << k;
+#pragma unroll
+            for (int j = 0; j < PER; ++j) len16[j >> 1] |= (uint32_t)j == k ? l << (16 * (j & 1)) : 0u;
+        }
+    }
+    uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < PER / 2; ++k) sum += (len16[k] & 0xFFFFu) + (len16[k] >> 16);
     uint32_t inc = sum;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -206,7 +220,7 @@ __global__ void __launch_bounds__(DC_T, MINB) decode_gather_kernel(const uint32_
     const uint32_t p = before + inc - sum;                 // my first byte, tile-relative
     // 3. assemble: plain stores of completed words
     DcStream s;
-    s.a0 = s.a1 = 0u; s.wi = p >> 2; s.fill = p & 3u;
+    s.a0 = 0u; s.wi = p >> 2; s.fill = p & 3u;
     if (fits) {
 #pragma unroll
         for (int k = 0; k < PER; ++k) {
@@ -214,12 +228,11 @@ __global__ void __launch_bounds__(DC_T, MINB) decode_gather_kernel(const uint32_
             if ((slow >> k) & 1u) {                        // its bytes come in step 4
                 dc_gap(bufw, s, l);
             } else {
-                dc_append(bufw, s, e[k].x >> 8, l < 3u ? l : 3u);
-                dc_append(bufw, s, e[k].y, l < 3u ? 0u : (l < 7u ? l - 3u : 4u));
+                dc_append(bufw, s, e[k].x, e[k].y & 0x00FFFFFFu, l < 7u ? l : 7u);
                 if (l > 7u) {                               // the second half of the cell (a fraction of a percent of the ids)
                     const uint2 c = __ldg(reinterpret_cast<const uint2*>(T.vocab_e16 + (__ldg(ids + i0 + k) - T.num_special)) + 1);
-                    dc_append(bufw, s, c.x, l < 11u ? l - 7u : 4u);
-                    dc_append(bufw, s, c.y, l < 11u ? 0u : l - 11u);
+                    dc_append(bufw, s, c.x, 0u, l < 11u ? l - 7u : 4u);
+                    dc_append(bufw, s, c.y, 0u, l < 11u ? 0u : l - 11u);
                 }
             }
         }

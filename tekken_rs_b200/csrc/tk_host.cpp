@@ -734,10 +734,15 @@ HostModel HostModel::build(const std::vector<VocabEntry>& vocab, const std::vect
         for (size_t r = 0; r < n_vocab; ++r) {
             uint32_t len = m.vocab_off[r + 1] - m.vocab_off[r];
             memcpy(&m.vocab_pad16[16 * r], &m.vocab_bytes[m.vocab_off[r]], std::min<uint32_t>(len, 16));
-            // decode's cell: the length, then 15 bytes -- the first 8-byte load gives the length and 7 bytes, which is the
-            // whole token for all but a fraction of a percent of the ids in text.  0xFF = longer than 15 (see vocab_off)
-            if (len <= 15) { m.vocab_e16[16 * r] = (uint8_t)len; memcpy(&m.vocab_e16[16 * r + 1], &m.vocab_bytes[m.vocab_off[r]], len); }
-            else m.vocab_e16[16 * r] = 0xFF;
+            // decode's cell: bytes 0..6, the length, bytes 7..14 -- the first 8-byte load gives the length and 7 bytes,
+            // which is the whole token for all but a fraction of a percent of the ids in text.  0xFF = longer than 15
+            // bytes (see vocab_off)
+            if (len <= 15) {
+                uint8_t* c = &m.vocab_e16[16 * r];
+                const uint8_t* b = &m.vocab_bytes[m.vocab_off[r]];
+                for (uint32_t j = 0; j < len; ++j) c[j < 7 ? j : j + 1] = b[j];
+                c[7] = (uint8_t)len;
+            } else m.vocab_e16[16 * r + 7] = 0xFF;
         }
     }
     // first-round pair ranks (both parts are single bytes): direct-indexed, no probing

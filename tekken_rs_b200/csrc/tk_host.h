@@ -81,7 +81,7 @@ struct HostModel {
     uint32_t bucket_mask = 0;
     std::vector<uint32_t> byte_pair;                          // 65536 entries, direct-indexed
     std::vector<uint8_t> vocab_pad16;                         // 16 bytes per rank (the encoder's whole-piece check)
-    std::vector<uint8_t> vocab_e16;                           // 16 bytes per rank: length (0xFF = longer than 15), then 15 token bytes; decode's gather source
+    std::vector<uint8_t> vocab_e16;                           // 16 bytes per rank: bytes 0..6, length (0xFF = longer than 15), bytes 7..14; decode's gather source
     std::vector<uint8_t> special_bytes;
     std::vector<uint32_t> special_off;
     size_t n_pairs = 0;
