@@ -126,7 +126,7 @@ __device__ __forceinline__ void dc_locate(const uint32_t (&len16)[PER / 2], uint
 #define DC_PER 8
 #endif
 #ifndef DC_MINB
-#define DC_MINB 4
+#define DC_MINB 5     // 48 registers: measured 3.35 ms for the bench batch (4 blocks, 62 registers: 3.56; 6 blocks, 40 registers and spills: 3.30)
 #endif
 template <int PER, int MINB>
 __global__ void __launch_bounds__(DC_T, MINB) decode_gather_kernel(const uint32_t* __restrict__ ids, uint64_t n_ids,
@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(DC_T, MINB) decode_gather_kernel(const uint32_
     __syncthreads();
     const uint32_t tile = s_tile;
     const uint64_t i0 = (uint64_t)tile * TILE + (uint64_t)t * PER;
+    const uint32_t tw = (__ldg(tds + (i0 >> 5)) >> (i0 & 31)) & ((1u << PER) - 1u);   // sequence starts among my ids (PER divides 32)
     // 1. the first half of one table cell per id: the length and 7 bytes.  Ids without a cell: special and unknown ids
     //    (`spec`: no bytes unless Keep, looked at again in step 6), positions past the end.
     uint2 e[PER];
@@ -269,7 +270,6 @@ __global__ void __launch_bounds__(DC_T, MINB) decode_gather_kernel(const uint32_
     // 6a. positions that need more than a copy: sequence starts (the end sentinel n_ids included), special and unknown ids;
     //     in an oversized tile every token (it is copied here)
     {
-        const uint32_t tw = (tds[i0 >> 5] >> (i0 & 31)) & ((1u << PER) - 1u);   // PER divides 32: my bits are in one word
         uint64_t seq = tw ? seq_first[i0 >> 5] : 0;         // first sequence of my group of 32 ids; advanced below
         uint32_t todo = fits ? (tw | spec) : ((1u << PER) - 1u);
 #pragma unroll 1
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(DC_T, MINB) decode_gather_kernel(const uint32_
             const uint32_t v = __ldg(ids + i);
             if (v < T.num_special) {
                 // a special id ends the ordinary run before it and starts a new one after it
-                mark_boundary(bmask, ok, out_cap);
+                if (!((tw >> k) & 1u)) mark_boundary(bmask, ok, out_cap);
                 if (policy == TK_POLICY_RAISE) {
                     const uint64_t d = seq_of(tok_off, off_base, n_docs, i);
                     atomicMin(&docerr[d].sp_tok, (unsigned long long)i);
