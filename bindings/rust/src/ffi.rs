@@ -143,6 +143,8 @@ extern "C" {
     pub fn tk_status_name(status: c_int) -> *const c_char;
     pub fn tk_set_chunk_bytes(bytes: u64);
     pub fn tk_debug_bounds_violations(t: *const tk_tokenizer, detail4: *mut u64) -> i64;
+    pub fn tk_set_pack_ids(mode: c_int);
+    pub fn tk_debug_unpack_ids(src: *const u8, n: usize, bits: c_int, dst: *mut u32) -> c_int;
     pub fn tk_kernel_launch_count() -> u64;
     pub fn tk_set_stage_timing(t: *mut tk_tokenizer, enabled: c_int);
     pub fn tk_last_stage_times(t: *const tk_tokenizer, names: *mut *const c_char, ms: *mut f32, cap: usize) -> usize;

@@ -241,10 +241,20 @@ const char *tk_status_name(int status);
    0 restores the default of 128 MB, also settable with TEKKEN_B200_CHUNK_MB).  The tests use it to exercise the
    chunk-boundary and document-slicing logic on small inputs. */
 void tk_set_chunk_bytes(uint64_t bytes);
+/* How the ids of a host-buffer encode cross PCIe (process-wide; also TEKKEN_B200_PACK_IDS): -1 = as an 18- or 24-bit
+   stream (the narrowest width the vocabulary fits) for calls of 32 MB of text and more, widened to uint32 on the host
+   while the next chunk is on the bus -- the default; 0 = always as uint32; 18 / 24 = that width for every call whose
+   ids fit.  The result is the same array either way. */
+void tk_set_pack_ids(int mode);
 /* Bounds-checked debug build (compile the library with -DTK_DEBUG_BOUNDS; compute-sanitizer substitute): number of
    out-of-range stores the encode kernels of the handle's device refused since the last call of this function, with
    detail4 = {count, source line, index, limit} of the first one.  -1 in a regular build (the checks compile away). */
 long long tk_debug_bounds_violations(const tk_tokenizer *t, uint64_t *detail4);
+/* Test hook for the host half of the packed-id download (large host-buffer encodes send their ids over PCIe as an
+   18- or 24-bit little-endian bit stream, 16 ids per group, and widen them on the host): dst[0..n) = the ids of the
+   stream at src, using the same multi-threaded routine the engine uses.  src must be readable 32 bytes past the
+   stream's end. */
+int tk_debug_unpack_ids(const uint8_t *src, size_t n, int bits, uint32_t *dst);
 /* Kernel launches issued by this process so far (for benchmark accounting). */
 uint64_t tk_kernel_launch_count(void);
 /* Per-stage device time of the most recent tk_encode_batch_device call on this handle, in

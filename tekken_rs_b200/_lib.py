@@ -88,6 +88,8 @@ PROTOTYPES = {
     "tk_status_name": (ctypes.c_char_p, [ctypes.c_int]),
     "tk_set_chunk_bytes": (None, [ctypes.c_uint64]),
     "tk_debug_bounds_violations": (ctypes.c_longlong, [c_vp, c_u64p]),
+    "tk_set_pack_ids": (None, [ctypes.c_int]),
+    "tk_debug_unpack_ids": (ctypes.c_int, [c_vp, ctypes.c_size_t, ctypes.c_int, c_vp]),
     "tk_kernel_launch_count": (ctypes.c_uint64, []),
     "tk_set_stage_timing": (None, [c_vp, ctypes.c_int]),
     "tk_last_encode_counters": (ctypes.c_size_t, [c_vp, c_u64p, ctypes.c_size_t]),

@@ -233,9 +233,19 @@ struct tk_tokenizer {
     // downloads shared the bus from start to end.  With the kernels free to run ahead the text is up after half the
     // call and the ids have the bus to themselves for the rest.
     struct OutSlot {
-        DevBuf tok, off;
+        DevBuf tok, off, pack;             // pack: the ids as an 18/24-bit stream (what crosses PCIe in large calls)
         cudaEvent_t ev_out = nullptr;      // the slot's ids have left
     };
+    // pinned landing buffers of the packed ids; a host thread widens them into the result (encode_worker)
+    struct PackStage {
+        uint8_t* h = nullptr;
+        size_t cap = 0;
+        cudaEvent_t ev = nullptr;          // the packed ids have arrived
+        cudaEvent_t ev_packed = nullptr;   // the pack kernel has run
+        std::atomic<int> busy{0};
+    };
+    static constexpr int kPackStages = 4;
+    PackStage pstage[kPackStages];
     static constexpr int kOutSlots = 12;
     OutSlot oslot[kOutSlots];
     struct DecSlot {
@@ -248,7 +258,7 @@ struct tk_tokenizer {
         tkk::DecodeLayout L;
     };
     DecSlot dslot[kSlots];         // host-buffer decode
-    cudaStream_t pipe_st[3] = {nullptr, nullptr, nullptr};   // ... on an upload, a kernel and a download stream
+    cudaStream_t pipe_st[4] = {nullptr, nullptr, nullptr, nullptr};   // ... on an upload, a kernel, a download and a pack stream
     EncSlot dev_slot;              // device-pointer encode (caller's stream)
     // the latency path (tk_encode of a short text): mapped pinned in/out buffers + a stream per slot
     struct FastSlot {
@@ -463,8 +473,13 @@ extern "C" void tk_free(tk_tokenizer* t) {
         }
         for (auto& ps : t->pipe_st) if (ps) { cudaStreamSynchronize(ps); cudaStreamDestroy(ps); }
         for (auto& sl : t->slot) drop(sl);
+        for (auto& ps : t->pstage) {
+            if (ps.h) cudaFreeHost(ps.h);
+            if (ps.ev) cudaEventDestroy(ps.ev);
+            if (ps.ev_packed) cudaEventDestroy(ps.ev_packed);
+        }
         for (auto& o : t->oslot) {
-            o.tok.release(); o.off.release();
+            o.tok.release(); o.off.release(); o.pack.release();
             if (o.ev_out) cudaEventDestroy(o.ev_out);
         }
         for (auto& d : t->dslot) {
@@ -718,11 +733,73 @@ class CopyPool {
         while (job->done.load(std::memory_order_acquire) < job->pieces) std::this_thread::yield();
     }
 
+    // dst[0 .. n) = the ids of a `bits`-bit stream (tkk::pack_ids); src is readable 32 bytes past its end
+    void parallel_unpack(uint32_t* dst, const uint8_t* src, size_t n, int bits) {
+        if (!n) return;
+        auto job = std::make_shared<Job>();
+        job->dst = (char*)dst; job->src = (const char*)src; job->n = n; job->bits = bits;
+        job->pieces = (n + kIdPiece - 1) / kIdPiece;
+        const size_t helpers = std::min(threads_.size(), job->pieces - 1);
+        if (helpers) {
+            std::lock_guard<std::mutex> g(mu_);
+            for (size_t i = 0; i < helpers; ++i) q_.push_back(job);
+        }
+        if (helpers) cv_.notify_all();
+        run(*job);
+        while (job->done.load(std::memory_order_acquire) < job->pieces) std::this_thread::yield();
+    }
+
   private:
+    static constexpr size_t kIdPiece = 1 << 18;      // ids per piece of an unpack job (a multiple of 16)
     struct Job {
         char* dst; const char* src; size_t n, pieces;
+        int bits = 0;                                 // 0: copy n bytes; 18 / 24: widen n ids
         std::atomic<size_t> next{0}, done{0};
     };
+    static inline uint32_t unpack_one(const uint8_t* src, size_t i, int bits) {
+        const uint64_t bit = (uint64_t)i * (uint64_t)bits;
+        uint32_t w;
+        memcpy(&w, src + (bit >> 3), 4);
+        return (w >> (bit & 7)) & ((1u << bits) - 1u);
+    }
+#if defined(__x86_64__)
+    // ids i0 .. i0 + n of the stream -> dst[0 .. n).  Eight ids per step: two 16-byte loads (4 ids = bits / 2 bytes
+    // apart), a byte shuffle that puts the three bytes of every id into its lane, a per-lane shift, a mask, and a
+    // non-temporal store (the result is not read again by this thread).
+    __attribute__((target("avx2"))) static void unpack_avx2(uint32_t* dst, const uint8_t* src, size_t i0, size_t n, int bits) {
+        size_t i = 0;
+        while (i < n && ((uintptr_t)(dst + i) & 31)) { dst[i] = unpack_one(src, i0 + i, bits); ++i; }
+        const uint64_t bit0 = (uint64_t)(i0 + i) * (uint64_t)bits;
+        const uint32_t s0 = (uint32_t)(bit0 & 7);    // bit phase of the first vector id; constant from step to step
+        alignas(32) int8_t sh8[32];
+        alignas(32) uint32_t sv[8];
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t bo = s0 + (uint32_t)bits * (uint32_t)j;
+            for (int b = 0; b < 3; ++b) sh8[4 * j + b] = sh8[16 + 4 * j + b] = (int8_t)((bo >> 3) + b);
+            sh8[4 * j + 3] = sh8[16 + 4 * j + 3] = (int8_t)-1;
+            sv[j] = sv[4 + j] = bo & 7;
+        }
+        const __m256i shuf = _mm256_load_si256((const __m256i*)sh8), shv = _mm256_load_si256((const __m256i*)sv);
+        const __m256i mask = _mm256_set1_epi32((int)((1u << bits) - 1u));
+        const size_t lane = (size_t)bits / 2;          // bytes per 4 ids
+        const uint8_t* p = src + (bit0 >> 3);
+        for (; i + 8 <= n; i += 8, p += 2 * lane) {
+            const __m128i lo = _mm_loadu_si128((const __m128i*)p), hi = _mm_loadu_si128((const __m128i*)(p + lane));
+            __m256i v = _mm256_set_m128i(hi, lo);
+            v = _mm256_and_si256(_mm256_srlv_epi32(_mm256_shuffle_epi8(v, shuf), shv), mask);
+            _mm256_stream_si256((__m256i*)(dst + i), v);
+        }
+        _mm_sfence();
+        for (; i < n; ++i) dst[i] = unpack_one(src, i0 + i, bits);
+    }
+#endif
+    static void unpack_piece(uint32_t* dst, const uint8_t* src, size_t i0, size_t n, int bits) {
+#if defined(__x86_64__)
+        static const bool avx2 = __builtin_cpu_supports("avx2");
+        if (avx2) { unpack_avx2(dst, src, i0, n, bits); return; }
+#endif
+        for (size_t i = 0; i < n; ++i) dst[i] = unpack_one(src, i0 + i, bits);
+    }
     // The destination is a pinned staging buffer that the DMA engine reads next and the CPU never reads back: write it
     // with non-temporal stores (no read-for-ownership of the destination lines, no cache pollution).  glibc's memcpy
     // only switches to them far above the 1 MB pieces used here.
@@ -757,8 +834,13 @@ class CopyPool {
         for (;;) {
             const size_t p = j.next.fetch_add(1);
             if (p >= j.pieces) return;
-            const size_t o = p * kPiece, len = std::min(kPiece, j.n - o);
-            copy_piece(j.dst + o, j.src + o, len);
+            if (j.bits) {
+                const size_t o = p * kIdPiece, len = std::min(kIdPiece, j.n - o);
+                unpack_piece((uint32_t*)j.dst + o, (const uint8_t*)j.src, o, len, j.bits);
+            } else {
+                const size_t o = p * kPiece, len = std::min(kPiece, j.n - o);
+                copy_piece(j.dst + o, j.src + o, len);
+            }
             j.done.fetch_add(1, std::memory_order_release);
         }
     }
@@ -862,6 +944,7 @@ struct EncodeJob {
     std::vector<Chunk> chunks;
     uint64_t forced_cap = 0;          // second attempt: worst-case output size
     float ratio_hint = 0.f;           // ids per byte recent calls on this handle needed
+    int pack_bits = 0;                // 18 / 24: the ids cross PCIe as a bit stream and are widened on the host; 0: as they are
     // progress shared by the device workers
     std::mutex mu;
     std::condition_variable cv;
@@ -894,6 +977,7 @@ const uint64_t kDefaultChunkBytes = [] {
     return (uint64_t)(mb > 0 ? mb : 128) << 20;
 }();
 std::atomic<uint64_t> g_chunk_bytes{0};                     // tk_set_chunk_bytes; 0 = the default
+std::atomic<int> g_pack_mode{[] { const char* e = getenv("TEKKEN_B200_PACK_IDS"); return e ? atoi(e) : -1; }()};   // tk_set_pack_ids
 
 }  // namespace
 
@@ -914,7 +998,7 @@ static int encode_worker(tk_tokenizer* t, EncodeJob& J, size_t g, size_t stride)
         if (e_ != cudaSuccess) return bail(fail(TK_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)));         \
     } while (0)
     for (auto& ps : t->pipe_st) if (!ps) W_CUDA(cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
-    cudaStream_t st_up = t->pipe_st[0], st_k = t->pipe_st[1], st_down = t->pipe_st[2];
+    cudaStream_t st_up = t->pipe_st[0], st_k = t->pipe_st[1], st_down = t->pipe_st[2], st_pack = t->pipe_st[3];
     std::vector<size_t> mine;
     for (size_t c = g; c < J.chunks.size(); c += stride) mine.push_back(c);
     const size_t n_mine = mine.size();
@@ -1051,6 +1135,48 @@ static int encode_worker(tk_tokenizer* t, EncodeJob& J, size_t g, size_t stride)
         return kick(i);
     };
 
+    // Packed ids (large calls): the download lands in a pinned stage and this thread widens it into the result while
+    // the next chunk's ids are on the bus.  1.64 GB of ids per GB of text become 0.92 GB (18 bits) on the link that
+    // bounds the call.
+    struct UnpackTask { int stage; uint32_t* dst; uint64_t n; };
+    std::deque<UnpackTask> uq;
+    std::mutex umu;
+    std::condition_variable ucv;
+    bool u_done = false;
+    std::thread unpacker;
+    struct UnpackJoin {
+        std::thread& th; std::mutex& mu; std::condition_variable& cv; bool& done;
+        void finish() {
+            if (!th.joinable()) return;
+            { std::lock_guard<std::mutex> g(mu); done = true; }
+            cv.notify_all();
+            th.join();
+        }
+        ~UnpackJoin() { finish(); }
+    } unpack_join{unpacker, umu, ucv, u_done};
+    const int pack_bits = J.pack_bits;
+    size_t n_packed = 0;
+    if (pack_bits) {
+        unpacker = std::thread([&] {
+            DeviceGuard g2(t->device);
+            for (;;) {
+                UnpackTask task;
+                {
+                    std::unique_lock<std::mutex> lk(umu);
+                    ucv.wait(lk, [&] { return u_done || !uq.empty(); });
+                    if (uq.empty()) return;
+                    task = uq.front();
+                    uq.pop_front();
+                }
+                tk_tokenizer::PackStage& ps = t->pstage[task.stage];
+                const cudaError_t e = cudaEventSynchronize(ps.ev);
+                if (e != cudaSuccess) J.fail_with(TK_ERR_CUDA, std::string("copying ids back: ") + cudaGetErrorString(e));
+                else if (!J.abort.load()) CopyPool::get().parallel_unpack(task.dst, ps.h, task.n, pack_bits);
+                ps.busy.store(0, std::memory_order_release);
+            }
+        });
+    }
+
     // kAhead chunks are always queued ahead, so this thread sits in the wait for chunk i when it completes and its
     // ids start their way back at once
     constexpr size_t kAhead = tk_tokenizer::kSlots - 1;
@@ -1112,7 +1238,39 @@ static int encode_worker(tk_tokenizer* t, EncodeJob& J, size_t g, size_t stride)
         if (kTrace) thost[3 + i * 3] = host_now();
         mark(i, 4, st_down);
         tk_tokenizer::OutSlot& o = t->oslot[i % tk_tokenizer::kOutSlots];
-        if (n_tok) e = cudaMemcpyAsync(J.h_tok + my_prefix, o.tok.p, n_tok * 4, cudaMemcpyDeviceToHost, st_down);
+        // a landing buffer that has been widened already; if the host threads are behind (all four still busy: a small
+        // or crowded host) this chunk's ids travel as they are -- the link never waits for the CPU
+        int stage = -1;
+        if (n_tok && pack_bits)
+            for (int k = 0; k < tk_tokenizer::kPackStages; ++k)
+                if (!t->pstage[k].busy.load(std::memory_order_acquire)) { stage = k; break; }
+        if (stage >= 0) {
+            tk_tokenizer::PackStage& ps = t->pstage[stage];
+            const size_t pb = tkk::packed_id_bytes(n_tok, pack_bits);
+            if (ps.cap < pb + 64) {
+                if (ps.h) cudaFreeHost(ps.h);
+                ps.h = nullptr; ps.cap = 0;
+                const size_t want = pb + pb / 8 + 4096;
+                W_CUDA(cudaHostAlloc((void**)&ps.h, want, cudaHostAllocPortable));
+                ps.cap = want;
+            }
+            if (!ps.ev) { W_CUDA(cudaEventCreateWithFlags(&ps.ev, cudaEventDisableTiming)); W_CUDA(cudaEventCreateWithFlags(&ps.ev_packed, cudaEventDisableTiming)); }
+            // the slot's pack buffer was last read by the download kOutSlots chunks ago (o.ev_out); packing on its own
+            // stream overlaps the previous chunk's download
+            if (i >= (size_t)tk_tokenizer::kOutSlots) W_CUDA(cudaStreamWaitEvent(st_pack, o.ev_out, 0));
+            W_CUDA(o.pack.ensure(pb));
+            W_CUDA(tkk::pack_ids((const uint32_t*)o.tok.p, n_tok, pack_bits, o.pack.p, st_pack));
+            W_CUDA(cudaEventRecord(ps.ev_packed, st_pack));
+            W_CUDA(cudaStreamWaitEvent(st_down, ps.ev_packed, 0));
+            e = cudaMemcpyAsync(ps.h, o.pack.p, pb, cudaMemcpyDeviceToHost, st_down);
+            if (e == cudaSuccess) e = cudaEventRecord(ps.ev, st_down);
+            if (e == cudaSuccess) {
+                ps.busy.store(1, std::memory_order_release);
+                { std::lock_guard<std::mutex> g2(umu); uq.push_back({stage, J.h_tok + my_prefix, n_tok}); }
+                ++n_packed;
+                ucv.notify_all();
+            }
+        } else if (n_tok) e = cudaMemcpyAsync(J.h_tok + my_prefix, o.tok.p, n_tok * 4, cudaMemcpyDeviceToHost, st_down);
         if (e == cudaSuccess && !c.partial && c.n_docs)
             e = cudaMemcpyAsync(J.h_off + c.doc_begin, o.off.p, c.n_docs * 8, cudaMemcpyDeviceToHost, st_down);
         mark(i, 5, st_down);
@@ -1123,6 +1281,8 @@ static int encode_worker(tk_tokenizer* t, EncodeJob& J, size_t g, size_t stride)
     {
         cudaError_t e = cudaStreamSynchronize(st_down);
         if (e != cudaSuccess) return bail(fail(TK_ERR_CUDA, "copying ids back: %s", cudaGetErrorString(e)));
+        unpack_join.finish();                                  // the last chunks' ids are in the result
+        if (J.abort.load()) return bail(J.rc ? J.rc : TK_ERR_CUDA);
     }
     // chunk-local token offsets -> batch offsets (every prefix is known by now: my last chunk waited for them)
     for (size_t i = 0; i < n_mine; ++i) {
@@ -1139,7 +1299,8 @@ static int encode_worker(tk_tokenizer* t, EncodeJob& J, size_t g, size_t stride)
             fprintf(stderr, "[tekken_b200 trace] %d/%3zu: %7.2f..%7.2f | %7.2f..%7.2f | %7.2f..%7.2f | %7.2f | %7.2f..%7.2f\n", t->device, mine[i],
                     thost[1 + i * 3] - thost[0], thost[2 + i * 3] - thost[0], v[0], v[1], v[2], v[3], thost[3 + i * 3] - thost[0], v[4], v[5]);
         }
-        fprintf(stderr, "[tekken_b200 trace] device %d: all copies done at host %.2f ms\n", t->device, host_now() - thost[0]);
+        fprintf(stderr, "[tekken_b200 trace] device %d: all copies done at host %.2f ms; %zu of %zu chunks came back as %d-bit ids\n", t->device,
+                host_now() - thost[0], n_packed, n_mine, pack_bits);
     }
 #undef W_CUDA
     return TK_OK;
@@ -1171,6 +1332,17 @@ static int encode_batch_engine(tk_tokenizer* const* handles, size_t n_handles, c
         J.pageable = pageable && total >= (1u << 16);       // small inputs: the driver's own staging is as good
         J.forced_cap = attempt ? total + 2 * (uint64_t)n_docs + 2 : 0;
         J.ratio_hint = handles[0]->ratio_hint.load();
+        {
+            // tk_set_pack_ids / TEKKEN_B200_PACK_IDS: 0 = never, 18 / 24 = that width whenever the ids fit, -1 (default) =
+            // the narrowest width that fits, for calls of 32 MB and more (below that the extra kernel and host pass cost
+            // more than the bytes they save)
+            const int mode = g_pack_mode.load();
+            const uint64_t n_ids_max = (uint64_t)handles[0]->tables.n_vocab + handles[0]->tables.num_special;
+            int bits = n_ids_max <= (1u << 18) ? 18 : n_ids_max <= (1u << 24) ? 24 : 0;
+            if (mode == 24 && bits) bits = 24;
+            if (mode == 0 || (mode < 0 && total < (32u << 20))) bits = 0;
+            J.pack_bits = bits;
+        }
         // chunks small enough that every device gets several, large enough to keep the launch overhead low
         uint64_t chunk = g_chunk_bytes.load() ? g_chunk_bytes.load() : kDefaultChunkBytes;
         if (n_handles > 1) chunk = std::max<uint64_t>(4u << 20, std::min<uint64_t>(chunk, total / (n_handles * 4) + 1));
@@ -1902,6 +2074,14 @@ extern "C" int tk_shard_plan(const uint64_t* doc_off, size_t n_docs, size_t n_sh
 }
 
 extern "C" void tk_set_chunk_bytes(uint64_t bytes) { g_chunk_bytes.store(bytes ? std::max<uint64_t>(bytes, 4096) : 0); }
+
+extern "C" void tk_set_pack_ids(int mode) { g_pack_mode.store(mode == 0 || mode == 18 || mode == 24 ? mode : -1); }
+
+extern "C" int tk_debug_unpack_ids(const uint8_t* src, size_t n, int bits, uint32_t* dst) {
+    if ((bits != 18 && bits != 24) || (n && (!src || !dst))) return fail(TK_ERR_INVALID_ARGUMENT, "bits must be 18 or 24");
+    CopyPool::get().parallel_unpack(dst, src, n, bits);
+    return TK_OK;
+}
 
 extern "C" long long tk_debug_bounds_violations(const tk_tokenizer* t, uint64_t* detail4) {
     if (!t || t->device < 0) return -1;

@@ -2033,4 +2033,47 @@ cudaError_t encode_small(const TkDeviceTables& T, const uint8_t* d_text, uint32_
     return encode_small_launch(T, d_text, n, add_bos, add_eos, d_out, seq, st);
 }
 
+// =====================================================================================================
+// Id packing for the trip over PCIe (host-buffer calls): ids are < 2^18 for Tekken (131,072 + specials), so 18 of the
+// 32 bits carry everything.  One thread packs 16 ids into bits / 2 words; all shifts are compile-time constants.
+// =====================================================================================================
+template <int BITS>
+__global__ void __launch_bounds__(256) pack_ids_kernel(const uint32_t* __restrict__ ids, uint64_t n, uint32_t* __restrict__ out) {
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;       // group of 16 ids
+    const uint64_t i0 = g * 16u;
+    if (i0 >= n) return;
+    uint32_t v[16];
+    if (i0 + 16u <= n && ((uintptr_t)ids & 15u) == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(ids + i0) + q);
+            v[4 * q] = a.x; v[4 * q + 1] = a.y; v[4 * q + 2] = a.z; v[4 * q + 3] = a.w;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = i0 + k < n ? __ldg(ids + i0 + k) : 0u;
+    }
+    constexpr int W = BITS / 2;
+    constexpr uint32_t MASK = (1u << BITS) - 1u;
+    uint32_t* o = out + g * W;
+    unsigned long long acc = 0;
+    int fill = 0, wi = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        acc |= (unsigned long long)(v[k] & MASK) << fill;
+        fill += BITS;
+        if (fill >= 32) { o[wi++] = (uint32_t)acc; acc >>= 32; fill -= 32; }
+    }
+}
+
+cudaError_t pack_ids(const uint32_t* d_ids, uint64_t n, int bits, void* d_out, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    const unsigned blocks = (unsigned)(((n + 15) / 16 + 255) / 256);
+    if (bits == 18) pack_ids_kernel<18><<<blocks, 256, 0, st>>>(d_ids, n, (uint32_t*)d_out);
+    else if (bits == 24) pack_ids_kernel<24><<<blocks, 256, 0, st>>>(d_ids, n, (uint32_t*)d_out);
+    else return cudaErrorInvalidValue;
+    count_launch();
+    return cudaGetLastError();
+}
+
 }  // namespace tkk

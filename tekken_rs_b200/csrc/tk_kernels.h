@@ -125,4 +125,10 @@ long long debug_bounds_violations(unsigned long long* out4);   // -1: not a -DTK
 uint64_t launch_count();
 void count_launch();
 
+// ids -> a little-endian bit stream of `bits` (18 or 24) bits per id, 16 ids per group of bits / 2 words; the host-buffer
+// engine sends this over PCIe instead of the 32-bit ids and widens it on the host (tk_api.cu).  d_out holds
+// packed_id_bytes(n, bits) bytes.
+inline size_t packed_id_bytes(uint64_t n, int bits) { return (size_t)((n + 15) / 16) * (size_t)bits * 2; }
+cudaError_t pack_ids(const uint32_t* d_ids, uint64_t n, int bits, void* d_out, cudaStream_t st);
+
 }  // namespace tkk

@@ -379,6 +379,11 @@ def set_chunk_bytes(n: int):
     _lib.load().tk_set_chunk_bytes(int(n))
 
 
+def set_pack_ids(mode: int):
+    """Tuning knob: how ids cross PCIe in host-buffer encodes (-1 default: 18/24-bit stream for large calls; 0 never; 18 / 24 always)."""
+    _lib.load().tk_set_pack_ids(int(mode))
+
+
 def audio_token_count(cfg: dict, n_samples: int):
     """(padded samples, number of [AUDIO] ids) for a clip under an AudioConfig given as the tekken.json `audio` dict."""
     lib = _lib.load()

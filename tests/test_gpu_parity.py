@@ -137,7 +137,7 @@ def test_host_engine_chunks_slices_and_devices(gpu_tok, oracle, tekken_json):
     # context-free piece boundaries, chunks dealt to several handles with the ids landing in document order, pageable
     # and page-locked callers.  Small chunk sizes make all of that happen on a few MB.
     import torch
-    from tekken_rs_b200 import encode_batch_multi, set_chunk_bytes
+    from tekken_rs_b200 import encode_batch_multi, set_chunk_bytes, set_pack_ids
     rng = random.Random(5)
     big = corpus.english_like(3 << 20, 99)                                   # sliced (many cut points)
     nocut = ("x" * 700000).encode()                                          # no cut point at all: one piece of work
@@ -149,8 +149,11 @@ def test_host_engine_chunks_slices_and_devices(gpu_tok, oracle, tekken_json):
     want, woff = oracle.encode_batch_np(data, off, True, True, n_threads=8)
     others = [Tekkenizer.from_file(tekken_json, device=0) for _ in range(2)]
     try:
-        for chunk in (64 << 10, 300 << 10, 1 << 20, 0):
+        # ... and the ids come back as uint32 (0), as an 18- or 24-bit stream widened on the host, or however the
+        # library decides for a call of this size (-1)
+        for chunk, pack in ((64 << 10, 18), (300 << 10, 24), (1 << 20, 0), (0, -1), (0, 18)):
             set_chunk_bytes(chunk)
+            set_pack_ids(pack)
             ids, toff = gpu_tok.encode_batch_np(data, off, True, True)                       # pageable caller memory
             assert np.array_equal(toff, woff) and np.array_equal(ids, want), "chunk %d" % chunk
             ids, toff = encode_batch_multi([gpu_tok] + others, data, off, True, True)       # three pipelines, one result
@@ -181,9 +184,12 @@ def test_host_engine_chunks_slices_and_devices(gpu_tok, oracle, tekken_json):
         set_chunk_bytes(64 << 10)
         skew = [b" " * 60000 + b"x"] + ["".join(chr(rng.randint(0x4E00, 0x9FA5)) for _ in range(300)).encode() for _ in range(2000)]
         sdata, soff = _pack(skew)
-        assert_same_batch(gpu_tok, oracle, sdata, soff, True, True)
+        for pack in (0, 18):
+            set_pack_ids(pack)
+            assert_same_batch(gpu_tok, oracle, sdata, soff, True, True)
     finally:
         set_chunk_bytes(0)
+        set_pack_ids(-1)
         for t in others:
             t.close()
 

@@ -228,3 +228,34 @@ def test_audio_token_counting(host_tok, tekken_json):
         with pytest.raises(TokenizerError) as e:
             Tekkenizer.from_file(p, device=-1)
         assert e.value.kind == "TokenNotFound"
+
+
+def _pack_ids_reference(ids: np.ndarray, bits: int) -> np.ndarray:
+    """The layout tkk::pack_ids writes: a little-endian bit stream, `bits` bits per id, padded to groups of 16 ids."""
+    n = len(ids)
+    groups = (n + 15) // 16
+    padded = np.zeros(groups * 16, dtype=np.uint64)
+    padded[:n] = ids
+    bit_matrix = ((padded[:, None] >> np.arange(bits, dtype=np.uint64)[None, :]) & 1).astype(np.uint8)   # id x bit, LSB first
+    return np.packbits(bit_matrix.reshape(-1), bitorder="little")
+
+
+@pytest.mark.parametrize("bits", [18, 24])
+def test_packed_id_stream_is_widened_exactly(bits):
+    """Host half of the packed download: every length (vector body, ragged head and tail), every destination
+    alignment, several threads' worth of ids."""
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    for n in [0, 1, 3, 7, 8, 15, 16, 17, 31, 33, 1000, (1 << 18) - 1, (1 << 18) + 5, 3 * (1 << 18) + 77]:
+        ids = rng.integers(0, 1 << bits, size=n, dtype=np.uint64).astype(np.uint32)
+        if n:
+            ids[0] = (1 << bits) - 1
+            ids[-1] = (1 << bits) - 1
+        stream = np.concatenate([_pack_ids_reference(ids, bits), np.full(64, 0xAB, dtype=np.uint8)])    # readable slack, not zero
+        for shift in (0, 1, 5):                                  # destination not 32-byte aligned
+            out = np.full(n + 16, 0xDEADBEEF, dtype=np.uint32)
+            dst = out[shift:shift + n]
+            assert lib.tk_debug_unpack_ids(stream.ctypes.data, n, bits, dst.ctypes.data) == 0
+            assert np.array_equal(dst, ids), (bits, n, shift)
+            assert (out[:shift] == 0xDEADBEEF).all() and (out[shift + n:] == 0xDEADBEEF).all()
+    assert lib.tk_debug_unpack_ids(None, 1, 17, None) != 0
