@@ -246,6 +246,7 @@ struct tk_tokenizer {
     };
     static constexpr int kPackStages = 4;
     PackStage pstage[kPackStages];
+    size_t pack_stage_want = 0;
     static constexpr int kOutSlots = 12;
     OutSlot oslot[kOutSlots];
     struct DecSlot {
@@ -845,7 +846,10 @@ class CopyPool {
         }
     }
     CopyPool() {
-        unsigned n = std::thread::hardware_concurrency() / 2;
+        // half the CPUs, but on a small host (16 CPUs: the 1-GPU boxes of the pool) all but four: the copies are
+        // bound by how many cores issue stores, not by the memory system
+        const unsigned hw = std::thread::hardware_concurrency();
+        unsigned n = std::max(hw / 2, hw > 4 ? hw - 4 : 1u);
         if (const char* e = getenv("TEKKEN_B200_COPY_THREADS")) n = (unsigned)atoi(e);
         n = std::max(1u, std::min(n, 12u));
         for (unsigned i = 0; i + 1 < n; ++i) threads_.emplace_back([this] { loop(); });
@@ -1240,19 +1244,28 @@ static int encode_worker(tk_tokenizer* t, EncodeJob& J, size_t g, size_t stride)
         tk_tokenizer::OutSlot& o = t->oslot[i % tk_tokenizer::kOutSlots];
         // a landing buffer that has been widened already; if the host threads are behind (all four still busy: a small
         // or crowded host) this chunk's ids travel as they are -- the link never waits for the CPU
+        // ... and the last chunk always does: nothing is left on the bus to hide its widening behind, so the packed
+        // trip (fewer bytes, then a host pass) would end later than the plain one
         int stage = -1;
-        if (n_tok && pack_bits)
-            for (int k = 0; k < tk_tokenizer::kPackStages; ++k)
-                if (!t->pstage[k].busy.load(std::memory_order_acquire)) { stage = k; break; }
+        if (n_tok && pack_bits && (i + 1 < n_mine || n_mine == 1)) {
+            int n_busy = 0;
+            for (int k = 0; k < tk_tokenizer::kPackStages; ++k) {
+                if (t->pstage[k].busy.load(std::memory_order_acquire)) ++n_busy;
+                else if (stage < 0) stage = k;
+            }
+            if (n_busy >= 2) stage = -1;                     // two chunks behind already
+        }
         if (stage >= 0) {
             tk_tokenizer::PackStage& ps = t->pstage[stage];
             const size_t pb = tkk::packed_id_bytes(n_tok, pack_bits);
+            // all landing buffers get the size of the largest chunk seen (page-locked allocation is slow: ~70 ms for
+            // 200 MB; sizes must settle after the first call, whichever buffer meets whichever chunk)
+            t->pack_stage_want = std::max(t->pack_stage_want, pb + pb / 4 + 4096);
             if (ps.cap < pb + 64) {
                 if (ps.h) cudaFreeHost(ps.h);
                 ps.h = nullptr; ps.cap = 0;
-                const size_t want = pb + pb / 8 + 4096;
-                W_CUDA(cudaHostAlloc((void**)&ps.h, want, cudaHostAllocPortable));
-                ps.cap = want;
+                W_CUDA(cudaHostAlloc((void**)&ps.h, t->pack_stage_want, cudaHostAllocPortable));
+                ps.cap = t->pack_stage_want;
             }
             if (!ps.ev) { W_CUDA(cudaEventCreateWithFlags(&ps.ev, cudaEventDisableTiming)); W_CUDA(cudaEventCreateWithFlags(&ps.ev_packed, cudaEventDisableTiming)); }
             // the slot's pack buffer was last read by the download kOutSlots chunks ago (o.ev_out); packing on its own
@@ -1341,6 +1354,13 @@ static int encode_batch_engine(tk_tokenizer* const* handles, size_t n_handles, c
             int bits = n_ids_max <= (1u << 18) ? 18 : n_ids_max <= (1u << 24) ? 24 : 0;
             if (mode == 24 && bits) bits = 24;
             if (mode == 0 || (mode < 0 && total < (32u << 20))) bits = 0;
+            if (mode < 0 && bits) {
+                // the widening needs CPUs: with one process per GPU (torchrun sets LOCAL_WORLD_SIZE) and fewer than eight
+                // CPUs for each, or with several devices driven by this call, leave the ids as they are
+                const char* lws = getenv("LOCAL_WORLD_SIZE");
+                const unsigned procs = lws && atoi(lws) > 0 ? (unsigned)atoi(lws) : 1u;
+                if (std::thread::hardware_concurrency() / (procs * (unsigned)n_handles) < 8u) bits = 0;
+            }
             J.pack_bits = bits;
         }
         // chunks small enough that every device gets several, large enough to keep the launch overhead low
