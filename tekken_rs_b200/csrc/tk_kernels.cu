@@ -1122,6 +1122,13 @@ __host__ __device__ __forceinline__ uint32_t lane_class(uint32_t len) {
     return 2u * (p - 2u) + (((len - 1u) >> (p - 1u)) & 1u);
 }
 
+// LK_COMPOSE=1: the tile's rank-stream words are composed in shared memory and stored once (16 KB more per block:
+// five resident blocks instead of eight).  0: the words are filled with EN_INVALID in global memory and the ranks
+// stored over them -- the L2 writes fully dirty lines back early, so the stream goes to DRAM twice (ncu: 8.1 GB
+// written by this kernel for a 3.9 GB stream).
+#ifndef LK_COMPOSE
+#define LK_COMPOSE 0
+#endif
 struct LkSmem {
     uint8_t bytes[LK_TILE + TK_LANE_MAX + 16];   // 16-byte aligned
     uint32_t mask[LK_WINS + 4];
@@ -1131,6 +1138,9 @@ struct LkSmem {
     uint32_t cls_n[TKK_N_CLASSES], cls_base[TKK_N_CLASSES], cls_pos[TKK_N_CLASSES];
     uint32_t n_pieces, n_miss, n_hit;
     unsigned long long mbar;           // mbarrier of the tile's bulk copy
+#if LK_COMPOSE
+    alignas(16) uint32_t out[LK_TILE]; // the tile's stream words, composed here and written once
+#endif
 };
 
 // tile-relative end of the piece that starts at tile-relative byte s (the next set bit of the start
@@ -1212,12 +1222,21 @@ __global__ void __launch_bounds__(LK_T, LK_MINB) lookup_kernel(const uint8_t* __
     }
     // the tile's stream words start out EN_INVALID (coalesced 16-byte stores); ranks and long-piece marks are
     // stored over them after the barrier (same block: ordered), K2m fills in the merged pieces later
+#if LK_COMPOSE
+    uint32_t* dst = S.out;
+    {
+        const uint4 inv = make_uint4(EN_INVALID, EN_INVALID, EN_INVALID, EN_INVALID);
+        uint4* d4 = reinterpret_cast<uint4*>(S.out);
+        for (uint32_t i = t; i < LK_TILE / 4; i += LK_T) d4[i] = inv;
+    }
+#else
     uint32_t* dst = stream + tile_pos;
     {
         const uint4 inv = make_uint4(EN_INVALID, EN_INVALID, EN_INVALID, EN_INVALID);
         uint4* d4 = reinterpret_cast<uint4*>(dst);
         for (uint32_t i = t; i < LK_TILE / 4; i += LK_T) if (TK_DBG(tile_pos + 4u * i + 3u, stream_words)) d4[i] = inv;
     }
+#endif
     __threadfence_block();
     __syncthreads();
     if (bulk) bulk_tile_wait(&S.mbar);
@@ -1266,6 +1285,13 @@ __global__ void __launch_bounds__(LK_T, LK_MINB) lookup_kernel(const uint8_t* __
         }
     }
     __syncthreads();
+#if LK_COMPOSE
+    {
+        uint4* g4 = reinterpret_cast<uint4*>(stream + tile_pos);
+        const uint4* s4 = reinterpret_cast<const uint4*>(S.out);
+        for (uint32_t i = t; i < LK_TILE / 4; i += LK_T) if (TK_DBG(tile_pos + 4u * i + 3u, stream_words)) g4[i] = s4[i];
+    }
+#endif
     if (t < TKK_N_CLASSES && S.cls_n[t]) S.cls_base[t] = atomicAdd(q_n + t, S.cls_n[t]);   // this tile's range of every queue
     if (t == 32 && S.n_hit) atomicAdd(tile_count + tile, (unsigned long long)S.n_hit);
     __syncthreads();
