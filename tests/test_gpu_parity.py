@@ -5,6 +5,7 @@ Every test here needs a B200 (`-m gpu`).  The gpu_tok fixture fails -- it never 
 CUDA library or the device is missing, so these tests cannot pass on a fallback."""
 import base64
 import ctypes
+import json
 import random
 
 import numpy as np
@@ -749,3 +750,113 @@ def test_concurrent_host_threads(gpu_tok, oracle):
     [t.start() for t in th]
     [t.join() for t in th]
     assert got == want
+
+
+# ------------------------------------------------------------------------------------------ decode kernels: every path of tk_decode.cu
+
+def _vocab_bytes(tekken_json):
+    cfg = json.load(open(tekken_json))
+    ns, vs = cfg["config"]["default_num_special_tokens"], cfg["config"]["default_vocab_size"]
+    return ns, [base64.b64decode(v["token_bytes"]) for v in cfg["vocab"][:vs - ns]]
+
+
+def _is_utf8(b):
+    try:
+        b.decode("utf-8")
+        return True
+    except UnicodeDecodeError:
+        return False
+
+
+def test_decode_token_lengths_and_tile_shapes(gpu_tok, oracle, tekken_json):
+    # The gather reads a token from the first half of its table cell (<= 7 bytes), from both halves (8..15) or from the
+    # byte table (>= 16); a tile whose text exceeds the staging buffer (> 7 bytes per id over 2,048 ids) takes the
+    # direct path; the copy-out shifts by the phase of the tile's first byte.  Drive every combination, with sequence
+    # starts at every position of a thread's group of ids and outputs that are not word aligned.
+    import torch
+    ns, voc = _vocab_bytes(tekken_json)
+    by_len = {}
+    for r, b in enumerate(voc):
+        if _is_utf8(b):
+            by_len.setdefault(len(b), []).append(ns + r)
+    pick = lambda L, k=0: by_len[L][k % len(by_len[L])]
+    long_len = max(L for L in by_len if L >= 16)
+    rng = np.random.default_rng(3)
+    seqs = []
+    seqs.append([pick(long_len)] * 5000)                                         # > 7 B/id: whole tiles on the direct path
+    seqs.append([pick(16, i) for i in range(4100)])                              # byte-table tokens, tiles on the direct path
+    seqs.append([x for i in range(3000) for x in (pick(16, i), pick(1, i), pick(2, i), pick(1, i + 1))])   # ... inside staged tiles
+    for L in (7, 8, 11, 12, 15):
+        seqs.append([x for i in range(2500) for x in (pick(L, i), pick(1, i), pick(3, i))])                 # cell halves
+        seqs.append([pick(L, i) for i in range(2100)])
+    lens = sorted(by_len)
+    for n in list(range(0, 20)) + [2047, 2048, 2049, 4096, 5000]:                # ragged: starts at every phase of a tile
+        seqs.append([pick(int(rng.choice(lens[:24])), int(rng.integers(0, 1000))) for _ in range(n)])
+    seqs.append([1] + [pick(5, 3)] * 10 + [4, 3, 2])                             # specials between ordinary runs
+    flat = np.concatenate([np.asarray(s, dtype=np.uint32) for s in seqs])
+    off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    np.cumsum([len(s) for s in seqs], out=off[1:])
+    sp = {1: b"<s>", 2: b"</s>", 3: b"[INST]", 4: b"[/INST]"}
+    for pol in ("Ignore", "Keep"):
+        want = [b"".join((sp[i] if pol == "Keep" else b"") if i < ns else voc[i - ns] for i in s) for s in seqs]
+        raw, boff = gpu_tok.decode_batch_np(flat, off, pol)
+        b = raw.tobytes()
+        assert [b[int(boff[i]):int(boff[i + 1])] for i in range(len(seqs))] == want, pol
+    # device pointers, output buffer at every byte phase
+    want = b"".join(voc[i - ns] for s in seqs for i in s if i >= ns)
+    d_ids = torch.from_numpy(flat.view(np.int32)).cuda()
+    d_off = torch.from_numpy(off.astype(np.int64)).cuda()
+    d_boff = torch.empty(len(seqs) + 1, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(len(want) + 80, dtype=torch.uint8, device="cuda")
+    for phase in range(0, 5):
+        buf.fill_(0xEE)
+        nb = gpu_tok.decode_batch_device(d_ids.data_ptr(), d_off.data_ptr(), len(seqs), len(flat), "Ignore", buf.data_ptr() + phase,
+                                         len(want), d_boff.data_ptr(), 0, 0)
+        got = buf.cpu().numpy()
+        assert nb == len(want) and got[phase:phase + nb].tobytes() == want, phase
+        assert (got[:phase] == 0xEE).all() and (got[phase + nb:] == 0xEE).all(), phase   # nothing outside the caller's range
+
+
+def test_decode_utf8_verdicts_at_every_boundary(gpu_tok, oracle):
+    # Strict UTF-8 per ordinary run (tk_decode.cu, validate): a character that is complete, cut off by a special id, by
+    # the end of its sequence, by a following ASCII byte, or missing its lead, slid over every position of a 32-byte
+    # window, a 4-byte word and a 2,048-id tile; plus the ranges a lead byte restricts its second byte to.
+    import torch
+    from oracle import tekken_oracle as TO
+    B = lambda *bs: [1000 + b for b in bs]
+    tails = [B(0xE4, 0xB8, 0xAD), B(0xE4, 0xB8), B(0xE4), B(0xE4, 0xB8) + [2] + B(0xAD), B(0xE4, 0xB8, 0x41), B(0xB8, 0xAD),
+             B(0xF0, 0x9F, 0x98, 0x80), B(0xF0, 0x9F, 0x98), B(0xF0, 0x9F) + [3] + B(0x98, 0x80), B(0xC3, 0xA9), B(0xC3), B(0xC3, 0x41),
+             B(0xE0, 0x80, 0x80), B(0xE0, 0xA0, 0x80), B(0xED, 0x9F, 0xBF), B(0xED, 0xA0, 0x80), B(0xF0, 0x8F, 0x80, 0x80),
+             B(0xF4, 0x8F, 0xBF, 0xBF), B(0xF4, 0x90, 0x80, 0x80), B(0xC1, 0x81), B(0xF5, 0x80, 0x80, 0x80), B(0xFF)]
+    seqs = []
+    for k in list(range(0, 70)) + [2040, 2045, 2046, 2047, 2048, 2049, 4095]:
+        for tail in tails:
+            seqs.append(B(*([0x61] * k)) + tail)
+            seqs.append(B(*([0x61] * k)) + tail + B(0x62, 0x63))
+    flat = np.concatenate([np.asarray(s, dtype=np.uint32) for s in seqs])
+    off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    np.cumsum([len(s) for s in seqs], out=off[1:])
+    codes = {"Tokenizers": -4, "SpecialTokenPolicy": -8}
+    d_ids = torch.from_numpy(flat.view(np.int32)).cuda()
+    d_off = torch.from_numpy(off.astype(np.int64)).cuda()
+    d_boff = torch.empty(len(seqs) + 1, dtype=torch.int64, device="cuda")
+    d_st = torch.empty(len(seqs), dtype=torch.int32, device="cuda")
+    d_out = torch.empty(len(flat) * 8 + 64, dtype=torch.uint8, device="cuda")
+    for pol in ("Ignore", "Keep", "Raise"):
+        want = []
+        for s in seqs:
+            try:
+                oracle.decode_bytes(s, pol)
+                want.append(0)
+            except TO.TokenizerError as e:
+                want.append(codes[e.kind])
+        try:
+            gpu_tok.decode_batch_device(d_ids.data_ptr(), d_off.data_ptr(), len(seqs), len(flat), pol, d_out.data_ptr(), len(flat) * 8 + 64,
+                                        d_boff.data_ptr(), d_st.data_ptr(), 0)
+            assert not any(want)
+        except TokenizerError as e:
+            first = next(i for i, w in enumerate(want) if w)
+            assert "sequence %d" % first in e.msg, (pol, e.msg, first)
+        got = d_st.cpu().numpy().tolist()
+        bad = [i for i in range(len(seqs)) if got[i] != want[i]]
+        assert not bad, (pol, bad[:5], [(seqs[i][-6:], got[i], want[i]) for i in bad[:5]])
