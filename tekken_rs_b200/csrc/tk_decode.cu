@@ -272,12 +272,17 @@ __global__ void __launch_bounds__(DC_T, MINB) decode_gather_kernel(const uint32_
     {
         uint64_t seq = tw ? seq_first[i0 >> 5] : 0;         // first sequence of my group of 32 ids; advanced below
         uint32_t todo = fits ? (tw | spec) : ((1u << PER) - 1u);
+        // sequence starts among my positions and the one after them (bit PER)
+        const uint32_t starts = todo ? tw | (((__ldg(tds + ((i0 + PER) >> 5)) >> ((i0 + PER) & 31)) & 1u) << PER) : 0u;
 #pragma unroll 1
         while (todo) {
             const uint32_t k = (uint32_t)(__ffs((int)todo) - 1);
             todo &= todo - 1;
             const uint64_t i = i0 + k;
             if (i > n_ids) break;
+            // the usual special id is the </s> that ends a sequence: dropped (Ignore), it sits on the byte where the next
+            // sequence starts, and that start marks the run boundary -- nothing to do here (half of this loop's trips)
+            if (fits && policy == TK_POLICY_IGNORE && ((starts >> k) & 3u) == 2u && i < n_ids && __ldg(ids + i) < T.num_special) continue;
             uint32_t rel = p, l = 0;
             dc_locate<PER>(len16, k, rel, l);
             const uint64_t ok = base + rel;
