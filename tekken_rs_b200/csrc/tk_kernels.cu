@@ -1134,10 +1134,9 @@ struct LkSmem {
     uint32_t mask[LK_WINS + 4];
     uint16_t list[LK_PCAP];            // tile-relative starts of all pieces, in order
     uint32_t missq[LK_TILE / 2 + 4];   // pieces to merge: start | len << 12
-    uint16_t tinyq[LK_TILE / 2 + 4];   // 2..4-byte misses, merged by this kernel in a dense second pass: start | (len - 1) << 12
     uint32_t wsum[LK_T / 32];
     uint32_t cls_n[TKK_N_CLASSES], cls_base[TKK_N_CLASSES], cls_pos[TKK_N_CLASSES];
-    uint32_t n_pieces, n_miss, n_hit, n_tiny;
+    uint32_t n_pieces, n_miss, n_hit;
     unsigned long long mbar;           // mbarrier of the tile's bulk copy
 #if LK_COMPOSE
     alignas(16) uint32_t out[LK_TILE]; // the tile's stream words, composed here and written once
@@ -1193,7 +1192,7 @@ __global__ void __launch_bounds__(LK_T, LK_MINB) lookup_kernel(const uint8_t* __
     const uint64_t tile_pos = (uint64_t)tile * LK_TILE;
     const uint64_t win0 = (uint64_t)tile * LK_WINS;
     if (t < TKK_N_CLASSES) { S.cls_n[t] = 0; S.cls_pos[t] = 0; }
-    if (t == 0) { S.n_miss = 0; S.n_hit = 0; S.n_tiny = 0; }
+    if (t == 0) { S.n_miss = 0; S.n_hit = 0; }
     // ---- A: stage bytes and mask words; list the piece starts ----
     bool bulk;
     {
@@ -1247,8 +1246,7 @@ __global__ void __launch_bounds__(LK_T, LK_MINB) lookup_kernel(const uint8_t* __
     for (uint32_t k0 = 0; k0 < np; k0 += LK_T) {
         const uint32_t k = k0 + t;
         uint32_t s = 0, len = 0, cls = 0xFFFFFFFFu;
-        uint32_t hit = 0;                                  // ranks this lane stored
-        bool tiny = false;
+        uint32_t hit = 0;                                  // ranks this lane stored (1 for a vocabulary entry, 2..4 for a tiny piece)
         if (k < np) {
             s = S.list[k];
             if (tile_pos + s < n) {                        // the end-of-data sentinel is not a piece
@@ -1259,21 +1257,21 @@ __global__ void __launch_bounds__(LK_T, LK_MINB) lookup_kernel(const uint8_t* __
                     if (!TK_DBG(tile_pos + s, stream_words)) { }
                     else if (whole != TK_INF) { dst[s] = whole; hit = 1; }
                     else if (len == 1) { dst[s] = (uint32_t)S.bytes[s]; hit = 1; }
-                    else if (len <= 4u && s + len <= LK_TILE) tiny = true;      // merged below, lanes packed
+                    else if (len <= 4u && s + len <= LK_TILE) {
+                        // 2..4 bytes: the merge loop written out (tk_bpe_tiny), ranks straight into the piece's own positions
+                        // (a piece that reaches into the next tile's words is queued: that tile's block clears them)
+                        uint32_t r[4];
+                        hit = tk_bpe_tiny(T, S.bytes[s], S.bytes[s + 1], S.bytes[s + 2], S.bytes[s + 3], len, r);
+                        dst[s] = r[0]; dst[s + 1] = r[1];
+                        if (hit > 2u) dst[s + 2] = r[2];
+                        if (hit > 3u) dst[s + 3] = r[3];
+                    }
                     else cls = lane_class(len);
                 } else if (TK_DBG(tile_pos + s, stream_words)) dst[s] = EN_LONGREF;      // longer pieces: K3
             }
         }
         const uint32_t hm = __reduce_add_sync(0xFFFFFFFFu, hit);
         if (lane == 0 && hm) atomicAdd(&S.n_hit, hm);
-        const uint32_t tm = __ballot_sync(0xFFFFFFFFu, tiny);
-        if (tm) {
-            uint32_t base = 0;
-            const int leader = __ffs((int)tm) - 1;
-            if ((int)lane == leader) base = atomicAdd(&S.n_tiny, (uint32_t)__popc(tm));
-            base = __shfl_sync(0xFFFFFFFFu, base, leader);
-            if (tiny) S.tinyq[base + (uint32_t)__popc(tm & ((1u << lane) - 1u))] = (uint16_t)(s | ((len - 1u) << 12));
-        }
         const uint32_t mm = __ballot_sync(0xFFFFFFFFu, cls != 0xFFFFFFFFu);
         if (mm) {
             uint32_t base = 0;
@@ -1284,30 +1282,6 @@ __global__ void __launch_bounds__(LK_T, LK_MINB) lookup_kernel(const uint8_t* __
             // misses per length class (one shared-memory atomic per class per warp)
             const uint32_t peers = __match_any_sync(0xFFFFFFFFu, cls);
             if (cls != 0xFFFFFFFFu && (uint32_t)(__ffs((int)peers) - 1) == lane) atomicAdd(&S.cls_n[cls], (uint32_t)__popc(peers));
-        }
-    }
-    __syncthreads();
-    // ---- B2: misses of 2..4 bytes: the merge loop written out (tk_bpe_tiny), one lane per piece with the lanes
-    //      packed (inside pass B the few lanes that missed ran it at 2 of 32: 12 % of the kernel's instructions);
-    //      ranks go straight to the piece's own positions (a piece that reaches into the next tile's words was
-    //      queued instead: that tile's block clears them)
-    {
-        const uint32_t nt = S.n_tiny;
-        for (uint32_t i0 = 0; i0 < nt; i0 += LK_T) {
-            const uint32_t i = i0 + t;
-            uint32_t hit = 0;
-            if (i < nt) {
-                const uint32_t e = S.tinyq[i], s = e & 4095u, len = (e >> 12) + 1u;
-                uint32_t r[4];
-                hit = tk_bpe_tiny(T, S.bytes[s], S.bytes[s + 1], S.bytes[s + 2], S.bytes[s + 3], len, r);
-                if (TK_DBG(tile_pos + s, stream_words)) {
-                    dst[s] = r[0]; dst[s + 1] = r[1];
-                    if (hit > 2u) dst[s + 2] = r[2];
-                    if (hit > 3u) dst[s + 3] = r[3];
-                }
-            }
-            const uint32_t hm = __reduce_add_sync(0xFFFFFFFFu, hit);
-            if (lane == 0 && hm) atomicAdd(&S.n_hit, hm);
         }
     }
     __syncthreads();
