@@ -660,6 +660,34 @@ def latency_table(tk, lib, path):
             for _ in range(creps):
                 enc.encode_ordinary(text)
             row["cpu_engine_us"] = (time.perf_counter() - t0) / creps * 1e6
+        # ... and the way back: Tekkenizer::decode of that string's ids (src/tekkenizer.rs:436-443)
+        ids = np.asarray(orc.encode_np(a, True, True), dtype=np.uint32)
+
+        def gpu_dec():
+            out, n = ctypes.c_void_p(), ctypes.c_size_t()
+            rc = lib.tk_decode(tk._h, ids.ctypes.data, len(ids), 0, ctypes.byref(out), ctypes.byref(n))
+            assert rc == 0 and n.value == len(raw)
+            lib.tk_buffer_free(out)
+        for _ in range(10):
+            gpu_dec()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            gpu_dec()
+            ts.append(time.perf_counter() - t0)
+        ts.sort()
+        row["decode_ids"] = int(len(ids))
+        row["decode_gpu_us_median"] = ts[len(ts) // 2] * 1e6
+        t0 = time.perf_counter()
+        for _ in range(creps):
+            orc.decode_bytes(ids, "Ignore")
+        row["decode_cpu_port_us"] = (time.perf_counter() - t0) / creps * 1e6
+        if enc is not None:
+            plain = [int(i) - 1000 for i in ids.tolist() if i >= 1000]
+            t0 = time.perf_counter()
+            for _ in range(creps):
+                enc.decode_bytes(plain)
+            row["decode_cpu_engine_us"] = (time.perf_counter() - t0) / creps * 1e6
         rows.append(row)
     return rows
 

@@ -1823,8 +1823,67 @@ extern "C" int tk_decode_batch(const tk_tokenizer* tc, const uint32_t* ids, cons
     return decode_batch_engine(t, ids, tok_off, n_docs, policy, out, byte_off, bad_doc, cap + 1);
 }
 
+// The latency path of tk_decode: one id list of at most kSmallDecodeIds ids in one single-block kernel that reads the ids
+// from and writes the text to mapped pinned memory (tk_decode.cu, decode_small_kernel); the slots are the ones the
+// short-text encode uses.  *fallback: the text is longer than the kernel's tile, take the batch path.
+static int decode_small_ids(tk_tokenizer* t, const uint32_t* ids, size_t n, int policy, uint8_t** out, size_t* n_out, bool* fallback) {
+    *fallback = false;
+    tk_tokenizer::FastSlot* s = nullptr;
+    for (auto& f : t->fast) if (f.mu.try_lock()) { s = &f; break; }
+    if (!s) { s = &t->fast[0]; s->mu.lock(); }
+    std::lock_guard<std::mutex> g(s->mu, std::adopt_lock);
+    DeviceGuard dg(t->device);
+    if (!dg.ok) return fail(TK_ERR_CUDA, "cudaSetDevice(%d) failed", t->device);
+    static_assert(tkk::kSmallDecodeIds * 4 <= tkk::kSmallMaxBytes + 128 && (8 + tkk::kSmallDecodeBytes / 4) <= tkk::kSmallOutWords,
+                  "the decode tile fits the latency slots");
+    if (!s->st) {
+        CUDA_OR_FAIL(cudaHostAlloc((void**)&s->h_in, tkk::kSmallMaxBytes + 128, cudaHostAllocMapped));
+        CUDA_OR_FAIL(cudaHostAlloc((void**)&s->h_out, tkk::kSmallOutWords * 4, cudaHostAllocMapped));
+        CUDA_OR_FAIL(cudaHostGetDevicePointer((void**)&s->d_in, s->h_in, 0));
+        CUDA_OR_FAIL(cudaHostGetDevicePointer((void**)&s->d_out, s->h_out, 0));
+        memset(s->h_out, 0, 64);
+        CUDA_OR_FAIL(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
+    }
+    if (n) memcpy(s->h_in, ids, n * 4);
+    const uint32_t seq = ++s->seq ? s->seq : ++s->seq;
+    cudaError_t e = tkk::decode_small(t->tables, (const uint32_t*)s->d_in, (uint32_t)n, policy, s->d_out, seq, s->st);
+    if (e != cudaSuccess) return fail(TK_ERR_CUDA, "decode launch: %s", cudaGetErrorString(e));
+    volatile uint32_t* hdr = s->h_out;
+    for (uint32_t spin = 1;; ++spin) {
+        if (hdr[4] == seq) break;
+        if ((spin & 4095u) == 0u) {
+            const cudaError_t q = cudaStreamQuery(s->st);
+            if (q == cudaSuccess) { if (hdr[4] == seq) break; return fail(TK_ERR_CUDA, "single-block decode kernel ended without a result"); }
+            if (q != cudaErrorNotReady) return fail(TK_ERR_CUDA, "single-block decode kernel: %s", cudaGetErrorString(q));
+        }
+        cpu_relax();
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    const uint32_t n_bytes = hdr[0], flags = hdr[2];
+    const int status = (int)(int32_t)hdr[1];
+    if (flags & tkk::kSmallNeedBatch) { *fallback = true; return TK_OK; }
+    if (status == TK_ERR_SPECIAL_TOKEN_POLICY)
+        return fail(TK_ERR_SPECIAL_TOKEN_POLICY, "Decoding tokens that contain special tokens is not allowed (sequence 0)");
+    if (status != TK_OK)
+        return fail(TK_ERR_TOKENIZERS, "decode failed for sequence 0: unknown token id or the bytes of an ordinary run are not valid UTF-8");
+    uint8_t* b = (uint8_t*)g_pool.get((size_t)n_bytes + 1, false);
+    if (!b) return fail(TK_ERR_CUDA, "out of host memory");
+    if (n_bytes) memcpy(b, s->h_out + 8, n_bytes);
+    b[n_bytes] = 0;
+    *out = b;
+    *n_out = n_bytes;
+    return TK_OK;
+}
+
 extern "C" int tk_decode(const tk_tokenizer* t, const uint32_t* ids, size_t n, int policy, uint8_t** out, size_t* n_out) {
     if (!out || !n_out) return fail(TK_ERR_INVALID_ARGUMENT, "null argument");
+    static const bool kNoFast = getenv("TEKKEN_B200_NO_FAST") != nullptr;      // measurements: force the batch path
+    if (t && t->device >= 0 && n <= tkk::kSmallDecodeIds && (ids || !n) && !kNoFast &&
+        (policy == TK_POLICY_IGNORE || policy == TK_POLICY_KEEP || policy == TK_POLICY_RAISE)) {
+        bool fallback = false;
+        const int rc = decode_small_ids(const_cast<tk_tokenizer*>(t), ids, n, policy, out, n_out, &fallback);
+        if (rc || !fallback) return rc;
+    }
     uint64_t off[2] = {0, n};
     uint64_t* byte_off = nullptr;
     int rc = tk_decode_batch(t, ids, off, 1, policy, out, &byte_off, nullptr);

@@ -490,6 +490,134 @@ __global__ void decode_status_kernel(const DocErr* __restrict__ docerr, uint64_t
     if (s != TK_OK) atomicMin(first_bad, (unsigned long long)d);
 }
 
+// ---- the latency path: one sequence of at most kSmallDecodeIds ids in ONE single-block kernel ---------------------------
+// (the reference's own call shape: Tekkenizer::decode of one id list).  The ids come from and the text goes to mapped
+// pinned memory that the calling thread polls: no copies, no memsets, no stream synchronisation.  Same arithmetic as
+// D0-D3 -- lengths from the table cells, block scan, run boundaries, strict UTF-8 per ordinary run (dv_window), the
+// status rule of decode_status_kernel -- on one tile in shared memory.
+#define DS_T 256
+#define DS_PER (kSmallDecodeIds / DS_T)
+struct DsSmem {
+    uint32_t bufw[kSmallDecodeBytes / 4 + 8];
+    uint32_t bmask[kSmallDecodeBytes / 32 + 4];
+    uint32_t wsum[DS_T / 32];
+    uint64_t boff[2];
+    DocErr err;
+};
+struct DsResult {
+    uint32_t n_bytes, status, flags, pad;
+    uint32_t done;                          // == the call's sequence number when everything above and the text are visible
+    uint32_t pad2[3];
+};
+
+__global__ void __launch_bounds__(DS_T) decode_small_kernel(const uint32_t* __restrict__ ids, uint32_t n, int policy, TkDeviceTables T,
+                                                            uint32_t* __restrict__ out, uint32_t seq) {
+    __shared__ __align__(16) DsSmem S;
+    const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    for (uint32_t i = t; i < sizeof(S.bufw) / 4; i += DS_T) S.bufw[i] = 0u;
+    for (uint32_t i = t; i < sizeof(S.bmask) / 4; i += DS_T) S.bmask[i] = 0u;
+    if (t == 0) { S.err.unk_tok = S.err.sp_tok = S.err.sp_byte = S.err.utf_byte = ~0ull; S.boff[0] = 0; }
+    uint32_t v[DS_PER], len[DS_PER];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < DS_PER; ++k) {
+        const uint32_t i = t * DS_PER + k;
+        v[k] = i < n ? ids[i] : 0u;
+        uint32_t l = 0;
+        if (i < n) {
+            if (v[k] < T.num_special) l = policy == TK_POLICY_KEEP ? T.special_off[v[k] + 1] - T.special_off[v[k]] : 0u;
+            else {
+                const uint32_t r = v[k] - T.num_special;
+                if (r < T.n_vocab) {
+                    l = __ldg(reinterpret_cast<const uint32_t*>(T.vocab_e16 + r) + 1) >> 24;
+                    if (l == 0xFFu) l = T.vocab_off[r + 1] - T.vocab_off[r];
+                }
+            }
+        }
+        len[k] = l;
+        sum += l;
+    }
+    uint32_t inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if (lane >= (uint32_t)d) inc += o;
+    }
+    if (lane == 31) S.wsum[warp] = inc;
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < DS_T / 32; ++w) { if (w < (int)warp) before += S.wsum[w]; total += S.wsum[w]; }
+    DsResult* res = reinterpret_cast<DsResult*>(out);
+    if (total > kSmallDecodeBytes) {                       // block-uniform: more text than the tile holds -> the batch path
+        if (t == 0) {
+            res->n_bytes = 0; res->status = 0; res->flags = kSmallNeedBatch;
+            __threadfence_system();
+            *(volatile uint32_t*)&res->done = seq;
+        }
+        return;
+    }
+    uint8_t* buf = reinterpret_cast<uint8_t*>(S.bufw);
+    uint32_t o = before + inc - sum;
+    if (t == 0) { atomicOr(&S.bmask[0], 1u); atomicOr(&S.bmask[total >> 5], 1u << (total & 31u)); S.boff[1] = total; }
+#pragma unroll 1
+    for (int k = 0; k < DS_PER; ++k) {
+        const uint32_t i = t * DS_PER + k;
+        if (i >= n) break;
+        const uint32_t l = len[k];
+        const uint8_t* src = nullptr;
+        if (v[k] < T.num_special) {
+            // a special id ends the ordinary run before it and starts a new one after it
+            atomicOr(&S.bmask[o >> 5], 1u << (o & 31u));
+            if (policy == TK_POLICY_RAISE) { atomicMin(&S.err.sp_tok, (unsigned long long)i); atomicMin(&S.err.sp_byte, (unsigned long long)o); }
+            else if (policy == TK_POLICY_KEEP) { atomicOr(&S.bmask[(o + l) >> 5], 1u << ((o + l) & 31u)); src = T.special_bytes + T.special_off[v[k]]; }
+        } else {
+            const uint32_t r = v[k] - T.num_special;
+            if (r >= T.n_vocab) atomicMin(&S.err.unk_tok, (unsigned long long)i);
+            else src = T.vocab_bytes + T.vocab_off[r];
+        }
+        if (src)
+            for (uint32_t j = 0; j < l; ++j) buf[o + j] = __ldg(src + j);
+        o += l;
+    }
+    __syncthreads();
+    // strict UTF-8 per ordinary run
+    for (uint32_t wi = t; wi < total / 32u + 1u; wi += DS_T) {
+        uint32_t w[9];
+        w[0] = wi ? S.bufw[wi * 8u - 1u] : 0u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[j + 1] = S.bufw[wi * 8u + j];          // zero beyond the text
+        uint32_t any = 0;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) any |= w[j];
+        if (!(any & TK_H)) continue;
+        const uint32_t bm = S.bmask[wi], bm0 = wi ? S.bmask[wi - 1u] >> 28 : 0u;
+        if (dv_window<false>(w, bm, bm0, (uint64_t)wi * 32u, (uint64_t)total, S.boff, 1, &S.err))
+            dv_window<true>(w, bm, bm0, (uint64_t)wi * 32u, (uint64_t)total, S.boff, 1, &S.err);
+    }
+    __syncthreads();
+    for (uint32_t j = t; j < (total + 3u) / 4u; j += DS_T) out[8 + j] = S.bufw[j];
+    __threadfence_system();
+    __syncthreads();
+    if (t == 0) {
+        const DocErr e = S.err;
+        int32_t st = TK_OK;
+        if (e.sp_tok != ~0ull) {
+            const bool earlier = (e.unk_tok != ~0ull && e.unk_tok < e.sp_tok) || (e.utf_byte != ~0ull && e.utf_byte < e.sp_byte);
+            st = earlier ? TK_ERR_TOKENIZERS : TK_ERR_SPECIAL_TOKEN_POLICY;
+        } else if (e.unk_tok != ~0ull || e.utf_byte != ~0ull) st = TK_ERR_TOKENIZERS;
+        res->n_bytes = total; res->status = (uint32_t)st; res->flags = 0;
+        __threadfence_system();
+        *(volatile uint32_t*)&res->done = seq;
+    }
+}
+
+cudaError_t decode_small(const TkDeviceTables& T, const uint32_t* d_ids, uint32_t n, int policy, uint32_t* d_out, uint32_t seq, cudaStream_t st) {
+    decode_small_kernel<<<1, DS_T, 0, st>>>(d_ids, n, policy, T, d_out, seq);
+    count_launch();
+    return cudaGetLastError();
+}
+
 static inline uint64_t ceil_div(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
 
 size_t decode_workspace_bytes(uint64_t n_ids, uint64_t n_docs, uint64_t out_cap, DecodeLayout* L) {

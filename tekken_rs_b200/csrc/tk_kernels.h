@@ -110,6 +110,10 @@ cudaError_t encode_device(const TkDeviceTables& T, const uint8_t* d_data, const 
 constexpr uint32_t kSmallMaxBytes = 256 * 32 - 64;
 constexpr uint32_t kSmallOutWords = 8 + kSmallMaxBytes + 2 + 6;
 constexpr uint32_t kSmallNeedBatch = 1u, kSmallBadUtf8 = 2u;
+// ... and one id list of at most kSmallDecodeIds ids that decodes to at most kSmallDecodeBytes bytes (tk_decode.cu).  d_out:
+// 8 header words {n_bytes, status, flags, -, done = seq, ...}, then the text; both buffers are mapped pinned memory.
+constexpr uint32_t kSmallDecodeIds = 2048, kSmallDecodeBytes = 24576;
+cudaError_t decode_small(const TkDeviceTables& T, const uint32_t* d_ids, uint32_t n, int policy, uint32_t* d_out, uint32_t seq, cudaStream_t st);
 cudaError_t encode_small(const TkDeviceTables& T, const uint8_t* d_text, uint32_t n, int add_bos, int add_eos, uint32_t* d_out,
                          uint32_t seq, cudaStream_t st);
 

@@ -133,6 +133,35 @@ def test_single_text_latency_path(gpu_tok, oracle):
         assert e.value.kind == "InvalidUtf8"
 
 
+def test_single_sequence_decode_latency_path(gpu_tok, oracle):
+    # tk_decode of at most 2,048 ids that decode to at most 24 KiB runs the single-block kernel (decode_small_kernel),
+    # anything larger the batch pipeline: the same bytes and the same errors as the oracle on both sides of each switch
+    from oracle import tekken_oracle as TO
+    rng = random.Random(29)
+    long_word = gpu_tok.encode("internationalization " * 3, False, False)
+    cases = [[], [1], [2], [1, 2], gpu_tok.encode("Hello, world!", True, True), gpu_tok.encode("日本語 😀 é", True, True)]
+    for n in (1, 7, 8, 9, 255, 256, 257, 2047, 2048, 2049, 3000):
+        cases.append([rng.choice(long_word) for _ in range(n)])                      # long tokens: up to > 24 KiB of text
+        cases.append(gpu_tok.encode("".join(rng.choice("abc de.\n1'é日") for _ in range(n)), True, True)[:n])
+        cases.append([1000 + rng.randrange(256) for _ in range(n)])                 # raw bytes: mostly invalid UTF-8
+        cases.append([rng.randrange(0, 1300) for _ in range(n)])                    # specials and bytes
+    cases += [[1000 + 0xE4, 1000 + 0xB8, 1000 + 0xAD], [1000 + 0xE4, 1000 + 0xB8], [1000 + 0xE4, 2, 1000 + 0xB8, 1000 + 0xAD], [200000], [131071]]
+    longest = max(long_word, key=lambda i: len(oracle.decode_bytes([i], "Ignore")))
+    assert len(oracle.decode_bytes([longest], "Ignore")) >= 13
+    cases += [[longest] * 2048, [longest] * 1800 + [1] * 248]                       # <= 2,048 ids but more than 24 KiB of text
+    for ids in cases:
+        for pol in ("Ignore", "Keep", "Raise"):
+            try:
+                want = ("ok", oracle.decode_bytes(ids, pol))
+            except TO.TokenizerError as e:
+                want = ("err", e.kind)
+            try:
+                got = ("ok", gpu_tok.decode_bytes(ids, pol))
+            except TokenizerError as e:
+                got = ("err", e.kind)
+            assert got == want, (len(ids), ids[:8], pol)
+
+
 def test_host_engine_chunks_slices_and_devices(gpu_tok, oracle, tekken_json):
     # the host-buffer engine (tk_api.cu): chunks cut at document boundaries, documents larger than a chunk sliced at
     # context-free piece boundaries, chunks dealt to several handles with the ids landing in document order, pageable
