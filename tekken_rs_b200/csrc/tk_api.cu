@@ -1368,6 +1368,8 @@ static int encode_batch_engine(tk_tokenizer* const* handles, size_t n_handles, c
         if (n_handles > 1) chunk = std::max<uint64_t>(4u << 20, std::min<uint64_t>(chunk, total / (n_handles * 4) + 1));
         int rc = plan_chunks(data, doc_off, n_docs, chunk, n_handles, J.chunks);
         if (rc) return rc;
+        // ... and only a pipeline of several chunks per device hides the widening behind later transfers
+        if (g_pack_mode.load() < 0 && J.chunks.size() < 4 * n_handles) J.pack_bits = 0;
         J.ntok.assign(J.chunks.size(), -1);
         J.prefix.assign(J.chunks.size() + 1, 0);
         J.h_off = (uint64_t*)g_pool.get((n_docs + 1) * 8);
