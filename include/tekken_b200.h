@@ -128,7 +128,9 @@ int tk_id_to_byte_piece(const tk_tokenizer *t, uint32_t id, int policy, uint8_t 
 
 /* ---- encode: Tekkenizer::encode (src/tekkenizer.rs:378-405) --------------------------- */
 
-/* One text.  ids = CoreBPE ranks + num_special_tokens, optional BOS first / EOS last. */
+/* One text.  ids = CoreBPE ranks + num_special_tokens, optional BOS first / EOS last.  A text of at most 8,128 bytes is
+   encoded by ONE single-block kernel that reads it from and writes the ids to mapped pinned memory (about 23 us host to
+   host); longer texts go through the chunk pipeline of tk_encode_batch.  *out is library-allocated (tk_buffer_free). */
 int tk_encode(const tk_tokenizer *t, const uint8_t *utf8, size_t len, int add_bos, int add_eos,
               uint32_t **out, size_t *n_out);
 
@@ -163,6 +165,10 @@ int tk_encode_batch_device(const tk_tokenizer *t, const uint8_t *d_data, const u
 
 /* ---- decode: Tekkenizer::decode / decode_all (src/tekkenizer.rs:436-560) -------------- */
 
+/* decode (:436-443): the bytes of the concatenated elements (valid UTF-8 on success).  policy: tk_policy.  Errors as
+   the reference: TK_ERR_SPECIAL_TOKEN_POLICY (Raise and a special id, :531-535), TK_ERR_TOKENIZERS (unknown id, or an
+   ordinary run that is not valid UTF-8, :555).  At most 2,048 ids that decode to at most 24 KiB take a single-block
+   kernel over mapped pinned memory (about 20 us host to host); longer lists the pipeline of tk_decode_batch. */
 int tk_decode(const tk_tokenizer *t, const uint32_t *ids, size_t n, int policy, uint8_t **out,
               size_t *n_out);
 
