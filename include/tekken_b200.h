@@ -253,8 +253,8 @@ void tk_set_chunk_bytes(uint64_t bytes);
    ids fit.  The result is the same array either way. */
 void tk_set_pack_ids(int mode);
 /* Bounds-checked debug build (compile the library with -DTK_DEBUG_BOUNDS; compute-sanitizer substitute): number of
-   out-of-range stores the encode kernels of the handle's device refused since the last call of this function, with
-   detail4 = {count, source line, index, limit} of the first one.  -1 in a regular build (the checks compile away). */
+   out-of-range stores the encode and decode kernels of the handle's device refused since the last call of this function,
+   with detail4 = {count, source line (tk_kernels.cu; + 1,000,000: tk_decode.cu), index, limit} of the first one.  -1 in a regular build (the checks compile away). */
 long long tk_debug_bounds_violations(const tk_tokenizer *t, uint64_t *detail4);
 /* Test hook for the host half of the packed-id download (large host-buffer encodes send their ids over PCIe as an
    18- or 24-bit little-endian bit stream, 16 ids per group, and widen them on the host): dst[0..n) = the ids of the

@@ -2168,10 +2168,12 @@ extern "C" long long tk_debug_bounds_violations(const tk_tokenizer* t, uint64_t*
     if (!t || t->device < 0) return -1;
     DeviceGuard dg(t->device);
     cudaDeviceSynchronize();
-    unsigned long long d[4] = {0, 0, 0, 0};
-    const long long n = tkk::debug_bounds_violations(d);
-    if (detail4) for (int i = 0; i < 4; ++i) detail4[i] = d[i];
-    return n;
+    unsigned long long d[4] = {0, 0, 0, 0}, d2[4] = {0, 0, 0, 0};
+    const long long n = tkk::debug_bounds_violations(d), n2 = tkk::decode_debug_bounds_violations(d2);
+    if (n < 0 || n2 < 0) return n < 0 ? n : n2;
+    if (detail4) for (int i = 0; i < 4; ++i) detail4[i] = n ? d[i] : d2[i];     // (decode lines are reported + 1,000,000)
+    if (detail4) detail4[0] = (unsigned long long)(n + n2);
+    return n + n2;
 }
 
 extern "C" uint64_t tk_kernel_launch_count(void) { return tkk::launch_count(); }

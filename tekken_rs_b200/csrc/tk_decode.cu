@@ -24,6 +24,21 @@ struct DocErr {
     unsigned long long unk_tok, sp_tok, sp_byte, utf_byte;
 };
 
+// Bounds-checked debug build (-DTK_DEBUG_BOUNDS, see tk_kernels.cu): every store of the decode kernels into the
+// staging buffers, the output and the per-sequence arrays first compares its index with the array's size; a violation
+// is skipped and recorded (line + 1,000,000 to tell it from an encode line, index, limit).  Compiled away otherwise.
+#ifdef TK_DEBUG_BOUNDS
+__device__ unsigned long long g_dc_hit[4];
+__device__ __forceinline__ bool dc_in(unsigned long long i, unsigned long long n, int line) {
+    if (i < n) return true;
+    if (atomicAdd(&g_dc_hit[0], 1ull) == 0ull) { g_dc_hit[1] = 1000000ull + (unsigned long long)line; g_dc_hit[2] = i; g_dc_hit[3] = n; }
+    return false;
+}
+#define DC_DBG(index, limit) dc_in((unsigned long long)(index), (unsigned long long)(limit), __LINE__)
+#else
+#define DC_DBG(index, limit) true
+#endif
+
 __global__ void tokmark_kernel(const uint64_t* __restrict__ tok_off, uint64_t off_base, uint64_t n_docs, uint64_t total,
                                uint32_t* __restrict__ tds, uint32_t* __restrict__ seq_first, uint32_t* __restrict__ flags) {
     uint64_t d = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -89,23 +104,26 @@ struct DcStream {
     uint32_t fill;             // bytes of it that are decided (0..3 between calls)
 };
 // l <= 7 bytes in (v1:v0), zero beyond l; branch-free: up to two completed words are stored under predicates
-__device__ __forceinline__ void dc_append(uint32_t* __restrict__ bufw, DcStream& s, uint32_t v0, uint32_t v1, uint32_t l) {
+#define DC_BUFW_OF(PER) (DC_T * (PER) * 7u / 4u + 4u)       // words of a tile's staging buffer
+__device__ __forceinline__ void dc_append(uint32_t* __restrict__ bufw, DcStream& s, uint32_t v0, uint32_t v1, uint32_t l, uint32_t bufw_n) {
     const uint32_t sh = 8u * s.fill;
     s.a0 |= v0 << sh;
     const uint32_t a1 = __funnelshift_l(v0, v1, sh);        // bits 32..63 of (v1:v0) << sh
     const uint32_t a2 = __funnelshift_l(v1, 0u, sh);        // bits 64..95
     const uint32_t end = s.fill + l, c = end >> 2;          // words completed: 0, 1 or 2
-    if (c >= 1u) bufw[s.wi] = s.a0;
-    if (c >= 2u) bufw[s.wi + 1u] = a1;
+    (void)bufw_n;
+    if (c >= 1u && DC_DBG(s.wi, bufw_n)) bufw[s.wi] = s.a0;
+    if (c >= 2u && DC_DBG(s.wi + 1u, bufw_n)) bufw[s.wi + 1u] = a1;
     s.a0 = c == 0u ? s.a0 : (c == 1u ? a1 : a2);
     s.wi += c;
     s.fill = end & 3u;
 }
 // l bytes that somebody else writes (zeros here)
-__device__ __forceinline__ void dc_gap(uint32_t* __restrict__ bufw, DcStream& s, uint32_t l) {
+__device__ __forceinline__ void dc_gap(uint32_t* __restrict__ bufw, DcStream& s, uint32_t l, uint32_t bufw_n) {
     const uint32_t end = s.fill + l;
+    (void)bufw_n;
     if (end >= 4u) {
-        bufw[s.wi] = s.a0;                                   // my bytes of this word; the rest of it is the gap's
+        if (DC_DBG(s.wi, bufw_n)) bufw[s.wi] = s.a0;         // my bytes of this word; the rest of it is the gap's
         s.a0 = 0u;
     }
     s.wi += end >> 2;
@@ -227,13 +245,13 @@ __global__ void __launch_bounds__(DC_T, MINB) decode_gather_kernel(const uint32_
         for (int k = 0; k < PER; ++k) {
             const uint32_t l = (len16[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
             if ((slow >> k) & 1u) {                        // its bytes come in step 4
-                dc_gap(bufw, s, l);
+                dc_gap(bufw, s, l, BUFW);
             } else {
-                dc_append(bufw, s, e[k].x, e[k].y & 0x00FFFFFFu, l < 7u ? l : 7u);
+                dc_append(bufw, s, e[k].x, e[k].y & 0x00FFFFFFu, l < 7u ? l : 7u, BUFW);
                 if (l > 7u) {                               // the second half of the cell (a fraction of a percent of the ids)
                     const uint2 c = __ldg(reinterpret_cast<const uint2*>(T.vocab_e16 + (__ldg(ids + i0 + k) - T.num_special)) + 1);
-                    dc_append(bufw, s, c.x, 0u, l < 11u ? l - 7u : 4u);
-                    dc_append(bufw, s, c.y, 0u, l < 11u ? 0u : l - 11u);
+                    dc_append(bufw, s, c.x, 0u, l < 11u ? l - 7u : 4u, BUFW);
+                    dc_append(bufw, s, c.y, 0u, l < 11u ? 0u : l - 11u, BUFW);
                 }
             }
         }
@@ -241,7 +259,7 @@ __global__ void __launch_bounds__(DC_T, MINB) decode_gather_kernel(const uint32_
     __syncthreads();
     // 4. OR in what is not part of a completed word
     if (fits) {
-        if (s.fill) atomicOr(bufw + s.wi, s.a0);
+        if (s.fill && DC_DBG(s.wi, BUFW)) atomicOr(bufw + s.wi, s.a0);
         uint32_t todo = slow;
 #pragma unroll 1
         while (todo) {                                      // tokens outside the cells: byte by byte
@@ -251,7 +269,8 @@ __global__ void __launch_bounds__(DC_T, MINB) decode_gather_kernel(const uint32_
             dc_locate<PER>(len16, k, rel, l);
             const uint8_t* src = dc_slow_bytes(T, policy, __ldg(ids + i0 + k));
             if (src)
-                for (uint32_t j = 0; j < l; ++j) atomicOr(bufw + ((rel + j) >> 2), (uint32_t)__ldg(src + j) << (8u * ((rel + j) & 3u)));
+                for (uint32_t j = 0; j < l; ++j)
+                    if (DC_DBG((rel + j) >> 2, BUFW)) atomicOr(bufw + ((rel + j) >> 2), (uint32_t)__ldg(src + j) << (8u * ((rel + j) & 3u)));
         }
     }
     // 5. where the tile starts in the output
@@ -288,7 +307,7 @@ __global__ void __launch_bounds__(DC_T, MINB) decode_gather_kernel(const uint32_
             const uint64_t ok = base + rel;
             if ((tw >> k) & 1u) {
                 while (tok_off[seq] - off_base < i) ++seq;   // sequences that start earlier in the group
-                for (; seq <= n_docs && tok_off[seq] - off_base == i; ++seq) byte_off[seq] = ok;
+                for (; seq <= n_docs && tok_off[seq] - off_base == i; ++seq) if (DC_DBG(seq, n_docs + 1)) byte_off[seq] = ok;
                 mark_boundary(bmask, ok, out_cap);
             }
             if (i == n_ids) break;
@@ -310,7 +329,7 @@ __global__ void __launch_bounds__(DC_T, MINB) decode_gather_kernel(const uint32_
             if (!fits && l && ok + l <= out_cap) {
                 const uint8_t* src = dc_slow_bytes(T, policy, v);
                 if (src)
-                    for (uint32_t j = 0; j < l; ++j) out[ok + j] = __ldg(src + j);
+                    for (uint32_t j = 0; j < l; ++j) if (DC_DBG(ok + j, out_cap)) out[ok + j] = __ldg(src + j);
             }
         }
     }
@@ -325,16 +344,19 @@ __global__ void __launch_bounds__(DC_T, MINB) decode_gather_kernel(const uint32_
         const uint32_t n_full = n_bytes >> 2;                   // words 1 .. n_full - 1 are whole words of this tile
         const uint32_t fs = 8u * (4u - sh);
         uint32_t* const ow = reinterpret_cast<uint32_t*>(o0);
+        // (debug build: the word's last byte must be inside the caller's buffer, and the staging index inside its array)
         if (sh) {
-            for (uint32_t j = 1u + t; j < n_full; j += DC_T) ow[j] = __funnelshift_r(bufw[j - 1], bufw[j], fs);
+            for (uint32_t j = 1u + t; j < n_full; j += DC_T)
+                if (DC_DBG(base - sh + 4ull * j + 3u, out_cap) && DC_DBG(j, BUFW)) ow[j] = __funnelshift_r(bufw[j - 1], bufw[j], fs);
         } else {
-            for (uint32_t j = 1u + t; j < n_full; j += DC_T) ow[j] = bufw[j];
+            for (uint32_t j = 1u + t; j < n_full; j += DC_T)
+                if (DC_DBG(base + 4ull * j + 3u, out_cap) && DC_DBG(j, BUFW)) ow[j] = bufw[j];
         }
         // the two ragged ends, byte by byte: word 0 (bytes sh..3) and the bytes after the last whole word
         if (t < 8u) {
             const uint32_t q = t < 4u ? t : 4u * n_full + (t - 4u);      // byte index from o0
             const bool mine = t < 4u ? (q >= sh && q < n_bytes) : (n_full >= 1u && q < n_bytes);
-            if (mine) o0[q] = reinterpret_cast<const uint8_t*>(bufw)[q - sh];
+            if (mine && DC_DBG(base - sh + q, out_cap) && DC_DBG((q - sh) >> 2, BUFW)) o0[q] = reinterpret_cast<const uint8_t*>(bufw)[q - sh];
         }
     }
 }
@@ -577,7 +599,7 @@ __global__ void __launch_bounds__(DS_T) decode_small_kernel(const uint32_t* __re
             else src = T.vocab_bytes + T.vocab_off[r];
         }
         if (src)
-            for (uint32_t j = 0; j < l; ++j) buf[o + j] = __ldg(src + j);
+            for (uint32_t j = 0; j < l; ++j) if (DC_DBG(o + j, kSmallDecodeBytes)) buf[o + j] = __ldg(src + j);
         o += l;
     }
     __syncthreads();
@@ -596,7 +618,7 @@ __global__ void __launch_bounds__(DS_T) decode_small_kernel(const uint32_t* __re
             dv_window<true>(w, bm, bm0, (uint64_t)wi * 32u, (uint64_t)total, S.boff, 1, &S.err);
     }
     __syncthreads();
-    for (uint32_t j = t; j < (total + 3u) / 4u; j += DS_T) out[8 + j] = S.bufw[j];
+    for (uint32_t j = t; j < (total + 3u) / 4u; j += DS_T) if (DC_DBG(j, kSmallDecodeBytes / 4u)) out[8 + j] = S.bufw[j];
     __threadfence_system();
     __syncthreads();
     if (t == 0) {
@@ -616,6 +638,19 @@ cudaError_t decode_small(const TkDeviceTables& T, const uint32_t* d_ids, uint32_
     decode_small_kernel<<<1, DS_T, 0, st>>>(d_ids, n, policy, T, d_out, seq);
     count_launch();
     return cudaGetLastError();
+}
+
+long long decode_debug_bounds_violations(unsigned long long* out4) {
+#ifdef TK_DEBUG_BOUNDS
+    unsigned long long h[4] = {0, 0, 0, 0}, z[4] = {0, 0, 0, 0};
+    if (cudaMemcpyFromSymbol(h, g_dc_hit, sizeof h) != cudaSuccess) return -2;
+    cudaMemcpyToSymbol(g_dc_hit, z, sizeof z);
+    if (out4) for (int i = 0; i < 4; ++i) out4[i] = h[i];
+    return (long long)h[0];
+#else
+    (void)out4;
+    return -1;
+#endif
 }
 
 static inline uint64_t ceil_div(uint64_t a, uint64_t b) { return (a + b - 1) / b; }

@@ -128,6 +128,7 @@ cudaError_t decode_device(const TkDeviceTables& T, const uint32_t* d_ids, const 
 long long debug_bounds_violations(unsigned long long* out4);   // -1: not a -DTK_DEBUG_BOUNDS build
 uint64_t launch_count();
 void count_launch();
+long long decode_debug_bounds_violations(unsigned long long* out4);     // tk_decode.cu's share of tk_debug_bounds_violations
 
 // ids -> a little-endian bit stream of `bits` (18 or 24) bits per id, 16 ids per group of bits / 2 words; the host-buffer
 // engine sends this over PCIe instead of the 32-bit ids and widens it on the host (tk_api.cu).  d_out holds

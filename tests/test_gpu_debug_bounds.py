@@ -1,5 +1,5 @@
-"""The bounds-checked build (-DTK_DEBUG_BOUNDS: every store of the encode kernels into a workspace / output array is
-checked against the array's size) run over a parity corpus in a child process.  compute-sanitizer is closed on the GPU
+"""The bounds-checked build (-DTK_DEBUG_BOUNDS: every store of the encode and decode kernels into a workspace / staging /
+output array is checked against the array's size) run over a parity corpus in a child process.  compute-sanitizer is closed on the GPU
 pool this library is developed on; this is its substitute: zero refused stores, and results equal to the oracle's."""
 import json
 import os
@@ -39,6 +39,28 @@ for chunk in (0, 256 << 10):
             ok &= bool(np.array_equal(ids, rid) and np.array_equal(toff, roff))
 for t in fuzz[:500]:
     ok &= tk.encode(t, True, True) == orc.encode(t, True, True)
+# ... and the decode kernels: the batches back to their bytes (Ignore) and with the specials kept, oversized tiles
+# (long tokens), the single-sequence kernel, invalid runs
+set_chunk_bytes(0)
+for data, off in cases:
+    ids, toff = tk.encode_batch_np(data, off, True, True)
+    back, boff = tk.decode_batch_np(ids, toff, "Ignore")
+    ok &= bool(np.array_equal(back, data) and np.array_equal(boff, off))
+    kept, koff = tk.decode_batch_np(ids, toff, "Keep")
+    ok &= len(kept) == len(data) + 7 * (len(off) - 1)
+long_tok = max(orc.encode("internationalization " * 3, False, False), key=lambda i: len(orc.decode_bytes([i], "Ignore")))
+for seq in ([long_tok] * 5000, [long_tok, 1, 1044] * 3000, orc.encode(" " * 3000 + "x", True, True) * 40):
+    raw, _ = tk.decode_batch_np(np.asarray(seq, dtype=np.uint32), np.array([0, len(seq)], dtype=np.uint64), "Keep")
+    ok &= raw.tobytes() == orc.decode_bytes(seq, "Keep")
+for t in fuzz[:300]:
+    ids = orc.encode(t, True, True)
+    ok &= tk.decode_bytes(ids, "Keep") == orc.decode_bytes(ids, "Keep")
+for bad in ([1228, 1184], [1228, 2, 1184, 1173], [1000 + 0xFF] * 70, [200000]):
+    try:
+        tk.decode_bytes(bad, "Ignore")
+        ok = False
+    except Exception:
+        pass
 d4 = (ctypes.c_uint64 * 4)()
 n = lib.tk_debug_bounds_violations(tk._h, d4)
 print(json.dumps({"parity": ok, "violations": n, "detail": list(d4)}))
@@ -52,7 +74,7 @@ def test_debug_bounds_build_refuses_no_store():
     out = subprocess.run([sys.executable, "-c", CHILD % ROOT], env=env, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stderr[-2000:]
     res = json.loads(out.stdout.strip().splitlines()[-1])
-    assert res["violations"] == 0, "out-of-range store refused at tk_kernels.cu:%d (index %d, limit %d)" % tuple(res["detail"][1:])
+    assert res["violations"] == 0, "out-of-range store refused at line %d (tk_kernels.cu; + 1,000,000: tk_decode.cu), index %d, limit %d" % tuple(res["detail"][1:])
     assert res["parity"]
 
 
