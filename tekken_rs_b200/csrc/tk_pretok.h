@@ -342,7 +342,29 @@ TK_HD TkEval tk_eval_window(const TkWin& p, const TkWin& c, const TkWin& nx, con
         start |= c.lead & c.mW & nds & (P_L | P_N | P_O | (P_W & nxt_lead));
     }
     // digits: every third char of a run, counted from the run start
-    {
+    if ((c.mN & ~c.lead) == 0u) {
+        // every digit of the window is one byte (no continuation byte is N): bit arithmetic instead of a loop over
+        // the digits.  Seeds: the first digit of every run that starts here, and for the run that enters the window
+        // with n_in digits counted the first position where the count is a multiple of three again; then every third
+        // position of the same run (doubling: 3, 6, 12, 24).
+        const uint32_t D = c.mN;
+        uint32_t S = D & (ds | ~P_N);
+        if ((D & 1u) && !(ds & 1u) && (P_N & 1u)) {
+            const uint32_t j0 = (3u - n_in % 3u) % 3u;
+            const uint32_t need = (2u << j0) - 1u;                       // bits 0 .. j0
+            if ((D & need) == need && !(ds & need)) S |= 1u << j0;
+        }
+        const uint32_t dsx = ds | (ds << 1) | (ds << 2);
+        const uint32_t ok3 = D & (D << 1) & (D << 2) & ~dsx;             // i, i-1, i-2 digits of one run: i-3 is the same run's
+        S |= (S << 3) & ok3;
+        const uint32_t ok6 = ok3 & (ok3 << 3);
+        S |= (S << 6) & ok6;
+        const uint32_t ok12 = ok6 & (ok6 << 6);
+        S |= (S << 12) & ok12;
+        const uint32_t ok24 = ok12 & (ok12 << 12);
+        S |= (S << 24) & ok24;
+        start |= S;
+    } else {
         uint32_t m = c.lead & c.mN;
         uint32_t stop = ~c.mN | ds;
         while (m) {

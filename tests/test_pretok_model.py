@@ -92,3 +92,31 @@ def test_invalid_utf8_is_flagged(model):
     b = "中".encode()
     rc, _ = model_starts(model, b, [0, 1, 3])
     assert rc < 0
+
+
+def test_digit_runs_at_every_offset(model):
+    # \p{N}{1,3}: every third digit of a run starts a piece, counted from the run's start -- across windows, across
+    # document starts inside the run, with one-byte and multi-byte digits (the window evaluator has a bit-arithmetic
+    # path for windows whose digits are all one byte and a per-digit loop for the rest)
+    rng = random.Random(11)
+    for lead in list(range(0, 70, 1)):
+        for run in (1, 2, 3, 4, 5, 29, 30, 31, 32, 33, 34, 35, 64, 65, 66, 97, 200):
+            body = "".join(rng.choice("0123456789") for _ in range(run))
+            for tail in ("", "a", " 12", "٣٤٥٦", "x٣" + "7" * 40):
+                s = ("a" * lead + body + tail).encode()
+                offs = [0, len(s)]
+                rc, m = model_starts(model, s, offs)
+                assert rc >= 0 and m == oracle_starts(s, offs), (s, offs)
+                cut = lead + rng.randint(0, run)
+                offs = [0, cut, len(s)]
+                rc, m = model_starts(model, s, offs)
+                assert rc >= 0 and m == oracle_starts(s, offs), (s, offs)
+    s = ("٣" * 50 + "1234567" + "٣" * 3 + "89" * 40).encode()
+    for cut in range(0, len(s), 2):
+        try:
+            s[:cut].decode()
+        except UnicodeDecodeError:
+            continue
+        offs = [0, cut, len(s)]
+        rc, m = model_starts(model, s, offs)
+        assert rc >= 0 and m == oracle_starts(s, offs), (cut,)
