@@ -21,10 +21,13 @@ enum { TK_CL_O = 0, TK_CL_L = 1, TK_CL_N = 2, TK_CL_W = 3, TK_CL_R = 4 };
 
 // Two-stage Unicode class table: stage1[cp >> 7] -> block index; stage2 holds 128 two-bit
 // entries per block (32 bytes), values TK_CL_O/L/N/W.  R (CR/LF) is ASCII and handled inline.
+// A block of one class is TK_UNI_UNIFORM | class in stage 1 and has no stage-2 entry.
 #define TK_UNI_STAGE1_N (0x110000 >> 7)
+#define TK_UNI_UNIFORM 0x8000u
 
 TK_HD uint32_t tk_class_lookup(const uint16_t* stage1, const uint8_t* stage2, uint32_t cp) {
     uint32_t blk = stage1[cp >> 7];
+    if (blk & TK_UNI_UNIFORM) return blk & 3u;
     uint32_t b = stage2[blk * 32u + ((cp & 127u) >> 2)];
     return (b >> ((cp & 3u) * 2u)) & 3u;
 }

@@ -473,6 +473,11 @@ void build_unicode_tables(std::vector<uint16_t>& stage1, std::vector<uint8_t>& s
             uint8_t c = cls[b * 128 + i];
             blk[i >> 2] = (char)((uint8_t)blk[i >> 2] | (uint8_t)(c << ((i & 3) * 2)));
         }
+        // a block whose 128 code points share one class (CJK ideographs, Hangul, unassigned planes: most of the
+        // non-ASCII text there is) is answered by stage 1 alone: TK_UNI_UNIFORM | class, no second dependent load
+        bool uniform = true;
+        for (uint32_t i = 1; i < 128; ++i) uniform &= cls[b * 128 + i] == cls[b * 128];
+        if (uniform) { stage1[b] = (uint16_t)(TK_UNI_UNIFORM | cls[b * 128]); continue; }
         auto it = seen.find(blk);
         if (it == seen.end()) {
             uint16_t idx = (uint16_t)seen.size();
@@ -483,6 +488,7 @@ void build_unicode_tables(std::vector<uint16_t>& stage1, std::vector<uint8_t>& s
             stage1[b] = it->second;
         }
     }
+    if (stage2.empty()) stage2.assign(32, 0);
 }
 
 // Class tables of the TK_SPLIT_CONFIG split: 4-bit classes of tk_pretok_cfg.h (TK_CC_*), two-stage:

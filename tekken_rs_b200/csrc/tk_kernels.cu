@@ -1243,6 +1243,7 @@ __global__ void __launch_bounds__(LK_T, LK_MINB) lookup_kernel(const uint8_t* __
     const uint32_t np = S.n_pieces;
 
     // ---- B: one lane per piece: whole-piece vocabulary lookup; entries written, misses collected ----
+    uint32_t hits = 0;                                     // ranks this thread stored, summed once after the loop
     for (uint32_t k0 = 0; k0 < np; k0 += LK_T) {
         const uint32_t k = k0 + t;
         uint32_t s = 0, len = 0, cls = 0xFFFFFFFFu;
@@ -1270,8 +1271,7 @@ __global__ void __launch_bounds__(LK_T, LK_MINB) lookup_kernel(const uint8_t* __
                 } else if (TK_DBG(tile_pos + s, stream_words)) dst[s] = EN_LONGREF;      // longer pieces: K3
             }
         }
-        const uint32_t hm = __reduce_add_sync(0xFFFFFFFFu, hit);
-        if (lane == 0 && hm) atomicAdd(&S.n_hit, hm);
+        hits += hit;
         const uint32_t mm = __ballot_sync(0xFFFFFFFFu, cls != 0xFFFFFFFFu);
         if (mm) {
             uint32_t base = 0;
@@ -1283,6 +1283,10 @@ __global__ void __launch_bounds__(LK_T, LK_MINB) lookup_kernel(const uint8_t* __
             const uint32_t peers = __match_any_sync(0xFFFFFFFFu, cls);
             if (cls != 0xFFFFFFFFu && (uint32_t)(__ffs((int)peers) - 1) == lane) atomicAdd(&S.cls_n[cls], (uint32_t)__popc(peers));
         }
+    }
+    {
+        const uint32_t hm = __reduce_add_sync(0xFFFFFFFFu, hits);
+        if (lane == 0 && hm) atomicAdd(&S.n_hit, hm);
     }
     __syncthreads();
 #if LK_COMPOSE
