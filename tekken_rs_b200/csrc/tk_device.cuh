@@ -313,43 +313,20 @@ __device__ __forceinline__ uint32_t tk_popc_m(tk_u128 m) {
 #ifndef TK_BUCKET_ABOVE
 #define TK_BUCKET_ABOVE 16      // lane-merge classes of pieces longer than this use the bucket layout of the pair table
 #endif
-// Classes of TK_LM_BLOCKMIN bytes and more keep the minimum of every block of eight keys next to the keys (bm, per lane,
-// shared memory): a merge changes three keys, so three blocks are rescanned (24 loads) and the block minima compared
-// (MAXLEN / 8 loads) instead of all MAXLEN keys -- 36 instead of 96 loads per merge in the longest class.  Every lane
-// rescans exactly three blocks (a missing left neighbour repeats the merged pair's block): no divergence.
-#ifndef TK_LM_BLOCKMIN
-#define TK_LM_BLOCKMIN 48
-#endif
-__device__ __forceinline__ uint32_t tk_key_block_min(const uint32_t* key, uint32_t b) {
-    const uint32_t* k = key + 8u * b;
-    return min(min(min(k[0], k[1]), min(k[2], k[3])), min(min(k[4], k[5]), min(k[6], k[7])));
-}
 template <class M, int MAXLEN>
-__device__ __forceinline__ M tk_bpe_merge_loop(const TkDeviceTables& T, uint32_t len, uint32_t* id, uint32_t* key, uint32_t& lookups,
-                                               uint32_t* bm = nullptr) {
+__device__ __forceinline__ M tk_bpe_merge_loop(const TkDeviceTables& T, uint32_t len, uint32_t* id, uint32_t* key, uint32_t& lookups) {
     constexpr uint32_t kBits = sizeof(M) * 8;
     static_assert(MAXLEN % 4 == 0 && MAXLEN <= (int)kBits, "scan is unrolled by four; one live bit per offset");
-    constexpr bool kBlocked = MAXLEN >= TK_LM_BLOCKMIN && MAXLEN % 8 == 0;
-    constexpr int NB = MAXLEN / 8;
     const M one = 1;
     M live = len >= kBits ? ~(M)0 : (M)((one << len) - one);
-    if (kBlocked) {
-#pragma unroll
-        for (int b = 0; b < NB; ++b) bm[b] = tk_key_block_min(key, (uint32_t)b);
-    }
     for (;;) {
+        // all MAXLEN slots are scanned (the caller set the ones past the piece to TK_INF): a fixed trip
+        // count keeps the loop free of remainder branches, and a class holds lengths near MAXLEN anyway
         uint32_t best = TK_INF;
-        if (kBlocked) {
 #pragma unroll
-            for (int b = 0; b < NB; ++b) best = min(best, bm[b]);
-        } else {
-            // all MAXLEN slots are scanned (the caller set the ones past the piece to TK_INF): a fixed trip
-            // count keeps the loop free of remainder branches, and a class holds lengths near MAXLEN anyway
-#pragma unroll
-            for (int j = 0; j < MAXLEN; j += 4) {
-                const uint32_t a0 = key[j], a1 = key[j + 1], a2 = key[j + 2], a3 = key[j + 3];
-                best = min(min(best, a0), min(a1, min(a2, a3)));
-            }
+        for (int j = 0; j < MAXLEN; j += 4) {
+            const uint32_t a0 = key[j], a1 = key[j + 1], a2 = key[j + 2], a3 = key[j + 3];
+            best = min(min(best, a0), min(a1, min(a2, a3)));
         }
         if (best == TK_INF) break;
         const uint32_t bp = best & ((1u << TK_KEY_SHIFT) - 1u), rank = best >> TK_KEY_SHIFT;
@@ -369,12 +346,6 @@ __device__ __forceinline__ M tk_bpe_merge_loop(const TkDeviceTables& T, uint32_t
         lookups += (lft != TK_INF ? 1u : 0u) + (rgt != TK_INF ? 1u : 0u);
         if (pv != 0xFFFFFFFFu) key[pv] = r0 == TK_INF ? TK_INF : ((r0 << TK_KEY_SHIFT) | pv);
         key[bp] = r1 == TK_INF ? TK_INF : ((r1 << TK_KEY_SHIFT) | bp);
-        if (kBlocked) {
-            const uint32_t b0 = bp >> 3, b1 = q >> 3, b2 = pv != 0xFFFFFFFFu ? pv >> 3 : b0;
-            bm[b0] = tk_key_block_min(key, b0);
-            bm[b1] = tk_key_block_min(key, b1);
-            bm[b2] = tk_key_block_min(key, b2);
-        }
     }
     return live;
 }

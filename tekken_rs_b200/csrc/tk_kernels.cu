@@ -1356,8 +1356,6 @@ __global__ void __launch_bounds__(THREADS, MINB) lanemerge_kernel(const uint8_t*
     extern __shared__ __align__(16) uint32_t lm_raw[];
     uint32_t* id = lm_raw + threadIdx.x * STRIDE;
     uint32_t* key = lm_raw + THREADS * STRIDE + threadIdx.x * STRIDE;
-    constexpr int BM_STRIDE = (MAXLEN / 8) | 1;      // per-lane block minima of the long classes (tk_bpe_merge_loop); odd: no bank conflicts
-    uint32_t* bm = lm_raw + 2 * THREADS * STRIDE + threadIdx.x * BM_STRIDE;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t total = *q_n;
     // short pieces cost about the same: warps stride over the queue.  Long ones vary more: warps take
@@ -1442,7 +1440,7 @@ __global__ void __launch_bounds__(THREADS, MINB) lanemerge_kernel(const uint8_t*
             using Mask = typename std::conditional<(MAXLEN <= 32), uint32_t,
                                                    typename std::conditional<(MAXLEN <= 64), unsigned long long, tk_u128>::type>::type;
             n_bp += len - 1u;
-            Mask live = tk_bpe_merge_loop<Mask, MAXLEN>(T, len, id, key, n_pair, bm);
+            Mask live = tk_bpe_merge_loop<Mask, MAXLEN>(T, len, id, key, n_pair);
             {
                 // the ranks go to consecutive byte positions from `start`: count them for the tile each one lands in
                 const uint32_t cnt = tk_popc_m(live);
@@ -1859,7 +1857,7 @@ template <int MAXLEN, int THREADS, int MINB>
 static cudaError_t launch_lanemerge(int blocks_per_sm, int sm_count, const uint8_t* d_data, uint64_t n, const TkDeviceTables& T,
                                     const unsigned long long* queue, const uint32_t* q_n, uint32_t* q_w, uint32_t* stream,
                                     unsigned long long* tile_count, unsigned long long* stats, const HotTables* hot, cudaStream_t st) {
-    const size_t smem = ((size_t)2 * THREADS * (MAXLEN + 1) + (MAXLEN >= TK_LM_BLOCKMIN ? (size_t)THREADS * ((MAXLEN / 8) | 1) : 0)) * sizeof(uint32_t);
+    const size_t smem = (size_t)2 * THREADS * (MAXLEN + 1) * sizeof(uint32_t);
     static std::atomic<uint64_t> attr_set{0};   // bit per device ordinal
     int dev = 0;
     CK(cudaGetDevice(&dev));
