@@ -357,3 +357,14 @@ pub fn shard_plan(doc_off: &[u64], n_shards: usize) -> Result<Vec<u64>> {
 pub fn status_name(status: i32) -> String {
     unsafe { CStr::from_ptr(ffi::tk_status_name(status)) }.to_string_lossy().into_owned()
 }
+
+/// Tuning knob of the host-buffer calls: chunk size in bytes (0 = the default of 128 MB).
+pub fn set_chunk_bytes(bytes: u64) {
+    unsafe { ffi::tk_set_chunk_bytes(bytes) }
+}
+
+/// How ids cross PCIe in host-buffer encodes: -1 = as an 18/24-bit stream for large pipelined calls (default),
+/// 0 = always as `u32`, 18 / 24 = that width whenever the ids fit.  The result is the same either way.
+pub fn set_pack_ids(mode: i32) {
+    unsafe { ffi::tk_set_pack_ids(mode) }
+}
