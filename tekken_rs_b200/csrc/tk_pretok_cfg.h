@@ -78,8 +78,17 @@ struct TkCfgEndMask {
     const uint32_t* ds_mask;     // bit = a document starts at this byte
     int64_t n;                   // end of the text
     int64_t own_start;           // the start of the walk's own document segment is not an end
+    // the matcher asks about consecutive positions: the last mask word read is kept (one load per 32 bytes walked
+    // instead of one per question)
+    mutable int64_t word_idx = -1;
+    mutable uint32_t word = 0;
+    TK_HD TkCfgEndMask(const uint32_t* m, int64_t n_, int64_t own) : ds_mask(m), n(n_), own_start(own) {}
     TK_HD bool at_end(int64_t pos) const {
-        return pos >= n || (pos > own_start && ((ds_mask[pos >> 5] >> (pos & 31)) & 1u));
+        if (pos >= n) return true;
+        if (pos <= own_start) return false;
+        const int64_t w = pos >> 5;
+        if (w != word_idx) { word_idx = w; word = ds_mask[w]; }
+        return (word >> (pos & 31)) & 1u;
     }
 };
 
@@ -133,11 +142,17 @@ TK_HD int64_t tk_cfg_match_end(const B& src, int64_t q, const E& end, const TkCf
     const bool has1 = !end.at_end(q + l0);
     if (has1) tk_cfg_char(src, q + l0, T, &k1, &c1);
     int64_t e;
-    // B1: P?U*L+ (greedy optional prefix first, then without it), B2: P?U+L*
-    if (tk_cfg_is_prefix(k0) && has1 && (e = tk_cfg_match_UL(src, q + l0, end, T)) >= 0) return e;
-    if ((e = tk_cfg_match_UL(src, q, end, T)) >= 0) return e;
-    if (tk_cfg_is_prefix(k0) && has1 && (e = tk_cfg_match_UpL(src, q + l0, end, T)) >= 0) return e;
-    if ((e = tk_cfg_match_UpL(src, q, end, T)) >= 0) return e;
+    // B1: P?U*L+ (greedy optional prefix first, then without it), B2: P?U+L*.  Which of the four attempts can match at
+    // all follows from the first two classes: a word alternative needs a word character (U, Ll, C or M) at q, or a
+    // prefix character at q and a word character after it -- so a digit, and punctuation or whitespace that no word
+    // character follows, skip all four, and only a mark (prefix AND word character) has to try them all.
+    const bool w0 = tk_cfg_in_U(k0) || tk_cfg_in_L(k0);
+    const bool w1 = has1 && (tk_cfg_in_U(k1) || tk_cfg_in_L(k1));
+    const bool pre = tk_cfg_is_prefix(k0) && w1;
+    if (pre && (e = tk_cfg_match_UL(src, q + l0, end, T)) >= 0) return e;
+    if (w0 && (e = tk_cfg_match_UL(src, q, end, T)) >= 0) return e;
+    if (pre && (e = tk_cfg_match_UpL(src, q + l0, end, T)) >= 0) return e;
+    if (w0 && (e = tk_cfg_match_UpL(src, q, end, T)) >= 0) return e;
     // B3: \p{N}
     if (k0 == TK_CC_N) return q + l0;
     // B4:  ?[^\s\p{L}\p{N}]+[\r\n/]*

@@ -68,7 +68,7 @@ def oracle_starts(orc, b, offs):
     return out
 
 
-@pytest.mark.parametrize("seed", [1, 2])
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
 def test_piece_starts_match_oracle(model, oracle, seed):
     rng = random.Random(seed)
     alpha = ALPHABET + FUZZ_ALPHABET
