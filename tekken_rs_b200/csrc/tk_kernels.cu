@@ -576,7 +576,6 @@ __global__ void __launch_bounds__(PT_T) cfg_mask_kernel(const uint8_t* __restric
 // than reading the text through L1 -- the walk is a chain of dependent ALU work per character, not memory-bound -- so
 // the text and the masks are read from global memory.)
 #define CW_T 256
-#define CW_KEYS 10u     // eight ASCII classes, non-ASCII, the end sentinel
 __global__ void __launch_bounds__(CW_T) cfg_walk_kernel(const uint8_t* __restrict__ data, uint64_t n, const uint32_t* __restrict__ ds_mask,
                                                         const uint32_t* __restrict__ safe_mask, uint32_t* __restrict__ start_mask,
                                                         uint64_t n_windows, TkCfgTables T, const unsigned long long* __restrict__ err_pos) {
@@ -609,31 +608,8 @@ __global__ void __launch_bounds__(CW_T) cfg_walk_kernel(const uint8_t* __restric
     const uint32_t cnt = n_list;
     const TkBytesChecked src{data, n};
     const uint64_t tile_pos = (uint64_t)blockIdx.x * CW_T * 32u;
-    // The lanes of a warp walk different segments, each through its own alternatives of the pattern: ncu measured 6 of
-    // 32 lanes per instruction.  Segments that begin with the same class take the same alternative (a space: " word";
-    // a letter; a digit; punctuation; ...), so the tile's safe starts are bucketed by the class of their first byte
-    // before the lanes take them in order.
-    __shared__ uint16_t list2[CW_T * 32];
-    __shared__ uint32_t bcnt[CW_KEYS], bpos[CW_KEYS];
-    if (t < CW_KEYS) bcnt[t] = 0;
-    __syncthreads();
-    auto key_of = [&](uint32_t k) -> uint32_t {
-        const uint64_t q = tile_pos + list[k];
-        if (q >= n) return CW_KEYS - 1u;
-        const uint32_t b0 = data[q];
-        return b0 < 0x80u ? tk_cfg_class_ascii(b0) : 8u;
-    };
-    for (uint32_t k = t; k < cnt; k += CW_T) atomicAdd(&bcnt[key_of(k)], 1u);
-    __syncthreads();
-    if (t == 0) {
-        uint32_t run = 0;
-        for (uint32_t b = 0; b < CW_KEYS; ++b) { bpos[b] = run; run += bcnt[b]; }
-    }
-    __syncthreads();
-    for (uint32_t k = t; k < cnt; k += CW_T) list2[atomicAdd(&bpos[key_of(k)], 1u)] = list[k];
-    __syncthreads();
     for (uint32_t k = t; k < cnt; k += CW_T) {
-        const int64_t q0 = (int64_t)(tile_pos + list2[k]);
+        const int64_t q0 = (int64_t)(tile_pos + list[k]);
         if ((uint64_t)q0 >= n) continue;              // the end sentinel is not a piece
         tk_cfg_walk(src, q0, safe_mask, ds_mask, (int64_t)n, T,
                     [&](int64_t p) { atomicOr(start_mask + (p >> 5), 1u << (p & 31)); });
