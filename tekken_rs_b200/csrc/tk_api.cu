@@ -698,7 +698,7 @@ extern "C" int tk_encode_batch_device(const tk_tokenizer* tc, const uint8_t* d_d
 //             (the previous piece cannot contain the space, and " x..." matches the word alternative), and no lookahead
 //             of an earlier piece reaches past the letter / digit.  The slices are encoded as separate texts; BOS / EOS
 //             go to the first / last slice.  So a 1 GiB document pipelines like a batch and needs a chunk's workspace.
-//   deal      chunk c goes to device c mod N.  Every device runs the three-stream pipeline (upload, kernels,
+//   deal      chunk c goes to device c mod N.  Every device runs the stream pipeline (upload, kernels,
 //             download; kSlots buffer slots) over its chunks on its own host thread.
 //   stitch    the id count of a chunk is known when its kernels finish; its place in the output when every earlier
 //             chunk has reported its count.  Ids are then copied straight to that place in ONE pinned result buffer

@@ -10,6 +10,7 @@
 //                 unknown-id / Raise errors, word copy to the output
 //   D2 validate   one thread per 32 output bytes: strict UTF-8 with run boundaries, as flag arithmetic on words
 //   D3 status     per sequence: the error the reference would have returned first
+//   S'            one id list of at most 2,048 ids in a single block over mapped pinned memory (tk_decode's latency path)
 #include "tk_kernels.h"
 
 #include "../../include/tekken_b200.h"
