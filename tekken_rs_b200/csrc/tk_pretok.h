@@ -106,10 +106,10 @@ TK_HD int tk_decode_at(const B& src, int64_t pos, const TkDeviceTables& T, uint3
     return len;
 }
 
-// Classify the 32-byte window at byte offset `pos` (a multiple of 32).  w[0..7] are its bytes as
-// little-endian words, zero padded beyond n.  ds_word = document-start bits of the window.
-template <class B>
-TK_HD TkWin tk_classify_window(const B& src, uint64_t pos, const uint32_t* w, uint32_t ds_word, const TkDeviceTables& T) {
+// The ASCII half of the classification of a 32-byte window: class masks of its ASCII bytes, lead / continuation
+// bytes, *hi = bytes >= 0x80 (their classes are still missing: tk_classify_window adds them char by char, the
+// pre-tokeniser kernel spreads that work over the block).  bad = 0.
+TK_HD TkWin tk_classify_ascii(const uint32_t* w, uint32_t ds_word, uint32_t* hi_out) {
     TkWin r;
     uint32_t mL = 0, mN = 0, mR = 0, mW = 0, sp = 0, ap = 0, hi = 0;
 #pragma unroll
@@ -134,34 +134,53 @@ TK_HD TkWin tk_classify_window(const B& src, uint64_t pos, const uint32_t* w, ui
         ap |= tk_swar_nib(e27) << s;
         hi |= tk_swar_nib(h) << s;
     }
-    uint32_t lead = 0xFFFFFFFFu, bad = 0;
+    uint32_t lead = 0xFFFFFFFFu;
     if (hi) {
         // continuation bytes: 10xxxxxx.  (hi bytes with bit 6 clear)
         uint32_t cont = 0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) cont |= tk_swar_nib((w[j] & TK_H) & ~((w[j] << 1) & TK_H)) << (4 * j);
         lead = ~cont;
+    }
+    r.lead = lead; r.mL = mL; r.mN = mN; r.mR = mR; r.mW = mW; r.sp = sp; r.ap = ap; r.ds = ds_word; r.bad = 0;
+    *hi_out = hi;
+    return r;
+}
+
+// Leading continuation bytes of the window at pos belong to a char that starts in the window before: its class for the
+// bytes that fall into this window (*cov = the bytes it covers; continuation bytes beyond them stay uncovered).
+template <class B>
+TK_HD void tk_cover_leading(const B& src, uint64_t pos, uint32_t cont, const TkDeviceTables& T, uint32_t* cov, uint32_t* mL,
+                            uint32_t* mN, uint32_t* mW) {
+    uint32_t lc = (uint32_t)(TK_FFS(~cont) - 1);  // number of leading continuation bytes (cont != ~0 -> <32)
+    if (cont == 0xFFFFFFFFu) lc = 32;
+    if (lc == 0) return;
+    int back = 0;
+    int64_t q = (int64_t)pos - 1;
+    while (back < 3 && q >= 0 && (src.at(q) & 0xC0u) == 0x80u) { --q; ++back; }
+    uint32_t cls = TK_CL_O;
+    const int len = (q >= 0) ? tk_decode_at(src, q, T, &cls) : 0;
+    const int64_t over = len ? q + len - (int64_t)pos : 0;
+    if (over > 0) {
+        const uint32_t m = (1u << (over < (int64_t)lc ? (uint32_t)over : lc)) - 1u;
+        *cov |= m;
+        if (cls == TK_CL_L) *mL |= m; else if (cls == TK_CL_N) *mN |= m; else if (cls == TK_CL_W) *mW |= m;
+    }
+}
+
+// Classify the 32-byte window at byte offset `pos` (a multiple of 32).  w[0..7] are its bytes as
+// little-endian words, zero padded beyond n.  ds_word = document-start bits of the window.
+template <class B>
+TK_HD TkWin tk_classify_window(const B& src, uint64_t pos, const uint32_t* w, uint32_t ds_word, const TkDeviceTables& T) {
+    uint32_t hi;
+    TkWin r = tk_classify_ascii(w, ds_word, &hi);
+    uint32_t bad = 0;
+    if (hi) {
+        const uint32_t cont = ~r.lead;
         uint32_t covered = ~hi;  // ASCII bytes are done
-        // leading continuation bytes belong to a char that starts in the previous window
-        uint32_t lc = (uint32_t)(TK_FFS(~cont) - 1);  // number of leading continuation bytes (cont != ~0 -> <32)
-        if (cont == 0xFFFFFFFFu) lc = 32;
-        if (lc > 0) {
-            int back = 0;
-            int64_t q = (int64_t)pos - 1;
-            while (back < 3 && q >= 0 && (src.at(q) & 0xC0u) == 0x80u) { --q; ++back; }
-            uint32_t cls = TK_CL_O;
-            const int len = (q >= 0) ? tk_decode_at(src, q, T, &cls) : 0;
-            // bytes of that char that fall into this window; leading continuation bytes beyond
-            // them stay uncovered and are flagged below
-            const int64_t over = len ? q + len - (int64_t)pos : 0;
-            if (over > 0) {
-                const uint32_t m = (1u << (over < (int64_t)lc ? (uint32_t)over : lc)) - 1u;
-                covered |= m;
-                if (cls == TK_CL_L) mL |= m; else if (cls == TK_CL_N) mN |= m; else if (cls == TK_CL_W) mW |= m;
-            }
-        }
+        tk_cover_leading(src, pos, cont, T, &covered, &r.mL, &r.mN, &r.mW);
         // chars whose lead byte is in this window
-        uint32_t todo = hi & lead;
+        uint32_t todo = hi & r.lead;
         while (todo) {
             int i = TK_FFS(todo) - 1;
             todo &= todo - 1;
@@ -170,12 +189,12 @@ TK_HD TkWin tk_classify_window(const B& src, uint64_t pos, const uint32_t* w, ui
             if (len == 0) { bad |= 1u << i; continue; }
             uint32_t m = (len >= 32 - i) ? (0xFFFFFFFFu << i) : (((1u << len) - 1u) << i);
             covered |= m;
-            if (cls == TK_CL_L) mL |= m; else if (cls == TK_CL_N) mN |= m; else if (cls == TK_CL_W) mW |= m;
+            if (cls == TK_CL_L) r.mL |= m; else if (cls == TK_CL_N) r.mN |= m; else if (cls == TK_CL_W) r.mW |= m;
         }
         bad |= ~covered;               // stray continuation bytes
     }
-    bad |= ds_word & ~lead;            // a document may not start inside a char
-    r.lead = lead; r.mL = mL; r.mN = mN; r.mR = mR; r.mW = mW; r.sp = sp; r.ap = ap; r.ds = ds_word; r.bad = bad;
+    bad |= ds_word & ~r.lead;          // a document may not start inside a char
+    r.bad = bad;
     return r;
 }
 
