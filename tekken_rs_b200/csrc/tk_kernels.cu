@@ -307,12 +307,10 @@ __device__ __forceinline__ void pretok_tile(PtSmem& S, uint32_t b, const uint8_t
         const int lane0 = t & 31, warp0 = t >> 5;
         uint32_t inc0 = (uint32_t)__popc(todo);
         const uint32_t mine0 = inc0;
-        if (__any_sync(0xFFFFFFFFu, todo != 0u)) {           // (a warp of ASCII windows skips the scan)
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc0, d);
-                if (lane0 >= d) inc0 += o;
-            }
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc0, d);
+            if (lane0 >= d) inc0 += o;
         }
         if (lane0 == 31) S.csum[warp0] = inc0;
         pt_store(S, t + 1, c);
@@ -325,16 +323,11 @@ __device__ __forceinline__ void pretok_tile(PtSmem& S, uint32_t b, const uint8_t
             S.cov[t == 0 ? 0 : PT_T + 1] = 0xFFFFFFFFu; S.bad[t == 0 ? 0 : PT_T + 1] = 0u;
         }
         if (t == 0) S.pend = -1;
-        // a tile of ASCII text (or with chars only where the tile before reaches in) is done here, as before
-        const bool any_chars = __syncthreads_or(todo != 0u) != 0;
+        __syncthreads();
         uint32_t before0 = inc0 - mine0, all0 = 0;
-        if (any_chars) {
 #pragma unroll
-            for (int x = 0; x < PT_T / 32; ++x) { if (x < warp0) before0 += S.csum[x]; all0 += S.csum[x]; }
-        }
-        if (!any_chars) {
-            c.bad = ~cov;                                    // continuation bytes without a lead (invalid text)
-        } else if (all0 <= PT_CLIST) {                       // block-uniform
+        for (int x = 0; x < PT_T / 32; ++x) { if (x < warp0) before0 += S.csum[x]; all0 += S.csum[x]; }
+        if (all0 <= PT_CLIST) {                              // block-uniform
             // (b) the list of lead bytes, in text order
             while (todo) {
                 S.clist[before0++] = (uint16_t)(t * 32 + (TK_FFS(todo) - 1));
