@@ -197,14 +197,6 @@ __device__ __forceinline__ TkRunSummary rs_unpack(uint32_t p) {
 #define RS_IDENTITY (1u | (2u << 3))
 
 #define PT_HALO 64
-// PT_COOP=1: the non-ASCII characters of a tile are classified by the whole block, one character per thread and round,
-// instead of by the thread that owns their window (ncu: that per-window loop was 30 % of the kernel's instructions at
-// 12 of 32 lanes -- a window of CJK text has ten characters, a window of ASCII none).  Tiles with more than PT_CLIST
-// such characters (only invalid UTF-8 can do that) take the per-window path.
-#ifndef PT_COOP
-#define PT_COOP 1
-#endif
-#define PT_CLIST 4096
 struct PtSmem {
     uint8_t bytes[PT_HALO + PT_T * 32 + PT_HALO];   // the tile's text with a halo; zero outside the text
     uint32_t lead[PT_T + 2], mL[PT_T + 2], mN[PT_T + 2], mR[PT_T + 2], mW[PT_T + 2], sp[PT_T + 2], ap[PT_T + 2],
@@ -213,11 +205,6 @@ struct PtSmem {
     uint32_t wtot[PT_T / 32];
     long long pend;
     unsigned long long mbar;           // mbarrier of the tile's bulk copy
-#if PT_COOP
-    uint32_t cov[PT_T + 2], bad[PT_T + 2];   // bytes whose char is classified / invalid bytes (cooperative classification)
-    uint32_t csum[PT_T / 32], n_chars;
-    uint16_t clist[PT_CLIST];          // tile-relative positions of the lead bytes of the tile's non-ASCII chars
-#endif
 };
 
 __device__ __forceinline__ void pt_store(PtSmem& S, int i, const TkWin& w) {
@@ -287,85 +274,6 @@ __device__ __forceinline__ void pretok_tile(PtSmem& S, uint32_t b, const uint8_t
     __syncthreads();
     if (bulk) bulk_tile_wait(&S.mbar);
     const TkBytesTile src{S.bytes + PT_HALO, (int64_t)b * (PT_T * 32)};
-#if PT_COOP
-    TkWin c;
-    {
-        // (a) ASCII masks of my window; its non-ASCII lead bytes counted
-        const bool inside = wi >= 0 && (uint64_t)wi < n_windows;
-        uint32_t hi = 0;
-        c.lead = 0xFFFFFFFFu; c.mL = c.mN = c.mR = c.mW = c.sp = c.ap = c.ds = c.bad = 0;
-        if (inside) {
-            const uint4* q = reinterpret_cast<const uint4*>(S.bytes + PT_HALO + t * 32);
-            const uint4 a = q[0], bq = q[1];
-            const uint32_t w[8] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w};
-            c = tk_classify_ascii(w, ds_mask[wi], &hi);
-        }
-        uint32_t todo = hi & c.lead;
-        uint32_t cov = ~hi, bad0 = 0;
-        // the first window of the tile: a char that starts in the tile before may reach into it
-        if (t == 0 && hi) tk_cover_leading(src, pos, ~c.lead, T, &cov, &c.mL, &c.mN, &c.mW);
-        const int lane0 = t & 31, warp0 = t >> 5;
-        uint32_t inc0 = (uint32_t)__popc(todo);
-        const uint32_t mine0 = inc0;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc0, d);
-            if (lane0 >= d) inc0 += o;
-        }
-        if (lane0 == 31) S.csum[warp0] = inc0;
-        pt_store(S, t + 1, c);
-        S.cov[t + 1] = cov; S.bad[t + 1] = bad0;
-        if (t < 2) {
-            // the windows before and after the tile, whole (their chars are not in the list)
-            const long long hw = t == 0 ? (long long)b * PT_T - 1 : (long long)b * PT_T + PT_T;
-            TkWin h = pt_classify(S, src, ds_mask, n_windows, hw, t == 0 ? -1 : PT_T, T);
-            pt_store(S, t == 0 ? 0 : PT_T + 1, h);
-            S.cov[t == 0 ? 0 : PT_T + 1] = 0xFFFFFFFFu; S.bad[t == 0 ? 0 : PT_T + 1] = 0u;
-        }
-        if (t == 0) S.pend = -1;
-        __syncthreads();
-        uint32_t before0 = inc0 - mine0, all0 = 0;
-#pragma unroll
-        for (int x = 0; x < PT_T / 32; ++x) { if (x < warp0) before0 += S.csum[x]; all0 += S.csum[x]; }
-        if (all0 <= PT_CLIST) {                              // block-uniform
-            // (b) the list of lead bytes, in text order
-            while (todo) {
-                S.clist[before0++] = (uint16_t)(t * 32 + (TK_FFS(todo) - 1));
-                todo &= todo - 1;
-            }
-            __syncthreads();
-            // (c) one char per thread and round: decode, class, and the bytes it covers in its window and the next
-            for (uint32_t k = t; k < all0; k += PT_T) {
-                const uint32_t p = S.clist[k], wl = p >> 5, i = p & 31u;
-                uint32_t cls = TK_CL_O;
-                const int len = tk_decode_at(src, (int64_t)b * (PT_T * 32) + p, T, &cls);
-                if (len == 0) { atomicOr(&S.bad[wl + 1], 1u << i); continue; }
-                uint32_t* arr = cls == TK_CL_L ? S.mL : cls == TK_CL_N ? S.mN : cls == TK_CL_W ? S.mW : nullptr;
-                const uint32_t m = ((uint32_t)len >= 32u - i) ? (0xFFFFFFFFu << i) : (((1u << len) - 1u) << i);
-                atomicOr(&S.cov[wl + 1], m);
-                if (arr) atomicOr(&arr[wl + 1], m);
-                const int over = (int)i + len - 32;
-                if (over > 0) {
-                    const uint32_t m2 = (1u << over) - 1u;
-                    atomicOr(&S.cov[wl + 2], m2);
-                    if (arr) atomicOr(&arr[wl + 2], m2);
-                }
-            }
-            __syncthreads();
-            // (d) my window again, complete
-            c.mL = S.mL[t + 1]; c.mN = S.mN[t + 1]; c.mW = S.mW[t + 1];
-            c.bad = S.bad[t + 1] | ~S.cov[t + 1];            // stray continuation bytes
-        } else {
-            c = pt_classify(S, src, ds_mask, n_windows, wi, t, T);
-            __syncthreads();                                 // (everybody has read csum / the ASCII masks)
-            pt_store(S, t + 1, c);
-            __syncthreads();
-            c.bad &= ~(c.ds & ~c.lead);                      // (added again below)
-        }
-        c.bad |= c.ds & ~c.lead;                             // a document may not start inside a char
-        if (!inside) c.bad = 0;
-    }
-#else
     TkWin c = pt_classify(S, src, ds_mask, n_windows, wi, t, T);
     pt_store(S, t + 1, c);
     if (t < 2) {
@@ -375,7 +283,6 @@ __device__ __forceinline__ void pretok_tile(PtSmem& S, uint32_t b, const uint8_t
     }
     if (t == 0) S.pend = -1;
     __syncthreads();
-#endif
     const TkWin p = pt_load(S, t), nx = pt_load(S, t + 2);
     TkWin zero;
     zero.lead = 0xFFFFFFFFu; zero.mL = zero.mN = zero.mR = zero.mW = zero.sp = zero.ap = zero.ds = zero.bad = 0;
