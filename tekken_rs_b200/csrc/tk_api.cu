@@ -1355,11 +1355,12 @@ static int encode_batch_engine(tk_tokenizer* const* handles, size_t n_handles, c
             if (mode == 24 && bits) bits = 24;
             if (mode == 0 || (mode < 0 && total < (32u << 20))) bits = 0;
             if (mode < 0 && bits) {
-                // the widening needs CPUs: with one process per GPU (torchrun sets LOCAL_WORLD_SIZE) and fewer than eight
-                // CPUs for each, or with several devices driven by this call, leave the ids as they are
+                // the widening needs CPUs: with one process per GPU (torchrun sets LOCAL_WORLD_SIZE) and fewer than twelve
+                // CPUs for each (the copy pool's size), or with several devices driven by this call, leave the ids as
+                // they are
                 const char* lws = getenv("LOCAL_WORLD_SIZE");
                 const unsigned procs = lws && atoi(lws) > 0 ? (unsigned)atoi(lws) : 1u;
-                if (std::thread::hardware_concurrency() / (procs * (unsigned)n_handles) < 8u) bits = 0;
+                if (std::thread::hardware_concurrency() / (procs * (unsigned)n_handles) < 12u) bits = 0;
             }
             J.pack_bits = bits;
         }
